@@ -1,0 +1,307 @@
+// convmod.cu -- interior of the conformer convolution module (TA:52-65): depthwise conv k=31
+// with SAME zero padding per utterance, BatchNorm1d (eval: folded; train: batch statistics
+// over all B*T frames incl. padding), SiLU, GLU backward, and the matching backward kernels.
+//
+// Depthwise kernel shape: one thread per channel (a warp reads 32 contiguous channels of one
+// frame = one coalesced line), a block walks a tile of TT output frames; every input frame is
+// loaded ONCE into a register and scattered into the <=31 accumulators it feeds (loops are
+// fully unrolled, so tap indices are compile-time).  Algorithmic bytes: read g + write out.
+#include "common.cuh"
+
+namespace eec {
+
+constexpr int KW = 31;
+constexpr int HALF = 15;
+constexpr int TT = 64;
+constexpr float BN_EPS = 1e-5f;
+
+enum { DW_EVAL = 0, DW_STATS = 1, DW_BWD_DATA = 2 };
+
+template <typename TI, typename TO, int MODE>
+__global__ void __launch_bounds__(256) dwconv_kernel(const TI* __restrict__ g, const float* __restrict__ w,
+                                                     const float* __restrict__ bias, const float* __restrict__ bn_scale_src_w,
+                                                     const float* __restrict__ bn_b, const float* __restrict__ run_mean,
+                                                     const float* __restrict__ run_var, TO* __restrict__ out,
+                                                     double* __restrict__ sums, int T, int C) {
+  const int ch = blockIdx.z * 256 + threadIdx.x;
+  const int b = blockIdx.y, t0 = blockIdx.x * TT;
+  float wr[KW];
+#pragma unroll
+  for (int j = 0; j < KW; ++j) wr[j] = (MODE == DW_BWD_DATA) ? w[ch * KW + (KW - 1 - j)] : w[ch * KW + j];
+  const float bv = (MODE == DW_BWD_DATA) ? 0.f : bias[ch];
+  float acc[TT];
+#pragma unroll
+  for (int t = 0; t < TT; ++t) acc[t] = bv;
+  const TI* gb = g + (long)b * T * C + ch;
+#pragma unroll
+  for (int r = 0; r < TT + KW - 1; ++r) {
+    const int tin = t0 + r - HALF;
+    float x = 0.f;
+    if (tin >= 0 && tin < T) x = ld_as_float<TI>(gb + (long)tin * C);
+#pragma unroll
+    for (int t = 0; t < TT; ++t) {
+      const int j = r - t;
+      if (j >= 0 && j < KW) acc[t] = fmaf(wr[j], x, acc[t]);
+    }
+  }
+  TO* ob = out + (long)b * T * C + ch;
+  if (MODE == DW_EVAL) {
+    const float sc = bn_scale_src_w[ch] * rsqrtf(run_var[ch] + BN_EPS);
+    const float sh = bn_b[ch] - run_mean[ch] * sc;
+#pragma unroll
+    for (int t = 0; t < TT; ++t)
+      if (t0 + t < T) {
+        float n = fmaf(acc[t], sc, sh);
+        st_from_float<TO>(ob + (long)(t0 + t) * C, n * sigmoid_acc(n));
+      }
+  } else if (MODE == DW_STATS) {
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int t = 0; t < TT; ++t)
+      if (t0 + t < T) {
+        st_from_float<TO>(ob + (long)(t0 + t) * C, acc[t]);
+        s1 += acc[t];
+        s2 = fmaf(acc[t], acc[t], s2);
+      }
+    atomicAdd(sums + ch, (double)s1);
+    atomicAdd(sums + C + ch, (double)s2);
+  } else {
+#pragma unroll
+    for (int t = 0; t < TT; ++t)
+      if (t0 + t < T) st_from_float<TO>(ob + (long)(t0 + t) * C, acc[t]);
+  }
+}
+
+// dW[ch][j] += sum_{b,t} dc[b,t,ch] * g[b,t+j-15,ch];  dbias[ch] += sum dc
+template <typename TI>
+__global__ void __launch_bounds__(256) dwconv_wgrad_kernel(const float* __restrict__ dc, const TI* __restrict__ g,
+                                                           float* __restrict__ dw, float* __restrict__ dbias, int T, int C) {
+  const int ch = blockIdx.z * 256 + threadIdx.x;
+  const int b = blockIdx.y, t0 = blockIdx.x * TT;
+  float d[TT], acc[KW];
+  float sb = 0.f;
+  const float* db = dc + (long)b * T * C + ch;
+#pragma unroll
+  for (int t = 0; t < TT; ++t) {
+    d[t] = (t0 + t < T) ? db[(long)(t0 + t) * C] : 0.f;
+    sb += d[t];
+  }
+#pragma unroll
+  for (int j = 0; j < KW; ++j) acc[j] = 0.f;
+  const TI* gb = g + (long)b * T * C + ch;
+#pragma unroll
+  for (int r = 0; r < TT + KW - 1; ++r) {
+    const int tin = t0 + r - HALF;
+    float x = 0.f;
+    if (tin >= 0 && tin < T) x = ld_as_float<TI>(gb + (long)tin * C);
+#pragma unroll
+    for (int t = 0; t < TT; ++t) {
+      const int j = r - t;
+      if (j >= 0 && j < KW) acc[j] = fmaf(d[t], x, acc[j]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < KW; ++j) atomicAdd(dw + ch * KW + j, acc[j]);
+  atomicAdd(dbias + ch, sb);
+}
+
+// train-mode BN + SiLU (pass B).  thread = channel, block walks a chunk of rows.
+template <typename TO>
+__global__ void __launch_bounds__(256) bn_silu_train_kernel(const float* __restrict__ c, const double* __restrict__ sums,
+                                                            const float* __restrict__ bn_w, const float* __restrict__ bn_b,
+                                                            float* __restrict__ run_mean, float* __restrict__ run_var,
+                                                            int64_t* __restrict__ nbt, float momentum,
+                                                            float* __restrict__ save_mean, float* __restrict__ save_rstd,
+                                                            TO* __restrict__ out, int rows, int C, int rows_per_block) {
+  const int ch = blockIdx.y * 256 + threadIdx.x;
+  const double n = (double)rows;
+  const double mean_d = sums[ch] / n;
+  double var_d = sums[C + ch] / n - mean_d * mean_d;
+  if (var_d < 0.0) var_d = 0.0;
+  const float mean = (float)mean_d;
+  const float rstd = (float)(1.0 / sqrt(var_d + (double)BN_EPS));
+  const float gam = bn_w[ch], bet = bn_b[ch];
+  if (blockIdx.x == 0) {
+    save_mean[ch] = mean;
+    save_rstd[ch] = rstd;
+    if (run_mean) {
+      run_mean[ch] = (1.f - momentum) * run_mean[ch] + momentum * mean;
+      const double unb = (rows > 1) ? var_d * n / (n - 1.0) : var_d;
+      run_var[ch] = (1.f - momentum) * run_var[ch] + momentum * (float)unb;
+      if (ch == 0 && nbt) *nbt += 1;
+    }
+  }
+  const int r0 = blockIdx.x * rows_per_block, r1 = min(rows, r0 + rows_per_block);
+  for (int r = r0; r < r1; ++r) {
+    float y = fmaf((c[(long)r * C + ch] - mean) * rstd, gam, bet);
+    st_from_float<TO>(out + (long)r * C + ch, y * sigmoid_acc(y));
+  }
+}
+
+template <typename TI>
+__global__ void __launch_bounds__(256) bn_silu_bwd_stats_kernel(const TI* __restrict__ ds, const float* __restrict__ c,
+                                                                const float* __restrict__ save_mean,
+                                                                const float* __restrict__ save_rstd,
+                                                                const float* __restrict__ bn_w, const float* __restrict__ bn_b,
+                                                                double* __restrict__ sums2, int rows, int C, int rows_per_block) {
+  const int ch = blockIdx.y * 256 + threadIdx.x;
+  const float mean = save_mean[ch], rstd = save_rstd[ch], gam = bn_w[ch], bet = bn_b[ch];
+  const int r0 = blockIdx.x * rows_per_block, r1 = min(rows, r0 + rows_per_block);
+  float s1 = 0.f, s2 = 0.f;
+  for (int r = r0; r < r1; ++r) {
+    float nh = (c[(long)r * C + ch] - mean) * rstd;
+    float y = fmaf(nh, gam, bet);
+    float sg = sigmoid_acc(y);
+    float dn = ld_as_float<TI>(ds + (long)r * C + ch) * sg * (1.f + y * (1.f - sg));
+    s1 += dn;
+    s2 = fmaf(dn, nh, s2);
+  }
+  atomicAdd(sums2 + ch, (double)s1);
+  atomicAdd(sums2 + C + ch, (double)s2);
+}
+
+template <typename TI>
+__global__ void __launch_bounds__(256) bn_silu_bwd_apply_kernel(const TI* __restrict__ ds, const float* __restrict__ c,
+                                                                const float* __restrict__ save_mean,
+                                                                const float* __restrict__ save_rstd,
+                                                                const float* __restrict__ bn_w, const float* __restrict__ bn_b,
+                                                                const double* __restrict__ sums2, float* __restrict__ dc,
+                                                                float* __restrict__ dgamma, float* __restrict__ dbeta, int rows,
+                                                                int C, int rows_per_block) {
+  const int ch = blockIdx.y * 256 + threadIdx.x;
+  const float mean = save_mean[ch], rstd = save_rstd[ch], gam = bn_w[ch], bet = bn_b[ch];
+  const float m1 = (float)(sums2[ch] / (double)rows);
+  const float m2 = (float)(sums2[C + ch] / (double)rows);
+  if (blockIdx.x == 0) {
+    atomicAdd(dbeta + ch, (float)sums2[ch]);
+    atomicAdd(dgamma + ch, (float)sums2[C + ch]);
+  }
+  const int r0 = blockIdx.x * rows_per_block, r1 = min(rows, r0 + rows_per_block);
+  const float gr = gam * rstd;
+  for (int r = r0; r < r1; ++r) {
+    float nh = (c[(long)r * C + ch] - mean) * rstd;
+    float y = fmaf(nh, gam, bet);
+    float sg = sigmoid_acc(y);
+    float dn = ld_as_float<TI>(ds + (long)r * C + ch) * sg * (1.f + y * (1.f - sg));
+    dc[(long)r * C + ch] = gr * (dn - m1 - nh * m2);
+  }
+}
+
+template <typename T>
+__global__ void glu_bwd_kernel(const T* __restrict__ z, const T* __restrict__ dg, T* __restrict__ dz, long rows, int C) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * C) return;
+  long r = i / C;
+  int cc = (int)(i % C);
+  float a = ld_as_float<T>(z + r * 2 * C + cc);
+  float bgate = ld_as_float<T>(z + r * 2 * C + C + cc);
+  float d = ld_as_float<T>(dg + i);
+  float s = sigmoid_acc(bgate);
+  st_from_float<T>(dz + r * 2 * C + cc, d * s);
+  st_from_float<T>(dz + r * 2 * C + C + cc, d * a * s * (1.f - s));
+}
+
+}  // namespace eec
+
+using namespace eec;
+
+#define DW_ARGS_OK()                                                                 \
+  EEC_CHECK_ARG(K == KW, "dwconv: depthwise_kernel_size must be 31 (got %d)", K);    \
+  EEC_CHECK_ARG(C % 256 == 0, "dwconv: channels must be a multiple of 256 (got %d)", C); \
+  if (B == 0 || T == 0) return 0;                                                    \
+  dim3 grid(cdiv(T, TT), B, C / 256)
+
+extern "C" int eec_dwconv_bn_silu_eval(const void* g, int dtype, const float* w, const float* bias, const float* bn_w,
+                                       const float* bn_b, const float* run_mean, const float* run_var, void* out, int B,
+                                       int T, int C, int K, eec_stream_t stream) {
+  DW_ARGS_OK();
+  if (dtype == EEC_F32)
+    dwconv_kernel<float, float, DW_EVAL><<<grid, 256, 0, S(stream)>>>((const float*)g, w, bias, bn_w, bn_b, run_mean, run_var, (float*)out, nullptr, T, C);
+  else
+    dwconv_kernel<__nv_bfloat16, __nv_bfloat16, DW_EVAL><<<grid, 256, 0, S(stream)>>>((const __nv_bfloat16*)g, w, bias, bn_w, bn_b, run_mean, run_var, (__nv_bfloat16*)out, nullptr, T, C);
+  EEC_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int eec_dwconv_stats(const void* g, int dtype, const float* w, const float* bias, float* c, double* sums,
+                                int B, int T, int C, int K, eec_stream_t stream) {
+  DW_ARGS_OK();
+  if (dtype == EEC_F32)
+    dwconv_kernel<float, float, DW_STATS><<<grid, 256, 0, S(stream)>>>((const float*)g, w, bias, nullptr, nullptr, nullptr, nullptr, c, sums, T, C);
+  else
+    dwconv_kernel<__nv_bfloat16, float, DW_STATS><<<grid, 256, 0, S(stream)>>>((const __nv_bfloat16*)g, w, bias, nullptr, nullptr, nullptr, nullptr, c, sums, T, C);
+  EEC_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int eec_bn_silu_train(const float* c, const double* sums, const float* bn_w, const float* bn_b,
+                                 float* run_mean, float* run_var, int64_t* num_batches_tracked, float momentum,
+                                 float* save_mean, float* save_rstd, void* out, int dtype, int rows, int C,
+                                 eec_stream_t stream) {
+  EEC_CHECK_ARG(C % 256 == 0, "bn_silu_train: C %% 256");
+  if (rows == 0) return 0;
+  const int rpb = 64;
+  dim3 grid(cdiv(rows, rpb), C / 256);
+  if (dtype == EEC_F32)
+    bn_silu_train_kernel<float><<<grid, 256, 0, S(stream)>>>(c, sums, bn_w, bn_b, run_mean, run_var, num_batches_tracked, momentum, save_mean, save_rstd, (float*)out, rows, C, rpb);
+  else
+    bn_silu_train_kernel<__nv_bfloat16><<<grid, 256, 0, S(stream)>>>(c, sums, bn_w, bn_b, run_mean, run_var, num_batches_tracked, momentum, save_mean, save_rstd, (__nv_bfloat16*)out, rows, C, rpb);
+  EEC_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int eec_bn_silu_bwd_stats(const void* ds, int dtype, const float* c, const float* save_mean,
+                                     const float* save_rstd, const float* bn_w, const float* bn_b, double* sums2,
+                                     int rows, int C, eec_stream_t stream) {
+  EEC_CHECK_ARG(C % 256 == 0, "bn_silu_bwd_stats: C %% 256");
+  if (rows == 0) return 0;
+  const int rpb = 64;
+  dim3 grid(cdiv(rows, rpb), C / 256);
+  if (dtype == EEC_F32)
+    bn_silu_bwd_stats_kernel<float><<<grid, 256, 0, S(stream)>>>((const float*)ds, c, save_mean, save_rstd, bn_w, bn_b, sums2, rows, C, rpb);
+  else
+    bn_silu_bwd_stats_kernel<__nv_bfloat16><<<grid, 256, 0, S(stream)>>>((const __nv_bfloat16*)ds, c, save_mean, save_rstd, bn_w, bn_b, sums2, rows, C, rpb);
+  EEC_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int eec_bn_silu_bwd_apply(const void* ds, int dtype, const float* c, const float* save_mean,
+                                     const float* save_rstd, const float* bn_w, const float* bn_b, const double* sums2,
+                                     float* dc, float* dgamma, float* dbeta, int rows, int C, eec_stream_t stream) {
+  EEC_CHECK_ARG(C % 256 == 0, "bn_silu_bwd_apply: C %% 256");
+  if (rows == 0) return 0;
+  const int rpb = 64;
+  dim3 grid(cdiv(rows, rpb), C / 256);
+  if (dtype == EEC_F32)
+    bn_silu_bwd_apply_kernel<float><<<grid, 256, 0, S(stream)>>>((const float*)ds, c, save_mean, save_rstd, bn_w, bn_b, sums2, dc, dgamma, dbeta, rows, C, rpb);
+  else
+    bn_silu_bwd_apply_kernel<__nv_bfloat16><<<grid, 256, 0, S(stream)>>>((const __nv_bfloat16*)ds, c, save_mean, save_rstd, bn_w, bn_b, sums2, dc, dgamma, dbeta, rows, C, rpb);
+  EEC_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int eec_dwconv_bwd(const float* dc, const void* g, int dtype, const float* w, void* dg, float* dw,
+                              float* dbias, int B, int T, int C, int K, eec_stream_t stream) {
+  DW_ARGS_OK();
+  if (dtype == EEC_F32) {
+    dwconv_kernel<float, float, DW_BWD_DATA><<<grid, 256, 0, S(stream)>>>(dc, w, nullptr, nullptr, nullptr, nullptr, nullptr, (float*)dg, nullptr, T, C);
+    EEC_LAUNCH_CHECK();
+    dwconv_wgrad_kernel<float><<<grid, 256, 0, S(stream)>>>(dc, (const float*)g, dw, dbias, T, C);
+  } else {
+    dwconv_kernel<float, __nv_bfloat16, DW_BWD_DATA><<<grid, 256, 0, S(stream)>>>(dc, w, nullptr, nullptr, nullptr, nullptr, nullptr, (__nv_bfloat16*)dg, nullptr, T, C);
+    EEC_LAUNCH_CHECK();
+    dwconv_wgrad_kernel<__nv_bfloat16><<<grid, 256, 0, S(stream)>>>(dc, (const __nv_bfloat16*)g, dw, dbias, T, C);
+  }
+  EEC_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int eec_glu_bwd(const void* z, const void* dg, void* dz, int dtype, int rows, int C, eec_stream_t stream) {
+  if (rows == 0) return 0;
+  long total = (long)rows * C;
+  int blocks = (int)cdiv64(total, 256);
+  if (dtype == EEC_F32) glu_bwd_kernel<float><<<blocks, 256, 0, S(stream)>>>((const float*)z, (const float*)dg, (float*)dz, rows, C);
+  else glu_bwd_kernel<__nv_bfloat16><<<blocks, 256, 0, S(stream)>>>((const __nv_bfloat16*)z, (const __nv_bfloat16*)dg, (__nv_bfloat16*)dz, rows, C);
+  EEC_LAUNCH_CHECK();
+  return 0;
+}

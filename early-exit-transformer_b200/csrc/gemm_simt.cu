@@ -1,0 +1,196 @@
+// gemm_simt.cu -- fp32 FFMA GEMM with fused epilogue: the fp32 *parity* path (tcgen05 has no
+// fp32 MMA; SURVEY §7-H4 requires genuinely fp32-accurate arithmetic for bit-exact greedy CTC).
+// Also instantiated for bf16 operands as a debugging cross-check of the tcgen05 kernels
+// (EEC_FORCE_SIMT=1); it is never chosen silently for bf16.
+#include "common.cuh"
+
+namespace eec {
+
+constexpr int BM = 128, BN = 128, BK = 16, NT = 256;
+
+struct SimtParams {
+  int M, N, K;
+  const void* A; long sa_m, sa_k;
+  const void* B; long sb_n, sb_k;
+  const float* bias;
+  int act;
+  void* preact; int ldp;
+  float alpha;
+  const float* residual; int ldr; int res_row_mod;
+  void* C; int ldc;
+  int accumulate;
+  int k_per_split;
+};
+
+template <typename TIn, typename TOut, typename TPre, bool ACC>
+__global__ void __launch_bounds__(NT) gemm_simt_kernel(SimtParams p) {
+  __shared__ float As[BK][BM + 4];
+  __shared__ float Bs[BK][BN + 4];
+  const TIn* __restrict__ A = reinterpret_cast<const TIn*>(p.A);
+  const TIn* __restrict__ B = reinterpret_cast<const TIn*>(p.B);
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int k_begin = blockIdx.z * p.k_per_split;
+  const int k_end = min(p.K, k_begin + p.k_per_split);
+  const int ty = tid / 16, tx = tid % 16;
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+  const bool a_k = (p.sa_k == 1), b_k = (p.sb_k == 1);
+  for (int k0 = k_begin; k0 < k_end; k0 += BK) {
+#pragma unroll
+    for (int i = 0; i < (BM * BK) / NT; ++i) {
+      int idx = tid + NT * i;
+      int m, k;
+      if (a_k) { m = idx / BK; k = idx % BK; } else { m = idx % BM; k = idx / BM; }
+      float v = 0.f;
+      if (m0 + m < p.M && k0 + k < k_end) v = ld_as_float<TIn>(A + (long)(m0 + m) * p.sa_m + (long)(k0 + k) * p.sa_k);
+      As[k][m] = v;
+    }
+#pragma unroll
+    for (int i = 0; i < (BN * BK) / NT; ++i) {
+      int idx = tid + NT * i;
+      int n, k;
+      if (b_k) { n = idx / BK; k = idx % BK; } else { n = idx % BN; k = idx / BN; }
+      float v = 0.f;
+      if (n0 + n < p.N && k0 + k < k_end) v = ld_as_float<TIn>(B + (long)(n0 + n) * p.sb_n + (long)(k0 + k) * p.sb_k);
+      Bs[k][n] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      float a[8], b[8];
+      float4 a0 = *reinterpret_cast<const float4*>(&As[k][ty * 8]);
+      float4 a1 = *reinterpret_cast<const float4*>(&As[k][ty * 8 + 4]);
+      float4 b0 = *reinterpret_cast<const float4*>(&Bs[k][tx * 8]);
+      float4 b1 = *reinterpret_cast<const float4*>(&Bs[k][tx * 8 + 4]);
+      a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+      b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w; b[4] = b1.x; b[5] = b1.y; b[6] = b1.z; b[7] = b1.w;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+
+  TOut* __restrict__ C = reinterpret_cast<TOut*>(p.C);
+  TPre* __restrict__ P = reinterpret_cast<TPre*>(p.preact);
+  const bool first_split = (blockIdx.z == 0);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    int m = m0 + ty * 8 + i;
+    if (m >= p.M) continue;
+    int rr = p.res_row_mod ? (m % p.res_row_mod) : m;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      int n = n0 + tx * 8 + j;
+      if (n >= p.N) continue;
+      float v = acc[i][j];
+      if (p.bias && first_split) v += p.bias[n];
+      if (p.act == EEC_ACT_SILU) {
+        if (P) st_from_float<TPre>(P + (long)m * p.ldp + n, v);
+        v = v * (ACC ? sigmoid_acc(v) : sigmoidf_(v));
+      } else if (p.act == EEC_ACT_DSILU) {
+        float h = ld_as_float<TPre>(P + (long)m * p.ldp + n);
+        float s = ACC ? sigmoid_acc(h) : sigmoidf_(h);
+        v *= s * (1.0f + h * (1.0f - s));
+      }
+      v *= p.alpha;
+      if (p.residual && first_split) v += p.residual[(long)rr * p.ldr + n];
+      if (p.accumulate) {
+        atomicAdd(reinterpret_cast<float*>(p.C) + (long)m * p.ldc + n, v);
+      } else {
+        st_from_float<TOut>(C + (long)m * p.ldc + n, v);
+      }
+    }
+  }
+}
+
+template <typename T, bool ACC>
+__global__ void glu_tail_kernel(const T* __restrict__ z, int ldz, T* __restrict__ out, int ldo, int rows, int C,
+                                float alpha) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  long total = (long)rows * C;
+  if (i >= total) return;
+  int r = (int)(i / C), c = (int)(i % C);
+  float a = ld_as_float<T>(z + (long)r * ldz + c);
+  float g = ld_as_float<T>(z + (long)r * ldz + C + c);
+  float s = ACC ? sigmoid_acc(g) : sigmoidf_(g);
+  st_from_float<T>(out + (long)r * ldo + c, alpha * a * s);
+}
+
+template <typename TIn, typename TOut, typename TPre>
+static int launch(const SimtParams& p, dim3 grid, cudaStream_t st, bool acc) {
+  if (acc) gemm_simt_kernel<TIn, TOut, TPre, true><<<grid, NT, 0, st>>>(p);
+  else gemm_simt_kernel<TIn, TOut, TPre, false><<<grid, NT, 0, st>>>(p);
+  EEC_LAUNCH_CHECK();
+  return 0;
+}
+
+int gemm_simt(const eec_gemm_desc* d, cudaStream_t st) {
+  SimtParams p{};
+  p.M = d->M; p.N = d->N; p.K = d->K;
+  p.A = d->A; p.B = d->B;
+  p.sa_m = d->a_kmajor ? d->lda : 1; p.sa_k = d->a_kmajor ? 1 : d->lda;
+  p.sb_n = d->b_kmajor ? d->ldb : 1; p.sb_k = d->b_kmajor ? 1 : d->ldb;
+  p.bias = d->bias; p.act = d->act; p.preact = d->preact; p.ldp = d->ldp;
+  p.alpha = d->alpha; p.residual = d->residual; p.ldr = d->ldr; p.res_row_mod = d->res_row_mod;
+  p.C = d->C; p.ldc = d->ldc; p.accumulate = d->accumulate;
+  const bool glu = (d->act == EEC_ACT_GLU);
+  int out_dtype = d->out_dtype;
+  if (glu) {
+    EEC_CHECK_ARG(d->preact != nullptr, "gemm(simt): GLU needs a preact (z) buffer");
+    EEC_CHECK_ARG(d->residual == nullptr && !d->accumulate, "gemm(simt): GLU with residual/accumulate unsupported");
+    EEC_CHECK_ARG(d->preact_dtype == d->out_dtype, "gemm(simt): GLU preact dtype must equal out dtype");
+    p.act = EEC_ACT_NONE; p.C = d->preact; p.ldc = d->ldp; p.alpha = 1.f; p.preact = nullptr;
+    out_dtype = d->preact_dtype;
+  }
+  if (p.act == EEC_ACT_DSILU) EEC_CHECK_ARG(d->preact != nullptr, "gemm: DSILU needs preact");
+  if (d->accumulate) EEC_CHECK_ARG(d->out_dtype == EEC_F32, "gemm: accumulate needs fp32 C");
+  int tiles = cdiv(p.N, BN) * cdiv(p.M, BM);
+  int splits = 1;
+  if (d->accumulate && p.K >= 1024 && tiles < 296) {
+    splits = min(cdiv(p.K, 512), max(1, 592 / tiles));
+  }
+  p.k_per_split = cdiv(cdiv(p.K, splits), BK) * BK;
+  splits = cdiv(p.K, p.k_per_split);
+  dim3 grid(cdiv(p.N, BN), cdiv(p.M, BM), splits);
+  const bool acc = (d->in_dtype == EEC_F32);
+  const bool pre_bf16 = (d->preact_dtype == EEC_BF16) && !glu;
+  if (d->in_dtype == EEC_F32) {
+    if (out_dtype == EEC_F32) {
+      if (pre_bf16) { if (int r = launch<float, float, __nv_bfloat16>(p, grid, st, acc)) return r; }
+      else { if (int r = launch<float, float, float>(p, grid, st, acc)) return r; }
+    } else {
+      if (pre_bf16) { if (int r = launch<float, __nv_bfloat16, __nv_bfloat16>(p, grid, st, acc)) return r; }
+      else { if (int r = launch<float, __nv_bfloat16, float>(p, grid, st, acc)) return r; }
+    }
+  } else {
+    if (out_dtype == EEC_F32) {
+      if (pre_bf16) { if (int r = launch<__nv_bfloat16, float, __nv_bfloat16>(p, grid, st, acc)) return r; }
+      else { if (int r = launch<__nv_bfloat16, float, float>(p, grid, st, acc)) return r; }
+    } else {
+      if (pre_bf16) { if (int r = launch<__nv_bfloat16, __nv_bfloat16, __nv_bfloat16>(p, grid, st, acc)) return r; }
+      else { if (int r = launch<__nv_bfloat16, __nv_bfloat16, float>(p, grid, st, acc)) return r; }
+    }
+  }
+  if (glu) {
+    int C = d->N / 2;
+    long total = (long)d->M * C;
+    int blocks = (int)cdiv64(total, 256);
+    if (d->out_dtype == EEC_F32) {
+      if (acc) glu_tail_kernel<float, true><<<blocks, 256, 0, st>>>((const float*)d->preact, d->ldp, (float*)d->C, d->ldc, d->M, C, d->alpha);
+      else glu_tail_kernel<float, false><<<blocks, 256, 0, st>>>((const float*)d->preact, d->ldp, (float*)d->C, d->ldc, d->M, C, d->alpha);
+    } else {
+      glu_tail_kernel<__nv_bfloat16, false><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)d->preact, d->ldp, (__nv_bfloat16*)d->C, d->ldc, d->M, C, d->alpha);
+    }
+    EEC_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+}  // namespace eec

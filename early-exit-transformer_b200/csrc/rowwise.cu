@@ -1,0 +1,395 @@
+// rowwise.cu -- bandwidth-bound row kernels: LayerNorm fwd/bwd, log-softmax (+argmax/entropy),
+// casts, column sums, small glue.  One warp per 256-wide row, 8 contiguous channels per lane
+// (128-bit loads), statistics in fp32 with a two-pass variance held in registers.
+#include "common.cuh"
+
+namespace eec {
+
+constexpr float LN_EPS = 1e-5f;
+
+// ------------------------------------------------------------------ LayerNorm forward
+template <typename TOut>
+__global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta, TOut* __restrict__ out,
+                                                            float* __restrict__ mean, float* __restrict__ rstd, int rows) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const int c0 = lane * 8;
+  float v[8], g[8], b[8];
+  ld8<float>(x + (long)warp * 256 + c0, v);
+  ld8<float>(gamma + c0, g);
+  ld8<float>(beta + c0, b);
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += v[i];
+  const float mu = warp_sum(s) * (1.0f / 256.0f);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { float d = v[i] - mu; q += d * d; }
+  const float rs = rsqrtf(warp_sum(q) * (1.0f / 256.0f) + LN_EPS);
+  float o[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) o[i] = (v[i] - mu) * rs * g[i] + b[i];
+  st8<TOut>(out + (long)warp * 256 + c0, o);
+  if (lane == 0) {
+    if (mean) mean[warp] = mu;
+    if (rstd) rstd[warp] = rs;
+  }
+}
+
+// ------------------------------------------------------------------ LayerNorm backward
+__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                                            const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                            const float* __restrict__ gamma, float* __restrict__ dx,
+                                                            int dx_accumulate, float* __restrict__ dgamma,
+                                                            float* __restrict__ dbeta, int rows) {
+  __shared__ float red[8][256];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int c0 = lane * 8;
+  float g[8], dg[8], db[8];
+  ld8<float>(gamma + c0, g);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { dg[i] = 0.f; db[i] = 0.f; }
+  for (int r = blockIdx.x * 8 + wib; r < rows; r += gridDim.x * 8) {
+    float d[8], v[8];
+    ld8<float>(dy + (long)r * 256 + c0, d);
+    ld8<float>(x + (long)r * 256 + c0, v);
+    const float mu = mean[r], rs = rstd[r];
+    float s1 = 0.f, s2 = 0.f, xh[8], dg_[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      xh[i] = (v[i] - mu) * rs;
+      dg_[i] = d[i] * g[i];
+      s1 += dg_[i];
+      s2 += dg_[i] * xh[i];
+      dg[i] += d[i] * xh[i];
+      db[i] += d[i];
+    }
+    s1 = warp_sum(s1) * (1.0f / 256.0f);
+    s2 = warp_sum(s2) * (1.0f / 256.0f);
+    float o[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = rs * (dg_[i] - s1 - xh[i] * s2);
+    if (dx_accumulate) {
+      float old[8];
+      ld8<float>(dx + (long)r * 256 + c0, old);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] += old[i];
+    }
+    st8<float>(dx + (long)r * 256 + c0, o);
+  }
+  if (dgamma) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) red[wib][c0 + i] = dg[i];
+    __syncthreads();
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
+    atomicAdd(dgamma + threadIdx.x, s);
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) red[wib][c0 + i] = db[i];
+    __syncthreads();
+    s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
+    atomicAdd(dbeta + threadIdx.x, s);
+  }
+}
+
+// ------------------------------------------------------------------ log-softmax (+argmax, entropy), V = 256
+__global__ void __launch_bounds__(256) logsoftmax_kernel(const float* __restrict__ logits, float* __restrict__ out,
+                                                         int32_t* __restrict__ argmax, float* __restrict__ entropy,
+                                                         int rows) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const int c0 = lane * 8;
+  float v[8];
+  ld8<float>(logits + (long)warp * 256 + c0, v);
+  float m = v[0];
+  int mi = c0;
+#pragma unroll
+  for (int i = 1; i < 8; ++i)
+    if (v[i] > m) { m = v[i]; mi = c0 + i; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    float om = __shfl_xor_sync(0xffffffffu, m, o);
+    int oi = __shfl_xor_sync(0xffffffffu, mi, o);
+    if (om > m || (om == m && oi < mi)) { m = om; mi = oi; }
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += expf(v[i] - m);
+  s = warp_sum(s);
+  const float lse = m + logf(s);
+  float o[8], h = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    o[i] = v[i] - lse;
+    h -= expf(o[i]) * o[i];
+  }
+  st8<float>(out + (long)warp * 256 + c0, o);
+  if (entropy) {
+    h = warp_sum(h);
+    if (lane == 0) entropy[warp] = h;
+  }
+  if (argmax && lane == 0) argmax[warp] = mi;
+}
+
+// generic log-softmax backward: dlogits = g - exp(lp) * sum(g)   (V = 256)
+__global__ void __launch_bounds__(256) logsoftmax_bwd_kernel(const float* __restrict__ g, const float* __restrict__ lp,
+                                                             float* __restrict__ dl, int rows) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const int c0 = lane * 8;
+  float gv[8], l[8];
+  ld8<float>(g + (long)warp * 256 + c0, gv);
+  ld8<float>(lp + (long)warp * 256 + c0, l);
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += gv[i];
+  s = warp_sum(s);
+  float o[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) o[i] = gv[i] - expf(l[i]) * s;
+  st8<float>(dl + (long)warp * 256 + c0, o);
+}
+
+// ------------------------------------------------------------------ casts
+template <typename TI, typename TO>
+__global__ void cast_kernel(const TI* __restrict__ in, TO* __restrict__ out, long n) {
+  long i = ((long)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  if (i + 8 <= n) {
+    float v[8];
+    ld8<TI>(in + i, v);
+    st8<TO>(out + i, v);
+  } else {
+    for (; i < n; ++i) st_from_float<TO>(out + i, ld_as_float<TI>(in + i));
+  }
+}
+
+// ------------------------------------------------------------------ column sums: out[c] += sum_r in[r,c]
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ in, int ld, float* __restrict__ out, int rows,
+                                                     int cols, int rows_per_block, float scale) {
+  __shared__ float red[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx;
+  const int r0 = blockIdx.y * rows_per_block;
+  const int r1 = min(rows, r0 + rows_per_block);
+  float s = 0.f;
+  if (c < cols)
+    for (int r = r0 + ty; r < r1; r += 8) s += ld_as_float<T>(in + (long)r * ld + c);
+  red[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i][tx];
+    if (c < cols) atomicAdd(out + c, t * scale);
+  }
+}
+
+__global__ void axpy_kernel(const float* __restrict__ x, float a, float* __restrict__ y, long n) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = fmaf(a, x[i], y[i]);
+}
+
+__global__ void scale_dev_kernel(const float* __restrict__ x, const float* __restrict__ s, float* __restrict__ y, long n) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const float a = *s;
+  if (i < n) y[i] = a * x[i];
+}
+
+__global__ void encoder_lengths_kernel(const int64_t* __restrict__ lengths, int32_t* __restrict__ key_len, int B, int T,
+                                       int div, int add) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  // torch: clamp((lengths+add) / div, max=T).to(int): float32 true division, truncation
+  float q = (float)(lengths[b] + add) / (float)div;
+  q = fminf(q, (float)T);
+  key_len[b] = (int32_t)q;
+}
+
+// ------------------------------------------------------------------ Splitformer glue (early_exit.py:318-356)
+__global__ void stride2_gather_kernel(const float4* __restrict__ x, float4* __restrict__ y, int B, int T, int T2, int D4) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  long total = (long)B * T2 * D4;
+  if (i >= total) return;
+  int c = (int)(i % D4);
+  long r = i / D4;
+  int t2 = (int)(r % T2), b = (int)(r / T2);
+  int t = 2 * t2;
+  y[i] = (t < T) ? x[((long)b * T + t) * D4 + c] : make_float4(0.f, 0.f, 0.f, 0.f);
+}
+__global__ void repeat2_add_kernel(const float4* __restrict__ up, float4* __restrict__ y, int B, int T, int T2, int D4) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  long total = (long)B * T * D4;
+  if (i >= total) return;
+  int c = (int)(i % D4);
+  long r = i / D4;
+  int t = (int)(r % T), b = (int)(r / T);
+  float4 u = up[((long)b * T2 + (t >> 1)) * D4 + c];
+  float4 v = y[i];
+  y[i] = make_float4(v.x + u.x, v.y + u.y, v.z + u.z, v.w + u.w);
+}
+__global__ void repeat2_bwd_kernel(const float4* __restrict__ dy, float4* __restrict__ dh, int B, int T, int T2, int D4) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  long total = (long)B * T2 * D4;
+  if (i >= total) return;
+  int c = (int)(i % D4);
+  long r = i / D4;
+  int t2 = (int)(r % T2), b = (int)(r / T2);
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int j = 0; j < 2; ++j) {
+    int t = 2 * t2 + j;
+    if (t < T) {
+      float4 v = dy[((long)b * T + t) * D4 + c];
+      a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+    }
+  }
+  dh[i] = a;
+}
+__global__ void stride2_scatter_add_kernel(const float4* __restrict__ dh, float4* __restrict__ dx, int B, int T, int T2, int D4) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  long total = (long)B * T2 * D4;
+  if (i >= total) return;
+  int c = (int)(i % D4);
+  long r = i / D4;
+  int t2 = (int)(r % T2), b = (int)(r / T2);
+  int t = 2 * t2;
+  if (t >= T) return;
+  long o = ((long)b * T + t) * D4 + c;
+  float4 v = dx[o], u = dh[i];
+  dx[o] = make_float4(v.x + u.x, v.y + u.y, v.z + u.z, v.w + u.w);
+}
+
+}  // namespace eec
+
+using namespace eec;
+
+extern "C" int eec_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* out, int out_dtype,
+                                 float* mean, float* rstd, int rows, int d, eec_stream_t stream) {
+  EEC_CHECK_ARG(d == 256, "layernorm_fwd: d must be 256 (got %d)", d);
+  if (rows == 0) return 0;
+  int blocks = cdiv(rows, 8);
+  if (out_dtype == EEC_F32)
+    layernorm_fwd_kernel<float><<<blocks, 256, 0, S(stream)>>>(x, gamma, beta, (float*)out, mean, rstd, rows);
+  else
+    layernorm_fwd_kernel<__nv_bfloat16><<<blocks, 256, 0, S(stream)>>>(x, gamma, beta, (__nv_bfloat16*)out, mean, rstd, rows);
+  EEC_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int eec_layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd,
+                                 const float* gamma, float* dx, int dx_accumulate, float* dgamma, float* dbeta,
+                                 int rows, int d, eec_stream_t stream) {
+  EEC_CHECK_ARG(d == 256, "layernorm_bwd: d must be 256 (got %d)", d);
+  if (rows == 0) return 0;
+  int blocks = min(cdiv(rows, 8), 148 * 4);
+  layernorm_bwd_kernel<<<blocks, 256, 0, S(stream)>>>(dy, x, mean, rstd, gamma, dx, dx_accumulate, dgamma, dbeta, rows);
+  EEC_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int eec_logsoftmax_fwd(const float* logits, float* out, int32_t* argmax, float* entropy, int rows, int V,
+                                  eec_stream_t stream) {
+  EEC_CHECK_ARG(V == 256, "logsoftmax: V must be 256 (got %d)", V);
+  if (rows == 0) return 0;
+  logsoftmax_kernel<<<cdiv(rows, 8), 256, 0, S(stream)>>>(logits, out, argmax, entropy, rows);
+  EEC_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int eec_logsoftmax_bwd(const float* g, const float* lp, float* dlogits, int rows, int V, eec_stream_t stream) {
+  EEC_CHECK_ARG(V == 256, "logsoftmax_bwd: V must be 256 (got %d)", V);
+  if (rows == 0) return 0;
+  logsoftmax_bwd_kernel<<<cdiv(rows, 8), 256, 0, S(stream)>>>(g, lp, dlogits, rows);
+  EEC_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int eec_cast(const void* in, int in_dtype, void* out, int out_dtype, int64_t n, eec_stream_t stream) {
+  if (n == 0) return 0;
+  int blocks = (int)cdiv64(cdiv64(n, 8), 256);
+  if (in_dtype == EEC_F32 && out_dtype == EEC_BF16)
+    cast_kernel<float, __nv_bfloat16><<<blocks, 256, 0, S(stream)>>>((const float*)in, (__nv_bfloat16*)out, n);
+  else if (in_dtype == EEC_BF16 && out_dtype == EEC_F32)
+    cast_kernel<__nv_bfloat16, float><<<blocks, 256, 0, S(stream)>>>((const __nv_bfloat16*)in, (float*)out, n);
+  else if (in_dtype == EEC_F32 && out_dtype == EEC_F32)
+    cast_kernel<float, float><<<blocks, 256, 0, S(stream)>>>((const float*)in, (float*)out, n);
+  else
+    cast_kernel<__nv_bfloat16, __nv_bfloat16><<<blocks, 256, 0, S(stream)>>>((const __nv_bfloat16*)in, (__nv_bfloat16*)out, n);
+  EEC_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int eec_colsum(const void* in, int dtype, int ld, float* out, float scale, int rows, int cols,
+                          eec_stream_t stream) {
+  if (rows == 0 || cols == 0) return 0;
+  int rpb = 256;
+  dim3 grid(cdiv(cols, 32), cdiv(rows, rpb));
+  if (dtype == EEC_F32) colsum_kernel<float><<<grid, 256, 0, S(stream)>>>((const float*)in, ld, out, rows, cols, rpb, scale);
+  else colsum_kernel<__nv_bfloat16><<<grid, 256, 0, S(stream)>>>((const __nv_bfloat16*)in, ld, out, rows, cols, rpb, scale);
+  EEC_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int eec_axpy(const float* x, float a, float* y, int64_t n, eec_stream_t stream) {
+  if (n == 0) return 0;
+  axpy_kernel<<<(int)cdiv64(n, 256), 256, 0, S(stream)>>>(x, a, y, n);
+  EEC_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int eec_scale_dev(const float* x, const float* s_dev, float* y, int64_t n, eec_stream_t stream) {
+  if (n == 0) return 0;
+  scale_dev_kernel<<<(int)cdiv64(n, 256), 256, 0, S(stream)>>>(x, s_dev, y, n);
+  EEC_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int eec_encoder_lengths(const int64_t* lengths, int32_t* key_len, int B, int T, int div, int add,
+                                   eec_stream_t stream) {
+  if (B == 0) return 0;
+  encoder_lengths_kernel<<<cdiv(B, 128), 128, 0, S(stream)>>>(lengths, key_len, B, T, div, add);
+  EEC_LAUNCH_CHECK();
+  return 0;
+}
+
+#define EEC_SPLIT_LAUNCH(kernel, total, ...)                                        \
+  do {                                                                              \
+    long tot_ = (total);                                                            \
+    if (tot_ > 0) {                                                                 \
+      kernel<<<(int)cdiv64(tot_, 256), 256, 0, S(stream)>>>(__VA_ARGS__);           \
+      EEC_LAUNCH_CHECK();                                                           \
+    }                                                                               \
+  } while (0)
+
+extern "C" int eec_stride2_gather(const float* x, float* y, int B, int T, int D, eec_stream_t stream) {
+  EEC_CHECK_ARG(D % 4 == 0, "stride2_gather: D %% 4");
+  int T2 = (T + 1) / 2;
+  EEC_SPLIT_LAUNCH(stride2_gather_kernel, (long)B * T2 * (D / 4), (const float4*)x, (float4*)y, B, T, T2, D / 4);
+  return 0;
+}
+extern "C" int eec_repeat2_add(const float* up, float* y, int B, int T, int D, eec_stream_t stream) {
+  EEC_CHECK_ARG(D % 4 == 0, "repeat2_add: D %% 4");
+  int T2 = (T + 1) / 2;
+  EEC_SPLIT_LAUNCH(repeat2_add_kernel, (long)B * T * (D / 4), (const float4*)up, (float4*)y, B, T, T2, D / 4);
+  return 0;
+}
+extern "C" int eec_repeat2_bwd(const float* dy, float* dhalf, int B, int T, int D, eec_stream_t stream) {
+  EEC_CHECK_ARG(D % 4 == 0, "repeat2_bwd: D %% 4");
+  int T2 = (T + 1) / 2;
+  EEC_SPLIT_LAUNCH(repeat2_bwd_kernel, (long)B * T2 * (D / 4), (const float4*)dy, (float4*)dhalf, B, T, T2, D / 4);
+  return 0;
+}
+extern "C" int eec_stride2_scatter_add(const float* dhalf, float* dx, int B, int T, int D, eec_stream_t stream) {
+  EEC_CHECK_ARG(D % 4 == 0, "stride2_scatter_add: D %% 4");
+  int T2 = (T + 1) / 2;
+  EEC_SPLIT_LAUNCH(stride2_scatter_add_kernel, (long)B * T2 * (D / 4), (const float4*)dhalf, (float4*)dx, B, T, T2, D / 4);
+  return 0;
+}

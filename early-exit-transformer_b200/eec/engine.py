@@ -1,0 +1,452 @@
+"""Forward / backward orchestration of the early-exit conformer encoder over libeec.so kernels.
+
+This is the "manual tape" engine behind ``eec.early_exit.Early_conformer``: one Python function
+launches every kernel of the forward pass (and records the buffers backward needs), a second one
+replays the exact adjoint.  No autograd graph, no torch arithmetic: torch tensors are device
+buffers only.  Layer arithmetic follows torchaudio ``ConformerLayer.forward`` (TA:176-212) as
+restated in SURVEY.md Appendix A; model structure follows early_exit.py:617-634 (Early_conformer)
+and :299-364 (Splitformer).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional
+
+import torch
+
+from . import ops
+from .lib import ACT_DSILU, ACT_GLU, ACT_NONE, ACT_SILU, EecError
+
+Tensor = torch.Tensor
+D, F, H, KW, V = 256, 2048, 8, 31, 256
+BN_MOMENTUM = 0.1
+
+MATRIX_SUFFIXES = (
+    "ffn1.sequential.1.weight", "ffn1.sequential.4.weight", "ffn2.sequential.1.weight", "ffn2.sequential.4.weight",
+    "self_attn.in_proj_weight", "self_attn.out_proj.weight", "conv_module.sequential.0.weight",
+    "conv_module.sequential.5.weight",
+)
+
+
+@dataclass
+class Config:
+    n_exits: int
+    n_layers: int          # per exit group
+    n_mels: int = 80
+    splitformer: bool = False
+    precision: str = "fp32"   # "fp32" (FFMA parity path) or "bf16" (tcgen05 path)
+
+    @property
+    def act_dtype(self):
+        return torch.bfloat16 if self.precision == "bf16" else torch.float32
+
+
+def _empty(shape, dtype, dev):
+    return torch.empty(shape, dtype=dtype, device=dev)
+
+
+class Operands:
+    """GEMM-operand views of the parameters in the activation dtype.  fp32: zero-copy reshapes;
+    bf16: cast by eec_cast into buffers that are refreshed when a parameter's version changes."""
+
+    def __init__(self, cfg: Config):
+        self.cfg = cfg
+        self._cache: Dict[str, tuple] = {}
+
+    def get(self, name: str, p: Tensor, shape2d) -> Tensor:
+        if self.cfg.precision == "fp32":
+            return p.detach().reshape(shape2d)
+        key = (p.data_ptr(), p._version)
+        hit = self._cache.get(name)
+        if hit is not None and hit[0] == key:
+            return hit[1]
+        buf = hit[1] if hit is not None else _empty(shape2d, torch.bfloat16, p.device)
+        ops.cast(p.detach(), buf)
+        self._cache[name] = (key, buf)
+        return buf
+
+    def front_w1(self, p: Tensor) -> Tensor:
+        """conv1 weight (256, n_mels, 3) -> zero-padded (256, 256) operand (K = 3*n_mels padded to 256)."""
+        name = "conv_subsample.sequential.0.weight"
+        key = (p.data_ptr(), p._version)
+        hit = self._cache.get(name)
+        if hit is not None and hit[0] == key:
+            return hit[1]
+        k = p.shape[1] * 3
+        staged = torch.zeros(256, 256, dtype=torch.float32, device=p.device)
+        staged[:, :k].copy_(p.detach().reshape(256, k))  # layout plumbing only
+        if self.cfg.precision == "fp32":
+            buf = staged
+        else:
+            buf = hit[1] if hit is not None else _empty((256, 256), torch.bfloat16, p.device)
+            ops.cast(staged, buf)
+        self._cache[name] = (key, buf)
+        return buf
+
+
+# ----------------------------------------------------------------------------------------------
+# small helpers over ops.gemm
+# ----------------------------------------------------------------------------------------------
+def linear(A, W, out, M, N, K, **kw):
+    ops.gemm(A, W, out, M, N, K, a_kmajor=True, b_kmajor=True, **kw)
+
+
+def dgrad(dY, W, out, M, N_out, K_in, **kw):
+    """out[M,K_in] = dY[M,N_out] @ W[N_out,K_in]"""
+    ops.gemm(dY, W, out, M, K_in, N_out, a_kmajor=True, b_kmajor=False, lda=N_out, ldb=K_in, **kw)
+
+
+def wgrad(dY, X, dW, M, N_out, K_in, alpha=1.0):
+    """dW[N_out,K_in] += alpha * dY[M,N_out]^T @ X[M,K_in]"""
+    ops.gemm(dY, X, dW, N_out, K_in, M, a_kmajor=False, b_kmajor=False, lda=N_out, ldb=K_in, alpha=alpha, accumulate=True)
+
+
+def to_act(x32: Tensor, cfg: Config) -> Tensor:
+    if cfg.precision == "fp32":
+        return x32
+    out = _empty(x32.shape, torch.bfloat16, x32.device)
+    ops.cast(x32, out)
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
+# one ConformerLayer
+# ----------------------------------------------------------------------------------------------
+def layer_forward(P: Dict[str, Tensor], W: Operands, pre: str, x: Tensor, key_len: Tensor, B: int, T: int, cfg: Config,
+                  training: bool, tape: Optional[dict]):
+    """x: fp32 [B*T, 256] -> fp32 [B*T, 256].  TA:176-212."""
+    N = B * T
+    dev = x.device
+    TD = cfg.act_dtype
+    f32 = torch.float32
+    save = tape is not None
+
+    def stat():
+        return (_empty((N,), f32, dev), _empty((N,), f32, dev)) if save else (None, None)
+
+    def ffn(tag: str, x_in: Tensor, u: Tensor, ln_next_g, ln_next_b, ln_out_dtype):
+        q = pre + tag + ".sequential."
+        W1 = W.get(q + "1.weight", P[q + "1.weight"], (F, D))
+        W2 = W.get(q + "4.weight", P[q + "4.weight"], (D, F))
+        hpre = _empty((N, F), TD, dev) if save else None
+        a = _empty((N, F), TD, dev)
+        linear(u, W1, a, N, F, D, bias=P[q + "1.bias"], act=ACT_SILU, preact=hpre)
+        x_out = _empty((N, D), f32, dev)
+        u_next = _empty((N, D), ln_out_dtype, dev)
+        m, r = stat()
+        linear(a, W2, x_out, N, D, F, bias=P[q + "4.bias"], alpha=0.5, residual=x_in, ln_gamma=ln_next_g, ln_beta=ln_next_b,
+               ln_out=u_next, ln_mean=m, ln_rstd=r)
+        return x_out, u_next, hpre, a, m, r
+
+    # ---- FFN1 (TA:185-187): x1 = x + 0.5*FFN(LN(x));  u2 = LN_attn(x1) fused into the GEMM tail
+    q = pre + "ffn1.sequential."
+    u1 = _empty((N, D), TD, dev)
+    m1, r1 = stat()
+    ops.layernorm_fwd(x, P[q + "0.weight"], P[q + "0.bias"], u1, m1, r1)
+    x1, u2, h1pre, a1, m2, r2 = ffn("ffn1", x, u1, P[pre + "self_attn_layer_norm.weight"], P[pre + "self_attn_layer_norm.bias"], TD)
+
+    # ---- MHSA (TA:192-202)
+    Wqkv = W.get(pre + "self_attn.in_proj_weight", P[pre + "self_attn.in_proj_weight"], (3 * D, D))
+    Wo = W.get(pre + "self_attn.out_proj.weight", P[pre + "self_attn.out_proj.weight"], (D, D))
+    qkv = _empty((N, 3 * D), TD, dev)
+    linear(u2, Wqkv, qkv, N, 3 * D, D, bias=P[pre + "self_attn.in_proj_bias"])
+    ctx = _empty((N, D), TD, dev)
+    lse = _empty((B, H, T), f32, dev)
+    ops.attn_fwd(qkv, key_len, ctx, lse, B, T, H)
+    x2 = _empty((N, D), f32, dev)
+    u3 = _empty((N, D), TD, dev)
+    m3, r3 = stat()
+    c = pre + "conv_module."
+    linear(ctx, Wo, x2, N, D, D, bias=P[pre + "self_attn.out_proj.bias"], residual=x1, ln_gamma=P[c + "layer_norm.weight"],
+           ln_beta=P[c + "layer_norm.bias"], ln_out=u3, ln_mean=m3, ln_rstd=r3)
+
+    # ---- convolution module (TA:42-75, 168-174)
+    Wp1 = W.get(c + "sequential.0.weight", P[c + "sequential.0.weight"], (2 * D, D))
+    Wp2 = W.get(c + "sequential.5.weight", P[c + "sequential.5.weight"], (D, D))
+    z = _empty((N, 2 * D), TD, dev) if (save or cfg.precision == "fp32") else None
+    g = _empty((N, D), TD, dev)
+    linear(u3, Wp1, g, N, 2 * D, D, bias=P[c + "sequential.0.bias"], act=ACT_GLU, preact=z)
+    s = _empty((N, D), TD, dev)
+    wdw = P[c + "sequential.2.weight"].detach().reshape(D, KW)
+    cbuf = sm = sr = None
+    if training:
+        cbuf = _empty((N, D), f32, dev)
+        sums = torch.zeros(2 * D, dtype=torch.float64, device=dev)
+        ops.dwconv_stats(g, wdw, P[c + "sequential.2.bias"], cbuf, sums, B, T, KW)
+        sm, sr = _empty((D,), f32, dev), _empty((D,), f32, dev)
+        ops.bn_silu_train(cbuf, sums, P[c + "sequential.3.weight"], P[c + "sequential.3.bias"],
+                          P[c + "sequential.3.running_mean"], P[c + "sequential.3.running_var"],
+                          P[c + "sequential.3.num_batches_tracked"], BN_MOMENTUM, sm, sr, s)
+    else:
+        ops.dwconv_bn_silu_eval(g, wdw, P[c + "sequential.2.bias"], P[c + "sequential.3.weight"], P[c + "sequential.3.bias"],
+                                P[c + "sequential.3.running_mean"], P[c + "sequential.3.running_var"], s, B, T, KW)
+    x3 = _empty((N, D), f32, dev)
+    u4 = _empty((N, D), TD, dev)
+    m4, r4 = stat()
+    q2 = pre + "ffn2.sequential."
+    linear(s, Wp2, x3, N, D, D, bias=P[c + "sequential.5.bias"], residual=x2, ln_gamma=P[q2 + "0.weight"],
+           ln_beta=P[q2 + "0.bias"], ln_out=u4, ln_mean=m4, ln_rstd=r4)
+
+    # ---- FFN2 + final LayerNorm (TA:207-211): x4 = x3 + 0.5*FFN(u4); y = LN_final(x4)
+    x4, y, h2pre, a2, m5, r5 = ffn("ffn2", x3, u4, P[pre + "final_layer_norm.weight"], P[pre + "final_layer_norm.bias"], f32)
+
+    if save:
+        tape.update(dict(x=x, u1=u1, m1=m1, r1=r1, h1pre=h1pre, a1=a1, x1=x1, u2=u2, m2=m2, r2=r2, qkv=qkv, ctx=ctx, lse=lse,
+                         x2=x2, u3=u3, m3=m3, r3=r3, z=z, g=g, c=cbuf, sm=sm, sr=sr, s=s, x3=x3, u4=u4, m4=m4, r4=r4,
+                         h2pre=h2pre, a2=a2, x4=x4, m5=m5, r5=r5, key_len=key_len, B=B, T=T))
+    return y
+
+
+def layer_backward(P, W: Operands, G: Dict[str, Tensor], pre: str, t: dict, dY: Tensor, cfg: Config) -> Tensor:
+    """dY: fp32 grad wrt the layer output -> fp32 grad wrt the layer input (dY's buffer is reused)."""
+    B, T = t["B"], t["T"]
+    N = B * T
+    dev = dY.device
+    TD = cfg.act_dtype
+    f32 = torch.float32
+    c = pre + "conv_module."
+
+    # final LayerNorm
+    dX = _empty((N, D), f32, dev)
+    k = pre + "final_layer_norm."
+    ops.layernorm_bwd(dY, t["x4"], t["m5"], t["r5"], P[k + "weight"], dX, False, G[k + "weight"], G[k + "bias"])
+
+    def ffn_bwd(tag, x_in, u, m, r, hpre, a):
+        q = pre + tag + ".sequential."
+        W1 = W.get(q + "1.weight", P[q + "1.weight"], (F, D))
+        W2 = W.get(q + "4.weight", P[q + "4.weight"], (D, F))
+        dXh = to_act(dX, cfg)
+        wgrad(dXh, a, G[q + "4.weight"], N, D, F, alpha=0.5)
+        ops.colsum(dX, G[q + "4.bias"], N, D, scale=0.5)
+        dh = _empty((N, F), TD, dev)
+        dgrad(dXh, W2, dh, N, D, F, act=ACT_DSILU, preact=hpre, alpha=0.5)
+        wgrad(dh, u, G[q + "1.weight"], N, F, D)
+        ops.colsum(dh, G[q + "1.bias"], N, F)
+        du = _empty((N, D), f32, dev)
+        dgrad(dh, W1, du, N, F, D)
+        ops.layernorm_bwd(du, x_in, m, r, P[q + "0.weight"], dX, True, G[q + "0.weight"], G[q + "0.bias"])
+
+    # FFN2: x4 = x3 + 0.5*FFN(u4), u4 = LN(x3)
+    ffn_bwd("ffn2", t["x3"], t["u4"], t["m4"], t["r4"], t["h2pre"], t["a2"])
+
+    # conv module: x3 = x2 + pw2(s) + b
+    Wp1 = W.get(c + "sequential.0.weight", P[c + "sequential.0.weight"], (2 * D, D))
+    Wp2 = W.get(c + "sequential.5.weight", P[c + "sequential.5.weight"], (D, D))
+    dXh = to_act(dX, cfg)
+    wgrad(dXh, t["s"], G[c + "sequential.5.weight"].view(D, D), N, D, D)
+    ops.colsum(dX, G[c + "sequential.5.bias"], N, D)
+    ds = _empty((N, D), TD, dev)
+    dgrad(dXh, Wp2, ds, N, D, D)
+    dc = _empty((N, D), f32, dev)
+    sums2 = torch.zeros(2 * D, dtype=torch.float64, device=dev)
+    ops.bn_silu_bwd(ds, t["c"], t["sm"], t["sr"], P[c + "sequential.3.weight"], P[c + "sequential.3.bias"], sums2, dc,
+                    G[c + "sequential.3.weight"], G[c + "sequential.3.bias"])
+    dg = _empty((N, D), TD, dev)
+    wdw = P[c + "sequential.2.weight"].detach().reshape(D, KW)
+    ops.dwconv_bwd(dc, t["g"], wdw, dg, G[c + "sequential.2.weight"].view(D, KW), G[c + "sequential.2.bias"], B, T, KW)
+    dz = _empty((N, 2 * D), TD, dev)
+    ops.glu_bwd(t["z"], dg, dz)
+    wgrad(dz, t["u3"], G[c + "sequential.0.weight"].view(2 * D, D), N, 2 * D, D)
+    ops.colsum(dz, G[c + "sequential.0.bias"], N, 2 * D)
+    du3 = _empty((N, D), f32, dev)
+    dgrad(dz, Wp1, du3, N, 2 * D, D)
+    ops.layernorm_bwd(du3, t["x2"], t["m3"], t["r3"], P[c + "layer_norm.weight"], dX, True, G[c + "layer_norm.weight"],
+                      G[c + "layer_norm.bias"])
+
+    # MHSA: x2 = x1 + out_proj(attn(qkv)) ; qkv = in_proj(u2); u2 = LN(x1)
+    Wqkv = W.get(pre + "self_attn.in_proj_weight", P[pre + "self_attn.in_proj_weight"], (3 * D, D))
+    Wo = W.get(pre + "self_attn.out_proj.weight", P[pre + "self_attn.out_proj.weight"], (D, D))
+    dXh = to_act(dX, cfg)
+    wgrad(dXh, t["ctx"], G[pre + "self_attn.out_proj.weight"], N, D, D)
+    ops.colsum(dX, G[pre + "self_attn.out_proj.bias"], N, D)
+    dctx = _empty((N, D), TD, dev)
+    dgrad(dXh, Wo, dctx, N, D, D)
+    dqkv = _empty((N, 3 * D), TD, dev)
+    dvec = _empty((B * H * T,), f32, dev)
+    ops.attn_bwd(t["qkv"], t["ctx"], dctx, t["lse"], t["key_len"], dqkv, dvec, B, T, H)
+    wgrad(dqkv, t["u2"], G[pre + "self_attn.in_proj_weight"], N, 3 * D, D)
+    ops.colsum(dqkv, G[pre + "self_attn.in_proj_bias"], N, 3 * D)
+    du2 = _empty((N, D), f32, dev)
+    dgrad(dqkv, Wqkv, du2, N, 3 * D, D)
+    k = pre + "self_attn_layer_norm."
+    ops.layernorm_bwd(du2, t["x1"], t["m2"], t["r2"], P[k + "weight"], dX, True, G[k + "weight"], G[k + "bias"])
+
+    # FFN1
+    ffn_bwd("ffn1", t["x"], t["u1"], t["m1"], t["r1"], t["h1pre"], t["a1"])
+    return dX
+
+
+# ----------------------------------------------------------------------------------------------
+# front end (early_exit.py:24-48 + positional_encoding.py:70-72)
+# ----------------------------------------------------------------------------------------------
+def frontend_forward(P, W: Operands, src: Tensor, cfg: Config, tape: Optional[dict]):
+    B, n_mels, T_in = src.shape
+    T1 = (T_in - 3) // 2 + 1
+    T = (T1 - 3) // 2 + 1
+    if T < 1:
+        raise EecError(f"input too short: T_in={T_in}")
+    pe = P["positional_encoder.pe"]
+    if T > pe.shape[0]:
+        raise RuntimeError(f"The size of tensor a ({T}) must match the size of tensor b ({pe.shape[0]}) at non-singleton dimension 0")
+    dev, TD, f32 = src.device, cfg.act_dtype, torch.float32
+    W1 = W.front_w1(P["conv_subsample.sequential.0.weight"])
+    W2 = W.get("conv_subsample.sequential.1.weight", P["conv_subsample.sequential.1.weight"], (D, 3 * D))
+    cols1 = _empty((B * T1, 256), TD, dev)
+    ops.im2col_k3s2(src, n_mels * T_in, T_in, 1, cols1, 256, B, n_mels, T1)
+    x1 = _empty((B * T1, D), f32, dev)
+    linear(cols1, W1, x1, B * T1, D, 256, bias=P["conv_subsample.sequential.0.bias"])
+    cols2 = _empty((B * T, 3 * D), TD, dev)
+    ops.im2col_k3s2(x1, T1 * D, 1, D, cols2, 3 * D, B, D, T)
+    x0 = _empty((B * T, D), f32, dev)
+    linear(cols2, W2, x0, B * T, D, 3 * D, bias=P["conv_subsample.sequential.1.bias"], residual=pe.view(-1, D), res_row_mod=T)
+    if tape is not None:
+        tape.update(dict(cols1=cols1, cols2=cols2, B=B, T=T, T1=T1, n_mels=n_mels))
+    return x0, T
+
+
+def frontend_backward(P, W: Operands, G, t: dict, dX: Tensor, cfg: Config):
+    B, T, T1, n_mels = t["B"], t["T"], t["T1"], t["n_mels"]
+    dev, f32 = dX.device, torch.float32
+    W2 = W.get("conv_subsample.sequential.1.weight", P["conv_subsample.sequential.1.weight"], (D, 3 * D))
+    ops.colsum(dX, G["conv_subsample.sequential.1.bias"], B * T, D)
+    dXh = to_act(dX, cfg)
+    wgrad(dXh, t["cols2"], G["conv_subsample.sequential.1.weight"].view(D, 3 * D), B * T, D, 3 * D)
+    dcols2 = _empty((B * T, 3 * D), f32, dev)
+    dgrad(dXh, W2, dcols2, B * T, D, 3 * D)
+    dx1 = _empty((B * T1, D), f32, dev)
+    ops.col2im_k3s2(dcols2, 3 * D, dx1, B, D, T1, T)
+    ops.colsum(dx1, G["conv_subsample.sequential.0.bias"], B * T1, D)
+    dW1p = torch.zeros(256, 256, dtype=f32, device=dev)
+    wgrad(to_act(dx1, cfg), t["cols1"], dW1p, B * T1, D, 256)
+    k = 3 * n_mels
+    G["conv_subsample.sequential.0.weight"].view(D, k).copy_(dW1p[:, :k])  # un-pad into the zeroed grad (layout plumbing)
+
+
+# ----------------------------------------------------------------------------------------------
+# whole model
+# ----------------------------------------------------------------------------------------------
+@dataclass
+class Tape:
+    front: dict = field(default_factory=dict)
+    layers: List[dict] = field(default_factory=list)       # in execution order, each with "pre"
+    heads: List[dict] = field(default_factory=list)
+    branches: List[Optional[dict]] = field(default_factory=list)
+    out: Optional[Tensor] = None
+    B: int = 0
+    T: int = 0
+
+
+def check_lengths(lengths: Tensor, T: int):
+    """torchaudio builds the key-padding mask with width max(length) (TA:11-14) and
+    nn.MultiheadAttention asserts its shape: preserve that error."""
+    if not lengths.is_cuda:
+        mx = int(torch.clamp(lengths / 4, max=T).to(torch.int).max())
+        if mx < T:
+            raise AssertionError(f"Expected key_padded_mask.shape[1] to be {T}, but got {mx}")
+
+
+def model_forward(P: Dict[str, Tensor], W: Operands, cfg: Config, src: Tensor, lengths: Tensor, training: bool,
+                  want_tape: bool, side: Optional[dict] = None):
+    """-> (out [E,B,T,V] fp32 log-probs, Tape|None).  `side` (optional dict) receives per-exit
+    argmax / frame-entropy tensors when it contains the key "want"."""
+    if not src.is_cuda:
+        raise EecError("eec: input must be on a CUDA device; there is no CPU path")
+    src = src.contiguous()
+    if src.dtype != torch.float32:
+        src = src.float()
+    dev, f32 = src.device, torch.float32
+    tape = Tape() if want_tape else None
+    x, T = frontend_forward(P, W, src, cfg, tape.front if tape else None)
+    B = src.shape[0]
+    N = B * T
+    check_lengths(lengths, T)
+    lengths_dev = lengths.to(device=dev, dtype=torch.int64, non_blocking=True)
+    key_len = _empty((B,), torch.int32, dev)
+    ops.encoder_lengths(lengths_dev, key_len, T, 4, 0)
+    E = cfg.n_exits
+    out = _empty((E, B, T, V), f32, dev)
+    logits_ws = _empty((N, V), f32, dev) if cfg.precision == "fp32" else None
+    want_side = side is not None
+    for e in range(E):
+        x_in = x
+        for l in range(cfg.n_layers):
+            pre = f"conformer.{e}.conformer_layers.{l}."
+            lt = {"pre": pre} if tape else None
+            x = layer_forward(P, W, pre, x, key_len, B, T, cfg, training, lt)
+            if tape:
+                tape.layers.append(lt)
+        br = None
+        if cfg.splitformer and (e == 0 or e == E - 1):
+            # early_exit.py:314-356: parallel stride-2 branch on the group's INPUT; its key mask uses the RAW
+            # fbank lengths (reference quirk) -> clamp((lengths+pad)/2, max=T2)
+            i = e // (E - 1)
+            T2 = (T + 1) // 2
+            pad = T % 2
+            xd = _empty((B * T2, D), f32, dev)
+            ops.stride2_gather(x_in, xd, B, T)
+            len2 = _empty((B,), torch.int32, dev)
+            ops.encoder_lengths(lengths_dev, len2, T2, 2, pad)
+            pre = f"conformer_parallel.{i}.conformer_layers.0."
+            br = {"pre": pre} if tape else None
+            yd = layer_forward(P, W, pre, xd, len2, B, T2, cfg, training, br)
+            if x is x_in:
+                x = x.clone()
+            ops.repeat2_add(yd, x, B, T)
+        if tape:
+            tape.branches.append(br)
+        xh = to_act(x, cfg)
+        Wh = W.get(f"linears.{e}.weight", P[f"linears.{e}.weight"], (V, D))
+        am = _empty((N,), torch.int32, dev) if want_side else None
+        en = _empty((N,), f32, dev) if want_side else None
+        ops.head_logsoftmax(xh, Wh, P[f"linears.{e}.bias"], out[e], am, en, logits_ws)
+        if want_side:
+            side.setdefault("argmax", []).append(am.view(B, T))
+            side.setdefault("entropy", []).append(en.view(B, T))
+        if tape:
+            tape.heads.append({"xh": xh})
+    if want_side:
+        side["key_len"] = key_len
+    if tape:
+        tape.out, tape.B, tape.T = out, B, T
+    return out, tape
+
+
+def model_backward(P, W: Operands, cfg: Config, tape: Tape, gout: Tensor, names: List[str]) -> Dict[str, Tensor]:
+    """gout: grad wrt out [E,B,T,V] (fp32).  Returns fp32 grads for every name in `names`."""
+    dev, f32 = gout.device, torch.float32
+    gout = gout.contiguous()
+    B, T = tape.B, tape.T
+    N = B * T
+    E = cfg.n_exits
+    G = {n: torch.zeros_like(P[n], dtype=f32) for n in names}
+    dX: Optional[Tensor] = None
+    li = len(tape.layers)
+    for e in reversed(range(E)):
+        # exit head: out[e] = log_softmax(x W^T + b)
+        dlog = _empty((N, V), f32, dev)
+        ops.logsoftmax_bwd(gout[e], tape.out[e], dlog)
+        dlogh = to_act(dlog, cfg)
+        Wh = W.get(f"linears.{e}.weight", P[f"linears.{e}.weight"], (V, D))
+        wgrad(dlogh, tape.heads[e]["xh"], G[f"linears.{e}.weight"], N, V, D)
+        ops.colsum(dlog, G[f"linears.{e}.bias"], N, V)
+        if dX is None:
+            dX = _empty((N, D), f32, dev)
+            dgrad(dlogh, Wh, dX, N, V, D)
+        else:
+            dgrad(dlogh, Wh, dX, N, V, D, residual=dX)
+        br = tape.branches[e]
+        d_in_extra = None
+        if br is not None:
+            # x = x_main + repeat2(yd): d(yd)[t2] = dX[2 t2] + dX[2 t2 + 1]; d(x_in) += scatter(d(xd))
+            T2 = (T + 1) // 2
+            dyd = _empty((B * T2, D), f32, dev)
+            ops.repeat2_bwd(dX, dyd, B, T)
+            d_in_extra = layer_backward(P, W, G, br["pre"], br, dyd, cfg)
+        for l in reversed(range(cfg.n_layers)):
+            li -= 1
+            lt = tape.layers[li]
+            dX = layer_backward(P, W, G, lt["pre"], lt, dX, cfg)
+        if d_in_extra is not None:
+            ops.stride2_scatter_add(d_in_extra, dX, B, T)
+    frontend_backward(P, W, G, tape.front, dX, cfg)
+    return G

@@ -1,0 +1,192 @@
+"""Thin Python wrappers over the C ABI: one function per kernel family.  Tensors are torch CUDA
+tensors used purely as device-memory handles (data_ptr + shape); all arithmetic happens in
+libeec.so on torch's current stream."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import lib as L
+from .lib import ACT_DSILU, ACT_GLU, ACT_NONE, ACT_SILU, BF16, F32, call, dt, ptr, stream
+
+Tensor = torch.Tensor
+
+
+def _chk(t: Tensor, name: str):
+    if not t.is_cuda:
+        raise L.EecError(f"{name}: tensor must live on a CUDA device (no CPU path exists)")
+    if not t.is_contiguous():
+        raise L.EecError(f"{name}: tensor must be contiguous")
+
+
+def gemm(
+    A: Tensor, B: Tensor, C_out: Tensor, M: int, N: int, K: int, *,
+    a_kmajor: bool = True, b_kmajor: bool = True, lda: Optional[int] = None, ldb: Optional[int] = None,
+    bias: Optional[Tensor] = None, act: int = ACT_NONE, preact: Optional[Tensor] = None, alpha: float = 1.0,
+    residual: Optional[Tensor] = None, res_row_mod: int = 0, accumulate: bool = False,
+    ln_gamma: Optional[Tensor] = None, ln_beta: Optional[Tensor] = None, ln_out: Optional[Tensor] = None,
+    ln_mean: Optional[Tensor] = None, ln_rstd: Optional[Tensor] = None, ldc: Optional[int] = None,
+):
+    """C[M,N] = epi(A(m,k) B(n,k)).  See include/eec.h::eec_gemm_desc."""
+    for t, n in ((A, "A"), (B, "B"), (C_out, "C")):
+        _chk(t, "gemm." + n)
+    if A.dtype != B.dtype:
+        raise L.EecError("gemm: A and B dtypes differ")
+    d = L.GemmDesc()
+    d.M, d.N, d.K = M, N, K
+    d.A, d.lda, d.a_kmajor = ptr(A), (lda if lda is not None else (K if a_kmajor else M)), int(a_kmajor)
+    d.B, d.ldb, d.b_kmajor = ptr(B), (ldb if ldb is not None else (K if b_kmajor else N)), int(b_kmajor)
+    d.in_dtype = dt(A)
+    d.bias = ptr(bias)
+    d.act = act
+    d.preact = ptr(preact)
+    d.ldp = N
+    d.preact_dtype = dt(preact) if preact is not None else F32
+    d.alpha = alpha
+    d.residual = ptr(residual)
+    d.ldr = N
+    d.res_row_mod = res_row_mod
+    d.C = ptr(C_out)
+    n_out = N // 2 if act == ACT_GLU else N
+    d.ldc = ldc if ldc is not None else n_out
+    d.out_dtype = dt(C_out)
+    d.accumulate = int(accumulate)
+    d.ln_gamma, d.ln_beta, d.ln_out = ptr(ln_gamma), ptr(ln_beta), ptr(ln_out)
+    d.ln_dtype = dt(ln_out) if ln_out is not None else F32
+    d.ld_ln = N
+    d.ln_mean, d.ln_rstd = ptr(ln_mean), ptr(ln_rstd)
+    call("eec_gemm", C.byref(d), stream())
+
+
+def layernorm_fwd(x, gamma, beta, out, mean=None, rstd=None):
+    rows = x.numel() // 256
+    call("eec_layernorm_fwd", ptr(x), ptr(gamma), ptr(beta), ptr(out), dt(out), ptr(mean), ptr(rstd), rows, 256, stream())
+
+
+def layernorm_bwd(dy, x, mean, rstd, gamma, dx, accumulate, dgamma, dbeta):
+    rows = x.numel() // 256
+    call("eec_layernorm_bwd", ptr(dy), ptr(x), ptr(mean), ptr(rstd), ptr(gamma), ptr(dx), int(accumulate), ptr(dgamma),
+         ptr(dbeta), rows, 256, stream())
+
+
+def attn_fwd(qkv, key_len, ctx, lse, B, T, H):
+    call("eec_attn_fwd", ptr(qkv), dt(qkv), ptr(key_len), ptr(ctx), ptr(lse), B, T, H, 32, stream())
+
+
+def attn_bwd(qkv, ctx, dctx, lse, key_len, dqkv, dvec, B, T, H):
+    call("eec_attn_bwd", ptr(qkv), ptr(ctx), ptr(dctx), dt(qkv), ptr(lse), ptr(key_len), ptr(dqkv), ptr(dvec), B, T, H, 32,
+         stream())
+
+
+def dwconv_bn_silu_eval(g, w, bias, bn_w, bn_b, rm, rv, out, B, T, K):
+    call("eec_dwconv_bn_silu_eval", ptr(g), dt(g), ptr(w), ptr(bias), ptr(bn_w), ptr(bn_b), ptr(rm), ptr(rv), ptr(out), B, T,
+         256, K, stream())
+
+
+def dwconv_stats(g, w, bias, c, sums, B, T, K):
+    call("eec_dwconv_stats", ptr(g), dt(g), ptr(w), ptr(bias), ptr(c), ptr(sums), B, T, 256, K, stream())
+
+
+def bn_silu_train(c, sums, bn_w, bn_b, rm, rv, nbt, momentum, save_mean, save_rstd, out):
+    rows = c.numel() // 256
+    call("eec_bn_silu_train", ptr(c), ptr(sums), ptr(bn_w), ptr(bn_b), ptr(rm), ptr(rv), ptr(nbt), momentum, ptr(save_mean),
+         ptr(save_rstd), ptr(out), dt(out), rows, 256, stream())
+
+
+def bn_silu_bwd(ds, c, save_mean, save_rstd, bn_w, bn_b, sums2, dc, dgamma, dbeta):
+    rows = c.numel() // 256
+    call("eec_bn_silu_bwd_stats", ptr(ds), dt(ds), ptr(c), ptr(save_mean), ptr(save_rstd), ptr(bn_w), ptr(bn_b), ptr(sums2),
+         rows, 256, stream())
+    call("eec_bn_silu_bwd_apply", ptr(ds), dt(ds), ptr(c), ptr(save_mean), ptr(save_rstd), ptr(bn_w), ptr(bn_b), ptr(sums2),
+         ptr(dc), ptr(dgamma), ptr(dbeta), rows, 256, stream())
+
+
+def dwconv_bwd(dc, g, w, dg, dw, dbias, B, T, K):
+    call("eec_dwconv_bwd", ptr(dc), ptr(g), dt(g), ptr(w), ptr(dg), ptr(dw), ptr(dbias), B, T, 256, K, stream())
+
+
+def glu_bwd(z, dg, dz):
+    rows = dg.numel() // 256
+    call("eec_glu_bwd", ptr(z), ptr(dg), ptr(dz), dt(z), rows, 256, stream())
+
+
+def head_logsoftmax(x, w, bias, out, argmax=None, entropy=None, logits_ws=None):
+    rows = x.numel() // 256
+    call("eec_head_logsoftmax", ptr(x), dt(x), ptr(w), ptr(bias), ptr(out), ptr(argmax), ptr(entropy), ptr(logits_ws), rows,
+         256, 256, stream())
+
+
+def logsoftmax_bwd(g, lp, dlogits):
+    rows = lp.numel() // 256
+    call("eec_logsoftmax_bwd", ptr(g), ptr(lp), ptr(dlogits), rows, 256, stream())
+
+
+def ctc_fwd_bwd(lp, targets, target_len, nll, loss_out, grad, gscale=1.0, blank=0):
+    """lp [E,B,T,V] fp32; targets [B,Lmax] int64 (device); target_len [B] int64 (device)."""
+    E, B, T, V = lp.shape
+    Lmax = targets.shape[1]
+    nbytes = L.load().eec_ctc_workspace_bytes(E, B, T, Lmax)
+    ws = torch.empty(max(nbytes, 4) // 4, dtype=torch.float32, device=lp.device)
+    call("eec_ctc_fwd_bwd", ptr(lp), ptr(targets), ptr(target_len), E, B, T, V, Lmax, blank, gscale, ptr(nll), ptr(loss_out),
+         ptr(grad), ptr(ws), stream())
+
+
+def greedy_collapse(argmax, tokens, n_tokens, B, T, blank=0):
+    call("eec_greedy_collapse", ptr(argmax), ptr(tokens), ptr(n_tokens), B, T, blank, stream())
+
+
+def im2col_k3s2(inp, sb, sc, st, out, ldo, B, Cin, T_out):
+    call("eec_im2col_k3s2", ptr(inp), dt(inp), sb, sc, st, ptr(out), dt(out), ldo, B, Cin, T_out, stream())
+
+
+def col2im_k3s2(dcols, ldc, dx, B, Cc, T_in, T_out):
+    call("eec_col2im_k3s2", ptr(dcols), ldc, ptr(dx), B, Cc, T_in, T_out, stream())
+
+
+def encoder_lengths(lengths_dev, key_len, T, div=4, add=0):
+    call("eec_encoder_lengths", ptr(lengths_dev), ptr(key_len), lengths_dev.numel(), T, div, add, stream())
+
+
+def cast(inp, out):
+    call("eec_cast", ptr(inp), dt(inp), ptr(out), dt(out), inp.numel(), stream())
+
+
+def colsum(inp, out, rows, cols, scale=1.0, ld=None):
+    call("eec_colsum", ptr(inp), dt(inp), ld if ld is not None else cols, ptr(out), scale, rows, cols, stream())
+
+
+def axpy(x, a, y):
+    call("eec_axpy", ptr(x), a, ptr(y), x.numel(), stream())
+
+
+def scale_dev(x, s_dev, y):
+    call("eec_scale_dev", ptr(x), ptr(s_dev), ptr(y), x.numel(), stream())
+
+
+def exit_select(entropy, argmax, key_len_alive, row_map, n_alive, exit_idx, is_last, threshold, exit_index, tokens, n_tokens,
+                new_row_map, new_key_len, gather_idx, mean_entropy, B, T, blank=0):
+    call("eec_exit_select", ptr(entropy), ptr(argmax), ptr(key_len_alive), ptr(row_map), ptr(n_alive), exit_idx, int(is_last),
+         threshold, ptr(exit_index), ptr(tokens), ptr(n_tokens), ptr(new_row_map), ptr(new_key_len), ptr(gather_idx),
+         ptr(mean_entropy), B, T, blank, stream())
+
+
+def gather_rows(x, y, gather_idx, n_alive, B, row_elems):
+    call("eec_gather_rows", ptr(x), ptr(y), ptr(gather_idx), ptr(n_alive), B, row_elems, stream())
+
+
+def stride2_gather(x, y, B, T, D=256):
+    call("eec_stride2_gather", ptr(x), ptr(y), B, T, D, stream())
+
+
+def repeat2_add(up, y, B, T, D=256):
+    call("eec_repeat2_add", ptr(up), ptr(y), B, T, D, stream())
+
+
+def repeat2_bwd(dy, dhalf, B, T, D=256):
+    call("eec_repeat2_bwd", ptr(dy), ptr(dhalf), B, T, D, stream())
+
+
+def stride2_scatter_add(dhalf, dx, B, T, D=256):
+    call("eec_stride2_scatter_add", ptr(dhalf), ptr(dx), B, T, D, stream())

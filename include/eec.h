@@ -1,0 +1,205 @@
+/* eec.h -- C ABI of libeec.so: hand-written sm_100a kernels for the early-exit conformer
+ * hot path (Early_conformer encoder fwd/bwd + per-exit CTC heads).
+ *
+ * The reference (augustgw/early-exit-transformer) has no FFI of its own: its "operator
+ * interface" for this path is the Python class models/model/early_exit.py:565-634 plus the
+ * torch / torchaudio library calls it issues.  Each entry point below replaces one of those
+ * call sites (cited per function; TA = torchaudio/models/conformer.py 2.11.0).  The host-side
+ * mirror of the reference class that binds these symbols with ctypes lives in
+ * early-exit-transformer_b200/eec/ ; INTEGRATION.md shows the stub a reference maintainer adds.
+ *
+ * Conventions
+ *   - every pointer is a caller-owned DEVICE pointer unless named h_*; nothing is allocated
+ *     inside except small cached TMA descriptors; no implicit synchronisation;
+ *   - all work is enqueued on `stream` (pass torch's current stream);
+ *   - return 0 on success, non-zero on error; eec_last_error() gives a thread-local message;
+ *   - activations are frame-major: row r = b*T + t, channel contiguous;
+ *   - dtype enum selects the storage type of GEMM/attention operands (EEC_F32 = FFMA parity
+ *     path, EEC_BF16 = tcgen05/TMEM/TMA path).  The residual stream, statistics, log-probs,
+ *     CTC and all gradients of parameters are fp32 in both modes.
+ */
+#ifndef EEC_H_
+#define EEC_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* eec_stream_t; /* == cudaStream_t */
+
+typedef enum { EEC_F32 = 0, EEC_BF16 = 1 } eec_dtype;
+typedef enum {
+  EEC_ACT_NONE = 0,
+  EEC_ACT_SILU = 1,  /* out = silu(acc+bias); optional preact store                        */
+  EEC_ACT_GLU = 2,   /* N even; out[:, n] = z[n] * sigmoid(z[n+N/2]), out has N/2 columns   */
+  EEC_ACT_DSILU = 3, /* out = (acc) * silu'(preact[m,n])  (backward of SILU)                */
+} eec_act;
+
+const char* eec_last_error(void);
+int eec_version(void);
+/* 1 when the current device is compute capability 10.x (the only supported target) */
+int eec_device_ok(void);
+
+/* ---- GEMM with fused epilogue -------------------------------------------------------
+ * C[M,N] = epi( sum_k A(m,k) * B(n,k) ),  replaces torch F.linear / 1x1 Conv1d / cuBLAS calls
+ * at TA:104-108 (FFN), torch nn/functional.py in-proj/out-proj (TA:194-200), TA:44-51,66-73
+ * (pointwise convs), early_exit.py:28-43 (front-end convs after im2col), :629 (exit heads),
+ * and their autograd dgrad/wgrad.
+ *   a_kmajor=1: A(m,k) = A[m*lda + k]   a_kmajor=0: A(m,k) = A[k*lda + m]
+ *   b_kmajor=1: B(n,k) = B[n*ldb + k]   b_kmajor=0: B(n,k) = B[k*ldb + n]
+ * epi(v) for element (m,n):  v += bias[n];  v = act(v);  v = alpha*v;
+ *                            v += residual[(res_row_mod ? m % res_row_mod : m)*ldr + n];
+ *                            accumulate ? C[m,n] += v (fp32 atomics, split-K allowed) : C[m,n] = v
+ * Optional row-wise tails (need N == 256 so that one CTA owns whole rows):
+ *   ln_out != NULL : ln_out[m,:] = LayerNorm(C[m,:]; ln_gamma, ln_beta, eps 1e-5) stored as ln_dtype,
+ *                    optional ln_mean/ln_rstd [M] (TA:103,151,42,211)
+ *   ln2_*          : a second LayerNorm applied to ln_out's fp32 value (final_layer_norm followed by
+ *                    the next module's LayerNorm); when set, C receives the FIRST LN's output.
+ */
+typedef struct {
+  int M, N, K;
+  const void* A; int lda; int a_kmajor;
+  const void* B; int ldb; int b_kmajor;
+  int in_dtype;             /* eec_dtype of A and B                                         */
+  const float* bias;        /* [N] or NULL                                                  */
+  int act;                  /* eec_act                                                      */
+  void* preact; int ldp;    /* SILU: optional store of acc+bias (in_dtype... see preact_dtype) */
+  int preact_dtype;         /* eec_dtype of preact (read for DSILU, written for SILU/GLU)   */
+  float alpha;              /* scale applied after act (1.0f if unused)                     */
+  const float* residual; int ldr; int res_row_mod;
+  void* C; int ldc; int out_dtype;
+  int accumulate;           /* 1: fp32 C += result                                          */
+  const float* ln_gamma; const float* ln_beta; void* ln_out; int ln_dtype; int ld_ln;
+  float* ln_mean; float* ln_rstd;
+  const float* ln2_gamma; const float* ln2_beta; float* ln2_mean; float* ln2_rstd;
+  float* x_pre;             /* with ln2: optional fp32 store of the pre-LN1 value (needed for bwd) */
+} eec_gemm_desc;
+int eec_gemm(const eec_gemm_desc* d, eec_stream_t stream);
+
+/* ---- LayerNorm (TA:103,151,42,211) ------------------------------------------------- */
+int eec_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* out, int out_dtype,
+                      float* mean, float* rstd, int rows, int d, eec_stream_t stream);
+/* dx (+)= LN'(dy); dgamma += sum dy*xhat; dbeta += sum dy  (dgamma/dbeta accumulate) */
+int eec_layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd,
+                      const float* gamma, float* dx, int dx_accumulate, float* dgamma, float* dbeta,
+                      int rows, int d, eec_stream_t stream);
+
+/* ---- multi-head self-attention core (nn.MultiheadAttention SDPA branch, TA:194-200) -
+ * qkv [B*T, 3*H*dh] rows = [q | k | v], head h = columns [h*dh, (h+1)*dh) of each third.
+ * keys t' >= key_len[b] are masked; fully-masked rows produce 0.  lse [B,H,T] (natural log). */
+int eec_attn_fwd(const void* qkv, int dtype, const int32_t* key_len, void* ctx, float* lse,
+                 int B, int T, int H, int dh, eec_stream_t stream);
+/* dvec: fp32 workspace [B*H*T] (row dots dO.O) */
+int eec_attn_bwd(const void* qkv, const void* ctx, const void* dctx, int dtype, const float* lse,
+                 const int32_t* key_len, void* dqkv, float* dvec, int B, int T, int H, int dh,
+                 eec_stream_t stream);
+
+/* ---- conformer convolution module interior (TA:52-65) ------------------------------
+ * g [B,T,C] (dtype) -> depthwise conv k (SAME, zero pad per utterance) + bias.
+ * eval : out = silu(bn_eval(c))                     (one kernel)
+ * train: pass A writes c and per-channel sum / sumsq (double[2*C], caller zeroes);
+ *        pass B normalises with batch stats, SiLU, and updates running stats. */
+int eec_dwconv_bn_silu_eval(const void* g, int dtype, const float* w, const float* bias,
+                            const float* bn_w, const float* bn_b, const float* run_mean,
+                            const float* run_var, void* out, int B, int T, int C, int K,
+                            eec_stream_t stream);
+int eec_dwconv_stats(const void* g, int dtype, const float* w, const float* bias, float* c,
+                     double* sums, int B, int T, int C, int K, eec_stream_t stream);
+int eec_bn_silu_train(const float* c, const double* sums, const float* bn_w, const float* bn_b,
+                      float* run_mean, float* run_var, int64_t* num_batches_tracked, float momentum,
+                      float* save_mean, float* save_rstd, void* out, int dtype, int rows, int C,
+                      eec_stream_t stream);
+/* backward of train-mode BN+SiLU+dwconv.  Step 1: dn = ds*silu'(n); sums2 = {sum dn, sum dn*nhat}.
+ * Step 2: dc = gamma*rstd*(dn - mean(dn) - nhat*mean(dn*nhat)); dgamma/dbeta accumulate.
+ * Step 3: dg = dwconv^T(dc); dW/dbias accumulate. */
+int eec_bn_silu_bwd_stats(const void* ds, int dtype, const float* c, const float* save_mean,
+                          const float* save_rstd, const float* bn_w, const float* bn_b, double* sums2,
+                          int rows, int C, eec_stream_t stream);
+int eec_bn_silu_bwd_apply(const void* ds, int dtype, const float* c, const float* save_mean,
+                          const float* save_rstd, const float* bn_w, const float* bn_b,
+                          const double* sums2, float* dc, float* dgamma, float* dbeta, int rows, int C,
+                          eec_stream_t stream);
+int eec_dwconv_bwd(const float* dc, const void* g, int dtype, const float* w, void* dg, float* dw,
+                   float* dbias, int B, int T, int C, int K, eec_stream_t stream);
+/* GLU backward: z [rows, 2C] (dtype), dg [rows,C] (dtype) -> dz [rows,2C] (dtype) */
+int eec_glu_bwd(const void* z, const void* dg, void* dz, int dtype, int rows, int C, eec_stream_t stream);
+
+/* ---- exit head tail (early_exit.py:630): log_softmax over V, + by-products ---------
+ * argmax (int32 [rows]) and entropy (fp32 [rows], -sum p log p) may be NULL. */
+int eec_logsoftmax_fwd(const float* logits, float* out, int32_t* argmax, float* entropy, int rows, int V,
+                       eec_stream_t stream);
+
+/* generic log_softmax backward: dlogits = g - exp(lp) * rowsum(g) */
+int eec_logsoftmax_bwd(const float* g, const float* lp, float* dlogits, int rows, int V, eec_stream_t stream);
+
+/* fused exit head: Linear(d->V) + log_softmax (+argmax, +frame entropy), early_exit.py:629-630.
+ * bf16: one tcgen05 GEMM with the log-softmax in its epilogue; fp32: FFMA GEMM into logits_ws
+ * [rows,V] followed by the row kernel. */
+int eec_head_logsoftmax(const void* x, int dtype, const void* w, const float* bias, float* out,
+                        int32_t* argmax, float* entropy, float* logits_ws, int rows, int d, int V,
+                        eec_stream_t stream);
+
+/* ---- multi-exit CTC (train.py:57-65, nn.CTCLoss(blank=0, 'mean', zero_infinity=True)) --
+ * All E exits in one launch.  lp [E,B,T,V] fp32 log-probs (batch-major), targets [B,Lmax] int64,
+ * target_len [B] int64, input length = T for every utterance.  nll [E,B] (0 where infeasible).
+ * grad [E,B,T,V] (may be NULL) = gscale/(B*max(U_b,1)) * (exp(lp) - occupancy), i.e.
+ * d(loss)/d(logits).  loss_out[e] += sum_b nll_b/(B*max(U_b,1))  (caller zeroes).
+ * workspace: alpha scratch of eec_ctc_workspace_bytes(E,B,T,Lmax). */
+int64_t eec_ctc_workspace_bytes(int E, int B, int T, int Lmax);
+int eec_ctc_fwd_bwd(const float* lp, const int64_t* targets, const int64_t* target_len, int E, int B, int T,
+                    int V, int Lmax, int blank, float gscale, float* nll, float* loss_out, float* grad,
+                    void* workspace, eec_stream_t stream);
+
+/* ---- greedy CTC decode (util/beam_infer.py:21-23): collapse repeats, drop blank ---- */
+int eec_greedy_collapse(const int32_t* argmax, int32_t* tokens, int32_t* n_tokens, int B, int T, int blank,
+                        eec_stream_t stream);
+
+/* ---- front end (early_exit.py:24-48, positional_encoding.py:70-72) ----------------
+ * im2col for Conv1d(k=3,s=2): out[(b,t), c*3+j] = in[b*sb + c*sc + (2t+j)*st]; out row stride ldo */
+int eec_im2col_k3s2(const void* in, int in_dtype, int64_t sb, int64_t sc, int64_t st, void* out,
+                    int out_dtype, int ldo, int B, int C, int T_out, eec_stream_t stream);
+/* transpose of the above for the SECOND conv's input gradient (frame-major x1 [B,T_in,C]):
+ * dx[b,f,c] = sum_{j} dcols[(b,(f-j)/2), c*3+j] over valid (f-j) even */
+int eec_col2im_k3s2(const float* dcols, int ldc, float* dx, int B, int C, int T_in, int T_out,
+                    eec_stream_t stream);
+/* key_len[b] = (int) min(lengths[b]/4.0, T)   (early_exit.py:623) */
+int eec_encoder_lengths(const int64_t* lengths, int32_t* key_len, int B, int T, int div, int add,
+                        eec_stream_t stream);
+
+/* ---- small utilities ----------------------------------------------------------------- */
+int eec_cast(const void* in, int in_dtype, void* out, int out_dtype, int64_t n, eec_stream_t stream);
+/* out[n] += scale * sum_m in[m, n]   (bias gradients; out accumulates) */
+int eec_colsum(const void* in, int dtype, int ld, float* out, float scale, int rows, int cols,
+               eec_stream_t stream);
+/* y = (*s_dev) * x  (device scalar; used to apply an upstream loss gradient without a host sync) */
+int eec_scale_dev(const float* x, const float* s_dev, float* y, int64_t n, eec_stream_t stream);
+/* y = a*x + y over n floats */
+int eec_axpy(const float* x, float a, float* y, int64_t n, eec_stream_t stream);
+
+/* ---- early exit (north star; NOT in the reference) -------------------------------------
+ * mean frame entropy over t < key_len[b]; finalise rows with H < threshold (or last exit):
+ * writes exit_index / tokens for finalised ORIGINAL rows, compacts survivors (stable) and
+ * updates *n_alive on device.  No host sync. */
+int eec_exit_select(const float* entropy, const int32_t* argmax, const int32_t* key_len_alive,
+                    const int32_t* row_map, int32_t* n_alive, int exit_idx, int is_last, float threshold,
+                    int32_t* exit_index, int32_t* tokens, int32_t* n_tokens, int32_t* new_row_map,
+                    int32_t* new_key_len, int32_t* gather_idx, float* mean_entropy_out, int B, int T,
+                    int blank, eec_stream_t stream);
+int eec_gather_rows(const float* x, float* y, const int32_t* gather_idx, const int32_t* n_alive,
+                    int B, int64_t row_elems, eec_stream_t stream);
+
+/* ---- Splitformer branch glue (early_exit.py:318-356) --------------------------------- */
+int eec_stride2_gather(const float* x, float* y, int B, int T, int D, eec_stream_t stream);
+/* y[b,t,:] += up[b,t/2,:] */
+int eec_repeat2_add(const float* up, float* y, int B, int T, int D, eec_stream_t stream);
+/* dy_half[b,t2,:] = dy[b,2*t2,:] + dy[b,2*t2+1,:] (t < T) */
+int eec_repeat2_bwd(const float* dy, float* dhalf, int B, int T, int D, eec_stream_t stream);
+/* dx[b,2*t2,:] += dhalf[b,t2,:] */
+int eec_stride2_scatter_add(const float* dhalf, float* dx, int B, int T, int D, eec_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EEC_H_ */

@@ -1,0 +1,189 @@
+"""GPU parity of the whole hot path (through eec.Early_conformer / Splitformer -> C ABI -> sm_100a kernels)
+against (a) the committed golden vectors produced by the real reference and (b) the CPU oracle run live.
+Tolerances are the north star's: 1e-3 relative (maxabs(a-b)/maxabs(b)) for fp32, 2e-2 for bf16, greedy CTC
+tokens bit-exact for fp32."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import conformer_oracle as O
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+CASES = ["ec_e2l1_b3_t163", "ec_e3l2_b4_t331", "sf_e2l1_b3_t166", "sf_e3l1_b2_t203"]
+TOL = {"fp32": 1e-3, "bf16": 2e-2}
+
+
+def rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def build(name, g, precision):
+    import eec
+    split = name.startswith("sf")
+    cls = eec.Splitformer if split else eec.Early_conformer
+    m = cls(src_pad_idx=0, n_enc_exits=int(g["n_exits"]), enc_voc_size=256, dec_voc_size=256, d_model=256, n_head=8,
+            max_len=2000, d_feed_forward=2048, n_enc_layers=int(g["n_layers"]), features_length=80, drop_prob=0.0,
+            depthwise_kernel_size=31, device=torch.device("cuda"))
+    seed = int(g["seed"])
+    sd = O.make_params(seed, n_exits=int(g["n_exits"]), n_layers=int(g["n_layers"]), splitformer=split)
+    m.load_state_dict(sd, strict=True)
+    m = m.to("cuda")
+    m.precision = precision
+    src, lengths = O.synthetic_batch(int(g["B"]), int(g["t_in"]), seed=seed + 1)
+    return m, sd, src, lengths
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("name", CASES)
+def test_eval_logprobs_vs_reference_golden(name, precision):
+    import eec
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    m, sd, src, lengths = build(name, g, precision)
+    m.eval()
+    with torch.no_grad():
+        out = m(src.cuda(), lengths)
+    ref = torch.from_numpy(g["eval_logprobs"])
+    assert out.shape == ref.shape and out.dtype == torch.float32
+    for e in range(ref.shape[0]):
+        assert rel(out[e], ref[e]) < TOL[precision], (e, rel(out[e], ref[e]))
+    if precision == "fp32":
+        tokens, n_tok = eec.greedy_decode(out)
+        tokens, n_tok = tokens.cpu(), n_tok.cpu()
+        assert np.array_equal(n_tok.numpy(), g["greedy_counts"])  # bit-exact greedy CTC (north star)
+        flat = [int(t) for e in range(ref.shape[0]) for b in range(ref.shape[1]) for t in tokens[e, b, : int(n_tok[e, b])]]
+        assert np.array_equal(np.array(flat, dtype=np.int64), g["greedy_flat"])
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("name", CASES)
+def test_train_step_vs_reference_golden(name, precision):
+    import eec
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    m, sd, src, lengths = build(name, g, precision)
+    m.train()
+    out = m(src.cuda(), lengths)
+    ref = torch.from_numpy(g["train_logprobs"])
+    for e in range(ref.shape[0]):
+        assert rel(out[e], ref[e]) < TOL[precision]
+    targets, tl = torch.from_numpy(g["targets"]), torch.from_numpy(g["target_lengths"])
+    # (a) the reference's own call shape (train.py:57-63)
+    ctc = eec.CTCLoss(blank=0, zero_infinity=True)
+    in_len = torch.full((out.size(1),), out.size(2), dtype=torch.long)
+    loss = sum(ctc(enc.permute(1, 0, 2), targets, in_len, tl) for enc in out)
+    lt = TOL[precision]
+    assert abs(loss.item() - float(g["loss"])) / float(g["loss"]) < lt
+    m.zero_grad()
+    loss.backward()
+    names = [str(n) for n in g["grad_names"]]
+    P = dict(m.named_parameters())
+    gt = 5e-3 if precision == "fp32" else 6e-2
+    worst = 0.0
+    for n, refn in zip(names, g["grad_norms"]):
+        got = P[n].grad.double().norm().item()
+        err = abs(got - refn) / max(refn, 1e-3 * float(np.max(g["grad_norms"])))
+        worst = max(worst, err)
+        assert err < gt, (n, got, refn)
+    for k in g.files:
+        if k.startswith("grad::"):
+            r = torch.from_numpy(g[k])
+            if float(r.abs().max()) < 1e-4:  # e.g. dw-conv bias under train BN: pure round-off
+                continue
+            assert rel(P[k[6:]].grad, r) < gt, k
+    if precision == "fp32":
+        msd = m.state_dict()
+        bn = "conformer.0.conformer_layers.0.conv_module.sequential.3."
+        assert np.allclose(msd[bn + "running_mean"].cpu().numpy(), g["bn_running_mean"], rtol=1e-3, atol=1e-5)
+        assert np.allclose(msd[bn + "running_var"].cpu().numpy(), g["bn_running_var"], rtol=1e-3, atol=1e-5)
+        assert int(msd[bn + "num_batches_tracked"]) == int(g["bn_num_batches_tracked"])
+    # (b) fused multi-exit CTC: same value in one launch
+    m2, _, _, _ = build(name, g, precision)
+    m2.train()
+    out2 = m2(src.cuda(), lengths)
+    loss2 = eec.multi_exit_ctc_loss(out2, targets, tl)
+    assert abs(loss2.item() - loss.item()) < 1e-4 * abs(loss.item())
+    loss2.backward()
+    P2 = dict(m2.named_parameters())
+    k = "conformer.0.conformer_layers.0.ffn1.sequential.1.weight"
+    assert rel(P2[k].grad, P[k].grad) < 1e-3
+
+
+def test_ctc_known_answers():
+    import eec
+    g = np.load(os.path.join(GOLDEN, "ctc_kat.npz"))
+    lp = torch.from_numpy(g["lp"]).cuda().requires_grad_(True)  # (B,T,V)
+    loss = eec.multi_exit_ctc_loss(lp.unsqueeze(0), torch.from_numpy(g["targets"]), torch.from_numpy(g["target_lengths"]))
+    assert abs(loss.item() - float(g["loss"])) < 1e-5 * abs(float(g["loss"]))
+    loss.backward()
+    ref = torch.from_numpy(g["grad"])
+    assert float((lp.grad.cpu() - ref).abs().max()) < 1e-4 * float(ref.abs().max())
+    assert float(lp.grad[2].abs().max()) == 0.0  # infeasible utterance: zero_infinity
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_ragged_batch_vs_live_oracle(precision):
+    """Bigger ragged batch, 2 exits x 2 layers, checked against the CPU oracle run in this process."""
+    import eec
+    sd = O.make_params(7, n_exits=2, n_layers=2)
+    src, lengths = O.synthetic_batch(6, 419, seed=8, min_frac=0.3)
+    lengths[3] = 3  # length//4 == 0 -> every key masked for this utterance
+    m = eec.Early_conformer(src_pad_idx=0, n_enc_exits=2, enc_voc_size=256, dec_voc_size=256, d_model=256, n_head=8,
+                            max_len=2000, d_feed_forward=2048, n_enc_layers=2, features_length=80, drop_prob=0.1,
+                            depthwise_kernel_size=31, device=torch.device("cuda"))
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda().eval()
+    m.precision = precision
+    with torch.no_grad():
+        out = m(src.cuda(), lengths)
+        ref = O.early_conformer_forward(sd, src, lengths)
+    for e in range(2):
+        assert rel(out[e], ref[e]) < TOL[precision]
+    assert torch.isfinite(out).all()
+    # the reference's precondition
+    with pytest.raises(AssertionError):
+        m(src.cuda(), torch.full_like(lengths, 100))
+
+
+def test_early_exit_matches_oracle_selection():
+    import eec
+    sd = O.make_params(11, n_exits=3, n_layers=1)
+    src, lengths = O.synthetic_batch(5, 331, seed=12, min_frac=0.4)
+    m = eec.Early_conformer(src_pad_idx=0, n_enc_exits=3, enc_voc_size=256, dec_voc_size=256, d_model=256, n_head=8,
+                            max_len=2000, d_feed_forward=2048, n_enc_layers=1, features_length=80, drop_prob=0.0,
+                            depthwise_kernel_size=31, device=torch.device("cuda"))
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda().eval()
+    with torch.no_grad():
+        full = m(src.cuda(), lengths).cpu()
+    T = full.shape[2]
+    key_len = O.encoder_lengths(lengths, T)
+    _, _, Hm = O.early_exit_select(full, key_len, 1e9)
+    thr = float(Hm[0].median())  # some utterances leave at exit 0, others continue
+    ex_ref, tok_ref, _ = O.early_exit_select(full, key_len, thr)
+    exit_index, tokens, n_tokens, mean_ent = m.forward_early_exit(src.cuda(), lengths, thr)
+    assert exit_index.cpu().tolist() == ex_ref.tolist()
+    assert len(set(ex_ref.tolist())) > 1
+    for b in range(5):
+        assert tokens[b, : int(n_tokens[b])].cpu().tolist() == tok_ref[b]
+    # survivors' outputs are unchanged by compaction: entropies agree with the full-batch run
+    for b in range(5):
+        for e in range(int(ex_ref[b]) + 1):
+            assert abs(float(mean_ent[e, b]) - float(Hm[e, b])) < 1e-3
+
+
+def test_state_dict_roundtrip_and_errors():
+    import eec
+    kw = dict(src_pad_idx=0, n_enc_exits=6, enc_voc_size=256, dec_voc_size=256, d_model=256, n_head=8, max_len=2000,
+              d_feed_forward=2048, n_enc_layers=2, features_length=80, drop_prob=0.1, depthwise_kernel_size=31, device="cuda")
+    m = eec.Early_conformer(**kw)
+    assert len(m.state_dict()) == 413
+    assert sum(p.numel() for p in m.parameters()) == 31536128
+    with pytest.raises(ValueError):
+        eec.Early_conformer(**{**kw, "depthwise_kernel_size": 30})
+    with pytest.raises(AssertionError):
+        eec.Early_conformer(**{**kw, "n_head": 6})
+    with pytest.raises(eec.EecError):
+        m(torch.zeros(1, 80, 100), torch.tensor([100]))  # CPU input: no fallback
