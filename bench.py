@@ -1,0 +1,368 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the early-exit conformer hot path on B200.
+
+  python bench.py --gpus N --steps K --warmup W            # our arm (libeec.so kernels)
+  python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port)
+
+Workload (BASELINE.json configs[1]): early_conformer CTC training step -- forward, summed 6-exit CTC
+loss, backward -- bf16, batch 64 x 15 s (T_in=1501 -> T'=374), 12 layers / 6 exits, d_model 256,
+synthetic fbank + random-init weights.  N>1: batch-sharded data parallel, 64 utterances
+per GPU (weak scaling), one NCCL all-reduce of the flat fp32 gradient buffer per step.
+Prints ONE JSON line (rank 0).  A "step" = one pass of the hot path over one batch.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "early-exit-transformer_b200")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch  # noqa: E402
+
+B, T_IN, N_MELS = 64, 1501, 80
+N_EXITS = 6
+FRAME_S = 0.010  # hop 160 @ 16 kHz (util/conf.py:335-341)
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"hbm": p["hbm_gbs"], "tf_burst": p["bf16_tflops"], "tf_sust": p["bf16_tflops_sustained"], "src": "measured"}
+    return {"hbm": 6650.0, "tf_burst": 1590.0, "tf_sust": 1400.0, "src": "fallback"}
+
+
+def t_out(t_in):
+    return ((t_in - 3) // 2 + 1 - 3) // 2 + 1
+
+
+def model_flops_fwd(n_frames, t_enc, layers):
+    per_layer = 2 * 2097152 + 393216 + 131072 + 4 * t_enc * 256 + 262144 + 131072
+    return n_frames * (layers * per_layer + N_EXITS * 131072) + n_frames * 2 * (256 * 768 + 2 * 256 * 240)
+
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc = index, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            text, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            text = ""
+        sm, mx, reasons = [], [], set()
+        for line in text.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_model(layers_per_exit, precision, device):
+    import eec
+    from oracle import conformer_oracle as O  # only for the deterministic synthetic parameters / inputs
+    m = eec.Early_conformer(src_pad_idx=0, n_enc_exits=N_EXITS, enc_voc_size=256, dec_voc_size=256, d_model=256, n_head=8,
+                            max_len=2000, d_feed_forward=2048, n_enc_layers=layers_per_exit, features_length=N_MELS,
+                            drop_prob=0.0, depthwise_kernel_size=31, device=device)
+    sd = O.make_params(0, n_exits=N_EXITS, n_layers=layers_per_exit)
+    m.load_state_dict(sd, strict=True)
+    m = m.to(device)
+    m.precision = precision
+    return m
+
+
+def synthetic(rank):
+    from oracle import conformer_oracle as O
+    src, lengths = O.synthetic_batch(B, T_IN, seed=1234 + rank)
+    targets, tl = O.synthetic_targets(B, seed=4321 + rank)
+    return src, lengths, targets, tl
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    import eec
+    from eec import lib as L
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"WORLD_SIZE={world} != --gpus {args.gpus}")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    eec.load()
+    pk = peaks()
+    layers = args.layers_per_exit
+    model = build_model(layers, args.precision, dev).train()
+    src, lengths, targets, tl = synthetic(rank)
+    src_pin = src.pin_memory()
+    src_dev = src.to(dev)
+    tg_dev, tl_dev = targets.to(dev), tl.to(dev)
+    T = t_out(T_IN)
+
+    def step(x):
+        out = model(x, lengths)
+        loss = eec.multi_exit_ctc_loss(out, tg_dev, tl_dev)
+        model.zero_grad(set_to_none=True)
+        loss.backward()
+        if world > 1:
+            dist.all_reduce(model._flat_grad, op=dist.ReduceOp.AVG)
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        ev0.record()
+        for _ in range(steps):
+            fn()
+        ev1.record()
+        barrier()
+        ms = ev0.elapsed_time(ev1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    for _ in range(max(args.warmup, 3)):
+        step(src_dev)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = L.load().eec_launch_count()
+    if args.profile:
+        torch.cuda.profiler.start()
+    ms = timed(lambda: step(src_dev), args.steps)
+    if args.profile:
+        torch.cuda.profiler.stop()
+    launches = (L.load().eec_launch_count() - launches0) // args.steps
+    clocks = sampler.stop() if rank == 0 else None
+
+    # end to end: pinned host input -> device every step, loss read back every step
+    def e2e_step():
+        x = src_pin.to(dev, non_blocking=True)
+        return float(step(x).item())
+
+    if args.profile:
+        ms_e2e = float("nan")
+    else:
+        e2e_step()
+        ms_e2e = timed(e2e_step, args.steps)
+
+    # inference RTFx per exit (BASELINE metric part (i)): forward truncated after exit e, bf16, eval
+    rtfx = None
+    if rank == 0 and not args.skip_rtfx and not args.profile:
+        audio_s = float(lengths.sum()) * FRAME_S
+        rtfx = rtfx_per_exit(model, src_dev, lengths, audio_s)
+        model.train()
+
+    roof = cpu = None
+    if rank == 0:
+        roof = None if args.profile else roofline_dominant(dev, pk)
+        if world == 1 and not args.skip_cpu and not args.profile:
+            cpu = cpu_baseline(layers, sample_b=args.cpu_sample)
+
+    if rank == 0:
+        per_step = ms / args.steps
+        value = world * B / (per_step / 1e3)
+        flops = 3.0 * model_flops_fwd(B * T, T, N_EXITS * layers)
+        line = {
+            "metric": "train_utts_per_sec", "value": round(value, 2), "unit": "utt/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": round(per_step, 3), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+            "config": {"workload": f"early_conformer CTC training step (fwd + summed 6-exit CTC + bwd), {N_EXITS} exits x {layers} "
+                                   f"layers, d_model 256, batch {B}/GPU x 15 s (T_in {T_IN} -> T' {T}), grad all-reduce "
+                                   f"{'NCCL fp32 flat buffer' if world > 1 else 'n/a'}; optimizer step excluded (SURVEY 8f N1)",
+                       "global_batch": world * B, "parallelism": f"dp{world}",
+                       "l2": "per-step working set ~8 GB >> 126 MB L2 (no flush needed)",
+                       "step_tflops_algorithmic": round(flops / 1e12, 3),
+                       "step_tensor_frac_of_sustained": round(flops / (per_step / 1e3) / 1e12 / pk["tf_sust"], 4),
+                       "peaks": pk["src"]},
+            "e2e": {"value": round(world * B / (ms_e2e / args.steps / 1e3), 2), "unit": "utt/s",
+                    "h2d_bytes_per_step": src_pin.numel() * 4, "d2h_bytes_per_step": 4},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+        }
+        if rtfx is not None:
+            line["rtfx_per_exit"] = rtfx
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def rtfx_per_exit(model, src_dev, lengths, audio_s):
+    """Inference RTFx for a forward truncated after exit e (e = 1..6): time the full forward's prefix."""
+    from eec import engine
+    model.eval()
+    res = []
+    P, W = model._tensor_dict(), model._operands
+    full = model._cfg()
+    with torch.no_grad():
+        for e in range(1, N_EXITS + 1):
+            cfg = engine.Config(n_exits=e, n_layers=full.n_layers, n_mels=full.n_mels, precision=full.precision)
+            for _ in range(2):
+                engine.model_forward(P, W, cfg, src_dev, lengths, False, False)
+            torch.cuda.synchronize()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
+            for _ in range(5):
+                engine.model_forward(P, W, cfg, src_dev, lengths, False, False)
+            ev1.record()
+            torch.cuda.synchronize()
+            ms = ev0.elapsed_time(ev1) / 5
+            res.append({"exit": e, "ms": round(ms, 3), "rtfx": round(audio_s / (ms / 1e3), 1)})
+    return res
+
+
+def roofline_dominant(dev, pk):
+    """Dominant kernel = the FFN up-projection GEMM (M=23936, N=2048, K=256, bias+SiLU epilogue; 24 launches per
+    forward, ~37% of model FLOPs together with its twin).  Timed alone with CUDA events, L2 flushed between launches."""
+    from eec import ops
+    M, N, K = B * t_out(T_IN), 2048, 256
+    a = torch.randn(M, K, device=dev).to(torch.bfloat16)
+    w = (torch.randn(N, K, device=dev) * 0.05).to(torch.bfloat16)
+    bias = torch.zeros(N, device=dev)
+    out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    for _ in range(3):
+        ops.gemm(a, w, out, M, N, K, bias=bias, act=ops.ACT_SILU)
+    total, n = 0.0, 10
+    for _ in range(n):
+        flush.zero_()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        ops.gemm(a, w, out, M, N, K, bias=bias, act=ops.ACT_SILU)
+        ev1.record()
+        torch.cuda.synchronize()
+        total += ev0.elapsed_time(ev1)
+    ms = total / n
+    fl = 2.0 * M * N * K
+    ach = fl / (ms / 1e3) / 1e12
+    return {"kernel": "gemm_tc_kernel<K-major,K-major,EPI_GENERIC> FFN up-proj 23936x2048x256 +bias+SiLU", "bound": "tensor",
+            "achieved": round(ach, 2), "peak": pk["tf_burst"], "unit": "TFLOP/s", "frac": round(ach / pk["tf_burst"], 4),
+            "traffic": None, "ms_per_launch": round(ms, 4), "peak_source": pk["src"] + " burst (kernel timed alone)",
+            "algorithmic_flops_per_launch": fl, "algorithmic_bytes_per_launch": 2 * (M * K + N * K + M * N)}
+
+
+def cpu_step(sd, src, lengths, targets, tl):
+    from oracle import conformer_oracle as O
+    sdg = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k and k != "positional_encoder.pe" else v)
+           for k, v in sd.items()}
+    out = O.early_conformer_forward(sdg, src, lengths, training=True, bn_out={})
+    Tn = out.shape[2]
+    in_len = torch.full((out.shape[1],), Tn, dtype=torch.long)
+    loss = sum(torch.nn.functional.ctc_loss(out[e].permute(1, 0, 2), targets, in_len, tl, blank=0, zero_infinity=True)
+               for e in range(out.shape[0]))
+    loss.backward()
+    return float(loss.detach())
+
+
+def cpu_baseline(layers, sample_b=8, steps=1):
+    """The reference's CPU path (oracle port: same arithmetic, torch CPU ops, all host threads) on a bounded sample."""
+    from oracle import conformer_oracle as O
+    cores = len(os.sched_getaffinity(0))
+    torch.set_num_threads(cores)
+    sd = O.make_params(0, n_exits=N_EXITS, n_layers=layers)
+    src, lengths = O.synthetic_batch(sample_b, T_IN, seed=1234)
+    targets, tl = O.synthetic_targets(sample_b, seed=4321)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu_step(sd, src, lengths, targets, tl)
+    dt = (time.perf_counter() - t0) / steps
+    return {"value": round(sample_b / dt, 3), "unit": "utt/s", "cores": cores, "kind": "port",
+            "sample": f"{steps} training step(s) (fwd + 6-exit CTC + bwd, fp32) on {sample_b} of the 64 utterances, same T_in={T_IN}, "
+                      f"{N_EXITS}x{layers} layers; {dt:.1f} s per step"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import conformer_oracle as O
+    cores = len(os.sched_getaffinity(0))
+    torch.set_num_threads(cores)
+    layers = args.layers_per_exit
+    sb = args.cpu_sample
+    sd = O.make_params(0, n_exits=N_EXITS, n_layers=layers)
+    src, lengths = O.synthetic_batch(sb, T_IN, seed=1234)
+    targets, tl = O.synthetic_targets(sb, seed=4321)
+    for _ in range(min(args.warmup, 1)):
+        cpu_step(sd, src, lengths, targets, tl)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_step(sd, src, lengths, targets, tl)
+    dt = (time.perf_counter() - t0) / args.steps
+    value = sb / dt
+    T = t_out(T_IN)
+    line = {
+        "impl": "reference", "metric": "train_utts_per_sec", "value": round(value, 3), "unit": "utt/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": round(dt * 1e3, 1), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"early_conformer CTC training step (fwd + summed 6-exit CTC + bwd), {N_EXITS} exits x {layers} layers, "
+                               f"d_model 256, T_in {T_IN} -> T' {T}; CPU reference path, bounded sample of {sb} utterances per step",
+                   "global_batch": sb, "parallelism": "cpu"},
+        "cpu_baseline": {"value": round(value, 3), "unit": "utt/s", "cores": cores, "kind": "port",
+                         "sample": f"{args.steps} steps x {sb} utterances (of the 64-utterance batch), {dt:.1f} s per step"},
+        "e2e": {"value": round(value, 3), "unit": "utt/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--layers-per-exit", type=int, default=2, help="2 = BASELINE configs[1]; 3 = configs[2] (18 layers)")
+    ap.add_argument("--cpu-sample", type=int, default=64, help="utterances per CPU-baseline step (64 = the full batch)")
+    ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-rtfx", action="store_true")
+    ap.add_argument("--profile", action="store_true", help="bracket the timed region with cudaProfilerStart/Stop (for ncu "
+                    "--profile-from-start off) and skip the e2e / rtfx / roofline / cpu legs")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

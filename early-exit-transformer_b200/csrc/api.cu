@@ -1,4 +1,5 @@
 // api.cu -- C-ABI glue: error state, device check, GEMM backend dispatch.
+#include <atomic>
 #include <stdarg.h>
 #include <stdlib.h>
 #include <string.h>
@@ -8,6 +9,8 @@
 namespace eec {
 
 static thread_local char g_err[1024] = "";
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -47,6 +50,7 @@ using namespace eec;
 
 extern "C" const char* eec_last_error(void) { return g_err; }
 extern "C" int eec_version(void) { return 100; }
+extern "C" long long eec_launch_count(void) { return g_launches.load(); }
 
 extern "C" int eec_device_ok(void) {
   int dev = 0;

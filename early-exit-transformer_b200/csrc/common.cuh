@@ -29,7 +29,12 @@ void set_error(const char* fmt, ...);
     }                                                                                     \
   } while (0)
 
-#define EEC_LAUNCH_CHECK() EEC_CUDA(cudaGetLastError())
+void count_launch();
+#define EEC_LAUNCH_CHECK()         \
+  do {                             \
+    eec::count_launch();           \
+    EEC_CUDA(cudaGetLastError());  \
+  } while (0)
 
 static inline cudaStream_t S(eec_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 

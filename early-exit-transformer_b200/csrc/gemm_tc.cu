@@ -50,10 +50,10 @@ static int load_encode() {
 }
 
 static int get_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides,
-                    const uint32_t* box) {
-  struct Key { const void* b; int r; uint64_t d[3]; uint64_t s[2]; uint32_t x[3]; } k;
+                    const uint32_t* box, int swizzle) {
+  struct Key { const void* b; int r; int sw; uint64_t d[3]; uint64_t s[2]; uint32_t x[3]; } k;
   memset(&k, 0, sizeof(k));
-  k.b = base; k.r = rank;
+  k.b = base; k.r = rank; k.sw = swizzle;
   for (int i = 0; i < rank; ++i) { k.d[i] = dims[i]; k.x[i] = box[i]; }
   for (int i = 0; i + 1 < rank; ++i) k.s[i] = strides[i];
   std::string key(reinterpret_cast<const char*>(&k), sizeof(k));
@@ -69,7 +69,7 @@ static int get_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t
   for (int i = 0; i + 1 < rank; ++i) gs[i] = strides[i];
   alignas(64) CUtensorMap m;
   CUresult r = g_encode(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, (CUtensorMapSwizzle)swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (%d): rank %d dims %llu,%llu,%llu stride %llu box %u,%u", (int)r, rank,
@@ -85,16 +85,16 @@ static int get_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t
 }
 
 int get_tmap_2d(CUtensorMap* out, const void* base, uint64_t dim0, uint64_t dim1, uint64_t stride1_bytes, uint32_t box0,
-                uint32_t box1) {
+                uint32_t box1, int swizzle) {
   uint64_t d[2] = {dim0, dim1}, s[1] = {stride1_bytes};
   uint32_t b[2] = {box0, box1};
-  return get_tmap(out, base, 2, d, s, b);
+  return get_tmap(out, base, 2, d, s, b, swizzle);
 }
 int get_tmap_3d(CUtensorMap* out, const void* base, uint64_t dim0, uint64_t dim1, uint64_t dim2, uint64_t stride1_bytes,
                 uint64_t stride2_bytes, uint32_t box0, uint32_t box1, uint32_t box2) {
   uint64_t d[3] = {dim0, dim1, dim2}, s[2] = {stride1_bytes, stride2_bytes};
   uint32_t b[3] = {box0, box1, box2};
-  return get_tmap(out, base, 3, d, s, b);
+  return get_tmap(out, base, 3, d, s, b, 3);
 }
 
 // ------------------------------------------------------------------ kernel

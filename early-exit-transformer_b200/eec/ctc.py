@@ -23,7 +23,7 @@ class _CtcFn(torch.autograd.Function):
         tl = target_lengths.to(device=dev, dtype=torch.int64, non_blocking=True).contiguous()
         nll = torch.empty(E, B, dtype=torch.float32, device=dev)
         loss = torch.zeros(E, dtype=torch.float32, device=dev)
-        need_grad = lp_ebtv.requires_grad and torch.is_grad_enabled()
+        need_grad = ctx.needs_input_grad[0]
         grad = torch.empty_like(lp_ebtv) if need_grad else None
         ops.ctc_fwd_bwd(lp_ebtv, tg, tl, nll, loss, grad, 1.0, blank)
         ctx.grad = grad

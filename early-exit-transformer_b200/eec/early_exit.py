@@ -111,9 +111,8 @@ class Conformer(nn.Module):
 # ------------------------------------------------------------------ autograd bridge
 class _EncoderFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, module, src, lengths, *params):
+    def forward(ctx, module, want_tape, src, lengths, *params):
         P = module._tensor_dict()
-        want_tape = module.training and torch.is_grad_enabled() and any(p.requires_grad for p in params)
         out, tape = engine.model_forward(P, module._operands, module._cfg(), src, lengths, module.training, want_tape)
         ctx.module, ctx.tape, ctx.P = module, tape, P
         return out
@@ -127,7 +126,8 @@ class _EncoderFn(torch.autograd.Function):
         names = m._param_names
         G = engine.model_backward(ctx.P, m._operands, m._cfg(), ctx.tape, gout, names)
         ctx.tape = None
-        return (None, None, None) + tuple(G[n] for n in names)
+        m.__dict__["_flat_grad"] = G["__flat__"]  # p.grad tensors are views of this buffer (DP all-reduces it once)
+        return (None, None, None, None) + tuple(G[n] for n in names)
 
 
 class _EarlyExitBase(nn.Module):
@@ -201,7 +201,8 @@ class _EarlyExitBase(nn.Module):
     def forward(self, src: Tensor, lengths: Tensor) -> Tensor:
         self._check_supported()
         params = [p for _, p in self.named_parameters()]
-        return _EncoderFn.apply(self, src, lengths, *params)
+        want_tape = self.training and torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        return _EncoderFn.apply(self, want_tape, src, lengths, *params)
 
     # ---- north-star extension (not in the reference) -------------------------
     @torch.no_grad()

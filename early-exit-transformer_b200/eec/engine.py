@@ -418,7 +418,15 @@ def model_backward(P, W: Operands, cfg: Config, tape: Tape, gout: Tensor, names:
     B, T = tape.B, tape.T
     N = B * T
     E = cfg.n_exits
-    G = {n: torch.zeros_like(P[n], dtype=f32) for n in names}
+    # all parameter gradients live in ONE flat fp32 buffer (one memset; one NCCL all-reduce under DP)
+    total = sum(P[n].numel() for n in names)
+    flat = torch.zeros(total, dtype=f32, device=dev)
+    G, off = {}, 0
+    for n in names:
+        k = P[n].numel()
+        G[n] = flat[off:off + k].view(P[n].shape)
+        off += k
+    G["__flat__"] = flat
     dX: Optional[Tensor] = None
     li = len(tape.layers)
     for e in reversed(range(E)):

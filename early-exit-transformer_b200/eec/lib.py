@@ -72,7 +72,7 @@ _SIGS = {
     "eec_repeat2_bwd": [vp, vp, i32, i32, i32, vp],
     "eec_stride2_scatter_add": [vp, vp, i32, i32, i32, vp],
 }
-EXPORTS = sorted(list(_SIGS) + ["eec_last_error", "eec_version", "eec_device_ok", "eec_ctc_workspace_bytes"])
+EXPORTS = sorted(list(_SIGS) + ["eec_last_error", "eec_version", "eec_device_ok", "eec_ctc_workspace_bytes", "eec_launch_count"])
 
 _lib = None
 
@@ -100,6 +100,8 @@ def load():
     lib.eec_last_error.argtypes = []
     lib.eec_version.restype = i32
     lib.eec_device_ok.restype = i32
+    lib.eec_launch_count.restype = C.c_longlong
+    lib.eec_launch_count.argtypes = []
     lib.eec_ctc_workspace_bytes.restype = i64
     lib.eec_ctc_workspace_bytes.argtypes = [i32, i32, i32, i32]
     _lib = lib

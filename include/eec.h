@@ -41,6 +41,8 @@ const char* eec_last_error(void);
 int eec_version(void);
 /* 1 when the current device is compute capability 10.x (the only supported target) */
 int eec_device_ok(void);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+long long eec_launch_count(void);
 
 /* ---- GEMM with fused epilogue -------------------------------------------------------
  * C[M,N] = epi( sum_k A(m,k) * B(n,k) ),  replaces torch F.linear / 1x1 Conv1d / cuBLAS calls

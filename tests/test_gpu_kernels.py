@@ -32,7 +32,7 @@ def ref_gemm(A, B, a_k, b_k):
     A, B = A.double(), B.double()
     Am = A if a_k else A.t()
     Bm = B if b_k else B.t()
-    return Am @ Bm.t()
+    return (Am @ Bm.t()).cpu()
 
 
 MAJORS = [(True, True), (True, False), (False, False), (False, True)]
@@ -282,7 +282,7 @@ def test_frontend_pieces(ops):
     ops.col2im_k3s2(dcols, 3 * D, dx, B, D, T1, T2)
     lhs = (cols2.double() * dcols.double()).sum()
     rhs = (x1.double() * dx.double()).sum()
-    assert abs(float(lhs - rhs)) < 1e-8 * abs(float(lhs)) + 1e-6
+    assert abs(float(lhs - rhs)) < 1e-6 * abs(float(lhs)) + 1e-6
     kl = torch.empty(4, dtype=torch.int32, device="cuda")
     ops.encoder_lengths(torch.tensor([1500, 1499, 1000, 7], device="cuda"), kl, 374, 4, 0)
     assert kl.tolist() == [374, 374, 250, 1]

@@ -186,4 +186,6 @@ def test_state_dict_roundtrip_and_errors():
     with pytest.raises(AssertionError):
         eec.Early_conformer(**{**kw, "n_head": 6})
     with pytest.raises(eec.EecError):
-        m(torch.zeros(1, 80, 100), torch.tensor([100]))  # CPU input: no fallback
+        m.eval()(torch.zeros(1, 80, 100), torch.tensor([100]))  # CPU input: no fallback
+    with pytest.raises(NotImplementedError):
+        m.train()(torch.zeros(1, 80, 100, device="cuda"), torch.tensor([100]))  # dropout > 0 in training: explicit
