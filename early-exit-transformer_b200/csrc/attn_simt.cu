@@ -247,10 +247,10 @@ __global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(const T* __restrict__
 
 using namespace eec;
 
-// the tcgen05 attention kernel is opt-in (EEC_ATTN_TC=1) until it has passed GPU parity
+// EEC_ATTN_TC=0 routes bf16 attention to the CUDA-core kernels (debug cross-check); default = tcgen05
 static bool attn_tc_ready() {
   static int v = -1;
-  if (v < 0) { const char* e = getenv("EEC_ATTN_TC"); v = (e && e[0] == '1') ? 1 : 0; }
+  if (v < 0) { const char* e = getenv("EEC_ATTN_TC"); v = (e && e[0] == '0') ? 0 : 1; }
   return v == 1;
 }
 static bool force_simt() {

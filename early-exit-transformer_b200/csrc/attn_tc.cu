@@ -1,9 +1,213 @@
-// attn_tc.cu -- tcgen05 self-attention forward (placeholder until the TMEM kernel lands: routes to
-// the CUDA-core kernel, which is our own kernel, not a library fallback).
-#include "common.cuh"
+// attn_tc.cu -- self-attention forward on the tcgen05 tensor cores (bf16 in, fp32 softmax).
+//
+// One CTA per (128-query tile, head, utterance).  For every 128-key block:
+//   S = Q K^T            tcgen05.mma  M=128 N=128 K=32   (Q,K: K-major, 64B-swizzled TMA tiles)  -> TMEM cols [0,128)
+//   softmax warps (one thread per query row) read S with tcgen05.ld, apply the key-length mask,
+//   keep a running max / sum (exp2 domain), write P (bf16) into 128B-swizzled shared memory
+//   O_blk = P V          tcgen05.mma  M=128 N=32  K=128  (P: K-major smem; V: MN-major TMA tile)  -> TMEM cols [128,160)
+//   the softmax threads fold O_blk into their fp32 register accumulator with the online-softmax rescale.
+// Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer + TMEM allocator, warps 2..5 = softmax/epilogue.
+// Fully masked utterances (key_len == 0) produce zeros, like torch's CPU SDPA.
+// Padded QUERY rows are computed like any other row; only keys are masked.
+#include "tc_common.cuh"
+
 namespace eec {
-int attn_fwd_tc(const void* qkv, const int32_t* key_len, void* ctx, float* lse, int B, int T, int H, int dh, cudaStream_t st) {
-  set_error("attn_fwd_tc: not built");
-  return 9;
+namespace {
+using namespace tc;
+
+constexpr int QT = 128;            // queries per CTA
+constexpr int KB = 128;            // keys per block
+constexpr int DHEAD = 32;
+constexpr int KV_STAGES = 2;
+constexpr int Q_BYTES = QT * DHEAD * 2;       // 8 KB
+constexpr int K_BYTES = KB * DHEAD * 2;       // 8 KB
+constexpr int V_BYTES = KB * DHEAD * 2;       // 8 KB
+constexpr int P_BYTES = QT * KB * 2;          // 32 KB (two 64-key swizzle atoms of 16 KB)
+constexpr int AT_SMEM = Q_BYTES + KV_STAGES * (K_BYTES + V_BYTES) + P_BYTES + 1024 + 256;
+constexpr int AT_THREADS = 192;
+constexpr uint32_t TMEM_COLS = 256;
+constexpr uint32_t S_COL = 0, O_COL = 128;
+constexpr uint32_t SW64 = 4, SW128 = 2;
+
+__global__ void __launch_bounds__(AT_THREADS) attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv,
+                                                                 const int32_t* __restrict__ key_len,
+                                                                 __nv_bfloat16* __restrict__ ctx, float* __restrict__ lse,
+                                                                 int T, int H) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + Q_BYTES;                       // [stage]
+  uint8_t* sV = sK + KV_STAGES * K_BYTES;           // [stage]
+  uint8_t* sP = sV + KV_STAGES * V_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + P_BYTES);
+  uint64_t* q_full = bars;
+  uint64_t* kv_full = bars + 1;                     // [2]
+  uint64_t* kv_empty = bars + 3;                    // [2]
+  uint64_t* s_full = bars + 5;
+  uint64_t* s_free = bars + 6;
+  uint64_t* p_full = bars + 7;
+  uint64_t* o_full = bars + 8;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 9);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * QT;
+  const int klen = min(key_len[b], T);
+  const int nblk = (klen + KB - 1) / KB;
+  const int D = H * DHEAD;
+  const int row0 = b * T;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tm_qkv);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < KV_STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+    mbar_init(s_full, 1);
+    mbar_init(s_free, 128);
+    mbar_init(p_full, 128);
+    mbar_init(o_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_ptr_smem, TMEM_COLS); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    if (lane == 0 && nblk > 0) {
+      mbar_expect_tx(q_full, Q_BYTES);
+      tma_load_2d(sQ, &tm_qkv, q_full, h * DHEAD, row0 + q0);
+      for (int j = 0; j < nblk; ++j) {
+        const int s = j % KV_STAGES;
+        mbar_wait(&kv_empty[s], ((j / KV_STAGES) & 1) ^ 1);
+        mbar_expect_tx(&kv_full[s], K_BYTES + V_BYTES);
+        tma_load_2d(sK + s * K_BYTES, &tm_qkv, &kv_full[s], D + h * DHEAD, row0 + j * KB);
+        tma_load_2d(sV + s * V_BYTES, &tm_qkv, &kv_full[s], 2 * D + h * DHEAD, row0 + j * KB);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && nblk > 0) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(QT, KB, false, false);
+      constexpr uint32_t idesc_o = make_idesc_bf16(QT, DHEAD, false, true);
+      mbar_wait(q_full, 0);
+      for (int j = 0; j < nblk; ++j) {
+        const int s = j % KV_STAGES;
+        mbar_wait(&kv_full[s], (j / KV_STAGES) & 1);
+        if (j > 0) mbar_wait(s_free, (j - 1) & 1);   // softmax threads have drained S of block j-1
+        tc_fence_after();
+        const uint32_t aq = smem_u32(sQ), bk = smem_u32(sK + s * K_BYTES), bv = smem_u32(sV + s * V_BYTES);
+#pragma unroll
+        for (int k = 0; k < DHEAD / 16; ++k)
+          umma_bf16(tmem_base + S_COL, make_smem_desc(aq + k * 32, 0, 512, SW64), make_smem_desc(bk + k * 32, 0, 512, SW64),
+                    idesc_s, k > 0 ? 1u : 0u);
+        umma_commit(s_full);
+        mbar_wait(p_full, j & 1);                    // P_j is in smem (and O_{j-1} has been consumed)
+        tc_fence_after();
+        const uint32_t ap = smem_u32(sP);
+#pragma unroll
+        for (int k = 0; k < KB / 16; ++k)
+          umma_bf16(tmem_base + O_COL, make_smem_desc(ap + (k >> 2) * 16384 + (k & 3) * 32, 0, 1024, SW128),
+                    make_smem_desc(bv + k * 1024, 0, 512, SW64), idesc_o, k > 0 ? 1u : 0u);
+        umma_commit(o_full);
+        umma_commit(&kv_empty[s]);
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- softmax + epilogue: one thread per query row
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+    const float sc = rsqrtf((float)DHEAD) * 1.4426950408889634f;  // 1/sqrt(dh) * log2(e)
+    float m_run = -INFINITY, l_run = 0.f;
+    float o[DHEAD];
+#pragma unroll
+    for (int i = 0; i < DHEAD; ++i) o[i] = 0.f;
+    float v[32];
+    for (int j = 0; j < nblk; ++j) {
+      const int kbase = j * KB;
+      mbar_wait(s_full, j & 1);
+      tc_fence_after();
+      // pass 1: row max over the valid keys of this block
+      float mx = m_run;
+#pragma unroll
+      for (int c0 = 0; c0 < KB; c0 += 32) {
+        tmem_ld32(trow + S_COL + c0, v);
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (kbase + c0 + i < klen) mx = fmaxf(mx, v[i] * sc);
+      }
+      // pass 2: p = exp2(s - mx), row sum, bf16 P tile in swizzled smem
+      float psum = 0.f;
+#pragma unroll
+      for (int c0 = 0; c0 < KB; c0 += 32) {
+        tmem_ld32(trow + S_COL + c0, v);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float p = (kbase + c0 + i < klen) ? exp2f(v[i] * sc - mx) : 0.f;
+          psum += p;
+          v[i] = p;
+        }
+        uint8_t* prow = sP + (c0 >> 6) * 16384 + r * 128;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {  // 4 chunks of 8 keys (16 B) in this 32-key span
+          const int chunk = ((c0 & 63) >> 3) + g;
+          uint4 u;
+          __nv_bfloat162* hh = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) hh[e] = __floats2bfloat162_rn(v[g * 8 + 2 * e], v[g * 8 + 2 * e + 1]);
+          *reinterpret_cast<uint4*>(prow + ((chunk ^ (r & 7)) << 4)) = u;
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(s_free);
+      fence_proxy_async();
+      mbar_arrive(p_full);
+      const float corr = (m_run == -INFINITY) ? 0.f : exp2f(m_run - mx);
+      l_run = l_run * corr + psum;
+      m_run = mx;
+      mbar_wait(o_full, j & 1);
+      tc_fence_after();
+      tmem_ld32(trow + O_COL, v);
+#pragma unroll
+      for (int i = 0; i < DHEAD; ++i) o[i] = fmaf(o[i], corr, v[i]);
+    }
+    const int t = q0 + r;
+    if (t < T) {
+      const float inv = (l_run > 0.f) ? 1.0f / l_run : 0.f;
+      __nv_bfloat16* dst = ctx + ((long)(row0 + t)) * D + h * DHEAD;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        float tt[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) tt[e] = o[g * 8 + e] * inv;
+        st8<__nv_bfloat16>(dst + g * 8, tt);
+      }
+      if (lse) lse[((long)b * H + h) * T + t] = (l_run > 0.f) ? (m_run + log2f(l_run)) * 0.6931471805599453f : -INFINITY;
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
 }
+
+}  // namespace
+
+int attn_fwd_tc(const void* qkv, const int32_t* key_len, void* ctx, float* lse, int B, int T, int H, int dh, cudaStream_t st) {
+  EEC_CHECK_ARG(dh == DHEAD, "attn_fwd_tc: head dim must be 32");
+  CUtensorMap tm;
+  const int D3 = 3 * H * dh;
+  if (int r = get_tmap_2d(&tm, qkv, (uint64_t)D3, (uint64_t)B * T, (uint64_t)D3 * 2, DHEAD, 128, /*SWIZZLE_64B*/ 2)) return r;
+  static bool attr_set = false;
+  if (!attr_set) {
+    EEC_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
+    attr_set = true;
+  }
+  dim3 grid(cdiv(T, QT), H, B);
+  attn_fwd_tc_kernel<<<grid, AT_THREADS, AT_SMEM, st>>>(tm, key_len, (__nv_bfloat16*)ctx, lse, T, H);
+  EEC_LAUNCH_CHECK();
+  return 0;
+}
+
 }  // namespace eec

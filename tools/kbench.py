@@ -1,0 +1,91 @@
+"""Per-kernel micro-benchmarks at BASELINE shapes (CUDA events, L2 flushed between launches).
+Usage: python tools/kbench.py [attn] [gemm] [ffn] [conv] [ctc] ...   -> prints one line per kernel."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "early-exit-transformer_b200"))
+import torch
+import eec
+from eec import ops
+
+dev = torch.device("cuda")
+B, T, H, D, F = 64, 374, 8, 256, 2048
+N = B * T
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+
+def timeit(fn, n=10, warm=3):
+    for _ in range(warm):
+        fn()
+    tot = 0.0
+    for _ in range(n):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+        tot += e0.elapsed_time(e1)
+    return tot / n
+
+
+def report(name, ms, flops=None, bytes_=None):
+    s = f"{name:58s} {ms*1e3:9.1f} us"
+    if flops: s += f"  {flops/ms/1e9:8.1f} TFLOP/s"
+    if bytes_: s += f"  {bytes_/ms/1e6:8.1f} GB/s"
+    print(s, flush=True)
+
+
+def bf(*shape, scale=1.0):
+    return (torch.randn(*shape, device=dev) * scale).to(torch.bfloat16)
+
+
+which = set(sys.argv[1:]) or {"attn", "gemm", "conv", "ctc", "ln"}
+
+if "attn" in which:
+    qkv = bf(N, 768)
+    kl = torch.full((B,), T, dtype=torch.int32, device=dev)
+    ctx = torch.empty(N, D, device=dev, dtype=torch.bfloat16)
+    lse = torch.empty(B, H, T, device=dev)
+    fl = 4.0 * B * H * T * T * 32
+    report("attn_fwd (EEC_ATTN_TC=%s)" % os.environ.get("EEC_ATTN_TC", "0"), timeit(lambda: ops.attn_fwd(qkv, kl, ctx, lse, B, T, H)), fl)
+    dctx = bf(N, D); dqkv = torch.empty_like(qkv); dvec = torch.empty(B * H * T, device=dev)
+    report("attn_bwd", timeit(lambda: ops.attn_bwd(qkv, ctx, dctx, lse, kl, dqkv, dvec, B, T, H), n=3, warm=1), 2.5 * fl)
+
+if "gemm" in which:
+    a256, a2048, a768, a512 = bf(N, 256), bf(N, 2048), bf(N, 768), bf(N, 512)
+    w = {k: bf(*k, scale=0.05) for k in [(2048, 256), (256, 2048), (768, 256), (256, 256), (512, 256)]}
+    bias = {n: torch.zeros(n, device=dev) for n in (256, 512, 768, 2048)}
+    o2048 = torch.empty(N, 2048, device=dev, dtype=torch.bfloat16); pre2048 = torch.empty_like(o2048)
+    o768 = torch.empty(N, 768, device=dev, dtype=torch.bfloat16)
+    o256 = torch.empty(N, 256, device=dev, dtype=torch.bfloat16)
+    x32 = torch.randn(N, 256, device=dev); xo = torch.empty_like(x32); u = torch.empty(N, 256, device=dev, dtype=torch.bfloat16)
+    g = 1 + 0.1 * torch.randn(256, device=dev); b_ = torch.zeros(256, device=dev)
+    report("gemm ffn1 256->2048 +bias+SiLU (bf16 out)", timeit(lambda: ops.gemm(a256, w[(2048, 256)], o2048, N, 2048, 256, bias=bias[2048], act=ops.ACT_SILU)), 2.0 * N * 2048 * 256)
+    report("gemm ffn1 256->2048 +bias+SiLU +preact", timeit(lambda: ops.gemm(a256, w[(2048, 256)], o2048, N, 2048, 256, bias=bias[2048], act=ops.ACT_SILU, preact=pre2048)), 2.0 * N * 2048 * 256)
+    report("gemm ffn2 2048->256 +res+LN tail", timeit(lambda: ops.gemm(a2048, w[(256, 2048)], xo, N, 256, 2048, bias=bias[256], alpha=0.5, residual=x32, ln_gamma=g, ln_beta=b_, ln_out=u)), 2.0 * N * 2048 * 256)
+    report("gemm qkv 256->768 +bias", timeit(lambda: ops.gemm(a256, w[(768, 256)], o768, N, 768, 256, bias=bias[768])), 2.0 * N * 768 * 256)
+    report("gemm out-proj 256->256 +res+LN", timeit(lambda: ops.gemm(a256, w[(256, 256)], xo, N, 256, 256, bias=bias[256], residual=x32, ln_gamma=g, ln_beta=b_, ln_out=u)), 2.0 * N * 256 * 256)
+    report("gemm pw1 256->512 GLU", timeit(lambda: ops.gemm(a256, w[(512, 256)], o256, N, 512, 256, bias=bias[512], act=ops.ACT_GLU)), 2.0 * N * 512 * 256)
+    dW = torch.zeros(2048, 256, device=dev)
+    report("wgrad [N,2048]^T[N,256] split-K accumulate", timeit(lambda: ops.gemm(a2048, a256, dW, 2048, 256, N, a_kmajor=False, b_kmajor=False, lda=2048, ldb=256, accumulate=True)), 2.0 * N * 2048 * 256)
+    dh = torch.empty(N, 2048, device=dev, dtype=torch.bfloat16)
+    report("dgrad [N,256]x[256,2048] +dSiLU", timeit(lambda: ops.gemm(a256, w[(256, 2048)], dh, N, 2048, 256, a_kmajor=True, b_kmajor=False, lda=256, ldb=2048, act=ops.ACT_DSILU, preact=pre2048, alpha=0.5)), 2.0 * N * 2048 * 256)
+    du = torch.empty(N, 256, device=dev)
+    report("dgrad [N,2048]x[2048,256] fp32 out", timeit(lambda: ops.gemm(a2048, w[(2048, 256)], du, N, 256, 2048, a_kmajor=True, b_kmajor=False, lda=2048, ldb=256)), 2.0 * N * 2048 * 256)
+
+if "conv" in which:
+    gg = bf(B, T, 256); wdw = torch.randn(256, 31, device=dev) * 0.1; z = torch.zeros(256, device=dev); one = torch.ones(256, device=dev)
+    out = torch.empty(B, T, 256, device=dev, dtype=torch.bfloat16)
+    report("dwconv+BN+SiLU eval (bf16)", timeit(lambda: ops.dwconv_bn_silu_eval(gg, wdw, z, one, z, z, one, out, B, T, 31)), None, N * 256 * 4)
+    c = torch.empty(N, 256, device=dev); sums = torch.zeros(512, dtype=torch.float64, device=dev)
+    report("dwconv + stats (train pass A)", timeit(lambda: ops.dwconv_stats(gg, wdw, z, c, sums, B, T, 31)), None, N * 256 * 6)
+
+if "ln" in which:
+    x = torch.randn(N, 256, device=dev); g = torch.ones(256, device=dev); b_ = torch.zeros(256, device=dev)
+    o = torch.empty(N, 256, device=dev, dtype=torch.bfloat16)
+    report("layernorm fwd fp32->bf16", timeit(lambda: ops.layernorm_fwd(x, g, b_, o)), None, N * 256 * 6)
+
+if "ctc" in which:
+    from oracle import conformer_oracle as O
+    lp = torch.log_softmax(torch.randn(6, B, T, 256, device=dev), -1)
+    tg, tl = O.synthetic_targets(B)
+    tg, tl = tg.to(dev), tl.to(dev)
+    nll = torch.empty(6, B, device=dev); loss = torch.zeros(6, device=dev); grad = torch.empty_like(lp)
+    report("ctc fwd+bwd 6 exits x 64 utts", timeit(lambda: ops.ctc_fwd_bwd(lp, tg, tl, nll, loss, grad), n=5), None, lp.numel() * 8)
