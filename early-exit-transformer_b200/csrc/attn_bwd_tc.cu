@@ -1,0 +1,284 @@
+// attn_bwd_tc.cu -- self-attention backward on the tcgen05 tensor cores (bf16 operands, fp32 math).
+//
+// One CTA per (128-key block j, head, utterance); it keeps K_j, V_j resident and walks the query blocks i:
+//   S  = Q_i K_j^T          (M=128 q, N=128 k, K=32)        -> TMEM [0,128)
+//   dP = dO_i V_j^T         (M=128 q, N=128 k, K=32)        -> TMEM [128,256)
+//   row threads: P = exp2(S*c - lse_i), dS = P (dP - D_i)   -> bf16 P / dS tiles in 128B-swizzled smem
+//   dV_j += P^T  dO_i       (M=128 k, N=32, K=128 q; A = P  read MN-major, B = dO_i MN-major) -> TMEM [256,288)
+//   dK_j += dS^T Q_i        (M=128 k, N=32, K=128 q; A = dS read MN-major, B = Q_i  MN-major) -> TMEM [288,320)
+//   dQ_i  = dS  K_j         (M=128 q, N=32, K=128 k; A = dS K-major,       B = K_j  MN-major) -> TMEM [320,352)
+// dQ partials of the key blocks are summed with fp32 vector atomics into a workspace and converted
+// (with the 1/sqrt(dh) scale) by a small tail kernel; dK/dV are written directly by the owning CTA.
+// The same smem P/dS tile is consumed both K-major (dQ) and MN-major (dV, dK): no transposes.
+// D_i = dO_i . O_i comes from a tiny pre-pass.  Reference: autograd of nn.MultiheadAttention (TA:194-200).
+#include "tc_common.cuh"
+
+namespace eec {
+namespace {
+using namespace tc;
+
+constexpr int BT = 128;       // block of queries / keys
+constexpr int DHD = 32;
+constexpr int TILE_QD = BT * DHD * 2;      // 8 KB  ([128][32] bf16)
+constexpr int TILE_P = BT * BT * 2;        // 32 KB
+constexpr int ST = 2;                      // Q/dO stages
+constexpr int BW_SMEM = 2 * TILE_QD /*K,V*/ + ST * 2 * TILE_QD /*Q,dO*/ + 2 * TILE_P /*P,dS*/ + 1024 + 256;
+constexpr int BW_THREADS = 192;
+constexpr uint32_t C_S = 0, C_DP = 128, C_DV = 256, C_DK = 288, C_DQ = 320;
+constexpr uint32_t SW64 = 4, SW128 = 2;
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// D[b,h,t] = sum_d dO[b,t,h,d] * O[b,t,h,d]      (one warp per frame row: lane owns 8 channels = 1/4 head)
+__global__ void __launch_bounds__(256) attn_dvec_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ d_o,
+                                                        float* __restrict__ dvec, int B, int T, int H) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (row >= B * T) return;
+  float a[8], g[8];
+  ld8<__nv_bfloat16>(o + (long)row * 256 + lane * 8, a);
+  ld8<__nv_bfloat16>(d_o + (long)row * 256 + lane * 8, g);
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s = fmaf(a[i], g[i], s);
+  s += __shfl_xor_sync(0xffffffffu, s, 1);
+  s += __shfl_xor_sync(0xffffffffu, s, 2);
+  if ((lane & 3) == 0) {
+    const int b = row / T, t = row % T, h = lane >> 2;
+    dvec[((long)b * H + h) * T + t] = s;
+  }
+}
+
+// dqkv[:, 0:256] = bf16(scale * dq32)
+__global__ void dq_convert_kernel(const float* __restrict__ dq32, __nv_bfloat16* __restrict__ dqkv, long rows, float scale) {
+  long i = ((long)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  if (i >= rows * 256) return;
+  long r = i / 256;
+  int c = (int)(i % 256);
+  float v[8];
+  ld8<float>(dq32 + i, v);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) v[k] *= scale;
+  st8<__nv_bfloat16>(dqkv + r * 768 + c, v);
+}
+
+__global__ void __launch_bounds__(BW_THREADS) attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv,
+                                                                 const __grid_constant__ CUtensorMap tm_do,
+                                                                 const int32_t* __restrict__ key_len, const float* __restrict__ lse,
+                                                                 const float* __restrict__ dvec, float* __restrict__ dq32,
+                                                                 __nv_bfloat16* __restrict__ dqkv, int T, int H) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sK = smem;
+  uint8_t* sV = sK + TILE_QD;
+  uint8_t* sQ = sV + TILE_QD;                 // [ST]
+  uint8_t* sdO = sQ + ST * TILE_QD;           // [ST]
+  uint8_t* sP = sdO + ST * TILE_QD;
+  uint8_t* sdS = sP + TILE_P;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sdS + TILE_P);
+  uint64_t* kv_full = bars;
+  uint64_t* qdo_full = bars + 1;     // [2]
+  uint64_t* qdo_empty = bars + 3;    // [2]
+  uint64_t* sdp_full = bars + 5;
+  uint64_t* sdp_free = bars + 6;     // 128 arrivals
+  uint64_t* pds_full = bars + 7;     // 128 arrivals
+  uint64_t* dq_full = bars + 8;
+  uint64_t* acc_full = bars + 9;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 10);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.z, h = blockIdx.y, k0 = blockIdx.x * BT;
+  const int klen = min(key_len[b], T);
+  const int D = H * DHD, D3 = 3 * D;
+  const int row0 = b * T;
+  const int nq = (T + BT - 1) / BT;
+  const bool active = k0 < klen;   // block has at least one unmasked key
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tm_qkv);
+    tma_prefetch_desc(&tm_do);
+    mbar_init(kv_full, 1);
+    for (int s = 0; s < ST; ++s) { mbar_init(&qdo_full[s], 1); mbar_init(&qdo_empty[s], 1); }
+    mbar_init(sdp_full, 1);
+    mbar_init(sdp_free, 128);
+    mbar_init(pds_full, 128);
+    mbar_init(dq_full, 1);
+    mbar_init(acc_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_ptr_smem, 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    if (lane == 0 && active) {
+      mbar_expect_tx(kv_full, 2 * TILE_QD);
+      tma_load_2d(sK, &tm_qkv, kv_full, D + h * DHD, row0 + k0);
+      tma_load_2d(sV, &tm_qkv, kv_full, 2 * D + h * DHD, row0 + k0);
+      for (int i = 0; i < nq; ++i) {
+        const int s = i % ST;
+        mbar_wait(&qdo_empty[s], ((i / ST) & 1) ^ 1);
+        mbar_expect_tx(&qdo_full[s], 2 * TILE_QD);
+        tma_load_2d(sQ + s * TILE_QD, &tm_qkv, &qdo_full[s], h * DHD, row0 + i * BT);
+        tma_load_2d(sdO + s * TILE_QD, &tm_do, &qdo_full[s], h * DHD, row0 + i * BT);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && active) {
+      constexpr uint32_t id_s = make_idesc_bf16(BT, BT, false, false);    // S, dP
+      constexpr uint32_t id_t = make_idesc_bf16(BT, DHD, true, true);     // dV, dK : A^T (MN-major), B MN-major
+      constexpr uint32_t id_q = make_idesc_bf16(BT, DHD, false, true);    // dQ     : A K-major,      B MN-major
+      mbar_wait(kv_full, 0);
+      const uint32_t ak = smem_u32(sK), av = smem_u32(sV), ap = smem_u32(sP), ads = smem_u32(sdS);
+      for (int i = 0; i < nq; ++i) {
+        const int s = i % ST;
+        mbar_wait(&qdo_full[s], (i / ST) & 1);
+        if (i > 0) mbar_wait(sdp_free, (i - 1) & 1);
+        tc_fence_after();
+        const uint32_t aq = smem_u32(sQ + s * TILE_QD), ado = smem_u32(sdO + s * TILE_QD);
+#pragma unroll
+        for (int k = 0; k < DHD / 16; ++k)
+          umma_bf16(tmem_base + C_S, make_smem_desc(aq + k * 32, 0, 512, SW64), make_smem_desc(ak + k * 32, 0, 512, SW64), id_s, k);
+#pragma unroll
+        for (int k = 0; k < DHD / 16; ++k)
+          umma_bf16(tmem_base + C_DP, make_smem_desc(ado + k * 32, 0, 512, SW64), make_smem_desc(av + k * 32, 0, 512, SW64), id_s, k);
+        umma_commit(sdp_full);
+        mbar_wait(pds_full, i & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < BT / 16; ++k) {  // contraction over the 128 queries of block i
+          umma_bf16(tmem_base + C_DV, make_smem_desc(ap + k * 2048, 16384, 1024, SW128), make_smem_desc(ado + k * 1024, 0, 512, SW64),
+                    id_t, (i > 0 || k > 0) ? 1u : 0u);
+          umma_bf16(tmem_base + C_DK, make_smem_desc(ads + k * 2048, 16384, 1024, SW128), make_smem_desc(aq + k * 1024, 0, 512, SW64),
+                    id_t, (i > 0 || k > 0) ? 1u : 0u);
+        }
+#pragma unroll
+        for (int k = 0; k < BT / 16; ++k)    // contraction over the 128 keys of block j
+          umma_bf16(tmem_base + C_DQ, make_smem_desc(ads + (k >> 2) * 16384 + (k & 3) * 32, 0, 1024, SW128),
+                    make_smem_desc(ak + k * 1024, 0, 512, SW64), id_q, k > 0 ? 1u : 0u);
+        umma_commit(dq_full);
+        umma_commit(&qdo_empty[s]);
+      }
+      umma_commit(acc_full);
+    }
+  } else {
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+    const float LOG2E = 1.4426950408889634f;
+    const float sc2 = rsqrtf((float)DHD) * LOG2E;
+    float s[32], dp[32];
+    if (active) {
+      for (int i = 0; i < nq; ++i) {
+        const int t = i * BT + r;
+        const bool rvalid = t < T;
+        const float l2 = rvalid ? lse[((long)b * H + h) * T + t] * LOG2E : 0.f;
+        const float di = rvalid ? dvec[((long)b * H + h) * T + t] : 0.f;
+        mbar_wait(sdp_full, i & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int c0 = 0; c0 < BT; c0 += 32) {
+          tmem_ld32(trow + C_S + c0, s);
+          tmem_ld32(trow + C_DP + c0, dp);
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            const bool ok = rvalid && (k0 + c0 + e < klen);
+            const float p = ok ? exp2f(fmaf(s[e], sc2, -l2)) : 0.f;
+            s[e] = p;
+            dp[e] = p * (dp[e] - di);
+          }
+          uint8_t* prow = sP + (c0 >> 6) * 16384 + r * 128;
+          uint8_t* drow = sdS + (c0 >> 6) * 16384 + r * 128;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int off = ((((c0 & 63) >> 3) + g) ^ (r & 7)) << 4;
+            uint4 u, w;
+            __nv_bfloat162* hu = reinterpret_cast<__nv_bfloat162*>(&u);
+            __nv_bfloat162* hw = reinterpret_cast<__nv_bfloat162*>(&w);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              hu[e] = __floats2bfloat162_rn(s[g * 8 + 2 * e], s[g * 8 + 2 * e + 1]);
+              hw[e] = __floats2bfloat162_rn(dp[g * 8 + 2 * e], dp[g * 8 + 2 * e + 1]);
+            }
+            *reinterpret_cast<uint4*>(prow + off) = u;
+            *reinterpret_cast<uint4*>(drow + off) = w;
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(sdp_free);
+        fence_proxy_async();
+        mbar_arrive(pds_full);
+        mbar_wait(dq_full, i & 1);
+        tc_fence_after();
+        tmem_ld32(trow + C_DQ, s);
+        if (rvalid) {
+          float* dst = dq32 + ((long)(row0 + t)) * D + h * DHD;
+#pragma unroll
+          for (int g = 0; g < 8; ++g) red_add_v4(dst + g * 4, s[g * 4], s[g * 4 + 1], s[g * 4 + 2], s[g * 4 + 3]);
+        }
+        tc_fence_before();
+      }
+      mbar_wait(acc_full, 0);
+      tc_fence_after();
+    }
+    // dK / dV rows of this key block (zeros for fully masked blocks)
+    const int tk = k0 + r;
+    if (active) {
+      tmem_ld32(trow + C_DV, s);
+      tmem_ld32(trow + C_DK, dp);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 32; ++e) { s[e] = 0.f; dp[e] = 0.f; }
+    }
+    if (tk < T) {
+      const float scale = rsqrtf((float)DHD);
+      __nv_bfloat16* dk = dqkv + ((long)(row0 + tk)) * D3 + D + h * DHD;
+      __nv_bfloat16* dv = dqkv + ((long)(row0 + tk)) * D3 + 2 * D + h * DHD;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        float a[8], c[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { a[e] = dp[g * 8 + e] * scale; c[e] = s[g * 8 + e]; }
+        st8<__nv_bfloat16>(dk + g * 8, a);
+        st8<__nv_bfloat16>(dv + g * 8, c);
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace
+
+int attn_bwd_tc(const void* qkv, const void* ctx, const void* dctx, const float* lse, const int32_t* key_len, void* dqkv,
+                float* dvec, float* dq32, int B, int T, int H, int dh, cudaStream_t st) {
+  EEC_CHECK_ARG(dh == DHD && H * dh == 256, "attn_bwd_tc: needs 8 heads of 32");
+  EEC_CHECK_ARG(dq32 != nullptr, "attn_bwd_tc: dq32 workspace is NULL");
+  const long rows = (long)B * T;
+  attn_dvec_kernel<<<(int)cdiv64(rows * 32, 256), 256, 0, st>>>((const __nv_bfloat16*)ctx, (const __nv_bfloat16*)dctx, dvec, B, T, H);
+  EEC_LAUNCH_CHECK();
+  EEC_CUDA(cudaMemsetAsync(dq32, 0, (size_t)rows * 256 * sizeof(float), st));
+  CUtensorMap tq, td;
+  if (int r = get_tmap_2d(&tq, qkv, 768, (uint64_t)rows, 768 * 2, DHD, 128, /*SWIZZLE_64B*/ 2)) return r;
+  if (int r = get_tmap_2d(&td, dctx, 256, (uint64_t)rows, 256 * 2, DHD, 128, 2)) return r;
+  static bool attr_set = false;
+  if (!attr_set) {
+    EEC_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BW_SMEM));
+    attr_set = true;
+  }
+  dim3 grid(cdiv(T, BT), H, B);
+  attn_bwd_tc_kernel<<<grid, BW_THREADS, BW_SMEM, st>>>(tq, td, key_len, lse, dvec, dq32, (__nv_bfloat16*)dqkv, T, H);
+  EEC_LAUNCH_CHECK();
+  dq_convert_kernel<<<(int)cdiv64(rows * 32, 256), 256, 0, st>>>(dq32, (__nv_bfloat16*)dqkv, rows, rsqrtf((float)dh));
+  EEC_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace eec

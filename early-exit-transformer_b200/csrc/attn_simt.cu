@@ -274,10 +274,12 @@ extern "C" int eec_attn_fwd(const void* qkv, int dtype, const int32_t* key_len, 
 }
 
 extern "C" int eec_attn_bwd(const void* qkv, const void* ctx, const void* dctx, int dtype, const float* lse,
-                            const int32_t* key_len, void* dqkv, float* dvec, int B, int T, int H, int dh,
+                            const int32_t* key_len, void* dqkv, float* dvec, float* dq32, int B, int T, int H, int dh,
                             eec_stream_t stream) {
   EEC_CHECK_ARG(dh == 32, "attn_bwd: head dim must be 32 (got %d)", dh);
   if (B == 0 || T == 0) return 0;
+  if (dtype == EEC_BF16 && !force_simt() && attn_tc_ready())
+    return attn_bwd_tc(qkv, ctx, dctx, lse, key_len, dqkv, dvec, dq32, B, T, H, dh, S(stream));
   dim3 grid(cdiv(T, QB), H, B);
   if (dtype == EEC_F32) {
     attn_bwd_dq_kernel<float><<<grid, 128, 0, S(stream)>>>((const float*)qkv, (const float*)ctx, (const float*)dctx, lse, key_len, (float*)dqkv, dvec, T, H);

@@ -263,7 +263,8 @@ def layer_backward(P, W: Operands, G: Dict[str, Tensor], pre: str, t: dict, dY: 
     dgrad(dXh, Wo, dctx, N, D, D)
     dqkv = _empty((N, 3 * D), TD, dev)
     dvec = _empty((B * H * T,), f32, dev)
-    ops.attn_bwd(t["qkv"], t["ctx"], dctx, t["lse"], t["key_len"], dqkv, dvec, B, T, H)
+    dq32 = _empty((N, D), f32, dev) if cfg.precision == "bf16" else None
+    ops.attn_bwd(t["qkv"], t["ctx"], dctx, t["lse"], t["key_len"], dqkv, dvec, B, T, H, dq32)
     wgrad(dqkv, t["u2"], G[pre + "self_attn.in_proj_weight"], N, 3 * D, D)
     ops.colsum(dqkv, G[pre + "self_attn.in_proj_bias"], N, 3 * D)
     du2 = _empty((N, D), f32, dev)

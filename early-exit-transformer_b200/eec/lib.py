@@ -45,7 +45,7 @@ _SIGS = {
     "eec_layernorm_fwd": [vp, vp, vp, vp, i32, vp, vp, i32, i32, vp],
     "eec_layernorm_bwd": [vp, vp, vp, vp, vp, vp, i32, vp, vp, i32, i32, vp],
     "eec_attn_fwd": [vp, i32, vp, vp, vp, i32, i32, i32, i32, vp],
-    "eec_attn_bwd": [vp, vp, vp, i32, vp, vp, vp, vp, i32, i32, i32, i32, vp],
+    "eec_attn_bwd": [vp, vp, vp, i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp],
     "eec_dwconv_bn_silu_eval": [vp, i32, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp],
     "eec_dwconv_stats": [vp, i32, vp, vp, vp, vp, i32, i32, i32, i32, vp],
     "eec_bn_silu_train": [vp, vp, vp, vp, vp, vp, vp, f32, vp, vp, vp, i32, i32, i32, vp],

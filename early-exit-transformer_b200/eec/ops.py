@@ -75,9 +75,9 @@ def attn_fwd(qkv, key_len, ctx, lse, B, T, H):
     call("eec_attn_fwd", ptr(qkv), dt(qkv), ptr(key_len), ptr(ctx), ptr(lse), B, T, H, 32, stream())
 
 
-def attn_bwd(qkv, ctx, dctx, lse, key_len, dqkv, dvec, B, T, H):
-    call("eec_attn_bwd", ptr(qkv), ptr(ctx), ptr(dctx), dt(qkv), ptr(lse), ptr(key_len), ptr(dqkv), ptr(dvec), B, T, H, 32,
-         stream())
+def attn_bwd(qkv, ctx, dctx, lse, key_len, dqkv, dvec, B, T, H, dq32=None):
+    call("eec_attn_bwd", ptr(qkv), ptr(ctx), ptr(dctx), dt(qkv), ptr(lse), ptr(key_len), ptr(dqkv), ptr(dvec), ptr(dq32), B, T,
+         H, 32, stream())
 
 
 def dwconv_bn_silu_eval(g, w, bias, bn_w, bn_b, rm, rv, out, B, T, K):

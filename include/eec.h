@@ -93,9 +93,10 @@ int eec_layernorm_bwd(const float* dy, const float* x, const float* mean, const 
  * keys t' >= key_len[b] are masked; fully-masked rows produce 0.  lse [B,H,T] (natural log). */
 int eec_attn_fwd(const void* qkv, int dtype, const int32_t* key_len, void* ctx, float* lse,
                  int B, int T, int H, int dh, eec_stream_t stream);
-/* dvec: fp32 workspace [B*H*T] (row dots dO.O) */
+/* dvec: fp32 workspace [B*H*T] (row dots dO.O); dq32: fp32 workspace [B*T, H*dh] (bf16 path: dQ
+ * partials of the key blocks are summed there with vector atomics; may be NULL for EEC_F32) */
 int eec_attn_bwd(const void* qkv, const void* ctx, const void* dctx, int dtype, const float* lse,
-                 const int32_t* key_len, void* dqkv, float* dvec, int B, int T, int H, int dh,
+                 const int32_t* key_len, void* dqkv, float* dvec, float* dq32, int B, int T, int H, int dh,
                  eec_stream_t stream);
 
 /* ---- conformer convolution module interior (TA:52-65) ------------------------------

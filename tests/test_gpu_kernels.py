@@ -187,7 +187,7 @@ def test_attention_bwd(ops, dtype):
     ops.attn_fwd(qkv, key_len, ctx, lse, B, T, H)
     dqkv = torch.empty_like(qkv)
     dvec = torch.empty(B * H * T, device="cuda")
-    ops.attn_bwd(qkv, ctx, dctx, lse, key_len, dqkv, dvec, B, T, H)
+    ops.attn_bwd(qkv, ctx, dctx, lse, key_len, dqkv, dvec, B, T, H, torch.empty(B * T, 256, device='cuda'))
     x = qkv.double().cpu().requires_grad_(True)
     D = 256
     q, k, v = x.view(B, T, 3 * D).split(D, -1)

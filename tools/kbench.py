@@ -45,8 +45,8 @@ if "attn" in which:
     lse = torch.empty(B, H, T, device=dev)
     fl = 4.0 * B * H * T * T * 32
     report("attn_fwd (EEC_ATTN_TC=%s)" % os.environ.get("EEC_ATTN_TC", "0"), timeit(lambda: ops.attn_fwd(qkv, kl, ctx, lse, B, T, H)), fl)
-    dctx = bf(N, D); dqkv = torch.empty_like(qkv); dvec = torch.empty(B * H * T, device=dev)
-    report("attn_bwd", timeit(lambda: ops.attn_bwd(qkv, ctx, dctx, lse, kl, dqkv, dvec, B, T, H), n=3, warm=1), 2.5 * fl)
+    dctx = bf(N, D); dqkv = torch.empty_like(qkv); dvec = torch.empty(B * H * T, device=dev); dq32 = torch.empty(N, D, device=dev)
+    report("attn_bwd", timeit(lambda: ops.attn_bwd(qkv, ctx, dctx, lse, kl, dqkv, dvec, B, T, H, dq32), n=3, warm=1), 2.5 * fl)
 
 if "gemm" in which:
     a256, a2048, a768, a512 = bf(N, 256), bf(N, 2048), bf(N, 768), bf(N, 512)
