@@ -25,6 +25,15 @@ static bool force_simt_gemm() {
   return v == 1;
 }
 
+static bool gemm_v1() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("EEC_GEMM_V1"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v == 1;
+}
+static int tc_dispatch(const eec_gemm_desc* d, cudaStream_t st, int32_t* argmax, float* entropy, int logsoftmax) {
+  return gemm_v1() ? gemm_tc(d, st, argmax, entropy, logsoftmax) : gemm_tc2(d, st, argmax, entropy, logsoftmax);
+}
+
 // LayerNorm tails for the FFMA path (the tcgen05 path fuses them into the GEMM epilogue)
 static int simt_with_tails(const eec_gemm_desc* d, cudaStream_t st) {
   if (!d->ln_out) return gemm_simt(d, st);
@@ -64,7 +73,7 @@ extern "C" int eec_gemm(const eec_gemm_desc* d, eec_stream_t stream) {
   EEC_CHECK_ARG(d != nullptr, "gemm: NULL descriptor");
   if (d->M == 0 || d->N == 0) return 0;
   if (d->in_dtype == EEC_F32 || force_simt_gemm()) return simt_with_tails(d, S(stream));
-  return gemm_tc(d, S(stream), nullptr, nullptr, 0);
+  return tc_dispatch(d, S(stream), nullptr, nullptr, 0);
 }
 
 extern "C" int eec_head_logsoftmax(const void* x, int dtype, const void* w, const float* bias, float* out,
@@ -80,7 +89,7 @@ extern "C" int eec_head_logsoftmax(const void* x, int dtype, const void* w, cons
   g.in_dtype = dtype; g.bias = bias; g.alpha = 1.0f; g.out_dtype = EEC_F32;
   if (dtype == EEC_BF16 && !force_simt_gemm()) {
     g.C = out; g.ldc = V;
-    return gemm_tc(&g, S(stream), argmax, entropy, 1);
+    return tc_dispatch(&g, S(stream), argmax, entropy, 1);
   }
   EEC_CHECK_ARG(logits_ws != nullptr, "head: fp32 path needs a logits workspace");
   g.C = logits_ws; g.ldc = V;

@@ -50,10 +50,10 @@ static int load_encode() {
 }
 
 static int get_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides,
-                    const uint32_t* box, int swizzle) {
-  struct Key { const void* b; int r; int sw; uint64_t d[3]; uint64_t s[2]; uint32_t x[3]; } k;
+                    const uint32_t* box, int swizzle, bool f32 = false) {
+  struct Key { const void* b; int r; int sw; int f32; uint64_t d[3]; uint64_t s[2]; uint32_t x[3]; } k;
   memset(&k, 0, sizeof(k));
-  k.b = base; k.r = rank; k.sw = swizzle;
+  k.b = base; k.r = rank; k.sw = swizzle; k.f32 = f32 ? 1 : 0;
   for (int i = 0; i < rank; ++i) { k.d[i] = dims[i]; k.x[i] = box[i]; }
   for (int i = 0; i + 1 < rank; ++i) k.s[i] = strides[i];
   std::string key(reinterpret_cast<const char*>(&k), sizeof(k));
@@ -68,7 +68,7 @@ static int get_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t
   for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; }
   for (int i = 0; i + 1 < rank; ++i) gs[i] = strides[i];
   alignas(64) CUtensorMap m;
-  CUresult r = g_encode(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
+  CUresult r = g_encode(&m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, (CUtensorMapSwizzle)swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -89,6 +89,12 @@ int get_tmap_2d(CUtensorMap* out, const void* base, uint64_t dim0, uint64_t dim1
   uint64_t d[2] = {dim0, dim1}, s[1] = {stride1_bytes};
   uint32_t b[2] = {box0, box1};
   return get_tmap(out, base, 2, d, s, b, swizzle);
+}
+// [rows x cols] output tensor stored 32 columns x 128 rows at a time (gemm_tc2 epilogue staging tiles)
+int get_tmap_store(CUtensorMap* out, const void* base, bool bf16, uint64_t cols, uint64_t rows, uint64_t ld_elems) {
+  uint64_t d[2] = {cols, rows}, s[1] = {ld_elems * (bf16 ? 2 : 4)};
+  uint32_t b[2] = {32, 128};
+  return get_tmap(out, base, 2, d, s, b, bf16 ? 2 /*SWIZZLE_64B*/ : 3 /*SWIZZLE_128B*/, !bf16);
 }
 int get_tmap_3d(CUtensorMap* out, const void* base, uint64_t dim0, uint64_t dim1, uint64_t dim2, uint64_t stride1_bytes,
                 uint64_t stride2_bytes, uint32_t box0, uint32_t box1, uint32_t box2) {
