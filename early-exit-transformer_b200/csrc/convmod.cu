@@ -12,13 +12,14 @@ namespace eec {
 
 constexpr int KW = 31;
 constexpr int HALF = 15;
-constexpr int TT = 64;
+constexpr int TT = 32;     // output frames per block (62 input frames incl. halo)
+constexpr int LB = 16;     // input frames fetched per batch (independent loads in flight)
 constexpr float BN_EPS = 1e-5f;
 
 enum { DW_EVAL = 0, DW_STATS = 1, DW_BWD_DATA = 2 };
 
 template <typename TI, typename TO, int MODE>
-__global__ void __launch_bounds__(256) dwconv_kernel(const TI* __restrict__ g, const float* __restrict__ w,
+__global__ void __launch_bounds__(256, 2) dwconv_kernel(const TI* __restrict__ g, const float* __restrict__ w,
                                                      const float* __restrict__ bias, const float* __restrict__ bn_scale_src_w,
                                                      const float* __restrict__ bn_b, const float* __restrict__ run_mean,
                                                      const float* __restrict__ run_var, TO* __restrict__ out,
@@ -34,14 +35,21 @@ __global__ void __launch_bounds__(256) dwconv_kernel(const TI* __restrict__ g, c
   for (int t = 0; t < TT; ++t) acc[t] = bv;
   const TI* gb = g + (long)b * T * C + ch;
 #pragma unroll
-  for (int r = 0; r < TT + KW - 1; ++r) {
-    const int tin = t0 + r - HALF;
-    float x = 0.f;
-    if (tin >= 0 && tin < T) x = ld_as_float<TI>(gb + (long)tin * C);
+  for (int rb = 0; rb < TT + KW - 1; rb += LB) {
+    float xs[LB];
 #pragma unroll
-    for (int t = 0; t < TT; ++t) {
-      const int j = r - t;
-      if (j >= 0 && j < KW) acc[t] = fmaf(wr[j], x, acc[t]);
+    for (int i = 0; i < LB; ++i) {
+      const int tin = t0 + rb + i - HALF;
+      xs[i] = (rb + i < TT + KW - 1 && tin >= 0 && tin < T) ? ld_as_float<TI>(gb + (long)tin * C) : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < LB; ++i) {
+      const int r = rb + i;
+#pragma unroll
+      for (int t = 0; t < TT; ++t) {
+        const int j = r - t;
+        if (r < TT + KW - 1 && j >= 0 && j < KW) acc[t] = fmaf(wr[j], xs[i], acc[t]);
+      }
     }
   }
   TO* ob = out + (long)b * T * C + ch;
@@ -74,7 +82,7 @@ __global__ void __launch_bounds__(256) dwconv_kernel(const TI* __restrict__ g, c
 
 // dW[ch][j] += sum_{b,t} dc[b,t,ch] * g[b,t+j-15,ch];  dbias[ch] += sum dc
 template <typename TI>
-__global__ void __launch_bounds__(256) dwconv_wgrad_kernel(const float* __restrict__ dc, const TI* __restrict__ g,
+__global__ void __launch_bounds__(256, 2) dwconv_wgrad_kernel(const float* __restrict__ dc, const TI* __restrict__ g,
                                                            float* __restrict__ dw, float* __restrict__ dbias, int T, int C) {
   const int ch = blockIdx.z * 256 + threadIdx.x;
   const int b = blockIdx.y, t0 = blockIdx.x * TT;
@@ -90,14 +98,21 @@ __global__ void __launch_bounds__(256) dwconv_wgrad_kernel(const float* __restri
   for (int j = 0; j < KW; ++j) acc[j] = 0.f;
   const TI* gb = g + (long)b * T * C + ch;
 #pragma unroll
-  for (int r = 0; r < TT + KW - 1; ++r) {
-    const int tin = t0 + r - HALF;
-    float x = 0.f;
-    if (tin >= 0 && tin < T) x = ld_as_float<TI>(gb + (long)tin * C);
+  for (int rb = 0; rb < TT + KW - 1; rb += LB) {
+    float xs[LB];
 #pragma unroll
-    for (int t = 0; t < TT; ++t) {
-      const int j = r - t;
-      if (j >= 0 && j < KW) acc[j] = fmaf(d[t], x, acc[j]);
+    for (int i = 0; i < LB; ++i) {
+      const int tin = t0 + rb + i - HALF;
+      xs[i] = (rb + i < TT + KW - 1 && tin >= 0 && tin < T) ? ld_as_float<TI>(gb + (long)tin * C) : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < LB; ++i) {
+      const int r = rb + i;
+#pragma unroll
+      for (int t = 0; t < TT; ++t) {
+        const int j = r - t;
+        if (r < TT + KW - 1 && j >= 0 && j < KW) acc[j] = fmaf(d[t], xs[i], acc[j]);
+      }
     }
   }
 #pragma unroll
@@ -105,7 +120,31 @@ __global__ void __launch_bounds__(256) dwconv_wgrad_kernel(const float* __restri
   atomicAdd(dbias + ch, sb);
 }
 
-// train-mode BN + SiLU (pass B).  thread = channel, block walks a chunk of rows.
+// ---- train-mode BatchNorm kernels.  Block = 64 channel-quads x 4 row lanes (256 threads); a thread moves
+// 4 channels per access (float4 / 4 x bf16) and keeps RU rows in flight; per-channel partial sums are
+// combined across the 4 row lanes in shared memory before ONE double atomic per channel per block.
+constexpr int RU = 8;
+template <typename T> struct Vec4;
+template <> struct Vec4<float> {
+  static __device__ __forceinline__ void ld(const float* p, float (&v)[4]) {
+    float4 f = *reinterpret_cast<const float4*>(p); v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
+  }
+  static __device__ __forceinline__ void st(float* p, const float (&v)[4]) { *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]); }
+};
+template <> struct Vec4<__nv_bfloat16> {
+  static __device__ __forceinline__ void ld(const __nv_bfloat16* p, float (&v)[4]) {
+    uint2 u = *reinterpret_cast<const uint2*>(p);
+    float2 a = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u.x)), b = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u.y));
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+  }
+  static __device__ __forceinline__ void st(__nv_bfloat16* p, const float (&v)[4]) {
+    uint2 u;
+    *reinterpret_cast<__nv_bfloat162*>(&u.x) = __floats2bfloat162_rn(v[0], v[1]);
+    *reinterpret_cast<__nv_bfloat162*>(&u.y) = __floats2bfloat162_rn(v[2], v[3]);
+    *reinterpret_cast<uint2*>(p) = u;
+  }
+};
+
 template <typename TO>
 __global__ void __launch_bounds__(256) bn_silu_train_kernel(const float* __restrict__ c, const double* __restrict__ sums,
                                                             const float* __restrict__ bn_w, const float* __restrict__ bn_b,
@@ -113,77 +152,117 @@ __global__ void __launch_bounds__(256) bn_silu_train_kernel(const float* __restr
                                                             int64_t* __restrict__ nbt, float momentum,
                                                             float* __restrict__ save_mean, float* __restrict__ save_rstd,
                                                             TO* __restrict__ out, int rows, int C, int rows_per_block) {
-  const int ch = blockIdx.y * 256 + threadIdx.x;
+  const int cq = threadIdx.x & 63, rl = threadIdx.x >> 6;
+  const int ch0 = blockIdx.y * 256 + cq * 4;
   const double n = (double)rows;
-  const double mean_d = sums[ch] / n;
-  double var_d = sums[C + ch] / n - mean_d * mean_d;
-  if (var_d < 0.0) var_d = 0.0;
-  const float mean = (float)mean_d;
-  const float rstd = (float)(1.0 / sqrt(var_d + (double)BN_EPS));
-  const float gam = bn_w[ch], bet = bn_b[ch];
-  if (blockIdx.x == 0) {
-    save_mean[ch] = mean;
-    save_rstd[ch] = rstd;
-    if (run_mean) {
-      run_mean[ch] = (1.f - momentum) * run_mean[ch] + momentum * mean;
-      const double unb = (rows > 1) ? var_d * n / (n - 1.0) : var_d;
-      run_var[ch] = (1.f - momentum) * run_var[ch] + momentum * (float)unb;
-      if (ch == 0 && nbt) *nbt += 1;
+  float mean[4], rstd[4], gam[4], bet[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int ch = ch0 + k;
+    const double mean_d = sums[ch] / n;
+    double var_d = sums[C + ch] / n - mean_d * mean_d;
+    if (var_d < 0.0) var_d = 0.0;
+    mean[k] = (float)mean_d;
+    rstd[k] = (float)(1.0 / sqrt(var_d + (double)BN_EPS));
+    gam[k] = bn_w[ch]; bet[k] = bn_b[ch];
+    if (blockIdx.x == 0 && rl == 0) {
+      save_mean[ch] = mean[k];
+      save_rstd[ch] = rstd[k];
+      if (run_mean) {
+        run_mean[ch] = (1.f - momentum) * run_mean[ch] + momentum * mean[k];
+        const double unb = (rows > 1) ? var_d * n / (n - 1.0) : var_d;
+        run_var[ch] = (1.f - momentum) * run_var[ch] + momentum * (float)unb;
+        if (ch == 0 && nbt) *nbt += 1;
+      }
     }
   }
   const int r0 = blockIdx.x * rows_per_block, r1 = min(rows, r0 + rows_per_block);
-  for (int r = r0; r < r1; ++r) {
-    float y = fmaf((c[(long)r * C + ch] - mean) * rstd, gam, bet);
-    st_from_float<TO>(out + (long)r * C + ch, y * sigmoid_acc(y));
+  for (int rb = r0 + rl; rb < r1; rb += 4 * RU) {
+    float v[RU][4];
+#pragma unroll
+    for (int i = 0; i < RU; ++i) {
+      const int r = rb + 4 * i;
+      if (r < r1) Vec4<float>::ld(c + (long)r * C + ch0, v[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < RU; ++i) {
+      const int r = rb + 4 * i;
+      if (r < r1) {
+        float o[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float y = fmaf((v[i][k] - mean[k]) * rstd[k], gam[k], bet[k]);
+          o[k] = y * sigmoid_acc(y);
+        }
+        Vec4<TO>::st(out + (long)r * C + ch0, o);
+      }
+    }
   }
 }
 
-template <typename TI>
-__global__ void __launch_bounds__(256) bn_silu_bwd_stats_kernel(const TI* __restrict__ ds, const float* __restrict__ c,
-                                                                const float* __restrict__ save_mean,
-                                                                const float* __restrict__ save_rstd,
-                                                                const float* __restrict__ bn_w, const float* __restrict__ bn_b,
-                                                                double* __restrict__ sums2, int rows, int C, int rows_per_block) {
-  const int ch = blockIdx.y * 256 + threadIdx.x;
-  const float mean = save_mean[ch], rstd = save_rstd[ch], gam = bn_w[ch], bet = bn_b[ch];
-  const int r0 = blockIdx.x * rows_per_block, r1 = min(rows, r0 + rows_per_block);
-  float s1 = 0.f, s2 = 0.f;
-  for (int r = r0; r < r1; ++r) {
-    float nh = (c[(long)r * C + ch] - mean) * rstd;
-    float y = fmaf(nh, gam, bet);
-    float sg = sigmoid_acc(y);
-    float dn = ld_as_float<TI>(ds + (long)r * C + ch) * sg * (1.f + y * (1.f - sg));
-    s1 += dn;
-    s2 = fmaf(dn, nh, s2);
-  }
-  atomicAdd(sums2 + ch, (double)s1);
-  atomicAdd(sums2 + C + ch, (double)s2);
-}
-
-template <typename TI>
-__global__ void __launch_bounds__(256) bn_silu_bwd_apply_kernel(const TI* __restrict__ ds, const float* __restrict__ c,
-                                                                const float* __restrict__ save_mean,
-                                                                const float* __restrict__ save_rstd,
-                                                                const float* __restrict__ bn_w, const float* __restrict__ bn_b,
-                                                                const double* __restrict__ sums2, float* __restrict__ dc,
-                                                                float* __restrict__ dgamma, float* __restrict__ dbeta, int rows,
-                                                                int C, int rows_per_block) {
-  const int ch = blockIdx.y * 256 + threadIdx.x;
-  const float mean = save_mean[ch], rstd = save_rstd[ch], gam = bn_w[ch], bet = bn_b[ch];
-  const float m1 = (float)(sums2[ch] / (double)rows);
-  const float m2 = (float)(sums2[C + ch] / (double)rows);
-  if (blockIdx.x == 0) {
-    atomicAdd(dbeta + ch, (float)sums2[ch]);
-    atomicAdd(dgamma + ch, (float)sums2[C + ch]);
+template <typename TI, bool APPLY>
+__global__ void __launch_bounds__(256) bn_silu_bwd_kernel(const TI* __restrict__ ds, const float* __restrict__ c,
+                                                          const float* __restrict__ save_mean, const float* __restrict__ save_rstd,
+                                                          const float* __restrict__ bn_w, const float* __restrict__ bn_b,
+                                                          double* __restrict__ sums2, float* __restrict__ dc,
+                                                          float* __restrict__ dgamma, float* __restrict__ dbeta, int rows, int C,
+                                                          int rows_per_block) {
+  __shared__ float red[2][4][256];
+  const int cq = threadIdx.x & 63, rl = threadIdx.x >> 6;
+  const int ch0 = blockIdx.y * 256 + cq * 4;
+  float mean[4], rstd[4], gam[4], bet[4], m1[4], m2[4], s1[4], s2[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int ch = ch0 + k;
+    mean[k] = save_mean[ch]; rstd[k] = save_rstd[ch]; gam[k] = bn_w[ch]; bet[k] = bn_b[ch];
+    s1[k] = 0.f; s2[k] = 0.f;
+    if (APPLY) {
+      m1[k] = (float)(sums2[ch] / (double)rows);
+      m2[k] = (float)(sums2[C + ch] / (double)rows);
+      if (blockIdx.x == 0 && rl == 0) {
+        atomicAdd(dbeta + ch, (float)sums2[ch]);
+        atomicAdd(dgamma + ch, (float)sums2[C + ch]);
+      }
+    }
   }
   const int r0 = blockIdx.x * rows_per_block, r1 = min(rows, r0 + rows_per_block);
-  const float gr = gam * rstd;
-  for (int r = r0; r < r1; ++r) {
-    float nh = (c[(long)r * C + ch] - mean) * rstd;
-    float y = fmaf(nh, gam, bet);
-    float sg = sigmoid_acc(y);
-    float dn = ld_as_float<TI>(ds + (long)r * C + ch) * sg * (1.f + y * (1.f - sg));
-    dc[(long)r * C + ch] = gr * (dn - m1 - nh * m2);
+  for (int rb = r0 + rl; rb < r1; rb += 4 * RU) {
+    float v[RU][4], g[RU][4];
+#pragma unroll
+    for (int i = 0; i < RU; ++i) {
+      const int r = rb + 4 * i;
+      if (r < r1) {
+        Vec4<float>::ld(c + (long)r * C + ch0, v[i]);
+        Vec4<TI>::ld(ds + (long)r * C + ch0, g[i]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < RU; ++i) {
+      const int r = rb + 4 * i;
+      if (r < r1) {
+        float o[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float nh = (v[i][k] - mean[k]) * rstd[k];
+          const float y = fmaf(nh, gam[k], bet[k]);
+          const float sg = sigmoid_acc(y);
+          const float dn = g[i][k] * sg * (1.f + y * (1.f - sg));
+          if (APPLY) o[k] = gam[k] * rstd[k] * (dn - m1[k] - nh * m2[k]);
+          else { s1[k] += dn; s2[k] = fmaf(dn, nh, s2[k]); }
+        }
+        if (APPLY) Vec4<float>::st(dc + (long)r * C + ch0, o);
+      }
+    }
+  }
+  if (!APPLY) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { red[0][rl][cq * 4 + k] = s1[k]; red[1][rl][cq * 4 + k] = s2[k]; }
+    __syncthreads();
+    const int ch = threadIdx.x;
+    const float a = red[0][0][ch] + red[0][1][ch] + red[0][2][ch] + red[0][3][ch];
+    const float b = red[1][0][ch] + red[1][1][ch] + red[1][2][ch] + red[1][3][ch];
+    atomicAdd(sums2 + blockIdx.y * 256 + ch, (double)a);
+    atomicAdd(sums2 + C + blockIdx.y * 256 + ch, (double)b);
   }
 }
 
@@ -240,7 +319,7 @@ extern "C" int eec_bn_silu_train(const float* c, const double* sums, const float
                                  eec_stream_t stream) {
   EEC_CHECK_ARG(C % 256 == 0, "bn_silu_train: C %% 256");
   if (rows == 0) return 0;
-  const int rpb = 64;
+  const int rpb = 32;
   dim3 grid(cdiv(rows, rpb), C / 256);
   if (dtype == EEC_F32)
     bn_silu_train_kernel<float><<<grid, 256, 0, S(stream)>>>(c, sums, bn_w, bn_b, run_mean, run_var, num_batches_tracked, momentum, save_mean, save_rstd, (float*)out, rows, C, rpb);
@@ -255,12 +334,12 @@ extern "C" int eec_bn_silu_bwd_stats(const void* ds, int dtype, const float* c, 
                                      int rows, int C, eec_stream_t stream) {
   EEC_CHECK_ARG(C % 256 == 0, "bn_silu_bwd_stats: C %% 256");
   if (rows == 0) return 0;
-  const int rpb = 64;
+  const int rpb = 32;
   dim3 grid(cdiv(rows, rpb), C / 256);
   if (dtype == EEC_F32)
-    bn_silu_bwd_stats_kernel<float><<<grid, 256, 0, S(stream)>>>((const float*)ds, c, save_mean, save_rstd, bn_w, bn_b, sums2, rows, C, rpb);
+    bn_silu_bwd_kernel<float, false><<<grid, 256, 0, S(stream)>>>((const float*)ds, c, save_mean, save_rstd, bn_w, bn_b, sums2, nullptr, nullptr, nullptr, rows, C, rpb);
   else
-    bn_silu_bwd_stats_kernel<__nv_bfloat16><<<grid, 256, 0, S(stream)>>>((const __nv_bfloat16*)ds, c, save_mean, save_rstd, bn_w, bn_b, sums2, rows, C, rpb);
+    bn_silu_bwd_kernel<__nv_bfloat16, false><<<grid, 256, 0, S(stream)>>>((const __nv_bfloat16*)ds, c, save_mean, save_rstd, bn_w, bn_b, sums2, nullptr, nullptr, nullptr, rows, C, rpb);
   EEC_LAUNCH_CHECK();
   return 0;
 }
@@ -270,12 +349,12 @@ extern "C" int eec_bn_silu_bwd_apply(const void* ds, int dtype, const float* c, 
                                      float* dc, float* dgamma, float* dbeta, int rows, int C, eec_stream_t stream) {
   EEC_CHECK_ARG(C % 256 == 0, "bn_silu_bwd_apply: C %% 256");
   if (rows == 0) return 0;
-  const int rpb = 64;
+  const int rpb = 32;
   dim3 grid(cdiv(rows, rpb), C / 256);
   if (dtype == EEC_F32)
-    bn_silu_bwd_apply_kernel<float><<<grid, 256, 0, S(stream)>>>((const float*)ds, c, save_mean, save_rstd, bn_w, bn_b, sums2, dc, dgamma, dbeta, rows, C, rpb);
+    bn_silu_bwd_kernel<float, true><<<grid, 256, 0, S(stream)>>>((const float*)ds, c, save_mean, save_rstd, bn_w, bn_b, const_cast<double*>(sums2), dc, dgamma, dbeta, rows, C, rpb);
   else
-    bn_silu_bwd_apply_kernel<__nv_bfloat16><<<grid, 256, 0, S(stream)>>>((const __nv_bfloat16*)ds, c, save_mean, save_rstd, bn_w, bn_b, sums2, dc, dgamma, dbeta, rows, C, rpb);
+    bn_silu_bwd_kernel<__nv_bfloat16, true><<<grid, 256, 0, S(stream)>>>((const __nv_bfloat16*)ds, c, save_mean, save_rstd, bn_w, bn_b, const_cast<double*>(sums2), dc, dgamma, dbeta, rows, C, rpb);
   EEC_LAUNCH_CHECK();
   return 0;
 }

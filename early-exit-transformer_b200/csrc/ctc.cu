@@ -111,6 +111,217 @@ __global__ void __launch_bounds__(NT) ctc_kernel(const float* __restrict__ lp_al
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Warp-per-utterance CTC (the fast path, 2L+1 <= 256): lane l owns SPL consecutive extended-target states
+// in registers (even = blank, odd = label), neighbours come from ONE warp shuffle per alpha step (two per
+// beta step), log-sum-exp uses MUFU ex2/lg2, emissions and alpha rows are prefetched PF steps ahead.
+// No block barriers and no shared memory: 2*T dependent steps of ~150 cycles per utterance, all
+// E*B utterances in flight at once.  The dense part of the gradient (scale*softmax) is written by a
+// separate streaming kernel; this kernel subtracts the sparse occupancies with fp32 RED atomics.
+__device__ __forceinline__ float fexp(float x) { return __expf(x); }
+__device__ __forceinline__ float flse2(float a, float b) {
+  const float m = fmaxf(a, b);
+  return (m == -INFINITY) ? -INFINITY : m + __logf(fexp(a - m) + fexp(b - m));
+}
+__device__ __forceinline__ float flse3(float a, float b, float c) {
+  const float m = fmaxf(a, fmaxf(b, c));
+  return (m == -INFINITY) ? -INFINITY : m + __logf(fexp(a - m) + fexp(b - m) + fexp(c - m));
+}
+
+__global__ void ctc_grad_init_kernel(const float4* __restrict__ lp, const int64_t* __restrict__ target_len, float4* __restrict__ grad,
+                                     int B, long tv4, float gscale, long total4) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long)gridDim.x * blockDim.x) {
+    const int b = (int)((i / tv4) % B);
+    const float sc = gscale / ((float)B * (float)max((int)target_len[b], 1));
+    const float4 v = lp[i];
+    grad[i] = make_float4(sc * __expf(v.x), sc * __expf(v.y), sc * __expf(v.z), sc * __expf(v.w));
+  }
+}
+
+template <int SPL>
+__global__ void __launch_bounds__(128) ctc_warp_kernel(const float* __restrict__ lp_all, const int64_t* __restrict__ targets,
+                                                       const int64_t* __restrict__ target_len, int EB, int B, int T, int V, int Lmax,
+                                                       int blank, float gscale, float* __restrict__ nll_all,
+                                                       float* __restrict__ loss_out, float* __restrict__ grad_all,
+                                                       float* __restrict__ alpha_ws) {
+  constexpr int NL = SPL / 2;   // label states per lane
+  constexpr int PF = 4;         // prefetch distance (time steps)
+  constexpr int SW = 32 * SPL;  // workspace row width
+  const int wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (wg >= EB) return;
+  const int e = wg / B, b = wg % B;
+  const float* lp = lp_all + (long)wg * T * V;
+  float* grad = grad_all ? grad_all + (long)wg * T * V : nullptr;
+  float* aw = alpha_ws + (long)wg * T * SW + lane * SPL;
+  int U = (int)target_len[b];
+  if (U > Lmax) U = Lmax;
+  const int S = 2 * U + 1;
+  const int s0 = lane * SPL;
+  int lab[NL];
+  bool skip[NL], skipf[NL];
+#pragma unroll
+  for (int j = 0; j < NL; ++j) {
+    const int li = lane * NL + j;   // label index of state s0 + 2j + 1
+    lab[j] = (li < U) ? (int)targets[(long)b * Lmax + li] : blank;
+    const int lprev = (li >= 1 && li - 1 < U) ? (int)targets[(long)b * Lmax + li - 1] : -1;
+    const int lnext = (li + 1 < U) ? (int)targets[(long)b * Lmax + li + 1] : -1;
+    skip[j] = (li < U) && (li >= 1) && lab[j] != lprev;
+    skipf[j] = (li + 1 < U) && lab[j] != lnext;
+  }
+  float a[SPL];
+  // ---------------- alpha
+#pragma unroll
+  for (int i = 0; i < SPL; ++i) {
+    const int s = s0 + i;
+    a[i] = -INFINITY;
+    if (s == 0) a[i] = lp[blank];
+    if (s == 1 && S > 1) a[i] = lp[lab[0]];
+  }
+#pragma unroll
+  for (int i = 0; i < SPL; ++i) aw[i] = a[i];
+  float emb[PF], eml[PF][NL];
+#pragma unroll
+  for (int k = 0; k < PF; ++k) {
+    const int t = 1 + k;
+    if (t < T) {
+      emb[k] = lp[(long)t * V + blank];
+#pragma unroll
+      for (int j = 0; j < NL; ++j) eml[k][j] = lp[(long)t * V + lab[j]];
+    }
+  }
+  for (int t0 = 1; t0 < T; t0 += PF) {
+#pragma unroll
+    for (int k = 0; k < PF; ++k) {
+      const int t = t0 + k;
+      if (t < T) {
+        const float lb_ = emb[k];
+        float ll_[NL];
+#pragma unroll
+        for (int j = 0; j < NL; ++j) ll_[j] = eml[k][j];
+        if (t + PF < T) {
+          emb[k] = lp[(long)(t + PF) * V + blank];
+#pragma unroll
+          for (int j = 0; j < NL; ++j) eml[k][j] = lp[(long)(t + PF) * V + lab[j]];
+        }
+        float prev_last = __shfl_up_sync(0xffffffffu, a[SPL - 1], 1);
+        if (lane == 0) prev_last = -INFINITY;
+        float na[SPL];
+#pragma unroll
+        for (int i = 0; i < SPL; ++i) {
+          const float am1 = (i == 0) ? prev_last : a[i - 1];
+          if ((i & 1) == 0) {
+            na[i] = flse2(a[i], am1) + lb_;
+          } else {
+            const float am2 = (i == 1) ? prev_last : a[i - 2];
+            na[i] = flse3(a[i], am1, skip[i >> 1] ? am2 : -INFINITY) + ll_[i >> 1];
+          }
+          if (s0 + i >= S) na[i] = -INFINITY;
+        }
+#pragma unroll
+        for (int i = 0; i < SPL; ++i) { a[i] = na[i]; aw[(long)t * SW + i] = na[i]; }
+      }
+    }
+  }
+  // log-likelihood = lse(alpha_T-1[S-1], alpha_T-1[S-2])
+  float mine = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < SPL; ++i) {
+    const int s = s0 + i;
+    if (s == S - 1 || (s == S - 2 && S >= 2)) mine = flse2(mine, a[i]);
+  }
+  float mx = mine;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  float se = (mine == -INFINITY) ? 0.f : fexp(mine - mx);
+  se = warp_sum(se);
+  const float ll = (mx == -INFINITY) ? -INFINITY : mx + __logf(se);
+  const bool feasible = (ll != -INFINITY);
+  const float denom = (float)B * (float)max(U, 1);
+  if (lane == 0) {
+    nll_all[wg] = feasible ? -ll : 0.f;
+    if (feasible && loss_out) atomicAdd(loss_out + e, -ll / denom);
+  }
+  if (!grad) return;
+  if (!feasible) {  // zero_infinity: the dense init wrote scale*softmax; zero the whole slab
+    float4* g4 = reinterpret_cast<float4*>(grad);
+    for (long i = lane; i < (long)T * V / 4; i += 32) g4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    return;
+  }
+  // ---------------- beta + occupancy
+  const float sc = gscale / denom;
+  float bt[SPL];
+  float al[PF][SPL];
+#pragma unroll
+  for (int k = 0; k < PF; ++k) {
+    const int t = T - 1 - k;
+    if (t >= 0) {
+      emb[k] = lp[(long)t * V + blank];
+#pragma unroll
+      for (int j = 0; j < NL; ++j) eml[k][j] = lp[(long)t * V + lab[j]];
+#pragma unroll
+      for (int i = 0; i < SPL; ++i) al[k][i] = aw[(long)t * SW + i];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < SPL; ++i) bt[i] = -INFINITY;
+  for (int t0 = T - 1; t0 >= 0; t0 -= PF) {
+#pragma unroll
+    for (int k = 0; k < PF; ++k) {
+      const int t = t0 - k;
+      if (t >= 0) {
+        const float lb_ = emb[k];
+        float ll_[NL], av[SPL];
+#pragma unroll
+        for (int j = 0; j < NL; ++j) ll_[j] = eml[k][j];
+#pragma unroll
+        for (int i = 0; i < SPL; ++i) av[i] = al[k][i];
+        if (t - PF >= 0) {
+          emb[k] = lp[(long)(t - PF) * V + blank];
+#pragma unroll
+          for (int j = 0; j < NL; ++j) eml[k][j] = lp[(long)(t - PF) * V + lab[j]];
+#pragma unroll
+          for (int i = 0; i < SPL; ++i) al[k][i] = aw[(long)(t - PF) * SW + i];
+        }
+        float nb[SPL];
+        if (t == T - 1) {
+#pragma unroll
+          for (int i = 0; i < SPL; ++i) {
+            const int s = s0 + i;
+            nb[i] = (s < S && s >= S - 2) ? (((i & 1) == 0) ? lb_ : ll_[i >> 1]) : -INFINITY;
+          }
+        } else {
+          float n0 = __shfl_down_sync(0xffffffffu, bt[0], 1);
+          float n1 = __shfl_down_sync(0xffffffffu, bt[1], 1);
+          if (lane == 31) { n0 = -INFINITY; n1 = -INFINITY; }
+#pragma unroll
+          for (int i = 0; i < SPL; ++i) {
+            const float bp1 = (i == SPL - 1) ? n0 : bt[i + 1];
+            if ((i & 1) == 0) {
+              nb[i] = flse2(bt[i], bp1) + lb_;
+            } else {
+              const float bp2 = (i == SPL - 1) ? n1 : bt[(i + 2 < SPL) ? i + 2 : i];
+              nb[i] = flse3(bt[i], bp1, skipf[i >> 1] ? bp2 : -INFINITY) + ll_[i >> 1];
+            }
+            if (s0 + i >= S) nb[i] = -INFINITY;
+          }
+        }
+        float occ_blank = 0.f;
+#pragma unroll
+        for (int i = 0; i < SPL; ++i) {
+          bt[i] = nb[i];
+          const float em = ((i & 1) == 0) ? lb_ : ll_[i >> 1];
+          const float o = (av[i] == -INFINITY || nb[i] == -INFINITY) ? 0.f : fexp(av[i] + nb[i] - em - ll);
+          if ((i & 1) == 0) occ_blank += o;
+          else if (o != 0.f) atomicAdd(grad + (long)t * V + lab[i >> 1], -sc * o);
+        }
+        occ_blank = warp_sum(occ_blank);
+        if (lane == 0 && occ_blank != 0.f) atomicAdd(grad + (long)t * V + blank, -sc * occ_blank);
+      }
+    }
+  }
+}
+
 // greedy collapse: one warp per utterance
 __global__ void greedy_collapse_kernel(const int32_t* __restrict__ argmax, int32_t* __restrict__ tokens,
                                        int32_t* __restrict__ n_tokens, int B, int T, int blank) {
@@ -248,9 +459,20 @@ __global__ void col2im_k3s2_kernel(const float* __restrict__ dcols, int ldc, flo
 using namespace eec;
 
 static int ctc_smax(int Lmax) { return ((2 * Lmax + 1 + 31) / 32) * 32; }
+// states per lane of the warp kernel (0 = too long, use the block kernel)
+static int ctc_spl(int Lmax) {
+  const int S = 2 * Lmax + 1;
+  if (S <= 64) return 2;
+  if (S <= 128) return 4;
+  if (S <= 192) return 6;
+  if (S <= 256) return 8;
+  return 0;
+}
 
 extern "C" int64_t eec_ctc_workspace_bytes(int E, int B, int T, int Lmax) {
-  return (int64_t)E * B * T * ctc_smax(Lmax) * (int64_t)sizeof(float);
+  const int spl = ctc_spl(Lmax);
+  const int width = spl ? 32 * spl : ctc_smax(Lmax);
+  return (int64_t)E * B * T * width * (int64_t)sizeof(float);
 }
 
 extern "C" int eec_ctc_fwd_bwd(const float* lp, const int64_t* targets, const int64_t* target_len, int E, int B, int T,
@@ -258,9 +480,30 @@ extern "C" int eec_ctc_fwd_bwd(const float* lp, const int64_t* targets, const in
                                void* workspace, eec_stream_t stream) {
   if (E == 0 || B == 0) return 0;
   EEC_CHECK_ARG(T >= 1, "ctc: T must be >= 1");
+  EEC_CHECK_ARG(workspace != nullptr, "ctc: workspace is NULL");
+  const int spl = ctc_spl(Lmax);
+  if (spl && V % 4 == 0) {
+    float* wsf = reinterpret_cast<float*>(workspace);
+    if (grad) {
+      const long total4 = (long)E * B * T * V / 4;
+      const int blocks = (int)min((long)148 * 16, cdiv64(total4, 256));
+      ctc_grad_init_kernel<<<blocks, 256, 0, S(stream)>>>((const float4*)lp, target_len, (float4*)grad, B, (long)T * V / 4, gscale, total4);
+      EEC_LAUNCH_CHECK();
+    }
+    const int EB = E * B;
+    const int blocks = cdiv(EB * 32, 128);
+#define EEC_CTC_WARP(SPLV)                                                                                              \
+  ctc_warp_kernel<SPLV><<<blocks, 128, 0, S(stream)>>>(lp, targets, target_len, EB, B, T, V, Lmax, blank, gscale, nll, \
+                                                      loss_out, grad, wsf)
+    if (spl == 2) EEC_CTC_WARP(2);
+    else if (spl == 4) EEC_CTC_WARP(4);
+    else if (spl == 6) EEC_CTC_WARP(6);
+    else EEC_CTC_WARP(8);
+    EEC_LAUNCH_CHECK();
+    return 0;
+  }
   const int Smax = ctc_smax(Lmax);
   EEC_CHECK_ARG(Smax <= 1024, "ctc: target length %d too long (2L+1 must be <= 1024)", Lmax);
-  EEC_CHECK_ARG(workspace != nullptr, "ctc: workspace is NULL");
   size_t smem = (size_t)(2 * (Smax + 2) + V) * sizeof(float) + (size_t)Smax * sizeof(int);
   dim3 grid(B, E);
   float* ws = reinterpret_cast<float*>(workspace);

@@ -43,7 +43,8 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
                                                             const float* __restrict__ mean, const float* __restrict__ rstd,
                                                             const float* __restrict__ gamma, float* __restrict__ dx,
                                                             int dx_accumulate, float* __restrict__ dgamma,
-                                                            float* __restrict__ dbeta, int rows) {
+                                                            float* __restrict__ dbeta, __nv_bfloat16* __restrict__ dx_bf16,
+                                                            int rows) {
   __shared__ float red[8][256];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int c0 = lane * 8;
@@ -78,6 +79,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
       for (int i = 0; i < 8; ++i) o[i] += old[i];
     }
     st8<float>(dx + (long)r * 256 + c0, o);
+    if (dx_bf16) st8<__nv_bfloat16>(dx_bf16 + (long)r * 256 + c0, o);
   }
   if (dgamma) {
 #pragma unroll
@@ -193,6 +195,42 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ in, i
   }
 }
 
+// cols % 256 == 0: block = 32 column-octets x 8 row lanes, 128-bit loads, 4 rows in flight per thread
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_vec_kernel(const T* __restrict__ in, int ld, float* __restrict__ out, int rows,
+                                                         int rows_per_block, float scale) {
+  __shared__ float red[8][256];
+  const int cg = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int c0 = blockIdx.x * 256 + cg * 8;
+  const int r0 = blockIdx.y * rows_per_block, r1 = min(rows, r0 + rows_per_block);
+  float acc[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+  for (int rb = r0 + rl; rb < r1; rb += 32) {
+    float v[4][8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = rb + 8 * i;
+      if (r < r1) ld8<T>(in + (long)r * ld + c0, v[i]);
+      else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[i][k] = 0.f;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] += v[i][k];
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) red[rl][cg * 8 + k] = acc[k];
+  __syncthreads();
+  float t = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
+  atomicAdd(out + blockIdx.x * 256 + threadIdx.x, t * scale);
+}
+
 __global__ void axpy_kernel(const float* __restrict__ x, float a, float* __restrict__ y, long n) {
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) y[i] = fmaf(a, x[i], y[i]);
@@ -286,11 +324,11 @@ extern "C" int eec_layernorm_fwd(const float* x, const float* gamma, const float
 
 extern "C" int eec_layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd,
                                  const float* gamma, float* dx, int dx_accumulate, float* dgamma, float* dbeta,
-                                 int rows, int d, eec_stream_t stream) {
+                                 void* dx_bf16, int rows, int d, eec_stream_t stream) {
   EEC_CHECK_ARG(d == 256, "layernorm_bwd: d must be 256 (got %d)", d);
   if (rows == 0) return 0;
   int blocks = min(cdiv(rows, 8), 148 * 4);
-  layernorm_bwd_kernel<<<blocks, 256, 0, S(stream)>>>(dy, x, mean, rstd, gamma, dx, dx_accumulate, dgamma, dbeta, rows);
+  layernorm_bwd_kernel<<<blocks, 256, 0, S(stream)>>>(dy, x, mean, rstd, gamma, dx, dx_accumulate, dgamma, dbeta, (__nv_bfloat16*)dx_bf16, rows);
   EEC_LAUNCH_CHECK();
   return 0;
 }
@@ -330,6 +368,14 @@ extern "C" int eec_cast(const void* in, int in_dtype, void* out, int out_dtype, 
 extern "C" int eec_colsum(const void* in, int dtype, int ld, float* out, float scale, int rows, int cols,
                           eec_stream_t stream) {
   if (rows == 0 || cols == 0) return 0;
+  if (cols % 256 == 0 && ld % 8 == 0) {
+    const int rpbv = 128;
+    dim3 gv(cols / 256, cdiv(rows, rpbv));
+    if (dtype == EEC_F32) colsum_vec_kernel<float><<<gv, 256, 0, S(stream)>>>((const float*)in, ld, out, rows, rpbv, scale);
+    else colsum_vec_kernel<__nv_bfloat16><<<gv, 256, 0, S(stream)>>>((const __nv_bfloat16*)in, ld, out, rows, rpbv, scale);
+    EEC_LAUNCH_CHECK();
+    return 0;
+  }
   int rpb = 256;
   dim3 grid(cdiv(cols, 32), cdiv(rows, rpb));
   if (dtype == EEC_F32) colsum_kernel<float><<<grid, 256, 0, S(stream)>>>((const float*)in, ld, out, rows, cols, rpb, scale);

@@ -83,10 +83,11 @@ int eec_gemm(const eec_gemm_desc* d, eec_stream_t stream);
 /* ---- LayerNorm (TA:103,151,42,211) ------------------------------------------------- */
 int eec_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* out, int out_dtype,
                       float* mean, float* rstd, int rows, int d, eec_stream_t stream);
-/* dx (+)= LN'(dy); dgamma += sum dy*xhat; dbeta += sum dy  (dgamma/dbeta accumulate) */
+/* dx (+)= LN'(dy); dgamma += sum dy*xhat; dbeta += sum dy  (dgamma/dbeta accumulate);
+ * dx_bf16 (optional): bf16 copy of the final dx (operand of the next dgrad/wgrad GEMM) */
 int eec_layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd,
                       const float* gamma, float* dx, int dx_accumulate, float* dgamma, float* dbeta,
-                      int rows, int d, eec_stream_t stream);
+                      void* dx_bf16, int rows, int d, eec_stream_t stream);
 
 /* ---- multi-head self-attention core (nn.MultiheadAttention SDPA branch, TA:194-200) -
  * qkv [B*T, 3*H*dh] rows = [q | k | v], head h = columns [h*dh, (h+1)*dh) of each third.
