@@ -13,13 +13,34 @@ namespace eec {
 constexpr int KW = 31;
 constexpr int HALF = 15;
 constexpr int TT = 32;     // output frames per block (62 input frames incl. halo)
-constexpr int LB = 16;     // input frames fetched per batch (independent loads in flight)
 constexpr float BN_EPS = 1e-5f;
 
 enum { DW_EVAL = 0, DW_STATS = 1, DW_BWD_DATA = 2 };
 
+// copy rows [t_first, t_first + TT+30) x 256 channels of one utterance into smem (row pitch 256 elements)
+template <typename TI>
+__device__ __forceinline__ void stage_tile(TI* tile, const TI* __restrict__ src, int t_first, int T, int C) {
+  constexpr int ROWS = TT + KW - 1;
+  constexpr int CPR = 256 * sizeof(TI) / 16;   // 16-byte chunks per row
+  for (int i = threadIdx.x; i < ROWS * CPR; i += 256) {
+    const int r = i / CPR, c = i % CPR;
+    const int t = t_first + r;
+    uint8_t* dst = reinterpret_cast<uint8_t*>(tile) + (size_t)i * 16;
+    if (t >= 0 && t < T) {
+      const uint8_t* s = reinterpret_cast<const uint8_t*>(src + (long)t * C) + c * 16;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(s) : "memory");
+    } else {
+      *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
+    }
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+}
+template <typename TI> constexpr int dw_smem_bytes() { return (TT + KW - 1) * 256 * (int)sizeof(TI); }
+
 template <typename TI, typename TO, int MODE>
-__global__ void __launch_bounds__(256, 2) dwconv_kernel(const TI* __restrict__ g, const float* __restrict__ w,
+__global__ void __launch_bounds__(256, 3) dwconv_kernel(const TI* __restrict__ g, const float* __restrict__ w,
                                                      const float* __restrict__ bias, const float* __restrict__ bn_scale_src_w,
                                                      const float* __restrict__ bn_b, const float* __restrict__ run_mean,
                                                      const float* __restrict__ run_var, TO* __restrict__ out,
@@ -33,23 +54,17 @@ __global__ void __launch_bounds__(256, 2) dwconv_kernel(const TI* __restrict__ g
   float acc[TT];
 #pragma unroll
   for (int t = 0; t < TT; ++t) acc[t] = bv;
-  const TI* gb = g + (long)b * T * C + ch;
+  // stage the (TT+30) x 256 input tile in shared memory: 16-byte cp.async per thread, zero rows outside [0,T)
+  extern __shared__ __align__(16) uint8_t dw_smem[];
+  TI* tile = reinterpret_cast<TI*>(dw_smem);
+  stage_tile<TI>(tile, g + (long)b * T * C + blockIdx.z * 256, t0 - HALF, T, C);
 #pragma unroll
-  for (int rb = 0; rb < TT + KW - 1; rb += LB) {
-    float xs[LB];
+  for (int r = 0; r < TT + KW - 1; ++r) {
+    const float x = ld_as_float<TI>(tile + r * 256 + threadIdx.x);
 #pragma unroll
-    for (int i = 0; i < LB; ++i) {
-      const int tin = t0 + rb + i - HALF;
-      xs[i] = (rb + i < TT + KW - 1 && tin >= 0 && tin < T) ? ld_as_float<TI>(gb + (long)tin * C) : 0.f;
-    }
-#pragma unroll
-    for (int i = 0; i < LB; ++i) {
-      const int r = rb + i;
-#pragma unroll
-      for (int t = 0; t < TT; ++t) {
-        const int j = r - t;
-        if (r < TT + KW - 1 && j >= 0 && j < KW) acc[t] = fmaf(wr[j], xs[i], acc[t]);
-      }
+    for (int t = 0; t < TT; ++t) {
+      const int j = r - t;
+      if (j >= 0 && j < KW) acc[t] = fmaf(wr[j], x, acc[t]);
     }
   }
   TO* ob = out + (long)b * T * C + ch;
@@ -82,7 +97,7 @@ __global__ void __launch_bounds__(256, 2) dwconv_kernel(const TI* __restrict__ g
 
 // dW[ch][j] += sum_{b,t} dc[b,t,ch] * g[b,t+j-15,ch];  dbias[ch] += sum dc
 template <typename TI>
-__global__ void __launch_bounds__(256, 2) dwconv_wgrad_kernel(const float* __restrict__ dc, const TI* __restrict__ g,
+__global__ void __launch_bounds__(256, 3) dwconv_wgrad_kernel(const float* __restrict__ dc, const TI* __restrict__ g,
                                                            float* __restrict__ dw, float* __restrict__ dbias, int T, int C) {
   const int ch = blockIdx.z * 256 + threadIdx.x;
   const int b = blockIdx.y, t0 = blockIdx.x * TT;
@@ -96,23 +111,16 @@ __global__ void __launch_bounds__(256, 2) dwconv_wgrad_kernel(const float* __res
   }
 #pragma unroll
   for (int j = 0; j < KW; ++j) acc[j] = 0.f;
-  const TI* gb = g + (long)b * T * C + ch;
+  extern __shared__ __align__(16) uint8_t dw_smem[];
+  TI* tile = reinterpret_cast<TI*>(dw_smem);
+  stage_tile<TI>(tile, g + (long)b * T * C + blockIdx.z * 256, t0 - HALF, T, C);
 #pragma unroll
-  for (int rb = 0; rb < TT + KW - 1; rb += LB) {
-    float xs[LB];
+  for (int r = 0; r < TT + KW - 1; ++r) {
+    const float x = ld_as_float<TI>(tile + r * 256 + threadIdx.x);
 #pragma unroll
-    for (int i = 0; i < LB; ++i) {
-      const int tin = t0 + rb + i - HALF;
-      xs[i] = (rb + i < TT + KW - 1 && tin >= 0 && tin < T) ? ld_as_float<TI>(gb + (long)tin * C) : 0.f;
-    }
-#pragma unroll
-    for (int i = 0; i < LB; ++i) {
-      const int r = rb + i;
-#pragma unroll
-      for (int t = 0; t < TT; ++t) {
-        const int j = r - t;
-        if (r < TT + KW - 1 && j >= 0 && j < KW) acc[j] = fmaf(d[t], xs[i], acc[j]);
-      }
+    for (int t = 0; t < TT; ++t) {
+      const int j = r - t;
+      if (j >= 0 && j < KW) acc[j] = fmaf(d[t], x, acc[j]);
     }
   }
 #pragma unroll
@@ -284,6 +292,17 @@ __global__ void glu_bwd_kernel(const T* __restrict__ z, const T* __restrict__ dg
 
 using namespace eec;
 
+// dynamic-smem launch of a dwconv kernel whose staged input type is TI (fp32 tiles exceed the 48 KB default)
+#define EEC_DW_LAUNCH(kernel, TI, ...)                                                                                   \
+  do {                                                                                                                   \
+    static bool attr_ = false;                                                                                           \
+    if (!attr_) {                                                                                                        \
+      EEC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dw_smem_bytes<TI>()));          \
+      attr_ = true;                                                                                                      \
+    }                                                                                                                    \
+    kernel<<<grid, 256, dw_smem_bytes<TI>(), S(stream)>>>(__VA_ARGS__);                                                   \
+  } while (0)
+
 #define DW_ARGS_OK()                                                                 \
   EEC_CHECK_ARG(K == KW, "dwconv: depthwise_kernel_size must be 31 (got %d)", K);    \
   EEC_CHECK_ARG(C % 256 == 0, "dwconv: channels must be a multiple of 256 (got %d)", C); \
@@ -295,9 +314,9 @@ extern "C" int eec_dwconv_bn_silu_eval(const void* g, int dtype, const float* w,
                                        int T, int C, int K, eec_stream_t stream) {
   DW_ARGS_OK();
   if (dtype == EEC_F32)
-    dwconv_kernel<float, float, DW_EVAL><<<grid, 256, 0, S(stream)>>>((const float*)g, w, bias, bn_w, bn_b, run_mean, run_var, (float*)out, nullptr, T, C);
+    EEC_DW_LAUNCH((dwconv_kernel<float, float, DW_EVAL>), float, (const float*)g, w, bias, bn_w, bn_b, run_mean, run_var, (float*)out, nullptr, T, C);
   else
-    dwconv_kernel<__nv_bfloat16, __nv_bfloat16, DW_EVAL><<<grid, 256, 0, S(stream)>>>((const __nv_bfloat16*)g, w, bias, bn_w, bn_b, run_mean, run_var, (__nv_bfloat16*)out, nullptr, T, C);
+    EEC_DW_LAUNCH((dwconv_kernel<__nv_bfloat16, __nv_bfloat16, DW_EVAL>), __nv_bfloat16, (const __nv_bfloat16*)g, w, bias, bn_w, bn_b, run_mean, run_var, (__nv_bfloat16*)out, nullptr, T, C);
   EEC_LAUNCH_CHECK();
   return 0;
 }
@@ -306,9 +325,9 @@ extern "C" int eec_dwconv_stats(const void* g, int dtype, const float* w, const 
                                 int B, int T, int C, int K, eec_stream_t stream) {
   DW_ARGS_OK();
   if (dtype == EEC_F32)
-    dwconv_kernel<float, float, DW_STATS><<<grid, 256, 0, S(stream)>>>((const float*)g, w, bias, nullptr, nullptr, nullptr, nullptr, c, sums, T, C);
+    EEC_DW_LAUNCH((dwconv_kernel<float, float, DW_STATS>), float, (const float*)g, w, bias, nullptr, nullptr, nullptr, nullptr, c, sums, T, C);
   else
-    dwconv_kernel<__nv_bfloat16, float, DW_STATS><<<grid, 256, 0, S(stream)>>>((const __nv_bfloat16*)g, w, bias, nullptr, nullptr, nullptr, nullptr, c, sums, T, C);
+    EEC_DW_LAUNCH((dwconv_kernel<__nv_bfloat16, float, DW_STATS>), __nv_bfloat16, (const __nv_bfloat16*)g, w, bias, nullptr, nullptr, nullptr, nullptr, c, sums, T, C);
   EEC_LAUNCH_CHECK();
   return 0;
 }
@@ -363,13 +382,13 @@ extern "C" int eec_dwconv_bwd(const float* dc, const void* g, int dtype, const f
                               float* dbias, int B, int T, int C, int K, eec_stream_t stream) {
   DW_ARGS_OK();
   if (dtype == EEC_F32) {
-    dwconv_kernel<float, float, DW_BWD_DATA><<<grid, 256, 0, S(stream)>>>(dc, w, nullptr, nullptr, nullptr, nullptr, nullptr, (float*)dg, nullptr, T, C);
+    EEC_DW_LAUNCH((dwconv_kernel<float, float, DW_BWD_DATA>), float, dc, w, nullptr, nullptr, nullptr, nullptr, nullptr, (float*)dg, nullptr, T, C);
     EEC_LAUNCH_CHECK();
-    dwconv_wgrad_kernel<float><<<grid, 256, 0, S(stream)>>>(dc, (const float*)g, dw, dbias, T, C);
+    EEC_DW_LAUNCH((dwconv_wgrad_kernel<float>), float, dc, (const float*)g, dw, dbias, T, C);
   } else {
-    dwconv_kernel<float, __nv_bfloat16, DW_BWD_DATA><<<grid, 256, 0, S(stream)>>>(dc, w, nullptr, nullptr, nullptr, nullptr, nullptr, (__nv_bfloat16*)dg, nullptr, T, C);
+    EEC_DW_LAUNCH((dwconv_kernel<float, __nv_bfloat16, DW_BWD_DATA>), float, dc, w, nullptr, nullptr, nullptr, nullptr, nullptr, (__nv_bfloat16*)dg, nullptr, T, C);
     EEC_LAUNCH_CHECK();
-    dwconv_wgrad_kernel<__nv_bfloat16><<<grid, 256, 0, S(stream)>>>(dc, (const __nv_bfloat16*)g, dw, dbias, T, C);
+    EEC_DW_LAUNCH((dwconv_wgrad_kernel<__nv_bfloat16>), __nv_bfloat16, dc, (const __nv_bfloat16*)g, dw, dbias, T, C);
   }
   EEC_LAUNCH_CHECK();
   return 0;

@@ -118,14 +118,20 @@ __global__ void __launch_bounds__(NT) ctc_kernel(const float* __restrict__ lp_al
 // No block barriers and no shared memory: 2*T dependent steps of ~150 cycles per utterance, all
 // E*B utterances in flight at once.  The dense part of the gradient (scale*softmax) is written by a
 // separate streaming kernel; this kernel subtracts the sparse occupancies with fp32 RED atomics.
-__device__ __forceinline__ float fexp(float x) { return __expf(x); }
+// The recursion runs in the log2 domain with a FINITE "minus infinity" sentinel so that every
+// log-sum-exp is branch-free (no inf-inf NaNs) and the compiler can interleave the lane's states.
+constexpr float CTC_NEG = -1.0e30f;
+constexpr float LOG2E_F = 1.4426950408889634f;
+constexpr float LN2_F = 0.6931471805599453f;
+__device__ __forceinline__ float fex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float flg2(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float flse2(float a, float b) {
   const float m = fmaxf(a, b);
-  return (m == -INFINITY) ? -INFINITY : m + __logf(fexp(a - m) + fexp(b - m));
+  return m + flg2(fex2(a - m) + fex2(b - m));
 }
 __device__ __forceinline__ float flse3(float a, float b, float c) {
   const float m = fmaxf(a, fmaxf(b, c));
-  return (m == -INFINITY) ? -INFINITY : m + __logf(fexp(a - m) + fexp(b - m) + fexp(c - m));
+  return m + flg2(fex2(a - m) + fex2(b - m) + fex2(c - m));
 }
 
 __global__ void ctc_grad_init_kernel(const float4* __restrict__ lp, const int64_t* __restrict__ target_len, float4* __restrict__ grad,
@@ -174,9 +180,9 @@ __global__ void __launch_bounds__(128) ctc_warp_kernel(const float* __restrict__
 #pragma unroll
   for (int i = 0; i < SPL; ++i) {
     const int s = s0 + i;
-    a[i] = -INFINITY;
-    if (s == 0) a[i] = lp[blank];
-    if (s == 1 && S > 1) a[i] = lp[lab[0]];
+    a[i] = CTC_NEG;
+    if (s == 0) a[i] = lp[blank] * LOG2E_F;
+    if (s == 1 && S > 1) a[i] = lp[lab[0]] * LOG2E_F;
   }
 #pragma unroll
   for (int i = 0; i < SPL; ++i) aw[i] = a[i];
@@ -185,9 +191,9 @@ __global__ void __launch_bounds__(128) ctc_warp_kernel(const float* __restrict__
   for (int k = 0; k < PF; ++k) {
     const int t = 1 + k;
     if (t < T) {
-      emb[k] = lp[(long)t * V + blank];
+      emb[k] = lp[(long)t * V + blank] * LOG2E_F;
 #pragma unroll
-      for (int j = 0; j < NL; ++j) eml[k][j] = lp[(long)t * V + lab[j]];
+      for (int j = 0; j < NL; ++j) eml[k][j] = lp[(long)t * V + lab[j]] * LOG2E_F;
     }
   }
   for (int t0 = 1; t0 < T; t0 += PF) {
@@ -200,12 +206,12 @@ __global__ void __launch_bounds__(128) ctc_warp_kernel(const float* __restrict__
 #pragma unroll
         for (int j = 0; j < NL; ++j) ll_[j] = eml[k][j];
         if (t + PF < T) {
-          emb[k] = lp[(long)(t + PF) * V + blank];
+          emb[k] = lp[(long)(t + PF) * V + blank] * LOG2E_F;
 #pragma unroll
-          for (int j = 0; j < NL; ++j) eml[k][j] = lp[(long)(t + PF) * V + lab[j]];
+          for (int j = 0; j < NL; ++j) eml[k][j] = lp[(long)(t + PF) * V + lab[j]] * LOG2E_F;
         }
         float prev_last = __shfl_up_sync(0xffffffffu, a[SPL - 1], 1);
-        if (lane == 0) prev_last = -INFINITY;
+        if (lane == 0) prev_last = CTC_NEG;
         float na[SPL];
 #pragma unroll
         for (int i = 0; i < SPL; ++i) {
@@ -214,9 +220,9 @@ __global__ void __launch_bounds__(128) ctc_warp_kernel(const float* __restrict__
             na[i] = flse2(a[i], am1) + lb_;
           } else {
             const float am2 = (i == 1) ? prev_last : a[i - 2];
-            na[i] = flse3(a[i], am1, skip[i >> 1] ? am2 : -INFINITY) + ll_[i >> 1];
+            na[i] = flse3(a[i], am1, skip[i >> 1] ? am2 : CTC_NEG) + ll_[i >> 1];
           }
-          if (s0 + i >= S) na[i] = -INFINITY;
+          na[i] = (s0 + i >= S) ? CTC_NEG : fmaxf(na[i], CTC_NEG);
         }
 #pragma unroll
         for (int i = 0; i < SPL; ++i) { a[i] = na[i]; aw[(long)t * SW + i] = na[i]; }
@@ -224,7 +230,7 @@ __global__ void __launch_bounds__(128) ctc_warp_kernel(const float* __restrict__
     }
   }
   // log-likelihood = lse(alpha_T-1[S-1], alpha_T-1[S-2])
-  float mine = -INFINITY;
+  float mine = CTC_NEG;   // log2 domain
 #pragma unroll
   for (int i = 0; i < SPL; ++i) {
     const int s = s0 + i;
@@ -233,14 +239,14 @@ __global__ void __launch_bounds__(128) ctc_warp_kernel(const float* __restrict__
   float mx = mine;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-  float se = (mine == -INFINITY) ? 0.f : fexp(mine - mx);
+  float se = fex2(mine - mx);
   se = warp_sum(se);
-  const float ll = (mx == -INFINITY) ? -INFINITY : mx + __logf(se);
-  const bool feasible = (ll != -INFINITY);
+  const float ll = mx + flg2(se);                 // log2 P(y|x)
+  const bool feasible = ll > 0.5f * CTC_NEG;
   const float denom = (float)B * (float)max(U, 1);
   if (lane == 0) {
-    nll_all[wg] = feasible ? -ll : 0.f;
-    if (feasible && loss_out) atomicAdd(loss_out + e, -ll / denom);
+    nll_all[wg] = feasible ? -ll * LN2_F : 0.f;
+    if (feasible && loss_out) atomicAdd(loss_out + e, -ll * LN2_F / denom);
   }
   if (!grad) return;
   if (!feasible) {  // zero_infinity: the dense init wrote scale*softmax; zero the whole slab
@@ -256,15 +262,15 @@ __global__ void __launch_bounds__(128) ctc_warp_kernel(const float* __restrict__
   for (int k = 0; k < PF; ++k) {
     const int t = T - 1 - k;
     if (t >= 0) {
-      emb[k] = lp[(long)t * V + blank];
+      emb[k] = lp[(long)t * V + blank] * LOG2E_F;
 #pragma unroll
-      for (int j = 0; j < NL; ++j) eml[k][j] = lp[(long)t * V + lab[j]];
+      for (int j = 0; j < NL; ++j) eml[k][j] = lp[(long)t * V + lab[j]] * LOG2E_F;
 #pragma unroll
       for (int i = 0; i < SPL; ++i) al[k][i] = aw[(long)t * SW + i];
     }
   }
 #pragma unroll
-  for (int i = 0; i < SPL; ++i) bt[i] = -INFINITY;
+  for (int i = 0; i < SPL; ++i) bt[i] = CTC_NEG;
   for (int t0 = T - 1; t0 >= 0; t0 -= PF) {
 #pragma unroll
     for (int k = 0; k < PF; ++k) {
@@ -277,9 +283,9 @@ __global__ void __launch_bounds__(128) ctc_warp_kernel(const float* __restrict__
 #pragma unroll
         for (int i = 0; i < SPL; ++i) av[i] = al[k][i];
         if (t - PF >= 0) {
-          emb[k] = lp[(long)(t - PF) * V + blank];
+          emb[k] = lp[(long)(t - PF) * V + blank] * LOG2E_F;
 #pragma unroll
-          for (int j = 0; j < NL; ++j) eml[k][j] = lp[(long)(t - PF) * V + lab[j]];
+          for (int j = 0; j < NL; ++j) eml[k][j] = lp[(long)(t - PF) * V + lab[j]] * LOG2E_F;
 #pragma unroll
           for (int i = 0; i < SPL; ++i) al[k][i] = aw[(long)(t - PF) * SW + i];
         }
@@ -288,12 +294,12 @@ __global__ void __launch_bounds__(128) ctc_warp_kernel(const float* __restrict__
 #pragma unroll
           for (int i = 0; i < SPL; ++i) {
             const int s = s0 + i;
-            nb[i] = (s < S && s >= S - 2) ? (((i & 1) == 0) ? lb_ : ll_[i >> 1]) : -INFINITY;
+            nb[i] = (s < S && s >= S - 2) ? (((i & 1) == 0) ? lb_ : ll_[i >> 1]) : CTC_NEG;
           }
         } else {
           float n0 = __shfl_down_sync(0xffffffffu, bt[0], 1);
           float n1 = __shfl_down_sync(0xffffffffu, bt[1], 1);
-          if (lane == 31) { n0 = -INFINITY; n1 = -INFINITY; }
+          if (lane == 31) { n0 = CTC_NEG; n1 = CTC_NEG; }
 #pragma unroll
           for (int i = 0; i < SPL; ++i) {
             const float bp1 = (i == SPL - 1) ? n0 : bt[i + 1];
@@ -301,9 +307,9 @@ __global__ void __launch_bounds__(128) ctc_warp_kernel(const float* __restrict__
               nb[i] = flse2(bt[i], bp1) + lb_;
             } else {
               const float bp2 = (i == SPL - 1) ? n1 : bt[(i + 2 < SPL) ? i + 2 : i];
-              nb[i] = flse3(bt[i], bp1, skipf[i >> 1] ? bp2 : -INFINITY) + ll_[i >> 1];
+              nb[i] = flse3(bt[i], bp1, skipf[i >> 1] ? bp2 : CTC_NEG) + ll_[i >> 1];
             }
-            if (s0 + i >= S) nb[i] = -INFINITY;
+            nb[i] = (s0 + i >= S) ? CTC_NEG : fmaxf(nb[i], CTC_NEG);
           }
         }
         float occ_blank = 0.f;
@@ -311,12 +317,12 @@ __global__ void __launch_bounds__(128) ctc_warp_kernel(const float* __restrict__
         for (int i = 0; i < SPL; ++i) {
           bt[i] = nb[i];
           const float em = ((i & 1) == 0) ? lb_ : ll_[i >> 1];
-          const float o = (av[i] == -INFINITY || nb[i] == -INFINITY) ? 0.f : fexp(av[i] + nb[i] - em - ll);
+          const float o = fex2(fmaxf(av[i] + nb[i] - em - ll, -126.f));   // posterior of state s at time t (<= 1)
           if ((i & 1) == 0) occ_blank += o;
-          else if (o != 0.f) atomicAdd(grad + (long)t * V + lab[i >> 1], -sc * o);
+          else if (o > 1e-30f) atomicAdd(grad + (long)t * V + lab[i >> 1], -sc * o);
         }
         occ_blank = warp_sum(occ_blank);
-        if (lane == 0 && occ_blank != 0.f) atomicAdd(grad + (long)t * V + blank, -sc * occ_blank);
+        if (lane == 0 && occ_blank > 1e-30f) atomicAdd(grad + (long)t * V + blank, -sc * occ_blank);
       }
     }
   }
