@@ -96,31 +96,38 @@ __global__ void __launch_bounds__(256, 3) dwconv_kernel(const TI* __restrict__ g
 }
 
 // dW[ch][j] += sum_{b,t} dc[b,t,ch] * g[b,t+j-15,ch];  dbias[ch] += sum dc
+// grid (WG_SPLIT, B): a block walks every WG_SPLIT-th time tile of its utterance and issues its 31 x 256
+// atomics once at the end (contention per address = WG_SPLIT * B instead of tiles * B).
+constexpr int WG_SPLIT = 3;
 template <typename TI>
 __global__ void __launch_bounds__(256, 3) dwconv_wgrad_kernel(const float* __restrict__ dc, const TI* __restrict__ g,
                                                            float* __restrict__ dw, float* __restrict__ dbias, int T, int C) {
   const int ch = blockIdx.z * 256 + threadIdx.x;
-  const int b = blockIdx.y, t0 = blockIdx.x * TT;
-  float d[TT], acc[KW];
+  const int b = blockIdx.y;
+  float acc[KW];
   float sb = 0.f;
-  const float* db = dc + (long)b * T * C + ch;
-#pragma unroll
-  for (int t = 0; t < TT; ++t) {
-    d[t] = (t0 + t < T) ? db[(long)(t0 + t) * C] : 0.f;
-    sb += d[t];
-  }
 #pragma unroll
   for (int j = 0; j < KW; ++j) acc[j] = 0.f;
   extern __shared__ __align__(16) uint8_t dw_smem[];
   TI* tile = reinterpret_cast<TI*>(dw_smem);
-  stage_tile<TI>(tile, g + (long)b * T * C + blockIdx.z * 256, t0 - HALF, T, C);
-#pragma unroll
-  for (int r = 0; r < TT + KW - 1; ++r) {
-    const float x = ld_as_float<TI>(tile + r * 256 + threadIdx.x);
+  const float* db = dc + (long)b * T * C + ch;
+  for (int t0 = blockIdx.x * TT; t0 < T; t0 += WG_SPLIT * TT) {
+    float d[TT];
 #pragma unroll
     for (int t = 0; t < TT; ++t) {
-      const int j = r - t;
-      if (j >= 0 && j < KW) acc[j] = fmaf(d[t], x, acc[j]);
+      d[t] = (t0 + t < T) ? db[(long)(t0 + t) * C] : 0.f;
+      sb += d[t];
+    }
+    __syncthreads();   // previous tile fully consumed
+    stage_tile<TI>(tile, g + (long)b * T * C + blockIdx.z * 256, t0 - HALF, T, C);
+#pragma unroll
+    for (int r = 0; r < TT + KW - 1; ++r) {
+      const float x = ld_as_float<TI>(tile + r * 256 + threadIdx.x);
+#pragma unroll
+      for (int t = 0; t < TT; ++t) {
+        const int j = r - t;
+        if (j >= 0 && j < KW) acc[j] = fmaf(d[t], x, acc[j]);
+      }
     }
   }
 #pragma unroll
@@ -384,10 +391,12 @@ extern "C" int eec_dwconv_bwd(const float* dc, const void* g, int dtype, const f
   if (dtype == EEC_F32) {
     EEC_DW_LAUNCH((dwconv_kernel<float, float, DW_BWD_DATA>), float, dc, w, nullptr, nullptr, nullptr, nullptr, nullptr, (float*)dg, nullptr, T, C);
     EEC_LAUNCH_CHECK();
+    grid.x = WG_SPLIT;
     EEC_DW_LAUNCH((dwconv_wgrad_kernel<float>), float, dc, (const float*)g, dw, dbias, T, C);
   } else {
     EEC_DW_LAUNCH((dwconv_kernel<float, __nv_bfloat16, DW_BWD_DATA>), float, dc, w, nullptr, nullptr, nullptr, nullptr, nullptr, (__nv_bfloat16*)dg, nullptr, T, C);
     EEC_LAUNCH_CHECK();
+    grid.x = WG_SPLIT;
     EEC_DW_LAUNCH((dwconv_wgrad_kernel<__nv_bfloat16>), __nv_bfloat16, dc, (const __nv_bfloat16*)g, dw, dbias, T, C);
   }
   EEC_LAUNCH_CHECK();

@@ -51,12 +51,36 @@ struct P2 {
   int accumulate;
   const float* ln_gamma; const float* ln_beta; float* ln_mean; float* ln_rstd;
   int32_t* argmax; float* entropy;
+  int debug;   // EEC_GEMM_DEBUG bitmask (perf triage only): 1 = skip bulk store issue, 2 = skip staging entirely, 4 = skip activation math
 };
 
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem_src, int x, int y) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(m)),
                "r"(smem_u32(smem_src)), "r"(x), "r"(y)
                : "memory");
+}
+// multicast variants (thread-block cluster of CS CTAs stacked along M share every B tile: each CTA fetches
+// 1/CS of it and the TMA unit writes that slice into the same smem offset of all CTAs in `mask`)
+__device__ __forceinline__ void tma_load_2d_mc(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int x, int y, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(x), "r"(y), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
@@ -96,9 +120,11 @@ struct Stager {
   int bar_id;    // named barrier of this column half (128 threads)
   bool leader;   // one thread per half issues the bulk stores
   int r;         // row in tile
+  int debug;
 
   // values -> swizzled smem tile -> bulk tensor store of a [128 rows x 32 cols] box at (x, y)
   __device__ __forceinline__ void store(const CUtensorMap* tm, int x, int y, const float (&v)[32], bool bf16) {
+    if (debug & 2) return;
     uint8_t* b = buf[next];
     if (leader) bulk_wait_read<1>();   // the store that last used this buffer has finished reading it
     bar_sync(bar_id, 128);
@@ -122,7 +148,7 @@ struct Stager {
     }
     fence_proxy_async();
     bar_sync(bar_id, 128);
-    if (leader) {
+    if (leader && !(debug & 1)) {
       tma_store_2d(tm, b, x, y);
       bulk_commit();
     }
@@ -130,7 +156,7 @@ struct Stager {
   }
 };
 
-template <bool A_KMAJ, bool B_KMAJ, int EPI>
+template <bool A_KMAJ, bool B_KMAJ, int EPI, int CS>
 __global__ void __launch_bounds__(NT2, 1) gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                                                           const __grid_constant__ CUtensorMap tmC,   // main output
                                                           const __grid_constant__ CUtensorMap tmP,   // pre-activation store
@@ -147,29 +173,35 @@ __global__ void __launch_bounds__(NT2, 1) gemm_tc2_kernel(const __grid_constant_
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tiles = p.m_tiles * p.n_tiles;
+  // work units: (m super-tile of CS m-tiles, n tile, k split); CTA `rank` of a cluster owns m-tile msuper*CS + rank
+  const int rank = (CS > 1) ? (int)cluster_ctarank() : 0;
+  const int cid = blockIdx.x / CS, n_clusters = gridDim.x / CS;
+  const int m_super = (p.m_tiles + CS - 1) / CS;
+  const int tiles = m_super * p.n_tiles;
   const int n_units = tiles * p.splits;
   const int total_kb = (p.K + BK - 1) / BK;
+  constexpr uint16_t MC_MASK = (uint16_t)((1u << CS) - 1u);
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
-    for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], CS); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 8); }
     fence_barrier_init();
   }
   if (warp == 1) { tmem_alloc(tmem_ptr_smem, 512); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
+  if (CS > 1) cluster_sync_all();   // peers' barriers are initialised before any multicast can land
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
   if (warp == 0) {
     if (lane == 0) {
       uint32_t it = 0;  // global k-block counter (stage ring position)
-      for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+      for (int u = cid; u < n_units; u += n_clusters) {
         const int tile = u % tiles, split = u / tiles;
-        const int m0 = (tile / p.n_tiles) * BM;
+        const int m0 = ((tile / p.n_tiles) * CS + rank) * BM;
         const int nt = tile % p.n_tiles;
         const int n0 = (EPI == EPI_GLU) ? nt * 128 : nt * BN;
         const int kb0 = split * p.kb_per_split, kb1 = min(total_kb, kb0 + p.kb_per_split);
@@ -186,16 +218,33 @@ __global__ void __launch_bounds__(NT2, 1) gemm_tc2_kernel(const __grid_constant_
             tma_load_2d(sa, &tmA, &full_bar[s], m0, k);
             tma_load_2d(sa + 8192, &tmA, &full_bar[s], m0 + 64, k);
           }
-          if (B_KMAJ) {
-            if (EPI == EPI_GLU) {
-              tma_load_2d(sb, &tmB, &full_bar[s], k, n0);
-              tma_load_2d(sb + 16384, &tmB, &full_bar[s], k, p.N / 2 + n0);
+          if (CS == 1) {
+            if (B_KMAJ) {
+              if (EPI == EPI_GLU) {
+                tma_load_2d(sb, &tmB, &full_bar[s], k, n0);
+                tma_load_2d(sb + 16384, &tmB, &full_bar[s], k, p.N / 2 + n0);
+              } else {
+                tma_load_2d(sb, &tmB, &full_bar[s], k, n0);
+              }
             } else {
-              tma_load_2d(sb, &tmB, &full_bar[s], k, n0);
+#pragma unroll
+              for (int a = 0; a < BN / 64; ++a) tma_load_2d(sb + a * 8192, &tmB, &full_bar[s], n0 + a * 64, k);
             }
           } else {
+            // this CTA fetches slice `rank` of the B tile and multicasts it to every CTA of the cluster
+            constexpr int SLICE = B_BYTES / CS;
+            uint8_t* dst = sb + rank * SLICE;
+            if (B_KMAJ) {
+              if (EPI == EPI_GLU) {   // CS == 2: rank 0 -> the 128 "a" rows, rank 1 -> the 128 gate rows
+                tma_load_2d_mc(dst, &tmB, &full_bar[s], k, (rank == 0) ? n0 : p.N / 2 + n0, MC_MASK);
+              } else {
+                tma_load_2d_mc(dst, &tmB, &full_bar[s], k, n0 + rank * (BN / CS), MC_MASK);   // box {64 k, 256/CS n}
+              }
+            } else {
 #pragma unroll
-            for (int a = 0; a < BN / 64; ++a) tma_load_2d(sb + a * 8192, &tmB, &full_bar[s], n0 + a * 64, k);
+              for (int a = 0; a < BN / 64 / CS; ++a)
+                tma_load_2d_mc(dst + a * 8192, &tmB, &full_bar[s], n0 + (rank * (BN / 64 / CS) + a) * 64, k, MC_MASK);
+            }
           }
         }
       }
@@ -204,7 +253,7 @@ __global__ void __launch_bounds__(NT2, 1) gemm_tc2_kernel(const __grid_constant_
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(BM, BN, !A_KMAJ, !B_KMAJ);
       uint32_t it = 0, ut = 0;
-      for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++ut) {
+      for (int u = cid; u < n_units; u += n_clusters, ++ut) {
         const int split = u / tiles;
         const int kb0 = split * p.kb_per_split, kb1 = min(total_kb, kb0 + p.kb_per_split);
         const uint32_t acc = ut & 1;
@@ -223,7 +272,8 @@ __global__ void __launch_bounds__(NT2, 1) gemm_tc2_kernel(const __grid_constant_
             const uint64_t bd = B_KMAJ ? make_smem_desc(sb + k * 32, 0, 1024) : make_smem_desc(sb + k * 2048, 8192, 1024);
             umma_bf16(d_tmem, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[s]);
+          if (CS == 1) umma_commit(&empty_bar[s]);
+          else umma_commit_mc(&empty_bar[s], MC_MASK);   // frees this stage in every CTA that multicasts into it
         }
         umma_commit(&tfull_bar[acc]);
       }
@@ -242,11 +292,12 @@ __global__ void __launch_bounds__(NT2, 1) gemm_tc2_kernel(const __grid_constant_
     st.bar_id = 1 + half;
     st.leader = (et == half * 128);
     st.r = r;
+    st.debug = p.debug;
     float v[32];
     uint32_t ut = 0;
-    for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++ut) {
+    for (int u = cid; u < n_units; u += n_clusters, ++ut) {
       const int tile = u % tiles, split = u / tiles;
-      const int m0 = (tile / p.n_tiles) * BM;
+      const int m0 = ((tile / p.n_tiles) * CS + rank) * BM;
       const int nt = tile % p.n_tiles;
       const int n0 = (EPI == EPI_GLU) ? nt * 128 : nt * BN;
       const uint32_t acc = ut & 1;
@@ -280,8 +331,10 @@ __global__ void __launch_bounds__(NT2, 1) gemm_tc2_kernel(const __grid_constant_
           }
           if (p.act == EEC_ACT_SILU) {
             if (p.has_pre) st.store(&tmP, n, m0, v, true);
+            if (!(p.debug & 4)) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] *= sigmoid_fast(v[j]);
+              for (int j = 0; j < 32; ++j) v[j] *= sigmoid_fast(v[j]);
+            }
           } else if (p.act == EEC_ACT_DSILU) {
             if (valid) {
               const __nv_bfloat16* hp = reinterpret_cast<const __nv_bfloat16*>(p.preact_in) + (long)m * p.ldp + n;
@@ -440,23 +493,40 @@ __global__ void __launch_bounds__(NT2, 1) gemm_tc2_kernel(const __grid_constant_
     tc_fence_before();
   }
   __syncthreads();
+  if (CS > 1) cluster_sync_all();   // no CTA exits while a peer can still multicast into its smem / barriers
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
 }
 
-template <bool AK, bool BK_, int EPI>
-int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc_, const CUtensorMap& tp, const CUtensorMap& tl,
-            const P2& p, int grid, cudaStream_t st) {
+template <bool AK, bool BK_, int EPI, int CS>
+int launch2cs(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc_, const CUtensorMap& tp, const CUtensorMap& tl,
+              const P2& p, int grid, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    EEC_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<AK, BK_, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
+    EEC_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<AK, BK_, EPI, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
     attr_set = true;
   }
-  gemm_tc2_kernel<AK, BK_, EPI><<<grid, NT2, SMEM2_BYTES, st>>>(ta, tb, tc_, tp, tl, p);
-  EEC_LAUNCH_CHECK();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(NT2);
+  cfg.dynamicSmemBytes = SMEM2_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  count_launch();
+  EEC_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc2_kernel<AK, BK_, EPI, CS>, ta, tb, tc_, tp, tl, p));
   return 0;
+}
+
+template <bool AK, bool BK_, int EPI>
+int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc_, const CUtensorMap& tp, const CUtensorMap& tl,
+            const P2& p, int grid, cudaStream_t st, int cs) {
+  if (cs == 2) return launch2cs<AK, BK_, EPI, 2>(ta, tb, tc_, tp, tl, p, grid, st);
+  return launch2cs<AK, BK_, EPI, 1>(ta, tb, tc_, tp, tl, p, grid, st);
 }
 
 int g_num_sms = 0;
@@ -492,11 +562,15 @@ int gemm_tc2(const eec_gemm_desc* d, cudaStream_t st, int32_t* argmax, float* en
     EEC_CUDA(cudaGetDevice(&dev));
     EEC_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
+  // cluster of 2 CTAs along M (B-tile multicast) whenever there are at least two m-tiles
+  static int cs_env = -1;
+  if (cs_env < 0) { const char* e = getenv("EEC_GEMM_CLUSTER"); cs_env = e ? atoi(e) : 2; }
+  const int cs = (cs_env >= 2 && cdiv(d->M, BM) >= 2) ? 2 : 1;
   CUtensorMap ta, tb, tcm, tpm, tlm;
   if (d->a_kmajor) { if (int r = get_tmap_2d(&ta, d->A, d->K, d->M, (uint64_t)d->lda * 2, 64, 128)) return r; }
   else { if (int r = get_tmap_2d(&ta, d->A, d->M, d->K, (uint64_t)d->lda * 2, 64, 64)) return r; }
   if (d->b_kmajor) {
-    if (int r = get_tmap_2d(&tb, d->B, d->K, d->N, (uint64_t)d->ldb * 2, 64, epi == EPI_GLU ? 128 : 256)) return r;
+    if (int r = get_tmap_2d(&tb, d->B, d->K, d->N, (uint64_t)d->ldb * 2, 64, (epi == EPI_GLU || cs == 2) ? 128 : 256)) return r;
   } else {
     if (int r = get_tmap_2d(&tb, d->B, d->N, d->K, (uint64_t)d->ldb * 2, 64, 64)) return r;
   }
@@ -529,17 +603,20 @@ int gemm_tc2(const eec_gemm_desc* d, cudaStream_t st, int32_t* argmax, float* en
   p.c_acc = reinterpret_cast<float*>(d->C); p.ldc = d->ldc; p.accumulate = d->accumulate;
   p.ln_gamma = d->ln_gamma; p.ln_beta = d->ln_beta; p.ln_mean = d->ln_mean; p.ln_rstd = d->ln_rstd;
   p.argmax = argmax; p.entropy = entropy;
-  const int n_units = p.m_tiles * p.n_tiles * p.splits;
-  const int grid = min(n_units, g_num_sms);
+  static int dbg = -1;
+  if (dbg < 0) { const char* e = getenv("EEC_GEMM_DEBUG"); dbg = e ? atoi(e) : 0; }
+  p.debug = dbg;
+  const int n_units = cdiv(p.m_tiles, cs) * p.n_tiles * p.splits;
+  const int grid = min(n_units, g_num_sms / cs) * cs;
 
 #define EEC_TC2_DISPATCH(AK, BK_)                                                                       \
   switch (epi) {                                                                                        \
-    case EPI_GENERIC: return launch2<AK, BK_, EPI_GENERIC>(ta, tb, tcm, tpm, tlm, p, grid, st);          \
+    case EPI_GENERIC: return launch2<AK, BK_, EPI_GENERIC>(ta, tb, tcm, tpm, tlm, p, grid, st, cs);          \
     default: break;                                                                                     \
   }
-  if (epi == EPI_GLU) return launch2<true, true, EPI_GLU>(ta, tb, tcm, tpm, tlm, p, grid, st);
-  if (epi == EPI_LN) return launch2<true, true, EPI_LN>(ta, tb, tcm, tpm, tlm, p, grid, st);
-  if (epi == EPI_LOGSOFTMAX) return launch2<true, true, EPI_LOGSOFTMAX>(ta, tb, tcm, tpm, tlm, p, grid, st);
+  if (epi == EPI_GLU) return launch2<true, true, EPI_GLU>(ta, tb, tcm, tpm, tlm, p, grid, st, cs);
+  if (epi == EPI_LN) return launch2<true, true, EPI_LN>(ta, tb, tcm, tpm, tlm, p, grid, st, cs);
+  if (epi == EPI_LOGSOFTMAX) return launch2<true, true, EPI_LOGSOFTMAX>(ta, tb, tcm, tpm, tlm, p, grid, st, cs);
   if (d->a_kmajor && d->b_kmajor) { EEC_TC2_DISPATCH(true, true) }
   else if (d->a_kmajor && !d->b_kmajor) { EEC_TC2_DISPATCH(true, false) }
   else if (!d->a_kmajor && !d->b_kmajor) { EEC_TC2_DISPATCH(false, false) }

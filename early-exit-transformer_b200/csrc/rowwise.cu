@@ -44,14 +44,14 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
                                                             const float* __restrict__ gamma, float* __restrict__ dx,
                                                             int dx_accumulate, float* __restrict__ dgamma,
                                                             float* __restrict__ dbeta, __nv_bfloat16* __restrict__ dx_bf16,
-                                                            int rows) {
+                                                            float* __restrict__ dx_colsum, float colsum_scale, int rows) {
   __shared__ float red[8][256];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int c0 = lane * 8;
-  float g[8], dg[8], db[8];
+  float g[8], dg[8], db[8], cs[8];
   ld8<float>(gamma + c0, g);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) { dg[i] = 0.f; db[i] = 0.f; }
+  for (int i = 0; i < 8; ++i) { dg[i] = 0.f; db[i] = 0.f; cs[i] = 0.f; }
   for (int r = blockIdx.x * 8 + wib; r < rows; r += gridDim.x * 8) {
     float d[8], v[8];
     ld8<float>(dy + (long)r * 256 + c0, d);
@@ -80,6 +80,18 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
     }
     st8<float>(dx + (long)r * 256 + c0, o);
     if (dx_bf16) st8<__nv_bfloat16>(dx_bf16 + (long)r * 256 + c0, o);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) cs[i] += o[i];
+  }
+  if (dx_colsum) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) red[wib][c0 + i] = cs[i];
+    __syncthreads();
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
+    atomicAdd(dx_colsum + threadIdx.x, s * colsum_scale);
+    __syncthreads();
   }
   if (dgamma) {
 #pragma unroll
@@ -324,11 +336,11 @@ extern "C" int eec_layernorm_fwd(const float* x, const float* gamma, const float
 
 extern "C" int eec_layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd,
                                  const float* gamma, float* dx, int dx_accumulate, float* dgamma, float* dbeta,
-                                 void* dx_bf16, int rows, int d, eec_stream_t stream) {
+                                 void* dx_bf16, float* dx_colsum, float colsum_scale, int rows, int d, eec_stream_t stream) {
   EEC_CHECK_ARG(d == 256, "layernorm_bwd: d must be 256 (got %d)", d);
   if (rows == 0) return 0;
   int blocks = min(cdiv(rows, 8), 148 * 4);
-  layernorm_bwd_kernel<<<blocks, 256, 0, S(stream)>>>(dy, x, mean, rstd, gamma, dx, dx_accumulate, dgamma, dbeta, (__nv_bfloat16*)dx_bf16, rows);
+  layernorm_bwd_kernel<<<blocks, 256, 0, S(stream)>>>(dy, x, mean, rstd, gamma, dx, dx_accumulate, dgamma, dbeta, (__nv_bfloat16*)dx_bf16, dx_colsum, colsum_scale, rows);
   EEC_LAUNCH_CHECK();
   return 0;
 }

@@ -208,38 +208,38 @@ def layer_backward(P, W: Operands, G: Dict[str, Tensor], pre: str, t: dict, dY: 
 
     bf16 = cfg.precision == "bf16"
 
-    def ln_bwd(dy, x_in, m, r, key, accumulate, want_h=True):
-        """LayerNorm backward into the residual-gradient stream dX; also emits the GEMM-operand copy of dX."""
+    def ln_bwd(dy, x_in, m, r, key, accumulate, want_h=True, bias_key=None, bias_scale=1.0):
+        """LayerNorm backward into the residual-gradient stream dX; also emits the GEMM-operand copy of dX and,
+        fused, the column sums of the new dX (= bias gradient `bias_key` of the next projection in the chain)."""
         dXh = _empty((N, D), TD, dev) if (bf16 and want_h) else None
-        ops.layernorm_bwd(dy, x_in, m, r, P[key + "weight"], dX, accumulate, G[key + "weight"], G[key + "bias"], dXh)
+        ops.layernorm_bwd(dy, x_in, m, r, P[key + "weight"], dX, accumulate, G[key + "weight"], G[key + "bias"], dXh,
+                          G[bias_key] if bias_key else None, bias_scale)
         return dXh if bf16 else dX
 
     # final LayerNorm
     dX = _empty((N, D), f32, dev)
-    dXh = ln_bwd(dY, t["x4"], t["m5"], t["r5"], pre + "final_layer_norm.", False)
+    dXh = ln_bwd(dY, t["x4"], t["m5"], t["r5"], pre + "final_layer_norm.", False, True, pre + "ffn2.sequential.4.bias", 0.5)
 
-    def ffn_bwd(tag, x_in, u, m, r, hpre, a, dXh, want_h):
+    def ffn_bwd(tag, x_in, u, m, r, hpre, a, dXh, want_h, next_bias=None):
         q = pre + tag + ".sequential."
         W1 = W.get(q + "1.weight", P[q + "1.weight"], (F, D))
         W2 = W.get(q + "4.weight", P[q + "4.weight"], (D, F))
-        wgrad(dXh, a, G[q + "4.weight"], N, D, F, alpha=0.5)
-        ops.colsum(dX, G[q + "4.bias"], N, D, scale=0.5)
+        wgrad(dXh, a, G[q + "4.weight"], N, D, F, alpha=0.5)     # (this FFN's output-bias grad came fused from ln_bwd)
         dh = _empty((N, F), TD, dev)
         dgrad(dXh, W2, dh, N, D, F, act=ACT_DSILU, preact=hpre, alpha=0.5)
         wgrad(dh, u, G[q + "1.weight"], N, F, D)
         ops.colsum(dh, G[q + "1.bias"], N, F)
         du = _empty((N, D), f32, dev)
         dgrad(dh, W1, du, N, F, D)
-        return ln_bwd(du, x_in, m, r, q + "0.", True, want_h)
+        return ln_bwd(du, x_in, m, r, q + "0.", True, want_h, next_bias)
 
     # FFN2: x4 = x3 + 0.5*FFN(u4), u4 = LN(x3)
-    dXh = ffn_bwd("ffn2", t["x3"], t["u4"], t["m4"], t["r4"], t["h2pre"], t["a2"], dXh, True)
+    dXh = ffn_bwd("ffn2", t["x3"], t["u4"], t["m4"], t["r4"], t["h2pre"], t["a2"], dXh, True, c + "sequential.5.bias")
 
     # conv module: x3 = x2 + pw2(s) + b
     Wp1 = W.get(c + "sequential.0.weight", P[c + "sequential.0.weight"], (2 * D, D))
     Wp2 = W.get(c + "sequential.5.weight", P[c + "sequential.5.weight"], (D, D))
     wgrad(dXh, t["s"], G[c + "sequential.5.weight"].view(D, D), N, D, D)
-    ops.colsum(dX, G[c + "sequential.5.bias"], N, D)
     ds = _empty((N, D), TD, dev)
     dgrad(dXh, Wp2, ds, N, D, D)
     dc = _empty((N, D), f32, dev)
@@ -255,13 +255,12 @@ def layer_backward(P, W: Operands, G: Dict[str, Tensor], pre: str, t: dict, dY: 
     ops.colsum(dz, G[c + "sequential.0.bias"], N, 2 * D)
     du3 = _empty((N, D), f32, dev)
     dgrad(dz, Wp1, du3, N, 2 * D, D)
-    dXh = ln_bwd(du3, t["x2"], t["m3"], t["r3"], c + "layer_norm.", True)
+    dXh = ln_bwd(du3, t["x2"], t["m3"], t["r3"], c + "layer_norm.", True, True, pre + "self_attn.out_proj.bias")
 
     # MHSA: x2 = x1 + out_proj(attn(qkv)) ; qkv = in_proj(u2); u2 = LN(x1)
     Wqkv = W.get(pre + "self_attn.in_proj_weight", P[pre + "self_attn.in_proj_weight"], (3 * D, D))
     Wo = W.get(pre + "self_attn.out_proj.weight", P[pre + "self_attn.out_proj.weight"], (D, D))
     wgrad(dXh, t["ctx"], G[pre + "self_attn.out_proj.weight"], N, D, D)
-    ops.colsum(dX, G[pre + "self_attn.out_proj.bias"], N, D)
     dctx = _empty((N, D), TD, dev)
     dgrad(dXh, Wo, dctx, N, D, D)
     dqkv = _empty((N, 3 * D), TD, dev)
@@ -272,7 +271,7 @@ def layer_backward(P, W: Operands, G: Dict[str, Tensor], pre: str, t: dict, dY: 
     ops.colsum(dqkv, G[pre + "self_attn.in_proj_bias"], N, 3 * D)
     du2 = _empty((N, D), f32, dev)
     dgrad(dqkv, Wqkv, du2, N, 3 * D, D)
-    dXh = ln_bwd(du2, t["x1"], t["m2"], t["r2"], pre + "self_attn_layer_norm.", True)
+    dXh = ln_bwd(du2, t["x1"], t["m2"], t["r2"], pre + "self_attn_layer_norm.", True, True, pre + "ffn1.sequential.4.bias", 0.5)
 
     # FFN1
     ffn_bwd("ffn1", t["x"], t["u1"], t["m1"], t["r1"], t["h1pre"], t["a1"], dXh, False)

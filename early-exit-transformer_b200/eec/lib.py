@@ -43,7 +43,7 @@ class GemmDesc(C.Structure):
 _SIGS = {
     "eec_gemm": [C.POINTER(GemmDesc), vp],
     "eec_layernorm_fwd": [vp, vp, vp, vp, i32, vp, vp, i32, i32, vp],
-    "eec_layernorm_bwd": [vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, i32, i32, vp],
+    "eec_layernorm_bwd": [vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, f32, i32, i32, vp],
     "eec_attn_fwd": [vp, i32, vp, vp, vp, i32, i32, i32, i32, vp],
     "eec_attn_bwd": [vp, vp, vp, i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp],
     "eec_dwconv_bn_silu_eval": [vp, i32, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp],

@@ -65,10 +65,10 @@ def layernorm_fwd(x, gamma, beta, out, mean=None, rstd=None):
     call("eec_layernorm_fwd", ptr(x), ptr(gamma), ptr(beta), ptr(out), dt(out), ptr(mean), ptr(rstd), rows, 256, stream())
 
 
-def layernorm_bwd(dy, x, mean, rstd, gamma, dx, accumulate, dgamma, dbeta, dx_bf16=None):
+def layernorm_bwd(dy, x, mean, rstd, gamma, dx, accumulate, dgamma, dbeta, dx_bf16=None, dx_colsum=None, colsum_scale=1.0):
     rows = x.numel() // 256
     call("eec_layernorm_bwd", ptr(dy), ptr(x), ptr(mean), ptr(rstd), ptr(gamma), ptr(dx), int(accumulate), ptr(dgamma),
-         ptr(dbeta), ptr(dx_bf16), rows, 256, stream())
+         ptr(dbeta), ptr(dx_bf16), ptr(dx_colsum), colsum_scale, rows, 256, stream())
 
 
 def attn_fwd(qkv, key_len, ctx, lse, B, T, H):

@@ -84,10 +84,13 @@ int eec_gemm(const eec_gemm_desc* d, eec_stream_t stream);
 int eec_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* out, int out_dtype,
                       float* mean, float* rstd, int rows, int d, eec_stream_t stream);
 /* dx (+)= LN'(dy); dgamma += sum dy*xhat; dbeta += sum dy  (dgamma/dbeta accumulate);
- * dx_bf16 (optional): bf16 copy of the final dx (operand of the next dgrad/wgrad GEMM) */
+ * dx_bf16 (optional): bf16 copy of the final dx (operand of the next dgrad/wgrad GEMM);
+ * dx_colsum (optional): dx_colsum[c] += colsum_scale * sum_rows dx[:,c]  (the bias gradient of the
+ * projection that precedes this LayerNorm's residual branch in the forward pass) */
 int eec_layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd,
                       const float* gamma, float* dx, int dx_accumulate, float* dgamma, float* dbeta,
-                      void* dx_bf16, int rows, int d, eec_stream_t stream);
+                      void* dx_bf16, float* dx_colsum, float colsum_scale, int rows, int d,
+                      eec_stream_t stream);
 
 /* ---- multi-head self-attention core (nn.MultiheadAttention SDPA branch, TA:194-200) -
  * qkv [B*T, 3*H*dh] rows = [q | k | v], head h = columns [h*dh, (h+1)*dh) of each third.

@@ -1,0 +1,133 @@
+"""CPU tests: C-ABI surface (load + every declared symbol, no compute), host-side mirror of the reference
+interface, and the world_size-2 data-parallel exchange step over gloo."""
+import ctypes
+import os
+import re
+import socket
+
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    import eec
+    lib = eec.load()
+    header = open(os.path.join(ROOT, "include", "eec.h")).read()
+    declared = set(re.findall(r"\b(eec_[a-z0-9_]+)\s*\(", header))
+    declared -= {"eec_gemm_desc"}
+    assert len(declared) >= 35
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/eec.h but not exported by libeec.so"
+    assert set(eec.EXPORTS) <= declared
+    assert lib.eec_version() >= 100
+    assert isinstance(lib.eec_last_error(), bytes)
+    # struct layout the Python side marshals must match the C side (size check against the header's field list)
+    from eec.lib import GemmDesc
+    assert ctypes.sizeof(GemmDesc) % 8 == 0 and ctypes.sizeof(GemmDesc) >= 200
+
+
+def test_module_mirror_matches_reference_state_dict_layout():
+    import eec
+    from oracle import conformer_oracle as O
+    kw = dict(src_pad_idx=0, n_enc_exits=6, enc_voc_size=256, dec_voc_size=256, d_model=256, n_head=8, max_len=2000,
+              d_feed_forward=2048, n_enc_layers=2, features_length=80, drop_prob=0.1, depthwise_kernel_size=31, device="cpu")
+    m = eec.Early_conformer(**kw)
+    sd = m.state_dict()
+    assert len(sd) == 413 and sum(p.numel() for p in m.parameters()) == 31536128
+    ref = O.make_params(0)
+    assert set(ref) == set(sd) and all(tuple(ref[k].shape) == tuple(sd[k].shape) for k in sd)
+    assert sd["conformer.0.conformer_layers.0.conv_module.sequential.3.num_batches_tracked"].dtype == torch.int64
+    s = eec.Splitformer(**kw)
+    assert len(s.state_dict()) == 479
+    with pytest.raises(eec.EecError):
+        m.eval()(torch.zeros(1, 80, 100), torch.tensor([100]))    # no CPU fallback: fails loudly
+    with pytest.raises(ValueError):
+        eec.Early_conformer(**{**kw, "depthwise_kernel_size": 30})
+    with pytest.raises(AssertionError):
+        eec.Early_conformer(**{**kw, "n_head": 6})
+
+
+def test_same_seed_same_init_as_torch_containers():
+    """Construction order mirrors the reference, so a fixed seed gives identical default weights."""
+    import eec
+    kw = dict(src_pad_idx=0, n_enc_exits=2, enc_voc_size=256, dec_voc_size=256, d_model=256, n_head=8, max_len=100,
+              d_feed_forward=2048, n_enc_layers=1, features_length=80, drop_prob=0.0, depthwise_kernel_size=31, device="cpu")
+    torch.manual_seed(0)
+    a = eec.Early_conformer(**kw).state_dict()
+    torch.manual_seed(0)
+    b = eec.Early_conformer(**kw).state_dict()
+    assert all(torch.equal(a[k], b[k]) for k in a)
+    torchaudio = pytest.importorskip("torchaudio")
+    torch.manual_seed(0)
+    # the reference's constructor sequence: conv_subsample, pos-enc, linears, then torchaudio Conformers
+    _ = [torch.nn.Conv1d(80, 256, 3, 2), torch.nn.Conv1d(256, 256, 3, 2)]
+    _ = [torch.nn.Linear(256, 256) for _ in range(2)]
+    ta = torchaudio.models.Conformer(input_dim=256, num_heads=8, ffn_dim=2048, num_layers=1, depthwise_conv_kernel_size=31)
+    tsd = ta.state_dict()
+    for k, v in tsd.items():
+        assert torch.equal(a["conformer.0." + k], v), k
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _dp_worker(rank, world, port, q):
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "early-exit-transformer_b200"))
+    import torch.distributed as dist
+    from eec import distributed as D
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    # a model whose grads live in one flat buffer, exactly as engine.model_backward leaves them
+    torch.manual_seed(1)
+    model = torch.nn.Sequential(torch.nn.Linear(8, 4), torch.nn.LayerNorm(4))
+    if rank == 1:
+        for p in model.parameters():
+            p.data.add_(1.0)
+    D.broadcast_parameters(model, 0)
+    names = [n for n, _ in model.named_parameters()]
+    total = sum(p.numel() for p in model.parameters())
+    flat = torch.arange(total, dtype=torch.float32) * (rank + 1)
+    off = 0
+    for p in model.parameters():
+        p.grad = flat[off:off + p.numel()].view_as(p)
+        off += p.numel()
+    model.__dict__["_flat_grad"] = flat
+    D.all_reduce_gradients(model)
+    lo, hi = D.shard_range(7, rank, world)
+    q.put((rank, flat.tolist(), [p.detach().reshape(-1).tolist() for p in model.parameters()], (lo, hi), names))
+    dist.destroy_process_group()
+
+
+def test_data_parallel_exchange_world2_gloo():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_dp_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda x: x[0])
+    for p in procs:
+        p.join(30)
+        assert p.exitcode == 0
+    flat0, flat1 = torch.tensor(res[0][1]), torch.tensor(res[1][1])
+    expect = torch.arange(flat0.numel(), dtype=torch.float32) * 1.5      # mean of 1x and 2x
+    assert torch.allclose(flat0, expect) and torch.allclose(flat1, expect)
+    for a, b in zip(res[0][2], res[1][2]):
+        assert a == b                                                     # broadcast made the replicas identical
+    assert res[0][3] == (0, 4) and res[1][3] == (4, 7)                    # utterance sharding covers [0,7) once
+
+
+def test_shard_batch_partitions_every_utterance_once():
+    from eec import distributed as D
+    x = torch.arange(10)
+    parts = [D.shard_batch([x], r, 4)[0] for r in range(4)]
+    assert torch.equal(torch.cat(parts), x) and max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
