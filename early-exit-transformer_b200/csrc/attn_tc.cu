@@ -29,7 +29,13 @@ constexpr uint32_t TMEM_COLS = 256;
 constexpr uint32_t S_COL = 0, O_COL = 128;
 constexpr uint32_t SW64 = 4, SW128 = 2;
 
-__global__ void __launch_bounds__(AT_THREADS) attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv,
+__device__ __forceinline__ float ex2_fast(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__global__ void __launch_bounds__(AT_THREADS, 2) attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv,
                                                                  const int32_t* __restrict__ key_len,
                                                                  __nv_bfloat16* __restrict__ ctx, float* __restrict__ lse,
                                                                  int T, int H) {
@@ -123,28 +129,41 @@ __global__ void __launch_bounds__(AT_THREADS) attn_fwd_tc_kernel(const __grid_co
     for (int i = 0; i < DHEAD; ++i) o[i] = 0.f;
     float v[32];
     for (int j = 0; j < nblk; ++j) {
-      const int kbase = j * KB;
+      const int nvalid = min(KB, klen - j * KB);   // only the last key block can be partial
       mbar_wait(s_full, j & 1);
       tc_fence_after();
-      // pass 1: row max over the valid keys of this block
-      float mx = m_run;
-#pragma unroll
+      // pass 1: row max (raw scores; the positive scale is applied once) over the valid keys of this block
+      float mraw = -INFINITY;
+#pragma unroll 1
       for (int c0 = 0; c0 < KB; c0 += 32) {
+        if (c0 >= nvalid) break;               // uniform
         tmem_ld32(trow + S_COL + c0, v);
+        if (c0 + 32 <= nvalid) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (kbase + c0 + i < klen) mx = fmaxf(mx, v[i] * sc);
+          for (int i = 0; i < 32; ++i) mraw = fmaxf(mraw, v[i]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c0 + i < nvalid) mraw = fmaxf(mraw, v[i]);
+        }
       }
-      // pass 2: p = exp2(s - mx), row sum, bf16 P tile in swizzled smem
+      const float mx = fmaxf(m_run, mraw * sc);
+      // pass 2: p = exp2(s*sc - mx), row sum, bf16 P tile in swizzled smem
       float psum = 0.f;
-#pragma unroll
+#pragma unroll 1
       for (int c0 = 0; c0 < KB; c0 += 32) {
-        tmem_ld32(trow + S_COL + c0, v);
+        if (c0 < nvalid) {
+          tmem_ld32(trow + S_COL + c0, v);
+          if (c0 + 32 <= nvalid) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float p = (kbase + c0 + i < klen) ? exp2f(v[i] * sc - mx) : 0.f;
-          psum += p;
-          v[i] = p;
+            for (int i = 0; i < 32; ++i) { v[i] = ex2_fast(fmaf(v[i], sc, -mx)); psum += v[i]; }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) { v[i] = (c0 + i < nvalid) ? ex2_fast(fmaf(v[i], sc, -mx)) : 0.f; psum += v[i]; }
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = 0.f;
         }
         uint8_t* prow = sP + (c0 >> 6) * 16384 + r * 128;
 #pragma unroll
@@ -161,7 +180,7 @@ __global__ void __launch_bounds__(AT_THREADS) attn_fwd_tc_kernel(const __grid_co
       mbar_arrive(s_free);
       fence_proxy_async();
       mbar_arrive(p_full);
-      const float corr = (m_run == -INFINITY) ? 0.f : exp2f(m_run - mx);
+      const float corr = (m_run == -INFINITY) ? 0.f : ex2_fast(m_run - mx);
       l_run = l_run * corr + psum;
       m_run = mx;
       mbar_wait(o_full, j & 1);
