@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(256, 3) dwconv_kernel(const TI* __restrict__ g
 // dW[ch][j] += sum_{b,t} dc[b,t,ch] * g[b,t+j-15,ch];  dbias[ch] += sum dc
 // grid (WG_SPLIT, B): a block walks every WG_SPLIT-th time tile of its utterance and issues its 31 x 256
 // atomics once at the end (contention per address = WG_SPLIT * B instead of tiles * B).
-constexpr int WG_SPLIT = 3;
+constexpr int WG_SPLIT = 6;
 template <typename TI>
 __global__ void __launch_bounds__(256, 3) dwconv_wgrad_kernel(const float* __restrict__ dc, const TI* __restrict__ g,
                                                            float* __restrict__ dw, float* __restrict__ dbias, int T, int C) {

@@ -10,7 +10,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libeec.so")
+LIB_PATH = os.environ.get("EEC_LIB") or os.path.join(_HERE, "libeec.so")   # EEC_LIB: A/B-test another build of the same ABI
 
 F32, BF16 = 0, 1
 ACT_NONE, ACT_SILU, ACT_GLU, ACT_DSILU = 0, 1, 2, 3
@@ -42,6 +42,7 @@ class GemmDesc(C.Structure):
 # name -> argtypes (stream last); every function returns int unless noted
 _SIGS = {
     "eec_gemm": [C.POINTER(GemmDesc), vp],
+    "eec_ffn_fwd": [vp, vp, vp, vp, vp, vp, f32, vp, vp, vp, vp, i32, vp, vp, vp, i32, i32, i32, vp],
     "eec_layernorm_fwd": [vp, vp, vp, vp, i32, vp, vp, i32, i32, vp],
     "eec_layernorm_bwd": [vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, f32, i32, i32, vp],
     "eec_attn_fwd": [vp, i32, vp, vp, vp, i32, i32, i32, i32, vp],

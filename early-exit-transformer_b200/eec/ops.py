@@ -60,6 +60,15 @@ def gemm(
     call("eec_gemm", C.byref(d), stream())
 
 
+def ffn_fwd(u, w1, b1, w2, b2, residual, alpha, ln_gamma, ln_beta, x_out, ln_out, ln_mean=None, ln_rstd=None, hpre=None):
+    """Fused feed-forward module + following LayerNorm (include/eec.h::eec_ffn_fwd); bf16 operands."""
+    for t, n in ((u, "u"), (w1, "w1"), (w2, "w2"), (residual, "residual"), (x_out, "x_out"), (ln_out, "ln_out")):
+        _chk(t, "ffn_fwd." + n)
+    rows, f = u.numel() // 256, w1.shape[0]
+    call("eec_ffn_fwd", ptr(u), ptr(w1), ptr(b1), ptr(w2), ptr(b2), ptr(residual), alpha, ptr(ln_gamma), ptr(ln_beta),
+         ptr(x_out), ptr(ln_out), dt(ln_out), ptr(ln_mean), ptr(ln_rstd), ptr(hpre), rows, 256, f, stream())
+
+
 def layernorm_fwd(x, gamma, beta, out, mean=None, rstd=None):
     rows = x.numel() // 256
     call("eec_layernorm_fwd", ptr(x), ptr(gamma), ptr(beta), ptr(out), dt(out), ptr(mean), ptr(rstd), rows, 256, stream())

@@ -70,12 +70,43 @@ if "gemm" in which:
     du = torch.empty(N, 256, device=dev)
     report("dgrad [N,2048]x[2048,256] fp32 out", timeit(lambda: ops.gemm(a2048, w[(2048, 256)], du, N, 256, 2048, a_kmajor=True, b_kmajor=False, lda=2048, ldb=256)), 2.0 * N * 2048 * 256)
 
+if "ffn" in which:
+    uu = bf(N, 256); w1 = bf(2048, 256, scale=0.05); w2 = bf(256, 2048, scale=0.02)
+    b1 = torch.randn(2048, device=dev) * 0.1; b2 = torch.randn(256, device=dev) * 0.1
+    xin = torch.randn(N, 256, device=dev); xo = torch.empty_like(xin); lo = torch.empty(N, 256, device=dev, dtype=torch.bfloat16)
+    g = 1 + 0.1 * torch.randn(256, device=dev); b_ = 0.1 * torch.randn(256, device=dev)
+    hp = torch.empty(N, 2048, device=dev, dtype=torch.bfloat16)
+    fl = 4.0 * N * 2048 * 256
+    report("ffn fused fwd (inference: no pre-activation store)", timeit(lambda: ops.ffn_fwd(uu, w1, b1, w2, b2, xin, 0.5, g, b_, xo, lo)), fl)
+    report("ffn fused fwd (training: + bf16 pre-activation store)", timeit(lambda: ops.ffn_fwd(uu, w1, b1, w2, b2, xin, 0.5, g, b_, xo, lo, hpre=hp)), fl)
+    # reference: plain torch in fp32 on the same bf16-rounded operands
+    h = uu.float() @ w1.float().t() + b1
+    a = (h * torch.sigmoid(h)).to(torch.bfloat16).float()
+    xr = xin + 0.5 * (a @ w2.float().t() + b2)
+    lr = torch.nn.functional.layer_norm(xr, (256,), g, b_, 1e-5)
+    print("   max|x_out - ref| = %.3e (ref max %.3e)   max|ln - ref| = %.3e   max|hpre - ref| = %.3e" % (
+        (xo - xr).abs().max().item(), xr.abs().max().item(), (lo.float() - lr).abs().max().item(), (hp.float() - h).abs().max().item()), flush=True)
+
 if "conv" in which:
     gg = bf(B, T, 256); wdw = torch.randn(256, 31, device=dev) * 0.1; z = torch.zeros(256, device=dev); one = torch.ones(256, device=dev)
     out = torch.empty(B, T, 256, device=dev, dtype=torch.bfloat16)
     report("dwconv+BN+SiLU eval (bf16)", timeit(lambda: ops.dwconv_bn_silu_eval(gg, wdw, z, one, z, z, one, out, B, T, 31)), None, N * 256 * 4)
     c = torch.empty(N, 256, device=dev); sums = torch.zeros(512, dtype=torch.float64, device=dev)
     report("dwconv + stats (train pass A)", timeit(lambda: ops.dwconv_stats(gg, wdw, z, c, sums, B, T, 31)), None, N * 256 * 6)
+
+    dc = torch.randn(N, 256, device=dev); dg = torch.empty(N, 256, device=dev, dtype=torch.bfloat16)
+    dw = torch.zeros(256, 31, device=dev); dbias = torch.zeros(256, device=dev)
+    report("dwconv bwd (data + wgrad, 2 launches)", timeit(lambda: ops.dwconv_bwd(dc, gg, wdw, dg, dw, dbias, B, T, 31)), None, N * 256 * (4 + 2 + 4 + 2))
+    s_ = torch.empty(N, 256, device=dev, dtype=torch.bfloat16); sm = torch.empty(256, device=dev); sr = torch.empty(256, device=dev)
+    rm = torch.zeros(256, device=dev); rv = torch.ones(256, device=dev); nbt = torch.zeros((), dtype=torch.int64, device=dev)
+    sums.zero_(); ops.dwconv_stats(gg, wdw, z, c, sums, B, T, 31)
+    report("bn_silu_train", timeit(lambda: ops.bn_silu_train(c, sums, one, z, rm, rv, nbt, 0.1, sm, sr, s_)), None, N * 256 * 6)
+    sums2 = torch.zeros(512, dtype=torch.float64, device=dev); dgam = torch.zeros(256, device=dev); dbet = torch.zeros(256, device=dev)
+    def bnb():
+        sums2.zero_(); ops.bn_silu_bwd(dg, c, sm, sr, one, z, sums2, dc, dgam, dbet)
+    report("bn_silu_bwd (stats + apply, 2 launches + memset)", timeit(bnb), None, N * 256 * (6 + 6 + 4))
+    zz = bf(N, 512); dz = torch.empty_like(zz)
+    report("glu_bwd", timeit(lambda: ops.glu_bwd(zz, dg, dz)), None, N * 256 * (4 + 2 + 4))
 
 if "ln" in which:
     x = torch.randn(N, 256, device=dev); g = torch.ones(256, device=dev); b_ = torch.zeros(256, device=dev)
