@@ -51,7 +51,7 @@ struct P2 {
   int accumulate;
   const float* ln_gamma; const float* ln_beta; float* ln_mean; float* ln_rstd;
   int32_t* argmax; float* entropy;
-  int debug;   // EEC_GEMM_DEBUG bitmask (perf triage only): 1 = skip bulk store issue, 2 = skip staging entirely, 4 = skip activation math
+  int debug;   // EEC_GEMM_DEBUG bitmask (perf triage only): 1 = skip bulk store issue, 2 = skip staging entirely, 4 = skip activation math, 8 = no operand TMA, 16 = no MMA issue
 };
 
 template <bool A_KMAJ, bool B_KMAJ, int EPI, int CS>
@@ -108,6 +108,7 @@ __global__ void __launch_bounds__(NT2, 1) gemm_tc2_kernel(const __grid_constant_
           mbar_wait(&empty_bar[s], ((it / NSTAGE) & 1) ^ 1);
           uint8_t* sa = smem + s * STAGE_BYTES;
           uint8_t* sb = sa + A_BYTES;
+          if (p.debug & 8) { mbar_arrive(&full_bar[s]); continue; }
           mbar_expect_tx(&full_bar[s], STAGE_BYTES);
           const int k = kb * BK;
           if (A_KMAJ) {
@@ -164,6 +165,7 @@ __global__ void __launch_bounds__(NT2, 1) gemm_tc2_kernel(const __grid_constant_
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
           const uint32_t sb = sa + A_BYTES;
+          if (!(p.debug & 16))
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             const uint64_t ad = A_KMAJ ? make_smem_desc(sa + k * 32, 0, 1024) : make_smem_desc(sa + k * 2048, 8192, 1024);
@@ -455,6 +457,12 @@ int gemm_tc2(const eec_gemm_desc* d, cudaStream_t st, int32_t* argmax, float* en
   if (d->act == EEC_ACT_SILU && d->preact) EEC_CHECK_ARG(d->preact_dtype == EEC_BF16, "gemm_tc2: preact store must be bf16");
   if (d->accumulate) EEC_CHECK_ARG(d->out_dtype == EEC_F32 && d->act == EEC_ACT_NONE, "gemm_tc2: accumulate needs fp32 C, no act");
 
+  {
+    // GENERIC / GLU epilogues run on the v3 kernel (16 epilogue warps, warp-private staging); EEC_GEMM_V2=1 keeps v2 for A/B runs
+    static int v2_env = -1;
+    if (v2_env < 0) { const char* e = getenv("EEC_GEMM_V2"); v2_env = (e && e[0] == '1') ? 1 : 0; }
+    if (!v2_env && (epi == EPI_GENERIC || epi == EPI_GLU)) return gemm_tc3(d, st);
+  }
   if (!g_num_sms) {
     int dev = 0;
     EEC_CUDA(cudaGetDevice(&dev));

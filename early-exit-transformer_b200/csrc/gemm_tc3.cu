@@ -1,0 +1,502 @@
+// gemm_tc3.cu -- persistent bf16 tcgen05 GEMM, v3 epilogue: 16 epilogue warps with warp-private TMA staging.
+//
+//   C[M,N] = epi( A(m,k) * B(n,k) )        128 x 256 tile, BLOCK_K = 64, one CTA per SM, static tile loop
+//
+//   warp 0       : TMA producer (3-stage 128B-swizzled smem ring, runs ahead across tiles)
+//   warp 1       : tcgen05.mma issuer; TWO 256-column TMEM accumulators (tile t+1's main loop overlaps tile t's epilogue)
+//   warps 2..17  : epilogue; quarter = warp%4 selects the TMEM lane quarter (row = quarter*32 + lane),
+//                  column group = (warp-2)/4 selects accumulator columns [cg*64, cg*64+64)
+//
+// What changed against v2 (measured there: the epilogue skeleton alone cost ~2.5 us per tile, more than the tile's MMAs):
+//   * every epilogue warp owns a 4 KB staging buffer and issues its own [32 rows x 32 cols] bulk tensor stores:
+//     no named barriers between warps, only __syncwarp + one proxy fence per box;
+//   * both 32-column slabs of a warp are read from TMEM by back-to-back tcgen05.ld with ONE wait, and the
+//     accumulator is handed back to the MMA warp right after that read (before any math or store);
+//   * the bias vector lives in shared memory for the whole kernel (no per-tile global load + block barrier);
+//   * dSiLU reads its bf16 pre-activation through TMA loads issued before the accumulator wait (full-line reads,
+//     latency hidden behind the main loop) instead of row-strided per-thread global loads;
+//   * split-K accumulation leaves through cp.reduce.async.bulk.tensor (fp32 add in L2) instead of per-thread red.v4.
+//
+// Epilogue modes
+//   EPI_GENERIC    bias, SiLU (+ optional bf16 pre-activation store) / dSiLU (reads bf16 pre-activation),
+//                  alpha, fp32 (row-periodic) residual, bf16|fp32 out, or fp32 reduce-add (split-K wgrad)
+//   EPI_GLU        B rows [n0,n0+128) | [N/2+n0,+128): out = alpha * a * sigmoid(g) (+ optional z store)
+// (the row-wise LayerNorm / log-softmax epilogues stay in gemm_tc2.cu)
+#include <stdlib.h>
+#include "tc_common.cuh"
+
+namespace eec {
+namespace {
+using namespace tc;
+
+constexpr int BM = 128, BN = 256, BK = 64, NSTAGE = 3;
+constexpr int A_BYTES = BM * BK * 2;              // 16 KB
+constexpr int B_BYTES = BN * BK * 2;              // 32 KB
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;    // 48 KB
+constexpr int NEW = 16;                           // epilogue warps
+constexpr int WBUF = 4096;                        // staging bytes per epilogue warp: one fp32 box or two bf16 boxes
+constexpr int OFF_STG = NSTAGE * STAGE_BYTES;
+constexpr int MAX_BIAS = 2048;
+constexpr int OFF_BIAS = OFF_STG + NEW * WBUF;    // float[MAX_BIAS]
+constexpr int OFF_BAR = OFF_BIAS + MAX_BIAS * 4;
+constexpr int SMEM3_BYTES = OFF_BAR + 512 + 1024;
+constexpr int NT3 = 64 + NEW * 32;                // 576
+
+enum { EPI_GENERIC = 0, EPI_GLU = 1 };
+
+struct P3 {
+  int M, N, K;
+  int m_tiles, n_tiles, splits, kb_per_split;
+  const float* bias;
+  int act;
+  float alpha;
+  const float* residual; int ldr; int res_row_mod;
+  int out_bf16, has_pre, accumulate;
+  int debug;       // EEC_GEMM_DEBUG bitmask (perf triage only): 1 = no bulk store issue, 2 = no staging, 4 = no activation math
+  long long* tl;   // EEC_GEMM_TL=1 (perf triage only): clock64 accumulators of CTA 0, see gemm_tc3()
+};
+
+// per-warp staging: values -> swizzled smem box -> bulk tensor store / reduce of a [32 rows x 32 cols] box
+struct WStager {
+  uint8_t* buf;
+  int lane;
+  int sub;        // next bf16 sub-buffer (2 KB each)
+  bool pend_f32;  // the newest outstanding bulk group reads the whole 4 KB buffer
+  int debug;      // EEC_GEMM_DEBUG (perf triage only): 1 = no bulk store issue, 2 = no staging at all
+
+  __device__ __forceinline__ void store_bf16(const CUtensorMap* tm, int x, int y, const float (&v)[32]) {
+    if (debug & 2) return;
+    if (lane == 0) {
+      if (pend_f32) bulk_wait_read<0>();
+      else bulk_wait_read<1>();   // the group before the newest one used this sub-buffer
+    }
+    __syncwarp();
+    uint8_t* b = buf + sub * 2048;
+    uint8_t* row = b + lane * 64;
+    const int sw = (lane >> 1) & 3;
+    if (!(debug & 16))
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      uint4 u;
+      __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(v[g * 8 + 2 * e], v[g * 8 + 2 * e + 1]);
+      *reinterpret_cast<uint4*>(row + ((g ^ sw) << 4)) = u;
+    }
+    if (!(debug & 8)) fence_proxy_async();
+    __syncwarp();
+    if (lane == 0 && !(debug & 1)) {
+      tma_store_2d(tm, b, x, y);
+      bulk_commit();
+    }
+    sub ^= 1;
+    pend_f32 = false;
+  }
+  template <bool REDUCE>
+  __device__ __forceinline__ void store_f32(const CUtensorMap* tm, int x, int y, const float (&v)[32]) {
+    if (debug & 2) return;
+    if (lane == 0) bulk_wait_read<0>();
+    __syncwarp();
+    uint8_t* row = buf + lane * 128;
+    const int sw = lane & 7;
+#pragma unroll
+    for (int g = 0; g < 8; ++g)
+      *reinterpret_cast<float4*>(row + ((g ^ sw) << 4)) = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0 && !(debug & 1)) {
+      if (REDUCE) tma_reduce_add_2d(tm, buf, x, y);
+      else tma_store_2d(tm, buf, x, y);
+      bulk_commit();
+    }
+    pend_f32 = true;
+  }
+};
+
+__device__ __forceinline__ void add_bias32(float (&v)[32], const float* b) {
+  const float4* bp = reinterpret_cast<const float4*>(b);   // warp-uniform address: smem broadcast
+#pragma unroll
+  for (int g = 0; g < 8; ++g) {
+    const float4 f = bp[g];
+    v[g * 4] += f.x; v[g * 4 + 1] += f.y; v[g * 4 + 2] += f.z; v[g * 4 + 3] += f.w;
+  }
+}
+// v[j] *= dSiLU(h[j]) with h = this lane's row (32 bf16) of a 64B-swizzled [32 x 32] bf16 box
+__device__ __forceinline__ void mul_dsilu32(float (&v)[32], const uint8_t* box, int lane) {
+  const uint8_t* row = box + lane * 64;
+  const int sw = (lane >> 1) & 3;
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const uint4 u = *reinterpret_cast<const uint4*>(row + ((g ^ sw) << 4));
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 f = __bfloat1622float2(h[e]);
+      const float s0 = sigmoid_fast(f.x), s1 = sigmoid_fast(f.y);
+      v[g * 8 + 2 * e] *= s0 * fmaf(f.x, 1.0f - s0, 1.0f);
+      v[g * 8 + 2 * e + 1] *= s1 * fmaf(f.y, 1.0f - s1, 1.0f);
+    }
+  }
+}
+
+template <bool A_KMAJ, bool B_KMAJ, int EPI>
+__global__ void __launch_bounds__(NT3, 1) gemm_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                                                          const __grid_constant__ CUtensorMap tmC,   // main output (box 32 x 32)
+                                                          const __grid_constant__ CUtensorMap tmP,   // bf16 pre-activation: store (SiLU/GLU) or load (dSiLU)
+                                                          const P3 p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  float* bias_s = reinterpret_cast<float*>(smem + OFF_BIAS);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+  uint64_t* empty_bar = full_bar + NSTAGE;
+  uint64_t* tfull_bar = empty_bar + NSTAGE;   // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;       // [2]
+  uint64_t* load_bar = tempty_bar + 2;        // [NEW] per-warp pre-activation loads
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(load_bar + NEW);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  auto gtime = [] { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return (long long)t; };
+#ifndef EEC_GEMM_TIMELINE
+  (void)gtime;
+#endif
+  if (p.tl && blockIdx.x == 0 && threadIdx.x == 0) p.tl[8] = gtime();
+  const int tiles = p.m_tiles * p.n_tiles;
+  const int n_units = tiles * p.splits;
+  const int total_kb = (p.K + BK - 1) / BK;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmC);
+    for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], NEW); }
+    for (int w = 0; w < NEW; ++w) mbar_init(&load_bar[w], 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_ptr_smem, 512); tmem_relinquish(); }
+  if (p.bias) {
+    for (int i = threadIdx.x; i < p.N; i += NT3) bias_s[i] = p.bias[i];
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  if (p.tl && blockIdx.x == 0 && threadIdx.x == 0) p.tl[9] = gtime();
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it = 0;  // global k-block counter (stage ring position)
+      for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+        const int tile = u % tiles, split = u / tiles;
+        const int m0 = (tile / p.n_tiles) * BM;
+        const int nt = tile % p.n_tiles;
+        const int n0 = (EPI == EPI_GLU) ? nt * 128 : nt * BN;
+        const int kb0 = split * p.kb_per_split, kb1 = min(total_kb, kb0 + p.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+          const int s = it % NSTAGE;
+          mbar_wait(&empty_bar[s], ((it / NSTAGE) & 1) ^ 1);
+          uint8_t* sa = smem + s * STAGE_BYTES;
+          uint8_t* sb = sa + A_BYTES;
+          mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+          const int k = kb * BK;
+          if (A_KMAJ) {
+            tma_load_2d(sa, &tmA, &full_bar[s], k, m0);
+          } else {
+            tma_load_2d(sa, &tmA, &full_bar[s], m0, k);
+            tma_load_2d(sa + 8192, &tmA, &full_bar[s], m0 + 64, k);
+          }
+          if (B_KMAJ) {
+            if (EPI == EPI_GLU) {
+              tma_load_2d(sb, &tmB, &full_bar[s], k, n0);
+              tma_load_2d(sb + 16384, &tmB, &full_bar[s], k, p.N / 2 + n0);
+            } else {
+              tma_load_2d(sb, &tmB, &full_bar[s], k, n0);
+            }
+          } else {
+#pragma unroll
+            for (int a = 0; a < BN / 64; ++a) tma_load_2d(sb + a * 8192, &tmB, &full_bar[s], n0 + a * 64, k);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, !A_KMAJ, !B_KMAJ);
+      uint32_t it = 0, ut = 0;
+#ifdef EEC_GEMM_TIMELINE
+      const bool prof = p.tl && blockIdx.x == 0;
+#else
+      constexpr bool prof = false;
+#endif
+      long long w_tempty = 0, w_full = 0, t_ = 0, t_begin = prof ? clock64() : 0;
+      for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++ut) {
+        const int split = u / tiles;
+        const int kb0 = split * p.kb_per_split, kb1 = min(total_kb, kb0 + p.kb_per_split);
+        const uint32_t acc = ut & 1;
+        if (prof) t_ = clock64();
+        mbar_wait(&tempty_bar[acc], ((ut >> 1) & 1) ^ 1);   // epilogue has read this accumulator out of TMEM
+        if (prof) w_tempty += clock64() - t_;
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+          const int s = it % NSTAGE;
+          if (prof) t_ = clock64();
+          mbar_wait(&full_bar[s], (it / NSTAGE) & 1);
+          if (prof) w_full += clock64() - t_;
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+          const uint32_t sb = sa + A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t ad = A_KMAJ ? make_smem_desc(sa + k * 32, 0, 1024) : make_smem_desc(sa + k * 2048, 8192, 1024);
+            const uint64_t bd = B_KMAJ ? make_smem_desc(sb + k * 32, 0, 1024) : make_smem_desc(sb + k * 2048, 8192, 1024);
+            umma_bf16(d_tmem, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[s]);
+        }
+        umma_commit(&tfull_bar[acc]);
+      }
+      if (prof) p.tl[10] = gtime();
+      if (prof) { p.tl[0] = clock64() - t_begin; p.tl[1] = w_tempty; p.tl[2] = w_full; p.tl[3] = ut; }
+    }
+  } else {
+    // ================================================================== epilogue warps
+    const int e = warp - 2;
+    const int q = warp & 3;
+    const int cg = e >> 2;
+    WStager st;
+    st.buf = smem + OFF_STG + e * WBUF;
+    st.lane = lane;
+    st.sub = 0;
+    st.pend_f32 = false;
+    st.debug = p.debug;
+    uint64_t* lbar = &load_bar[e];
+    uint32_t lphase = 0;
+    float v[32], w[32];
+    uint32_t ut = 0;
+#ifdef EEC_GEMM_TIMELINE
+    const bool prof = p.tl && blockIdx.x == 0 && e == 0 && lane == 0;
+    long long e_wait = 0, e_ld = 0, e_rest = 0, t0_ = 0, t1_ = 0, t2_ = 0;
+#define TL_STAMP(t) do { if (prof) t = clock64(); } while (0)
+#define TL_ACC(a, d) do { if (prof) a += (d); } while (0)
+#else
+#define TL_STAMP(t) do { } while (0)
+#define TL_ACC(a, d) do { } while (0)
+#endif
+    for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++ut) {
+      TL_STAMP(t0_); TL_ACC(e_rest, ut ? t0_ - t2_ : 0);
+      const int tile = u % tiles, split = u / tiles;
+      const int m0 = (tile / p.n_tiles) * BM;
+      const int nt = tile % p.n_tiles;
+      const int n0 = (EPI == EPI_GLU) ? nt * 128 : nt * BN;
+      const uint32_t acc = ut & 1;
+      const int row0 = m0 + q * 32;
+      const int m = row0 + lane;
+      const bool valid = m < p.M;
+      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
+      const bool first_split = (split == 0);
+
+      if (EPI == EPI_GENERIC) {
+        const int cb = cg * 64;
+        const int nb = n0 + cb;
+        const int nslab = (nb + 32 < p.N) ? 2 : (nb < p.N) ? 1 : 0;   // warp-uniform
+        if (p.act == EEC_ACT_DSILU && nslab && p.out_bf16) {
+          // pre-activation boxes for this warp's two slabs: in flight while the main loop of this tile runs
+          if (lane == 0) {
+            bulk_wait_read<0>();   // the previous tile's stores have finished reading the staging buffer
+            mbar_expect_tx(lbar, nslab * 2048);
+            tma_load_2d(st.buf, &tmP, lbar, nb, row0);
+            if (nslab == 2) tma_load_2d(st.buf + 2048, &tmP, lbar, nb + 32, row0);
+          }
+          __syncwarp();
+        }
+        mbar_wait(&tfull_bar[acc], (ut >> 1) & 1);
+        TL_STAMP(t1_); TL_ACC(e_wait, t1_ - t0_);
+        tc_fence_after();
+        // one 32-column slab at a time: 32 live accumulator registers keep the warp under the 96-register cap without spills
+#pragma unroll 1
+        for (int sl = 0; sl < 2; ++sl) {
+          const int n = nb + sl * 32;
+          tmem_ld32(trow + cb + sl * 32, v);
+          if (sl == 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[acc]);   // accumulator is in registers: the MMA warp may reuse it
+            TL_STAMP(t2_); TL_ACC(e_ld, t2_ - t1_);
+          }
+          if (sl >= nslab) continue;
+          if (first_split && p.bias) add_bias32(v, bias_s + n);
+          if (p.act == EEC_ACT_SILU) {
+            if (p.has_pre) st.store_bf16(&tmP, n, row0, v);
+            if (!(p.debug & 4)) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] *= sigmoid_fast(v[j]);
+            }
+          } else if (p.act == EEC_ACT_DSILU) {
+            if (!p.out_bf16) {   // fp32 output boxes fill the whole staging buffer: fetch this slab's pre-activation now (test-only path)
+              if (lane == 0) {
+                bulk_wait_read<0>();
+                mbar_expect_tx(lbar, 2048);
+                tma_load_2d(st.buf + sl * 2048, &tmP, lbar, n, row0);
+              }
+              __syncwarp();
+            }
+            if (sl == 0 || !p.out_bf16) {
+              mbar_wait(lbar, lphase);
+              lphase ^= 1;
+            }
+            mul_dsilu32(v, st.buf + sl * 2048, lane);
+          }
+          if (p.alpha != 1.0f) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] *= p.alpha;
+          }
+          if (p.residual && first_split && valid) {
+            const long rr = p.res_row_mod ? (m % p.res_row_mod) : m;
+            const float* rp = p.residual + rr * p.ldr + n;
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+              const float4 f = *reinterpret_cast<const float4*>(rp + g * 4);
+              v[g * 4] += f.x; v[g * 4 + 1] += f.y; v[g * 4 + 2] += f.z; v[g * 4 + 3] += f.w;
+            }
+          }
+          if (p.act == EEC_ACT_DSILU && p.out_bf16) {
+            // slab sl's output goes into the sub-buffer its own pre-activation came from (each lane rewrites the row it just read)
+            st.sub = sl;
+            st.pend_f32 = false;   // slab 0: nothing outstanding (lane 0 waited at tile start); slab 1: only slab 0's store from the other sub-buffer
+          }
+          if (p.accumulate) st.store_f32<true>(&tmC, n, row0, v);
+          else if (p.out_bf16) st.store_bf16(&tmC, n, row0, v);
+          else st.store_f32<false>(&tmC, n, row0, v);
+        }
+      } else {  // EPI_GLU: v = "a" half, w = gate half of the same 32 output channels
+        const int c = cg * 32;
+        mbar_wait(&tfull_bar[acc], (ut >> 1) & 1);
+        TL_STAMP(t1_); TL_ACC(e_wait, t1_ - t0_);
+        tc_fence_after();
+        tmem_ld32x2(trow + c, trow + 128 + c, v, w);
+        TL_STAMP(t2_); TL_ACC(e_ld, t2_ - t1_);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        if (p.bias) {
+          add_bias32(v, bias_s + n0 + c);
+          add_bias32(w, bias_s + p.N / 2 + n0 + c);
+        }
+        if (p.has_pre) {
+          st.store_bf16(&tmP, n0 + c, row0, v);
+          st.store_bf16(&tmP, p.N / 2 + n0 + c, row0, w);
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = p.alpha * v[j] * sigmoid_fast(w[j]);
+        if (p.out_bf16) st.store_bf16(&tmC, n0 + c, row0, v);
+        else st.store_f32<false>(&tmC, n0 + c, row0, v);
+      }
+    }
+#ifdef EEC_GEMM_TIMELINE
+    if (prof) { e_rest += clock64() - t2_; p.tl[4] = e_wait; p.tl[5] = e_ld; p.tl[6] = e_rest; }
+#endif
+    if (lane == 0) bulk_wait_all();
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+  if (p.tl && blockIdx.x == 0 && threadIdx.x == 32) p.tl[11] = gtime();
+}
+
+template <bool AK, bool BK_, int EPI>
+int launch3(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc_, const CUtensorMap& tp, const P3& p, int grid,
+            cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    EEC_CUDA(cudaFuncSetAttribute(gemm_tc3_kernel<AK, BK_, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM3_BYTES));
+    attr_set = true;
+  }
+  gemm_tc3_kernel<AK, BK_, EPI><<<grid, NT3, SMEM3_BYTES, st>>>(ta, tb, tc_, tp, p);
+  EEC_LAUNCH_CHECK();
+  return 0;
+}
+
+int g_sms3 = 0;
+
+}  // namespace
+
+// GENERIC / GLU epilogues of eec_gemm (bf16 operands); the caller (gemm_tc2) has validated the descriptor
+int gemm_tc3(const eec_gemm_desc* d, cudaStream_t st) {
+  const int epi = (d->act == EEC_ACT_GLU) ? EPI_GLU : EPI_GENERIC;
+  EEC_CHECK_ARG(!d->bias || d->N <= MAX_BIAS, "gemm_tc3: N (%d) > %d with a bias vector is unsupported", d->N, MAX_BIAS);
+  if (!g_sms3) {
+    int dev = 0;
+    EEC_CUDA(cudaGetDevice(&dev));
+    EEC_CUDA(cudaDeviceGetAttribute(&g_sms3, cudaDevAttrMultiProcessorCount, dev));
+  }
+  CUtensorMap ta, tb, tcm, tpm;
+  if (d->a_kmajor) { if (int r = get_tmap_2d(&ta, d->A, d->K, d->M, (uint64_t)d->lda * 2, 64, 128)) return r; }
+  else { if (int r = get_tmap_2d(&ta, d->A, d->M, d->K, (uint64_t)d->lda * 2, 64, 64)) return r; }
+  if (d->b_kmajor) {
+    if (int r = get_tmap_2d(&tb, d->B, d->K, d->N, (uint64_t)d->ldb * 2, 64, epi == EPI_GLU ? 128 : 256)) return r;
+  } else {
+    if (int r = get_tmap_2d(&tb, d->B, d->N, d->K, (uint64_t)d->ldb * 2, 64, 64)) return r;
+  }
+  const int n_out = (epi == EPI_GLU) ? d->N / 2 : d->N;
+  const bool out_bf16 = d->out_dtype == EEC_BF16;
+  if (int r = get_tmap_box32(&tcm, d->C, out_bf16, (uint64_t)n_out, (uint64_t)d->M, (uint64_t)d->ldc)) return r;
+  const bool store_pre = d->preact && (d->act == EEC_ACT_SILU || epi == EPI_GLU);
+  tpm = tcm;
+  if (store_pre || d->act == EEC_ACT_DSILU) {
+    if (int r = get_tmap_box32(&tpm, d->preact, true, (uint64_t)d->N, (uint64_t)d->M, (uint64_t)d->ldp)) return r;
+  }
+  P3 p{};
+  p.M = d->M; p.N = d->N; p.K = d->K;
+  p.m_tiles = cdiv(d->M, BM);
+  p.n_tiles = (epi == EPI_GLU) ? d->N / 256 : cdiv(d->N, BN);
+  const int total_kb = cdiv(d->K, BK);
+  int splits = 1;
+  if (d->accumulate) {
+    const int tiles = p.m_tiles * p.n_tiles;
+    if (tiles < g_sms3 && total_kb >= 16) splits = min(cdiv(total_kb, 8), max(1, g_sms3 / tiles));
+  }
+  p.kb_per_split = cdiv(total_kb, splits);
+  p.splits = cdiv(total_kb, p.kb_per_split);
+  p.bias = d->bias; p.act = d->act; p.alpha = d->alpha;
+  p.residual = d->residual; p.ldr = d->ldr; p.res_row_mod = d->res_row_mod;
+  p.out_bf16 = out_bf16; p.has_pre = store_pre; p.accumulate = d->accumulate;
+  const int n_units = p.m_tiles * p.n_tiles * p.splits;
+  const int grid = min(n_units, g_sms3);
+  static int dbg = -1;
+  if (dbg < 0) { const char* e = getenv("EEC_GEMM_DEBUG"); dbg = e ? atoi(e) : 0; }
+  p.debug = dbg;
+  static int tl_env = -1;
+  static long long* tl_buf = nullptr;
+  if (tl_env < 0) { const char* e = getenv("EEC_GEMM_TL"); tl_env = (e && e[0] == '1') ? 1 : 0; }
+  if (tl_env) {
+    if (!tl_buf) EEC_CUDA(cudaMalloc(&tl_buf, 128));
+    p.tl = tl_buf;
+    struct Report {
+      long long* b; cudaStream_t s; int M, N, K;
+      ~Report() {
+        long long h[12];
+        if (cudaStreamSynchronize(s) != cudaSuccess || cudaMemcpy(h, b, sizeof(h), cudaMemcpyDeviceToHost) != cudaSuccess) return;
+        const double t = h[3] ? (double)h[3] : 1.0;
+        fprintf(stderr, "gemm_tc3 %dx%dx%d CTA0: %lld units; per unit (clk): MMA thread total %.0f = wait accumulator %.0f + wait operands %.0f + issue;"
+                " epilogue warp: wait tfull %.0f, tmem ld %.0f, math+stores %.0f\n", M, N, K, h[3], h[0] / t, h[1] / t, h[2] / t, h[4] / t, h[5] / t, h[6] / t);
+        fprintf(stderr, "          CTA0 globaltimer (ns): setup %lld, main loop %lld, drain+teardown %lld, total %lld\n", h[9] - h[8], h[10] - h[9], h[11] - h[10], h[11] - h[8]);
+      }
+    } report{tl_buf, st, d->M, d->N, d->K};
+    if (epi == EPI_GLU) return launch3<true, true, EPI_GLU>(ta, tb, tcm, tpm, p, grid, st);
+    if (d->a_kmajor && d->b_kmajor) return launch3<true, true, EPI_GENERIC>(ta, tb, tcm, tpm, p, grid, st);
+    if (d->a_kmajor && !d->b_kmajor) return launch3<true, false, EPI_GENERIC>(ta, tb, tcm, tpm, p, grid, st);
+    if (!d->a_kmajor && !d->b_kmajor) return launch3<false, false, EPI_GENERIC>(ta, tb, tcm, tpm, p, grid, st);
+    return launch3<false, true, EPI_GENERIC>(ta, tb, tcm, tpm, p, grid, st);
+  }
+  if (epi == EPI_GLU) return launch3<true, true, EPI_GLU>(ta, tb, tcm, tpm, p, grid, st);
+  if (d->a_kmajor && d->b_kmajor) return launch3<true, true, EPI_GENERIC>(ta, tb, tcm, tpm, p, grid, st);
+  if (d->a_kmajor && !d->b_kmajor) return launch3<true, false, EPI_GENERIC>(ta, tb, tcm, tpm, p, grid, st);
+  if (!d->a_kmajor && !d->b_kmajor) return launch3<false, false, EPI_GENERIC>(ta, tb, tcm, tpm, p, grid, st);
+  return launch3<false, true, EPI_GENERIC>(ta, tb, tcm, tpm, p, grid, st);
+}
+
+}  // namespace eec

@@ -116,7 +116,10 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 }
 
 // 32 lanes x 64 consecutive fp32 columns with ONE wait: two back-to-back loads, then tcgen05.wait::ld
-__device__ __forceinline__ void tmem_ld64(uint32_t taddr, float (&v)[32], float (&w)[32]) {
+__device__ __forceinline__ void tmem_ld32x2(uint32_t taddr0, uint32_t taddr1, float (&v)[32], float (&w)[32]);
+__device__ __forceinline__ void tmem_ld64(uint32_t taddr, float (&v)[32], float (&w)[32]) { tmem_ld32x2(taddr, taddr + 32, v, w); }
+// two independent 32-lane x 32-column loads (any two column offsets) retired by ONE wait
+__device__ __forceinline__ void tmem_ld32x2(uint32_t taddr0, uint32_t taddr1, float (&v)[32], float (&w)[32]) {
   uint32_t a[32], b[32];
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -133,7 +136,7 @@ __device__ __forceinline__ void tmem_ld64(uint32_t taddr, float (&v)[32], float 
         "=r"(b[6]), "=r"(b[7]), "=r"(b[8]), "=r"(b[9]), "=r"(b[10]), "=r"(b[11]), "=r"(b[12]), "=r"(b[13]), "=r"(b[14]),
         "=r"(b[15]), "=r"(b[16]), "=r"(b[17]), "=r"(b[18]), "=r"(b[19]), "=r"(b[20]), "=r"(b[21]), "=r"(b[22]), "=r"(b[23]),
         "=r"(b[24]), "=r"(b[25]), "=r"(b[26]), "=r"(b[27]), "=r"(b[28]), "=r"(b[29]), "=r"(b[30]), "=r"(b[31])
-      : "r"(taddr), "r"(taddr + 32)
+      : "r"(taddr0), "r"(taddr1)
       : "memory");
 #pragma unroll
   for (int i = 0; i < 32; ++i) { v[i] = __uint_as_float(a[i]); w[i] = __uint_as_float(b[i]); }
@@ -167,6 +170,12 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
   return r;
+}
+// smem tile -> global with an element-wise fp32 add performed by the L2 (split-K partial sums without per-thread atomics)
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, const void* smem_src, int x, int y) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(smem_src)), "r"(x), "r"(y)
+               : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
@@ -277,6 +286,8 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, bool a_mn_m
 int get_tmap_2d(CUtensorMap* out, const void* base, uint64_t dim0, uint64_t dim1, uint64_t stride1_bytes, uint32_t box0,
                 uint32_t box1, int swizzle = 3);
 int get_tmap_store(CUtensorMap* out, const void* base, bool bf16, uint64_t cols, uint64_t rows, uint64_t ld_elems);
+// 32 x 32 element boxes (one epilogue warp's staging tile): fp32 -> 128B swizzle, bf16 -> 64B swizzle
+int get_tmap_box32(CUtensorMap* out, const void* base, bool bf16, uint64_t cols, uint64_t rows, uint64_t ld_elems);
 int get_tmap_3d(CUtensorMap* out, const void* base, uint64_t dim0, uint64_t dim1, uint64_t dim2, uint64_t stride1_bytes,
                 uint64_t stride2_bytes, uint32_t box0, uint32_t box1, uint32_t box2);
 

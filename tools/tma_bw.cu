@@ -34,18 +34,21 @@ __global__ void __launch_bounds__(64, 1) bw_kernel(const __grid_constant__ CUten
   }
   __syncthreads();
   if (threadIdx.x == 0) {
-    for (int it = 0; it < n_boxes; ++it) {
-      const int s = it % ring;
-      mbar_wait(&empty[s], ((it / ring) & 1) ^ 1);
+    const int total = row_tiles * 4;
+    int box = (int)(((long)blockIdx.x * stride_ctas) % total);
+    for (int it = 0, s = 0, ph = 1; it < n_boxes; ++it) {
+      mbar_wait(&empty[s], ph);
       mbar_expect(&full[s], 16384);
-      const int box = it + blockIdx.x * stride_ctas;   // stride_ctas = 0: every CTA reads the same boxes (weights); else distinct
-      tma2d(smem + s * 16384, &tm, &full[s], (box & 3) * 64, ((box >> 2) % row_tiles) * 128);
+      // stride_ctas = 0: every CTA reads the same boxes (weights); else CTA b starts b*stride_ctas boxes into the matrix (distinct data)
+      tma2d(smem + s * 16384, &tm, &full[s], (box & 3) * 64, (box >> 2) * 128);
+      if (++box == total) box = 0;
+      if (++s == ring) { s = 0; ph ^= 1; }
     }
   } else if (threadIdx.x == 32) {
-    for (int it = 0; it < n_boxes; ++it) {
-      const int s = it % ring;
-      mbar_wait(&full[s], (it / ring) & 1);
+    for (int it = 0, s = 0, ph = 0; it < n_boxes; ++it) {
+      mbar_wait(&full[s], ph);
       mbar_arrive(&empty[s]);
+      if (++s == ring) { s = 0; ph ^= 1; }
     }
   }
 }
@@ -60,9 +63,11 @@ int main() {
   CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr));
   EncodeFn enc = (EncodeFn)fn;
   CK(cudaFuncSetAttribute(bw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 14 * 16384 + 512));
-  for (int big = 0; big < 2; ++big) {
-    // small: 2048 x 256 bf16 = 1 MB (L2-resident weights); big: 1M rows x 256 = 512 MB (streams from HBM)
-    const uint64_t rows = big ? (1ull << 20) : 2048;
+  for (int big = 0; big < 3; ++big) {
+    // 0: 2048 x 256 bf16 = 1 MB, every CTA reads the same boxes (L2-resident weights)
+    // 1: 128K rows = 64 MB, L2-resident, every CTA reads a distinct region (true L2 -> SM aggregate bandwidth)
+    // 2: 8M rows = 4 GB, distinct regions, streams from HBM
+    const uint64_t rows = big == 2 ? (8ull << 20) : big == 1 ? (128ull << 10) : 2048;
     void* buf;
     CK(cudaMalloc(&buf, rows * 512));
     CK(cudaMemset(buf, 0, rows * 512));
@@ -71,7 +76,7 @@ int main() {
     cuuint32_t bx[2] = {64, 128}, es[2] = {1, 1};
     if (enc(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, buf, gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) { printf("encode failed\n"); return 1; }
-    const int n_boxes = 4096;   // 64 MB per CTA
+    const int n_boxes = 4096;   // 64 MB per CTA (wraps around the matrix)
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     const int grids[3] = {148, 74, 16};
@@ -79,7 +84,7 @@ int main() {
     for (int gi = 0; gi < 3; ++gi)
       for (int ri = 0; ri < 7; ++ri) {
         const int ring = rings[ri], grid = grids[gi];
-        const int stride = big ? n_boxes : 0;
+        const int stride = big ? (int)(rows / 128 * 4 / grid) : 0;
         bw_kernel<<<grid, 64, ring * 16384 + 512>>>(tm, ring, n_boxes, (int)(rows / 128), stride);
         CK(cudaDeviceSynchronize());
         CK(cudaEventRecord(e0));
@@ -89,7 +94,7 @@ int main() {
         float ms;
         CK(cudaEventElapsedTime(&ms, e0, e1));
         const double per_sm = (double)n_boxes * 16384 / (ms * 1e-3) / 1e9;
-        printf("%s grid %3d ring %2d (%3d KB in flight): %7.1f GB/s per SM  %8.1f GB/s total   %.0f ns per box\n", big ? "HBM" : "L2 ", grid, ring,
+        printf("%s grid %3d ring %2d (%3d KB in flight): %7.1f GB/s per SM  %8.1f GB/s total   %.0f ns per box\n", big == 2 ? "HBM    " : big == 1 ? "L2 dist" : "L2 same", grid, ring,
                ring * 16, per_sm, per_sm * grid, ms * 1e6 / n_boxes);
       }
     CK(cudaFree(buf));
