@@ -461,7 +461,9 @@ int gemm_tc2(const eec_gemm_desc* d, cudaStream_t st, int32_t* argmax, float* en
     // GENERIC / GLU epilogues run on the v3 kernel (16 epilogue warps, warp-private staging); EEC_GEMM_V2=1 keeps v2 for A/B runs
     static int v2_env = -1;
     if (v2_env < 0) { const char* e = getenv("EEC_GEMM_V2"); v2_env = (e && e[0] == '1') ? 1 : 0; }
-    if (!v2_env && (epi == EPI_GENERIC || epi == EPI_GLU)) return gemm_tc3(d, st);
+    // (v3 stages dSiLU / SiLU+pre-activation outputs in bf16 boxes only; the fp32-output variants of those stay here)
+    const bool v3_ok = d->out_dtype == EEC_BF16 || !(d->act == EEC_ACT_DSILU || (d->act == EEC_ACT_SILU && d->preact));
+    if (!v2_env && v3_ok && (epi == EPI_GENERIC || epi == EPI_GLU)) return gemm_tc3(d, st);
   }
   if (!g_num_sms) {
     int dev = 0;

@@ -47,6 +47,7 @@ enum { EPI_GENERIC = 0, EPI_GLU = 1 };
 struct P3 {
   int M, N, K;
   int m_tiles, n_tiles, splits, kb_per_split;
+  int step_split, step_mt, step_nt;   // one grid stride (gridDim.x units) expressed in (split, m-tile, n-tile) steps: no divisions in the tile loops
   const float* bias;
   int act;
   float alpha;
@@ -121,23 +122,64 @@ __device__ __forceinline__ void add_bias32(float (&v)[32], const float* b) {
     v[g * 4] += f.x; v[g * 4 + 1] += f.y; v[g * 4 + 2] += f.z; v[g * 4 + 3] += f.w;
   }
 }
-// v[j] *= dSiLU(h[j]) with h = this lane's row (32 bf16) of a 64B-swizzled [32 x 32] bf16 box
-__device__ __forceinline__ void mul_dsilu32(float (&v)[32], const uint8_t* box, int lane) {
+// 16 values of this lane's row -> column half `half` of a [32 rows x 32 cols] staging box (bf16: 64B swizzle, fp32: 128B swizzle)
+__device__ __forceinline__ void put16_bf16(uint8_t* box, int half, int lane, const float (&x)[16]) {
+  uint8_t* row = box + lane * 64;
+  const int sw = (lane >> 1) & 3;
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    uint4 u;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(x[c * 8 + 2 * e], x[c * 8 + 2 * e + 1]);
+    *reinterpret_cast<uint4*>(row + (((half * 2 + c) ^ sw) << 4)) = u;
+  }
+}
+__device__ __forceinline__ void put16_f32(uint8_t* box, int half, int lane, const float (&x)[16]) {
+  uint8_t* row = box + lane * 128;
+  const int sw = lane & 7;
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+    *reinterpret_cast<float4*>(row + (((half * 4 + c) ^ sw) << 4)) = make_float4(x[c * 4], x[c * 4 + 1], x[c * 4 + 2], x[c * 4 + 3]);
+}
+// x[j] *= dSiLU(h[j]) with h = 16 bf16 of this lane's row (column half `half`) of a 64B-swizzled [32 x 32] bf16 box
+__device__ __forceinline__ void mul_dsilu16(float (&x)[16], const uint8_t* box, int half, int lane) {
   const uint8_t* row = box + lane * 64;
   const int sw = (lane >> 1) & 3;
 #pragma unroll
-  for (int g = 0; g < 4; ++g) {
-    const uint4 u = *reinterpret_cast<const uint4*>(row + ((g ^ sw) << 4));
+  for (int c = 0; c < 2; ++c) {
+    const uint4 u = *reinterpret_cast<const uint4*>(row + (((half * 2 + c) ^ sw) << 4));
     const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const float2 f = __bfloat1622float2(h[e]);
       const float s0 = sigmoid_fast(f.x), s1 = sigmoid_fast(f.y);
-      v[g * 8 + 2 * e] *= s0 * fmaf(f.x, 1.0f - s0, 1.0f);
-      v[g * 8 + 2 * e + 1] *= s1 * fmaf(f.y, 1.0f - s1, 1.0f);
+      x[c * 8 + 2 * e] *= s0 * fmaf(f.x, 1.0f - s0, 1.0f);
+      x[c * 8 + 2 * e + 1] *= s1 * fmaf(f.y, 1.0f - s1, 1.0f);
     }
   }
 }
+
+// work unit u = split * (m_tiles * n_tiles) + mt * n_tiles + nt, walked with a stride of gridDim.x units
+struct UnitIter {
+  int u, mt, nt, split;
+  __device__ __forceinline__ UnitIter(const P3& p) {
+    u = blockIdx.x;
+    const int tiles = p.m_tiles * p.n_tiles;
+    split = u / tiles;
+    const int t = u - split * tiles;
+    mt = t / p.n_tiles;
+    nt = t - mt * p.n_tiles;
+  }
+  __device__ __forceinline__ void next(const P3& p) {
+    u += gridDim.x;
+    split += p.step_split;
+    mt += p.step_mt;
+    nt += p.step_nt;
+    if (nt >= p.n_tiles) { nt -= p.n_tiles; ++mt; }
+    if (mt >= p.m_tiles) { mt -= p.m_tiles; ++split; }
+  }
+};
 
 template <bool A_KMAJ, bool B_KMAJ, int EPI>
 __global__ void __launch_bounds__(NT3, 1) gemm_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -185,18 +227,17 @@ __global__ void __launch_bounds__(NT3, 1) gemm_tc3_kernel(const __grid_constant_
 
   if (warp == 0) {
     if (lane == 0) {
-      uint32_t it = 0;  // global k-block counter (stage ring position)
-      for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
-        const int tile = u % tiles, split = u / tiles;
-        const int m0 = (tile / p.n_tiles) * BM;
-        const int nt = tile % p.n_tiles;
-        const int n0 = (EPI == EPI_GLU) ? nt * 128 : nt * BN;
-        const int kb0 = split * p.kb_per_split, kb1 = min(total_kb, kb0 + p.kb_per_split);
-        for (int kb = kb0; kb < kb1; ++kb, ++it) {
-          const int s = it % NSTAGE;
-          mbar_wait(&empty_bar[s], ((it / NSTAGE) & 1) ^ 1);
+      int s = 0;
+      uint32_t ph = 1;   // stage ring position + parity of the "empty" wait
+      for (UnitIter ui(p); ui.u < n_units; ui.next(p)) {
+        const int m0 = ui.mt * BM;
+        const int n0 = (EPI == EPI_GLU) ? ui.nt * 128 : ui.nt * BN;
+        const int kb0 = ui.split * p.kb_per_split, kb1 = min(total_kb, kb0 + p.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb, s = (s + 1 == NSTAGE) ? 0 : s + 1, ph ^= (s == 0)) {
+          mbar_wait(&empty_bar[s], ph);
           uint8_t* sa = smem + s * STAGE_BYTES;
           uint8_t* sb = sa + A_BYTES;
+          if (p.debug & 32) { mbar_arrive(&full_bar[s]); continue; }   // triage: MMAs run on whatever is in smem
           mbar_expect_tx(&full_bar[s], STAGE_BYTES);
           const int k = kb * BK;
           if (A_KMAJ) {
@@ -222,37 +263,43 @@ __global__ void __launch_bounds__(NT3, 1) gemm_tc3_kernel(const __grid_constant_
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(BM, BN, !A_KMAJ, !B_KMAJ);
-      uint32_t it = 0, ut = 0;
+      uint32_t ut = 0;
+      int s = 0;
+      uint32_t ph = 0;
+      // UMMA descriptors of every stage, built once (per MMA only the 16-element k offset is added)
+      uint64_t adesc[NSTAGE], bdesc[NSTAGE];
+#pragma unroll
+      for (int i = 0; i < NSTAGE; ++i) {
+        const uint32_t sa = smem_u32(smem + i * STAGE_BYTES), sb = sa + A_BYTES;
+        adesc[i] = A_KMAJ ? make_smem_desc(sa, 0, 1024) : make_smem_desc(sa, 8192, 1024);
+        bdesc[i] = B_KMAJ ? make_smem_desc(sb, 0, 1024) : make_smem_desc(sb, 8192, 1024);
+      }
+      constexpr uint64_t A_KSTEP = (A_KMAJ ? 32 : 2048) >> 4, B_KSTEP = (B_KMAJ ? 32 : 2048) >> 4;   // descriptor address field is in 16-byte units
 #ifdef EEC_GEMM_TIMELINE
       const bool prof = p.tl && blockIdx.x == 0;
 #else
       constexpr bool prof = false;
 #endif
       long long w_tempty = 0, w_full = 0, t_ = 0, t_begin = prof ? clock64() : 0;
-      for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++ut) {
-        const int split = u / tiles;
-        const int kb0 = split * p.kb_per_split, kb1 = min(total_kb, kb0 + p.kb_per_split);
+      for (UnitIter ui(p); ui.u < n_units; ui.next(p), ++ut) {
+        const int kb0 = ui.split * p.kb_per_split, kb1 = min(total_kb, kb0 + p.kb_per_split);
         const uint32_t acc = ut & 1;
         if (prof) t_ = clock64();
         mbar_wait(&tempty_bar[acc], ((ut >> 1) & 1) ^ 1);   // epilogue has read this accumulator out of TMEM
         if (prof) w_tempty += clock64() - t_;
-        tc_fence_after();
+        if (!(p.debug & 64)) tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = kb0; kb < kb1; ++kb, ++it) {
-          const int s = it % NSTAGE;
+        for (int kb = kb0; kb < kb1; ++kb) {
           if (prof) t_ = clock64();
-          mbar_wait(&full_bar[s], (it / NSTAGE) & 1);
+          mbar_wait(&full_bar[s], ph);
           if (prof) w_full += clock64() - t_;
-          tc_fence_after();
-          const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
-          const uint32_t sb = sa + A_BYTES;
+          if (!(p.debug & 128)) tc_fence_after();
+          const uint64_t ad = (s == 0) ? adesc[0] : (s == 1) ? adesc[1] : adesc[2];
+          const uint64_t bd = (s == 0) ? bdesc[0] : (s == 1) ? bdesc[1] : bdesc[2];
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            const uint64_t ad = A_KMAJ ? make_smem_desc(sa + k * 32, 0, 1024) : make_smem_desc(sa + k * 2048, 8192, 1024);
-            const uint64_t bd = B_KMAJ ? make_smem_desc(sb + k * 32, 0, 1024) : make_smem_desc(sb + k * 2048, 8192, 1024);
-            umma_bf16(d_tmem, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-          }
+          for (int k = 0; k < BK / 16; ++k) umma_bf16(d_tmem, ad + k * A_KSTEP, bd + k * B_KSTEP, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           umma_commit(&empty_bar[s]);
+          if (++s == NSTAGE) { s = 0; ph ^= 1; }
         }
         umma_commit(&tfull_bar[acc]);
       }
@@ -283,11 +330,11 @@ __global__ void __launch_bounds__(NT3, 1) gemm_tc3_kernel(const __grid_constant_
 #define TL_STAMP(t) do { } while (0)
 #define TL_ACC(a, d) do { } while (0)
 #endif
-    for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++ut) {
+    for (UnitIter ui(p); ui.u < n_units; ui.next(p), ++ut) {
       TL_STAMP(t0_); TL_ACC(e_rest, ut ? t0_ - t2_ : 0);
-      const int tile = u % tiles, split = u / tiles;
-      const int m0 = (tile / p.n_tiles) * BM;
-      const int nt = tile % p.n_tiles;
+      const int split = ui.split;
+      const int m0 = ui.mt * BM;
+      const int nt = ui.nt;
       const int n0 = (EPI == EPI_GLU) ? nt * 128 : nt * BN;
       const uint32_t acc = ut & 1;
       const int row0 = m0 + q * 32;
@@ -297,11 +344,14 @@ __global__ void __launch_bounds__(NT3, 1) gemm_tc3_kernel(const __grid_constant_
       const bool first_split = (split == 0);
 
       if (EPI == EPI_GENERIC) {
+        // 64 accumulator columns per warp = 2 output boxes of 32 columns, read from TMEM 16 columns at a time with the next
+        // read in flight while the current 16 values are processed (TMEM drains at 64 B/clk/SM: it must overlap the math)
         const int cb = cg * 64;
         const int nb = n0 + cb;
         const int nslab = (nb + 32 < p.N) ? 2 : (nb < p.N) ? 1 : 0;   // warp-uniform
-        if (p.act == EEC_ACT_DSILU && nslab && p.out_bf16) {
-          // pre-activation boxes for this warp's two slabs: in flight while the main loop of this tile runs
+        const bool dsilu = p.act == EEC_ACT_DSILU, silu = p.act == EEC_ACT_SILU;
+        if (dsilu && nslab) {
+          // pre-activation boxes of both slabs: in flight while the main loop of this tile runs
           if (lane == 0) {
             bulk_wait_read<0>();   // the previous tile's stores have finished reading the staging buffer
             mbar_expect_tx(lbar, nslab * 2048);
@@ -313,61 +363,97 @@ __global__ void __launch_bounds__(NT3, 1) gemm_tc3_kernel(const __grid_constant_
         mbar_wait(&tfull_bar[acc], (ut >> 1) & 1);
         TL_STAMP(t1_); TL_ACC(e_wait, t1_ - t0_);
         tc_fence_after();
-        // one 32-column slab at a time: 32 live accumulator registers keep the warp under the 96-register cap without spills
-#pragma unroll 1
-        for (int sl = 0; sl < 2; ++sl) {
-          const int n = nb + sl * 32;
-          tmem_ld32(trow + cb + sl * 32, v);
-          if (sl == 1) {
+        uint32_t ra[16], rb[16];
+        const uint32_t tcol = trow + cb;
+        if (p.debug & 256) {   // triage: no TMEM reads at all
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+          continue;
+        }
+        tmem_ld16_async(tcol, ra);
+#pragma unroll
+        for (int ss = 0; ss < 4; ++ss) {
+          uint32_t(&cur)[16] = (ss & 1) ? rb : ra;
+          uint32_t(&nxt)[16] = (ss & 1) ? ra : rb;
+          tmem_ld_wait16(cur);
+          if (ss < 3) {
+            tmem_ld16_async(tcol + (ss + 1) * 16, nxt);
+          } else {
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty_bar[acc]);   // accumulator is in registers: the MMA warp may reuse it
             TL_STAMP(t2_); TL_ACC(e_ld, t2_ - t1_);
           }
+          const int sl = ss >> 1, half = ss & 1;
           if (sl >= nslab) continue;
-          if (first_split && p.bias) add_bias32(v, bias_s + n);
-          if (p.act == EEC_ACT_SILU) {
-            if (p.has_pre) st.store_bf16(&tmP, n, row0, v);
+          const int n = nb + ss * 16;
+          float x[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) x[j] = __uint_as_float(cur[j]);
+          if (first_split && p.bias) {
+            const float4* bp = reinterpret_cast<const float4*>(bias_s + n);   // warp-uniform address: smem broadcast
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const float4 f = bp[g];
+              x[g * 4] += f.x; x[g * 4 + 1] += f.y; x[g * 4 + 2] += f.z; x[g * 4 + 3] += f.w;
+            }
+          }
+          // staging sub-buffers (2 KB bf16 boxes): SiLU+pre-activation store: pre -> 0, out -> 1; dSiLU: slab sl reuses the
+          // sub-buffer its pre-activation arrived in; otherwise the two slabs alternate.  fp32 boxes take the whole 4 KB.
+          const int osub = p.has_pre ? 1 : dsilu ? sl : st.sub;
+          if (half == 0 && !dsilu) {
+            if (lane == 0) {
+              if (!p.out_bf16 || p.has_pre) bulk_wait_read<0>();
+              else bulk_wait_read<1>();
+            }
+            __syncwarp();
+          }
+          if (silu) {
+            if (p.has_pre) put16_bf16(st.buf, half, lane, x);
             if (!(p.debug & 4)) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] *= sigmoid_fast(v[j]);
-            }
-          } else if (p.act == EEC_ACT_DSILU) {
-            if (!p.out_bf16) {   // fp32 output boxes fill the whole staging buffer: fetch this slab's pre-activation now (test-only path)
-              if (lane == 0) {
-                bulk_wait_read<0>();
-                mbar_expect_tx(lbar, 2048);
-                tma_load_2d(st.buf + sl * 2048, &tmP, lbar, n, row0);
+              for (int j = 0; j < 16; ++j) {   // x * sigmoid(x) = h + h * tanh(h), h = x / 2
+                const float h = 0.5f * x[j];
+                x[j] = fmaf(h, tanh_fast(h), h);
               }
-              __syncwarp();
             }
-            if (sl == 0 || !p.out_bf16) {
+          } else if (dsilu) {
+            if (ss == 0) {
               mbar_wait(lbar, lphase);
               lphase ^= 1;
             }
-            mul_dsilu32(v, st.buf + sl * 2048, lane);
+            mul_dsilu16(x, st.buf + sl * 2048, half, lane);
           }
           if (p.alpha != 1.0f) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] *= p.alpha;
+            for (int j = 0; j < 16; ++j) x[j] *= p.alpha;
           }
           if (p.residual && first_split && valid) {
             const long rr = p.res_row_mod ? (m % p.res_row_mod) : m;
             const float* rp = p.residual + rr * p.ldr + n;
 #pragma unroll
-            for (int g = 0; g < 8; ++g) {
+            for (int g = 0; g < 4; ++g) {
               const float4 f = *reinterpret_cast<const float4*>(rp + g * 4);
-              v[g * 4] += f.x; v[g * 4 + 1] += f.y; v[g * 4 + 2] += f.z; v[g * 4 + 3] += f.w;
+              x[g * 4] += f.x; x[g * 4 + 1] += f.y; x[g * 4 + 2] += f.z; x[g * 4 + 3] += f.w;
             }
           }
-          if (p.act == EEC_ACT_DSILU && p.out_bf16) {
-            // slab sl's output goes into the sub-buffer its own pre-activation came from (each lane rewrites the row it just read)
-            st.sub = sl;
-            st.pend_f32 = false;   // slab 0: nothing outstanding (lane 0 waited at tile start); slab 1: only slab 0's store from the other sub-buffer
+          uint8_t* ob = p.out_bf16 ? st.buf + osub * 2048 : st.buf;
+          if (p.debug & 2) continue;
+          if (p.out_bf16) put16_bf16(ob, half, lane, x);
+          else put16_f32(ob, half, lane, x);
+          if (half == 1) {
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0 && !(p.debug & 1)) {
+              const int nx = nb + sl * 32;
+              if (p.has_pre) tma_store_2d(&tmP, st.buf, nx, row0);   // same bulk group as the output box
+              if (p.accumulate) tma_reduce_add_2d(&tmC, ob, nx, row0);
+              else tma_store_2d(&tmC, ob, nx, row0);
+              bulk_commit();
+            }
+            st.sub ^= 1;
           }
-          if (p.accumulate) st.store_f32<true>(&tmC, n, row0, v);
-          else if (p.out_bf16) st.store_bf16(&tmC, n, row0, v);
-          else st.store_f32<false>(&tmC, n, row0, v);
         }
       } else {  // EPI_GLU: v = "a" half, w = gate half of the same 32 output channels
         const int c = cg * 32;
@@ -466,6 +552,13 @@ int gemm_tc3(const eec_gemm_desc* d, cudaStream_t st) {
   p.out_bf16 = out_bf16; p.has_pre = store_pre; p.accumulate = d->accumulate;
   const int n_units = p.m_tiles * p.n_tiles * p.splits;
   const int grid = min(n_units, g_sms3);
+  {
+    const int tiles = p.m_tiles * p.n_tiles;
+    p.step_split = grid / tiles;
+    const int rem = grid - p.step_split * tiles;
+    p.step_mt = rem / p.n_tiles;
+    p.step_nt = rem - p.step_mt * p.n_tiles;
+  }
   static int dbg = -1;
   if (dbg < 0) { const char* e = getenv("EEC_GEMM_DEBUG"); dbg = e ? atoi(e) : 0; }
   p.debug = dbg;
