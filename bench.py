@@ -221,7 +221,7 @@ def run_ours(args):
         }
         if rtfx is not None:
             line["rtfx_per_exit"] = rtfx
-        print(json.dumps(line))
+        print(json.dumps(line), file=_JSON_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
@@ -341,7 +341,10 @@ def run_reference(args):
                          "sample": f"{args.steps} steps x {sb} utterances (of the 64-utterance batch), {dt:.1f} s per step"},
         "e2e": {"value": round(value, 3), "unit": "utt/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    print(json.dumps(line), file=_JSON_OUT, flush=True)
+
+
+_JSON_OUT = sys.stdout
 
 
 def main():
@@ -358,6 +361,11 @@ def main():
     ap.add_argument("--profile", action="store_true", help="bracket the timed region with cudaProfilerStart/Stop (for ncu "
                     "--profile-from-start off) and skip the e2e / rtfx / roofline / cpu legs")
     args = ap.parse_args()
+    # stdout carries exactly ONE JSON line: anything a library prints on fd 1 meanwhile (NCCL's version banner, ...) goes to stderr
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -135,21 +135,34 @@ __global__ void __launch_bounds__(256, 3) dwconv_wgrad_kernel(const float* __res
   atomicAdd(dbias + ch, sb);
 }
 
-// ---- train-mode BatchNorm kernels.  Block = 64 channel-quads x 4 row lanes (256 threads); a thread moves
-// 4 channels per access (float4 / 4 x bf16) and keeps RU rows in flight; per-channel partial sums are
-// combined across the 4 row lanes in shared memory before ONE double atomic per channel per block.
-constexpr int RU = 8;
-template <typename T> struct Vec4;
-template <> struct Vec4<float> {
+// ---- streaming kernels of the conv module (train-mode BatchNorm + SiLU forward / backward, GLU backward).
+// A warp owns half frames: lane l holds channels [4l, 4l+4) of a 128-channel half of the 256-channel slice, so a row half
+// is ONE fully coalesced 512 B (fp32) / 256 B (bf16) access per tensor; a warp keeps RB rows in flight and strides over
+// the rows of a persistent grid (3 CTAs per SM), so loads, math and stores of different warps overlap instead of moving
+// in lock-step.
+// Per-channel parameters live in registers.  bf16 activations use the one-MUFU sigmoid (tanh.approx); the fp32 parity
+// path keeps the accurate one.
+constexpr int RB = 4;            // rows in flight per warp
+constexpr int SW_WARPS = 8;      // warps per CTA
+__device__ __forceinline__ float sigmoid_tanh(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(0.5f * x));
+  return fmaf(y, 0.5f, 0.5f);
+}
+template <bool FAST> __device__ __forceinline__ float sigm(float x) { return FAST ? sigmoid_tanh(x) : sigmoid_acc(x); }
+
+constexpr int CPL = 4;           // channels per lane
+template <typename T> struct Row8;   // CPL consecutive channels of one row
+template <> struct Row8<float> {
   static __device__ __forceinline__ void ld(const float* p, float (&v)[4]) {
-    float4 f = *reinterpret_cast<const float4*>(p); v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
+    const float4 f = *reinterpret_cast<const float4*>(p); v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
   }
   static __device__ __forceinline__ void st(float* p, const float (&v)[4]) { *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]); }
 };
-template <> struct Vec4<__nv_bfloat16> {
+template <> struct Row8<__nv_bfloat16> {
   static __device__ __forceinline__ void ld(const __nv_bfloat16* p, float (&v)[4]) {
     uint2 u = *reinterpret_cast<const uint2*>(p);
-    float2 a = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u.x)), b = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u.y));
+    const float2 a = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u.x)), b = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u.y));
     v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
   }
   static __device__ __forceinline__ void st(__nv_bfloat16* p, const float (&v)[4]) {
@@ -160,144 +173,181 @@ template <> struct Vec4<__nv_bfloat16> {
   }
 };
 
+// batch statistics -> per-channel mean / rstd (no double division or square root on the hot path)
+template <bool FAST>
+__device__ __forceinline__ void bn_mean_rstd(const double* sums, int C, int ch, double inv_n, float& mean, float& rstd, double& var_d) {
+  const double mean_d = sums[ch] * inv_n;
+  var_d = fma(-mean_d, mean_d, sums[C + ch] * inv_n);
+  if (var_d < 0.0) var_d = 0.0;
+  mean = (float)mean_d;
+  rstd = FAST ? rsqrtf((float)var_d + BN_EPS) : 1.0f / sqrtf((float)var_d + BN_EPS);
+}
+
 template <typename TO>
-__global__ void __launch_bounds__(256) bn_silu_train_kernel(const float* __restrict__ c, const double* __restrict__ sums,
+__global__ void __launch_bounds__(SW_WARPS * 32, 3) bn_silu_train_kernel(const float* __restrict__ c, const double* __restrict__ sums,
                                                             const float* __restrict__ bn_w, const float* __restrict__ bn_b,
                                                             float* __restrict__ run_mean, float* __restrict__ run_var,
                                                             int64_t* __restrict__ nbt, float momentum,
                                                             float* __restrict__ save_mean, float* __restrict__ save_rstd,
-                                                            TO* __restrict__ out, int rows, int C, int rows_per_block) {
-  const int cq = threadIdx.x & 63, rl = threadIdx.x >> 6;
-  const int ch0 = blockIdx.y * 256 + cq * 4;
-  const double n = (double)rows;
-  float mean[4], rstd[4], gam[4], bet[4];
+                                                            TO* __restrict__ out, int rows, int C) {
+  constexpr bool FAST = sizeof(TO) == 2;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ch0 = blockIdx.y * 256 + (warp & 1) * 128 + lane * CPL;
+  const double inv_n = 1.0 / (double)rows;
+  float sc[CPL], sh[CPL];
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
+  for (int k = 0; k < CPL; ++k) {
     const int ch = ch0 + k;
-    const double mean_d = sums[ch] / n;
-    double var_d = sums[C + ch] / n - mean_d * mean_d;
-    if (var_d < 0.0) var_d = 0.0;
-    mean[k] = (float)mean_d;
-    rstd[k] = (float)(1.0 / sqrt(var_d + (double)BN_EPS));
-    gam[k] = bn_w[ch]; bet[k] = bn_b[ch];
-    if (blockIdx.x == 0 && rl == 0) {
-      save_mean[ch] = mean[k];
-      save_rstd[ch] = rstd[k];
+    float mean, rstd;
+    double var_d;
+    bn_mean_rstd<FAST>(sums, C, ch, inv_n, mean, rstd, var_d);
+    sc[k] = rstd * bn_w[ch];
+    sh[k] = fmaf(-mean, sc[k], bn_b[ch]);
+    if (blockIdx.x == 0 && warp < 2) {   // warps 0 and 1 cover the two channel halves
+      save_mean[ch] = mean;
+      save_rstd[ch] = rstd;
       if (run_mean) {
-        run_mean[ch] = (1.f - momentum) * run_mean[ch] + momentum * mean[k];
-        const double unb = (rows > 1) ? var_d * n / (n - 1.0) : var_d;
+        run_mean[ch] = (1.f - momentum) * run_mean[ch] + momentum * mean;
+        const double unb = (rows > 1) ? var_d * ((double)rows / ((double)rows - 1.0)) : var_d;
         run_var[ch] = (1.f - momentum) * run_var[ch] + momentum * (float)unb;
         if (ch == 0 && nbt) *nbt += 1;
       }
     }
   }
-  const int r0 = blockIdx.x * rows_per_block, r1 = min(rows, r0 + rows_per_block);
-  for (int rb = r0 + rl; rb < r1; rb += 4 * RU) {
-    float v[RU][4];
+  const int stride = gridDim.x * (SW_WARPS / 2);
+  for (int r = blockIdx.x * (SW_WARPS / 2) + (warp >> 1); r < rows; r += stride * RB) {
+    float v[RB][CPL];
 #pragma unroll
-    for (int i = 0; i < RU; ++i) {
-      const int r = rb + 4 * i;
-      if (r < r1) Vec4<float>::ld(c + (long)r * C + ch0, v[i]);
-    }
+    for (int i = 0; i < RB; ++i)
+      if (r + i * stride < rows) Row8<float>::ld(c + (long)(r + i * stride) * C + ch0, v[i]);
 #pragma unroll
-    for (int i = 0; i < RU; ++i) {
-      const int r = rb + 4 * i;
-      if (r < r1) {
-        float o[4];
+    for (int i = 0; i < RB; ++i)
+      if (r + i * stride < rows) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const float y = fmaf((v[i][k] - mean[k]) * rstd[k], gam[k], bet[k]);
-          o[k] = y * sigmoid_acc(y);
+        for (int k = 0; k < CPL; ++k) {
+          const float y = fmaf(v[i][k], sc[k], sh[k]);
+          v[i][k] = y * sigm<FAST>(y);
         }
-        Vec4<TO>::st(out + (long)r * C + ch0, o);
+        Row8<TO>::st(out + (long)(r + i * stride) * C + ch0, v[i]);
       }
-    }
   }
 }
 
+// APPLY = false: sums2[ch] += sum dn, sums2[C + ch] += sum dn * nhat   (dn = d/dn of SiLU(BN(c)))
+// APPLY = true : dc = gamma * rstd * (dn - mean(dn) - nhat * mean(dn * nhat)); dgamma / dbeta from sums2
 template <typename TI, bool APPLY>
-__global__ void __launch_bounds__(256) bn_silu_bwd_kernel(const TI* __restrict__ ds, const float* __restrict__ c,
+__global__ void __launch_bounds__(SW_WARPS * 32, 3) bn_silu_bwd_kernel(const TI* __restrict__ ds, const float* __restrict__ c,
                                                           const float* __restrict__ save_mean, const float* __restrict__ save_rstd,
                                                           const float* __restrict__ bn_w, const float* __restrict__ bn_b,
                                                           double* __restrict__ sums2, float* __restrict__ dc,
-                                                          float* __restrict__ dgamma, float* __restrict__ dbeta, int rows, int C,
-                                                          int rows_per_block) {
-  __shared__ float red[2][4][256];
-  const int cq = threadIdx.x & 63, rl = threadIdx.x >> 6;
-  const int ch0 = blockIdx.y * 256 + cq * 4;
-  float mean[4], rstd[4], gam[4], bet[4], m1[4], m2[4], s1[4], s2[4];
+                                                          float* __restrict__ dgamma, float* __restrict__ dbeta, int rows, int C) {
+  constexpr bool FAST = sizeof(TI) == 2;
+  __shared__ float red[2][SW_WARPS / 2][256];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ch0 = blockIdx.y * 256 + (warp & 1) * 128 + lane * CPL;
+  float a1[CPL], a0[CPL], gam[CPL], bet[CPL], m1[CPL], m2[CPL], s1[CPL], s2[CPL];   // nhat = c * a1 + a0
+  const float inv_n = 1.0f / (float)rows;
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
+  for (int k = 0; k < CPL; ++k) {
     const int ch = ch0 + k;
-    mean[k] = save_mean[ch]; rstd[k] = save_rstd[ch]; gam[k] = bn_w[ch]; bet[k] = bn_b[ch];
+    a1[k] = save_rstd[ch];
+    a0[k] = -save_mean[ch] * a1[k];
+    gam[k] = bn_w[ch]; bet[k] = bn_b[ch];
     s1[k] = 0.f; s2[k] = 0.f;
     if (APPLY) {
-      m1[k] = (float)(sums2[ch] / (double)rows);
-      m2[k] = (float)(sums2[C + ch] / (double)rows);
-      if (blockIdx.x == 0 && rl == 0) {
-        atomicAdd(dbeta + ch, (float)sums2[ch]);
-        atomicAdd(dgamma + ch, (float)sums2[C + ch]);
+      const float t1 = (float)sums2[ch], t2 = (float)sums2[C + ch];
+      m1[k] = t1 * inv_n;
+      m2[k] = t2 * inv_n;
+      if (blockIdx.x == 0 && warp < 2) {   // warps 0 and 1 cover the two channel halves
+        atomicAdd(dbeta + ch, t1);
+        atomicAdd(dgamma + ch, t2);
       }
     }
   }
-  const int r0 = blockIdx.x * rows_per_block, r1 = min(rows, r0 + rows_per_block);
-  for (int rb = r0 + rl; rb < r1; rb += 4 * RU) {
-    float v[RU][4], g[RU][4];
+  const int stride = gridDim.x * (SW_WARPS / 2);
+  for (int r = blockIdx.x * (SW_WARPS / 2) + (warp >> 1); r < rows; r += stride * RB) {
+    float v[RB][CPL], g[RB][CPL];
 #pragma unroll
-    for (int i = 0; i < RU; ++i) {
-      const int r = rb + 4 * i;
-      if (r < r1) {
-        Vec4<float>::ld(c + (long)r * C + ch0, v[i]);
-        Vec4<TI>::ld(ds + (long)r * C + ch0, g[i]);
+    for (int i = 0; i < RB; ++i)
+      if (r + i * stride < rows) {
+        Row8<float>::ld(c + (long)(r + i * stride) * C + ch0, v[i]);
+        Row8<TI>::ld(ds + (long)(r + i * stride) * C + ch0, g[i]);
       }
-    }
 #pragma unroll
-    for (int i = 0; i < RU; ++i) {
-      const int r = rb + 4 * i;
-      if (r < r1) {
-        float o[4];
+    for (int i = 0; i < RB; ++i)
+      if (r + i * stride < rows) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const float nh = (v[i][k] - mean[k]) * rstd[k];
+        for (int k = 0; k < CPL; ++k) {
+          const float nh = fmaf(v[i][k], a1[k], a0[k]);
           const float y = fmaf(nh, gam[k], bet[k]);
-          const float sg = sigmoid_acc(y);
-          const float dn = g[i][k] * sg * (1.f + y * (1.f - sg));
-          if (APPLY) o[k] = gam[k] * rstd[k] * (dn - m1[k] - nh * m2[k]);
+          const float sg = sigm<FAST>(y);
+          const float dn = g[i][k] * sg * fmaf(y, 1.f - sg, 1.f);
+          if (APPLY) v[i][k] = gam[k] * a1[k] * (dn - m1[k] - nh * m2[k]);
           else { s1[k] += dn; s2[k] = fmaf(dn, nh, s2[k]); }
         }
-        if (APPLY) Vec4<float>::st(dc + (long)r * C + ch0, o);
+        if (APPLY) Row8<float>::st(dc + (long)(r + i * stride) * C + ch0, v[i]);
       }
-    }
   }
   if (!APPLY) {
 #pragma unroll
-    for (int k = 0; k < 4; ++k) { red[0][rl][cq * 4 + k] = s1[k]; red[1][rl][cq * 4 + k] = s2[k]; }
+    for (int k = 0; k < CPL; ++k) { red[0][warp >> 1][(warp & 1) * 128 + lane * CPL + k] = s1[k]; red[1][warp >> 1][(warp & 1) * 128 + lane * CPL + k] = s2[k]; }
     __syncthreads();
     const int ch = threadIdx.x;
-    const float a = red[0][0][ch] + red[0][1][ch] + red[0][2][ch] + red[0][3][ch];
-    const float b = red[1][0][ch] + red[1][1][ch] + red[1][2][ch] + red[1][3][ch];
+    float a = 0.f, b = 0.f;
+#pragma unroll
+    for (int w = 0; w < SW_WARPS / 2; ++w) { a += red[0][w][ch]; b += red[1][w][ch]; }
     atomicAdd(sums2 + blockIdx.y * 256 + ch, (double)a);
     atomicAdd(sums2 + C + blockIdx.y * 256 + ch, (double)b);
   }
 }
 
+// z = [a | gate] (rows x 2C), dg (rows x C) -> dz = [dg * sigmoid(gate) | dg * a * sigmoid(gate) * (1 - sigmoid(gate))]
 template <typename T>
-__global__ void glu_bwd_kernel(const T* __restrict__ z, const T* __restrict__ dg, T* __restrict__ dz, long rows, int C) {
-  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= rows * C) return;
-  long r = i / C;
-  int cc = (int)(i % C);
-  float a = ld_as_float<T>(z + r * 2 * C + cc);
-  float bgate = ld_as_float<T>(z + r * 2 * C + C + cc);
-  float d = ld_as_float<T>(dg + i);
-  float s = sigmoid_acc(bgate);
-  st_from_float<T>(dz + r * 2 * C + cc, d * s);
-  st_from_float<T>(dz + r * 2 * C + C + cc, d * a * s * (1.f - s));
+__global__ void __launch_bounds__(SW_WARPS * 32, 3) glu_bwd_kernel(const T* __restrict__ z, const T* __restrict__ dg, T* __restrict__ dz, int rows, int C) {
+  constexpr bool FAST = sizeof(T) == 2;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ch0 = blockIdx.y * 256 + (warp & 1) * 128 + lane * CPL;
+  const int stride = gridDim.x * (SW_WARPS / 2);
+  for (int r = blockIdx.x * (SW_WARPS / 2) + (warp >> 1); r < rows; r += stride * RB) {
+    float a[RB][CPL], gt[RB][CPL], d[RB][CPL];
+#pragma unroll
+    for (int i = 0; i < RB; ++i)
+      if (r + i * stride < rows) {
+        const long rr = r + i * stride;
+        Row8<T>::ld(z + rr * 2 * C + ch0, a[i]);
+        Row8<T>::ld(z + rr * 2 * C + C + ch0, gt[i]);
+        Row8<T>::ld(dg + rr * C + ch0, d[i]);
+      }
+#pragma unroll
+    for (int i = 0; i < RB; ++i)
+      if (r + i * stride < rows) {
+        const long rr = r + i * stride;
+#pragma unroll
+        for (int k = 0; k < CPL; ++k) {
+          const float sg = sigm<FAST>(gt[i][k]);
+          const float da = d[i][k] * sg;
+          gt[i][k] = da * a[i][k] * (1.f - sg);
+          a[i][k] = da;
+        }
+        Row8<T>::st(dz + rr * 2 * C + ch0, a[i]);
+        Row8<T>::st(dz + rr * 2 * C + C + ch0, gt[i]);
+      }
+  }
 }
 
 }  // namespace eec
 
 using namespace eec;
+
+// persistent grid of the streaming kernels: 3 CTAs per SM (24 warps), never more CTAs than row batches
+static int stream_grid(int rows) {
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 148;
+  }
+  return max(1, min(sms * 3, cdiv(rows, SW_WARPS / 2)));
+}
 
 // dynamic-smem launch of a dwconv kernel whose staged input type is TI (fp32 tiles exceed the 48 KB default)
 #define EEC_DW_LAUNCH(kernel, TI, ...)                                                                                   \
@@ -345,12 +395,11 @@ extern "C" int eec_bn_silu_train(const float* c, const double* sums, const float
                                  eec_stream_t stream) {
   EEC_CHECK_ARG(C % 256 == 0, "bn_silu_train: C %% 256");
   if (rows == 0) return 0;
-  const int rpb = 32;
-  dim3 grid(cdiv(rows, rpb), C / 256);
+  dim3 grid(stream_grid(rows), C / 256);
   if (dtype == EEC_F32)
-    bn_silu_train_kernel<float><<<grid, 256, 0, S(stream)>>>(c, sums, bn_w, bn_b, run_mean, run_var, num_batches_tracked, momentum, save_mean, save_rstd, (float*)out, rows, C, rpb);
+    bn_silu_train_kernel<float><<<grid, SW_WARPS * 32, 0, S(stream)>>>(c, sums, bn_w, bn_b, run_mean, run_var, num_batches_tracked, momentum, save_mean, save_rstd, (float*)out, rows, C);
   else
-    bn_silu_train_kernel<__nv_bfloat16><<<grid, 256, 0, S(stream)>>>(c, sums, bn_w, bn_b, run_mean, run_var, num_batches_tracked, momentum, save_mean, save_rstd, (__nv_bfloat16*)out, rows, C, rpb);
+    bn_silu_train_kernel<__nv_bfloat16><<<grid, SW_WARPS * 32, 0, S(stream)>>>(c, sums, bn_w, bn_b, run_mean, run_var, num_batches_tracked, momentum, save_mean, save_rstd, (__nv_bfloat16*)out, rows, C);
   EEC_LAUNCH_CHECK();
   return 0;
 }
@@ -360,12 +409,11 @@ extern "C" int eec_bn_silu_bwd_stats(const void* ds, int dtype, const float* c, 
                                      int rows, int C, eec_stream_t stream) {
   EEC_CHECK_ARG(C % 256 == 0, "bn_silu_bwd_stats: C %% 256");
   if (rows == 0) return 0;
-  const int rpb = 32;
-  dim3 grid(cdiv(rows, rpb), C / 256);
+  dim3 grid(stream_grid(rows), C / 256);
   if (dtype == EEC_F32)
-    bn_silu_bwd_kernel<float, false><<<grid, 256, 0, S(stream)>>>((const float*)ds, c, save_mean, save_rstd, bn_w, bn_b, sums2, nullptr, nullptr, nullptr, rows, C, rpb);
+    bn_silu_bwd_kernel<float, false><<<grid, SW_WARPS * 32, 0, S(stream)>>>((const float*)ds, c, save_mean, save_rstd, bn_w, bn_b, sums2, nullptr, nullptr, nullptr, rows, C);
   else
-    bn_silu_bwd_kernel<__nv_bfloat16, false><<<grid, 256, 0, S(stream)>>>((const __nv_bfloat16*)ds, c, save_mean, save_rstd, bn_w, bn_b, sums2, nullptr, nullptr, nullptr, rows, C, rpb);
+    bn_silu_bwd_kernel<__nv_bfloat16, false><<<grid, SW_WARPS * 32, 0, S(stream)>>>((const __nv_bfloat16*)ds, c, save_mean, save_rstd, bn_w, bn_b, sums2, nullptr, nullptr, nullptr, rows, C);
   EEC_LAUNCH_CHECK();
   return 0;
 }
@@ -375,12 +423,11 @@ extern "C" int eec_bn_silu_bwd_apply(const void* ds, int dtype, const float* c, 
                                      float* dc, float* dgamma, float* dbeta, int rows, int C, eec_stream_t stream) {
   EEC_CHECK_ARG(C % 256 == 0, "bn_silu_bwd_apply: C %% 256");
   if (rows == 0) return 0;
-  const int rpb = 32;
-  dim3 grid(cdiv(rows, rpb), C / 256);
+  dim3 grid(stream_grid(rows), C / 256);
   if (dtype == EEC_F32)
-    bn_silu_bwd_kernel<float, true><<<grid, 256, 0, S(stream)>>>((const float*)ds, c, save_mean, save_rstd, bn_w, bn_b, const_cast<double*>(sums2), dc, dgamma, dbeta, rows, C, rpb);
+    bn_silu_bwd_kernel<float, true><<<grid, SW_WARPS * 32, 0, S(stream)>>>((const float*)ds, c, save_mean, save_rstd, bn_w, bn_b, const_cast<double*>(sums2), dc, dgamma, dbeta, rows, C);
   else
-    bn_silu_bwd_kernel<__nv_bfloat16, true><<<grid, 256, 0, S(stream)>>>((const __nv_bfloat16*)ds, c, save_mean, save_rstd, bn_w, bn_b, const_cast<double*>(sums2), dc, dgamma, dbeta, rows, C, rpb);
+    bn_silu_bwd_kernel<__nv_bfloat16, true><<<grid, SW_WARPS * 32, 0, S(stream)>>>((const __nv_bfloat16*)ds, c, save_mean, save_rstd, bn_w, bn_b, const_cast<double*>(sums2), dc, dgamma, dbeta, rows, C);
   EEC_LAUNCH_CHECK();
   return 0;
 }
@@ -404,11 +451,11 @@ extern "C" int eec_dwconv_bwd(const float* dc, const void* g, int dtype, const f
 }
 
 extern "C" int eec_glu_bwd(const void* z, const void* dg, void* dz, int dtype, int rows, int C, eec_stream_t stream) {
+  EEC_CHECK_ARG(C % 256 == 0, "glu_bwd: C %% 256");
   if (rows == 0) return 0;
-  long total = (long)rows * C;
-  int blocks = (int)cdiv64(total, 256);
-  if (dtype == EEC_F32) glu_bwd_kernel<float><<<blocks, 256, 0, S(stream)>>>((const float*)z, (const float*)dg, (float*)dz, rows, C);
-  else glu_bwd_kernel<__nv_bfloat16><<<blocks, 256, 0, S(stream)>>>((const __nv_bfloat16*)z, (const __nv_bfloat16*)dg, (__nv_bfloat16*)dz, rows, C);
+  dim3 grid(stream_grid(rows), C / 256);
+  if (dtype == EEC_F32) glu_bwd_kernel<float><<<grid, SW_WARPS * 32, 0, S(stream)>>>((const float*)z, (const float*)dg, (float*)dz, rows, C);
+  else glu_bwd_kernel<__nv_bfloat16><<<grid, SW_WARPS * 32, 0, S(stream)>>>((const __nv_bfloat16*)z, (const __nv_bfloat16*)dg, (__nv_bfloat16*)dz, rows, C);
   EEC_LAUNCH_CHECK();
   return 0;
 }
