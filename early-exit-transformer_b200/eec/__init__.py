@@ -1,8 +1,9 @@
 """eec -- B200-native early-exit conformer (CTC hot path) behind the reference's module interface.
 
-    from eec import Early_conformer, Splitformer, CTCLoss, multi_exit_ctc_loss, greedy_decode
+    from eec import Early_conformer, Splitformer, CTCLoss, multi_exit_ctc_loss, greedy_decode, GraphedTrainStep
 """
 from .lib import EecError, load, LIB_PATH, EXPORTS  # noqa: F401
 from .early_exit import Early_conformer, Splitformer, greedy_decode  # noqa: F401
 from .ctc import CTCLoss, multi_exit_ctc_loss  # noqa: F401
+from .graph import GraphedTrainStep  # noqa: F401
 from . import distributed  # noqa: F401,E402

@@ -1,0 +1,118 @@
+"""Whole training step as ONE CUDA graph (north star: "CUDA streams and graphs instead of a tracing compiler").
+
+The eager step (train.py:53-69: forward, summed multi-exit CTC, backward) issues ~600 kernel launches through
+ctypes; at ~20 ms of GPU work per step the Python launch path is as long as the GPU time, so every kernel speed-up
+disappears behind launch gaps.  ``GraphedTrainStep`` runs the step once under ``torch.cuda.graph`` with static
+input / target buffers and replays it: one ``cudaGraphLaunch`` per step.
+
+    step = eec.GraphedTrainStep(model, batch_size=64, t_in=1501, max_target_len=82)
+    loss = step(src, lengths, targets, target_lengths)      # same tensors the reference's train() feeds
+    eec.distributed.all_reduce_gradients(model)              # DP: one flat-buffer all-reduce (outside the graph)
+    optimizer.step()
+
+What is inside the graph: bf16 operand casts of every parameter (so weight updates between replays are seen),
+the encoder forward, the fused 6-exit CTC forward-backward, the backward pass into ONE flat fp32 gradient buffer
+(zeroed inside the graph).  ``p.grad`` tensors are views of that buffer and stay valid across replays.
+What stays outside: host-side argument checks (the reference's ``max(lengths)//4 >= T'`` precondition,
+early_exit.py:623 / TA:9-15), host->device copies of the step's inputs, the NCCL all-reduce, the optimiser.
+Shapes are static: a new (batch, T_in, max_target_len) needs a new GraphedTrainStep (the reference's length-sorted
+sub-batches, data_loader.py:166-188, map to a small set of bucketed shapes).
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import engine
+from .ctc import multi_exit_ctc_loss
+from .lib import EecError, load
+
+
+class GraphedTrainStep:
+    def __init__(self, model, batch_size: int, t_in: int, max_target_len: int, n_mels: Optional[int] = None, blank: int = 0,
+                 pad_token: int = 126, warmup: int = 2):
+        params = list(model.parameters())
+        if not params or not params[0].is_cuda:
+            raise EecError("GraphedTrainStep: move the model to a CUDA device first (no CPU path)")
+        if not model.training:
+            raise EecError("GraphedTrainStep captures a TRAINING step: call model.train() first")
+        dev = params[0].device
+        self.model, self.blank, self.pad_token = model, blank, pad_token
+        self.B, self.T_in, self.L = batch_size, t_in, max_target_len
+        n_mels = n_mels if n_mels is not None else model._features_length
+        # static device buffers the graph reads, and pinned host staging for the per-step uploads
+        self.src = torch.zeros(batch_size, n_mels, t_in, dtype=torch.float32, device=dev)
+        self.lengths = torch.full((batch_size,), t_in, dtype=torch.int64, device=dev)
+        self.targets = torch.full((batch_size, max_target_len), pad_token, dtype=torch.int64, device=dev)
+        self.target_lengths = torch.ones(batch_size, dtype=torch.int64, device=dev)
+        self._pin_src = torch.empty(self.src.shape, dtype=torch.float32).pin_memory()
+        self._pin_small = torch.empty(batch_size * (max_target_len + 2), dtype=torch.int64).pin_memory()
+        self._dev_small = torch.empty_like(self._pin_small, device=dev)
+        self.t_out = ((t_in - 3) // 2 + 1 - 3) // 2 + 1
+
+        lib = load()
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):   # eager warm-up off the default stream (lazy module loads, kernel attributes, tensor maps)
+            for _ in range(max(warmup, 1)):
+                self._eager_step()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        # parameter casts must be IN the graph: drop the operand cache so capture re-issues them
+        model._operands._cache.clear()
+        model.zero_grad(set_to_none=True)
+        self.graph = torch.cuda.CUDAGraph()
+        n0 = lib.eec_launch_count()
+        with torch.cuda.graph(self.graph):
+            loss = self._eager_step()
+        self.launches_per_step = int(lib.eec_launch_count() - n0)   # kernels of ours inside one replay
+        self.loss = loss.detach()
+        self.flat_grad = model.__dict__.get("_flat_grad")
+
+    def _eager_step(self):
+        out = self.model(self.src, self.lengths)
+        loss = multi_exit_ctc_loss(out, self.targets, self.target_lengths, self.blank)
+        loss.backward()
+        return loss
+
+    def load_inputs(self, src: torch.Tensor, lengths: torch.Tensor, targets: torch.Tensor, target_lengths: torch.Tensor) -> None:
+        """Validate one batch on the host and upload it into the graph's static buffers (async on the current stream)."""
+        B, L = self.B, self.L
+        if tuple(src.shape) != tuple(self.src.shape):
+            raise EecError(f"GraphedTrainStep: src shape {tuple(src.shape)} != captured {tuple(self.src.shape)}")
+        if targets.shape[0] != B or targets.shape[1] > L or lengths.numel() != B or target_lengths.numel() != B:
+            raise EecError("GraphedTrainStep: batch / target shape does not fit the captured step")
+        if not lengths.is_cuda:
+            engine.check_lengths(lengths, self.t_out)   # the reference's AssertionError, raised on the host before any launch
+        if src.is_cuda:
+            self.src.copy_(src, non_blocking=True)
+        else:
+            self._pin_src.copy_(src)
+            self.src.copy_(self._pin_src, non_blocking=True)
+        if lengths.is_cuda or targets.is_cuda or target_lengths.is_cuda:
+            self.lengths.copy_(lengths, non_blocking=True)
+            self.targets.fill_(self.pad_token)
+            self.targets[:, : targets.shape[1]].copy_(targets, non_blocking=True)
+            self.target_lengths.copy_(target_lengths, non_blocking=True)
+            return
+        # one pinned staging buffer, one H2D copy for the three small integer tensors
+        st = self._pin_small
+        st[:B].copy_(lengths.reshape(-1))
+        st[B:2 * B].copy_(target_lengths.reshape(-1))
+        tg = st[2 * B:].view(B, L)
+        tg.fill_(self.pad_token)
+        tg[:, : targets.shape[1]].copy_(targets)
+        self._dev_small.copy_(st, non_blocking=True)
+        self.lengths.copy_(self._dev_small[:B])
+        self.target_lengths.copy_(self._dev_small[B:2 * B])
+        self.targets.copy_(self._dev_small[2 * B:].view(B, L))
+
+    def replay(self) -> torch.Tensor:
+        """Re-run the captured step on whatever the static buffers hold; returns the (static) loss tensor."""
+        self.graph.replay()
+        return self.loss
+
+    def __call__(self, src, lengths, targets, target_lengths) -> torch.Tensor:
+        self.load_inputs(src, lengths, targets, target_lengths)
+        return self.replay()

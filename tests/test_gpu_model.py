@@ -189,3 +189,50 @@ def test_state_dict_roundtrip_and_errors():
         m.eval()(torch.zeros(1, 80, 100), torch.tensor([100]))  # CPU input: no fallback
     with pytest.raises(NotImplementedError):
         m.train()(torch.zeros(1, 80, 100, device="cuda"), torch.tensor([100]))  # dropout > 0 in training: explicit
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_graphed_train_step_matches_eager(precision):
+    """The CUDA-graph replay of a training step (eec.GraphedTrainStep) gives the eager step's loss and gradients,
+    sees new inputs and updated weights between replays, and raises the reference's length precondition on the host."""
+    import eec
+    name = "ec_e2l1_b3_t163"
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    m, sd, src, lengths = build(name, g, precision)
+    m.train()
+    Bn = src.shape[0]
+    targets, tl = O.synthetic_targets(Bn, seed=11, lo=3, hi=6)
+
+    def eager(x, ln, tg, tlen):
+        m.zero_grad(set_to_none=True)
+        out = m(x.cuda(), ln)
+        loss = eec.multi_exit_ctc_loss(out, tg, tlen)
+        loss.backward()
+        return float(loss.detach()), {n: p.grad.detach().clone() for n, p in m.named_parameters()}
+
+    ref_loss, ref_g = eager(src, lengths, targets, tl)
+    step = eec.GraphedTrainStep(m, Bn, src.shape[2], targets.shape[1] + 3)   # wider target buffer than this batch: padded
+    assert step.launches_per_step > 50
+    loss = step(src, lengths, targets, tl)
+    torch.cuda.synchronize()
+    tol = 1e-5 if precision == "fp32" else 1e-2   # same kernels, same order: only atomics reorder
+    assert abs(float(loss) - ref_loss) <= tol * abs(ref_loss)
+    gmax = max(float(v.abs().max()) for v in ref_g.values())
+    for n, p in m.named_parameters():   # (gradients that are analytically zero, e.g. the key bias, are compared on the global scale)
+        err = float((p.grad - ref_g[n]).abs().max())
+        assert err <= max(tol, 2e-4) * max(float(ref_g[n].abs().max()), 1e-3 * gmax), (n, err)
+    assert m._flat_grad.data_ptr() == next(m.parameters()).grad.data_ptr()
+    # new batch + changed weights: the replay must see both
+    src2, lengths2 = O.synthetic_batch(Bn, src.shape[2], seed=77)
+    targets2, tl2 = O.synthetic_targets(Bn, seed=12, lo=3, hi=6)
+    with torch.no_grad():
+        for p in m.parameters():
+            p.mul_(1.01)
+    ref_loss2, ref_g2 = eager(src2, lengths2, targets2, tl2)
+    loss2 = step(src2, lengths2, targets2, tl2)
+    torch.cuda.synchronize()
+    assert abs(float(loss2) - ref_loss2) <= tol * abs(ref_loss2)
+    k = "conformer.0.conformer_layers.0.ffn1.sequential.1.weight"
+    assert rel(dict(m.named_parameters())[k].grad, ref_g2[k]) < max(tol, 2e-4)
+    with pytest.raises(AssertionError):
+        step(src2, torch.full((Bn,), 100, dtype=torch.int64), targets2, tl2)
