@@ -1,12 +1,14 @@
 // attn_bwd_tc.cu -- self-attention backward on the tcgen05 tensor cores (bf16 operands, fp32 math).
 //
 // One CTA per (128-key block j, head, utterance); it keeps K_j, V_j resident and walks the query blocks i:
-//   S  = Q_i K_j^T          (M=128 q, N=128 k, K=32)        -> TMEM [0,128)
-//   dP = dO_i V_j^T         (M=128 q, N=128 k, K=32)        -> TMEM [128,256)
-//   row threads: P = exp2(S*c - lse_i), dS = P (dP - D_i)   -> bf16 P / dS tiles in 128B-swizzled smem
-//   dV_j += P^T  dO_i       (M=128 k, N=32, K=128 q; A = P  read MN-major, B = dO_i MN-major) -> TMEM [256,288)
-//   dK_j += dS^T Q_i        (M=128 k, N=32, K=128 q; A = dS read MN-major, B = Q_i  MN-major) -> TMEM [288,320)
-//   dQ_i  = dS  K_j         (M=128 q, N=32, K=128 k; A = dS K-major,       B = K_j  MN-major) -> TMEM [320,352)
+//   for each 64-key half hk of the block (S / dP are single-buffered 64-column tiles so that the CTA needs only 256 TMEM
+//   columns and TWO CTAs share an SM: one CTA's softmax math overlaps the other's MMAs and barrier latencies):
+//     S  = Q_i K_j[hk]^T      (M=128 q, N=64 k, K=32)         -> TMEM [0,64)
+//     dP = dO_i V_j[hk]^T     (M=128 q, N=64 k, K=32)         -> TMEM [64,128)
+//     8 softmax warps: P = exp2(S*c - lse_i), dS = P (dP - D_i) -> bf16 P / dS tiles in 128B-swizzled smem
+//   dV_j += P^T  dO_i       (M=128 k, N=32, K=128 q; A = P  read MN-major, B = dO_i MN-major) -> TMEM [128,160)
+//   dK_j += dS^T Q_i        (M=128 k, N=32, K=128 q; A = dS read MN-major, B = Q_i  MN-major) -> TMEM [160,192)
+//   dQ_i  = dS  K_j         (M=128 q, N=32, K=128 k; A = dS K-major,       B = K_j  MN-major) -> TMEM [192,224)
 // dQ partials of the key blocks are summed with fp32 vector atomics into a workspace and converted
 // (with the 1/sqrt(dh) scale) by a small tail kernel; dK/dV are written directly by the owning CTA.
 // The same smem P/dS tile is consumed both K-major (dQ) and MN-major (dV, dK): no transposes.
@@ -22,9 +24,11 @@ constexpr int DHD = 32;
 constexpr int TILE_QD = BT * DHD * 2;      // 8 KB  ([128][32] bf16)
 constexpr int TILE_P = BT * BT * 2;        // 32 KB
 constexpr int ST = 2;                      // Q/dO stages
-constexpr int BW_SMEM = 2 * TILE_QD /*K,V*/ + ST * 2 * TILE_QD /*Q,dO*/ + 2 * TILE_P /*P,dS*/ + 1024 + 256;
-constexpr int BW_THREADS = 192;
-constexpr uint32_t C_S = 0, C_DP = 128, C_DV = 256, C_DK = 288, C_DQ = 320;
+constexpr int BW_SMEM = 2 * TILE_QD /*K,V*/ + ST * 2 * TILE_QD /*Q,dO*/ + 2 * TILE_P /*P,dS*/ + 256;   // 2 CTAs/SM: 2 x (112.25 KB + 1 KB reserved) <= 228 KB
+constexpr int BW_THREADS = 320;           // TMA warp, MMA warp, 8 softmax warps (2 per TMEM lane quarter: 64 of the 128 keys each)
+constexpr int N_MATH = 256;
+constexpr uint32_t C_S = 0, C_DP = 64, C_DV = 128, C_DK = 160, C_DQ = 192;
+constexpr uint32_t TMEM_COLS = 256;
 constexpr uint32_t SW64 = 4, SW128 = 2;
 
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
@@ -63,13 +67,13 @@ __global__ void dq_convert_kernel(const float* __restrict__ dq32, __nv_bfloat16*
   st8<__nv_bfloat16>(dqkv + r * 768 + c, v);
 }
 
-__global__ void __launch_bounds__(BW_THREADS) attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv,
+__global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv,
                                                                  const __grid_constant__ CUtensorMap tm_do,
                                                                  const int32_t* __restrict__ key_len, const float* __restrict__ lse,
                                                                  const float* __restrict__ dvec, float* __restrict__ dq32,
                                                                  __nv_bfloat16* __restrict__ dqkv, int T, int H) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if (threadIdx.x == 0 && (smem_u32(smem) & 1023u)) { printf("eec: attn_bwd smem base not 1024-aligned\n"); __trap(); }
   uint8_t* sK = smem;
   uint8_t* sV = sK + TILE_QD;
   uint8_t* sQ = sV + TILE_QD;                 // [ST]
@@ -81,8 +85,8 @@ __global__ void __launch_bounds__(BW_THREADS) attn_bwd_tc_kernel(const __grid_co
   uint64_t* qdo_full = bars + 1;     // [2]
   uint64_t* qdo_empty = bars + 3;    // [2]
   uint64_t* sdp_full = bars + 5;
-  uint64_t* sdp_free = bars + 6;     // 128 arrivals
-  uint64_t* pds_full = bars + 7;     // 128 arrivals
+  uint64_t* sdp_free = bars + 6;     // N_MATH arrivals
+  uint64_t* pds_full = bars + 7;     // N_MATH arrivals
   uint64_t* dq_full = bars + 8;
   uint64_t* acc_full = bars + 9;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 10);
@@ -101,13 +105,13 @@ __global__ void __launch_bounds__(BW_THREADS) attn_bwd_tc_kernel(const __grid_co
     mbar_init(kv_full, 1);
     for (int s = 0; s < ST; ++s) { mbar_init(&qdo_full[s], 1); mbar_init(&qdo_empty[s], 1); }
     mbar_init(sdp_full, 1);
-    mbar_init(sdp_free, 128);
-    mbar_init(pds_full, 128);
+    mbar_init(sdp_free, N_MATH);
+    mbar_init(pds_full, N_MATH);
     mbar_init(dq_full, 1);
     mbar_init(acc_full, 1);
     fence_barrier_init();
   }
-  if (warp == 1) { tmem_alloc(tmem_ptr_smem, 512); tmem_relinquish(); }
+  if (warp == 1) { tmem_alloc(tmem_ptr_smem, TMEM_COLS); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -128,7 +132,7 @@ __global__ void __launch_bounds__(BW_THREADS) attn_bwd_tc_kernel(const __grid_co
     }
   } else if (warp == 1) {
     if (lane == 0 && active) {
-      constexpr uint32_t id_s = make_idesc_bf16(BT, BT, false, false);    // S, dP
+      constexpr uint32_t id_s = make_idesc_bf16(BT, 64, false, false);    // S, dP (64-key half)
       constexpr uint32_t id_t = make_idesc_bf16(BT, DHD, true, true);     // dV, dK : A^T (MN-major), B MN-major
       constexpr uint32_t id_q = make_idesc_bf16(BT, DHD, false, true);    // dQ     : A K-major,      B MN-major
       mbar_wait(kv_full, 0);
@@ -136,17 +140,22 @@ __global__ void __launch_bounds__(BW_THREADS) attn_bwd_tc_kernel(const __grid_co
       for (int i = 0; i < nq; ++i) {
         const int s = i % ST;
         mbar_wait(&qdo_full[s], (i / ST) & 1);
-        if (i > 0) mbar_wait(sdp_free, (i - 1) & 1);
-        tc_fence_after();
         const uint32_t aq = smem_u32(sQ + s * TILE_QD), ado = smem_u32(sdO + s * TILE_QD);
+        for (int hk = 0; hk < 2; ++hk) {
+          const int n = 2 * i + hk;                    // half-step counter: phases of sdp_full / sdp_free / pds_full
+          if (n > 0) mbar_wait(sdp_free, (n - 1) & 1);  // the softmax warps have read the previous S / dP out of TMEM
+          tc_fence_after();
+          const uint32_t koff = hk * 64 * 64;          // 64 key rows of 64 B
 #pragma unroll
-        for (int k = 0; k < DHD / 16; ++k)
-          umma_bf16(tmem_base + C_S, make_smem_desc(aq + k * 32, 0, 512, SW64), make_smem_desc(ak + k * 32, 0, 512, SW64), id_s, k);
+          for (int k = 0; k < DHD / 16; ++k)
+            umma_bf16(tmem_base + C_S, make_smem_desc(aq + k * 32, 0, 512, SW64), make_smem_desc(ak + koff + k * 32, 0, 512, SW64), id_s, k);
 #pragma unroll
-        for (int k = 0; k < DHD / 16; ++k)
-          umma_bf16(tmem_base + C_DP, make_smem_desc(ado + k * 32, 0, 512, SW64), make_smem_desc(av + k * 32, 0, 512, SW64), id_s, k);
-        umma_commit(sdp_full);
-        mbar_wait(pds_full, i & 1);
+          for (int k = 0; k < DHD / 16; ++k)
+            umma_bf16(tmem_base + C_DP, make_smem_desc(ado + k * 32, 0, 512, SW64), make_smem_desc(av + koff + k * 32, 0, 512, SW64), id_s, k);
+          umma_commit(sdp_full);
+          if (hk == 1) mbar_wait(pds_full, (n - 1) & 1);   // phases complete in order: wait for both halves' P / dS
+        }
+        mbar_wait(pds_full, (2 * i + 1) & 1);
         tc_fence_after();
 #pragma unroll
         for (int k = 0; k < BT / 16; ++k) {  // contraction over the 128 queries of block i
@@ -166,6 +175,7 @@ __global__ void __launch_bounds__(BW_THREADS) attn_bwd_tc_kernel(const __grid_co
     }
   } else {
     const int q = warp & 3;
+    const int half = (warp - 2) >> 2;          // 32 of the 64 key columns of a half-step
     const int r = q * 32 + lane;
     const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
     const float LOG2E = 1.4426950408889634f;
@@ -177,24 +187,44 @@ __global__ void __launch_bounds__(BW_THREADS) attn_bwd_tc_kernel(const __grid_co
         const bool rvalid = t < T;
         const float l2 = rvalid ? lse[((long)b * H + h) * T + t] * LOG2E : 0.f;
         const float di = rvalid ? dvec[((long)b * H + h) * T + t] : 0.f;
-        mbar_wait(sdp_full, i & 1);
-        tc_fence_after();
+#pragma unroll 1
+        for (int hk = 0; hk < 2; ++hk) {
+          const int n = 2 * i + hk;
+          const int c0 = hk * 64 + half * 32;    // first key column (within the block) of this warp's slab
+          mbar_wait(sdp_full, n & 1);
+          tc_fence_after();
+          tmem_ld32x2(trow + C_S + half * 32, trow + C_DP + half * 32, s, dp);
+          tc_fence_before();
+          mbar_arrive(sdp_free);                  // S / dP are in registers: the MMA warp may start the next half
+          if (rvalid && k0 + c0 + 32 <= klen) {   // common case: no masked key in this slab
 #pragma unroll
-        for (int c0 = 0; c0 < BT; c0 += 32) {
-          tmem_ld32(trow + C_S + c0, s);
-          tmem_ld32(trow + C_DP + c0, dp);
+            for (int e = 0; e < 32; ++e) {
+              float p;
+              asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p) : "f"(fmaf(s[e], sc2, -l2)));
+              s[e] = p;
+              dp[e] = p * (dp[e] - di);
+            }
+          } else {
 #pragma unroll
-          for (int e = 0; e < 32; ++e) {
-            const bool ok = rvalid && (k0 + c0 + e < klen);
-            const float p = ok ? exp2f(fmaf(s[e], sc2, -l2)) : 0.f;
-            s[e] = p;
-            dp[e] = p * (dp[e] - di);
+            for (int e = 0; e < 32; ++e) {
+              const bool ok = rvalid && (k0 + c0 + e < klen);
+              float p;
+              asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p) : "f"(fmaf(s[e], sc2, -l2)));
+              p = ok ? p : 0.f;
+              s[e] = p;
+              dp[e] = ok ? p * (dp[e] - di) : 0.f;
+            }
           }
-          uint8_t* prow = sP + (c0 >> 6) * 16384 + r * 128;
-          uint8_t* drow = sdS + (c0 >> 6) * 16384 + r * 128;
+          if (hk == 0 && i > 0 && half == 1) {
+            // (P / dS of the previous query block are still being read by its dV / dK / dQ MMAs until dq_full flips;
+            //  the half-0 warps wait for dq_full anyway when they drain dQ)
+            mbar_wait(dq_full, (i - 1) & 1);
+          }
+          uint8_t* prow = sP + hk * 16384 + r * 128;
+          uint8_t* drow = sdS + hk * 16384 + r * 128;
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
-            const int off = ((((c0 & 63) >> 3) + g) ^ (r & 7)) << 4;
+            const int off = ((half * 4 + g) ^ (r & 7)) << 4;
             uint4 u, w;
             __nv_bfloat162* hu = reinterpret_cast<__nv_bfloat162*>(&u);
             __nv_bfloat162* hw = reinterpret_cast<__nv_bfloat162*>(&w);
@@ -206,44 +236,41 @@ __global__ void __launch_bounds__(BW_THREADS) attn_bwd_tc_kernel(const __grid_co
             *reinterpret_cast<uint4*>(prow + off) = u;
             *reinterpret_cast<uint4*>(drow + off) = w;
           }
+          fence_proxy_async();
+          mbar_arrive(pds_full);
         }
-        tc_fence_before();
-        mbar_arrive(sdp_free);
-        fence_proxy_async();
-        mbar_arrive(pds_full);
-        mbar_wait(dq_full, i & 1);
-        tc_fence_after();
-        tmem_ld32(trow + C_DQ, s);
-        if (rvalid) {
-          float* dst = dq32 + ((long)(row0 + t)) * D + h * DHD;
+        if (half == 0) {   // dQ partial of this (query block, key block): 128 rows x 32, one lane quarter per warp
+          mbar_wait(dq_full, i & 1);
+          tc_fence_after();
+          tmem_ld32(trow + C_DQ, s);
+          if (rvalid) {
+            float* dst = dq32 + ((long)(row0 + t)) * D + h * DHD;
 #pragma unroll
-          for (int g = 0; g < 8; ++g) red_add_v4(dst + g * 4, s[g * 4], s[g * 4 + 1], s[g * 4 + 2], s[g * 4 + 3]);
+            for (int g = 0; g < 8; ++g) red_add_v4(dst + g * 4, s[g * 4], s[g * 4 + 1], s[g * 4 + 2], s[g * 4 + 3]);
+          }
+          tc_fence_before();
         }
-        tc_fence_before();
       }
       mbar_wait(acc_full, 0);
       tc_fence_after();
     }
-    // dK / dV rows of this key block (zeros for fully masked blocks)
+    // dK / dV rows of this key block (zeros for fully masked blocks): the half-0 warps write dV, the half-1 warps dK
     const int tk = k0 + r;
     if (active) {
-      tmem_ld32(trow + C_DV, s);
-      tmem_ld32(trow + C_DK, dp);
+      tmem_ld32(trow + (half == 0 ? C_DV : C_DK), s);
     } else {
 #pragma unroll
-      for (int e = 0; e < 32; ++e) { s[e] = 0.f; dp[e] = 0.f; }
+      for (int e = 0; e < 32; ++e) s[e] = 0.f;
     }
     if (tk < T) {
-      const float scale = rsqrtf((float)DHD);
-      __nv_bfloat16* dk = dqkv + ((long)(row0 + tk)) * D3 + D + h * DHD;
-      __nv_bfloat16* dv = dqkv + ((long)(row0 + tk)) * D3 + 2 * D + h * DHD;
+      const float scale = (half == 0) ? 1.0f : rsqrtf((float)DHD);
+      __nv_bfloat16* dst = dqkv + ((long)(row0 + tk)) * D3 + (half == 0 ? 2 * D : D) + h * DHD;
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
-        float a[8], c[8];
+        float a[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) { a[e] = dp[g * 8 + e] * scale; c[e] = s[g * 8 + e]; }
-        st8<__nv_bfloat16>(dk + g * 8, a);
-        st8<__nv_bfloat16>(dv + g * 8, c);
+        for (int e = 0; e < 8; ++e) a[e] = s[g * 8 + e] * scale;
+        st8<__nv_bfloat16>(dst + g * 8, a);
       }
     }
     tc_fence_before();
@@ -251,7 +278,7 @@ __global__ void __launch_bounds__(BW_THREADS) attn_bwd_tc_kernel(const __grid_co
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
