@@ -6,7 +6,8 @@
 
 `install()` imports the reference's ``models.model.early_exit`` and replaces ``Early_conformer`` and
 ``Splitformer`` (early_exit.py:565-634, :227-364) by the eec classes of the same constructor signature,
-forward contract and state_dict layout.  ``full_conformer`` / ``Early_zipformer`` stay the reference's own
+forward contract and state_dict layout; ``full_conformer`` (AED mode, :637-811) is replaced by ``eec.full_conformer``
+(encoder half on the B200 kernels, torch.nn decoders as in the reference).  ``Early_zipformer`` stays the reference's own
 (out of this path's scope).  `install(ctc=True)` additionally makes ``torch.nn.CTCLoss`` calls
 with the reference's configuration (blank=0, zero_infinity=True) resolve to ``eec.CTCLoss``.
 """
@@ -21,6 +22,7 @@ def install(ctc: bool = False, precision: str | None = None):
     ref = importlib.import_module("models.model.early_exit")
     ref.Early_conformer = eec.Early_conformer
     ref.Splitformer = eec.Splitformer
+    ref.full_conformer = eec.full_conformer
     if precision is not None:
         import os
         os.environ["EEC_PRECISION"] = precision

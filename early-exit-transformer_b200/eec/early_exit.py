@@ -110,24 +110,28 @@ class Conformer(nn.Module):
 
 # ------------------------------------------------------------------ autograd bridge
 class _EncoderFn(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, module, want_tape, src, lengths, *params):
-        P = module._tensor_dict()
-        out, tape = engine.model_forward(P, module._operands, module._cfg(), src, lengths, module.training, want_tape)
-        ctx.module, ctx.tape, ctx.P = module, tape, P
-        return out
+    """forward(module, want_tape, cfg, want_hidden, src, lengths, *params) -> out | (out, hidden)."""
 
     @staticmethod
-    def backward(ctx, gout):
+    def forward(ctx, module, want_tape, cfg, want_hidden, src, lengths, *params):
+        P = module._tensor_dict()
+        side = {"want_hidden": True} if want_hidden else None
+        out, tape = engine.model_forward(P, module._operands, cfg, src, lengths, module.training, want_tape, side)
+        ctx.module, ctx.tape, ctx.P, ctx.cfg, ctx.want_hidden = module, tape, P, cfg, want_hidden
+        return (out, side["hidden"]) if want_hidden else out
+
+    @staticmethod
+    def backward(ctx, gout, ghid=None):
         m = ctx.module
         if ctx.tape is None:
             raise NotImplementedError("eec: backward is only supported in train() mode with grad enabled "
                                       "(eval-mode BatchNorm backward is not implemented)")
         names = m._param_names
-        G = engine.model_backward(ctx.P, m._operands, m._cfg(), ctx.tape, gout, names)
+        G = engine.model_backward(ctx.P, m._operands, ctx.cfg, ctx.tape, gout, names,
+                                  ghid.contiguous() if ctx.want_hidden and ghid is not None else None)
         ctx.tape = None
         m.__dict__["_flat_grad"] = G["__flat__"]  # p.grad tensors are views of this buffer (DP all-reduces it once)
-        return (None, None, None, None) + tuple(G[n] for n in names)
+        return (None, None, None, None, None, None) + tuple(G[n] for n in names)
 
 
 class _EarlyExitBase(nn.Module):
@@ -202,7 +206,7 @@ class _EarlyExitBase(nn.Module):
         self._check_supported()
         params = [p for _, p in self.named_parameters()]
         want_tape = self.training and torch.is_grad_enabled() and any(p.requires_grad for p in params)
-        return _EncoderFn.apply(self, want_tape, src, lengths, *params)
+        return _EncoderFn.apply(self, want_tape, self._cfg(), False, src, lengths, *params)
 
     # ---- north-star extension (not in the reference) -------------------------
     @torch.no_grad()

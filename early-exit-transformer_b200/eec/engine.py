@@ -350,7 +350,9 @@ def check_lengths(lengths: Tensor, T: int):
 def model_forward(P: Dict[str, Tensor], W: Operands, cfg: Config, src: Tensor, lengths: Tensor, training: bool,
                   want_tape: bool, side: Optional[dict] = None):
     """-> (out [E,B,T,V] fp32 log-probs, Tape|None).  `side` (optional dict) receives per-exit
-    argmax / frame-entropy tensors when it contains the key "want"."""
+    argmax / frame-entropy tensors when it contains the key "want", and -- when it contains the key
+    "want_hidden" -- side["hidden"] = [E,B,T,D] fp32 encoder states after every exit group (what
+    full_conformer's decoders attend to, early_exit.py:783-786)."""
     if not src.is_cuda:
         raise EecError("eec: input must be on a CUDA device; there is no CPU path")
     src = src.contiguous()
@@ -368,7 +370,11 @@ def model_forward(P: Dict[str, Tensor], W: Operands, cfg: Config, src: Tensor, l
     E = cfg.n_exits
     out = _empty((E, B, T, V), f32, dev)
     logits_ws = _empty((N, V), f32, dev) if cfg.precision == "fp32" else None
-    want_side = side is not None
+    want_side = side is not None and "want" in side
+    hidden = None
+    if side is not None and "want_hidden" in side:
+        hidden = _empty((E, B, T, D), f32, dev)
+        side["hidden"] = hidden
     for e in range(E):
         x_in = x
         for l in range(cfg.n_layers):
@@ -396,6 +402,8 @@ def model_forward(P: Dict[str, Tensor], W: Operands, cfg: Config, src: Tensor, l
             ops.repeat2_add(yd, x, B, T)
         if tape:
             tape.branches.append(br)
+        if hidden is not None:
+            hidden[e].view(N, D).copy_(x)   # layout plumbing: the residual stream buffer is reused by later layers
         xh = to_act(x, cfg)
         Wh = W.get(f"linears.{e}.weight", P[f"linears.{e}.weight"], (V, D))
         am = _empty((N,), torch.int32, dev) if want_side else None
@@ -413,8 +421,10 @@ def model_forward(P: Dict[str, Tensor], W: Operands, cfg: Config, src: Tensor, l
     return out, tape
 
 
-def model_backward(P, W: Operands, cfg: Config, tape: Tape, gout: Tensor, names: List[str]) -> Dict[str, Tensor]:
-    """gout: grad wrt out [E,B,T,V] (fp32).  Returns fp32 grads for every name in `names`."""
+def model_backward(P, W: Operands, cfg: Config, tape: Tape, gout: Tensor, names: List[str],
+                   ghid: Optional[Tensor] = None) -> Dict[str, Tensor]:
+    """gout: grad wrt out [E,B,T,V] (fp32); ghid (optional): grad wrt the per-exit encoder states [E,B,T,D]
+    (the decoders' cross-attention in AED mode).  Returns fp32 grads for every name in `names`."""
     dev, f32 = gout.device, torch.float32
     gout = gout.contiguous()
     B, T = tape.B, tape.T
@@ -444,6 +454,8 @@ def model_backward(P, W: Operands, cfg: Config, tape: Tape, gout: Tensor, names:
             dgrad(dlogh, Wh, dX, N, V, D)
         else:
             dgrad(dlogh, Wh, dX, N, V, D, residual=dX)
+        if ghid is not None:
+            dX.add_(ghid[e].reshape(N, D))   # plumbing: the second consumer of this exit's state
         br = tape.branches[e]
         d_in_extra = None
         if br is not None:

@@ -22,7 +22,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, "/root/reference")
 sys.dont_write_bytecode = True
 
-from models.model.early_exit import Early_conformer, Splitformer  # noqa: E402  (the reference)
+from models.model.early_exit import Early_conformer, Splitformer, full_conformer  # noqa: E402  (the reference)
 from oracle import conformer_oracle as O  # noqa: E402
 
 CASES = {
@@ -111,6 +111,75 @@ def run_case(name, kind, n_exits, n_layers, B, t_in, lo, hi, seed):
     print(name, "T'=", T, "loss=", loss.item(), os.path.getsize(path) // 1024, "KiB")
 
 
+FC_RENAME = (("linears.", "linears_1."), ("positional_encoder.", "positional_encoder_1."))
+AED_CE_WEIGHT, AED_CTC_WEIGHT = 0.7, 0.3   # util/conf.py --aed_ce_weight / --aed_ctc_weight defaults
+
+
+def fc_state_dict(sd):
+    """Early_conformer-layout encoder parameters -> full_conformer key names (early_exit.py:671-686)."""
+    out = {}
+    for k, v in sd.items():
+        for a, b in FC_RENAME:
+            if k.startswith(a):
+                k = b + k[len(a):]
+                break
+        out[k] = v
+    return out
+
+
+def run_fc_case(name, n_exits, n_layers, n_dec, B, t_in, lo, hi, seed):
+    """full_conformer (AED mode, early_exit.py:637-811): encoder parameters from make_params, decoder /
+    embedding parameters = the reference's own default init under torch.manual_seed(seed) (regenerated at test time)."""
+    kw = dict(trg_pad_idx=126, n_enc_exits=n_exits, enc_voc_size=256, dec_voc_size=256, d_model=256, n_head=8, max_len=2000,
+              d_feed_forward=2048, n_enc_layers=n_layers, n_dec_layers=n_dec, features_length=80, drop_prob=0.0,
+              depthwise_kernel_size=31, device=torch.device("cpu"))
+    enc_sd = fc_state_dict(O.make_params(seed, n_exits=n_exits, n_layers=n_layers))
+    src, lengths = O.synthetic_batch(B, t_in, seed=seed + 1)
+    targets, tl = O.synthetic_targets(B, seed=seed + 2, lo=lo, hi=hi)
+    trg, trg_expect = targets[:, :-1], targets[:, 1:]     # train.py:30-32
+
+    def build():
+        torch.manual_seed(seed)
+        m = full_conformer(**kw)
+        r = m.load_state_dict(enc_sd, strict=False)
+        assert not r.unexpected_keys and all(k.startswith(("decoders.", "emb.", "layer_norm.", "linears_2.", "positional_encoder_2."))
+                                             for k in r.missing_keys), r
+        return m
+
+    out = {"seed": seed, "B": B, "t_in": t_in, "n_exits": n_exits, "n_layers": n_layers, "n_dec": n_dec,
+           "lengths": lengths.numpy(), "targets": targets.numpy(), "target_lengths": tl.numpy()}
+    m = build().eval()
+    with torch.no_grad():
+        dec_out, enc_out = m(src, lengths, trg)
+        enc1 = m._encoder_(src, lengths, 1)
+        dec1 = m._decoder_(trg, enc1, 1)
+    out.update(eval_dec_out=dec_out.numpy(), eval_enc_out=enc_out.numpy(), encoder_1=enc1.numpy(), decoder_1=dec1.numpy())
+    m = build().train()
+    att_dec, encoder = m(src, lengths, trg)
+    ctc = torch.nn.CTCLoss(blank=0, zero_infinity=True)
+    ce = torch.nn.CrossEntropyLoss()
+    in_len = torch.full((B,), encoder.size(2), dtype=torch.long)
+    loss_ctc = sum(ctc(enc.permute(1, 0, 2), targets, in_len, tl) for enc in encoder)        # train.py:44-46
+    loss_ce = sum(ce(dec.permute(0, 2, 1), trg_expect) for dec in att_dec)                   # train.py:47
+    loss = AED_CE_WEIGHT * loss_ce + AED_CTC_WEIGHT * loss_ctc                                # train.py:51
+    m.zero_grad()
+    loss.backward()
+    out["loss"], out["loss_ce"], out["loss_ctc"] = np.float64(loss.item()), np.float64(loss_ce.item()), np.float64(loss_ctc.item())
+    names, norms = [], []
+    for k, p in m.named_parameters():
+        names.append(k)
+        norms.append(0.0 if p.grad is None else p.grad.double().norm().item())
+    out["grad_names"], out["grad_norms"] = np.array(names), np.array(norms)
+    P = dict(m.named_parameters())
+    l0 = "conformer.0.conformer_layers.0."
+    for k in ["conv_subsample.sequential.0.bias", "linears_1.0.bias", "linears_2.1.bias", l0 + "ffn1.sequential.1.bias",
+              l0 + "final_layer_norm.weight", "layer_norm.weight"]:
+        out["grad::" + k] = P[k].grad.numpy()
+    path = os.path.join(ROOT, "tests", "golden", name + ".npz")
+    np.savez_compressed(path, **out)
+    print(name, "loss=", loss.item(), "ce=", loss_ce.item(), "ctc=", loss_ctc.item(), os.path.getsize(path) // 1024, "KiB")
+
+
 def ctc_cases():
     """Stand-alone CTC known answers from torch.nn.CTCLoss incl. repeats, empty and
     infeasible targets (zero_infinity)."""
@@ -135,3 +204,4 @@ if __name__ == "__main__":
     for i, (name, (kind, e, l, B, t, lo, hi)) in enumerate(CASES.items()):
         run_case(name, kind, e, l, B, t, lo, hi, seed=100 + 10 * i)
     ctc_cases()
+    run_fc_case("fc_e2l1d1_b2_t163", 2, 1, 1, 2, 163, 3, 8, seed=150)

@@ -236,3 +236,60 @@ def test_graphed_train_step_matches_eager(precision):
     assert rel(dict(m.named_parameters())[k].grad, ref_g2[k]) < max(tol, 2e-4)
     with pytest.raises(AssertionError):
         step(src2, torch.full((Bn,), 100, dtype=torch.int64), targets2, tl2)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_full_conformer_aed_vs_reference_golden(precision):
+    """SURVEY §8 row a17 / BASELINE configs[4]: eec.full_conformer (encoder half on the sm_100a kernels, torch.nn decoders
+    as in the reference) against the real reference's outputs: CTC log-probs, decoder logits, `_encoder_` / `_decoder_`,
+    the AED loss (0.7 CE + 0.3 CTC, train.py:44-51) and gradients on both sides of the encoder/decoder boundary."""
+    import eec
+    g = np.load(os.path.join(GOLDEN, "fc_e2l1d1_b2_t163.npz"))
+    seed, B = int(g["seed"]), int(g["B"])
+    kw = dict(trg_pad_idx=126, n_enc_exits=int(g["n_exits"]), enc_voc_size=256, dec_voc_size=256, d_model=256, n_head=8,
+              max_len=2000, d_feed_forward=2048, n_enc_layers=int(g["n_layers"]), n_dec_layers=int(g["n_dec"]), features_length=80,
+              drop_prob=0.0, depthwise_kernel_size=31, device=torch.device("cuda"))
+    torch.manual_seed(seed)                      # decoder / embedding parameters: the reference's default init under this seed
+    m = eec.full_conformer(**kw)
+    enc_sd = {}
+    for k, v in O.make_params(seed, n_exits=kw["n_enc_exits"], n_layers=kw["n_enc_layers"]).items():
+        k = k.replace("linears.", "linears_1.", 1) if k.startswith("linears.") else k
+        k = k.replace("positional_encoder.", "positional_encoder_1.", 1) if k.startswith("positional_encoder.") else k
+        enc_sd[k] = v
+    r = m.load_state_dict(enc_sd, strict=False)
+    assert not r.unexpected_keys
+    m = m.to("cuda")
+    m.precision = precision
+    src, lengths = O.synthetic_batch(B, int(g["t_in"]), seed=seed + 1)
+    targets, tl = torch.from_numpy(g["targets"]), torch.from_numpy(g["target_lengths"])
+    trg, trg_expect = targets[:, :-1].cuda(), targets[:, 1:].cuda()
+    tol = TOL[precision]
+    m.eval()
+    with torch.no_grad():
+        dec_out, enc_out = m(src.cuda(), lengths, trg)
+        enc1 = m._encoder_(src.cuda(), lengths, 1)
+        dec1 = m._decoder_(trg, enc1, 1)
+    assert rel(enc_out, torch.from_numpy(g["eval_enc_out"])) < tol
+    assert rel(dec_out, torch.from_numpy(g["eval_dec_out"])) < tol
+    assert rel(enc1, torch.from_numpy(g["encoder_1"])) < tol
+    assert rel(dec1, torch.from_numpy(g["decoder_1"])) < tol
+    m.train()
+    att_dec, encoder = m(src.cuda(), lengths, trg)
+    ctc = eec.CTCLoss(blank=0, zero_infinity=True)
+    ce = torch.nn.CrossEntropyLoss()
+    in_len = torch.full((B,), encoder.size(2), dtype=torch.long)
+    loss_ctc = sum(ctc(enc.permute(1, 0, 2), targets, in_len, tl) for enc in encoder)
+    loss_ce = sum(ce(dec.permute(0, 2, 1), trg_expect) for dec in att_dec)
+    loss = 0.7 * loss_ce + 0.3 * loss_ctc
+    m.zero_grad()
+    loss.backward()
+    assert abs(float(loss_ctc.detach()) - float(g["loss_ctc"])) < tol * float(g["loss_ctc"])
+    assert abs(float(loss_ce.detach()) - float(g["loss_ce"])) < tol * float(g["loss_ce"])
+    gtol = 5e-3 if precision == "fp32" else 6e-2
+    P = dict(m.named_parameters())
+    gmax = float(np.max(g["grad_norms"]))
+    for name, ref_norm in zip(g["grad_names"], g["grad_norms"]):
+        got = float(P[str(name)].grad.double().norm())
+        assert abs(got - ref_norm) <= gtol * max(ref_norm, 1e-3 * gmax), (str(name), got, ref_norm)
+    for k in ["conv_subsample.sequential.0.bias", "linears_1.0.bias", "linears_2.1.bias", "layer_norm.weight"]:
+        assert rel(P[k].grad, torch.from_numpy(g["grad::" + k])) < gtol * 4, k

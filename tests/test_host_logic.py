@@ -131,3 +131,28 @@ def test_shard_batch_partitions_every_utterance_once():
     x = torch.arange(10)
     parts = [D.shard_batch([x], r, 4)[0] for r in range(4)]
     assert torch.equal(torch.cat(parts), x) and max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
+
+
+def test_full_conformer_mirror_layout_and_init():
+    """eec.full_conformer (AED mode) instantiates the reference's modules in the reference's order:
+    123-entry state_dict for 2 exits x 1 layer x 1 decoder layer, decoder / embedding parameters reproducible from the
+    seed (the golden fixture relies on this), constructor errors preserved."""
+    import eec
+    kw = dict(trg_pad_idx=126, n_enc_exits=2, enc_voc_size=256, dec_voc_size=256, d_model=256, n_head=8, max_len=2000,
+              d_feed_forward=2048, n_enc_layers=1, n_dec_layers=1, features_length=80, drop_prob=0.0, depthwise_kernel_size=31,
+              device=torch.device("cpu"))
+    torch.manual_seed(5)
+    a = eec.full_conformer(**kw)
+    torch.manual_seed(5)
+    b = eec.full_conformer(**kw)
+    sa, sb = a.state_dict(), b.state_dict()
+    assert len(sa) == 123 and list(sa) == list(sb) and all(torch.equal(sa[k], sb[k]) for k in sa)
+    keys = list(sa)
+    assert keys[0] == "layer_norm.weight" and keys[2] == "emb.weight" and "linears_1.0.weight" in sa and "linears_2.1.bias" in sa
+    assert "positional_encoder_1.pe" in sa and "decoders.1.layers.0.multihead_attn.in_proj_weight" in sa
+    assert a._param_names[0] == "conv_subsample.sequential.0.weight" and "linears.0.weight" in a._param_names
+    assert not any(n.startswith(("decoders", "emb", "linears_2")) for n in a._param_names)
+    with pytest.raises(AssertionError):
+        eec.full_conformer(**{**kw, "n_head": 6})
+    with pytest.raises(Exception):   # no CPU path: the encoder half refuses CPU tensors
+        a(torch.zeros(1, 80, 163), torch.tensor([163]), torch.zeros(1, 4, dtype=torch.long))
