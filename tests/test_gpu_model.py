@@ -293,3 +293,28 @@ def test_full_conformer_aed_vs_reference_golden(precision):
         assert abs(got - ref_norm) <= gtol * max(ref_norm, 1e-3 * gmax), (str(name), got, ref_norm)
     for k in ["conv_subsample.sequential.0.bias", "linears_1.0.bias", "linears_2.1.bias", "layer_norm.weight"]:
         assert rel(P[k].grad, torch.from_numpy(g["grad::" + k])) < gtol * 4, k
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_long_utterance_max_len_vs_live_oracle(precision):
+    """BASELINE configs[4] shape edge: T_in = 8001 -> T' = 1999 frames (max_len 2000, the positional table's limit), ragged
+    lengths, one layer: log-probs and the multi-exit CTC loss against the CPU oracle run live."""
+    import eec
+    sd = O.make_params(21, n_exits=1, n_layers=1)
+    src, lengths = O.synthetic_batch(2, 8001, seed=22)
+    targets, tl = O.synthetic_targets(2, seed=23, lo=20, hi=60)
+    m = eec.Early_conformer(src_pad_idx=0, n_enc_exits=1, enc_voc_size=256, dec_voc_size=256, d_model=256, n_head=8, max_len=2000,
+                            d_feed_forward=2048, n_enc_layers=1, features_length=80, drop_prob=0.0, depthwise_kernel_size=31,
+                            device=torch.device("cuda"))
+    m.load_state_dict(sd, strict=True)
+    m = m.to("cuda").train()
+    m.precision = precision
+    out = m(src.cuda(), lengths)
+    assert out.shape == (1, 2, 1999, 256)
+    loss = eec.multi_exit_ctc_loss(out, targets, tl)
+    loss.backward()
+    ref = O.early_conformer_forward(sd, src, lengths, training=True)
+    ref_loss, _, _ = O.multi_exit_ctc(ref.double(), targets, tl)
+    assert rel(out.detach(), ref.detach()) < TOL[precision]
+    assert abs(float(loss.detach()) - float(ref_loss)) < TOL[precision] * abs(float(ref_loss))
+    assert float(m.conformer[0].conformer_layers[0].ffn1.sequential[1].weight.grad.norm()) > 0
