@@ -132,10 +132,14 @@ def run_ours(args):
     tg_dev, tl_dev = targets.to(dev), tl.to(dev)
     T = t_out(T_IN)
 
+    # optimiser: clip_grad_norm_ + Noam + AdamW as three launches over flat buffers, reference hyper-parameters
+    opt = None if args.no_opt else eec.FusedNoamAdamW(model, model_size=256, warmup=25000, betas=(0.9, 0.98), eps=1e-9,
+                                                      weight_decay=5e-4, clip=1.0)
     graphed = None
     if not args.no_graph:
-        # the whole step (operand casts, forward, 6-exit CTC, backward) is ONE CUDA graph: one launch per step
-        graphed = eec.GraphedTrainStep(model, B, T_IN, targets.shape[1])
+        # the whole step (forward, 6-exit CTC, backward; + the optimiser at N=1) is ONE CUDA graph: one launch per step.
+        # Under data parallelism the NCCL all-reduce sits between backward and the update, so the update stays outside.
+        graphed = eec.GraphedTrainStep(model, B, T_IN, targets.shape[1], optimizer=opt if world == 1 else None)
         graphed.load_inputs(src_dev, lengths, tg_dev, tl_dev)
 
     def step(x):
@@ -148,8 +152,12 @@ def run_ours(args):
             loss = eec.multi_exit_ctc_loss(out, tg_dev, tl_dev)
             model.zero_grad(set_to_none=True)
             loss.backward()
+            if opt is not None and world == 1:
+                opt.step()
         if world > 1:
             dist.all_reduce(model._flat_grad, op=dist.ReduceOp.AVG)
+            if opt is not None:
+                opt.step()
         return loss
 
     if graphed is not None:
@@ -226,7 +234,8 @@ def run_ours(args):
             "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
             "config": {"workload": f"early_conformer CTC training step (fwd + summed 6-exit CTC + bwd), {N_EXITS} exits x {layers} "
                                    f"layers, d_model 256, batch {B}/GPU x 15 s (T_in {T_IN} -> T' {T}), grad all-reduce "
-                                   f"{'NCCL fp32 flat buffer' if world > 1 else 'n/a'}; optimizer step excluded (SURVEY 8f N1)",
+                                   f"{'NCCL fp32 flat buffer' if world > 1 else 'n/a'}; "
+                                   + ("optimizer step excluded" if opt is None else "clip_grad_norm + Noam + AdamW update included (fused, flat buffers)"),
                        "global_batch": world * B, "parallelism": f"dp{world}",
                        "l2": "per-step working set ~8 GB >> 126 MB L2 (no flush needed)",
                        "launch": "eager (ctypes launches)" if graphed is None else "one CUDA graph replay per step",
@@ -375,6 +384,7 @@ def main():
     ap.add_argument("--layers-per-exit", type=int, default=2, help="2 = BASELINE configs[1]; 3 = configs[2] (18 layers)")
     ap.add_argument("--cpu-sample", type=int, default=64, help="utterances per CPU-baseline step (64 = the full batch)")
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--no-opt", action="store_true", help="time forward + loss + backward only (no clip / Noam / AdamW update)")
     ap.add_argument("--no-graph", action="store_true", help="issue the ~600 kernels of a step eagerly instead of replaying the CUDA graph")
     ap.add_argument("--skip-rtfx", action="store_true")
     ap.add_argument("--profile", action="store_true", help="bracket the timed region with cudaProfilerStart/Stop (for ncu "

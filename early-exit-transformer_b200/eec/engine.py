@@ -52,10 +52,23 @@ class Operands:
     def __init__(self, cfg: Config):
         self.cfg = cfg
         self._cache: Dict[str, tuple] = {}
+        self._shadow: Optional[Tensor] = None      # flat bf16 copy of all parameters maintained by eec.FusedNoamAdamW
+        self._shadow_off: Dict[str, tuple] = {}
+        self._shadow_ver: Dict[str, int] = {}
+
+    def attach_shadow(self, shadow: Tensor, offsets: Dict[str, tuple], versions: Dict[str, int]) -> None:
+        self._shadow, self._shadow_off, self._shadow_ver = shadow, offsets, versions
+
+    def invalidate(self) -> None:
+        """Parameters changed through a raw pointer (fused optimiser): drop every cached cast."""
+        self._cache.clear()
 
     def get(self, name: str, p: Tensor, shape2d) -> Tensor:
         if self.cfg.precision == "fp32":
             return p.detach().reshape(shape2d)
+        if self._shadow is not None and self._shadow_ver.get(name) == p._version and name in self._shadow_off:
+            off, k = self._shadow_off[name]
+            return self._shadow[off:off + k].view(shape2d)   # kept current by the optimiser's own update pass
         key = (p.data_ptr(), p._version)
         hit = self._cache.get(name)
         if hit is not None and hit[0] == key:

@@ -31,7 +31,7 @@ from .lib import EecError, load
 
 class GraphedTrainStep:
     def __init__(self, model, batch_size: int, t_in: int, max_target_len: int, n_mels: Optional[int] = None, blank: int = 0,
-                 pad_token: int = 126, warmup: int = 2):
+                 pad_token: int = 126, warmup: int = 2, optimizer=None):
         params = list(model.parameters())
         if not params or not params[0].is_cuda:
             raise EecError("GraphedTrainStep: move the model to a CUDA device first (no CPU path)")
@@ -39,6 +39,9 @@ class GraphedTrainStep:
             raise EecError("GraphedTrainStep captures a TRAINING step: call model.train() first")
         dev = params[0].device
         self.model, self.blank, self.pad_token = model, blank, pad_token
+        # optimizer (eec.FusedNoamAdamW, single-GPU): its three launches join the graph, so a replay is a COMPLETE training
+        # step; under data parallelism leave it None and call all_reduce_gradients(model); opt.step() after the replay
+        self.optimizer = optimizer
         self.B, self.T_in, self.L = batch_size, t_in, max_target_len
         n_mels = n_mels if n_mels is not None else model._features_length
         # static device buffers the graph reads, and pinned host staging for the per-step uploads
@@ -56,7 +59,7 @@ class GraphedTrainStep:
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):   # eager warm-up off the default stream (lazy module loads, kernel attributes, tensor maps)
             for _ in range(max(warmup, 1)):
-                self._eager_step()
+                self._eager_step(with_optimizer=False)   # (warm-up must not move the weights)
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         # parameter casts must be IN the graph: drop the operand cache so capture re-issues them
@@ -70,10 +73,12 @@ class GraphedTrainStep:
         self.loss = loss.detach()
         self.flat_grad = model.__dict__.get("_flat_grad")
 
-    def _eager_step(self):
+    def _eager_step(self, with_optimizer: bool = True):
         out = self.model(self.src, self.lengths)
         loss = multi_exit_ctc_loss(out, self.targets, self.target_lengths, self.blank)
         loss.backward()
+        if with_optimizer and self.optimizer is not None:
+            self.optimizer.step()
         return loss
 
     def load_inputs(self, src: torch.Tensor, lengths: torch.Tensor, targets: torch.Tensor, target_lengths: torch.Tensor) -> None:

@@ -193,6 +193,16 @@ int eec_colsum(const void* in, int dtype, int ld, float* out, float scale, int r
                eec_stream_t stream);
 /* y = (*s_dev) * x  (device scalar; used to apply an upstream loss gradient without a host sync) */
 int eec_scale_dev(const float* x, const float* s_dev, float* y, int64_t n, eec_stream_t stream);
+
+/* ---- optimiser step over flat buffers: torch.nn.utils.clip_grad_norm_ (train.py:69) + NoamOpt.step
+ *      (util/noam_opt.py:26-40) + torch.optim.AdamW.step (train.py:261-262) in three launches, no host sync.
+ *      params / grads / exp_avg / exp_avg_sq: fp32 [n], 16-byte aligned.  bf16_shadow (optional, bf16 [n]) receives the
+ *      updated parameters as GEMM operands.  state: double[4] on the device = {step t, sum g^2, last lr, last clip coefficient};
+ *      the call increments t.  clip <= 0 disables clipping; lr_fixed >= 0 replaces the Noam rate
+ *      lr = model_size^-0.5 * min(t^-0.5, t * warmup^-1.5). */
+int eec_noam_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, void* bf16_shadow, int64_t n,
+                        double* state, float model_size, float warmup, float beta1, float beta2, float eps, float weight_decay,
+                        float clip, float lr_fixed, eec_stream_t stream);
 /* y = a*x + y over n floats */
 int eec_axpy(const float* x, float a, float* y, int64_t n, eec_stream_t stream);
 

@@ -318,3 +318,85 @@ def test_long_utterance_max_len_vs_live_oracle(precision):
     assert rel(out.detach(), ref.detach()) < TOL[precision]
     assert abs(float(loss.detach()) - float(ref_loss)) < TOL[precision] * abs(float(ref_loss))
     assert float(m.conformer[0].conformer_layers[0].ffn1.sequential[1].weight.grad.norm()) > 0
+
+
+def _noam_rate(step, d_model, warmup):   # util/noam_opt.py:35-40
+    return d_model ** (-0.5) * min(step ** (-0.5), step * warmup ** (-1.5))
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_fused_noam_adamw_matches_torch(precision):
+    """eec.FusedNoamAdamW == clip_grad_norm_ (train.py:69) + NoamOpt (util/noam_opt.py) + torch.optim.AdamW
+    (train.py:261-262) applied on the CPU to the SAME gradients, over several steps; the bf16 operand shadow follows the
+    weights (the next forward equals a forward of a fresh model holding the updated parameters)."""
+    import eec
+    name = "ec_e2l1_b3_t163"
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    m, sd, src, lengths = build(name, g, precision)
+    m.train()
+    targets, tl = O.synthetic_targets(src.shape[0], seed=31, lo=3, hi=6)
+    warmup, clip, wd = 4, 0.05, 5e-4     # tiny warm-up so the rate moves; clip small enough to be active
+    opt = eec.FusedNoamAdamW(m, model_size=256, warmup=warmup, betas=(0.9, 0.98), eps=1e-9, weight_decay=wd, clip=clip)
+    ref_p = [p.detach().cpu().clone().requires_grad_(True) for p in m.parameters()]
+    ref_opt = torch.optim.AdamW(ref_p, lr=0.0, betas=(0.9, 0.98), eps=1e-9, weight_decay=wd)
+    x = src.cuda()
+    for step in range(1, 4):
+        opt.zero_grad()
+        loss = eec.multi_exit_ctc_loss(m(x, lengths), targets, tl)
+        loss.backward()
+        grads = [p.grad.detach().cpu().clone() for p in m.parameters()]
+        opt.step()
+        for rp, gr in zip(ref_p, grads):
+            rp.grad = gr
+        total = torch.nn.utils.clip_grad_norm_(ref_p, clip)
+        for grp in ref_opt.param_groups:
+            grp["lr"] = _noam_rate(step, 256, warmup)
+        ref_opt.step()
+        assert opt._step == step
+        assert abs(opt.last_grad_norm() - float(total)) < 1e-4 * float(total)
+        assert abs(opt.rate() - _noam_rate(step, 256, warmup)) < 1e-12
+        for (n, p), rp in zip(m.named_parameters(), ref_p):
+            err = float((p.detach().cpu() - rp.detach()).abs().max())
+            assert err <= 2e-6 * max(1.0, float(rp.detach().abs().max())), (step, n, err)
+    # the next forward sees the updated weights (bf16: through the operand shadow written by the update kernel)
+    m.eval()
+    with torch.no_grad():
+        out = m(x, lengths)
+    m2, _, _, _ = build(name, g, precision)
+    m2.load_state_dict(m.state_dict(), strict=True)
+    m2.eval()
+    with torch.no_grad():
+        out2 = m2(x, lengths)
+    assert rel(out, out2) < 1e-6
+
+
+def test_graphed_step_with_fused_optimizer_trains():
+    """One CUDA graph = forward + 6-exit CTC + backward + clip + Noam/AdamW; replaying it on a fixed batch lowers the loss
+    and matches the eager sequence step for step."""
+    import eec
+    name = "ec_e2l1_b3_t163"
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    targets, tl = O.synthetic_targets(3, seed=41, lo=3, hi=6)
+    losses = {}
+    for mode in ("eager", "graph"):
+        m, sd, src, lengths = build(name, g, "bf16")
+        m.train()
+        opt = eec.FusedNoamAdamW(m, model_size=256, warmup=50, clip=1.0)
+        x = src.cuda()
+        if mode == "graph":
+            step = eec.GraphedTrainStep(m, 3, src.shape[2], targets.shape[1], optimizer=opt)
+            step.load_inputs(x, lengths, targets, tl)
+            losses[mode] = [float(step.replay().clone()) for _ in range(6)]
+            assert opt._step == 6
+        else:
+            ls = []
+            for _ in range(6):
+                opt.zero_grad()
+                loss = eec.multi_exit_ctc_loss(m(x, lengths), targets, tl)
+                loss.backward()
+                opt.step()
+                ls.append(float(loss.detach()))
+            losses[mode] = ls
+    assert losses["graph"][-1] < losses["graph"][0]
+    for a, b in zip(losses["eager"], losses["graph"]):
+        assert abs(a - b) < 2e-2 * abs(a), (losses["eager"], losses["graph"])
