@@ -106,6 +106,7 @@ int gemm_simt(const eec_gemm_desc* d, cudaStream_t st);
 int gemm_tc(const eec_gemm_desc* d, cudaStream_t st, int32_t* argmax, float* entropy, int logsoftmax);   // v1 (EEC_GEMM_V1=1)
 int gemm_tc2(const eec_gemm_desc* d, cudaStream_t st, int32_t* argmax, float* entropy, int logsoftmax);  // persistent v2
 int gemm_tc3(const eec_gemm_desc* d, cudaStream_t st);   // v3 epilogue (GENERIC / GLU modes), called by gemm_tc2
+int gemm_ln3(const eec_gemm_desc* d, cudaStream_t st);   // v3 LayerNorm-tail epilogue (N == 256), called by gemm_tc2
 int attn_bwd_tc(const void* qkv, const void* ctx, const void* dctx, const float* lse, const int32_t* key_len, void* dqkv,
                 float* dvec, float* dq32, int B, int T, int H, int dh, cudaStream_t st);
 int attn_fwd_tc(const void* qkv, const int32_t* key_len, void* ctx, float* lse, int B, int T, int H, int dh,

@@ -464,6 +464,7 @@ int gemm_tc2(const eec_gemm_desc* d, cudaStream_t st, int32_t* argmax, float* en
     // (v3 stages dSiLU / SiLU+pre-activation outputs in bf16 boxes only; the fp32-output variants of those stay here)
     const bool v3_ok = d->out_dtype == EEC_BF16 || !(d->act == EEC_ACT_DSILU || (d->act == EEC_ACT_SILU && d->preact));
     if (!v2_env && v3_ok && (epi == EPI_GENERIC || epi == EPI_GLU)) return gemm_tc3(d, st);
+    if (!v2_env && epi == EPI_LN && d->res_row_mod == 0 && (!d->residual || d->ldr == 256)) return gemm_ln3(d, st);
   }
   if (!g_num_sms) {
     int dev = 0;

@@ -493,6 +493,253 @@ __global__ void __launch_bounds__(NT3, 1) gemm_tc3_kernel(const __grid_constant_
   if (p.tl && blockIdx.x == 0 && threadIdx.x == 32) p.tl[11] = gtime();
 }
 
+
+// ================================================================================================================
+// LayerNorm-tail GEMM (N == 256, K-major operands):  x = residual + alpha * (A W^T + bias) -> fp32 C;  LayerNorm(x) -> ln_out
+// (out-projection, pointwise conv 2 and FFN down-projection of a conformer layer: TA:202, :65, :107 followed by :151/:42/:103/:211).
+// 8 epilogue warps: warp (quarter q, half h) owns rows [32q, 32q+32) x columns [128h, 128h+128) of the tile and keeps its
+// 128 x-values per thread in REGISTERS across the row-statistics exchange, so the accumulator is read from TMEM exactly once
+// (TMEM drains at 64 B/clk: the v2 kernel's TMEM round trip cost two more passes).  The fp32 residual arrives through
+// per-warp TMA loads into two 4 KB staging buffers (first two slabs prefetched before the accumulator is ready); the same
+// buffers stage the x store (each lane overwrites the residual row it just consumed) and the LayerNorm output store.
+constexpr int LN_WARPS = 8;
+constexpr int LN_NT = 64 + LN_WARPS * 32;                 // 320
+constexpr int LN_WBUF = 8192;                             // two 4 KB staging buffers per epilogue warp
+constexpr int LN_OFF_STG = NSTAGE * STAGE_BYTES;
+constexpr int LN_OFF_VEC = LN_OFF_STG + LN_WARPS * LN_WBUF;   // float[3][256]: bias, gamma, beta
+constexpr int LN_OFF_XCH = LN_OFF_VEC + 3 * 256 * 4;          // float[2 halves][128 rows][2]
+constexpr int LN_OFF_BAR = LN_OFF_XCH + 2 * 128 * 2 * 4;
+constexpr int LN_SMEM_BYTES = LN_OFF_BAR + 512 + 1024;
+
+struct PLN {
+  int M, K, m_tiles;
+  const float* bias;
+  float alpha;
+  int has_res, ln_bf16;
+  const float* ln_gamma; const float* ln_beta; float* ln_mean; float* ln_rstd;
+};
+
+__global__ void __launch_bounds__(LN_NT, 1) gemm_ln3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                                                            const __grid_constant__ CUtensorMap tmC,   // fp32 x out (box 32 x 32)
+                                                            const __grid_constant__ CUtensorMap tmR,   // fp32 residual in (box 32 x 32)
+                                                            const __grid_constant__ CUtensorMap tmL,   // LayerNorm out (box 32 x 32)
+                                                            const PLN p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  float* vecs = reinterpret_cast<float*>(smem + LN_OFF_VEC);
+  float* xch = reinterpret_cast<float*>(smem + LN_OFF_XCH);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + LN_OFF_BAR);
+  uint64_t* empty_bar = full_bar + NSTAGE;
+  uint64_t* tfull_bar = empty_bar + NSTAGE;   // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;       // [2]
+  uint64_t* res_bar = tempty_bar + 2;         // [LN_WARPS][2]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(res_bar + 2 * LN_WARPS);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total_kb = (p.K + BK - 1) / BK;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmR);
+    for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], LN_WARPS); }
+    for (int w = 0; w < 2 * LN_WARPS; ++w) mbar_init(&res_bar[w], 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_ptr_smem, 512); tmem_relinquish(); }
+  for (int i = threadIdx.x; i < 256; i += LN_NT) {
+    vecs[i] = p.bias ? p.bias[i] : 0.f;
+    vecs[256 + i] = p.ln_gamma[i];
+    vecs[512 + i] = p.ln_beta[i];
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 1;
+      for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x) {
+        const int m0 = mt * BM;
+        for (int kb = 0; kb < total_kb; ++kb) {
+          mbar_wait(&empty_bar[s], ph);
+          uint8_t* sa = smem + s * STAGE_BYTES;
+          mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+          tma_load_2d(sa, &tmA, &full_bar[s], kb * BK, m0);
+          tma_load_2d(sa + A_BYTES, &tmB, &full_bar[s], kb * BK, 0);
+          if (++s == NSTAGE) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, false, false);
+      uint32_t ut = 0, ph = 0;
+      int s = 0;
+      for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x, ++ut) {
+        const uint32_t acc = ut & 1;
+        mbar_wait(&tempty_bar[acc], ((ut >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < total_kb; ++kb) {
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + s * STAGE_BYTES), sb = sa + A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            umma_bf16(d_tmem, make_smem_desc(sa + k * 32, 0, 1024), make_smem_desc(sb + k * 32, 0, 1024), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          umma_commit(&empty_bar[s]);
+          if (++s == NSTAGE) { s = 0; ph ^= 1; }
+        }
+        umma_commit(&tfull_bar[acc]);
+      }
+    }
+  } else {
+    // ================================================================== epilogue warps
+    const int e = warp - 2;
+    const int q = warp & 3;
+    const int half = e >> 2;
+    const int r = q * 32 + lane;
+    const int cb = half * 128;
+    uint8_t* buf[2] = {smem + LN_OFF_STG + e * LN_WBUF, smem + LN_OFF_STG + e * LN_WBUF + 4096};
+    uint64_t* rbar = res_bar + 2 * e;
+    const int sw = lane & 7;
+    float x[128];   // this thread's 128 x-values (its row, its column half): TMEM is read once, the values never leave registers
+    uint32_t ut = 0;
+    for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x, ++ut) {
+      const int m0 = mt * BM;
+      const int row0 = m0 + q * 32;
+      const int m = m0 + r;
+      const bool valid = m < p.M;
+      const uint32_t acc = ut & 1;
+      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + cb;
+      if (p.has_res && lane == 0) {
+        bulk_wait_read<0>();   // the previous tile's stores have finished reading both staging buffers
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          mbar_expect_tx(&rbar[s], 4096);
+          tma_load_2d(buf[s], &tmR, &rbar[s], cb + s * 32, row0);
+        }
+      }
+      __syncwarp();
+      mbar_wait(&tfull_bar[acc], (ut >> 1) & 1);
+      tc_fence_after();
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int s = 0; s < 4; ++s) {
+        float(&v)[32] = *reinterpret_cast<float(*)[32]>(&x[s * 32]);
+        tmem_ld32(trow + s * 32, v);
+        if (s == 3) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty_bar[acc]);   // the whole accumulator slice is in registers
+        }
+        const float4* bp = reinterpret_cast<const float4*>(vecs + cb + s * 32);
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          const float4 f = bp[g];
+          v[g * 4] = (v[g * 4] + f.x) * p.alpha; v[g * 4 + 1] = (v[g * 4 + 1] + f.y) * p.alpha;
+          v[g * 4 + 2] = (v[g * 4 + 2] + f.z) * p.alpha; v[g * 4 + 3] = (v[g * 4 + 3] + f.w) * p.alpha;
+        }
+        uint8_t* b = buf[s & 1];
+        uint8_t* row = b + lane * 128;
+        if (p.has_res) {
+          mbar_wait(&rbar[s & 1], (s >> 1) & 1);   // each buffer's barrier completes twice per tile
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const float4 f = *reinterpret_cast<const float4*>(row + ((g ^ sw) << 4));
+            v[g * 4] += f.x; v[g * 4 + 1] += f.y; v[g * 4 + 2] += f.z; v[g * 4 + 3] += f.w;
+          }
+        } else {
+          if (lane == 0) bulk_wait_read<1>();
+          __syncwarp();
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          s1 += v[j];
+          s2 = fmaf(v[j], v[j], s2);
+        }
+        // x slab -> same staging buffer (every lane rewrites the row it has just consumed) -> fp32 store
+#pragma unroll
+        for (int g = 0; g < 8; ++g)
+          *reinterpret_cast<float4*>(row + ((g ^ sw) << 4)) = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&tmC, b, cb + s * 32, row0);
+          bulk_commit();
+          if (p.has_res && s < 2) {   // refill this buffer with the residual of slab s + 2 once the store has read it
+            bulk_wait_read<0>();
+            mbar_expect_tx(&rbar[s & 1], 4096);
+            tma_load_2d(b, &tmR, &rbar[s & 1], cb + (s + 2) * 32, row0);
+          }
+        }
+        __syncwarp();
+      }
+      // row statistics: combine with the warp that owns the other 128 columns of the same rows
+      xch[half * 256 + r * 2] = s1;
+      xch[half * 256 + r * 2 + 1] = s2;
+      bar_sync(1 + q, 64);
+      s1 += xch[(half ^ 1) * 256 + r * 2];
+      s2 += xch[(half ^ 1) * 256 + r * 2 + 1];
+      const float mu = s1 * (1.f / 256.f);
+      const float rs = rsqrtf(fmaxf(s2 * (1.f / 256.f) - mu * mu, 0.f) + 1e-5f);
+      if (half == 0 && valid && p.ln_mean) { p.ln_mean[m] = mu; p.ln_rstd[m] = rs; }
+      bar_sync(1 + q, 64);   // both warps have read the exchange slots: the next tile may overwrite them
+#pragma unroll
+      for (int s = 0; s < 4; ++s) {
+        float(&v)[32] = *reinterpret_cast<float(*)[32]>(&x[s * 32]);
+        const float4* gp = reinterpret_cast<const float4*>(vecs + 256 + cb + s * 32);
+        const float4* bp2 = reinterpret_cast<const float4*>(vecs + 512 + cb + s * 32);
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          const float4 gg = gp[g], bb = bp2[g];
+          v[g * 4] = (v[g * 4] - mu) * rs * gg.x + bb.x;
+          v[g * 4 + 1] = (v[g * 4 + 1] - mu) * rs * gg.y + bb.y;
+          v[g * 4 + 2] = (v[g * 4 + 2] - mu) * rs * gg.z + bb.z;
+          v[g * 4 + 3] = (v[g * 4 + 3] - mu) * rs * gg.w + bb.w;
+        }
+        uint8_t* b = buf[s & 1];
+        if (lane == 0) bulk_wait_read<1>();   // the store before the newest one used this buffer
+        __syncwarp();
+        if (p.ln_bf16) {
+          uint8_t* row = b + lane * 64;
+          const int sw64 = (lane >> 1) & 3;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint4 u;
+            __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) h[k] = __floats2bfloat162_rn(v[g * 8 + 2 * k], v[g * 8 + 2 * k + 1]);
+            *reinterpret_cast<uint4*>(row + ((g ^ sw64) << 4)) = u;
+          }
+        } else {
+          uint8_t* row = b + lane * 128;
+#pragma unroll
+          for (int g = 0; g < 8; ++g)
+            *reinterpret_cast<float4*>(row + ((g ^ sw) << 4)) = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&tmL, b, cb + s * 32, row0);
+          bulk_commit();
+        }
+      }
+    }
+    if (lane == 0) bulk_wait_all();
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 template <bool AK, bool BK_, int EPI>
 int launch3(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc_, const CUtensorMap& tp, const P3& p, int grid,
             cudaStream_t st) {
@@ -590,6 +837,37 @@ int gemm_tc3(const eec_gemm_desc* d, cudaStream_t st) {
   if (d->a_kmajor && !d->b_kmajor) return launch3<true, false, EPI_GENERIC>(ta, tb, tcm, tpm, p, grid, st);
   if (!d->a_kmajor && !d->b_kmajor) return launch3<false, false, EPI_GENERIC>(ta, tb, tcm, tpm, p, grid, st);
   return launch3<false, true, EPI_GENERIC>(ta, tb, tcm, tpm, p, grid, st);
+}
+
+// LayerNorm-tail epilogue of eec_gemm (N == 256, K-major bf16 operands, fp32 C with ldc 256); validated by gemm_tc2
+int gemm_ln3(const eec_gemm_desc* d, cudaStream_t st) {
+  EEC_CHECK_ARG(d->res_row_mod == 0, "gemm_ln3: row-periodic residual unsupported");
+  EEC_CHECK_ARG(!d->residual || d->ldr == 256, "gemm_ln3: residual must have ld 256");
+  if (!g_sms3) {
+    int dev = 0;
+    EEC_CUDA(cudaGetDevice(&dev));
+    EEC_CUDA(cudaDeviceGetAttribute(&g_sms3, cudaDevAttrMultiProcessorCount, dev));
+  }
+  CUtensorMap ta, tb, tcm, trm, tlm;
+  if (int r = get_tmap_2d(&ta, d->A, d->K, d->M, (uint64_t)d->lda * 2, 64, 128)) return r;
+  if (int r = get_tmap_2d(&tb, d->B, d->K, d->N, (uint64_t)d->ldb * 2, 64, 256)) return r;
+  if (int r = get_tmap_box32(&tcm, d->C, false, 256, (uint64_t)d->M, (uint64_t)d->ldc)) return r;
+  trm = tcm;
+  if (d->residual) { if (int r = get_tmap_box32(&trm, d->residual, false, 256, (uint64_t)d->M, 256)) return r; }
+  if (int r = get_tmap_box32(&tlm, d->ln_out, d->ln_dtype == EEC_BF16, 256, (uint64_t)d->M, (uint64_t)d->ld_ln)) return r;
+  PLN p{};
+  p.M = d->M; p.K = d->K; p.m_tiles = cdiv(d->M, BM);
+  p.bias = d->bias; p.alpha = d->alpha; p.has_res = d->residual != nullptr; p.ln_bf16 = d->ln_dtype == EEC_BF16;
+  p.ln_gamma = d->ln_gamma; p.ln_beta = d->ln_beta; p.ln_mean = d->ln_mean; p.ln_rstd = d->ln_rstd;
+  static bool attr_set = false;
+  if (!attr_set) {
+    EEC_CUDA(cudaFuncSetAttribute(gemm_ln3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LN_SMEM_BYTES));
+    attr_set = true;
+  }
+  const int grid = min(p.m_tiles, g_sms3);
+  gemm_ln3_kernel<<<grid, LN_NT, LN_SMEM_BYTES, st>>>(ta, tb, tcm, trm, tlm, p);
+  EEC_LAUNCH_CHECK();
+  return 0;
 }
 
 }  // namespace eec
