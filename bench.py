@@ -215,7 +215,7 @@ def run_ours(args):
     rtfx = None
     if rank == 0 and not args.skip_rtfx and not args.profile:
         audio_s = float(lengths.sum()) * FRAME_S
-        rtfx = rtfx_per_exit(model, src_dev, lengths, audio_s)
+        rtfx = rtfx_per_exit(model, src_dev, lengths, audio_s, use_graph=not args.no_graph)
         model.train()
 
     roof = cpu = None
@@ -253,8 +253,10 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def rtfx_per_exit(model, src_dev, lengths, audio_s):
-    """Inference RTFx for a forward truncated after exit e (e = 1..6): time the full forward's prefix."""
+def rtfx_per_exit(model, src_dev, lengths, audio_s, use_graph=True):
+    """Inference RTFx for a forward truncated after exit e (e = 1..6): front end + e exit groups + heads 1..e, bf16, eval;
+    each truncated forward is one CUDA graph replay (eager launches with --no-graph)."""
+    import eec
     from eec import engine
     model.eval()
     res = []
@@ -262,14 +264,20 @@ def rtfx_per_exit(model, src_dev, lengths, audio_s):
     full = model._cfg()
     with torch.no_grad():
         for e in range(1, N_EXITS + 1):
-            cfg = engine.Config(n_exits=e, n_layers=full.n_layers, n_mels=full.n_mels, precision=full.precision)
+            if use_graph:
+                fwd = eec.GraphedForward(model, src_dev.shape[0], src_dev.shape[2], n_exits=e)
+                fwd(src_dev, lengths)
+                run = fwd.replay
+            else:
+                cfg = engine.Config(n_exits=e, n_layers=full.n_layers, n_mels=full.n_mels, precision=full.precision)
+                run = lambda: engine.model_forward(P, W, cfg, src_dev, lengths, False, False)   # noqa: E731
             for _ in range(2):
-                engine.model_forward(P, W, cfg, src_dev, lengths, False, False)
+                run()
             torch.cuda.synchronize()
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             ev0.record()
             for _ in range(5):
-                engine.model_forward(P, W, cfg, src_dev, lengths, False, False)
+                run()
             ev1.record()
             torch.cuda.synchronize()
             ms = ev0.elapsed_time(ev1) / 5

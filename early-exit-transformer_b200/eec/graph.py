@@ -121,3 +121,64 @@ class GraphedTrainStep:
     def __call__(self, src, lengths, targets, target_lengths) -> torch.Tensor:
         self.load_inputs(src, lengths, targets, target_lengths)
         return self.replay()
+
+
+class GraphedForward:
+    """Inference forward (eval mode, no grad) of the first ``n_exits`` exit groups as ONE CUDA graph: the ~35 launches per
+    exit group cost more on the host than on the GPU at batch 64, so RTFx is launch-bound when issued eagerly.
+
+        fwd = eec.GraphedForward(model, batch_size=64, t_in=1501)            # all exits
+        log_probs = fwd(src, lengths)                                        # (E, B, T', V) fp32, a static buffer
+
+    ``n_exits=e`` captures the truncated encoder (front end + e groups + heads 1..e) that BASELINE's "RTFx per exit" times."""
+
+    def __init__(self, model, batch_size: int, t_in: int, n_exits: Optional[int] = None, n_mels: Optional[int] = None, warmup: int = 2):
+        params = list(model.parameters())
+        if not params or not params[0].is_cuda:
+            raise EecError("GraphedForward: move the model to a CUDA device first (no CPU path)")
+        if model.training:
+            raise EecError("GraphedForward captures an inference forward: call model.eval() first")
+        model._check_supported()
+        dev = params[0].device
+        self.model = model
+        full = model._cfg()
+        self.cfg = engine.Config(n_exits=n_exits or full.n_exits, n_layers=full.n_layers, n_mels=full.n_mels,
+                                 splitformer=full.splitformer and (n_exits in (None, full.n_exits)), precision=full.precision)
+        n_mels = n_mels if n_mels is not None else model._features_length
+        self.src = torch.zeros(batch_size, n_mels, t_in, dtype=torch.float32, device=dev)
+        self.lengths = torch.full((batch_size,), t_in, dtype=torch.int64, device=dev)
+        self._pin_len = torch.empty(batch_size, dtype=torch.int64).pin_memory()
+        self.t_out = ((t_in - 3) // 2 + 1 - 3) // 2 + 1
+        lib = load()
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side), torch.no_grad():
+            for _ in range(max(warmup, 1)):
+                self._run()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        n0 = lib.eec_launch_count()
+        with torch.no_grad(), torch.cuda.graph(self.graph):
+            self.out = self._run()
+        self.launches = int(lib.eec_launch_count() - n0)
+
+    def _run(self):
+        m = self.model
+        out, _ = engine.model_forward(m._tensor_dict(), m._operands, self.cfg, self.src, self.lengths, False, False)
+        return out
+
+    def replay(self) -> torch.Tensor:
+        self.graph.replay()
+        return self.out
+
+    def __call__(self, src: torch.Tensor, lengths: torch.Tensor) -> torch.Tensor:
+        if tuple(src.shape) != tuple(self.src.shape) or lengths.numel() != self.src.shape[0]:
+            raise EecError(f"GraphedForward: input shape {tuple(src.shape)} != captured {tuple(self.src.shape)}")
+        if not lengths.is_cuda:
+            engine.check_lengths(lengths, self.t_out)
+            self._pin_len.copy_(lengths.reshape(-1))
+            lengths = self._pin_len
+        self.src.copy_(src, non_blocking=True)
+        self.lengths.copy_(lengths, non_blocking=True)
+        return self.replay()

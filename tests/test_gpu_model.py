@@ -400,3 +400,25 @@ def test_graphed_step_with_fused_optimizer_trains():
     assert losses["graph"][-1] < losses["graph"][0]
     for a, b in zip(losses["eager"], losses["graph"]):
         assert abs(a - b) < 2e-2 * abs(a), (losses["eager"], losses["graph"])
+
+
+def test_graphed_forward_matches_eager():
+    """eec.GraphedForward (inference forward as one CUDA graph, optionally truncated after exit e) == the eager forward."""
+    import eec
+    name = "ec_e3l2_b4_t331"
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    m, sd, src, lengths = build(name, g, "bf16")
+    m.eval()
+    with torch.no_grad():
+        ref = m(src.cuda(), lengths)
+    fwd = eec.GraphedForward(m, src.shape[0], src.shape[2])
+    out = fwd(src, lengths)
+    assert fwd.launches > 30 and rel(out, ref) < 1e-6
+    src2, lengths2 = O.synthetic_batch(src.shape[0], src.shape[2], seed=5)
+    with torch.no_grad():
+        ref2 = m(src2.cuda(), lengths2)
+    assert rel(fwd(src2.cuda(), lengths2), ref2) < 1e-6
+    fwd1 = eec.GraphedForward(m, src.shape[0], src.shape[2], n_exits=1)
+    assert rel(fwd1(src2, lengths2)[0], ref2[0]) < 1e-6 and fwd1.out.shape[0] == 1
+    with pytest.raises(AssertionError):
+        fwd(src2, torch.full((src.shape[0],), 100, dtype=torch.int64))
