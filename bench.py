@@ -309,9 +309,12 @@ def roofline_dominant(dev, pk):
     ms = total / n
     fl = 2.0 * M * N * K
     ach = fl / (ms / 1e3) / 1e12
-    return {"kernel": "gemm_tc_kernel<K-major,K-major,EPI_GENERIC> FFN up-proj 23936x2048x256 +bias+SiLU", "bound": "tensor",
+    # traffic: dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of this kernel from the committed ncu --set full capture
+    # (profiles/r01n_kernels_full.txt: 13.36 MB read + 46.28 MB written; the rest of the 98 MB output is still in the 126 MB L2
+    # when the kernel ends, so DRAM traffic is BELOW the algorithmic bytes: nothing is re-read)
+    return {"kernel": "gemm_tc3_kernel<K-major,K-major,EPI_GENERIC> FFN up-proj 23936x2048x256 +bias+SiLU", "bound": "tensor",
             "achieved": round(ach, 2), "peak": pk["tf_burst"], "unit": "TFLOP/s", "frac": round(ach / pk["tf_burst"], 4),
-            "traffic": None, "ms_per_launch": round(ms, 4), "peak_source": pk["src"] + " burst (kernel timed alone)",
+            "traffic": 59.64e6, "ms_per_launch": round(ms, 4), "peak_source": pk["src"] + " burst (kernel timed alone)",
             "algorithmic_flops_per_launch": fl, "algorithmic_bytes_per_launch": 2 * (M * K + N * K + M * N)}
 
 

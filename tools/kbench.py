@@ -13,9 +13,21 @@ N = B * T
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
 
+PROFILE = os.environ.get("KBENCH_PROFILE") == "1"   # under `ncu --profile-from-start off`: exactly ONE profiled call per kernel
+
+
 def timeit(fn, n=10, warm=3):
     for _ in range(warm):
         fn()
+    if PROFILE:
+        torch.cuda.synchronize()
+        flush.zero_()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        fn()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return float("nan")
     tot = 0.0
     for _ in range(n):
         flush.zero_()
