@@ -72,6 +72,8 @@ extern "C" int eec_device_ok(void) {
 extern "C" int eec_gemm(const eec_gemm_desc* d, eec_stream_t stream) {
   EEC_CHECK_ARG(d != nullptr, "gemm: NULL descriptor");
   if (d->M == 0 || d->N == 0) return 0;
+  EEC_CHECK_ARG(!d->a_colsum || (d->in_dtype == EEC_BF16 && !force_simt_gemm() && !gemm_v1()),
+                "gemm: a_colsum is implemented by the bf16 tcgen05 (v3) kernel only; use eec_colsum on the other paths");
   if (d->in_dtype == EEC_F32 || force_simt_gemm()) return simt_with_tails(d, S(stream));
   return tc_dispatch(d, S(stream), nullptr, nullptr, 0);
 }

@@ -466,6 +466,7 @@ int gemm_tc2(const eec_gemm_desc* d, cudaStream_t st, int32_t* argmax, float* en
     if (!v2_env && v3_ok && (epi == EPI_GENERIC || epi == EPI_GLU)) return gemm_tc3(d, st);
     if (!v2_env && epi == EPI_LN && d->res_row_mod == 0 && (!d->residual || d->ldr == 256)) return gemm_ln3(d, st);
   }
+  EEC_CHECK_ARG(!d->a_colsum, "gemm_tc2: a_colsum is implemented by the v3 kernel only (unset EEC_GEMM_V2)");
   if (!g_num_sms) {
     int dev = 0;
     EEC_CUDA(cudaGetDevice(&dev));

@@ -53,6 +53,7 @@ struct P3 {
   float alpha;
   const float* residual; int ldr; int res_row_mod;
   int out_bf16, has_pre, accumulate;
+  float* a_colsum; float a_colsum_scale;   // MN-major A only: a_colsum[m] += scale * sum_k A(m,k) from the smem A tiles
   int debug;       // EEC_GEMM_DEBUG bitmask (perf triage only): 1 = no bulk store issue, 2 = no staging, 4 = no activation math
   long long* tl;   // EEC_GEMM_TL=1 (perf triage only): clock64 accumulators of CTA 0, see gemm_tc3()
 };
@@ -210,7 +211,8 @@ __global__ void __launch_bounds__(NT3, 1) gemm_tc3_kernel(const __grid_constant_
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmC);
-    for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    // with a_colsum the 16 epilogue warps also read every A stage: the slot is free after the MMAs AND those readers
+    for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], (!A_KMAJ && p.a_colsum) ? 1 + NEW : 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], NEW); }
     for (int w = 0; w < NEW; ++w) mbar_init(&load_bar[w], 1);
     fence_barrier_init();
@@ -330,11 +332,44 @@ __global__ void __launch_bounds__(NT3, 1) gemm_tc3_kernel(const __grid_constant_
 #define TL_STAMP(t) do { } while (0)
 #define TL_ACC(a, d) do { } while (0)
 #endif
+    int cs = 0;             // a_colsum: this warp's position in the operand ring (walks every k-block of every unit)
+    uint32_t cph = 0;
     for (UnitIter ui(p); ui.u < n_units; ui.next(p), ++ut) {
       TL_STAMP(t0_); TL_ACC(e_rest, ut ? t0_ - t2_ : 0);
       const int split = ui.split;
       const int m0 = ui.mt * BM;
       const int nt = ui.nt;
+      if (!A_KMAJ && p.a_colsum) {
+        // bias gradient of the layer whose weight gradient this GEMM computes: column sums of the MN-major A operand
+        // ([64 k][128 m] bf16 per stage, 128B-swizzled) taken while the tile sits in shared memory.  Thread (cm, kq) adds
+        // 16 k-rows of column cm per k-block; units with n-tile 0 publish (one atomic per column per unit).
+        const int tid_e = threadIdx.x - 64, cm = tid_e & 127, kq = tid_e >> 7;
+        const int kb0 = split * p.kb_per_split, kb1 = min(total_kb, kb0 + p.kb_per_split);
+        const uint32_t coff = (uint32_t)((cm >> 6) * 8192 + (((cm & 63) & 7) * 2));
+        const int cchunk = (cm & 63) >> 3;
+        float csum = 0.f;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[cs], cph);
+          if (nt == 0) {
+            const uint8_t* a = smem + cs * STAGE_BYTES + coff;
+#pragma unroll
+            for (int kk = 0; kk < 16; ++kk) {
+              const int k = kq * 16 + kk;
+              csum += __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(a + k * 128 + ((cchunk ^ (k & 7)) << 4)));
+            }
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&empty_bar[cs]);
+          if (++cs == NSTAGE) { cs = 0; cph ^= 1; }
+        }
+        if (nt == 0) {
+          bias_s[kq * 128 + cm] = csum;     // (a weight-gradient GEMM has no bias vector: the area is free)
+          bar_sync(1, NEW * 32);
+          if (kq == 0 && m0 + cm < p.M)
+            atomicAdd(p.a_colsum + m0 + cm, p.a_colsum_scale * (bias_s[cm] + bias_s[128 + cm] + bias_s[256 + cm] + bias_s[384 + cm]));
+          bar_sync(1, NEW * 32);
+        }
+      }
       const int n0 = (EPI == EPI_GLU) ? nt * 128 : nt * BN;
       const uint32_t acc = ut & 1;
       const int row0 = m0 + q * 32;
@@ -797,6 +832,9 @@ int gemm_tc3(const eec_gemm_desc* d, cudaStream_t st) {
   p.bias = d->bias; p.act = d->act; p.alpha = d->alpha;
   p.residual = d->residual; p.ldr = d->ldr; p.res_row_mod = d->res_row_mod;
   p.out_bf16 = out_bf16; p.has_pre = store_pre; p.accumulate = d->accumulate;
+  EEC_CHECK_ARG(!d->a_colsum || (!d->a_kmajor && !d->b_kmajor && !d->bias && epi == EPI_GENERIC),
+                "gemm_tc3: a_colsum needs the weight-gradient form (MN-major A and B, no bias)");
+  p.a_colsum = d->a_colsum; p.a_colsum_scale = d->a_colsum_scale;
   const int n_units = p.m_tiles * p.n_tiles * p.splits;
   const int grid = min(n_units, g_sms3);
   {

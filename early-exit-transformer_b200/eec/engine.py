@@ -10,6 +10,7 @@ and :299-364 (Splitformer).
 from __future__ import annotations
 
 from dataclasses import dataclass, field
+import os
 from typing import Dict, List, Optional
 
 import torch
@@ -109,9 +110,18 @@ def dgrad(dY, W, out, M, N_out, K_in, **kw):
     ops.gemm(dY, W, out, M, K_in, N_out, a_kmajor=True, b_kmajor=False, lda=N_out, ldb=K_in, **kw)
 
 
-def wgrad(dY, X, dW, M, N_out, K_in, alpha=1.0):
-    """dW[N_out,K_in] += alpha * dY[M,N_out]^T @ X[M,K_in]"""
-    ops.gemm(dY, X, dW, N_out, K_in, M, a_kmajor=False, b_kmajor=False, lda=N_out, ldb=K_in, alpha=alpha, accumulate=True)
+_FUSE_COLSUM = not (os.environ.get("EEC_GEMM_V1") == "1" or os.environ.get("EEC_GEMM_V2") == "1" or os.environ.get("EEC_FORCE_SIMT") == "1")
+
+
+def wgrad(dY, X, dW, M, N_out, K_in, alpha=1.0, dbias=None):
+    """dW[N_out,K_in] += alpha * dY[M,N_out]^T @ X[M,K_in];  dbias[N_out] += column sums of dY (optional).
+    On the tcgen05 path the bias gradient is summed from the dY tiles while they sit in shared memory as the GEMM's
+    A operand (eec_gemm_desc.a_colsum): the [M, N_out] tensor is not read a second time."""
+    fuse = dbias is not None and _FUSE_COLSUM and dY.dtype == torch.bfloat16
+    ops.gemm(dY, X, dW, N_out, K_in, M, a_kmajor=False, b_kmajor=False, lda=N_out, ldb=K_in, alpha=alpha, accumulate=True,
+             a_colsum=dbias if fuse else None)
+    if dbias is not None and not fuse:
+        ops.colsum(dY, dbias, M, N_out)
 
 
 def to_act(x32: Tensor, cfg: Config) -> Tensor:
@@ -240,8 +250,7 @@ def layer_backward(P, W: Operands, G: Dict[str, Tensor], pre: str, t: dict, dY: 
         wgrad(dXh, a, G[q + "4.weight"], N, D, F, alpha=0.5)     # (this FFN's output-bias grad came fused from ln_bwd)
         dh = _empty((N, F), TD, dev)
         dgrad(dXh, W2, dh, N, D, F, act=ACT_DSILU, preact=hpre, alpha=0.5)
-        wgrad(dh, u, G[q + "1.weight"], N, F, D)
-        ops.colsum(dh, G[q + "1.bias"], N, F)
+        wgrad(dh, u, G[q + "1.weight"], N, F, D, dbias=G[q + "1.bias"])
         du = _empty((N, D), f32, dev)
         dgrad(dh, W1, du, N, F, D)
         return ln_bwd(du, x_in, m, r, q + "0.", True, want_h, next_bias)
@@ -264,8 +273,7 @@ def layer_backward(P, W: Operands, G: Dict[str, Tensor], pre: str, t: dict, dY: 
     ops.dwconv_bwd(dc, t["g"], wdw, dg, G[c + "sequential.2.weight"].view(D, KW), G[c + "sequential.2.bias"], B, T, KW)
     dz = _empty((N, 2 * D), TD, dev)
     ops.glu_bwd(t["z"], dg, dz)
-    wgrad(dz, t["u3"], G[c + "sequential.0.weight"].view(2 * D, D), N, 2 * D, D)
-    ops.colsum(dz, G[c + "sequential.0.bias"], N, 2 * D)
+    wgrad(dz, t["u3"], G[c + "sequential.0.weight"].view(2 * D, D), N, 2 * D, D, dbias=G[c + "sequential.0.bias"])
     du3 = _empty((N, D), f32, dev)
     dgrad(dz, Wp1, du3, N, 2 * D, D)
     dXh = ln_bwd(du3, t["x2"], t["m3"], t["r3"], c + "layer_norm.", True, True, pre + "self_attn.out_proj.bias")
@@ -280,8 +288,7 @@ def layer_backward(P, W: Operands, G: Dict[str, Tensor], pre: str, t: dict, dY: 
     dvec = _empty((B * H * T,), f32, dev)
     dq32 = _empty((N, D), f32, dev) if bf16 else None
     ops.attn_bwd(t["qkv"], t["ctx"], dctx, t["lse"], t["key_len"], dqkv, dvec, B, T, H, dq32)
-    wgrad(dqkv, t["u2"], G[pre + "self_attn.in_proj_weight"], N, 3 * D, D)
-    ops.colsum(dqkv, G[pre + "self_attn.in_proj_bias"], N, 3 * D)
+    wgrad(dqkv, t["u2"], G[pre + "self_attn.in_proj_weight"], N, 3 * D, D, dbias=G[pre + "self_attn.in_proj_bias"])
     du2 = _empty((N, D), f32, dev)
     dgrad(dqkv, Wqkv, du2, N, 3 * D, D)
     dXh = ln_bwd(du2, t["x1"], t["m2"], t["r2"], pre + "self_attn_layer_norm.", True, True, pre + "ffn1.sequential.4.bias", 0.5)

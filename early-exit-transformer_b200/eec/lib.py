@@ -36,6 +36,8 @@ class GemmDesc(C.Structure):
         ("ln_mean", vp), ("ln_rstd", vp),
         ("ln2_gamma", vp), ("ln2_beta", vp), ("ln2_mean", vp), ("ln2_rstd", vp),
         ("x_pre", vp),
+        ("a_colsum", vp),
+        ("a_colsum_scale", f32),
     ]
 
 

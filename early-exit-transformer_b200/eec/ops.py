@@ -28,6 +28,7 @@ def gemm(
     residual: Optional[Tensor] = None, res_row_mod: int = 0, accumulate: bool = False,
     ln_gamma: Optional[Tensor] = None, ln_beta: Optional[Tensor] = None, ln_out: Optional[Tensor] = None,
     ln_mean: Optional[Tensor] = None, ln_rstd: Optional[Tensor] = None, ldc: Optional[int] = None,
+    a_colsum: Optional[Tensor] = None, a_colsum_scale: float = 1.0,
 ):
     """C[M,N] = epi(A(m,k) B(n,k)).  See include/eec.h::eec_gemm_desc."""
     for t, n in ((A, "A"), (B, "B"), (C_out, "C")):
@@ -57,6 +58,7 @@ def gemm(
     d.ln_dtype = dt(ln_out) if ln_out is not None else F32
     d.ld_ln = N
     d.ln_mean, d.ln_rstd = ptr(ln_mean), ptr(ln_rstd)
+    d.a_colsum, d.a_colsum_scale = ptr(a_colsum), a_colsum_scale
     call("eec_gemm", C.byref(d), stream())
 
 

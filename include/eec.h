@@ -77,6 +77,9 @@ typedef struct {
   float* ln_mean; float* ln_rstd;
   const float* ln2_gamma; const float* ln2_beta; float* ln2_mean; float* ln2_rstd;
   float* x_pre;             /* with ln2: optional fp32 store of the pre-LN1 value (needed for bwd) */
+  float* a_colsum;          /* weight-gradient form only (a_kmajor = 0, b_kmajor = 0, accumulate, no bias, bf16):          */
+  float a_colsum_scale;     /*   a_colsum[m] += a_colsum_scale * sum_k A(m,k)  -- the bias gradient of the same layer, summed */
+                            /*   from the A tiles while they sit in shared memory (no second pass over the [rows, M] tensor) */
 } eec_gemm_desc;
 int eec_gemm(const eec_gemm_desc* d, eec_stream_t stream);
 

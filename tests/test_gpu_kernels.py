@@ -305,3 +305,20 @@ def test_misc(ops):
     y = a.clone()
     ops.repeat2_add(half, y, B, T)
     assert torch.allclose(y.view(B, T, 256), a.view(B, T, 256) + torch.repeat_interleave(ref, 2, 1)[:, :T])
+
+
+def test_wgrad_fused_bias_colsum():
+    """eec_gemm_desc.a_colsum: the weight-gradient GEMM (MN-major A and B, split-K, reduce-add) also accumulates the column
+    sums of its A operand (= the bias gradient) from the shared-memory tiles; compared with fp64 sums of the bf16 inputs."""
+    from eec import ops
+    torch.manual_seed(3)
+    for rows, m, n in ((23936, 2048, 256), (1000, 768, 256), (333, 512, 256)):
+        dy = (torch.randn(rows, m, device="cuda") * 0.5).to(torch.bfloat16)
+        x = torch.randn(rows, n, device="cuda").to(torch.bfloat16)
+        dw = torch.full((m, n), 0.25, device="cuda")          # accumulate semantics: += on top of what is there
+        db = torch.full((m,), -1.0, device="cuda")
+        ops.gemm(dy, x, dw, m, n, rows, a_kmajor=False, b_kmajor=False, lda=m, ldb=n, accumulate=True, a_colsum=db, a_colsum_scale=0.5)
+        ref_w = 0.25 + dy.double().t() @ x.double()
+        ref_b = -1.0 + 0.5 * dy.double().sum(0)
+        assert float((dw.double() - ref_w).abs().max() / ref_w.abs().max()) < 2e-5
+        assert float((db.double() - ref_b).abs().max() / ref_b.abs().max()) < 2e-5
