@@ -392,6 +392,15 @@ __global__ void __launch_bounds__(NT3, 1) gemm_tc3_kernel(const __grid_constant_
             mbar_expect_tx(lbar, nslab * 2048);
             tma_load_2d(st.buf, &tmP, lbar, nb, row0);
             if (nslab == 2) tma_load_2d(st.buf + 2048, &tmP, lbar, nb + 32, row0);
+            // the staging buffer is busy until this tile's stores have been read, so the NEXT tile's boxes cannot be loaded yet:
+            // pull them into L2 now, so that the load issued at the next tile start is an L2 hit instead of an HBM round trip
+            UnitIter nx = ui;
+            nx.next(p);
+            if (nx.u < n_units) {
+              const int nrow = nx.mt * BM + q * 32, nn = nx.nt * BN + cb;
+              if (nn < p.N) tma_prefetch_l2_2d(&tmP, nn, nrow);
+              if (nn + 32 < p.N) tma_prefetch_l2_2d(&tmP, nn + 32, nrow);
+            }
           }
           __syncwarp();
         }
