@@ -143,20 +143,26 @@ __device__ __forceinline__ void put16_f32(uint8_t* box, int half, int lane, cons
   for (int c = 0; c < 4; ++c)
     *reinterpret_cast<float4*>(row + (((half * 4 + c) ^ sw) << 4)) = make_float4(x[c * 4], x[c * 4 + 1], x[c * 4 + 2], x[c * 4 + 3]);
 }
-// x[j] *= dSiLU(h[j]) with h = 16 bf16 of this lane's row (column half `half`) of a 64B-swizzled [32 x 32] bf16 box
-__device__ __forceinline__ void mul_dsilu16(float (&x)[16], const uint8_t* box, int half, int lane) {
+// x[j] *= alpha * dSiLU(h[j]) with h = 16 bf16 of this lane's row (column half `half`) of a 64B-swizzled [32 x 32] bf16 box.
+// With t = tanh(h/2):  alpha * dSiLU(h) = c (1 + t) + (h/2) c (1 - t^2),  c = alpha / 2: one MUFU + six packed fp32x2 ops per pair
+__device__ __forceinline__ void mul_dsilu16(float (&x)[16], const uint8_t* box, int half, int lane, float alpha) {
   const uint8_t* row = box + lane * 64;
   const int sw = (lane >> 1) & 3;
+  const float c = 0.5f * alpha;
+  const float2 c2 = make_float2(c, c), nc2 = make_float2(-c, -c), half2 = make_float2(0.5f, 0.5f);
 #pragma unroll
-  for (int c = 0; c < 2; ++c) {
-    const uint4 u = *reinterpret_cast<const uint4*>(row + (((half * 2 + c) ^ sw) << 4));
+  for (int cc = 0; cc < 2; ++cc) {
+    const uint4 u = *reinterpret_cast<const uint4*>(row + (((half * 2 + cc) ^ sw) << 4));
     const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      const float2 f = __bfloat1622float2(h[e]);
-      const float s0 = sigmoid_fast(f.x), s1 = sigmoid_fast(f.y);
-      x[c * 8 + 2 * e] *= s0 * fmaf(f.x, 1.0f - s0, 1.0f);
-      x[c * 8 + 2 * e + 1] *= s1 * fmaf(f.y, 1.0f - s1, 1.0f);
+      const float2 hh = __fmul2_rn(__bfloat1622float2(h[e]), half2);
+      const float2 t = make_float2(tanh_fast(hh.x), tanh_fast(hh.y));
+      const float2 r = __ffma2_rn(t, c2, c2);                       // c (1 + t)
+      const float2 q = __ffma2_rn(__fmul2_rn(t, nc2), t, c2);       // c (1 - t^2)
+      const float2 d = __ffma2_rn(hh, q, r);
+      const float2 o = __fmul2_rn(make_float2(x[cc * 8 + 2 * e], x[cc * 8 + 2 * e + 1]), d);
+      x[cc * 8 + 2 * e] = o.x; x[cc * 8 + 2 * e + 1] = o.y;
     }
   }
 }
@@ -440,7 +446,9 @@ __global__ void __launch_bounds__(NT3, 1) gemm_tc3_kernel(const __grid_constant_
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
               const float4 f = bp[g];
-              x[g * 4] += f.x; x[g * 4 + 1] += f.y; x[g * 4 + 2] += f.z; x[g * 4 + 3] += f.w;
+              const float2 lo = __fadd2_rn(make_float2(x[g * 4], x[g * 4 + 1]), make_float2(f.x, f.y));
+              const float2 hi = __fadd2_rn(make_float2(x[g * 4 + 2], x[g * 4 + 3]), make_float2(f.z, f.w));
+              x[g * 4] = lo.x; x[g * 4 + 1] = lo.y; x[g * 4 + 2] = hi.x; x[g * 4 + 3] = hi.y;
             }
           }
           // staging sub-buffers (2 KB bf16 boxes): SiLU+pre-activation store: pre -> 0, out -> 1; dSiLU: slab sl reuses the
@@ -457,9 +465,10 @@ __global__ void __launch_bounds__(NT3, 1) gemm_tc3_kernel(const __grid_constant_
             if (p.has_pre) put16_bf16(st.buf, half, lane, x);
             if (!(p.debug & 4)) {
 #pragma unroll
-              for (int j = 0; j < 16; ++j) {   // x * sigmoid(x) = h + h * tanh(h), h = x / 2
-                const float h = 0.5f * x[j];
-                x[j] = fmaf(h, tanh_fast(h), h);
+              for (int j = 0; j < 16; j += 2) {   // x * sigmoid(x) = h + h * tanh(h), h = x / 2; packed fp32x2 FMUL2 / FFMA2 (sm_100)
+                const float2 h = __fmul2_rn(make_float2(x[j], x[j + 1]), make_float2(0.5f, 0.5f));
+                const float2 r = __ffma2_rn(h, make_float2(tanh_fast(h.x), tanh_fast(h.y)), h);
+                x[j] = r.x; x[j + 1] = r.y;
               }
             }
           } else if (dsilu) {
@@ -467,11 +476,15 @@ __global__ void __launch_bounds__(NT3, 1) gemm_tc3_kernel(const __grid_constant_
               mbar_wait(lbar, lphase);
               lphase ^= 1;
             }
-            mul_dsilu16(x, st.buf + sl * 2048, half, lane);
+            mul_dsilu16(x, st.buf + sl * 2048, half, lane, p.alpha);   // (alpha folded in)
           }
-          if (p.alpha != 1.0f) {
+          if (p.alpha != 1.0f && !dsilu) {
+            const float2 al = make_float2(p.alpha, p.alpha);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) x[j] *= p.alpha;
+            for (int j = 0; j < 16; j += 2) {
+              const float2 r = __fmul2_rn(make_float2(x[j], x[j + 1]), al);
+              x[j] = r.x; x[j + 1] = r.y;
+            }
           }
           if (p.residual && first_split && valid) {
             const long rr = p.res_row_mod ? (m % p.res_row_mod) : m;
