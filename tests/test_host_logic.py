@@ -156,3 +156,26 @@ def test_full_conformer_mirror_layout_and_init():
         eec.full_conformer(**{**kw, "n_head": 6})
     with pytest.raises(Exception):   # no CPU path: the encoder half refuses CPU tensors
         a(torch.zeros(1, 80, 163), torch.tensor([163]), torch.zeros(1, 4, dtype=torch.long))
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/models"), reason="the reference tree exists in the authoring container only")
+def test_dropin_rebinds_reference_classes():
+    """eec.dropin.install(): the unmodified reference package resolves Early_conformer / Splitformer /
+    full_conformer to the eec classes, which accept the reference's keyword call (train.py:166-178) and keep its layout."""
+    import importlib
+    import sys
+    import eec
+    import eec.dropin
+    sys.path.insert(0, "/root/reference")
+    try:
+        ref = eec.dropin.install()
+        assert ref.Early_conformer is eec.Early_conformer and ref.Splitformer is eec.Splitformer and ref.full_conformer is eec.full_conformer
+        m = ref.Early_conformer(src_pad_idx=0, n_enc_exits=2, enc_voc_size=256, dec_voc_size=256, d_model=256, n_head=8, max_len=2000,
+                                d_feed_forward=2048, n_enc_layers=1, features_length=80, drop_prob=0.1, depthwise_kernel_size=31,
+                                device=torch.device("cpu"))
+        assert len(m.state_dict()) == 1 + 4 + 2 * 2 + 2 * 33   # pe + front end + heads + 2 layers x 33 entries (413 at 12L/6E)
+    finally:
+        sys.path.remove("/root/reference")
+        for k in [k for k in sys.modules if k == "models" or k.startswith("models.")]:
+            del sys.modules[k]
+        importlib.invalidate_caches()
