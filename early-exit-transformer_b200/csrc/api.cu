@@ -25,6 +25,12 @@ static bool force_simt_gemm() {
   return v == 1;
 }
 
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("EEC_PDL"); v = (e && e[0] == '1') ? 1 : 0; }   // measured: see common.cuh
+  return v == 1;
+}
+
 static bool gemm_v1() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("EEC_GEMM_V1"); v = (e && e[0] == '1') ? 1 : 0; }

@@ -38,6 +38,8 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
 // D[b,h,t] = sum_d dO[b,t,h,d] * O[b,t,h,d]      (one warp per frame row: lane owns 8 channels = 1/4 head)
 __global__ void __launch_bounds__(256) attn_dvec_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ d_o,
                                                         float* __restrict__ dvec, int B, int T, int H) {
+  pdl_trigger();
+  pdl_wait();
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (row >= B * T) return;
   float a[8], g[8];
@@ -56,6 +58,8 @@ __global__ void __launch_bounds__(256) attn_dvec_kernel(const __nv_bfloat16* __r
 
 // dqkv[:, 0:256] = bf16(scale * dq32)
 __global__ void dq_convert_kernel(const float* __restrict__ dq32, __nv_bfloat16* __restrict__ dqkv, long rows, float scale) {
+  pdl_trigger();
+  pdl_wait();
   long i = ((long)blockIdx.x * blockDim.x + threadIdx.x) * 8;
   if (i >= rows * 256) return;
   long r = i / 256;
@@ -72,6 +76,8 @@ __global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_tc_kernel(const __grid
                                                                  const int32_t* __restrict__ key_len, const float* __restrict__ lse,
                                                                  const float* __restrict__ dvec, float* __restrict__ dq32,
                                                                  __nv_bfloat16* __restrict__ dqkv, int T, int H) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ __align__(1024) uint8_t smem[];
   if (threadIdx.x == 0 && (smem_u32(smem) & 1023u)) { printf("eec: attn_bwd smem base not 1024-aligned\n"); __trap(); }
   uint8_t* sK = smem;
@@ -289,7 +295,7 @@ int attn_bwd_tc(const void* qkv, const void* ctx, const void* dctx, const float*
   EEC_CHECK_ARG(dh == DHD && H * dh == 256, "attn_bwd_tc: needs 8 heads of 32");
   EEC_CHECK_ARG(dq32 != nullptr, "attn_bwd_tc: dq32 workspace is NULL");
   const long rows = (long)B * T;
-  attn_dvec_kernel<<<(int)cdiv64(rows * 32, 256), 256, 0, st>>>((const __nv_bfloat16*)ctx, (const __nv_bfloat16*)dctx, dvec, B, T, H);
+  launch_pdl(attn_dvec_kernel, dim3((int)cdiv64(rows * 32, 256)), dim3(256), 0, st, (const __nv_bfloat16*)ctx, (const __nv_bfloat16*)dctx, dvec, B, T, H);
   EEC_LAUNCH_CHECK();
   EEC_CUDA(cudaMemsetAsync(dq32, 0, (size_t)rows * 256 * sizeof(float), st));
   CUtensorMap tq, td;
@@ -301,9 +307,9 @@ int attn_bwd_tc(const void* qkv, const void* ctx, const void* dctx, const float*
     attr_set = true;
   }
   dim3 grid(cdiv(T, BT), H, B);
-  attn_bwd_tc_kernel<<<grid, BW_THREADS, BW_SMEM, st>>>(tq, td, key_len, lse, dvec, dq32, (__nv_bfloat16*)dqkv, T, H);
+  launch_pdl(attn_bwd_tc_kernel, dim3(grid), dim3(BW_THREADS), BW_SMEM, st, tq, td, key_len, lse, dvec, dq32, (__nv_bfloat16*)dqkv, T, H);
   EEC_LAUNCH_CHECK();
-  dq_convert_kernel<<<(int)cdiv64(rows * 32, 256), 256, 0, st>>>(dq32, (__nv_bfloat16*)dqkv, rows, rsqrtf((float)dh));
+  launch_pdl(dq_convert_kernel, dim3((int)cdiv64(rows * 32, 256)), dim3(256), 0, st, dq32, (__nv_bfloat16*)dqkv, rows, rsqrtf((float)dh));
   EEC_LAUNCH_CHECK();
   return 0;
 }

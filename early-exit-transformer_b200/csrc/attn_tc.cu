@@ -39,6 +39,8 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_fwd_tc_kernel(const __grid
                                                                  const int32_t* __restrict__ key_len,
                                                                  __nv_bfloat16* __restrict__ ctx, float* __restrict__ lse,
                                                                  int T, int H) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;
@@ -224,7 +226,7 @@ int attn_fwd_tc(const void* qkv, const int32_t* key_len, void* ctx, float* lse, 
     attr_set = true;
   }
   dim3 grid(cdiv(T, QT), H, B);
-  attn_fwd_tc_kernel<<<grid, AT_THREADS, AT_SMEM, st>>>(tm, key_len, (__nv_bfloat16*)ctx, lse, T, H);
+  launch_pdl(attn_fwd_tc_kernel, dim3(grid), dim3(AT_THREADS), AT_SMEM, st, tm, key_len, (__nv_bfloat16*)ctx, lse, T, H);
   EEC_LAUNCH_CHECK();
   return 0;
 }

@@ -38,6 +38,31 @@ void count_launch();
 
 static inline cudaStream_t S(eec_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// ---- programmatic dependent launch (PDL) -------------------------------------------------------------
+// A training step is a chain of ~600 dependent kernels, most of them 10-50 us long; launch latency, block scheduling and
+// the per-kernel prologue (barrier init, TMEM allocation, parameter staging) of kernel k+1 overlap the tail of kernel k
+// when k+1 is launched with programmatic stream serialisation and both follow this protocol:
+//   pdl_trigger()  first statement of every kernel: "my dependents may start launching" (they still WAIT below)
+//   pdl_wait()     before the first access to global memory another kernel may have written (or may still read):
+//                  returns when the preceding kernel has completed and its writes are visible
+// Every kernel launched through launch_pdl() MUST call pdl_wait(); both are no-ops under a plain launch.
+// Measured on B200 inside the CUDA graphs (bench.py, same box, 20 steps): training step 15.52 ms with vs 15.34-15.57 ms without,
+// inference forward 4.63 ms with vs 4.43 ms without -- graph replay already removes the launch gaps and the early-resident
+// blocks of kernel k+1 compete with kernel k's tail.  So the attribute is OFF by default; EEC_PDL=1 turns it on.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ---- device helpers ---------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -45,6 +45,8 @@ __global__ void __launch_bounds__(256, 3) dwconv_kernel(const TI* __restrict__ g
                                                      const float* __restrict__ bn_b, const float* __restrict__ run_mean,
                                                      const float* __restrict__ run_var, TO* __restrict__ out,
                                                      double* __restrict__ sums, int T, int C) {
+  pdl_trigger();
+  pdl_wait();
   const int ch = blockIdx.z * 256 + threadIdx.x;
   const int b = blockIdx.y, t0 = blockIdx.x * TT;
   float wr[KW];
@@ -102,6 +104,8 @@ constexpr int WG_SPLIT = 6;
 template <typename TI>
 __global__ void __launch_bounds__(256, 3) dwconv_wgrad_kernel(const float* __restrict__ dc, const TI* __restrict__ g,
                                                            float* __restrict__ dw, float* __restrict__ dbias, int T, int C) {
+  pdl_trigger();
+  pdl_wait();
   const int ch = blockIdx.z * 256 + threadIdx.x;
   const int b = blockIdx.y;
   float acc[KW];
@@ -190,6 +194,8 @@ __global__ void __launch_bounds__(SW_WARPS * 32, 3) bn_silu_train_kernel(const f
                                                             int64_t* __restrict__ nbt, float momentum,
                                                             float* __restrict__ save_mean, float* __restrict__ save_rstd,
                                                             TO* __restrict__ out, int rows, int C) {
+  pdl_trigger();
+  pdl_wait();
   constexpr bool FAST = sizeof(TO) == 2;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ch0 = blockIdx.y * 256 + (warp & 1) * 128 + lane * CPL;
@@ -241,6 +247,8 @@ __global__ void __launch_bounds__(SW_WARPS * 32, 3) bn_silu_bwd_kernel(const TI*
                                                           const float* __restrict__ bn_w, const float* __restrict__ bn_b,
                                                           double* __restrict__ sums2, float* __restrict__ dc,
                                                           float* __restrict__ dgamma, float* __restrict__ dbeta, int rows, int C) {
+  pdl_trigger();
+  pdl_wait();
   constexpr bool FAST = sizeof(TI) == 2;
   __shared__ float red[2][SW_WARPS / 2][256];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -304,6 +312,8 @@ __global__ void __launch_bounds__(SW_WARPS * 32, 3) bn_silu_bwd_kernel(const TI*
 // z = [a | gate] (rows x 2C), dg (rows x C) -> dz = [dg * sigmoid(gate) | dg * a * sigmoid(gate) * (1 - sigmoid(gate))]
 template <typename T>
 __global__ void __launch_bounds__(SW_WARPS * 32, 3) glu_bwd_kernel(const T* __restrict__ z, const T* __restrict__ dg, T* __restrict__ dz, int rows, int C) {
+  pdl_trigger();
+  pdl_wait();
   constexpr bool FAST = sizeof(T) == 2;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ch0 = blockIdx.y * 256 + (warp & 1) * 128 + lane * CPL;
@@ -357,7 +367,7 @@ static int stream_grid(int rows) {
       EEC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dw_smem_bytes<TI>()));          \
       attr_ = true;                                                                                                      \
     }                                                                                                                    \
-    kernel<<<grid, 256, dw_smem_bytes<TI>(), S(stream)>>>(__VA_ARGS__);                                                   \
+    launch_pdl(kernel, dim3(grid), dim3(256), dw_smem_bytes<TI>(), S(stream), __VA_ARGS__);                                                   \
   } while (0)
 
 #define DW_ARGS_OK()                                                                 \
@@ -397,9 +407,9 @@ extern "C" int eec_bn_silu_train(const float* c, const double* sums, const float
   if (rows == 0) return 0;
   dim3 grid(stream_grid(rows), C / 256);
   if (dtype == EEC_F32)
-    bn_silu_train_kernel<float><<<grid, SW_WARPS * 32, 0, S(stream)>>>(c, sums, bn_w, bn_b, run_mean, run_var, num_batches_tracked, momentum, save_mean, save_rstd, (float*)out, rows, C);
+    launch_pdl(bn_silu_train_kernel<float>, dim3(grid), dim3(SW_WARPS * 32), 0, S(stream), c, sums, bn_w, bn_b, run_mean, run_var, num_batches_tracked, momentum, save_mean, save_rstd, (float*)out, rows, C);
   else
-    bn_silu_train_kernel<__nv_bfloat16><<<grid, SW_WARPS * 32, 0, S(stream)>>>(c, sums, bn_w, bn_b, run_mean, run_var, num_batches_tracked, momentum, save_mean, save_rstd, (__nv_bfloat16*)out, rows, C);
+    launch_pdl(bn_silu_train_kernel<__nv_bfloat16>, dim3(grid), dim3(SW_WARPS * 32), 0, S(stream), c, sums, bn_w, bn_b, run_mean, run_var, num_batches_tracked, momentum, save_mean, save_rstd, (__nv_bfloat16*)out, rows, C);
   EEC_LAUNCH_CHECK();
   return 0;
 }
@@ -411,9 +421,9 @@ extern "C" int eec_bn_silu_bwd_stats(const void* ds, int dtype, const float* c, 
   if (rows == 0) return 0;
   dim3 grid(stream_grid(rows), C / 256);
   if (dtype == EEC_F32)
-    bn_silu_bwd_kernel<float, false><<<grid, SW_WARPS * 32, 0, S(stream)>>>((const float*)ds, c, save_mean, save_rstd, bn_w, bn_b, sums2, nullptr, nullptr, nullptr, rows, C);
+    launch_pdl(bn_silu_bwd_kernel<float, false>, dim3(grid), dim3(SW_WARPS * 32), 0, S(stream), (const float*)ds, c, save_mean, save_rstd, bn_w, bn_b, sums2, nullptr, nullptr, nullptr, rows, C);
   else
-    bn_silu_bwd_kernel<__nv_bfloat16, false><<<grid, SW_WARPS * 32, 0, S(stream)>>>((const __nv_bfloat16*)ds, c, save_mean, save_rstd, bn_w, bn_b, sums2, nullptr, nullptr, nullptr, rows, C);
+    launch_pdl(bn_silu_bwd_kernel<__nv_bfloat16, false>, dim3(grid), dim3(SW_WARPS * 32), 0, S(stream), (const __nv_bfloat16*)ds, c, save_mean, save_rstd, bn_w, bn_b, sums2, nullptr, nullptr, nullptr, rows, C);
   EEC_LAUNCH_CHECK();
   return 0;
 }
@@ -425,9 +435,9 @@ extern "C" int eec_bn_silu_bwd_apply(const void* ds, int dtype, const float* c, 
   if (rows == 0) return 0;
   dim3 grid(stream_grid(rows), C / 256);
   if (dtype == EEC_F32)
-    bn_silu_bwd_kernel<float, true><<<grid, SW_WARPS * 32, 0, S(stream)>>>((const float*)ds, c, save_mean, save_rstd, bn_w, bn_b, const_cast<double*>(sums2), dc, dgamma, dbeta, rows, C);
+    launch_pdl(bn_silu_bwd_kernel<float, true>, dim3(grid), dim3(SW_WARPS * 32), 0, S(stream), (const float*)ds, c, save_mean, save_rstd, bn_w, bn_b, const_cast<double*>(sums2), dc, dgamma, dbeta, rows, C);
   else
-    bn_silu_bwd_kernel<__nv_bfloat16, true><<<grid, SW_WARPS * 32, 0, S(stream)>>>((const __nv_bfloat16*)ds, c, save_mean, save_rstd, bn_w, bn_b, const_cast<double*>(sums2), dc, dgamma, dbeta, rows, C);
+    launch_pdl(bn_silu_bwd_kernel<__nv_bfloat16, true>, dim3(grid), dim3(SW_WARPS * 32), 0, S(stream), (const __nv_bfloat16*)ds, c, save_mean, save_rstd, bn_w, bn_b, const_cast<double*>(sums2), dc, dgamma, dbeta, rows, C);
   EEC_LAUNCH_CHECK();
   return 0;
 }
@@ -454,8 +464,8 @@ extern "C" int eec_glu_bwd(const void* z, const void* dg, void* dz, int dtype, i
   EEC_CHECK_ARG(C % 256 == 0, "glu_bwd: C %% 256");
   if (rows == 0) return 0;
   dim3 grid(stream_grid(rows), C / 256);
-  if (dtype == EEC_F32) glu_bwd_kernel<float><<<grid, SW_WARPS * 32, 0, S(stream)>>>((const float*)z, (const float*)dg, (float*)dz, rows, C);
-  else glu_bwd_kernel<__nv_bfloat16><<<grid, SW_WARPS * 32, 0, S(stream)>>>((const __nv_bfloat16*)z, (const __nv_bfloat16*)dg, (__nv_bfloat16*)dz, rows, C);
+  if (dtype == EEC_F32) launch_pdl(glu_bwd_kernel<float>, dim3(grid), dim3(SW_WARPS * 32), 0, S(stream), (const float*)z, (const float*)dg, (float*)dz, rows, C);
+  else launch_pdl(glu_bwd_kernel<__nv_bfloat16>, dim3(grid), dim3(SW_WARPS * 32), 0, S(stream), (const __nv_bfloat16*)z, (const __nv_bfloat16*)dg, (__nv_bfloat16*)dz, rows, C);
   EEC_LAUNCH_CHECK();
   return 0;
 }

@@ -28,6 +28,8 @@ __global__ void __launch_bounds__(NT) ctc_kernel(const float* __restrict__ lp_al
                                                  int blank, float gscale, float* __restrict__ nll_all,
                                                  float* __restrict__ loss_out, float* __restrict__ grad_all,
                                                  float* __restrict__ alpha_ws, int Smax) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float sm[];
   float* buf0 = sm;              // [Smax + 2] with 2 leading -inf pads
   float* buf1 = sm + (Smax + 2);
@@ -136,6 +138,8 @@ __device__ __forceinline__ float flse3(float a, float b, float c) {
 
 __global__ void ctc_grad_init_kernel(const float4* __restrict__ lp, const int64_t* __restrict__ target_len, float4* __restrict__ grad,
                                      int B, long tv4, float gscale, long total4) {
+  pdl_trigger();
+  pdl_wait();
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long)gridDim.x * blockDim.x) {
     const int b = (int)((i / tv4) % B);
     const float sc = gscale / ((float)B * (float)max((int)target_len[b], 1));
@@ -150,6 +154,8 @@ __global__ void __launch_bounds__(128) ctc_warp_kernel(const float* __restrict__
                                                        int blank, float gscale, float* __restrict__ nll_all,
                                                        float* __restrict__ loss_out, float* __restrict__ grad_all,
                                                        float* __restrict__ alpha_ws) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int NL = SPL / 2;   // label states per lane
   constexpr int PF = 4;         // prefetch distance (time steps)
   constexpr int SW = 32 * SPL;  // workspace row width
@@ -331,6 +337,8 @@ __global__ void __launch_bounds__(128) ctc_warp_kernel(const float* __restrict__
 // greedy collapse: one warp per utterance
 __global__ void greedy_collapse_kernel(const int32_t* __restrict__ argmax, int32_t* __restrict__ tokens,
                                        int32_t* __restrict__ n_tokens, int B, int T, int blank) {
+  pdl_trigger();
+  pdl_wait();
   const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (b >= B) return;
@@ -359,6 +367,8 @@ __global__ void __launch_bounds__(1024) exit_select_kernel(const float* __restri
                                                            int32_t* __restrict__ n_tokens, int32_t* __restrict__ new_row_map,
                                                            int32_t* __restrict__ new_key_len, int32_t* __restrict__ gather_idx,
                                                            float* __restrict__ mean_entropy_out, int B, int T, int blank) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ int done[1024];
   __shared__ int pos[1024];
   __shared__ int s_new;
@@ -419,6 +429,8 @@ __global__ void __launch_bounds__(1024) exit_select_kernel(const float* __restri
 
 __global__ void gather_rows_kernel(const float4* __restrict__ x, float4* __restrict__ y, const int32_t* __restrict__ gather_idx,
                                    const int32_t* __restrict__ n_alive, long row_vec) {
+  pdl_trigger();
+  pdl_wait();
   const int j = blockIdx.y;
   if (j >= *n_alive) return;
   const long src = (long)gather_idx[j] * row_vec, dst = (long)j * row_vec;
@@ -429,6 +441,8 @@ __global__ void gather_rows_kernel(const float4* __restrict__ x, float4* __restr
 template <typename TI, typename TO>
 __global__ void im2col_k3s2_kernel(const TI* __restrict__ in, long sb, long sc, long st, TO* __restrict__ out, int ldo, int B,
                                    int C, int T_out) {
+  pdl_trigger();
+  pdl_wait();
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   long total = (long)B * T_out * ldo;
   if (i >= total) return;
@@ -445,6 +459,8 @@ __global__ void im2col_k3s2_kernel(const TI* __restrict__ in, long sb, long sc, 
 
 __global__ void col2im_k3s2_kernel(const float* __restrict__ dcols, int ldc, float* __restrict__ dx, int B, int C, int T_in,
                                    int T_out) {
+  pdl_trigger();
+  pdl_wait();
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   long total = (long)B * T_in * C;
   if (i >= total) return;
@@ -493,13 +509,13 @@ extern "C" int eec_ctc_fwd_bwd(const float* lp, const int64_t* targets, const in
     if (grad) {
       const long total4 = (long)E * B * T * V / 4;
       const int blocks = (int)min((long)148 * 16, cdiv64(total4, 256));
-      ctc_grad_init_kernel<<<blocks, 256, 0, S(stream)>>>((const float4*)lp, target_len, (float4*)grad, B, (long)T * V / 4, gscale, total4);
+      launch_pdl(ctc_grad_init_kernel, dim3(blocks), dim3(256), 0, S(stream), (const float4*)lp, target_len, (float4*)grad, B, (long)T * V / 4, gscale, total4);
       EEC_LAUNCH_CHECK();
     }
     const int EB = E * B;
     const int blocks = cdiv(EB * 32, 128);
 #define EEC_CTC_WARP(SPLV)                                                                                              \
-  ctc_warp_kernel<SPLV><<<blocks, 128, 0, S(stream)>>>(lp, targets, target_len, EB, B, T, V, Lmax, blank, gscale, nll, \
+  launch_pdl(ctc_warp_kernel<SPLV>, dim3(blocks), dim3(128), 0, S(stream), lp, targets, target_len, EB, B, T, V, Lmax, blank, gscale, nll, \
                                                       loss_out, grad, wsf)
     if (spl == 2) EEC_CTC_WARP(2);
     else if (spl == 4) EEC_CTC_WARP(4);
@@ -514,11 +530,11 @@ extern "C" int eec_ctc_fwd_bwd(const float* lp, const int64_t* targets, const in
   dim3 grid(B, E);
   float* ws = reinterpret_cast<float*>(workspace);
   if (Smax <= 256)
-    ctc_kernel<256><<<grid, 256, smem, S(stream)>>>(lp, targets, target_len, B, T, V, Lmax, blank, gscale, nll, loss_out, grad, ws, Smax);
+    launch_pdl(ctc_kernel<256>, dim3(grid), dim3(256), smem, S(stream), lp, targets, target_len, B, T, V, Lmax, blank, gscale, nll, loss_out, grad, ws, Smax);
   else if (Smax <= 512)
-    ctc_kernel<512><<<grid, 512, smem, S(stream)>>>(lp, targets, target_len, B, T, V, Lmax, blank, gscale, nll, loss_out, grad, ws, Smax);
+    launch_pdl(ctc_kernel<512>, dim3(grid), dim3(512), smem, S(stream), lp, targets, target_len, B, T, V, Lmax, blank, gscale, nll, loss_out, grad, ws, Smax);
   else
-    ctc_kernel<1024><<<grid, 1024, smem, S(stream)>>>(lp, targets, target_len, B, T, V, Lmax, blank, gscale, nll, loss_out, grad, ws, Smax);
+    launch_pdl(ctc_kernel<1024>, dim3(grid), dim3(1024), smem, S(stream), lp, targets, target_len, B, T, V, Lmax, blank, gscale, nll, loss_out, grad, ws, Smax);
   EEC_LAUNCH_CHECK();
   return 0;
 }
@@ -526,7 +542,7 @@ extern "C" int eec_ctc_fwd_bwd(const float* lp, const int64_t* targets, const in
 extern "C" int eec_greedy_collapse(const int32_t* argmax, int32_t* tokens, int32_t* n_tokens, int B, int T, int blank,
                                    eec_stream_t stream) {
   if (B == 0) return 0;
-  greedy_collapse_kernel<<<cdiv(B * 32, 128), 128, 0, S(stream)>>>(argmax, tokens, n_tokens, B, T, blank);
+  launch_pdl(greedy_collapse_kernel, dim3(cdiv(B * 32, 128)), dim3(128), 0, S(stream), argmax, tokens, n_tokens, B, T, blank);
   EEC_LAUNCH_CHECK();
   return 0;
 }
@@ -538,7 +554,7 @@ extern "C" int eec_exit_select(const float* entropy, const int32_t* argmax, cons
                                eec_stream_t stream) {
   EEC_CHECK_ARG(B <= 1024, "exit_select: batch must be <= 1024 (got %d)", B);
   if (B == 0) return 0;
-  exit_select_kernel<<<1, 1024, 0, S(stream)>>>(entropy, argmax, key_len_alive, row_map, n_alive, exit_idx, is_last, threshold,
+  launch_pdl(exit_select_kernel, dim3(1), dim3(1024), 0, S(stream), entropy, argmax, key_len_alive, row_map, n_alive, exit_idx, is_last, threshold,
                                                exit_index, tokens, n_tokens, new_row_map, new_key_len, gather_idx,
                                                mean_entropy_out, B, T, blank);
   EEC_LAUNCH_CHECK();
@@ -551,7 +567,7 @@ extern "C" int eec_gather_rows(const float* x, float* y, const int32_t* gather_i
   if (B == 0) return 0;
   long rv = row_elems / 4;
   dim3 grid((unsigned)min((long)32, cdiv64(rv, 256)), B);
-  gather_rows_kernel<<<grid, 256, 0, S(stream)>>>((const float4*)x, (float4*)y, gather_idx, n_alive, rv);
+  launch_pdl(gather_rows_kernel, dim3(grid), dim3(256), 0, S(stream), (const float4*)x, (float4*)y, gather_idx, n_alive, rv);
   EEC_LAUNCH_CHECK();
   return 0;
 }
@@ -564,9 +580,9 @@ extern "C" int eec_im2col_k3s2(const void* in, int in_dtype, int64_t sb, int64_t
   if (total == 0) return 0;
   int blocks = (int)cdiv64(total, 256);
   if (out_dtype == EEC_F32)
-    im2col_k3s2_kernel<float, float><<<blocks, 256, 0, S(stream)>>>((const float*)in, sb, sc, st, (float*)out, ldo, B, C, T_out);
+    launch_pdl(im2col_k3s2_kernel<float, float>, dim3(blocks), dim3(256), 0, S(stream), (const float*)in, sb, sc, st, (float*)out, ldo, B, C, T_out);
   else
-    im2col_k3s2_kernel<float, __nv_bfloat16><<<blocks, 256, 0, S(stream)>>>((const float*)in, sb, sc, st, (__nv_bfloat16*)out, ldo, B, C, T_out);
+    launch_pdl(im2col_k3s2_kernel<float, __nv_bfloat16>, dim3(blocks), dim3(256), 0, S(stream), (const float*)in, sb, sc, st, (__nv_bfloat16*)out, ldo, B, C, T_out);
   EEC_LAUNCH_CHECK();
   return 0;
 }
@@ -575,7 +591,7 @@ extern "C" int eec_col2im_k3s2(const float* dcols, int ldc, float* dx, int B, in
                                eec_stream_t stream) {
   long total = (long)B * T_in * C;
   if (total == 0) return 0;
-  col2im_k3s2_kernel<<<(int)cdiv64(total, 256), 256, 0, S(stream)>>>(dcols, ldc, dx, B, C, T_in, T_out);
+  launch_pdl(col2im_k3s2_kernel, dim3((int)cdiv64(total, 256)), dim3(256), 0, S(stream), dcols, ldc, dx, B, C, T_in, T_out);
   EEC_LAUNCH_CHECK();
   return 0;
 }

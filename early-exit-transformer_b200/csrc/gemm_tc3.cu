@@ -193,6 +193,7 @@ __global__ void __launch_bounds__(NT3, 1) gemm_tc3_kernel(const __grid_constant_
                                                           const __grid_constant__ CUtensorMap tmC,   // main output (box 32 x 32)
                                                           const __grid_constant__ CUtensorMap tmP,   // bf16 pre-activation: store (SiLU/GLU) or load (dSiLU)
                                                           const P3 p) {
+  pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   float* bias_s = reinterpret_cast<float*>(smem + OFF_BIAS);
@@ -224,6 +225,7 @@ __global__ void __launch_bounds__(NT3, 1) gemm_tc3_kernel(const __grid_constant_
     fence_barrier_init();
   }
   if (warp == 1) { tmem_alloc(tmem_ptr_smem, 512); tmem_relinquish(); }
+  pdl_wait();   // everything above overlapped the previous kernel's tail; from here on its outputs are read
   if (p.bias) {
     for (int i = threadIdx.x; i < p.N; i += NT3) bias_s[i] = p.bias[i];
   }
@@ -581,6 +583,7 @@ __global__ void __launch_bounds__(LN_NT, 1) gemm_ln3_kernel(const __grid_constan
                                                             const __grid_constant__ CUtensorMap tmR,   // fp32 residual in (box 32 x 32)
                                                             const __grid_constant__ CUtensorMap tmL,   // LayerNorm out (box 32 x 32)
                                                             const PLN p) {
+  pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   float* vecs = reinterpret_cast<float*>(smem + LN_OFF_VEC);
@@ -605,6 +608,7 @@ __global__ void __launch_bounds__(LN_NT, 1) gemm_ln3_kernel(const __grid_constan
     fence_barrier_init();
   }
   if (warp == 1) { tmem_alloc(tmem_ptr_smem, 512); tmem_relinquish(); }
+  pdl_wait();   // everything above overlapped the previous kernel's tail
   for (int i = threadIdx.x; i < 256; i += LN_NT) {
     vecs[i] = p.bias ? p.bias[i] : 0.f;
     vecs[256 + i] = p.ln_gamma[i];
@@ -805,7 +809,7 @@ int launch3(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc_
     EEC_CUDA(cudaFuncSetAttribute(gemm_tc3_kernel<AK, BK_, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM3_BYTES));
     attr_set = true;
   }
-  gemm_tc3_kernel<AK, BK_, EPI><<<grid, NT3, SMEM3_BYTES, st>>>(ta, tb, tc_, tp, p);
+  launch_pdl(gemm_tc3_kernel<AK, BK_, EPI>, dim3(grid), dim3(NT3), SMEM3_BYTES, st, ta, tb, tc_, tp, p);
   EEC_LAUNCH_CHECK();
   return 0;
 }
@@ -925,7 +929,7 @@ int gemm_ln3(const eec_gemm_desc* d, cudaStream_t st) {
     attr_set = true;
   }
   const int grid = min(p.m_tiles, g_sms3);
-  gemm_ln3_kernel<<<grid, LN_NT, LN_SMEM_BYTES, st>>>(ta, tb, tcm, trm, tlm, p);
+  launch_pdl(gemm_ln3_kernel, dim3(grid), dim3(LN_NT), LN_SMEM_BYTES, st, ta, tb, tcm, trm, tlm, p);
   EEC_LAUNCH_CHECK();
   return 0;
 }

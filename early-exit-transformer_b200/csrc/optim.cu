@@ -13,11 +13,15 @@ namespace {
 
 // state[0] = step counter (as double), state[1] = sum of squares of the gradient, state[2] = last lr, state[3] = last clip coefficient
 __global__ void optim_begin_kernel(double* state) {
+  pdl_trigger();
+  pdl_wait();
   state[0] += 1.0;
   state[1] = 0.0;
 }
 
 __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, long n4, long n, double* __restrict__ state) {
+  pdl_trigger();
+  pdl_wait();
   float acc = 0.f;
   const long stride = (long)gridDim.x * blockDim.x;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
@@ -53,6 +57,8 @@ __device__ __forceinline__ void adamw1(float& p, float g, float& m, float& v, fl
 __global__ void __launch_bounds__(256) noam_adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                                          float* __restrict__ v, __nv_bfloat16* __restrict__ shadow, long n4, long n,
                                                          double* __restrict__ state, const OptP o) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float sh[4];
   if (threadIdx.x == 0) {
     const double t = state[0];
@@ -120,12 +126,12 @@ extern "C" int eec_noam_adamw_step(float* params, const float* grads, float* exp
   }
   const long n4 = n / 4;
   const int grid = (int)max(1L, min((long)sms * 8, (n4 + 255) / 256));
-  optim_begin_kernel<<<1, 1, 0, S(stream)>>>(state);
+  launch_pdl(optim_begin_kernel, dim3(1), dim3(1), 0, S(stream), state);
   EEC_LAUNCH_CHECK();
-  sumsq_kernel<<<grid, 256, 0, S(stream)>>>(grads, n4, n, state);
+  launch_pdl(sumsq_kernel, dim3(grid), dim3(256), 0, S(stream), grads, n4, n, state);
   EEC_LAUNCH_CHECK();
   OptP o{model_size, warmup, beta1, beta2, eps, weight_decay, clip, lr_fixed};
-  noam_adamw_kernel<<<grid, 256, 0, S(stream)>>>(params, grads, exp_avg, exp_avg_sq, reinterpret_cast<__nv_bfloat16*>(bf16_shadow), n4, n, state, o);
+  launch_pdl(noam_adamw_kernel, dim3(grid), dim3(256), 0, S(stream), params, grads, exp_avg, exp_avg_sq, reinterpret_cast<__nv_bfloat16*>(bf16_shadow), n4, n, state, o);
   EEC_LAUNCH_CHECK();
   return 0;
 }

@@ -12,6 +12,8 @@ template <typename TOut>
 __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                             const float* __restrict__ beta, TOut* __restrict__ out,
                                                             float* __restrict__ mean, float* __restrict__ rstd, int rows) {
+  pdl_trigger();
+  pdl_wait();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= rows) return;
@@ -45,6 +47,8 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
                                                             int dx_accumulate, float* __restrict__ dgamma,
                                                             float* __restrict__ dbeta, __nv_bfloat16* __restrict__ dx_bf16,
                                                             float* __restrict__ dx_colsum, float colsum_scale, int rows) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float red[8][256];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int c0 = lane * 8;
@@ -116,6 +120,8 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
 __global__ void __launch_bounds__(256) logsoftmax_kernel(const float* __restrict__ logits, float* __restrict__ out,
                                                          int32_t* __restrict__ argmax, float* __restrict__ entropy,
                                                          int rows) {
+  pdl_trigger();
+  pdl_wait();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= rows) return;
@@ -155,6 +161,8 @@ __global__ void __launch_bounds__(256) logsoftmax_kernel(const float* __restrict
 // generic log-softmax backward: dlogits = g - exp(lp) * sum(g)   (V = 256)
 __global__ void __launch_bounds__(256) logsoftmax_bwd_kernel(const float* __restrict__ g, const float* __restrict__ lp,
                                                              float* __restrict__ dl, int rows) {
+  pdl_trigger();
+  pdl_wait();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= rows) return;
@@ -175,6 +183,8 @@ __global__ void __launch_bounds__(256) logsoftmax_bwd_kernel(const float* __rest
 // ------------------------------------------------------------------ casts
 template <typename TI, typename TO>
 __global__ void cast_kernel(const TI* __restrict__ in, TO* __restrict__ out, long n) {
+  pdl_trigger();
+  pdl_wait();
   long i = ((long)blockIdx.x * blockDim.x + threadIdx.x) * 8;
   if (i + 8 <= n) {
     float v[8];
@@ -189,6 +199,8 @@ __global__ void cast_kernel(const TI* __restrict__ in, TO* __restrict__ out, lon
 template <typename T>
 __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ in, int ld, float* __restrict__ out, int rows,
                                                      int cols, int rows_per_block, float scale) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float red[8][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + tx;
@@ -211,6 +223,8 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ in, i
 template <typename T>
 __global__ void __launch_bounds__(256) colsum_vec_kernel(const T* __restrict__ in, int ld, float* __restrict__ out, int rows,
                                                          int rows_per_block, float scale) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float red[8][256];
   const int cg = threadIdx.x & 31, rl = threadIdx.x >> 5;
   const int c0 = blockIdx.x * 256 + cg * 8;
@@ -244,11 +258,15 @@ __global__ void __launch_bounds__(256) colsum_vec_kernel(const T* __restrict__ i
 }
 
 __global__ void axpy_kernel(const float* __restrict__ x, float a, float* __restrict__ y, long n) {
+  pdl_trigger();
+  pdl_wait();
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) y[i] = fmaf(a, x[i], y[i]);
 }
 
 __global__ void scale_dev_kernel(const float* __restrict__ x, const float* __restrict__ s, float* __restrict__ y, long n) {
+  pdl_trigger();
+  pdl_wait();
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const float a = *s;
   if (i < n) y[i] = a * x[i];
@@ -256,6 +274,8 @@ __global__ void scale_dev_kernel(const float* __restrict__ x, const float* __res
 
 __global__ void encoder_lengths_kernel(const int64_t* __restrict__ lengths, int32_t* __restrict__ key_len, int B, int T,
                                        int div, int add) {
+  pdl_trigger();
+  pdl_wait();
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   // torch: clamp((lengths+add) / div, max=T).to(int): float32 true division, truncation
@@ -266,6 +286,8 @@ __global__ void encoder_lengths_kernel(const int64_t* __restrict__ lengths, int3
 
 // ------------------------------------------------------------------ Splitformer glue (early_exit.py:318-356)
 __global__ void stride2_gather_kernel(const float4* __restrict__ x, float4* __restrict__ y, int B, int T, int T2, int D4) {
+  pdl_trigger();
+  pdl_wait();
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   long total = (long)B * T2 * D4;
   if (i >= total) return;
@@ -276,6 +298,8 @@ __global__ void stride2_gather_kernel(const float4* __restrict__ x, float4* __re
   y[i] = (t < T) ? x[((long)b * T + t) * D4 + c] : make_float4(0.f, 0.f, 0.f, 0.f);
 }
 __global__ void repeat2_add_kernel(const float4* __restrict__ up, float4* __restrict__ y, int B, int T, int T2, int D4) {
+  pdl_trigger();
+  pdl_wait();
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   long total = (long)B * T * D4;
   if (i >= total) return;
@@ -287,6 +311,8 @@ __global__ void repeat2_add_kernel(const float4* __restrict__ up, float4* __rest
   y[i] = make_float4(v.x + u.x, v.y + u.y, v.z + u.z, v.w + u.w);
 }
 __global__ void repeat2_bwd_kernel(const float4* __restrict__ dy, float4* __restrict__ dh, int B, int T, int T2, int D4) {
+  pdl_trigger();
+  pdl_wait();
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   long total = (long)B * T2 * D4;
   if (i >= total) return;
@@ -304,6 +330,8 @@ __global__ void repeat2_bwd_kernel(const float4* __restrict__ dy, float4* __rest
   dh[i] = a;
 }
 __global__ void stride2_scatter_add_kernel(const float4* __restrict__ dh, float4* __restrict__ dx, int B, int T, int T2, int D4) {
+  pdl_trigger();
+  pdl_wait();
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   long total = (long)B * T2 * D4;
   if (i >= total) return;
@@ -327,9 +355,9 @@ extern "C" int eec_layernorm_fwd(const float* x, const float* gamma, const float
   if (rows == 0) return 0;
   int blocks = cdiv(rows, 8);
   if (out_dtype == EEC_F32)
-    layernorm_fwd_kernel<float><<<blocks, 256, 0, S(stream)>>>(x, gamma, beta, (float*)out, mean, rstd, rows);
+    launch_pdl(layernorm_fwd_kernel<float>, dim3(blocks), dim3(256), 0, S(stream), x, gamma, beta, (float*)out, mean, rstd, rows);
   else
-    layernorm_fwd_kernel<__nv_bfloat16><<<blocks, 256, 0, S(stream)>>>(x, gamma, beta, (__nv_bfloat16*)out, mean, rstd, rows);
+    launch_pdl(layernorm_fwd_kernel<__nv_bfloat16>, dim3(blocks), dim3(256), 0, S(stream), x, gamma, beta, (__nv_bfloat16*)out, mean, rstd, rows);
   EEC_LAUNCH_CHECK();
   return 0;
 }
@@ -340,7 +368,7 @@ extern "C" int eec_layernorm_bwd(const float* dy, const float* x, const float* m
   EEC_CHECK_ARG(d == 256, "layernorm_bwd: d must be 256 (got %d)", d);
   if (rows == 0) return 0;
   int blocks = min(cdiv(rows, 8), 148 * 4);
-  layernorm_bwd_kernel<<<blocks, 256, 0, S(stream)>>>(dy, x, mean, rstd, gamma, dx, dx_accumulate, dgamma, dbeta, (__nv_bfloat16*)dx_bf16, dx_colsum, colsum_scale, rows);
+  launch_pdl(layernorm_bwd_kernel, dim3(blocks), dim3(256), 0, S(stream), dy, x, mean, rstd, gamma, dx, dx_accumulate, dgamma, dbeta, (__nv_bfloat16*)dx_bf16, dx_colsum, colsum_scale, rows);
   EEC_LAUNCH_CHECK();
   return 0;
 }
@@ -349,7 +377,7 @@ extern "C" int eec_logsoftmax_fwd(const float* logits, float* out, int32_t* argm
                                   eec_stream_t stream) {
   EEC_CHECK_ARG(V == 256, "logsoftmax: V must be 256 (got %d)", V);
   if (rows == 0) return 0;
-  logsoftmax_kernel<<<cdiv(rows, 8), 256, 0, S(stream)>>>(logits, out, argmax, entropy, rows);
+  launch_pdl(logsoftmax_kernel, dim3(cdiv(rows, 8)), dim3(256), 0, S(stream), logits, out, argmax, entropy, rows);
   EEC_LAUNCH_CHECK();
   return 0;
 }
@@ -357,7 +385,7 @@ extern "C" int eec_logsoftmax_fwd(const float* logits, float* out, int32_t* argm
 extern "C" int eec_logsoftmax_bwd(const float* g, const float* lp, float* dlogits, int rows, int V, eec_stream_t stream) {
   EEC_CHECK_ARG(V == 256, "logsoftmax_bwd: V must be 256 (got %d)", V);
   if (rows == 0) return 0;
-  logsoftmax_bwd_kernel<<<cdiv(rows, 8), 256, 0, S(stream)>>>(g, lp, dlogits, rows);
+  launch_pdl(logsoftmax_bwd_kernel, dim3(cdiv(rows, 8)), dim3(256), 0, S(stream), g, lp, dlogits, rows);
   EEC_LAUNCH_CHECK();
   return 0;
 }
@@ -366,13 +394,13 @@ extern "C" int eec_cast(const void* in, int in_dtype, void* out, int out_dtype, 
   if (n == 0) return 0;
   int blocks = (int)cdiv64(cdiv64(n, 8), 256);
   if (in_dtype == EEC_F32 && out_dtype == EEC_BF16)
-    cast_kernel<float, __nv_bfloat16><<<blocks, 256, 0, S(stream)>>>((const float*)in, (__nv_bfloat16*)out, n);
+    launch_pdl(cast_kernel<float, __nv_bfloat16>, dim3(blocks), dim3(256), 0, S(stream), (const float*)in, (__nv_bfloat16*)out, n);
   else if (in_dtype == EEC_BF16 && out_dtype == EEC_F32)
-    cast_kernel<__nv_bfloat16, float><<<blocks, 256, 0, S(stream)>>>((const __nv_bfloat16*)in, (float*)out, n);
+    launch_pdl(cast_kernel<__nv_bfloat16, float>, dim3(blocks), dim3(256), 0, S(stream), (const __nv_bfloat16*)in, (float*)out, n);
   else if (in_dtype == EEC_F32 && out_dtype == EEC_F32)
-    cast_kernel<float, float><<<blocks, 256, 0, S(stream)>>>((const float*)in, (float*)out, n);
+    launch_pdl(cast_kernel<float, float>, dim3(blocks), dim3(256), 0, S(stream), (const float*)in, (float*)out, n);
   else
-    cast_kernel<__nv_bfloat16, __nv_bfloat16><<<blocks, 256, 0, S(stream)>>>((const __nv_bfloat16*)in, (__nv_bfloat16*)out, n);
+    launch_pdl(cast_kernel<__nv_bfloat16, __nv_bfloat16>, dim3(blocks), dim3(256), 0, S(stream), (const __nv_bfloat16*)in, (__nv_bfloat16*)out, n);
   EEC_LAUNCH_CHECK();
   return 0;
 }
@@ -383,29 +411,29 @@ extern "C" int eec_colsum(const void* in, int dtype, int ld, float* out, float s
   if (cols % 256 == 0 && ld % 8 == 0) {
     const int rpbv = 128;
     dim3 gv(cols / 256, cdiv(rows, rpbv));
-    if (dtype == EEC_F32) colsum_vec_kernel<float><<<gv, 256, 0, S(stream)>>>((const float*)in, ld, out, rows, rpbv, scale);
-    else colsum_vec_kernel<__nv_bfloat16><<<gv, 256, 0, S(stream)>>>((const __nv_bfloat16*)in, ld, out, rows, rpbv, scale);
+    if (dtype == EEC_F32) launch_pdl(colsum_vec_kernel<float>, dim3(gv), dim3(256), 0, S(stream), (const float*)in, ld, out, rows, rpbv, scale);
+    else launch_pdl(colsum_vec_kernel<__nv_bfloat16>, dim3(gv), dim3(256), 0, S(stream), (const __nv_bfloat16*)in, ld, out, rows, rpbv, scale);
     EEC_LAUNCH_CHECK();
     return 0;
   }
   int rpb = 256;
   dim3 grid(cdiv(cols, 32), cdiv(rows, rpb));
-  if (dtype == EEC_F32) colsum_kernel<float><<<grid, 256, 0, S(stream)>>>((const float*)in, ld, out, rows, cols, rpb, scale);
-  else colsum_kernel<__nv_bfloat16><<<grid, 256, 0, S(stream)>>>((const __nv_bfloat16*)in, ld, out, rows, cols, rpb, scale);
+  if (dtype == EEC_F32) launch_pdl(colsum_kernel<float>, dim3(grid), dim3(256), 0, S(stream), (const float*)in, ld, out, rows, cols, rpb, scale);
+  else launch_pdl(colsum_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, S(stream), (const __nv_bfloat16*)in, ld, out, rows, cols, rpb, scale);
   EEC_LAUNCH_CHECK();
   return 0;
 }
 
 extern "C" int eec_axpy(const float* x, float a, float* y, int64_t n, eec_stream_t stream) {
   if (n == 0) return 0;
-  axpy_kernel<<<(int)cdiv64(n, 256), 256, 0, S(stream)>>>(x, a, y, n);
+  launch_pdl(axpy_kernel, dim3((int)cdiv64(n, 256)), dim3(256), 0, S(stream), x, a, y, n);
   EEC_LAUNCH_CHECK();
   return 0;
 }
 
 extern "C" int eec_scale_dev(const float* x, const float* s_dev, float* y, int64_t n, eec_stream_t stream) {
   if (n == 0) return 0;
-  scale_dev_kernel<<<(int)cdiv64(n, 256), 256, 0, S(stream)>>>(x, s_dev, y, n);
+  launch_pdl(scale_dev_kernel, dim3((int)cdiv64(n, 256)), dim3(256), 0, S(stream), x, s_dev, y, n);
   EEC_LAUNCH_CHECK();
   return 0;
 }
@@ -413,7 +441,7 @@ extern "C" int eec_scale_dev(const float* x, const float* s_dev, float* y, int64
 extern "C" int eec_encoder_lengths(const int64_t* lengths, int32_t* key_len, int B, int T, int div, int add,
                                    eec_stream_t stream) {
   if (B == 0) return 0;
-  encoder_lengths_kernel<<<cdiv(B, 128), 128, 0, S(stream)>>>(lengths, key_len, B, T, div, add);
+  launch_pdl(encoder_lengths_kernel, dim3(cdiv(B, 128)), dim3(128), 0, S(stream), lengths, key_len, B, T, div, add);
   EEC_LAUNCH_CHECK();
   return 0;
 }
@@ -422,7 +450,7 @@ extern "C" int eec_encoder_lengths(const int64_t* lengths, int32_t* key_len, int
   do {                                                                              \
     long tot_ = (total);                                                            \
     if (tot_ > 0) {                                                                 \
-      kernel<<<(int)cdiv64(tot_, 256), 256, 0, S(stream)>>>(__VA_ARGS__);           \
+      launch_pdl(kernel, dim3((int)cdiv64(tot_, 256)), dim3(256), 0, S(stream), __VA_ARGS__);           \
       EEC_LAUNCH_CHECK();                                                           \
     }                                                                               \
   } while (0)
