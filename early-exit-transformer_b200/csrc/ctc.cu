@@ -149,23 +149,28 @@ __global__ void ctc_grad_init_kernel(const float4* __restrict__ lp, const int64_
 }
 
 template <int SPL>
-__global__ void __launch_bounds__(128) ctc_warp_kernel(const float* __restrict__ lp_all, const int64_t* __restrict__ targets,
-                                                       const int64_t* __restrict__ target_len, int EB, int B, int T, int V, int Lmax,
-                                                       int blank, float gscale, float* __restrict__ nll_all,
-                                                       float* __restrict__ loss_out, float* __restrict__ grad_all,
-                                                       float* __restrict__ alpha_ws) {
+__global__ void __launch_bounds__(64) ctc_warp_kernel(const float* __restrict__ lp_all, const int64_t* __restrict__ targets,
+                                                      const int64_t* __restrict__ target_len, int EB, int B, int T, int V, int Lmax,
+                                                      int blank, float gscale, float* __restrict__ nll_all,
+                                                      float* __restrict__ loss_out, float* __restrict__ grad_all,
+                                                      float* __restrict__ alpha_ws, float* __restrict__ beta_ws) {
   pdl_trigger();
   pdl_wait();
+  // One CTA of TWO warps per (exit, utterance): warp 0 runs the alpha recursion forward in time while warp 1 runs the beta
+  // recursion backward in time (the two T-step dependency chains are the whole cost of this kernel and are independent);
+  // both leave their lattices in the workspace, then the two warps share the embarrassingly parallel occupancy pass.
   constexpr int NL = SPL / 2;   // label states per lane
   constexpr int PF = 4;         // prefetch distance (time steps)
   constexpr int SW = 32 * SPL;  // workspace row width
-  const int wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  __shared__ float s_ll;
+  const int wg = blockIdx.x;
+  const int role = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  if (wg >= EB) return;
   const int e = wg / B, b = wg % B;
   const float* lp = lp_all + (long)wg * T * V;
   float* grad = grad_all ? grad_all + (long)wg * T * V : nullptr;
   float* aw = alpha_ws + (long)wg * T * SW + lane * SPL;
+  float* bw = beta_ws + (long)wg * T * SW + lane * SPL;
   int U = (int)target_len[b];
   if (U > Lmax) U = Lmax;
   const int S = 2 * U + 1;
@@ -181,149 +186,169 @@ __global__ void __launch_bounds__(128) ctc_warp_kernel(const float* __restrict__
     skip[j] = (li < U) && (li >= 1) && lab[j] != lprev;
     skipf[j] = (li + 1 < U) && lab[j] != lnext;
   }
-  float a[SPL];
-  // ---------------- alpha
-#pragma unroll
-  for (int i = 0; i < SPL; ++i) {
-    const int s = s0 + i;
-    a[i] = CTC_NEG;
-    if (s == 0) a[i] = lp[blank] * LOG2E_F;
-    if (s == 1 && S > 1) a[i] = lp[lab[0]] * LOG2E_F;
-  }
-#pragma unroll
-  for (int i = 0; i < SPL; ++i) aw[i] = a[i];
+  const float denom = (float)B * (float)max(U, 1);
   float emb[PF], eml[PF][NL];
+  if (role == 0) {
+    // ---------------- alpha (forward in time)
+    float a[SPL];
 #pragma unroll
-  for (int k = 0; k < PF; ++k) {
-    const int t = 1 + k;
-    if (t < T) {
-      emb[k] = lp[(long)t * V + blank] * LOG2E_F;
-#pragma unroll
-      for (int j = 0; j < NL; ++j) eml[k][j] = lp[(long)t * V + lab[j]] * LOG2E_F;
+    for (int i = 0; i < SPL; ++i) {
+      const int s = s0 + i;
+      a[i] = CTC_NEG;
+      if (s == 0) a[i] = lp[blank] * LOG2E_F;
+      if (s == 1 && S > 1) a[i] = lp[lab[0]] * LOG2E_F;
     }
-  }
-  for (int t0 = 1; t0 < T; t0 += PF) {
+#pragma unroll
+    for (int i = 0; i < SPL; ++i) aw[i] = a[i];
 #pragma unroll
     for (int k = 0; k < PF; ++k) {
-      const int t = t0 + k;
+      const int t = 1 + k;
       if (t < T) {
-        const float lb_ = emb[k];
-        float ll_[NL];
+        emb[k] = lp[(long)t * V + blank] * LOG2E_F;
 #pragma unroll
-        for (int j = 0; j < NL; ++j) ll_[j] = eml[k][j];
-        if (t + PF < T) {
-          emb[k] = lp[(long)(t + PF) * V + blank] * LOG2E_F;
+        for (int j = 0; j < NL; ++j) eml[k][j] = lp[(long)t * V + lab[j]] * LOG2E_F;
+      }
+    }
+    for (int t0 = 1; t0 < T; t0 += PF) {
 #pragma unroll
-          for (int j = 0; j < NL; ++j) eml[k][j] = lp[(long)(t + PF) * V + lab[j]] * LOG2E_F;
-        }
-        float prev_last = __shfl_up_sync(0xffffffffu, a[SPL - 1], 1);
-        if (lane == 0) prev_last = CTC_NEG;
-        float na[SPL];
+      for (int k = 0; k < PF; ++k) {
+        const int t = t0 + k;
+        if (t < T) {
+          const float lb_ = emb[k];
+          float ll_[NL];
 #pragma unroll
-        for (int i = 0; i < SPL; ++i) {
-          const float am1 = (i == 0) ? prev_last : a[i - 1];
-          if ((i & 1) == 0) {
-            na[i] = flse2(a[i], am1) + lb_;
-          } else {
-            const float am2 = (i == 1) ? prev_last : a[i - 2];
-            na[i] = flse3(a[i], am1, skip[i >> 1] ? am2 : CTC_NEG) + ll_[i >> 1];
+          for (int j = 0; j < NL; ++j) ll_[j] = eml[k][j];
+          if (t + PF < T) {
+            emb[k] = lp[(long)(t + PF) * V + blank] * LOG2E_F;
+#pragma unroll
+            for (int j = 0; j < NL; ++j) eml[k][j] = lp[(long)(t + PF) * V + lab[j]] * LOG2E_F;
           }
-          na[i] = (s0 + i >= S) ? CTC_NEG : fmaxf(na[i], CTC_NEG);
-        }
+          float prev_last = __shfl_up_sync(0xffffffffu, a[SPL - 1], 1);
+          if (lane == 0) prev_last = CTC_NEG;
+          float na[SPL];
 #pragma unroll
-        for (int i = 0; i < SPL; ++i) { a[i] = na[i]; aw[(long)t * SW + i] = na[i]; }
+          for (int i = 0; i < SPL; ++i) {
+            const float am1 = (i == 0) ? prev_last : a[i - 1];
+            if ((i & 1) == 0) {
+              na[i] = flse2(a[i], am1) + lb_;
+            } else {
+              const float am2 = (i == 1) ? prev_last : a[i - 2];
+              na[i] = flse3(a[i], am1, skip[i >> 1] ? am2 : CTC_NEG) + ll_[i >> 1];
+            }
+            na[i] = (s0 + i >= S) ? CTC_NEG : fmaxf(na[i], CTC_NEG);
+          }
+#pragma unroll
+          for (int i = 0; i < SPL; ++i) { a[i] = na[i]; aw[(long)t * SW + i] = na[i]; }
+        }
+      }
+    }
+    // log-likelihood = lse(alpha_T-1[S-1], alpha_T-1[S-2])
+    float mine = CTC_NEG;   // log2 domain
+#pragma unroll
+    for (int i = 0; i < SPL; ++i) {
+      const int s = s0 + i;
+      if (s == S - 1 || (s == S - 2 && S >= 2)) mine = flse2(mine, a[i]);
+    }
+    float mx = mine;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float se = fex2(mine - mx);
+    se = warp_sum(se);
+    const float llv = mx + flg2(se);                 // log2 P(y|x)
+    if (lane == 0) {
+      const bool feas = llv > 0.5f * CTC_NEG;
+      s_ll = llv;
+      nll_all[wg] = feas ? -llv * LN2_F : 0.f;
+      if (feas && loss_out) atomicAdd(loss_out + e, -llv * LN2_F / denom);
+    }
+  } else if (grad) {
+    // ---------------- beta (backward in time); the workspace receives beta_t(s) - emission_t(s)
+    float bt[SPL];
+#pragma unroll
+    for (int k = 0; k < PF; ++k) {
+      const int t = T - 1 - k;
+      if (t >= 0) {
+        emb[k] = lp[(long)t * V + blank] * LOG2E_F;
+#pragma unroll
+        for (int j = 0; j < NL; ++j) eml[k][j] = lp[(long)t * V + lab[j]] * LOG2E_F;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < SPL; ++i) bt[i] = CTC_NEG;
+    for (int t0 = T - 1; t0 >= 0; t0 -= PF) {
+#pragma unroll
+      for (int k = 0; k < PF; ++k) {
+        const int t = t0 - k;
+        if (t >= 0) {
+          const float lb_ = emb[k];
+          float ll_[NL];
+#pragma unroll
+          for (int j = 0; j < NL; ++j) ll_[j] = eml[k][j];
+          if (t - PF >= 0) {
+            emb[k] = lp[(long)(t - PF) * V + blank] * LOG2E_F;
+#pragma unroll
+            for (int j = 0; j < NL; ++j) eml[k][j] = lp[(long)(t - PF) * V + lab[j]] * LOG2E_F;
+          }
+          float nb[SPL];
+          if (t == T - 1) {
+#pragma unroll
+            for (int i = 0; i < SPL; ++i) {
+              const int s = s0 + i;
+              nb[i] = (s < S && s >= S - 2) ? (((i & 1) == 0) ? lb_ : ll_[i >> 1]) : CTC_NEG;
+            }
+          } else {
+            float n0 = __shfl_down_sync(0xffffffffu, bt[0], 1);
+            float n1 = __shfl_down_sync(0xffffffffu, bt[1], 1);
+            if (lane == 31) { n0 = CTC_NEG; n1 = CTC_NEG; }
+#pragma unroll
+            for (int i = 0; i < SPL; ++i) {
+              const float bp1 = (i == SPL - 1) ? n0 : bt[i + 1];
+              if ((i & 1) == 0) {
+                nb[i] = flse2(bt[i], bp1) + lb_;
+              } else {
+                const float bp2 = (i == SPL - 1) ? n1 : bt[(i + 2 < SPL) ? i + 2 : i];
+                nb[i] = flse3(bt[i], bp1, skipf[i >> 1] ? bp2 : CTC_NEG) + ll_[i >> 1];
+              }
+              nb[i] = (s0 + i >= S) ? CTC_NEG : fmaxf(nb[i], CTC_NEG);
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < SPL; ++i) {
+            bt[i] = nb[i];
+            bw[(long)t * SW + i] = nb[i] - (((i & 1) == 0) ? lb_ : ll_[i >> 1]);
+          }
+        }
       }
     }
   }
-  // log-likelihood = lse(alpha_T-1[S-1], alpha_T-1[S-2])
-  float mine = CTC_NEG;   // log2 domain
-#pragma unroll
-  for (int i = 0; i < SPL; ++i) {
-    const int s = s0 + i;
-    if (s == S - 1 || (s == S - 2 && S >= 2)) mine = flse2(mine, a[i]);
-  }
-  float mx = mine;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-  float se = fex2(mine - mx);
-  se = warp_sum(se);
-  const float ll = mx + flg2(se);                 // log2 P(y|x)
-  const bool feasible = ll > 0.5f * CTC_NEG;
-  const float denom = (float)B * (float)max(U, 1);
-  if (lane == 0) {
-    nll_all[wg] = feasible ? -ll * LN2_F : 0.f;
-    if (feasible && loss_out) atomicAdd(loss_out + e, -ll * LN2_F / denom);
-  }
+  __syncthreads();
   if (!grad) return;
+  const float ll = s_ll;
+  const bool feasible = ll > 0.5f * CTC_NEG;
   if (!feasible) {  // zero_infinity: the dense init wrote scale*softmax; zero the whole slab
     float4* g4 = reinterpret_cast<float4*>(grad);
-    for (long i = lane; i < (long)T * V / 4; i += 32) g4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (long i = threadIdx.x; i < (long)T * V / 4; i += 64) g4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     return;
   }
-  // ---------------- beta + occupancy
+  // ---------------- occupancy: posterior of state s at time t = 2^(alpha + (beta - emission) - ll); no dependency between time steps
   const float sc = gscale / denom;
-  float bt[SPL];
-  float al[PF][SPL];
+  constexpr int OU = 8;   // time steps in flight per warp (the lattice rows come back from L2 / HBM)
+  for (int t0 = role * OU; t0 < T; t0 += 2 * OU) {
+    float av[OU][SPL], bv[OU][SPL];
 #pragma unroll
-  for (int k = 0; k < PF; ++k) {
-    const int t = T - 1 - k;
-    if (t >= 0) {
-      emb[k] = lp[(long)t * V + blank] * LOG2E_F;
+    for (int k = 0; k < OU; ++k)
+      if (t0 + k < T) {
 #pragma unroll
-      for (int j = 0; j < NL; ++j) eml[k][j] = lp[(long)t * V + lab[j]] * LOG2E_F;
+        for (int i = 0; i < SPL; ++i) { av[k][i] = aw[(long)(t0 + k) * SW + i]; bv[k][i] = bw[(long)(t0 + k) * SW + i]; }
+      }
 #pragma unroll
-      for (int i = 0; i < SPL; ++i) al[k][i] = aw[(long)t * SW + i];
-    }
-  }
-#pragma unroll
-  for (int i = 0; i < SPL; ++i) bt[i] = CTC_NEG;
-  for (int t0 = T - 1; t0 >= 0; t0 -= PF) {
-#pragma unroll
-    for (int k = 0; k < PF; ++k) {
-      const int t = t0 - k;
-      if (t >= 0) {
-        const float lb_ = emb[k];
-        float ll_[NL], av[SPL];
-#pragma unroll
-        for (int j = 0; j < NL; ++j) ll_[j] = eml[k][j];
-#pragma unroll
-        for (int i = 0; i < SPL; ++i) av[i] = al[k][i];
-        if (t - PF >= 0) {
-          emb[k] = lp[(long)(t - PF) * V + blank] * LOG2E_F;
-#pragma unroll
-          for (int j = 0; j < NL; ++j) eml[k][j] = lp[(long)(t - PF) * V + lab[j]] * LOG2E_F;
-#pragma unroll
-          for (int i = 0; i < SPL; ++i) al[k][i] = aw[(long)(t - PF) * SW + i];
-        }
-        float nb[SPL];
-        if (t == T - 1) {
-#pragma unroll
-          for (int i = 0; i < SPL; ++i) {
-            const int s = s0 + i;
-            nb[i] = (s < S && s >= S - 2) ? (((i & 1) == 0) ? lb_ : ll_[i >> 1]) : CTC_NEG;
-          }
-        } else {
-          float n0 = __shfl_down_sync(0xffffffffu, bt[0], 1);
-          float n1 = __shfl_down_sync(0xffffffffu, bt[1], 1);
-          if (lane == 31) { n0 = CTC_NEG; n1 = CTC_NEG; }
-#pragma unroll
-          for (int i = 0; i < SPL; ++i) {
-            const float bp1 = (i == SPL - 1) ? n0 : bt[i + 1];
-            if ((i & 1) == 0) {
-              nb[i] = flse2(bt[i], bp1) + lb_;
-            } else {
-              const float bp2 = (i == SPL - 1) ? n1 : bt[(i + 2 < SPL) ? i + 2 : i];
-              nb[i] = flse3(bt[i], bp1, skipf[i >> 1] ? bp2 : CTC_NEG) + ll_[i >> 1];
-            }
-            nb[i] = (s0 + i >= S) ? CTC_NEG : fmaxf(nb[i], CTC_NEG);
-          }
-        }
+    for (int k = 0; k < OU; ++k) {
+      const int t = t0 + k;
+      if (t < T) {
         float occ_blank = 0.f;
 #pragma unroll
         for (int i = 0; i < SPL; ++i) {
-          bt[i] = nb[i];
-          const float em = ((i & 1) == 0) ? lb_ : ll_[i >> 1];
-          const float o = fex2(fmaxf(av[i] + nb[i] - em - ll, -126.f));   // posterior of state s at time t (<= 1)
+          const float o = fex2(fmaxf(av[k][i] + bv[k][i] - ll, -126.f));
           if ((i & 1) == 0) occ_blank += o;
           else if (o > 1e-30f) atomicAdd(grad + (long)t * V + lab[i >> 1], -sc * o);
         }
@@ -494,7 +519,8 @@ static int ctc_spl(int Lmax) {
 extern "C" int64_t eec_ctc_workspace_bytes(int E, int B, int T, int Lmax) {
   const int spl = ctc_spl(Lmax);
   const int width = spl ? 32 * spl : ctc_smax(Lmax);
-  return (int64_t)E * B * T * width * (int64_t)sizeof(float);
+  // warp kernel: an alpha lattice AND a beta lattice (the two recursions run concurrently on two warps)
+  return (int64_t)(spl ? 2 : 1) * E * B * T * width * (int64_t)sizeof(float);
 }
 
 extern "C" int eec_ctc_fwd_bwd(const float* lp, const int64_t* targets, const int64_t* target_len, int E, int B, int T,
@@ -513,10 +539,10 @@ extern "C" int eec_ctc_fwd_bwd(const float* lp, const int64_t* targets, const in
       EEC_LAUNCH_CHECK();
     }
     const int EB = E * B;
-    const int blocks = cdiv(EB * 32, 128);
+    float* wsb = wsf + (long)EB * T * 32 * spl;
 #define EEC_CTC_WARP(SPLV)                                                                                              \
-  launch_pdl(ctc_warp_kernel<SPLV>, dim3(blocks), dim3(128), 0, S(stream), lp, targets, target_len, EB, B, T, V, Lmax, blank, gscale, nll, \
-                                                      loss_out, grad, wsf)
+  launch_pdl(ctc_warp_kernel<SPLV>, dim3(EB), dim3(64), 0, S(stream), lp, targets, target_len, EB, B, T, V, Lmax, blank, gscale, nll, \
+                                                      loss_out, grad, wsf, wsb)
     if (spl == 2) EEC_CTC_WARP(2);
     else if (spl == 4) EEC_CTC_WARP(4);
     else if (spl == 6) EEC_CTC_WARP(6);
