@@ -54,7 +54,7 @@ _SIGS = {
     "eec_bn_silu_train": [vp, vp, vp, vp, vp, vp, vp, f32, vp, vp, vp, i32, i32, i32, vp],
     "eec_bn_silu_bwd_stats": [vp, i32, vp, vp, vp, vp, vp, vp, i32, i32, vp],
     "eec_bn_silu_bwd_apply": [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, vp],
-    "eec_dwconv_bwd": [vp, vp, i32, vp, vp, vp, vp, i32, i32, i32, i32, vp],
+    "eec_dwconv_bwd": [vp, vp, i32, vp, vp, vp, vp, i32, i32, i32, i32, vp, vp],
     "eec_glu_bwd": [vp, vp, vp, i32, i32, i32, vp],
     "eec_logsoftmax_fwd": [vp, vp, vp, vp, i32, i32, vp],
     "eec_logsoftmax_bwd": [vp, vp, vp, i32, i32, vp],
@@ -76,7 +76,8 @@ _SIGS = {
     "eec_repeat2_bwd": [vp, vp, i32, i32, i32, vp],
     "eec_stride2_scatter_add": [vp, vp, i32, i32, i32, vp],
 }
-EXPORTS = sorted(list(_SIGS) + ["eec_last_error", "eec_version", "eec_device_ok", "eec_ctc_workspace_bytes", "eec_launch_count"])
+EXPORTS = sorted(list(_SIGS) + ["eec_last_error", "eec_version", "eec_device_ok", "eec_ctc_workspace_bytes", "eec_dwconv_bwd_workspace_bytes",
+                             "eec_launch_count"])
 
 _lib = None
 
@@ -108,6 +109,8 @@ def load():
     lib.eec_launch_count.argtypes = []
     lib.eec_ctc_workspace_bytes.restype = i64
     lib.eec_ctc_workspace_bytes.argtypes = [i32, i32, i32, i32]
+    lib.eec_dwconv_bwd_workspace_bytes.restype = i64
+    lib.eec_dwconv_bwd_workspace_bytes.argtypes = [i32, i32, i32]
     _lib = lib
     return lib
 

@@ -115,7 +115,8 @@ def bn_silu_bwd(ds, c, save_mean, save_rstd, bn_w, bn_b, sums2, dc, dgamma, dbet
 
 
 def dwconv_bwd(dc, g, w, dg, dw, dbias, B, T, K):
-    call("eec_dwconv_bwd", ptr(dc), ptr(g), dt(g), ptr(w), ptr(dg), ptr(dw), ptr(dbias), B, T, 256, K, stream())
+    ws = torch.empty(L.load().eec_dwconv_bwd_workspace_bytes(B, T, 256) // 4, dtype=torch.float32, device=dc.device)
+    call("eec_dwconv_bwd", ptr(dc), ptr(g), dt(g), ptr(w), ptr(dg), ptr(dw), ptr(dbias), B, T, 256, K, ptr(ws), stream())
 
 
 def glu_bwd(z, dg, dz):

@@ -142,8 +142,11 @@ int eec_bn_silu_bwd_apply(const void* ds, int dtype, const float* c, const float
                           const float* save_rstd, const float* bn_w, const float* bn_b,
                           const double* sums2, float* dc, float* dgamma, float* dbeta, int rows, int C,
                           eec_stream_t stream);
+/* workspace: eec_dwconv_bwd_workspace_bytes(B, T, C) bytes of device memory (per-block partial weight gradients: the kernel
+ * writes them without atomics and a second launch reduces them into dw / dbias, both accumulated) */
+int64_t eec_dwconv_bwd_workspace_bytes(int B, int T, int C);
 int eec_dwconv_bwd(const float* dc, const void* g, int dtype, const float* w, void* dg, float* dw,
-                   float* dbias, int B, int T, int C, int K, eec_stream_t stream);
+                   float* dbias, int B, int T, int C, int K, void* workspace, eec_stream_t stream);
 /* GLU backward: z [rows, 2C] (dtype), dg [rows,C] (dtype) -> dz [rows,2C] (dtype) */
 int eec_glu_bwd(const void* z, const void* dg, void* dz, int dtype, int rows, int C, eec_stream_t stream);
 
