@@ -101,6 +101,12 @@ int get_tmap_box32(CUtensorMap* out, const void* base, bool bf16, uint64_t cols,
   uint32_t b[2] = {32, 32};
   return get_tmap(out, base, 2, d, s, b, bf16 ? 2 /*SWIZZLE_64B*/ : 3 /*SWIZZLE_128B*/, !bf16);
 }
+int get_tmap_box(CUtensorMap* out, const void* base, bool bf16, uint64_t cols, uint64_t rows, uint64_t ld_elems, uint32_t box_cols,
+                 uint32_t box_rows, int swizzle) {
+  uint64_t d[2] = {cols, rows}, s[1] = {ld_elems * (bf16 ? 2 : 4)};
+  uint32_t b[2] = {box_cols, box_rows};
+  return get_tmap(out, base, 2, d, s, b, swizzle, !bf16);
+}
 int get_tmap_3d(CUtensorMap* out, const void* base, uint64_t dim0, uint64_t dim1, uint64_t dim2, uint64_t stride1_bytes,
                 uint64_t stride2_bytes, uint32_t box0, uint32_t box1, uint32_t box2) {
   uint64_t d[3] = {dim0, dim1, dim2}, s[2] = {stride1_bytes, stride2_bytes};

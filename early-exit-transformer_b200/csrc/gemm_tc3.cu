@@ -29,17 +29,23 @@ namespace eec {
 namespace {
 using namespace tc;
 
-constexpr int BM = 128, BN = 256, BK = 64, NSTAGE = 3;
+constexpr int BM = 128, BN = 256, BK = 64;
 constexpr int A_BYTES = BM * BK * 2;              // 16 KB
 constexpr int B_BYTES = BN * BK * 2;              // 32 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;    // 48 KB
 constexpr int NEW = 16;                           // epilogue warps
-constexpr int WBUF = 4096;                        // staging bytes per epilogue warp: one fp32 box or two bf16 boxes
-constexpr int OFF_STG = NSTAGE * STAGE_BYTES;
 constexpr int MAX_BIAS = 2048;
-constexpr int OFF_BIAS = OFF_STG + NEW * WBUF;    // float[MAX_BIAS]
-constexpr int OFF_BAR = OFF_BIAS + MAX_BIAS * 4;
-constexpr int SMEM3_BYTES = OFF_BAR + 512 + 1024;
+// Shared-memory layout for an NST-deep operand ring.  NST = 3: 4 KB of staging per epilogue warp (one fp32 box or two bf16
+// boxes of 32 columns) + the bias vector.  NST = 4 (plain fp32-output GEMMs: weight gradients, the long-K dgrad): these
+// kernels are bound by TMA latency x bytes in flight per SM (a CTA with 144 KB in flight streams 65 GB/s, 1.9 us per stage
+// round trip), so the ring gets a fourth stage and the staging shrinks to one 2 KB box of 16 fp32 columns per warp.
+template <int NST> struct L3 {
+  static constexpr int WB = (NST == 4) ? 2048 : 4096;
+  static constexpr int OFF_STG = NST * STAGE_BYTES;
+  static constexpr int OFF_BIAS = OFF_STG + NEW * WB;                       // float[MAX_BIAS] | 2 KB of scratch
+  static constexpr int OFF_BAR = OFF_BIAS + ((NST == 4) ? 2048 : MAX_BIAS * 4);
+  static constexpr int BYTES = OFF_BAR + 512;                               // base must be 1024-byte aligned (checked)
+};
 constexpr int NT3 = 64 + NEW * 32;                // 576
 
 enum { EPI_GENERIC = 0, EPI_GLU = 1 };
@@ -188,16 +194,19 @@ struct UnitIter {
   }
 };
 
-template <bool A_KMAJ, bool B_KMAJ, int EPI>
+template <bool A_KMAJ, bool B_KMAJ, int EPI, int NST>
 __global__ void __launch_bounds__(NT3, 1) gemm_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                                                           const __grid_constant__ CUtensorMap tmC,   // main output (box 32 x 32)
                                                           const __grid_constant__ CUtensorMap tmP,   // bf16 pre-activation: store (SiLU/GLU) or load (dSiLU)
                                                           const P3 p) {
   pdl_trigger();
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  float* bias_s = reinterpret_cast<float*>(smem + OFF_BIAS);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+  constexpr int NSTAGE = NST;
+  using LY = L3<NST>;
+  extern __shared__ __align__(1024) uint8_t smem_al[];
+  uint8_t* smem = smem_al;
+  if (threadIdx.x == 0 && (smem_u32(smem) & 1023u)) { printf("eec: gemm_tc3 smem base not 1024-aligned\n"); __trap(); }
+  float* bias_s = reinterpret_cast<float*>(smem + LY::OFF_BIAS);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + LY::OFF_BAR);
   uint64_t* empty_bar = full_bar + NSTAGE;
   uint64_t* tfull_bar = empty_bar + NSTAGE;   // [2]
   uint64_t* tempty_bar = tfull_bar + 2;       // [2]
@@ -304,8 +313,10 @@ __global__ void __launch_bounds__(NT3, 1) gemm_tc3_kernel(const __grid_constant_
           mbar_wait(&full_bar[s], ph);
           if (prof) w_full += clock64() - t_;
           if (!(p.debug & 128)) tc_fence_after();
-          const uint64_t ad = (s == 0) ? adesc[0] : (s == 1) ? adesc[1] : adesc[2];
-          const uint64_t bd = (s == 0) ? bdesc[0] : (s == 1) ? bdesc[1] : bdesc[2];
+          uint64_t ad = adesc[0], bd = bdesc[0];   // (explicit selects keep the descriptor arrays in registers)
+#pragma unroll
+          for (int i = 1; i < NSTAGE; ++i)
+            if (s == i) { ad = adesc[i]; bd = bdesc[i]; }
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) umma_bf16(d_tmem, ad + k * A_KSTEP, bd + k * B_KSTEP, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           umma_commit(&empty_bar[s]);
@@ -322,7 +333,7 @@ __global__ void __launch_bounds__(NT3, 1) gemm_tc3_kernel(const __grid_constant_
     const int q = warp & 3;
     const int cg = e >> 2;
     WStager st;
-    st.buf = smem + OFF_STG + e * WBUF;
+    st.buf = smem + LY::OFF_STG + e * LY::WB;
     st.lane = lane;
     st.sub = 0;
     st.pend_f32 = false;
@@ -443,6 +454,37 @@ __global__ void __launch_bounds__(NT3, 1) gemm_tc3_kernel(const __grid_constant_
           float x[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) x[j] = __uint_as_float(cur[j]);
+          if (NST == 4) {
+            // plain fp32 output (store or split-K reduce-add): one 2 KB box of 16 columns per sub-slab (64-byte rows, 64B swizzle)
+            if (p.alpha != 1.0f) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) x[j] *= p.alpha;
+            }
+            if (p.residual && first_split && valid) {
+              const long rr = p.res_row_mod ? (m % p.res_row_mod) : m;
+              const float* rp = p.residual + rr * p.ldr + n;
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                const float4 f = *reinterpret_cast<const float4*>(rp + g * 4);
+                x[g * 4] += f.x; x[g * 4 + 1] += f.y; x[g * 4 + 2] += f.z; x[g * 4 + 3] += f.w;
+              }
+            }
+            if (lane == 0) bulk_wait_read<0>();
+            __syncwarp();
+            uint8_t* row = st.buf + lane * 64;
+            const int sw = (lane >> 1) & 3;
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+              *reinterpret_cast<float4*>(row + ((c ^ sw) << 4)) = make_float4(x[c * 4], x[c * 4 + 1], x[c * 4 + 2], x[c * 4 + 3]);
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              if (p.accumulate) tma_reduce_add_2d(&tmC, st.buf, n, row0);
+              else tma_store_2d(&tmC, st.buf, n, row0);
+              bulk_commit();
+            }
+            continue;
+          }
           if (first_split && p.bias) {
             const float4* bp = reinterpret_cast<const float4*>(bias_s + n);   // warp-uniform address: smem broadcast
 #pragma unroll
@@ -564,7 +606,8 @@ __global__ void __launch_bounds__(NT3, 1) gemm_tc3_kernel(const __grid_constant_
 constexpr int LN_WARPS = 8;
 constexpr int LN_NT = 64 + LN_WARPS * 32;                 // 320
 constexpr int LN_WBUF = 8192;                             // two 4 KB staging buffers per epilogue warp
-constexpr int LN_OFF_STG = NSTAGE * STAGE_BYTES;
+constexpr int LN_NSTAGE = 3;
+constexpr int LN_OFF_STG = LN_NSTAGE * STAGE_BYTES;
 constexpr int LN_OFF_VEC = LN_OFF_STG + LN_WARPS * LN_WBUF;   // float[3][256]: bias, gamma, beta
 constexpr int LN_OFF_XCH = LN_OFF_VEC + 3 * 256 * 4;          // float[2 halves][128 rows][2]
 constexpr int LN_OFF_BAR = LN_OFF_XCH + 2 * 128 * 2 * 4;
@@ -589,8 +632,8 @@ __global__ void __launch_bounds__(LN_NT, 1) gemm_ln3_kernel(const __grid_constan
   float* vecs = reinterpret_cast<float*>(smem + LN_OFF_VEC);
   float* xch = reinterpret_cast<float*>(smem + LN_OFF_XCH);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + LN_OFF_BAR);
-  uint64_t* empty_bar = full_bar + NSTAGE;
-  uint64_t* tfull_bar = empty_bar + NSTAGE;   // [2]
+  uint64_t* empty_bar = full_bar + LN_NSTAGE;
+  uint64_t* tfull_bar = empty_bar + LN_NSTAGE;   // [2]
   uint64_t* tempty_bar = tfull_bar + 2;       // [2]
   uint64_t* res_bar = tempty_bar + 2;         // [LN_WARPS][2]
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(res_bar + 2 * LN_WARPS);
@@ -602,7 +645,7 @@ __global__ void __launch_bounds__(LN_NT, 1) gemm_ln3_kernel(const __grid_constan
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmR);
-    for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < LN_NSTAGE; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], LN_WARPS); }
     for (int w = 0; w < 2 * LN_WARPS; ++w) mbar_init(&res_bar[w], 1);
     fence_barrier_init();
@@ -631,7 +674,7 @@ __global__ void __launch_bounds__(LN_NT, 1) gemm_ln3_kernel(const __grid_constan
           mbar_expect_tx(&full_bar[s], STAGE_BYTES);
           tma_load_2d(sa, &tmA, &full_bar[s], kb * BK, m0);
           tma_load_2d(sa + A_BYTES, &tmB, &full_bar[s], kb * BK, 0);
-          if (++s == NSTAGE) { s = 0; ph ^= 1; }
+          if (++s == LN_NSTAGE) { s = 0; ph ^= 1; }
         }
       }
     }
@@ -653,7 +696,7 @@ __global__ void __launch_bounds__(LN_NT, 1) gemm_ln3_kernel(const __grid_constan
           for (int k = 0; k < BK / 16; ++k)
             umma_bf16(d_tmem, make_smem_desc(sa + k * 32, 0, 1024), make_smem_desc(sb + k * 32, 0, 1024), idesc, (kb > 0 || k > 0) ? 1u : 0u);
           umma_commit(&empty_bar[s]);
-          if (++s == NSTAGE) { s = 0; ph ^= 1; }
+          if (++s == LN_NSTAGE) { s = 0; ph ^= 1; }
         }
         umma_commit(&tfull_bar[acc]);
       }
@@ -801,17 +844,23 @@ __global__ void __launch_bounds__(LN_NT, 1) gemm_ln3_kernel(const __grid_constan
   }
 }
 
-template <bool AK, bool BK_, int EPI>
-int launch3(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc_, const CUtensorMap& tp, const P3& p, int grid,
-            cudaStream_t st) {
+template <bool AK, bool BK_, int EPI, int NST>
+int launch3n(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc_, const CUtensorMap& tp, const P3& p, int grid,
+             cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    EEC_CUDA(cudaFuncSetAttribute(gemm_tc3_kernel<AK, BK_, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM3_BYTES));
+    EEC_CUDA(cudaFuncSetAttribute(gemm_tc3_kernel<AK, BK_, EPI, NST>, cudaFuncAttributeMaxDynamicSharedMemorySize, L3<NST>::BYTES));
     attr_set = true;
   }
-  launch_pdl(gemm_tc3_kernel<AK, BK_, EPI>, dim3(grid), dim3(NT3), SMEM3_BYTES, st, ta, tb, tc_, tp, p);
+  launch_pdl(gemm_tc3_kernel<AK, BK_, EPI, NST>, dim3(grid), dim3(NT3), L3<NST>::BYTES, st, ta, tb, tc_, tp, p);
   EEC_LAUNCH_CHECK();
   return 0;
+}
+template <bool AK, bool BK_, int EPI>
+int launch3(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc_, const CUtensorMap& tp, const P3& p, int grid,
+            cudaStream_t st, bool four_stages = false) {
+  if (EPI == EPI_GENERIC && four_stages) return launch3n<AK, BK_, EPI_GENERIC, 4>(ta, tb, tc_, tp, p, grid, st);
+  return launch3n<AK, BK_, EPI, 3>(ta, tb, tc_, tp, p, grid, st);
 }
 
 int g_sms3 = 0;
@@ -837,7 +886,13 @@ int gemm_tc3(const eec_gemm_desc* d, cudaStream_t st) {
   }
   const int n_out = (epi == EPI_GLU) ? d->N / 2 : d->N;
   const bool out_bf16 = d->out_dtype == EEC_BF16;
-  if (int r = get_tmap_box32(&tcm, d->C, out_bf16, (uint64_t)n_out, (uint64_t)d->M, (uint64_t)d->ldc)) return r;
+  const bool store_pre_ = d->preact && (d->act == EEC_ACT_SILU || epi == EPI_GLU);
+  // plain fp32-output GEMMs (weight gradients, the long-K dgrad) run the 4-stage ring with 16-column output boxes
+  static int nst_env = -1;
+  if (nst_env < 0) { const char* e = getenv("EEC_GEMM_STAGES"); nst_env = e ? atoi(e) : 0; }
+  const bool four = nst_env != 3 && epi == EPI_GENERIC && !out_bf16 && !d->bias && d->act == EEC_ACT_NONE && !store_pre_;
+  if (four) { if (int r = get_tmap_box(&tcm, d->C, false, (uint64_t)n_out, (uint64_t)d->M, (uint64_t)d->ldc, 16, 32, 2 /*SWIZZLE_64B*/)) return r; }
+  else if (int r = get_tmap_box32(&tcm, d->C, out_bf16, (uint64_t)n_out, (uint64_t)d->M, (uint64_t)d->ldc)) return r;
   const bool store_pre = d->preact && (d->act == EEC_ACT_SILU || epi == EPI_GLU);
   tpm = tcm;
   if (store_pre || d->act == EEC_ACT_DSILU) {
@@ -891,16 +946,16 @@ int gemm_tc3(const eec_gemm_desc* d, cudaStream_t st) {
       }
     } report{tl_buf, st, d->M, d->N, d->K};
     if (epi == EPI_GLU) return launch3<true, true, EPI_GLU>(ta, tb, tcm, tpm, p, grid, st);
-    if (d->a_kmajor && d->b_kmajor) return launch3<true, true, EPI_GENERIC>(ta, tb, tcm, tpm, p, grid, st);
-    if (d->a_kmajor && !d->b_kmajor) return launch3<true, false, EPI_GENERIC>(ta, tb, tcm, tpm, p, grid, st);
-    if (!d->a_kmajor && !d->b_kmajor) return launch3<false, false, EPI_GENERIC>(ta, tb, tcm, tpm, p, grid, st);
-    return launch3<false, true, EPI_GENERIC>(ta, tb, tcm, tpm, p, grid, st);
+    if (d->a_kmajor && d->b_kmajor) return launch3<true, true, EPI_GENERIC>(ta, tb, tcm, tpm, p, grid, st, four);
+    if (d->a_kmajor && !d->b_kmajor) return launch3<true, false, EPI_GENERIC>(ta, tb, tcm, tpm, p, grid, st, four);
+    if (!d->a_kmajor && !d->b_kmajor) return launch3<false, false, EPI_GENERIC>(ta, tb, tcm, tpm, p, grid, st, four);
+    return launch3<false, true, EPI_GENERIC>(ta, tb, tcm, tpm, p, grid, st, four);
   }
   if (epi == EPI_GLU) return launch3<true, true, EPI_GLU>(ta, tb, tcm, tpm, p, grid, st);
-  if (d->a_kmajor && d->b_kmajor) return launch3<true, true, EPI_GENERIC>(ta, tb, tcm, tpm, p, grid, st);
-  if (d->a_kmajor && !d->b_kmajor) return launch3<true, false, EPI_GENERIC>(ta, tb, tcm, tpm, p, grid, st);
-  if (!d->a_kmajor && !d->b_kmajor) return launch3<false, false, EPI_GENERIC>(ta, tb, tcm, tpm, p, grid, st);
-  return launch3<false, true, EPI_GENERIC>(ta, tb, tcm, tpm, p, grid, st);
+  if (d->a_kmajor && d->b_kmajor) return launch3<true, true, EPI_GENERIC>(ta, tb, tcm, tpm, p, grid, st, four);
+  if (d->a_kmajor && !d->b_kmajor) return launch3<true, false, EPI_GENERIC>(ta, tb, tcm, tpm, p, grid, st, four);
+  if (!d->a_kmajor && !d->b_kmajor) return launch3<false, false, EPI_GENERIC>(ta, tb, tcm, tpm, p, grid, st, four);
+  return launch3<false, true, EPI_GENERIC>(ta, tb, tcm, tpm, p, grid, st, four);
 }
 
 // LayerNorm-tail epilogue of eec_gemm (N == 256, K-major bf16 operands, fp32 C with ldc 256); validated by gemm_tc2

@@ -306,6 +306,8 @@ int get_tmap_2d(CUtensorMap* out, const void* base, uint64_t dim0, uint64_t dim1
 int get_tmap_store(CUtensorMap* out, const void* base, bool bf16, uint64_t cols, uint64_t rows, uint64_t ld_elems);
 // 32 x 32 element boxes (one epilogue warp's staging tile): fp32 -> 128B swizzle, bf16 -> 64B swizzle
 int get_tmap_box32(CUtensorMap* out, const void* base, bool bf16, uint64_t cols, uint64_t rows, uint64_t ld_elems);
+int get_tmap_box(CUtensorMap* out, const void* base, bool bf16, uint64_t cols, uint64_t rows, uint64_t ld_elems, uint32_t box_cols,
+                 uint32_t box_rows, int swizzle);
 int get_tmap_3d(CUtensorMap* out, const void* base, uint64_t dim0, uint64_t dim1, uint64_t dim2, uint64_t stride1_bytes,
                 uint64_t stride2_bytes, uint32_t box0, uint32_t box1, uint32_t box2);
 
