@@ -272,6 +272,20 @@ __global__ void scale_dev_kernel(const float* __restrict__ x, const float* __res
   if (i < n) y[i] = a * x[i];
 }
 
+// y[r, :] = s[r] * x[r, :] for `rows` contiguous slabs of `slab` floats (slab % 4 == 0): all exits' CTC gradient slabs scaled by
+// their upstream scalars in ONE launch, 128-bit accesses, grid-stride
+__global__ void __launch_bounds__(256) scale_rows_dev_kernel(const float4* __restrict__ x, const float* __restrict__ s, float4* __restrict__ y,
+                                                             long slab4, long total4) {
+  pdl_trigger();
+  pdl_wait();
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long)gridDim.x * blockDim.x) {
+    const float a = s[i / slab4];
+    float4 v = x[i];
+    v.x *= a; v.y *= a; v.z *= a; v.w *= a;
+    y[i] = v;
+  }
+}
+
 __global__ void encoder_lengths_kernel(const int64_t* __restrict__ lengths, int32_t* __restrict__ key_len, int B, int T,
                                        int div, int add) {
   pdl_trigger();
@@ -434,6 +448,16 @@ extern "C" int eec_axpy(const float* x, float a, float* y, int64_t n, eec_stream
 extern "C" int eec_scale_dev(const float* x, const float* s_dev, float* y, int64_t n, eec_stream_t stream) {
   if (n == 0) return 0;
   launch_pdl(scale_dev_kernel, dim3((int)cdiv64(n, 256)), dim3(256), 0, S(stream), x, s_dev, y, n);
+  EEC_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int eec_scale_rows_dev(const float* x, const float* s_dev, float* y, int rows, int64_t slab, eec_stream_t stream) {
+  if (rows == 0 || slab == 0) return 0;
+  EEC_CHECK_ARG(slab % 4 == 0, "scale_rows_dev: slab (%lld) must be a multiple of 4", (long long)slab);
+  const long total4 = (long)rows * slab / 4;
+  const int blocks = (int)min((long)148 * 16, cdiv64(total4, 256));
+  launch_pdl(scale_rows_dev_kernel, dim3(blocks), dim3(256), 0, S(stream), (const float4*)x, s_dev, (float4*)y, (long)(slab / 4), total4);
   EEC_LAUNCH_CHECK();
   return 0;
 }

@@ -35,10 +35,8 @@ class _CtcFn(torch.autograd.Function):
         g = ctx.grad
         if g is None:
             raise EecError("ctc: gradient was not computed in forward")
-        E = g.shape[0]
         gl = gloss.contiguous().float()
-        for e in range(E):  # scale each exit's slab by its upstream scalar, on device
-            ops.scale_dev(g[e], gl[e:e + 1], g[e])
+        ops.scale_rows_dev(g, gl, g)   # every exit's slab times its upstream scalar, on device, one launch
         ctx.grad = None
         return g, None, None, None
 

@@ -69,6 +69,7 @@ _SIGS = {
     "eec_colsum": [vp, i32, i32, vp, f32, i32, i32, vp],
     "eec_axpy": [vp, f32, vp, i64, vp],
     "eec_scale_dev": [vp, vp, vp, i64, vp],
+    "eec_scale_rows_dev": [vp, vp, vp, i32, i64, vp],
     "eec_exit_select": [vp, vp, vp, vp, vp, i32, i32, f32, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp],
     "eec_gather_rows": [vp, vp, vp, vp, i32, i64, vp],
     "eec_stride2_gather": [vp, vp, i32, i32, i32, vp],

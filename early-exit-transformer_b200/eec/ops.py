@@ -173,6 +173,11 @@ def axpy(x, a, y):
     call("eec_axpy", ptr(x), a, ptr(y), x.numel(), stream())
 
 
+def scale_rows_dev(x, s_dev, y):
+    """y[r] = s_dev[r] * x[r] for the leading dimension r (contiguous tensors)."""
+    call("eec_scale_rows_dev", ptr(x), ptr(s_dev), ptr(y), x.shape[0], x.numel() // x.shape[0], stream())
+
+
 def scale_dev(x, s_dev, y):
     call("eec_scale_dev", ptr(x), ptr(s_dev), ptr(y), x.numel(), stream())
 

@@ -199,6 +199,9 @@ int eec_colsum(const void* in, int dtype, int ld, float* out, float scale, int r
                eec_stream_t stream);
 /* y = (*s_dev) * x  (device scalar; used to apply an upstream loss gradient without a host sync) */
 int eec_scale_dev(const float* x, const float* s_dev, float* y, int64_t n, eec_stream_t stream);
+/* y[r, 0:slab] = s_dev[r] * x[r, 0:slab], r < rows (x, y contiguous; slab % 4 == 0): every exit's CTC gradient scaled by its
+ * upstream scalar (train.py:63 sums the per-exit losses) in one launch */
+int eec_scale_rows_dev(const float* x, const float* s_dev, float* y, int rows, int64_t slab, eec_stream_t stream);
 
 /* ---- optimiser step over flat buffers: torch.nn.utils.clip_grad_norm_ (train.py:69) + NoamOpt.step
  *      (util/noam_opt.py:26-40) + torch.optim.AdamW.step (train.py:261-262) in three launches, no host sync.
