@@ -88,24 +88,66 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def synthetic_state_dict(layers_per_exit):
+    """Random-init weights of the named architecture: the host-side mirror of the reference class is built on
+    the CPU under torch.manual_seed(0) (same default init as the reference's ctor), every >= 2-D `.weight` of a leaf module gets
+    Xavier-uniform like util/model_utils.py:10-12 (model.apply(initialize_weights), train.py:229-230), and 1-D parameters /
+    BatchNorm buffers are randomised so that no scale or shift is a no-op.  No CUDA work, nothing from oracle/."""
+    import eec
+    torch.manual_seed(0)
+    m = eec.Early_conformer(src_pad_idx=0, n_enc_exits=N_EXITS, enc_voc_size=256, dec_voc_size=256, d_model=256, n_head=8,
+                            max_len=2000, d_feed_forward=2048, n_enc_layers=layers_per_exit, features_length=N_MELS,
+                            drop_prob=0.0, depthwise_kernel_size=31, device=torch.device("cpu"))
+    g = torch.Generator().manual_seed(0)
+    with torch.no_grad():
+        for mod in m.modules():
+            w = getattr(mod, "weight", None)
+            if isinstance(w, torch.nn.Parameter) and w.dim() > 1 and not list(mod.children()):
+                torch.nn.init.xavier_uniform_(w, generator=g)
+        for n, prm in m.named_parameters():
+            if prm.dim() == 1:
+                base = 1.0 if (n.endswith("norm.weight") or ".sequential.0.weight" in n and "ffn" in n or n.endswith("sequential.3.weight")) else 0.0
+                prm.copy_(base + 0.05 * (2 * torch.rand(prm.shape, generator=g) - 1))
+        for n, buf in m.named_buffers():
+            if n.endswith("running_mean"):
+                buf.copy_(0.1 * (2 * torch.rand(buf.shape, generator=g) - 1))
+            elif n.endswith("running_var"):
+                buf.copy_(1.0 + 0.2 * torch.rand(buf.shape, generator=g))
+    return {k: v.detach().clone() for k, v in m.state_dict().items()}
+
+
 def build_model(layers_per_exit, precision, device):
     import eec
-    from oracle import conformer_oracle as O  # only for the deterministic synthetic parameters / inputs
     m = eec.Early_conformer(src_pad_idx=0, n_enc_exits=N_EXITS, enc_voc_size=256, dec_voc_size=256, d_model=256, n_head=8,
                             max_len=2000, d_feed_forward=2048, n_enc_layers=layers_per_exit, features_length=N_MELS,
                             drop_prob=0.0, depthwise_kernel_size=31, device=device)
-    sd = O.make_params(0, n_exits=N_EXITS, n_layers=layers_per_exit)
-    m.load_state_dict(sd, strict=True)
+    m.load_state_dict(synthetic_state_dict(layers_per_exit), strict=True)
     m = m.to(device)
     m.precision = precision
     return m
 
 
+def synthetic_batch(n, seed):
+    """randn fbank (n, 80, 1501), lengths ~ U[750, 1501] with lengths[0] = 1501, padding zeroed
+    (util/data_loader.py:21-26); targets [<s>=1, tokens in 3..125, </s>=2, pad 126...] with 20..80 tokens (:207-214)."""
+    g = torch.Generator().manual_seed(seed)
+    src = torch.randn(n, N_MELS, T_IN, generator=g)
+    lengths = torch.randint(T_IN // 2, T_IN + 1, (n,), generator=g)
+    lengths[0] = T_IN
+    for b in range(n):
+        src[b, :, int(lengths[b]):] = 0.0
+    tl = torch.randint(20, 81, (n,), generator=g)
+    tg = torch.full((n, int(tl.max()) + 2), 126, dtype=torch.int64)
+    for b in range(n):
+        k = int(tl[b])
+        tg[b, 0] = 1
+        tg[b, 1:1 + k] = torch.randint(3, 126, (k,), generator=g)
+        tg[b, 1 + k] = 2
+    return src, lengths.to(torch.int64), tg, (tl + 2).to(torch.int64)
+
+
 def synthetic(rank):
-    from oracle import conformer_oracle as O
-    src, lengths = O.synthetic_batch(B, T_IN, seed=1234 + rank)
-    targets, tl = O.synthetic_targets(B, seed=4321 + rank)
-    return src, lengths, targets, tl
+    return synthetic_batch(B, 1234 + rank)
 
 
 def run_ours(args):
@@ -218,6 +260,30 @@ def run_ours(args):
         rtfx = rtfx_per_exit(model, src_dev, lengths, audio_s, use_graph=not args.no_graph)
         model.train()
 
+    # the same step at the reference's DEFAULT --drop_prob 0.1 (util/conf.py:283-291): fused counter-based dropout at all
+    # seven sites per layer + after the positional encoding, masks regenerated in backward (nothing stored)
+    drop_leg = None
+    if args.drop_prob > 0 and not args.profile and graphed is not None:
+        model.train()
+        model.dropout = args.drop_prob
+        g2 = eec.GraphedTrainStep(model, B, T_IN, targets.shape[1], optimizer=opt if world == 1 else None)
+        g2.load_inputs(src_dev, lengths, tg_dev, tl_dev)
+
+        def dstep():
+            loss = g2.replay()
+            if world > 1:
+                dist.all_reduce(model._flat_grad, op=dist.ReduceOp.AVG)
+                if opt is not None:
+                    opt.step()
+            return loss
+        for _ in range(3):
+            dstep()
+        ms_d = timed(dstep, args.steps)
+        drop_leg = {"drop_prob": args.drop_prob, "ms_per_step": round(ms_d / args.steps, 3),
+                    "value": round(world * B / (ms_d / args.steps / 1e3), 2), "unit": "utt/s", "gpu_launches": g2.launches_per_step}
+        model.dropout = 0.0
+        del g2
+
     roof = cpu = None
     if rank == 0:
         roof = None if args.profile else roofline_dominant(dev, pk)
@@ -248,6 +314,8 @@ def run_ours(args):
         }
         if rtfx is not None:
             line["rtfx_per_exit"] = rtfx
+        if drop_leg is not None:
+            line["train_with_dropout"] = drop_leg
         print(json.dumps(line), file=_JSON_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -333,12 +401,10 @@ def cpu_step(sd, src, lengths, targets, tl):
 
 def cpu_baseline(layers, sample_b=8, steps=1):
     """The reference's CPU path (oracle port: same arithmetic, torch CPU ops, all host threads) on a bounded sample."""
-    from oracle import conformer_oracle as O
     cores = len(os.sched_getaffinity(0))
     torch.set_num_threads(cores)
-    sd = O.make_params(0, n_exits=N_EXITS, n_layers=layers)
-    src, lengths = O.synthetic_batch(sample_b, T_IN, seed=1234)
-    targets, tl = O.synthetic_targets(sample_b, seed=4321)
+    sd = synthetic_state_dict(layers)
+    src, lengths, targets, tl = synthetic_batch(sample_b, 1234)
     t0 = time.perf_counter()
     for _ in range(steps):
         cpu_step(sd, src, lengths, targets, tl)
@@ -352,14 +418,12 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import conformer_oracle as O
     cores = len(os.sched_getaffinity(0))
     torch.set_num_threads(cores)
     layers = args.layers_per_exit
     sb = args.cpu_sample
-    sd = O.make_params(0, n_exits=N_EXITS, n_layers=layers)
-    src, lengths = O.synthetic_batch(sb, T_IN, seed=1234)
-    targets, tl = O.synthetic_targets(sb, seed=4321)
+    sd = synthetic_state_dict(layers)
+    src, lengths, targets, tl = synthetic_batch(sb, 1234)
     for _ in range(min(args.warmup, 1)):
         cpu_step(sd, src, lengths, targets, tl)
     t0 = time.perf_counter()
@@ -398,6 +462,8 @@ def main():
     ap.add_argument("--no-opt", action="store_true", help="time forward + loss + backward only (no clip / Noam / AdamW update)")
     ap.add_argument("--no-graph", action="store_true", help="issue the ~600 kernels of a step eagerly instead of replaying the CUDA graph")
     ap.add_argument("--skip-rtfx", action="store_true")
+    ap.add_argument("--drop-prob", type=float, default=0.1, help="extra leg: the same training step with dropout at this probability "
+                    "(the reference's default); the headline step runs at 0 like the parity tests (SURVEY 8d). 0 skips the leg")
     ap.add_argument("--profile", action="store_true", help="bracket the timed region with cudaProfilerStart/Stop (for ncu "
                     "--profile-from-start off) and skip the e2e / rtfx / roofline / cpu legs")
     args = ap.parse_args()

@@ -71,11 +71,12 @@ __global__ void dq_convert_kernel(const float* __restrict__ dq32, __nv_bfloat16*
   st8<__nv_bfloat16>(dqkv + r * 768 + c, v);
 }
 
+template <bool DROP>
 __global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv,
                                                                  const __grid_constant__ CUtensorMap tm_do,
                                                                  const int32_t* __restrict__ key_len, const float* __restrict__ lse,
                                                                  const float* __restrict__ dvec, float* __restrict__ dq32,
-                                                                 __nv_bfloat16* __restrict__ dqkv, int T, int H) {
+                                                                 __nv_bfloat16* __restrict__ dqkv, int T, int H, const DropArgs drop) {
   pdl_trigger();
   pdl_wait();
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -187,10 +188,15 @@ __global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_tc_kernel(const __grid
     const float LOG2E = 1.4426950408889634f;
     const float sc2 = rsqrtf((float)DHD) * LOG2E;
     float s[32], dp[32];
+    // dropout on the probabilities (DROP): with M = mask * scale regenerated from the forward's counters,
+    //   dV uses P.M (the tile written to sP), dS = P (dP.M - D) and D = dO . O is unchanged (O = (P.M) V).
+    DropKey dkey{};
+    if (DROP) dkey = drop_key(drop);
     if (active) {
       for (int i = 0; i < nq; ++i) {
         const int t = i * BT + r;
         const bool rvalid = t < T;
+        const uint64_t dgrp0 = ((uint64_t)(b * H + h) * T + t) * (uint64_t)((T + 7) >> 3);
         const float l2 = rvalid ? lse[((long)b * H + h) * T + t] * LOG2E : 0.f;
         const float di = rvalid ? dvec[((long)b * H + h) * T + t] : 0.f;
 #pragma unroll 1
@@ -202,7 +208,22 @@ __global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_tc_kernel(const __grid
           tmem_ld32x2(trow + C_S + half * 32, trow + C_DP + half * 32, s, dp);
           tc_fence_before();
           mbar_arrive(sdp_free);                  // S / dP are in registers: the MMA warp may start the next half
-          if (rvalid && k0 + c0 + 32 <= klen) {   // common case: no masked key in this slab
+          if (DROP) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              float f[8];
+              drop_factors8(dkey, drop, dgrp0 + (uint64_t)((k0 + c0) >> 3) + g, f);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const bool ok = rvalid && (k0 + c0 + g * 8 + e < klen);
+                float p;
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p) : "f"(fmaf(s[g * 8 + e], sc2, -l2)));
+                p = ok ? p : 0.f;
+                s[g * 8 + e] = p * f[e];
+                dp[g * 8 + e] = ok ? p * (dp[g * 8 + e] * f[e] - di) : 0.f;
+              }
+            }
+          } else if (rvalid && k0 + c0 + 32 <= klen) {   // common case: no masked key in this slab
 #pragma unroll
             for (int e = 0; e < 32; ++e) {
               float p;
@@ -291,7 +312,7 @@ __global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_tc_kernel(const __grid
 }  // namespace
 
 int attn_bwd_tc(const void* qkv, const void* ctx, const void* dctx, const float* lse, const int32_t* key_len, void* dqkv,
-                float* dvec, float* dq32, int B, int T, int H, int dh, cudaStream_t st) {
+                float* dvec, float* dq32, int B, int T, int H, int dh, const DropArgs& drop, cudaStream_t st) {
   EEC_CHECK_ARG(dh == DHD && H * dh == 256, "attn_bwd_tc: needs 8 heads of 32");
   EEC_CHECK_ARG(dq32 != nullptr, "attn_bwd_tc: dq32 workspace is NULL");
   const long rows = (long)B * T;
@@ -303,11 +324,13 @@ int attn_bwd_tc(const void* qkv, const void* ctx, const void* dctx, const float*
   if (int r = get_tmap_2d(&td, dctx, 256, (uint64_t)rows, 256 * 2, DHD, 128, 2)) return r;
   static bool attr_set = false;
   if (!attr_set) {
-    EEC_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BW_SMEM));
+    EEC_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BW_SMEM));
+    EEC_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BW_SMEM));
     attr_set = true;
   }
   dim3 grid(cdiv(T, BT), H, B);
-  launch_pdl(attn_bwd_tc_kernel, dim3(grid), dim3(BW_THREADS), BW_SMEM, st, tq, td, key_len, lse, dvec, dq32, (__nv_bfloat16*)dqkv, T, H);
+  if (drop.state) launch_pdl(attn_bwd_tc_kernel<true>, dim3(grid), dim3(BW_THREADS), BW_SMEM, st, tq, td, key_len, lse, dvec, dq32, (__nv_bfloat16*)dqkv, T, H, drop);
+  else launch_pdl(attn_bwd_tc_kernel<false>, dim3(grid), dim3(BW_THREADS), BW_SMEM, st, tq, td, key_len, lse, dvec, dq32, (__nv_bfloat16*)dqkv, T, H, drop);
   EEC_LAUNCH_CHECK();
   launch_pdl(dq_convert_kernel, dim3((int)cdiv64(rows * 32, 256)), dim3(256), 0, st, dq32, (__nv_bfloat16*)dqkv, rows, rsqrtf((float)dh));
   EEC_LAUNCH_CHECK();

@@ -13,9 +13,13 @@ constexpr int DH = 32;
 // grid (ceil(T/QB), H, B), 128 threads: warp w owns rows w*8 .. w*8+7 of the block
 template <typename T, bool ACC>
 __global__ void __launch_bounds__(128) attn_fwd_simt_kernel(const T* __restrict__ qkv, const int32_t* __restrict__ key_len,
-                                                           T* __restrict__ ctx, float* __restrict__ lse, int Tn, int H) {
+                                                           T* __restrict__ ctx, float* __restrict__ lse, int Tn, int H,
+                                                           const DropArgs drop) {
   __shared__ float Ks[KC][DH + 1];
   __shared__ float Vs[KC][DH];
+  DropKey dkey{};
+  if (drop.state) dkey = drop_key(drop);
+  const uint64_t tk8 = (uint64_t)((Tn + 7) >> 3) * 8;   // dropout element index of (b, h, t, key) = ((b*H + h)*T + t) * tk8 + key
   __shared__ float Qs[QB][DH];
   __shared__ float Ps[4][KC];
   const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * QB;
@@ -61,8 +65,9 @@ __global__ void __launch_bounds__(128) attn_fwd_simt_kernel(const T* __restrict_
 #pragma unroll
       for (int jj = 0; jj < 4; ++jj) {
         float p = (s[jj] == -INFINITY) ? 0.f : (ACC ? expf(s[jj] - mn) : __expf(s[jj] - mn));
+        psum += p;   // (the softmax denominator is taken before dropout)
+        if (drop.state) p *= drop_factor1(dkey, drop, ((uint64_t)(b * H + h) * Tn + (q0 + qr)) * tk8 + (k0 + lane + 32 * jj));
         Ps[w][lane + 32 * jj] = p;
-        psum += p;
       }
       psum = warp_sum(psum);
       const float corr = (m[qi] == -INFINITY) ? 0.f : (ACC ? expf(m[qi] - mn) : __expf(m[qi] - mn));
@@ -91,7 +96,10 @@ template <typename T>
 __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const T* __restrict__ qkv, const T* __restrict__ ctx,
                                                          const T* __restrict__ dctx, const float* __restrict__ lse,
                                                          const int32_t* __restrict__ key_len, T* __restrict__ dqkv,
-                                                         float* __restrict__ dvec, int Tn, int H) {
+                                                         float* __restrict__ dvec, int Tn, int H, const DropArgs drop) {
+  DropKey dkey{};
+  if (drop.state) dkey = drop_key(drop);
+  const uint64_t tk8 = (uint64_t)((Tn + 7) >> 3) * 8;
   __shared__ float Ks[KC][DH + 1];
   __shared__ float Vs[KC][DH + 1];
   __shared__ float Qs[QB][DH];
@@ -142,6 +150,7 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const T* __restrict__ 
           dp = fmaf(dOs[qr][d], Vs[key][d], dp);
         }
         float p = (k0 + key < klen && Li[qi] != -INFINITY) ? expf(a - Li[qi]) : 0.f;
+        if (drop.state) dp *= drop_factor1(dkey, drop, ((uint64_t)(b * H + h) * Tn + (q0 + qr)) * tk8 + (k0 + key));
         Ps[w][key] = p * (dp - Di[qi]);
       }
       __syncwarp();
@@ -164,7 +173,10 @@ template <typename T>
 __global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(const T* __restrict__ qkv, const T* __restrict__ dctx,
                                                           const float* __restrict__ lse, const float* __restrict__ dvec,
                                                           const int32_t* __restrict__ key_len, T* __restrict__ dqkv,
-                                                          int Tn, int H) {
+                                                          int Tn, int H, const DropArgs drop) {
+  DropKey dkey{};
+  if (drop.state) dkey = drop_key(drop);
+  const uint64_t tk8 = (uint64_t)((Tn + 7) >> 3) * 8;
   __shared__ float Qs[KC][DH + 1];
   __shared__ float dOs[KC][DH + 1];
   __shared__ float Ksm[QB][DH];
@@ -217,8 +229,10 @@ __global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(const T* __restrict__
             dp = fmaf(dOs[q][d], Vsm[kr][d], dp);
           }
           float p = (kvalid && Ls[q] != -INFINITY) ? expf(a - Ls[q]) : 0.f;
-          Ps[w][q] = p;
-          dSs[w][q] = p * (dp - Ds[q]);
+          float f = 1.f;
+          if (drop.state) f = drop_factor1(dkey, drop, ((uint64_t)(b * H + h) * Tn + (i0 + q)) * tk8 + (j0 + kr));
+          Ps[w][q] = p * f;                      // dV = (P.M)^T dO
+          dSs[w][q] = p * (dp * f - Ds[q]);      // dS = P (dP.M - D)
         }
         __syncwarp();
         float av = 0.f, ak = 0.f;
@@ -260,35 +274,37 @@ static bool force_simt() {
 }
 
 extern "C" int eec_attn_fwd(const void* qkv, int dtype, const int32_t* key_len, void* ctx, float* lse, int B, int T,
-                            int H, int dh, eec_stream_t stream) {
+                            int H, int dh, const uint64_t* drop_state, float drop_p, uint32_t drop_site, eec_stream_t stream) {
   EEC_CHECK_ARG(dh == 32, "attn_fwd: head dim must be 32 (got %d)", dh);
   if (B == 0 || T == 0) return 0;
-  if (dtype == EEC_BF16 && !force_simt() && attn_tc_ready()) return attn_fwd_tc(qkv, key_len, ctx, lse, B, T, H, dh, S(stream));
+  const DropArgs drop = make_drop(drop_state, drop_p, drop_site);
+  if (dtype == EEC_BF16 && !force_simt() && attn_tc_ready()) return attn_fwd_tc(qkv, key_len, ctx, lse, B, T, H, dh, drop, S(stream));
   dim3 grid(cdiv(T, QB), H, B);
   if (dtype == EEC_F32)
-    attn_fwd_simt_kernel<float, true><<<grid, 128, 0, S(stream)>>>((const float*)qkv, key_len, (float*)ctx, lse, T, H);
+    attn_fwd_simt_kernel<float, true><<<grid, 128, 0, S(stream)>>>((const float*)qkv, key_len, (float*)ctx, lse, T, H, drop);
   else
-    attn_fwd_simt_kernel<__nv_bfloat16, false><<<grid, 128, 0, S(stream)>>>((const __nv_bfloat16*)qkv, key_len, (__nv_bfloat16*)ctx, lse, T, H);
+    attn_fwd_simt_kernel<__nv_bfloat16, false><<<grid, 128, 0, S(stream)>>>((const __nv_bfloat16*)qkv, key_len, (__nv_bfloat16*)ctx, lse, T, H, drop);
   EEC_LAUNCH_CHECK();
   return 0;
 }
 
 extern "C" int eec_attn_bwd(const void* qkv, const void* ctx, const void* dctx, int dtype, const float* lse,
                             const int32_t* key_len, void* dqkv, float* dvec, float* dq32, int B, int T, int H, int dh,
-                            eec_stream_t stream) {
+                            const uint64_t* drop_state, float drop_p, uint32_t drop_site, eec_stream_t stream) {
   EEC_CHECK_ARG(dh == 32, "attn_bwd: head dim must be 32 (got %d)", dh);
   if (B == 0 || T == 0) return 0;
+  const DropArgs drop = make_drop(drop_state, drop_p, drop_site);
   if (dtype == EEC_BF16 && !force_simt() && attn_tc_ready())
-    return attn_bwd_tc(qkv, ctx, dctx, lse, key_len, dqkv, dvec, dq32, B, T, H, dh, S(stream));
+    return attn_bwd_tc(qkv, ctx, dctx, lse, key_len, dqkv, dvec, dq32, B, T, H, dh, drop, S(stream));
   dim3 grid(cdiv(T, QB), H, B);
   if (dtype == EEC_F32) {
-    attn_bwd_dq_kernel<float><<<grid, 128, 0, S(stream)>>>((const float*)qkv, (const float*)ctx, (const float*)dctx, lse, key_len, (float*)dqkv, dvec, T, H);
+    attn_bwd_dq_kernel<float><<<grid, 128, 0, S(stream)>>>((const float*)qkv, (const float*)ctx, (const float*)dctx, lse, key_len, (float*)dqkv, dvec, T, H, drop);
     EEC_LAUNCH_CHECK();
-    attn_bwd_dkv_kernel<float><<<grid, 128, 0, S(stream)>>>((const float*)qkv, (const float*)dctx, lse, dvec, key_len, (float*)dqkv, T, H);
+    attn_bwd_dkv_kernel<float><<<grid, 128, 0, S(stream)>>>((const float*)qkv, (const float*)dctx, lse, dvec, key_len, (float*)dqkv, T, H, drop);
   } else {
-    attn_bwd_dq_kernel<__nv_bfloat16><<<grid, 128, 0, S(stream)>>>((const __nv_bfloat16*)qkv, (const __nv_bfloat16*)ctx, (const __nv_bfloat16*)dctx, lse, key_len, (__nv_bfloat16*)dqkv, dvec, T, H);
+    attn_bwd_dq_kernel<__nv_bfloat16><<<grid, 128, 0, S(stream)>>>((const __nv_bfloat16*)qkv, (const __nv_bfloat16*)ctx, (const __nv_bfloat16*)dctx, lse, key_len, (__nv_bfloat16*)dqkv, dvec, T, H, drop);
     EEC_LAUNCH_CHECK();
-    attn_bwd_dkv_kernel<__nv_bfloat16><<<grid, 128, 0, S(stream)>>>((const __nv_bfloat16*)qkv, (const __nv_bfloat16*)dctx, lse, dvec, key_len, (__nv_bfloat16*)dqkv, T, H);
+    attn_bwd_dkv_kernel<__nv_bfloat16><<<grid, 128, 0, S(stream)>>>((const __nv_bfloat16*)qkv, (const __nv_bfloat16*)dctx, lse, dvec, key_len, (__nv_bfloat16*)dqkv, T, H, drop);
   }
   EEC_LAUNCH_CHECK();
   return 0;

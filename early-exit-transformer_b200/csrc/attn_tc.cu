@@ -35,10 +35,11 @@ __device__ __forceinline__ float ex2_fast(float x) {
   return y;
 }
 
+template <bool DROP>
 __global__ void __launch_bounds__(AT_THREADS, 2) attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv,
                                                                  const int32_t* __restrict__ key_len,
                                                                  __nv_bfloat16* __restrict__ ctx, float* __restrict__ lse,
-                                                                 int T, int H) {
+                                                                 int T, int H, const DropArgs drop) {
   pdl_trigger();
   pdl_wait();
   extern __shared__ uint8_t smem_raw[];
@@ -130,6 +131,10 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_fwd_tc_kernel(const __grid
 #pragma unroll
     for (int i = 0; i < DHEAD; ++i) o[i] = 0.f;
     float v[32];
+    // dropout on the probabilities (DROP): the row sum keeps the undropped values, the P tile fed to the P V product is masked
+    DropKey dkey{};
+    if (DROP) dkey = drop_key(drop);
+    const uint64_t dgrp0 = ((uint64_t)(b * H + h) * T + (q0 + r)) * (uint64_t)((T + 7) >> 3);   // group index of (b, h, t, key 0)
     for (int j = 0; j < nblk; ++j) {
       const int nvalid = min(KB, klen - j * KB);   // only the last key block can be partial
       mbar_wait(s_full, j & 1);
@@ -162,6 +167,15 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_fwd_tc_kernel(const __grid
           } else {
 #pragma unroll
             for (int i = 0; i < 32; ++i) { v[i] = (c0 + i < nvalid) ? ex2_fast(fmaf(v[i], sc, -mx)) : 0.f; psum += v[i]; }
+          }
+          if (DROP) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              float f[8];
+              drop_factors8(dkey, drop, dgrp0 + (uint64_t)((j * KB + c0) >> 3) + g, f);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[g * 8 + e] *= f[e];
+            }
           }
         } else {
 #pragma unroll
@@ -215,18 +229,21 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_fwd_tc_kernel(const __grid
 
 }  // namespace
 
-int attn_fwd_tc(const void* qkv, const int32_t* key_len, void* ctx, float* lse, int B, int T, int H, int dh, cudaStream_t st) {
+int attn_fwd_tc(const void* qkv, const int32_t* key_len, void* ctx, float* lse, int B, int T, int H, int dh, const DropArgs& drop,
+                cudaStream_t st) {
   EEC_CHECK_ARG(dh == DHEAD, "attn_fwd_tc: head dim must be 32");
   CUtensorMap tm;
   const int D3 = 3 * H * dh;
   if (int r = get_tmap_2d(&tm, qkv, (uint64_t)D3, (uint64_t)B * T, (uint64_t)D3 * 2, DHEAD, 128, /*SWIZZLE_64B*/ 2)) return r;
   static bool attr_set = false;
   if (!attr_set) {
-    EEC_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
+    EEC_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
+    EEC_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
     attr_set = true;
   }
   dim3 grid(cdiv(T, QT), H, B);
-  launch_pdl(attn_fwd_tc_kernel, dim3(grid), dim3(AT_THREADS), AT_SMEM, st, tm, key_len, (__nv_bfloat16*)ctx, lse, T, H);
+  if (drop.state) launch_pdl(attn_fwd_tc_kernel<true>, dim3(grid), dim3(AT_THREADS), AT_SMEM, st, tm, key_len, (__nv_bfloat16*)ctx, lse, T, H, drop);
+  else launch_pdl(attn_fwd_tc_kernel<false>, dim3(grid), dim3(AT_THREADS), AT_SMEM, st, tm, key_len, (__nv_bfloat16*)ctx, lse, T, H, drop);
   EEC_LAUNCH_CHECK();
   return 0;
 }

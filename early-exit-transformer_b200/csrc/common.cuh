@@ -123,6 +123,62 @@ template <> __device__ __forceinline__ void st8<__nv_bfloat16>(__nv_bfloat16* p,
   *reinterpret_cast<uint4*>(p) = u;
 }
 
+// ---- dropout: counter-based keep masks (Philox4x32-10; include/eec.h "dropout") -----------------------------------
+// One Philox call yields 128 random bits = the 16-bit draws of 8 consecutive elements (a "group"); every kernel that touches
+// a dropout site (forward epilogue, backward re-generation, the standalone eec_dropout used by the tests) derives the same
+// bits from (seed, offset, site, element index / 8) and nothing else, so no mask is ever stored.
+struct DropArgs {          // built on the host (make_drop), passed to kernels by value
+  const uint64_t* state;   // device {seed, offset}; NULL = dropout off
+  uint32_t site;
+  uint32_t thr;            // element dropped iff its 16-bit draw < thr   (thr = round(p * 65536))
+  float scale;             // 65536 / (65536 - thr)
+};
+static inline DropArgs make_drop(const uint64_t* state, float p, uint32_t site) {
+  DropArgs a{};
+  if (!state || !(p > 0.f)) return a;
+  double t = (double)p * 65536.0 + 0.5;
+  uint32_t thr = t >= 65535.0 ? 65535u : (uint32_t)t;
+  a.state = state; a.site = site; a.thr = thr; a.scale = (float)(65536.0 / (65536.0 - (double)thr));
+  return a;
+}
+struct DropKey { uint32_t k0, k1, c2, c3; };
+__device__ __forceinline__ DropKey drop_key(const DropArgs& a) {
+  const uint64_t seed = a.state[0], off = a.state[1];
+  DropKey k;
+  k.k0 = (uint32_t)seed; k.k1 = (uint32_t)(seed >> 32) ^ (uint32_t)(off >> 32);
+  k.c2 = a.site; k.c3 = (uint32_t)off;
+  return k;
+}
+__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+    c1 = (uint32_t)p1; c3 = (uint32_t)p0; c0 = n0; c2 = n2;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  return make_uint4(c0, c1, c2, c3);
+}
+// f[i] = scale (kept) or 0 (dropped) for elements 8*group .. 8*group+7
+__device__ __forceinline__ void drop_factors8(const DropKey& k, const DropArgs& a, uint64_t group, float (&f)[8]) {
+  const uint4 r = philox4x32_10((uint32_t)group, (uint32_t)(group >> 32), k.c2, k.c3, k.k0, k.k1);
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    f[2 * i] = ((w[i] & 0xffffu) >= a.thr) ? a.scale : 0.f;
+    f[2 * i + 1] = ((w[i] >> 16) >= a.thr) ? a.scale : 0.f;
+  }
+}
+// single element (the CUDA-core parity kernels touch one element per thread)
+__device__ __forceinline__ float drop_factor1(const DropKey& k, const DropArgs& a, uint64_t elem) {
+  const uint64_t group = elem >> 3;
+  const uint4 r = philox4x32_10((uint32_t)group, (uint32_t)(group >> 32), k.c2, k.c3, k.k0, k.k1);
+  const uint32_t i = (uint32_t)elem & 7u;
+  const uint32_t w = (i >> 1) == 0 ? r.x : (i >> 1) == 1 ? r.y : (i >> 1) == 2 ? r.z : r.w;
+  const uint32_t u = (i & 1u) ? (w >> 16) : (w & 0xffffu);
+  return (u >= a.thr) ? a.scale : 0.f;
+}
+
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 static inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
@@ -133,8 +189,8 @@ int gemm_tc2(const eec_gemm_desc* d, cudaStream_t st, int32_t* argmax, float* en
 int gemm_tc3(const eec_gemm_desc* d, cudaStream_t st);   // v3 epilogue (GENERIC / GLU modes), called by gemm_tc2
 int gemm_ln3(const eec_gemm_desc* d, cudaStream_t st);   // v3 LayerNorm-tail epilogue (N == 256), called by gemm_tc2
 int attn_bwd_tc(const void* qkv, const void* ctx, const void* dctx, const float* lse, const int32_t* key_len, void* dqkv,
-                float* dvec, float* dq32, int B, int T, int H, int dh, cudaStream_t st);
+                float* dvec, float* dq32, int B, int T, int H, int dh, const DropArgs& drop, cudaStream_t st);
 int attn_fwd_tc(const void* qkv, const int32_t* key_len, void* ctx, float* lse, int B, int T, int H, int dh,
-                cudaStream_t st);
+                const DropArgs& drop, cudaStream_t st);
 
 }  // namespace eec

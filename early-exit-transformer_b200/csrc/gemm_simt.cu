@@ -20,6 +20,7 @@ struct SimtParams {
   void* C; int ldc;
   int accumulate;
   int k_per_split;
+  DropArgs drop;   // dropout right after the activation (element index m*N + n); state NULL = off
 };
 
 template <typename TIn, typename TOut, typename TPre, bool ACC>
@@ -80,11 +81,15 @@ __global__ void __launch_bounds__(NT) gemm_simt_kernel(SimtParams p) {
   TOut* __restrict__ C = reinterpret_cast<TOut*>(p.C);
   TPre* __restrict__ P = reinterpret_cast<TPre*>(p.preact);
   const bool first_split = (blockIdx.z == 0);
+  DropKey dkey{};
+  if (p.drop.state) dkey = drop_key(p.drop);
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     int m = m0 + ty * 8 + i;
     if (m >= p.M) continue;
     int rr = p.res_row_mod ? (m % p.res_row_mod) : m;
+    float df[8];
+    if (p.drop.state) drop_factors8(dkey, p.drop, ((uint64_t)m * p.N + n0 + tx * 8) >> 3, df);   // (N % 8 == 0 checked on the host)
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       int n = n0 + tx * 8 + j;
@@ -99,6 +104,7 @@ __global__ void __launch_bounds__(NT) gemm_simt_kernel(SimtParams p) {
         float s = ACC ? sigmoid_acc(h) : sigmoidf_(h);
         v *= s * (1.0f + h * (1.0f - s));
       }
+      if (p.drop.state) v *= df[j];
       v *= p.alpha;
       if (p.residual && first_split) v += p.residual[(long)rr * p.ldr + n];
       if (p.accumulate) {
@@ -151,6 +157,8 @@ int gemm_simt(const eec_gemm_desc* d, cudaStream_t st) {
   }
   if (p.act == EEC_ACT_DSILU) EEC_CHECK_ARG(d->preact != nullptr, "gemm: DSILU needs preact");
   if (d->accumulate) EEC_CHECK_ARG(d->out_dtype == EEC_F32, "gemm: accumulate needs fp32 C");
+  p.drop = make_drop(d->drop_state, d->drop_p, d->drop_site);
+  if (p.drop.state) EEC_CHECK_ARG(!glu && !d->accumulate && d->N % 8 == 0, "gemm(simt): dropout with GLU / accumulate / N %% 8 != 0 unsupported");
   int tiles = cdiv(p.N, BN) * cdiv(p.M, BM);
   int splits = 1;
   if (d->accumulate && p.K >= 1024 && tiles < 296) {

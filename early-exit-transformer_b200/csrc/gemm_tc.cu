@@ -452,6 +452,7 @@ int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const TcParams& p, d
 }  // namespace
 
 int gemm_tc(const eec_gemm_desc* d, cudaStream_t st, int32_t* argmax, float* entropy, int logsoftmax) {
+  EEC_CHECK_ARG(!(d->drop_state && d->drop_p > 0.f), "gemm_tc (v1): dropout unsupported; unset EEC_GEMM_V1");
   EEC_CHECK_ARG(d->in_dtype == EEC_BF16, "gemm_tc: operands must be bf16");
   EEC_CHECK_ARG(d->N % 32 == 0, "gemm_tc: N (%d) must be a multiple of 32", d->N);
   EEC_CHECK_ARG(d->M > 0 && d->N > 0 && d->K > 0, "gemm_tc: empty problem %dx%dx%d", d->M, d->N, d->K);

@@ -467,6 +467,7 @@ int gemm_tc2(const eec_gemm_desc* d, cudaStream_t st, int32_t* argmax, float* en
     if (!v2_env && epi == EPI_LN && d->res_row_mod == 0 && (!d->residual || d->ldr == 256)) return gemm_ln3(d, st);
   }
   EEC_CHECK_ARG(!d->a_colsum, "gemm_tc2: a_colsum is implemented by the v3 kernel only (unset EEC_GEMM_V2)");
+  EEC_CHECK_ARG(!(d->drop_state && d->drop_p > 0.f), "gemm_tc2: dropout is implemented by the v3 kernels only (this descriptor routes to v2)");
   if (!g_num_sms) {
     int dev = 0;
     EEC_CUDA(cudaGetDevice(&dev));

@@ -62,6 +62,7 @@ struct P3 {
   float* a_colsum; float a_colsum_scale;   // MN-major A only: a_colsum[m] += scale * sum_k A(m,k) from the smem A tiles
   int debug;       // EEC_GEMM_DEBUG bitmask (perf triage only): 1 = no bulk store issue, 2 = no staging, 4 = no activation math
   long long* tl;   // EEC_GEMM_TL=1 (perf triage only): clock64 accumulators of CTA 0, see gemm_tc3()
+  DropArgs drop;   // DROP instantiations only: dropout right after the activation, element index m*N + n
 };
 
 // per-warp staging: values -> swizzled smem box -> bulk tensor store / reduce of a [32 rows x 32 cols] box
@@ -194,7 +195,7 @@ struct UnitIter {
   }
 };
 
-template <bool A_KMAJ, bool B_KMAJ, int EPI, int NST>
+template <bool A_KMAJ, bool B_KMAJ, int EPI, int NST, bool DROP = false>
 __global__ void __launch_bounds__(NT3, 1) gemm_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                                                           const __grid_constant__ CUtensorMap tmC,   // main output (box 32 x 32)
                                                           const __grid_constant__ CUtensorMap tmP,   // bf16 pre-activation: store (SiLU/GLU) or load (dSiLU)
@@ -353,6 +354,8 @@ __global__ void __launch_bounds__(NT3, 1) gemm_tc3_kernel(const __grid_constant_
 #endif
     int cs = 0;             // a_colsum: this warp's position in the operand ring (walks every k-block of every unit)
     uint32_t cph = 0;
+    DropKey dkey{};
+    if (DROP) dkey = drop_key(p.drop);
     for (UnitIter ui(p); ui.u < n_units; ui.next(p), ++ut) {
       TL_STAMP(t0_); TL_ACC(e_rest, ut ? t0_ - t2_ : 0);
       const int split = ui.split;
@@ -522,6 +525,15 @@ __global__ void __launch_bounds__(NT3, 1) gemm_tc3_kernel(const __grid_constant_
             }
             mul_dsilu16(x, st.buf + sl * 2048, half, lane, p.alpha);   // (alpha folded in)
           }
+          if (DROP) {   // keep masks regenerated from (seed, offset, site, element index): nothing is stored for the backward pass
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+              float f[8];
+              drop_factors8(dkey, p.drop, ((uint64_t)m * p.N + n + c * 8) >> 3, f);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) x[c * 8 + j] *= f[j];
+            }
+          }
           if (p.alpha != 1.0f && !dsilu) {
             const float2 al = make_float2(p.alpha, p.alpha);
 #pragma unroll
@@ -619,8 +631,10 @@ struct PLN {
   float alpha;
   int has_res, ln_bf16;
   const float* ln_gamma; const float* ln_beta; float* ln_mean; float* ln_rstd;
+  DropArgs drop;   // DROP instantiation only: x = residual + alpha * dropout(A W^T + bias), element index m*256 + n
 };
 
+template <bool DROP>
 __global__ void __launch_bounds__(LN_NT, 1) gemm_ln3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                                                             const __grid_constant__ CUtensorMap tmC,   // fp32 x out (box 32 x 32)
                                                             const __grid_constant__ CUtensorMap tmR,   // fp32 residual in (box 32 x 32)
@@ -713,6 +727,8 @@ __global__ void __launch_bounds__(LN_NT, 1) gemm_ln3_kernel(const __grid_constan
     const int sw = lane & 7;
     float x[128];   // this thread's 128 x-values (its row, its column half): TMEM is read once, the values never leave registers
     uint32_t ut = 0;
+    DropKey dkey{};
+    if (DROP) dkey = drop_key(p.drop);
     for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x, ++ut) {
       const int m0 = mt * BM;
       const int row0 = m0 + q * 32;
@@ -747,6 +763,15 @@ __global__ void __launch_bounds__(LN_NT, 1) gemm_ln3_kernel(const __grid_constan
           const float4 f = bp[g];
           v[g * 4] = (v[g * 4] + f.x) * p.alpha; v[g * 4 + 1] = (v[g * 4 + 1] + f.y) * p.alpha;
           v[g * 4 + 2] = (v[g * 4 + 2] + f.z) * p.alpha; v[g * 4 + 3] = (v[g * 4 + 3] + f.w) * p.alpha;
+        }
+        if (DROP) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            float f[8];
+            drop_factors8(dkey, p.drop, ((uint64_t)m * 256 + cb + s * 32 + g * 8) >> 3, f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[g * 8 + j] *= f[j];
+          }
         }
         uint8_t* b = buf[s & 1];
         uint8_t* row = b + lane * 128;
@@ -844,15 +869,15 @@ __global__ void __launch_bounds__(LN_NT, 1) gemm_ln3_kernel(const __grid_constan
   }
 }
 
-template <bool AK, bool BK_, int EPI, int NST>
+template <bool AK, bool BK_, int EPI, int NST, bool DROP = false>
 int launch3n(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc_, const CUtensorMap& tp, const P3& p, int grid,
              cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    EEC_CUDA(cudaFuncSetAttribute(gemm_tc3_kernel<AK, BK_, EPI, NST>, cudaFuncAttributeMaxDynamicSharedMemorySize, L3<NST>::BYTES));
+    EEC_CUDA(cudaFuncSetAttribute(gemm_tc3_kernel<AK, BK_, EPI, NST, DROP>, cudaFuncAttributeMaxDynamicSharedMemorySize, L3<NST>::BYTES));
     attr_set = true;
   }
-  launch_pdl(gemm_tc3_kernel<AK, BK_, EPI, NST>, dim3(grid), dim3(NT3), L3<NST>::BYTES, st, ta, tb, tc_, tp, p);
+  launch_pdl(gemm_tc3_kernel<AK, BK_, EPI, NST, DROP>, dim3(grid), dim3(NT3), L3<NST>::BYTES, st, ta, tb, tc_, tp, p);
   EEC_LAUNCH_CHECK();
   return 0;
 }
@@ -916,6 +941,10 @@ int gemm_tc3(const eec_gemm_desc* d, cudaStream_t st) {
   EEC_CHECK_ARG(!d->a_colsum || (!d->a_kmajor && !d->b_kmajor && !d->bias && epi == EPI_GENERIC),
                 "gemm_tc3: a_colsum needs the weight-gradient form (MN-major A and B, no bias)");
   p.a_colsum = d->a_colsum; p.a_colsum_scale = d->a_colsum_scale;
+  p.drop = make_drop(d->drop_state, d->drop_p, d->drop_site);
+  if (p.drop.state)
+    EEC_CHECK_ARG(epi == EPI_GENERIC && !four && d->a_kmajor && !d->accumulate && d->N % 16 == 0,
+                  "gemm_tc3: dropout is fused into the SiLU / dSiLU / plain bf16-output epilogues of K-major-A GEMMs only");
   const int n_units = p.m_tiles * p.n_tiles * p.splits;
   const int grid = min(n_units, g_sms3);
   {
@@ -951,6 +980,10 @@ int gemm_tc3(const eec_gemm_desc* d, cudaStream_t st) {
     if (!d->a_kmajor && !d->b_kmajor) return launch3<false, false, EPI_GENERIC>(ta, tb, tcm, tpm, p, grid, st, four);
     return launch3<false, true, EPI_GENERIC>(ta, tb, tcm, tpm, p, grid, st, four);
   }
+  if (p.drop.state) {
+    if (d->b_kmajor) return launch3n<true, true, EPI_GENERIC, 3, true>(ta, tb, tcm, tpm, p, grid, st);
+    return launch3n<true, false, EPI_GENERIC, 3, true>(ta, tb, tcm, tpm, p, grid, st);
+  }
   if (epi == EPI_GLU) return launch3<true, true, EPI_GLU>(ta, tb, tcm, tpm, p, grid, st);
   if (d->a_kmajor && d->b_kmajor) return launch3<true, true, EPI_GENERIC>(ta, tb, tcm, tpm, p, grid, st, four);
   if (d->a_kmajor && !d->b_kmajor) return launch3<true, false, EPI_GENERIC>(ta, tb, tcm, tpm, p, grid, st, four);
@@ -978,13 +1011,16 @@ int gemm_ln3(const eec_gemm_desc* d, cudaStream_t st) {
   p.M = d->M; p.K = d->K; p.m_tiles = cdiv(d->M, BM);
   p.bias = d->bias; p.alpha = d->alpha; p.has_res = d->residual != nullptr; p.ln_bf16 = d->ln_dtype == EEC_BF16;
   p.ln_gamma = d->ln_gamma; p.ln_beta = d->ln_beta; p.ln_mean = d->ln_mean; p.ln_rstd = d->ln_rstd;
+  p.drop = make_drop(d->drop_state, d->drop_p, d->drop_site);
   static bool attr_set = false;
   if (!attr_set) {
-    EEC_CUDA(cudaFuncSetAttribute(gemm_ln3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LN_SMEM_BYTES));
+    EEC_CUDA(cudaFuncSetAttribute(gemm_ln3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, LN_SMEM_BYTES));
+    EEC_CUDA(cudaFuncSetAttribute(gemm_ln3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, LN_SMEM_BYTES));
     attr_set = true;
   }
   const int grid = min(p.m_tiles, g_sms3);
-  launch_pdl(gemm_ln3_kernel, dim3(grid), dim3(LN_NT), LN_SMEM_BYTES, st, ta, tb, tcm, trm, tlm, p);
+  if (p.drop.state) launch_pdl(gemm_ln3_kernel<true>, dim3(grid), dim3(LN_NT), LN_SMEM_BYTES, st, ta, tb, tcm, trm, tlm, p);
+  else launch_pdl(gemm_ln3_kernel<false>, dim3(grid), dim3(LN_NT), LN_SMEM_BYTES, st, ta, tb, tcm, trm, tlm, p);
   EEC_LAUNCH_CHECK();
   return 0;
 }

@@ -41,14 +41,18 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
 }
 
 // ------------------------------------------------------------------ LayerNorm backward
+template <typename TC, bool DROP>
 __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
                                                             const float* __restrict__ mean, const float* __restrict__ rstd,
                                                             const float* __restrict__ gamma, float* __restrict__ dx,
                                                             int dx_accumulate, float* __restrict__ dgamma,
-                                                            float* __restrict__ dbeta, __nv_bfloat16* __restrict__ dx_bf16,
-                                                            float* __restrict__ dx_colsum, float colsum_scale, int rows) {
+                                                            float* __restrict__ dbeta, TC* __restrict__ dx_bf16,
+                                                            float* __restrict__ dx_colsum, float colsum_scale, int rows,
+                                                            const DropArgs drop) {
   pdl_trigger();
   pdl_wait();
+  DropKey dkey{};
+  if (DROP) dkey = drop_key(drop);
   __shared__ float red[8][256];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int c0 = lane * 8;
@@ -83,7 +87,13 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
       for (int i = 0; i < 8; ++i) o[i] += old[i];
     }
     st8<float>(dx + (long)r * 256 + c0, o);
-    if (dx_bf16) st8<__nv_bfloat16>(dx_bf16 + (long)r * 256 + c0, o);
+    if (DROP) {   // the copy / column sums feed the backward of a projection whose output was dropped out (dx itself is the residual gradient)
+      float f[8];
+      drop_factors8(dkey, drop, (uint64_t)r * 32 + lane, f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] *= f[i];
+    }
+    if (dx_bf16) st8<TC>(dx_bf16 + (long)r * 256 + c0, o);
 #pragma unroll
     for (int i = 0; i < 8; ++i) cs[i] += o[i];
   }
@@ -257,6 +267,33 @@ __global__ void __launch_bounds__(256) colsum_vec_kernel(const T* __restrict__ i
   atomicAdd(out + blockIdx.x * 256 + threadIdx.x, t * scale);
 }
 
+// ------------------------------------------------------------------ dropout (standalone: positional-encoding site, tests)
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256) dropout_kernel(const TI* __restrict__ in, TO* __restrict__ out, long n, const DropArgs drop) {
+  pdl_trigger();
+  pdl_wait();
+  const DropKey key = drop_key(drop);
+  for (long g = (long)blockIdx.x * blockDim.x + threadIdx.x; g * 8 < n; g += (long)gridDim.x * blockDim.x) {
+    const long i = g * 8;
+    float f[8];
+    drop_factors8(key, drop, (uint64_t)g, f);
+    if (i + 8 <= n) {
+      float v[8];
+      ld8<TI>(in + i, v);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] *= f[k];
+      st8<TO>(out + i, v);
+    } else {
+      for (int k = 0; i + k < n; ++k) st_from_float<TO>(out + i + k, ld_as_float<TI>(in + i + k) * f[k]);
+    }
+  }
+}
+__global__ void dropout_advance_kernel(uint64_t* state) {
+  pdl_trigger();
+  pdl_wait();
+  if (threadIdx.x == 0 && blockIdx.x == 0) state[1] += 1;
+}
+
 __global__ void axpy_kernel(const float* __restrict__ x, float a, float* __restrict__ y, long n) {
   pdl_trigger();
   pdl_wait();
@@ -378,11 +415,43 @@ extern "C" int eec_layernorm_fwd(const float* x, const float* gamma, const float
 
 extern "C" int eec_layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd,
                                  const float* gamma, float* dx, int dx_accumulate, float* dgamma, float* dbeta,
-                                 void* dx_bf16, float* dx_colsum, float colsum_scale, int rows, int d, eec_stream_t stream) {
+                                 void* dx_copy, int dx_copy_dtype, float* dx_colsum, float colsum_scale,
+                                 const uint64_t* drop_state, float drop_p, uint32_t drop_site, int rows, int d,
+                                 eec_stream_t stream) {
   EEC_CHECK_ARG(d == 256, "layernorm_bwd: d must be 256 (got %d)", d);
   if (rows == 0) return 0;
   int blocks = min(cdiv(rows, 8), 148 * 4);
-  launch_pdl(layernorm_bwd_kernel, dim3(blocks), dim3(256), 0, S(stream), dy, x, mean, rstd, gamma, dx, dx_accumulate, dgamma, dbeta, (__nv_bfloat16*)dx_bf16, dx_colsum, colsum_scale, rows);
+  const DropArgs drop = make_drop(drop_state, drop_p, drop_site);
+  EEC_CHECK_ARG(!drop.state || dx_copy || dx_colsum, "layernorm_bwd: dropout only affects dx_copy / dx_colsum, and neither was requested");
+#define EEC_LNB(TC, DROP) launch_pdl(layernorm_bwd_kernel<TC, DROP>, dim3(blocks), dim3(256), 0, S(stream), dy, x, mean, rstd, gamma, dx, dx_accumulate, dgamma, dbeta, (TC*)dx_copy, dx_colsum, colsum_scale, rows, drop)
+  if (dx_copy && dx_copy_dtype == EEC_F32) { if (drop.state) EEC_LNB(float, true); else EEC_LNB(float, false); }
+  else { if (drop.state) EEC_LNB(__nv_bfloat16, true); else EEC_LNB(__nv_bfloat16, false); }
+#undef EEC_LNB
+  EEC_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int eec_dropout(const void* x, int in_dtype, void* y, int out_dtype, int64_t n, const uint64_t* state, float p,
+                           uint32_t site, eec_stream_t stream) {
+  if (n == 0) return 0;
+  EEC_CHECK_ARG(state != nullptr, "dropout: state is NULL");
+  EEC_CHECK_ARG(p >= 0.f && p < 1.f, "dropout: p must be in [0, 1) (got %f)", p);
+  DropArgs drop = make_drop(state, p, site);
+  if (!drop.state) { drop.state = state; drop.site = site; drop.thr = 0; drop.scale = 1.f; }   // p == 0: identity through the same kernel
+  const int blocks = (int)min((long)148 * 16, cdiv64(cdiv64(n, 8), 256));
+#define EEC_DROPK(TI, TO) launch_pdl(dropout_kernel<TI, TO>, dim3(blocks), dim3(256), 0, S(stream), (const TI*)x, (TO*)y, (long)n, drop)
+  if (in_dtype == EEC_F32 && out_dtype == EEC_F32) EEC_DROPK(float, float);
+  else if (in_dtype == EEC_F32 && out_dtype == EEC_BF16) EEC_DROPK(float, __nv_bfloat16);
+  else if (in_dtype == EEC_BF16 && out_dtype == EEC_BF16) EEC_DROPK(__nv_bfloat16, __nv_bfloat16);
+  else EEC_DROPK(__nv_bfloat16, float);
+#undef EEC_DROPK
+  EEC_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int eec_dropout_advance(uint64_t* state, eec_stream_t stream) {
+  EEC_CHECK_ARG(state != nullptr, "dropout_advance: state is NULL");
+  launch_pdl(dropout_advance_kernel, dim3(1), dim3(32), 0, S(stream), state);
   EEC_LAUNCH_CHECK();
   return 0;
 }

@@ -98,7 +98,7 @@ class full_conformer(_EarlyExitBase):
         params = [p for _, p in self._encoder_named_parameters()]
         want_tape = self.training and torch.is_grad_enabled() and any(p.requires_grad for p in params)
         full = self._cfg()
-        cfg = engine.Config(n_exits=n_exits, n_layers=full.n_layers, n_mels=full.n_mels, precision=full.precision)
+        cfg = engine.Config(n_exits=n_exits, n_layers=full.n_layers, n_mels=full.n_mels, precision=full.precision, drop_p=full.drop_p)
         return _EncoderFn.apply(self, want_tape, cfg, True, src, lengths, *params)
 
     def _encoder_(self, src: Tensor, lengths: Tensor, layer_n: int) -> Tensor:

@@ -116,7 +116,14 @@ class _EncoderFn(torch.autograd.Function):
     def forward(ctx, module, want_tape, cfg, want_hidden, src, lengths, *params):
         P = module._tensor_dict()
         side = {"want_hidden": True} if want_hidden else None
-        out, tape = engine.model_forward(P, module._operands, cfg, src, lengths, module.training, want_tape, side)
+        drop_state = None
+        if module.training and cfg.drop_p > 0.0:
+            # this forward's own copy of {seed, offset}: backward regenerates the masks from it even if another forward
+            # ran in between; the module's counter moves on (on device: a graph replay draws new masks every step)
+            st = module._dropout_state(src.device)
+            drop_state = st.clone()
+            ops.dropout_advance(st)
+        out, tape = engine.model_forward(P, module._operands, cfg, src, lengths, module.training, want_tape, side, drop_state)
         ctx.module, ctx.tape, ctx.P, ctx.cfg, ctx.want_hidden = module, tape, P, cfg, want_hidden
         return (out, side["hidden"]) if want_hidden else out
 
@@ -174,16 +181,35 @@ class _EarlyExitBase(nn.Module):
         if 3 * self._features_length > 256: bad.append(f"features_length={self._features_length} (need <= 85)")
         if bad:
             raise EecError("eec kernels are specialised for the BASELINE early_conformer shape; unsupported: " + ", ".join(bad))
-        if self.training and self.dropout > 0:
-            raise NotImplementedError(
-                "eec: training with drop_prob > 0 is not implemented yet (dropout RNG cannot match PyTorch's streams; "
-                "pass --drop_prob 0). Eval mode ignores dropout as the reference does.")
+        if not (0.0 <= float(self.dropout) < 1.0):
+            raise ValueError(f"dropout probability has to be between 0 and 1, but got {self.dropout}")
         if self.precision not in ("fp32", "bf16"):
             raise EecError(f"precision must be 'fp32' or 'bf16', got {self.precision!r}")
 
     def _cfg(self) -> engine.Config:
         return engine.Config(n_exits=self.n_enc_exits, n_layers=self.num_layers, n_mels=self._features_length,
-                             splitformer=self._splitformer, precision=self.precision)
+                             splitformer=self._splitformer, precision=self.precision, drop_p=float(self.dropout))
+
+    # -- dropout (train mode, drop_prob > 0): counter-based masks, include/eec.h "dropout".  PyTorch's RNG streams cannot be
+    #    matched; the seed follows torch's global seed at first use, so torch.manual_seed(s) before training
+    #    makes runs repeatable, and set_dropout_seed() pins it explicitly.
+    def _dropout_state(self, dev) -> Tensor:
+        st = self.__dict__.get("_drop_state")
+        dev = torch.device(dev)
+        if st is None or st.device.type != dev.type or (dev.index is not None and st.device.index != dev.index):
+            seed = self.__dict__.get("_drop_seed")
+            if seed is None:
+                seed = torch.initial_seed()
+            st = torch.tensor([seed & 0x7FFFFFFFFFFFFFFF, 0], dtype=torch.int64, device=dev)
+            self.__dict__["_drop_state"] = st
+        return st
+
+    def set_dropout_seed(self, seed: int, offset: int = 0) -> None:
+        """Fix the dropout generator: masks are a pure function of (seed, offset, site, element index); offset counts forwards."""
+        self.__dict__["_drop_seed"] = int(seed)
+        st = self.__dict__.get("_drop_state")
+        if st is not None:
+            st.copy_(torch.tensor([int(seed) & 0x7FFFFFFFFFFFFFFF, int(offset)], dtype=torch.int64))
 
     @property
     def _operands(self) -> engine.Operands:

@@ -36,6 +36,7 @@ class Config:
     n_mels: int = 80
     splitformer: bool = False
     precision: str = "fp32"   # "fp32" (FFMA parity path) or "bf16" (tcgen05 path)
+    drop_p: float = 0.0       # train-mode dropout probability (the reference's --drop_prob; applied when a drop state is passed)
 
     @property
     def act_dtype(self):
@@ -135,9 +136,20 @@ def to_act(x32: Tensor, cfg: Config) -> Tensor:
 # ----------------------------------------------------------------------------------------------
 # one ConformerLayer
 # ----------------------------------------------------------------------------------------------
+# dropout sites of one ConformerLayer, as offsets from the layer's site base (ops.Drop.at): the nn.Dropout modules at
+# TA:106 / TA:108 (both FFNs), nn.MultiheadAttention's dropout on the probabilities (TA:152), TA:201, TA:73
+S_FFN1_ACT, S_FFN1_OUT, S_ATTN_P, S_ATTN_OUT, S_CONV_OUT, S_FFN2_ACT, S_FFN2_OUT = range(7)
+SITE_PE = 0                      # positional_encoding.py:72
+SITES_PER_LAYER = 8
+
+
+def _at(drop, k):
+    return drop.at(k) if drop is not None else None
+
+
 def layer_forward(P: Dict[str, Tensor], W: Operands, pre: str, x: Tensor, key_len: Tensor, B: int, T: int, cfg: Config,
-                  training: bool, tape: Optional[dict]):
-    """x: fp32 [B*T, 256] -> fp32 [B*T, 256].  TA:176-212."""
+                  training: bool, tape: Optional[dict], drop: Optional[ops.Drop] = None):
+    """x: fp32 [B*T, 256] -> fp32 [B*T, 256].  TA:176-212.  `drop` = this layer's dropout site base (train mode, p > 0)."""
     N = B * T
     dev = x.device
     TD = cfg.act_dtype
@@ -147,18 +159,18 @@ def layer_forward(P: Dict[str, Tensor], W: Operands, pre: str, x: Tensor, key_le
     def stat():
         return (_empty((N,), f32, dev), _empty((N,), f32, dev)) if save else (None, None)
 
-    def ffn(tag: str, x_in: Tensor, u: Tensor, ln_next_g, ln_next_b, ln_out_dtype):
+    def ffn(tag: str, x_in: Tensor, u: Tensor, ln_next_g, ln_next_b, ln_out_dtype, s_act: int, s_out: int):
         q = pre + tag + ".sequential."
         W1 = W.get(q + "1.weight", P[q + "1.weight"], (F, D))
         W2 = W.get(q + "4.weight", P[q + "4.weight"], (D, F))
         hpre = _empty((N, F), TD, dev) if save else None
         a = _empty((N, F), TD, dev)
-        linear(u, W1, a, N, F, D, bias=P[q + "1.bias"], act=ACT_SILU, preact=hpre)
+        linear(u, W1, a, N, F, D, bias=P[q + "1.bias"], act=ACT_SILU, preact=hpre, drop=_at(drop, s_act))
         x_out = _empty((N, D), f32, dev)
         u_next = _empty((N, D), ln_out_dtype, dev)
         m, r = stat()
         linear(a, W2, x_out, N, D, F, bias=P[q + "4.bias"], alpha=0.5, residual=x_in, ln_gamma=ln_next_g, ln_beta=ln_next_b,
-               ln_out=u_next, ln_mean=m, ln_rstd=r)
+               ln_out=u_next, ln_mean=m, ln_rstd=r, drop=_at(drop, s_out))
         return x_out, u_next, hpre, a, m, r
 
     # ---- FFN1 (TA:185-187): x1 = x + 0.5*FFN(LN(x));  u2 = LN_attn(x1) fused into the GEMM tail
@@ -166,7 +178,8 @@ def layer_forward(P: Dict[str, Tensor], W: Operands, pre: str, x: Tensor, key_le
     u1 = _empty((N, D), TD, dev)
     m1, r1 = stat()
     ops.layernorm_fwd(x, P[q + "0.weight"], P[q + "0.bias"], u1, m1, r1)
-    x1, u2, h1pre, a1, m2, r2 = ffn("ffn1", x, u1, P[pre + "self_attn_layer_norm.weight"], P[pre + "self_attn_layer_norm.bias"], TD)
+    x1, u2, h1pre, a1, m2, r2 = ffn("ffn1", x, u1, P[pre + "self_attn_layer_norm.weight"], P[pre + "self_attn_layer_norm.bias"], TD,
+                                    S_FFN1_ACT, S_FFN1_OUT)
 
     # ---- MHSA (TA:192-202)
     Wqkv = W.get(pre + "self_attn.in_proj_weight", P[pre + "self_attn.in_proj_weight"], (3 * D, D))
@@ -175,13 +188,13 @@ def layer_forward(P: Dict[str, Tensor], W: Operands, pre: str, x: Tensor, key_le
     linear(u2, Wqkv, qkv, N, 3 * D, D, bias=P[pre + "self_attn.in_proj_bias"])
     ctx = _empty((N, D), TD, dev)
     lse = _empty((B, H, T), f32, dev)
-    ops.attn_fwd(qkv, key_len, ctx, lse, B, T, H)
+    ops.attn_fwd(qkv, key_len, ctx, lse, B, T, H, drop=_at(drop, S_ATTN_P))
     x2 = _empty((N, D), f32, dev)
     u3 = _empty((N, D), TD, dev)
     m3, r3 = stat()
     c = pre + "conv_module."
     linear(ctx, Wo, x2, N, D, D, bias=P[pre + "self_attn.out_proj.bias"], residual=x1, ln_gamma=P[c + "layer_norm.weight"],
-           ln_beta=P[c + "layer_norm.bias"], ln_out=u3, ln_mean=m3, ln_rstd=r3)
+           ln_beta=P[c + "layer_norm.bias"], ln_out=u3, ln_mean=m3, ln_rstd=r3, drop=_at(drop, S_ATTN_OUT))
 
     # ---- convolution module (TA:42-75, 168-174)
     Wp1 = W.get(c + "sequential.0.weight", P[c + "sequential.0.weight"], (2 * D, D))
@@ -208,15 +221,16 @@ def layer_forward(P: Dict[str, Tensor], W: Operands, pre: str, x: Tensor, key_le
     m4, r4 = stat()
     q2 = pre + "ffn2.sequential."
     linear(s, Wp2, x3, N, D, D, bias=P[c + "sequential.5.bias"], residual=x2, ln_gamma=P[q2 + "0.weight"],
-           ln_beta=P[q2 + "0.bias"], ln_out=u4, ln_mean=m4, ln_rstd=r4)
+           ln_beta=P[q2 + "0.bias"], ln_out=u4, ln_mean=m4, ln_rstd=r4, drop=_at(drop, S_CONV_OUT))
 
     # ---- FFN2 + final LayerNorm (TA:207-211): x4 = x3 + 0.5*FFN(u4); y = LN_final(x4)
-    x4, y, h2pre, a2, m5, r5 = ffn("ffn2", x3, u4, P[pre + "final_layer_norm.weight"], P[pre + "final_layer_norm.bias"], f32)
+    x4, y, h2pre, a2, m5, r5 = ffn("ffn2", x3, u4, P[pre + "final_layer_norm.weight"], P[pre + "final_layer_norm.bias"], f32,
+                                   S_FFN2_ACT, S_FFN2_OUT)
 
     if save:
         tape.update(dict(x=x, u1=u1, m1=m1, r1=r1, h1pre=h1pre, a1=a1, x1=x1, u2=u2, m2=m2, r2=r2, qkv=qkv, ctx=ctx, lse=lse,
                          x2=x2, u3=u3, m3=m3, r3=r3, z=z, g=g, c=cbuf, sm=sm, sr=sr, s=s, x3=x3, u4=u4, m4=m4, r4=r4,
-                         h2pre=h2pre, a2=a2, x4=x4, m5=m5, r5=r5, key_len=key_len, B=B, T=T))
+                         h2pre=h2pre, a2=a2, x4=x4, m5=m5, r5=r5, key_len=key_len, B=B, T=T, drop=drop))
     return y
 
 
@@ -230,33 +244,38 @@ def layer_backward(P, W: Operands, G: Dict[str, Tensor], pre: str, t: dict, dY: 
     c = pre + "conv_module."
 
     bf16 = cfg.precision == "bf16"
+    drop = t.get("drop")     # the forward's dropout site base: every mask is regenerated from it, none was stored
 
-    def ln_bwd(dy, x_in, m, r, key, accumulate, want_h=True, bias_key=None, bias_scale=1.0):
+    def ln_bwd(dy, x_in, m, r, key, accumulate, want_h=True, bias_key=None, bias_scale=1.0, s_out=None):
         """LayerNorm backward into the residual-gradient stream dX; also emits the GEMM-operand copy of dX and,
-        fused, the column sums of the new dX (= bias gradient `bias_key` of the next projection in the chain)."""
-        dXh = _empty((N, D), TD, dev) if (bf16 and want_h) else None
+        fused, the column sums of the new dX (= bias gradient `bias_key` of the next projection in the chain).
+        s_out: dropout site of that projection's output -- copy and column sums then carry dropout'(dX)."""
+        dsite = _at(drop, s_out) if s_out is not None else None
+        dXh = _empty((N, D), TD, dev) if ((bf16 or dsite is not None) and want_h) else None
         ops.layernorm_bwd(dy, x_in, m, r, P[key + "weight"], dX, accumulate, G[key + "weight"], G[key + "bias"], dXh,
-                          G[bias_key] if bias_key else None, bias_scale)
-        return dXh if bf16 else dX
+                          G[bias_key] if bias_key else None, bias_scale, drop=dsite)
+        return dXh if dXh is not None else dX
 
     # final LayerNorm
     dX = _empty((N, D), f32, dev)
-    dXh = ln_bwd(dY, t["x4"], t["m5"], t["r5"], pre + "final_layer_norm.", False, True, pre + "ffn2.sequential.4.bias", 0.5)
+    dXh = ln_bwd(dY, t["x4"], t["m5"], t["r5"], pre + "final_layer_norm.", False, True, pre + "ffn2.sequential.4.bias", 0.5,
+                 s_out=S_FFN2_OUT)
 
-    def ffn_bwd(tag, x_in, u, m, r, hpre, a, dXh, want_h, next_bias=None):
+    def ffn_bwd(tag, x_in, u, m, r, hpre, a, dXh, want_h, s_act, next_bias=None, next_site=None):
         q = pre + tag + ".sequential."
         W1 = W.get(q + "1.weight", P[q + "1.weight"], (F, D))
         W2 = W.get(q + "4.weight", P[q + "4.weight"], (D, F))
         wgrad(dXh, a, G[q + "4.weight"], N, D, F, alpha=0.5)     # (this FFN's output-bias grad came fused from ln_bwd)
         dh = _empty((N, F), TD, dev)
-        dgrad(dXh, W2, dh, N, D, F, act=ACT_DSILU, preact=hpre, alpha=0.5)
+        dgrad(dXh, W2, dh, N, D, F, act=ACT_DSILU, preact=hpre, alpha=0.5, drop=_at(drop, s_act))
         wgrad(dh, u, G[q + "1.weight"], N, F, D, dbias=G[q + "1.bias"])
         du = _empty((N, D), f32, dev)
         dgrad(dh, W1, du, N, F, D)
-        return ln_bwd(du, x_in, m, r, q + "0.", True, want_h, next_bias)
+        return ln_bwd(du, x_in, m, r, q + "0.", True, want_h, next_bias, s_out=next_site)
 
     # FFN2: x4 = x3 + 0.5*FFN(u4), u4 = LN(x3)
-    dXh = ffn_bwd("ffn2", t["x3"], t["u4"], t["m4"], t["r4"], t["h2pre"], t["a2"], dXh, True, c + "sequential.5.bias")
+    dXh = ffn_bwd("ffn2", t["x3"], t["u4"], t["m4"], t["r4"], t["h2pre"], t["a2"], dXh, True, S_FFN2_ACT, c + "sequential.5.bias",
+                  S_CONV_OUT)
 
     # conv module: x3 = x2 + pw2(s) + b
     Wp1 = W.get(c + "sequential.0.weight", P[c + "sequential.0.weight"], (2 * D, D))
@@ -276,7 +295,7 @@ def layer_backward(P, W: Operands, G: Dict[str, Tensor], pre: str, t: dict, dY: 
     wgrad(dz, t["u3"], G[c + "sequential.0.weight"].view(2 * D, D), N, 2 * D, D, dbias=G[c + "sequential.0.bias"])
     du3 = _empty((N, D), f32, dev)
     dgrad(dz, Wp1, du3, N, 2 * D, D)
-    dXh = ln_bwd(du3, t["x2"], t["m3"], t["r3"], c + "layer_norm.", True, True, pre + "self_attn.out_proj.bias")
+    dXh = ln_bwd(du3, t["x2"], t["m3"], t["r3"], c + "layer_norm.", True, True, pre + "self_attn.out_proj.bias", s_out=S_ATTN_OUT)
 
     # MHSA: x2 = x1 + out_proj(attn(qkv)) ; qkv = in_proj(u2); u2 = LN(x1)
     Wqkv = W.get(pre + "self_attn.in_proj_weight", P[pre + "self_attn.in_proj_weight"], (3 * D, D))
@@ -287,21 +306,22 @@ def layer_backward(P, W: Operands, G: Dict[str, Tensor], pre: str, t: dict, dY: 
     dqkv = _empty((N, 3 * D), TD, dev)
     dvec = _empty((B * H * T,), f32, dev)
     dq32 = _empty((N, D), f32, dev) if bf16 else None
-    ops.attn_bwd(t["qkv"], t["ctx"], dctx, t["lse"], t["key_len"], dqkv, dvec, B, T, H, dq32)
+    ops.attn_bwd(t["qkv"], t["ctx"], dctx, t["lse"], t["key_len"], dqkv, dvec, B, T, H, dq32, drop=_at(drop, S_ATTN_P))
     wgrad(dqkv, t["u2"], G[pre + "self_attn.in_proj_weight"], N, 3 * D, D, dbias=G[pre + "self_attn.in_proj_bias"])
     du2 = _empty((N, D), f32, dev)
     dgrad(dqkv, Wqkv, du2, N, 3 * D, D)
-    dXh = ln_bwd(du2, t["x1"], t["m2"], t["r2"], pre + "self_attn_layer_norm.", True, True, pre + "ffn1.sequential.4.bias", 0.5)
+    dXh = ln_bwd(du2, t["x1"], t["m2"], t["r2"], pre + "self_attn_layer_norm.", True, True, pre + "ffn1.sequential.4.bias", 0.5,
+                 s_out=S_FFN1_OUT)
 
     # FFN1
-    ffn_bwd("ffn1", t["x"], t["u1"], t["m1"], t["r1"], t["h1pre"], t["a1"], dXh, False)
+    ffn_bwd("ffn1", t["x"], t["u1"], t["m1"], t["r1"], t["h1pre"], t["a1"], dXh, False, S_FFN1_ACT)
     return dX
 
 
 # ----------------------------------------------------------------------------------------------
 # front end (early_exit.py:24-48 + positional_encoding.py:70-72)
 # ----------------------------------------------------------------------------------------------
-def frontend_forward(P, W: Operands, src: Tensor, cfg: Config, tape: Optional[dict]):
+def frontend_forward(P, W: Operands, src: Tensor, cfg: Config, tape: Optional[dict], drop: Optional[ops.Drop] = None):
     B, n_mels, T_in = src.shape
     T1 = (T_in - 3) // 2 + 1
     T = (T1 - 3) // 2 + 1
@@ -321,8 +341,10 @@ def frontend_forward(P, W: Operands, src: Tensor, cfg: Config, tape: Optional[di
     ops.im2col_k3s2(x1, T1 * D, 1, D, cols2, 3 * D, B, D, T)
     x0 = _empty((B * T, D), f32, dev)
     linear(cols2, W2, x0, B * T, D, 3 * D, bias=P["conv_subsample.sequential.1.bias"], residual=pe.view(-1, D), res_row_mod=T)
+    if drop is not None:
+        ops.dropout(x0, x0, drop.at(SITE_PE))   # positional_encoding.py:72: dropout AFTER the sum with pe
     if tape is not None:
-        tape.update(dict(cols1=cols1, cols2=cols2, B=B, T=T, T1=T1, n_mels=n_mels))
+        tape.update(dict(cols1=cols1, cols2=cols2, B=B, T=T, T1=T1, n_mels=n_mels, drop=drop))
     return x0, T
 
 
@@ -330,6 +352,8 @@ def frontend_backward(P, W: Operands, G, t: dict, dX: Tensor, cfg: Config):
     B, T, T1, n_mels = t["B"], t["T"], t["T1"], t["n_mels"]
     dev, f32 = dX.device, torch.float32
     W2 = W.get("conv_subsample.sequential.1.weight", P["conv_subsample.sequential.1.weight"], (D, 3 * D))
+    if t.get("drop") is not None:
+        ops.dropout(dX, dX, t["drop"].at(SITE_PE))
     ops.colsum(dX, G["conv_subsample.sequential.1.bias"], B * T, D)
     dXh = to_act(dX, cfg)
     wgrad(dXh, t["cols2"], G["conv_subsample.sequential.1.weight"].view(D, 3 * D), B * T, D, 3 * D)
@@ -368,11 +392,13 @@ def check_lengths(lengths: Tensor, T: int):
 
 
 def model_forward(P: Dict[str, Tensor], W: Operands, cfg: Config, src: Tensor, lengths: Tensor, training: bool,
-                  want_tape: bool, side: Optional[dict] = None):
+                  want_tape: bool, side: Optional[dict] = None, drop_state: Optional[Tensor] = None):
     """-> (out [E,B,T,V] fp32 log-probs, Tape|None).  `side` (optional dict) receives per-exit
     argmax / frame-entropy tensors when it contains the key "want", and -- when it contains the key
     "want_hidden" -- side["hidden"] = [E,B,T,D] fp32 encoder states after every exit group (what
-    full_conformer's decoders attend to, early_exit.py:783-786)."""
+    full_conformer's decoders attend to, early_exit.py:783-786).
+    drop_state: int64[2] device tensor {seed, offset} owned by THIS forward (train mode with cfg.drop_p > 0); the tape
+    keeps it so that backward regenerates the same masks."""
     if not src.is_cuda:
         raise EecError("eec: input must be on a CUDA device; there is no CPU path")
     src = src.contiguous()
@@ -380,7 +406,16 @@ def model_forward(P: Dict[str, Tensor], W: Operands, cfg: Config, src: Tensor, l
         src = src.float()
     dev, f32 = src.device, torch.float32
     tape = Tape() if want_tape else None
-    x, T = frontend_forward(P, W, src, cfg, tape.front if tape else None)
+    drop0 = None
+    if training and cfg.drop_p > 0.0:
+        if drop_state is None:
+            raise EecError("eec: train-mode forward with drop_prob > 0 needs a dropout state (seed, offset) tensor")
+        drop0 = ops.Drop(drop_state, cfg.drop_p, 0)
+
+    def layer_drop(uid: int):
+        return drop0.at((1 + uid) * SITES_PER_LAYER) if drop0 is not None else None
+
+    x, T = frontend_forward(P, W, src, cfg, tape.front if tape else None, drop0)
     B = src.shape[0]
     N = B * T
     check_lengths(lengths, T)
@@ -400,7 +435,7 @@ def model_forward(P: Dict[str, Tensor], W: Operands, cfg: Config, src: Tensor, l
         for l in range(cfg.n_layers):
             pre = f"conformer.{e}.conformer_layers.{l}."
             lt = {"pre": pre} if tape else None
-            x = layer_forward(P, W, pre, x, key_len, B, T, cfg, training, lt)
+            x = layer_forward(P, W, pre, x, key_len, B, T, cfg, training, lt, layer_drop(e * cfg.n_layers + l))
             if tape:
                 tape.layers.append(lt)
         br = None
@@ -416,7 +451,7 @@ def model_forward(P: Dict[str, Tensor], W: Operands, cfg: Config, src: Tensor, l
             ops.encoder_lengths(lengths_dev, len2, T2, 2, pad)
             pre = f"conformer_parallel.{i}.conformer_layers.0."
             br = {"pre": pre} if tape else None
-            yd = layer_forward(P, W, pre, xd, len2, B, T2, cfg, training, br)
+            yd = layer_forward(P, W, pre, xd, len2, B, T2, cfg, training, br, layer_drop(1000 + i))
             if x is x_in:
                 x = x.clone()
             ops.repeat2_add(yd, x, B, T)

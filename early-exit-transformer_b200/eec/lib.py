@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get("EEC_LIB") or os.path.join(_HERE, "libeec.so")   # EEC
 F32, BF16 = 0, 1
 ACT_NONE, ACT_SILU, ACT_GLU, ACT_DSILU = 0, 1, 2, 3
 
-vp, i32, i64, f32 = C.c_void_p, C.c_int, C.c_int64, C.c_float
+vp, i32, i64, f32, u32 = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_uint32
 
 
 class GemmDesc(C.Structure):
@@ -38,6 +38,7 @@ class GemmDesc(C.Structure):
         ("x_pre", vp),
         ("a_colsum", vp),
         ("a_colsum_scale", f32),
+        ("drop_state", vp), ("drop_p", f32), ("drop_site", C.c_uint32),
     ]
 
 
@@ -46,9 +47,11 @@ _SIGS = {
     "eec_gemm": [C.POINTER(GemmDesc), vp],
     "eec_ffn_fwd": [vp, vp, vp, vp, vp, vp, f32, vp, vp, vp, vp, i32, vp, vp, vp, i32, i32, i32, vp],
     "eec_layernorm_fwd": [vp, vp, vp, vp, i32, vp, vp, i32, i32, vp],
-    "eec_layernorm_bwd": [vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, f32, i32, i32, vp],
-    "eec_attn_fwd": [vp, i32, vp, vp, vp, i32, i32, i32, i32, vp],
-    "eec_attn_bwd": [vp, vp, vp, i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp],
+    "eec_layernorm_bwd": [vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, i32, vp, f32, vp, f32, u32, i32, i32, vp],
+    "eec_attn_fwd": [vp, i32, vp, vp, vp, i32, i32, i32, i32, vp, f32, u32, vp],
+    "eec_attn_bwd": [vp, vp, vp, i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp, f32, u32, vp],
+    "eec_dropout": [vp, i32, vp, i32, i64, vp, f32, u32, vp],
+    "eec_dropout_advance": [vp, vp],
     "eec_dwconv_bn_silu_eval": [vp, i32, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp],
     "eec_dwconv_stats": [vp, i32, vp, vp, vp, vp, i32, i32, i32, i32, vp],
     "eec_bn_silu_train": [vp, vp, vp, vp, vp, vp, vp, f32, vp, vp, vp, i32, i32, i32, vp],

@@ -14,6 +14,25 @@ from .lib import ACT_DSILU, ACT_GLU, ACT_NONE, ACT_SILU, BF16, F32, call, dt, pt
 Tensor = torch.Tensor
 
 
+class Drop:
+    """One dropout site of one forward pass: (device state {seed, offset} as an int64[2] tensor, probability, site id).
+    Kernels regenerate the keep mask from these three and the element index (include/eec.h "dropout")."""
+    __slots__ = ("state", "p", "site")
+
+    def __init__(self, state: Tensor, p: float, site: int):
+        self.state, self.p, self.site = state, float(p), int(site)
+
+    def at(self, k: int) -> "Drop":
+        return Drop(self.state, self.p, self.site + k)
+
+
+def _d(drop):
+    """(state pointer, p, site) C arguments of an optional Drop"""
+    if drop is None or drop.p <= 0.0:
+        return None, 0.0, 0
+    return drop.state.data_ptr(), drop.p, drop.site
+
+
 def _chk(t: Tensor, name: str):
     if not t.is_cuda:
         raise L.EecError(f"{name}: tensor must live on a CUDA device (no CPU path exists)")
@@ -28,7 +47,7 @@ def gemm(
     residual: Optional[Tensor] = None, res_row_mod: int = 0, accumulate: bool = False,
     ln_gamma: Optional[Tensor] = None, ln_beta: Optional[Tensor] = None, ln_out: Optional[Tensor] = None,
     ln_mean: Optional[Tensor] = None, ln_rstd: Optional[Tensor] = None, ldc: Optional[int] = None,
-    a_colsum: Optional[Tensor] = None, a_colsum_scale: float = 1.0,
+    a_colsum: Optional[Tensor] = None, a_colsum_scale: float = 1.0, drop: Optional[Drop] = None,
 ):
     """C[M,N] = epi(A(m,k) B(n,k)).  See include/eec.h::eec_gemm_desc."""
     for t, n in ((A, "A"), (B, "B"), (C_out, "C")):
@@ -59,6 +78,7 @@ def gemm(
     d.ld_ln = N
     d.ln_mean, d.ln_rstd = ptr(ln_mean), ptr(ln_rstd)
     d.a_colsum, d.a_colsum_scale = ptr(a_colsum), a_colsum_scale
+    d.drop_state, d.drop_p, d.drop_site = _d(drop)
     call("eec_gemm", C.byref(d), stream())
 
 
@@ -76,19 +96,37 @@ def layernorm_fwd(x, gamma, beta, out, mean=None, rstd=None):
     call("eec_layernorm_fwd", ptr(x), ptr(gamma), ptr(beta), ptr(out), dt(out), ptr(mean), ptr(rstd), rows, 256, stream())
 
 
-def layernorm_bwd(dy, x, mean, rstd, gamma, dx, accumulate, dgamma, dbeta, dx_bf16=None, dx_colsum=None, colsum_scale=1.0):
+def layernorm_bwd(dy, x, mean, rstd, gamma, dx, accumulate, dgamma, dbeta, dx_copy=None, dx_colsum=None, colsum_scale=1.0,
+                  drop: Optional[Drop] = None):
     rows = x.numel() // 256
     call("eec_layernorm_bwd", ptr(dy), ptr(x), ptr(mean), ptr(rstd), ptr(gamma), ptr(dx), int(accumulate), ptr(dgamma),
-         ptr(dbeta), ptr(dx_bf16), ptr(dx_colsum), colsum_scale, rows, 256, stream())
+         ptr(dbeta), ptr(dx_copy), dt(dx_copy) if dx_copy is not None else BF16, ptr(dx_colsum), colsum_scale, *_d(drop), rows, 256,
+         stream())
 
 
-def attn_fwd(qkv, key_len, ctx, lse, B, T, H):
-    call("eec_attn_fwd", ptr(qkv), dt(qkv), ptr(key_len), ptr(ctx), ptr(lse), B, T, H, 32, stream())
+def attn_fwd(qkv, key_len, ctx, lse, B, T, H, drop: Optional[Drop] = None):
+    call("eec_attn_fwd", ptr(qkv), dt(qkv), ptr(key_len), ptr(ctx), ptr(lse), B, T, H, 32, *_d(drop), stream())
 
 
-def attn_bwd(qkv, ctx, dctx, lse, key_len, dqkv, dvec, B, T, H, dq32=None):
+def attn_bwd(qkv, ctx, dctx, lse, key_len, dqkv, dvec, B, T, H, dq32=None, drop: Optional[Drop] = None):
     call("eec_attn_bwd", ptr(qkv), ptr(ctx), ptr(dctx), dt(qkv), ptr(lse), ptr(key_len), ptr(dqkv), ptr(dvec), ptr(dq32), B, T,
-         H, 32, stream())
+         H, 32, *_d(drop), stream())
+
+
+def dropout(x, y, drop: Drop):
+    """y = x * keep_mask * 1/(1-p) for the dropout site `drop` (x, y contiguous, same numel; in place allowed)."""
+    _chk(x, "dropout.x")
+    _chk(y, "dropout.y")
+    call("eec_dropout", ptr(x), dt(x), ptr(y), dt(y), x.numel(), drop.state.data_ptr(), drop.p, drop.site, stream())
+
+
+def dropout_advance(state):
+    call("eec_dropout_advance", ptr(state), stream())
+
+
+def dropout_p_effective(p: float) -> float:
+    """the probability the kernels actually use: p quantised to 1/65536 (include/eec.h "dropout")"""
+    return min(int(p * 65536.0 + 0.5), 65535) / 65536.0
 
 
 def dwconv_bn_silu_eval(g, w, bias, bn_w, bn_b, rm, rv, out, B, T, K):

@@ -80,8 +80,25 @@ typedef struct {
   float* a_colsum;          /* weight-gradient form only (a_kmajor = 0, b_kmajor = 0, accumulate, no bias, bf16):          */
   float a_colsum_scale;     /*   a_colsum[m] += a_colsum_scale * sum_k A(m,k)  -- the bias gradient of the same layer, summed */
                             /*   from the A tiles while they sit in shared memory (no second pass over the [rows, M] tensor) */
+  /* dropout (see "dropout" below) applied right after the activation: v = act(v + bias); v = dropout(v); v = alpha * v; ...
+   * element index of (m, n) is m*N + n.  SILU / DSILU / NONE epilogues and the LayerNorm tail; drop_state NULL = off.     */
+  const uint64_t* drop_state; float drop_p; uint32_t drop_site;
 } eec_gemm_desc;
 int eec_gemm(const eec_gemm_desc* d, eec_stream_t stream);
+
+/* ---- dropout (train mode, drop_prob > 0): nn.Dropout at positional_encoding.py:72, TA:106 and TA:108 (feed-forward),
+ *      TA:73 (convolution module), TA:201 (after the attention out-projection) and the dropout nn.MultiheadAttention applies
+ *      to the attention probabilities (TA:152).  Masks are COUNTER-BASED, never stored: element i of the logical tensor at
+ *      dropout site `site` is kept iff   u16_{i%8}( Philox4x32-10( key = seed, counter = {i/8 lo, i/8 hi, site, offset} ) ) >= thr,
+ *      thr = round(p * 65536), and kept values are scaled by 65536 / (65536 - thr)  (p is quantised to 1/65536).
+ *      `state` is a DEVICE array {seed, offset}: the backward kernels regenerate the forward masks from the same
+ *      (state, site) and a CUDA-graph replay sees a new offset without being re-captured (eec_dropout_advance).
+ *      PyTorch's own RNG streams cannot be reproduced (SURVEY App. A "Dropout sites"); rate, scale and determinism can. */
+/* y[i] = x[i] * mask_i * scale  (dtype enums of x / y; x == y allowed when the dtypes agree) */
+int eec_dropout(const void* x, int in_dtype, void* y, int out_dtype, int64_t n, const uint64_t* state, float p,
+                uint32_t site, eec_stream_t stream);
+/* state[1] += 1 (one launch; lives inside the captured training step) */
+int eec_dropout_advance(uint64_t* state, eec_stream_t stream);
 
 /* ---- fused feed-forward module (TA:91-119 + half-step residual TA:185-187, 207-209 + the LayerNorm that follows:
  *      TA:151 self_attn_layer_norm after ffn1, TA:211 final_layer_norm after ffn2).  bf16 operands only (tcgen05):
@@ -98,24 +115,30 @@ int eec_ffn_fwd(const void* u, const void* w1, const float* b1, const void* w2, 
 int eec_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* out, int out_dtype,
                       float* mean, float* rstd, int rows, int d, eec_stream_t stream);
 /* dx (+)= LN'(dy); dgamma += sum dy*xhat; dbeta += sum dy  (dgamma/dbeta accumulate);
- * dx_bf16 (optional): bf16 copy of the final dx (operand of the next dgrad/wgrad GEMM);
- * dx_colsum (optional): dx_colsum[c] += colsum_scale * sum_rows dx[:,c]  (the bias gradient of the
- * projection that precedes this LayerNorm's residual branch in the forward pass) */
+ * dx_copy (optional, dtype dx_copy_dtype): copy of the final dx as the operand of the next dgrad/wgrad GEMM;
+ * dx_colsum (optional): dx_colsum[c] += colsum_scale * sum_rows dx_copy[:,c]  (the bias gradient of the
+ * projection that precedes this LayerNorm's residual branch in the forward pass);
+ * drop_state != NULL: that projection's output went through dropout (site drop_site, element index r*256 + c) before
+ * joining the residual stream, so dx_copy and dx_colsum receive dropout'(dx) = dx * mask * scale (dx itself does not). */
 int eec_layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd,
                       const float* gamma, float* dx, int dx_accumulate, float* dgamma, float* dbeta,
-                      void* dx_bf16, float* dx_colsum, float colsum_scale, int rows, int d,
+                      void* dx_copy, int dx_copy_dtype, float* dx_colsum, float colsum_scale,
+                      const uint64_t* drop_state, float drop_p, uint32_t drop_site, int rows, int d,
                       eec_stream_t stream);
 
 /* ---- multi-head self-attention core (nn.MultiheadAttention SDPA branch, TA:194-200) -
  * qkv [B*T, 3*H*dh] rows = [q | k | v], head h = columns [h*dh, (h+1)*dh) of each third.
- * keys t' >= key_len[b] are masked; fully-masked rows produce 0.  lse [B,H,T] (natural log). */
+ * keys t' >= key_len[b] are masked; fully-masked rows produce 0.  lse [B,H,T] (natural log).
+ * drop_state != NULL: dropout on the attention probabilities (after the softmax, before the product with V);
+ * element index of probability (b, h, t, t') is ((b*H + h)*T + t) * (8*ceil(T/8)) + t'. */
 int eec_attn_fwd(const void* qkv, int dtype, const int32_t* key_len, void* ctx, float* lse,
-                 int B, int T, int H, int dh, eec_stream_t stream);
+                 int B, int T, int H, int dh, const uint64_t* drop_state, float drop_p, uint32_t drop_site,
+                 eec_stream_t stream);
 /* dvec: fp32 workspace [B*H*T] (row dots dO.O); dq32: fp32 workspace [B*T, H*dh] (bf16 path: dQ
  * partials of the key blocks are summed there with vector atomics; may be NULL for EEC_F32) */
 int eec_attn_bwd(const void* qkv, const void* ctx, const void* dctx, int dtype, const float* lse,
                  const int32_t* key_len, void* dqkv, float* dvec, float* dq32, int B, int T, int H, int dh,
-                 eec_stream_t stream);
+                 const uint64_t* drop_state, float drop_p, uint32_t drop_site, eec_stream_t stream);
 
 /* ---- conformer convolution module interior (TA:52-65) ------------------------------
  * g [B,T,C] (dtype) -> depthwise conv k (SAME, zero pad per utterance) + bias.

@@ -183,14 +183,30 @@ def encoder_lengths(lengths: Tensor, t_out: int) -> Tensor:
     return torch.clamp(lengths / 4, max=t_out).to(torch.int)
 
 
-def ffn(x: Tensor, sd, p: str) -> Tensor:
-    """TA:102-109: LN -> Linear(d,F) -> SiLU -> Linear(F,d) (dropout = identity here)."""
+# Dropout sites (train mode, drop_prob > 0).  The reference draws its masks from torch's RNG, which no other implementation
+# can reproduce; the oracle therefore takes the masks as an INPUT: `drop(site, shape, row_stride=None)` returns the
+# keep-mask already multiplied by 1/(1-p) (oracle/philox_dropout.Masks restates the product's counter-based generator).
+# Site ids: 0 = after the positional encoding (pos_enc.py:72); layer uid u (main stack: e*L + l, Splitformer branch i:
+# 1000 + i) owns sites 8*(u+1) + k with k = the S_* constants below (the nn.Dropout modules of TA:106/108, TA:152, TA:201, TA:73).
+S_FFN1_ACT, S_FFN1_OUT, S_ATTN_P, S_ATTN_OUT, S_CONV_OUT, S_FFN2_ACT, S_FFN2_OUT = range(7)
+
+
+def _drop(x: Tensor, drop, site: Optional[int], row_stride: Optional[int] = None) -> Tensor:
+    if drop is None or site is None:
+        return x
+    return x * torch.as_tensor(drop(site, tuple(x.shape), row_stride)).to(x.dtype)
+
+
+def ffn(x: Tensor, sd, p: str, drop=None, s_act: Optional[int] = None, s_out: Optional[int] = None) -> Tensor:
+    """TA:102-109: LN -> Linear(d,F) -> SiLU -> Dropout -> Linear(F,d) -> Dropout."""
     u = layer_norm(x, sd[p + "sequential.0.weight"], sd[p + "sequential.0.bias"])
     h = u @ sd[p + "sequential.1.weight"].T + sd[p + "sequential.1.bias"]
-    return silu(h) @ sd[p + "sequential.4.weight"].T + sd[p + "sequential.4.bias"]
+    a = _drop(silu(h), drop, s_act)
+    return _drop(a @ sd[p + "sequential.4.weight"].T + sd[p + "sequential.4.bias"], drop, s_out)
 
 
-def mhsa(x: Tensor, key_len: Tensor, sd, p: str, n_head: int) -> Tensor:
+def mhsa(x: Tensor, key_len: Tensor, sd, p: str, n_head: int, drop=None, s_p: Optional[int] = None,
+         s_out: Optional[int] = None) -> Tensor:
     """TA:192-202 -> nn.MultiheadAttention: packed in-proj, per-head softmax(QK^T/sqrt(dh)
     + key-padding mask) V, out-proj.  Keys t' >= key_len[b] get -inf; a fully masked row
     yields 0 (torch 2.11 CPU SDPA behaviour)."""
@@ -210,11 +226,12 @@ def mhsa(x: Tensor, key_len: Tensor, sd, p: str, n_head: int) -> Tensor:
     e = torch.exp(s - m)
     den = e.sum(-1, keepdim=True)
     pr = torch.where(den > 0, e / torch.where(den > 0, den, torch.ones_like(den)), torch.zeros_like(e))
+    pr = _drop(pr, drop, s_p, row_stride=8 * ((T + 7) // 8))  # MultiheadAttention(dropout=p): on the probabilities (TA:152)
     o = (pr @ v).transpose(1, 2).reshape(B, T, D)
-    return o @ sd[p + "self_attn.out_proj.weight"].T + sd[p + "self_attn.out_proj.bias"]
+    return _drop(o @ sd[p + "self_attn.out_proj.weight"].T + sd[p + "self_attn.out_proj.bias"], drop, s_out)  # TA:201
 
 
-def conv_module(x: Tensor, sd, p: str, training: bool, bn_out: Optional[dict]) -> Tensor:
+def conv_module(x: Tensor, sd, p: str, training: bool, bn_out: Optional[dict], drop=None, s_out: Optional[int] = None) -> Tensor:
     """TA:42-75, 85-88: LN -> pw conv d->2d -> GLU -> depthwise conv k (SAME, zero pad per
     utterance) -> BatchNorm1d (train: batch stats over all B*T frames incl. padding;
     eval: running stats) -> SiLU -> pw conv d->d."""
@@ -241,15 +258,16 @@ def conv_module(x: Tensor, sd, p: str, training: bool, bn_out: Optional[dict]) -
     else:
         mean, var = sd[q + "sequential.3.running_mean"], sd[q + "sequential.3.running_var"]
     nrm = (c - mean) / torch.sqrt(var + BN_EPS) * gam + bet
-    return silu(nrm) @ sd[q + "sequential.5.weight"][:, :, 0].T + sd[q + "sequential.5.bias"]
+    return _drop(silu(nrm) @ sd[q + "sequential.5.weight"][:, :, 0].T + sd[q + "sequential.5.bias"], drop, s_out)  # TA:73
 
 
-def conformer_layer(x, key_len, sd, p, n_head, training=False, bn_out=None) -> Tensor:
+def conformer_layer(x, key_len, sd, p, n_head, training=False, bn_out=None, drop=None, uid: int = 0) -> Tensor:
     """TA:176-212 with convolution_first=False: FFN/2 -> MHSA -> conv -> FFN/2 -> LN."""
-    x = x + 0.5 * ffn(x, sd, p + "ffn1.")
-    x = x + mhsa(x, key_len, sd, p, n_head)
-    x = x + conv_module(x, sd, p, training, bn_out)
-    x = x + 0.5 * ffn(x, sd, p + "ffn2.")
+    base = 8 * (uid + 1)
+    x = x + 0.5 * ffn(x, sd, p + "ffn1.", drop, base + S_FFN1_ACT, base + S_FFN1_OUT)
+    x = x + mhsa(x, key_len, sd, p, n_head, drop, base + S_ATTN_P, base + S_ATTN_OUT)
+    x = x + conv_module(x, sd, p, training, bn_out, drop, base + S_CONV_OUT)
+    x = x + 0.5 * ffn(x, sd, p + "ffn2.", drop, base + S_FFN2_ACT, base + S_FFN2_OUT)
     return layer_norm(x, sd[p + "final_layer_norm.weight"], sd[p + "final_layer_norm.bias"])
 
 
@@ -269,12 +287,16 @@ def early_conformer_forward(
     bn_out: Optional[dict] = None,
     splitformer: bool = False,
     return_hidden: bool = False,
+    drop=None,
 ):
     """early_exit.py:617-634 (Early_conformer) / :299-364 (Splitformer).
     src (B,n_mels,T_in), lengths (B,) int64 fbank frame counts -> (E,B,T',V) log-probs."""
     x = conv_subsample(src, sd)
     B, T, D = x.shape
     x = x + sd["positional_encoder.pe"][:T, 0, :].to(x.dtype)  # pos_enc.py:70-72
+    if not training:
+        drop = None
+    x = _drop(x, drop, 0)  # pos_enc.py:72
     key_len = encoder_lengths(lengths, T)
     if int(key_len.max()) < T:
         # TA:11-14 builds a mask of width max(length); nn.MultiheadAttention then asserts
@@ -285,15 +307,16 @@ def early_conformer_forward(
     outs, hidden = [], []
     for e in range(n_exits):
         x_in = x
-        for l in range(_count_layers(sd, f"conformer.{e}.")):
-            x = conformer_layer(x, key_len, sd, f"conformer.{e}.conformer_layers.{l}.", n_head, training, bn_out)
+        n_l = _count_layers(sd, f"conformer.{e}.")
+        for l in range(n_l):
+            x = conformer_layer(x, key_len, sd, f"conformer.{e}.conformer_layers.{l}.", n_head, training, bn_out, drop, e * n_l + l)
         if splitformer and (e == 0 or e == n_exits - 1):
             i = e // (n_exits - 1)
             pad = T % 2
             xd = F.pad(x_in, (0, 0, 0, pad)) if pad else x_in  # early_exit.py:318-327
             xd = xd[:, ::2, :]  # :329-331
             len2 = torch.clamp((lengths + pad) / 2, max=xd.shape[1]).to(torch.int)  # :332-338 (raw lengths!)
-            xd = conformer_layer(xd, len2, sd, f"conformer_parallel.{i}.conformer_layers.0.", n_head, training, bn_out)
+            xd = conformer_layer(xd, len2, sd, f"conformer_parallel.{i}.conformer_layers.0.", n_head, training, bn_out, drop, 1000 + i)
             xd = torch.repeat_interleave(xd, 2, dim=1)  # :344-346
             if pad:
                 xd = xd[:, :-pad, :]

@@ -111,6 +111,147 @@ def run_case(name, kind, n_exits, n_layers, B, t_in, lo, hi, seed):
     print(name, "T'=", T, "loss=", loss.item(), os.path.getsize(path) // 1024, "KiB")
 
 
+# --------------------------------------------------------------------------- #
+# train mode WITH dropout (the reference's default --drop_prob 0.1, util/conf.py:283-291)
+# --------------------------------------------------------------------------- #
+DROP_CASES = {
+    # name: (model, n_exits, n_layers, B, T_in, target lo/hi, p, dropout seed)
+    "ecdrop_e2l2_b3_t203": ("early_conformer", 2, 2, 3, 203, 3, 8, 0.1, 31337),
+    "sfdrop_e2l1_b3_t166": ("splitformer", 2, 1, 3, 166, 3, 8, 0.1, 4242),
+}
+
+
+class ReferenceDropoutPatch:
+    """Runs the UNMODIFIED reference with its random draws replaced by given masks.  torch's RNG streams cannot be matched by
+    another implementation, so the parity question for dropout is: given the same keep-masks at the same places, does the
+    product compute what the reference computes?  Every mask the reference consumes goes through two functions:
+    ``torch.nn.functional.dropout`` (all nn.Dropout modules) and ``torch.nn.functional.scaled_dot_product_attention`` (the
+    dropout_p of nn.MultiheadAttention, need_weights=False branch, TORCH:nn/functional.py:6670-6695).  Both are patched
+    for the duration of one forward; the k-th call is mapped to the product's documented site id and the mask
+    (oracle/philox_dropout.Masks, element order (b, t, channel)) is permuted into the layout the reference holds there:
+      site 0            positional_encoding.py:72        (B, T, D)
+      layer sites 0,1   TA:106, TA:108 (ffn1)            (T, B, F) / (T, B, D)
+      layer site  2     SDPA probabilities (TA:152)      (B, H, T, T), rows of stride 8*ceil(T/8)
+      layer site  3     TA:201 self_attn_dropout         (T, B, D)
+      layer site  4     TA:73 conv-module dropout        (B, D, T)
+      layer sites 5,6   TA:106, TA:108 (ffn2)            (T, B, F) / (T, B, D)
+    """
+
+    def __init__(self, masks, layer_uids):
+        self.masks, self.uids = masks, list(layer_uids)
+        self.calls = 0
+
+    def _site(self):
+        k = self.calls
+        self.calls += 1
+        if k == 0:
+            return 0, None
+        layer, j = divmod(k - 1, 7)
+        return 8 * (self.uids[layer] + 1) + j, j
+
+    def dropout(self, input, p=0.5, training=True, inplace=False):
+        if not training or p == 0.0:
+            return input
+        site, j = self._site()
+        assert j != 2, "call order drifted: expected the SDPA call here"
+        if j is None:
+            f = torch.as_tensor(self.masks(site, tuple(input.shape)))
+        elif j == 4:
+            B, D, T = input.shape
+            f = torch.as_tensor(self.masks(site, (B, T, D))).permute(0, 2, 1)
+        else:
+            T, B, C = input.shape
+            f = torch.as_tensor(self.masks(site, (B, T, C))).permute(1, 0, 2)
+        return input * f.to(input.dtype)
+
+    def sdpa(self, query, key, value, attn_mask=None, dropout_p=0.0, is_causal=False, **kw):
+        import math
+        assert not is_causal
+        s = query @ key.transpose(-1, -2) / math.sqrt(query.shape[-1])
+        if attn_mask is not None:
+            s = s.masked_fill(attn_mask, float("-inf")) if attn_mask.dtype == torch.bool else s + attn_mask
+        pr = torch.nan_to_num(torch.softmax(s, -1), nan=0.0)   # fully masked rows -> 0 (torch 2.11 CPU SDPA, SURVEY App. B 5)
+        if dropout_p > 0.0:
+            site, j = self._site()
+            assert j == 2, "call order drifted: SDPA expected at layer slot 2"
+            T = pr.shape[-1]
+            pr = pr * torch.as_tensor(self.masks(site, tuple(pr.shape), 8 * ((T + 7) // 8))).to(pr.dtype)
+        return pr @ value
+
+    def __enter__(self):
+        import torch.nn.functional as F
+        self._saved = (F.dropout, F.scaled_dot_product_attention)
+        F.dropout, F.scaled_dot_product_attention = self.dropout, self.sdpa
+        return self
+
+    def __exit__(self, *a):
+        import torch.nn.functional as F
+        F.dropout, F.scaled_dot_product_attention = self._saved
+
+
+def run_dropout_case(name, kind, n_exits, n_layers, B, t_in, lo, hi, p, dseed, seed):
+    from oracle import philox_dropout as PH
+    split = kind == "splitformer"
+    sd = O.make_params(seed, n_exits=n_exits, n_layers=n_layers, splitformer=split)
+    src, lengths = O.synthetic_batch(B, t_in, seed=seed + 1)
+    targets, tl = O.synthetic_targets(B, seed=seed + 2, lo=lo, hi=hi)
+    cls = Splitformer if split else Early_conformer
+    m = cls(src_pad_idx=0, n_enc_exits=n_exits, enc_voc_size=256, dec_voc_size=256, d_model=256, n_head=8, max_len=2000,
+            d_feed_forward=2048, n_enc_layers=n_layers, features_length=80, drop_prob=p, depthwise_kernel_size=31,
+            device=torch.device("cpu"))
+    m.load_state_dict(sd, strict=True)
+    m.train()
+    uids = []      # layer execution order of the reference forward (early_exit.py:626-631 / :305-356)
+    for e in range(n_exits):
+        uids += [e * n_layers + l for l in range(n_layers)]
+        if split and e in (0, n_exits - 1):
+            uids.append(1000 + e // (n_exits - 1))
+    # sanity of the patch itself: with p-effective 0 masks (all ones) the patched forward equals the unpatched p = 0 model
+    patch = ReferenceDropoutPatch(PH.Masks(p, dseed, 0), uids)
+    with patch:
+        lp = m(src, lengths)
+    assert patch.calls == 1 + 7 * len(uids), (patch.calls, len(uids))
+    ctc = torch.nn.CTCLoss(blank=0, zero_infinity=True)
+    in_len = torch.full((B,), lp.size(2), dtype=torch.long)
+    per = [ctc(enc.permute(1, 0, 2), targets, in_len, tl) for enc in lp]
+    loss = sum(per)
+    m.zero_grad()
+    loss.backward()
+    out = {"seed": seed, "B": B, "t_in": t_in, "n_exits": n_exits, "n_layers": n_layers, "p": p, "drop_seed": dseed,
+           "lengths": lengths.numpy(), "targets": targets.numpy(), "target_lengths": tl.numpy(),
+           "train_logprobs": lp.detach().numpy(), "loss": np.float64(loss.item()),
+           "loss_per_exit": np.array([q.item() for q in per])}
+    names, norms = [], []
+    for k, q in m.named_parameters():
+        names.append(k)
+        norms.append(q.grad.double().norm().item())
+    out["grad_names"], out["grad_norms"] = np.array(names), np.array(norms)
+    P = dict(m.named_parameters())
+    l0 = "conformer.0.conformer_layers.0."
+    for k in ["conv_subsample.sequential.1.bias", "linears.0.bias", l0 + "ffn1.sequential.1.bias", l0 + "ffn1.sequential.4.bias",
+              l0 + "self_attn.in_proj_bias", l0 + "self_attn.out_proj.bias", l0 + "conv_module.sequential.5.bias",
+              l0 + "conv_module.sequential.2.weight", l0 + "ffn2.sequential.4.bias", l0 + "final_layer_norm.weight"]:
+        out["grad::" + k] = P[k].grad.numpy()
+    out["gradslice::" + l0 + "ffn1.sequential.1.weight"] = P[l0 + "ffn1.sequential.1.weight"].grad[:8, :].numpy()
+    out["gradslice::" + l0 + "self_attn.in_proj_weight"] = P[l0 + "self_attn.in_proj_weight"].grad[::96, :].numpy()
+    out["gradslice::conv_subsample.sequential.0.weight"] = P["conv_subsample.sequential.0.weight"].grad[:4].numpy()
+    # the patch is transparent: same patched functions, p-independent all-ones masks == the unpatched reference at p = 0
+    m0 = build_reference(kind, n_exits, n_layers, sd).train()
+    m0p = cls(src_pad_idx=0, n_enc_exits=n_exits, enc_voc_size=256, dec_voc_size=256, d_model=256, n_head=8, max_len=2000,
+              d_feed_forward=2048, n_enc_layers=n_layers, features_length=80, drop_prob=p, depthwise_kernel_size=31,
+              device=torch.device("cpu"))
+    m0p.load_state_dict(sd, strict=True)
+    m0p.train()
+    with torch.no_grad():
+        a = m0(src, lengths)
+        with ReferenceDropoutPatch(lambda site, shape, row_stride=None: np.ones(shape, dtype=np.float32), uids):
+            b = m0p(src, lengths)
+    assert float((a - b).abs().max()) < 2e-5, float((a - b).abs().max())
+    path = os.path.join(ROOT, "tests", "golden", name + ".npz")
+    np.savez_compressed(path, **out)
+    print(name, "T'=", lp.shape[2], "loss=", loss.item(), "(p=0 loss differs)", os.path.getsize(path) // 1024, "KiB")
+
+
 FC_RENAME = (("linears.", "linears_1."), ("positional_encoder.", "positional_encoder_1."))
 AED_CE_WEIGHT, AED_CTC_WEIGHT = 0.7, 0.3   # util/conf.py --aed_ce_weight / --aed_ctc_weight defaults
 
@@ -205,3 +346,5 @@ if __name__ == "__main__":
         run_case(name, kind, e, l, B, t, lo, hi, seed=100 + 10 * i)
     ctc_cases()
     run_fc_case("fc_e2l1d1_b2_t163", 2, 1, 1, 2, 163, 3, 8, seed=150)
+    for i, (name, (kind, e, l, B, t, lo, hi, p, ds)) in enumerate(DROP_CASES.items()):
+        run_dropout_case(name, kind, e, l, B, t, lo, hi, p, ds, seed=200 + 10 * i)

@@ -187,8 +187,10 @@ def test_state_dict_roundtrip_and_errors():
         eec.Early_conformer(**{**kw, "n_head": 6})
     with pytest.raises(eec.EecError):
         m.eval()(torch.zeros(1, 80, 100), torch.tensor([100]))  # CPU input: no fallback
-    with pytest.raises(NotImplementedError):
-        m.train()(torch.zeros(1, 80, 100, device="cuda"), torch.tensor([100]))  # dropout > 0 in training: explicit
+    out = m.cuda().train()(torch.zeros(1, 80, 100, device="cuda"), torch.tensor([100]))  # dropout > 0 in training runs (tests/test_gpu_dropout.py)
+    assert out.shape == (6, 1, 24, 256) and torch.isfinite(out).all()
+    with pytest.raises(ValueError):
+        eec.Early_conformer(**{**kw, "drop_prob": 1.5}).cuda().train()(torch.zeros(1, 80, 100, device="cuda"), torch.tensor([100]))
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
