@@ -177,11 +177,18 @@ def run_ours(args):
     # optimiser: clip_grad_norm_ + Noam + AdamW as three launches over flat buffers, reference hyper-parameters
     opt = None if args.no_opt else eec.FusedNoamAdamW(model, model_size=256, warmup=25000, betas=(0.9, 0.98), eps=1e-9,
                                                       weight_decay=5e-4, clip=1.0)
+    # data parallel: the gradient all-reduce runs DURING backward, one exit group (21 MB) at a time on a side stream
+    # (eec.distributed.OverlappedGradReducer); the collectives are stream-ordered, so they are captured into the step's graph
+    overlap = world > 1 and not args.no_overlap
+    if overlap:
+        eec.distributed.broadcast_parameters(model, 0)
+        eec.distributed.OverlappedGradReducer(model)
+    in_graph = world == 1 or overlap      # is the whole step (incl. exchange + update) one graph?
     graphed = None
     if not args.no_graph:
-        # the whole step (forward, 6-exit CTC, backward; + the optimiser at N=1) is ONE CUDA graph: one launch per step.
-        # Under data parallelism the NCCL all-reduce sits between backward and the update, so the update stays outside.
-        graphed = eec.GraphedTrainStep(model, B, T_IN, targets.shape[1], optimizer=opt if world == 1 else None)
+        # the whole step (forward, 6-exit CTC, backward, [overlapped all-reduce,] clip + Noam + AdamW) is ONE CUDA graph.
+        # With --no-overlap the single flat-buffer all-reduce sits between the graph and an eager update.
+        graphed = eec.GraphedTrainStep(model, B, T_IN, targets.shape[1], optimizer=opt if in_graph else None)
         graphed.load_inputs(src_dev, lengths, tg_dev, tl_dev)
 
     def step(x):
@@ -194,9 +201,9 @@ def run_ours(args):
             loss = eec.multi_exit_ctc_loss(out, tg_dev, tl_dev)
             model.zero_grad(set_to_none=True)
             loss.backward()
-            if opt is not None and world == 1:
+            if opt is not None and in_graph:
                 opt.step()
-        if world > 1:
+        if not in_graph:
             dist.all_reduce(model._flat_grad, op=dist.ReduceOp.AVG)
             if opt is not None:
                 opt.step()
@@ -266,12 +273,12 @@ def run_ours(args):
     if args.drop_prob > 0 and not args.profile and graphed is not None:
         model.train()
         model.dropout = args.drop_prob
-        g2 = eec.GraphedTrainStep(model, B, T_IN, targets.shape[1], optimizer=opt if world == 1 else None)
+        g2 = eec.GraphedTrainStep(model, B, T_IN, targets.shape[1], optimizer=opt if in_graph else None)
         g2.load_inputs(src_dev, lengths, tg_dev, tl_dev)
 
         def dstep():
             loss = g2.replay()
-            if world > 1:
+            if not in_graph:
                 dist.all_reduce(model._flat_grad, op=dist.ReduceOp.AVG)
                 if opt is not None:
                     opt.step()
@@ -300,7 +307,7 @@ def run_ours(args):
             "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
             "config": {"workload": f"early_conformer CTC training step (fwd + summed 6-exit CTC + bwd), {N_EXITS} exits x {layers} "
                                    f"layers, d_model 256, batch {B}/GPU x 15 s (T_in {T_IN} -> T' {T}), grad all-reduce "
-                                   f"{'NCCL fp32 flat buffer' if world > 1 else 'n/a'}; "
+                                   f"{('NCCL fp32, per exit group, overlapped with backward inside the graph' if overlap else 'NCCL fp32 flat buffer after backward') if world > 1 else 'n/a'}; "
                                    + ("optimizer step excluded" if opt is None else "clip_grad_norm + Noam + AdamW update included (fused, flat buffers)"),
                        "global_batch": world * B, "parallelism": f"dp{world}",
                        "l2": "per-step working set ~8 GB >> 126 MB L2 (no flush needed)",
@@ -318,6 +325,9 @@ def run_ours(args):
             line["train_with_dropout"] = drop_leg
         print(json.dumps(line), file=_JSON_OUT, flush=True)
     if world > 1:
+        graphed = None          # (graphs that hold captured NCCL kernels are released before the communicator)
+        torch.cuda.synchronize()
+        dist.barrier()
         dist.destroy_process_group()
 
 
@@ -462,6 +472,8 @@ def main():
     ap.add_argument("--no-opt", action="store_true", help="time forward + loss + backward only (no clip / Noam / AdamW update)")
     ap.add_argument("--no-graph", action="store_true", help="issue the ~600 kernels of a step eagerly instead of replaying the CUDA graph")
     ap.add_argument("--skip-rtfx", action="store_true")
+    ap.add_argument("--no-overlap", action="store_true", help="N > 1: one all-reduce of the flat gradient buffer after backward "
+                    "(outside the graph) instead of per-exit-group all-reduces overlapped with backward")
     ap.add_argument("--drop-prob", type=float, default=0.1, help="extra leg: the same training step with dropout at this probability "
                     "(the reference's default); the headline step runs at 0 like the parity tests (SURVEY 8d). 0 skips the leg")
     ap.add_argument("--profile", action="store_true", help="bracket the timed region with cudaProfilerStart/Stop (for ncu "

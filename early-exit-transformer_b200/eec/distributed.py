@@ -45,9 +45,66 @@ def all_reduce_flat(flat: torch.Tensor, average: bool = True) -> torch.Tensor:
     return flat
 
 
+class OverlappedGradReducer:
+    """All-reduce of the gradients DURING backward, one exit group at a time, on a side stream.
+
+        red = eec.distributed.OverlappedGradReducer(model)      # once, after dist.init_process_group
+        loss.backward()                                         # gradients are already averaged when this returns
+        optimizer.step()
+
+    The engine's backward finishes the exit groups last-to-first and calls `on_ready(flat, lo, hi)` when a group's slice of the
+    flat fp32 gradient buffer is final (12 layers / 6 exits: 21 MB per group, then 1.3 MB of front end + heads): the slice is
+    all-reduced over NCCL on `self.stream` while the earlier groups are still being differentiated on the compute stream;
+    `finish()` (called by the engine at the end of backward) joins the two streams, so `clip_grad_norm_` / the optimiser see
+    the complete, averaged buffer.  Everything is stream-ordered with no host synchronisation, so `GraphedTrainStep` captures
+    the collectives as parallel branches of the step's CUDA graph: a data-parallel step is still ONE graph launch.
+    BatchNorm statistics stay per rank.  With CPU tensors (gloo tests) the reduction is issued in line."""
+
+    def __init__(self, model: torch.nn.Module, average: bool = True, group=None):
+        self.average, self.group = average, group
+        p = next(model.parameters())
+        self.stream = torch.cuda.Stream(device=p.device) if p.is_cuda else None
+        self._forked = False
+        self.calls = 0            # slices reduced since construction (tests / bench report it)
+        model.__dict__["_grad_reducer"] = self
+
+    def _reduce(self, t: torch.Tensor) -> None:
+        if self.average and dist.get_backend(self.group) == "nccl":
+            dist.all_reduce(t, op=dist.ReduceOp.AVG, group=self.group)
+        else:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+            if self.average:
+                t.div_(dist.get_world_size(self.group))
+
+    def on_ready(self, flat: torch.Tensor, lo: int, hi: int) -> None:
+        if hi <= lo or not dist.is_initialized() or dist.get_world_size(self.group) == 1:
+            return
+        self.calls += 1
+        sl = flat[lo:hi]
+        if self.stream is None or not flat.is_cuda:
+            self._reduce(sl)
+            return
+        self.stream.wait_stream(torch.cuda.current_stream(flat.device))   # the slice is final on the compute stream
+        with torch.cuda.stream(self.stream):
+            self._reduce(sl)
+        self._forked = True
+
+    def finish(self) -> None:
+        if self._forked:
+            torch.cuda.current_stream(self.stream.device).wait_stream(self.stream)
+            self._forked = False
+
+    def remove(self, model: torch.nn.Module) -> None:
+        if model.__dict__.get("_grad_reducer") is self:
+            del model.__dict__["_grad_reducer"]
+
+
 def all_reduce_gradients(model: torch.nn.Module, average: bool = True) -> None:
     """Call after `loss.backward()`.  Uses the engine's flat buffer when present (one collective); falls back
-    to flattening `p.grad` (e.g. for a model that was not run through eec in this step)."""
+    to flattening `p.grad` (e.g. for a model that was not run through eec in this step).  A no-op when an
+    OverlappedGradReducer is installed on the model: backward has already averaged the gradients."""
+    if model.__dict__.get("_grad_reducer") is not None:
+        return
     flat = model.__dict__.get("_flat_grad")
     params = [p for p in model.parameters() if p.grad is not None]
     if flat is not None and params and params[0].grad.data_ptr() == flat.data_ptr():

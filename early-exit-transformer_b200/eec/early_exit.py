@@ -134,8 +134,12 @@ class _EncoderFn(torch.autograd.Function):
             raise NotImplementedError("eec: backward is only supported in train() mode with grad enabled "
                                       "(eval-mode BatchNorm backward is not implemented)")
         names = m._param_names
+        red = m.__dict__.get("_grad_reducer")     # eec.distributed.OverlappedGradReducer: per-exit-group all-reduce during backward
         G = engine.model_backward(ctx.P, m._operands, ctx.cfg, ctx.tape, gout, names,
-                                  ghid.contiguous() if ctx.want_hidden and ghid is not None else None)
+                                  ghid.contiguous() if ctx.want_hidden and ghid is not None else None,
+                                  on_ready=red.on_ready if red is not None else None)
+        if red is not None:
+            red.finish()
         ctx.tape = None
         m.__dict__["_flat_grad"] = G["__flat__"]  # p.grad tensors are views of this buffer (DP all-reduces it once)
         return (None, None, None, None, None, None) + tuple(G[n] for n in names)

@@ -476,10 +476,31 @@ def model_forward(P: Dict[str, Tensor], W: Operands, cfg: Config, src: Tensor, l
     return out, tape
 
 
+def group_ranges(P, names: List[str], n_exits: int):
+    """[lo, hi) of every exit group's parameters inside the flat gradient buffer (layout = `names` order), or None when a
+    group is not contiguous there.  Backward finishes the groups last-to-first: each slice can leave for the data-parallel
+    all-reduce while the earlier groups are still being differentiated."""
+    off, spans = 0, {}
+    for n in names:
+        k = P[n].numel()
+        if n.startswith("conformer."):
+            e = int(n.split(".")[1])
+            lo, hi = spans.get(e, (off, off))
+            if hi != off:
+                return None
+            spans[e] = (lo, off + k)
+        off += k
+    if sorted(spans) != list(range(n_exits)):
+        return None
+    return [spans[e] for e in range(n_exits)], off
+
+
 def model_backward(P, W: Operands, cfg: Config, tape: Tape, gout: Tensor, names: List[str],
-                   ghid: Optional[Tensor] = None) -> Dict[str, Tensor]:
+                   ghid: Optional[Tensor] = None, on_ready=None) -> Dict[str, Tensor]:
     """gout: grad wrt out [E,B,T,V] (fp32); ghid (optional): grad wrt the per-exit encoder states [E,B,T,D]
-    (the decoders' cross-attention in AED mode).  Returns fp32 grads for every name in `names`."""
+    (the decoders' cross-attention in AED mode).  Returns fp32 grads for every name in `names`.
+    on_ready(flat, lo, hi) (optional) is called as soon as flat[lo:hi] holds final gradients (one exit group at a time,
+    then the rest): the data-parallel reducer's hook (eec.distributed.OverlappedGradReducer)."""
     dev, f32 = gout.device, torch.float32
     gout = gout.contiguous()
     B, T = tape.B, tape.T
@@ -494,6 +515,7 @@ def model_backward(P, W: Operands, cfg: Config, tape: Tape, gout: Tensor, names:
         G[n] = flat[off:off + k].view(P[n].shape)
         off += k
     G["__flat__"] = flat
+    spans = group_ranges(P, names, E) if on_ready is not None else None
     dX: Optional[Tensor] = None
     li = len(tape.layers)
     for e in reversed(range(E)):
@@ -525,5 +547,16 @@ def model_backward(P, W: Operands, cfg: Config, tape: Tape, gout: Tensor, names:
             dX = layer_backward(P, W, G, lt["pre"], lt, dX, cfg)
         if d_in_extra is not None:
             ops.stride2_scatter_add(d_in_extra, dX, B, T)
+        if spans is not None:
+            on_ready(flat, *spans[0][e])
     frontend_backward(P, W, G, tape.front, dX, cfg)
+    if on_ready is not None:
+        if spans is None:
+            on_ready(flat, 0, total)
+        else:   # what is not an exit group: front end + heads (before the groups), Splitformer branches (after)
+            lo0, hi0 = spans[0][0][0], spans[0][-1][1]
+            if lo0 > 0:
+                on_ready(flat, 0, lo0)
+            if hi0 < total:
+                on_ready(flat, hi0, total)
     return G

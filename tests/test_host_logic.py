@@ -179,3 +179,52 @@ def test_dropin_rebinds_reference_classes():
         for k in [k for k in sys.modules if k == "models" or k.startswith("models.")]:
             del sys.modules[k]
         importlib.invalidate_caches()
+
+
+def _overlap_worker(rank, world, port, q):
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "early-exit-transformer_b200"))
+    import torch.distributed as dist
+    import eec
+    from eec import distributed as D, engine
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    kw = dict(src_pad_idx=0, n_enc_exits=3, enc_voc_size=256, dec_voc_size=256, d_model=256, n_head=8, max_len=2000,
+              d_feed_forward=2048, n_enc_layers=1, features_length=80, drop_prob=0.0, depthwise_kernel_size=31, device="cpu")
+    m = eec.Splitformer(**kw)       # host mirror only (no kernels run on the CPU): parameter layout of the flat gradient buffer
+    names = m._param_names
+    P = m._tensor_dict()
+    spans, total = engine.group_ranges(P, names, 3)
+    flat = torch.arange(total, dtype=torch.float32) * (rank + 1)
+    red = D.OverlappedGradReducer(m)
+    seen = []
+    # replay the order engine.model_backward issues: groups last to first, then what is not an exit group
+    for e in reversed(range(3)):
+        red.on_ready(flat, *spans[e])
+        seen.append(spans[e])
+    lo0, hi0 = spans[0][0], spans[-1][1]
+    red.on_ready(flat, 0, lo0)
+    red.on_ready(flat, hi0, total)
+    red.finish()
+    D.all_reduce_gradients(m)       # must be a no-op now (would average a second time otherwise: same values, so check calls)
+    q.put((rank, total, spans, (lo0, hi0), red.calls, bool(torch.allclose(flat, torch.arange(total, dtype=torch.float32) * 1.5))))
+    dist.destroy_process_group()
+
+
+def test_overlapped_grad_reducer_world2_gloo():
+    """Per-exit-group all-reduce (eec.distributed.OverlappedGradReducer) covers the flat gradient buffer exactly once."""
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_overlap_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=180) for _ in range(world)], key=lambda x: x[0])
+    for p in procs:
+        p.join(30)
+        assert p.exitcode == 0
+    for rank, total, spans, (lo0, hi0), calls, ok in res:
+        assert ok and calls == 5
+        assert spans[0][1] == spans[1][0] and spans[1][1] == spans[2][0]          # groups are contiguous and ordered
+        assert lo0 > 0 and hi0 < total                                               # front end + heads before, Splitformer branches after
+        assert all(hi - lo == spans[0][1] - spans[0][0] for lo, hi in spans)
