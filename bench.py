@@ -88,16 +88,17 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def synthetic_state_dict(layers_per_exit):
+def synthetic_state_dict(layers_per_exit, splitformer=False):
     """Random-init weights of the named architecture: the host-side mirror of the reference class is built on
     the CPU under torch.manual_seed(0) (same default init as the reference's ctor), every >= 2-D `.weight` of a leaf module gets
     Xavier-uniform like util/model_utils.py:10-12 (model.apply(initialize_weights), train.py:229-230), and 1-D parameters /
     BatchNorm buffers are randomised so that no scale or shift is a no-op.  No CUDA work, nothing from oracle/."""
     import eec
     torch.manual_seed(0)
-    m = eec.Early_conformer(src_pad_idx=0, n_enc_exits=N_EXITS, enc_voc_size=256, dec_voc_size=256, d_model=256, n_head=8,
-                            max_len=2000, d_feed_forward=2048, n_enc_layers=layers_per_exit, features_length=N_MELS,
-                            drop_prob=0.0, depthwise_kernel_size=31, device=torch.device("cpu"))
+    cls = eec.Splitformer if splitformer else eec.Early_conformer
+    m = cls(src_pad_idx=0, n_enc_exits=N_EXITS, enc_voc_size=256, dec_voc_size=256, d_model=256, n_head=8,
+            max_len=2000, d_feed_forward=2048, n_enc_layers=layers_per_exit, features_length=N_MELS,
+            drop_prob=0.0, depthwise_kernel_size=31, device=torch.device("cpu"))
     g = torch.Generator().manual_seed(0)
     with torch.no_grad():
         for mod in m.modules():
@@ -116,12 +117,13 @@ def synthetic_state_dict(layers_per_exit):
     return {k: v.detach().clone() for k, v in m.state_dict().items()}
 
 
-def build_model(layers_per_exit, precision, device):
+def build_model(layers_per_exit, precision, device, splitformer=False):
     import eec
-    m = eec.Early_conformer(src_pad_idx=0, n_enc_exits=N_EXITS, enc_voc_size=256, dec_voc_size=256, d_model=256, n_head=8,
-                            max_len=2000, d_feed_forward=2048, n_enc_layers=layers_per_exit, features_length=N_MELS,
-                            drop_prob=0.0, depthwise_kernel_size=31, device=device)
-    m.load_state_dict(synthetic_state_dict(layers_per_exit), strict=True)
+    cls = eec.Splitformer if splitformer else eec.Early_conformer
+    m = cls(src_pad_idx=0, n_enc_exits=N_EXITS, enc_voc_size=256, dec_voc_size=256, d_model=256, n_head=8,
+            max_len=2000, d_feed_forward=2048, n_enc_layers=layers_per_exit, features_length=N_MELS,
+            drop_prob=0.0, depthwise_kernel_size=31, device=device)
+    m.load_state_dict(synthetic_state_dict(layers_per_exit, splitformer), strict=True)
     m = m.to(device)
     m.precision = precision
     return m
@@ -261,11 +263,12 @@ def run_ours(args):
         ms_e2e = timed(e2e_step, args.steps)
 
     # inference RTFx per exit (BASELINE metric part (i)): forward truncated after exit e, bf16, eval
-    rtfx = None
+    rtfx = ee_leg = None
     if rank == 0 and not args.skip_rtfx and not args.profile:
         audio_s = float(lengths.sum()) * FRAME_S
         rtfx = rtfx_per_exit(model, src_dev, lengths, audio_s, use_graph=not args.no_graph)
         model.train()
+        ee_leg = early_exit_leg(layers, args.precision, dev, src_dev, lengths, audio_s) if not args.no_graph else None
 
     # the same step at the reference's DEFAULT --drop_prob 0.1 (util/conf.py:283-291): fused counter-based dropout at all
     # seven sites per layer + after the positional encoding, masks regenerated in backward (nothing stored)
@@ -323,6 +326,8 @@ def run_ours(args):
             line["rtfx_per_exit"] = rtfx
         if drop_leg is not None:
             line["train_with_dropout"] = drop_leg
+        if ee_leg is not None:
+            line["early_exit_inference"] = ee_leg
         print(json.dumps(line), file=_JSON_OUT, flush=True)
     if world > 1:
         graphed = None          # (graphs that hold captured NCCL kernels are released before the communicator)
@@ -361,6 +366,40 @@ def rtfx_per_exit(model, src_dev, lengths, audio_s, use_graph=True):
             ms = ev0.elapsed_time(ev1) / 5
             res.append({"exit": e, "ms": round(ms, 3), "rtfx": round(audio_s / (ms / 1e3), 1)})
     return res
+
+
+def early_exit_leg(layers, precision, dev, src_dev, lengths, audio_s):
+    """BASELINE configs[3]: Splitformer CTC inference with dynamic early exit and on-device batch compaction, one CUDA graph.
+    Random-init weights have no meaningful confidence, so the threshold is set from the measured entropies such that about half
+    of the utterances leave within the first three exits: the leg measures the MECHANISM (exit decision, compaction, later
+    layers skipping finished rows without a host sync), not an accuracy/latency trade-off."""
+    import eec
+    m = build_model(layers, precision, dev, splitformer=True).eval()
+    with torch.no_grad():
+        _, _, _, H = m.forward_early_exit(src_dev, lengths, -1.0)          # nobody leaves early: mean entropies of every exit
+        thr = float(H[:3].min(dim=0).values.median())
+        ee = eec.GraphedEarlyExit(m, src_dev.shape[0], src_dev.shape[2], thr)
+        full = eec.GraphedForward(m, src_dev.shape[0], src_dev.shape[2])
+        ee(src_dev, lengths)
+        full(src_dev, lengths)
+
+        def t(run, n=10):
+            for _ in range(3):
+                run()
+            torch.cuda.synchronize()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
+            for _ in range(n):
+                run()
+            ev1.record()
+            torch.cuda.synchronize()
+            return ev0.elapsed_time(ev1) / n
+        ms_ee, ms_full = t(ee.replay), t(full.replay)
+        exit_index = ee.out[0].cpu()
+    hist = [int((exit_index == e).sum()) for e in range(N_EXITS)]
+    return {"model": f"splitformer {N_EXITS} exits x {layers} layers, batch {src_dev.shape[0]}", "criterion": "mean frame entropy < threshold",
+            "threshold": round(thr, 4), "utterances_leaving_at_exit": hist, "ms": round(ms_ee, 3), "rtfx": round(audio_s / (ms_ee / 1e3), 1),
+            "all_exits_forward_ms": round(ms_full, 3), "gpu_launches": ee.launches, "launch": "one CUDA graph replay, no host sync"}
 
 
 def roofline_dominant(dev, pk):

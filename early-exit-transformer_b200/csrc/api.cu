@@ -19,6 +19,9 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+static thread_local ActiveItems g_active = {nullptr, 0, 0};
+ActiveItems active_items() { return g_active; }
+
 static bool force_simt_gemm() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("EEC_FORCE_SIMT"); v = (e && e[0] == '1') ? 1 : 0; }
@@ -73,6 +76,12 @@ extern "C" int eec_device_ok(void) {
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return 0;
   return prop.major == 10 ? 1 : 0;
+}
+
+extern "C" int eec_set_active_items(const int32_t* n_items_dev, int rows_per_item, int pad_items) {
+  EEC_CHECK_ARG(n_items_dev == nullptr || (rows_per_item > 0 && pad_items >= 0), "set_active_items: rows_per_item must be positive and pad_items >= 0 (got %d, %d)", rows_per_item, pad_items);
+  g_active.n_dev = n_items_dev; g_active.rows_per_item = rows_per_item; g_active.pad_items = pad_items;
+  return 0;
 }
 
 extern "C" int eec_gemm(const eec_gemm_desc* d, eec_stream_t stream) {

@@ -14,7 +14,8 @@ constexpr int DH = 32;
 template <typename T, bool ACC>
 __global__ void __launch_bounds__(128) attn_fwd_simt_kernel(const T* __restrict__ qkv, const int32_t* __restrict__ key_len,
                                                            T* __restrict__ ctx, float* __restrict__ lse, int Tn, int H,
-                                                           const DropArgs drop) {
+                                                           const DropArgs drop, const ActiveItems act_items) {
+  if (act_items.n_dev && (int)blockIdx.z >= active_count(act_items)) return;
   __shared__ float Ks[KC][DH + 1];
   __shared__ float Vs[KC][DH];
   DropKey dkey{};
@@ -281,9 +282,9 @@ extern "C" int eec_attn_fwd(const void* qkv, int dtype, const int32_t* key_len, 
   if (dtype == EEC_BF16 && !force_simt() && attn_tc_ready()) return attn_fwd_tc(qkv, key_len, ctx, lse, B, T, H, dh, drop, S(stream));
   dim3 grid(cdiv(T, QB), H, B);
   if (dtype == EEC_F32)
-    attn_fwd_simt_kernel<float, true><<<grid, 128, 0, S(stream)>>>((const float*)qkv, key_len, (float*)ctx, lse, T, H, drop);
+    attn_fwd_simt_kernel<float, true><<<grid, 128, 0, S(stream)>>>((const float*)qkv, key_len, (float*)ctx, lse, T, H, drop, active_items());
   else
-    attn_fwd_simt_kernel<__nv_bfloat16, false><<<grid, 128, 0, S(stream)>>>((const __nv_bfloat16*)qkv, key_len, (__nv_bfloat16*)ctx, lse, T, H, drop);
+    attn_fwd_simt_kernel<__nv_bfloat16, false><<<grid, 128, 0, S(stream)>>>((const __nv_bfloat16*)qkv, key_len, (__nv_bfloat16*)ctx, lse, T, H, drop, active_items());
   EEC_LAUNCH_CHECK();
   return 0;
 }

@@ -39,9 +39,10 @@ template <bool DROP>
 __global__ void __launch_bounds__(AT_THREADS, 2) attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv,
                                                                  const int32_t* __restrict__ key_len,
                                                                  __nv_bfloat16* __restrict__ ctx, float* __restrict__ lse,
-                                                                 int T, int H, const DropArgs drop) {
+                                                                 int T, int H, const DropArgs drop, const ActiveItems act_items) {
   pdl_trigger();
   pdl_wait();
+  if (act_items.n_dev && (int)blockIdx.z >= active_count(act_items)) return;   // utterance past the active-item limit (whole CTA, before any barrier)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;
@@ -242,8 +243,8 @@ int attn_fwd_tc(const void* qkv, const int32_t* key_len, void* ctx, float* lse, 
     attr_set = true;
   }
   dim3 grid(cdiv(T, QT), H, B);
-  if (drop.state) launch_pdl(attn_fwd_tc_kernel<true>, dim3(grid), dim3(AT_THREADS), AT_SMEM, st, tm, key_len, (__nv_bfloat16*)ctx, lse, T, H, drop);
-  else launch_pdl(attn_fwd_tc_kernel<false>, dim3(grid), dim3(AT_THREADS), AT_SMEM, st, tm, key_len, (__nv_bfloat16*)ctx, lse, T, H, drop);
+  if (drop.state) launch_pdl(attn_fwd_tc_kernel<true>, dim3(grid), dim3(AT_THREADS), AT_SMEM, st, tm, key_len, (__nv_bfloat16*)ctx, lse, T, H, drop, active_items());
+  else launch_pdl(attn_fwd_tc_kernel<false>, dim3(grid), dim3(AT_THREADS), AT_SMEM, st, tm, key_len, (__nv_bfloat16*)ctx, lse, T, H, drop, active_items());
   EEC_LAUNCH_CHECK();
   return 0;
 }

@@ -182,6 +182,20 @@ __device__ __forceinline__ float drop_factor1(const DropKey& k, const DropArgs& 
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 static inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
+// ---- active-item limit (early-exit inference with batch compaction; include/eec.h eec_set_active_items) ----------------
+// When set, the inference kernels process only the first *n_dev utterances (= *n_dev * rows_per_item leading rows of every
+// frame-major tensor): tiles / rows / utterance blocks past that limit return immediately.  The count lives on the DEVICE
+// (eec_exit_select updates it), so no host synchronisation and no re-capture of a CUDA graph is needed when it changes.
+// pad_items extra utterances past the count are still processed: the tcgen05 attention loads 128-row K/V tiles that overhang into the
+// next utterance's rows (masked in the softmax, but 0 x NaN = NaN in P.V), so the rows right behind the last survivor must hold
+// finite numbers -- one padding utterance (T' >= 128 rows) of stale-but-finite data guarantees that.
+struct ActiveItems { const int32_t* n_dev; int rows_per_item; int pad_items; };
+ActiveItems active_items();
+__device__ __forceinline__ int active_count(const ActiveItems& a) { return *a.n_dev + a.pad_items; }
+__device__ __forceinline__ int active_rows(const ActiveItems& a, int rows) {
+  return a.n_dev ? min(rows, active_count(a) * a.rows_per_item) : rows;
+}
+
 // backends implemented in separate translation units
 int gemm_simt(const eec_gemm_desc* d, cudaStream_t st);
 int gemm_tc(const eec_gemm_desc* d, cudaStream_t st, int32_t* argmax, float* entropy, int logsoftmax);   // v1 (EEC_GEMM_V1=1)

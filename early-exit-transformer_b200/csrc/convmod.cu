@@ -44,9 +44,10 @@ __global__ void __launch_bounds__(256, 3) dwconv_kernel(const TI* __restrict__ g
                                                      const float* __restrict__ bias, const float* __restrict__ bn_scale_src_w,
                                                      const float* __restrict__ bn_b, const float* __restrict__ run_mean,
                                                      const float* __restrict__ run_var, TO* __restrict__ out,
-                                                     double* __restrict__ sums, int T, int C) {
+                                                     double* __restrict__ sums, int T, int C, const ActiveItems act_items) {
   pdl_trigger();
   pdl_wait();
+  if (MODE == DW_EVAL && act_items.n_dev && (int)blockIdx.y >= active_count(act_items)) return;   // utterance past the active-item limit
   const int ch = blockIdx.z * 256 + threadIdx.x;
   const int b = blockIdx.y, t0 = blockIdx.x * TT;
   float wr[KW];
@@ -407,9 +408,9 @@ extern "C" int eec_dwconv_bn_silu_eval(const void* g, int dtype, const float* w,
                                        int T, int C, int K, eec_stream_t stream) {
   DW_ARGS_OK();
   if (dtype == EEC_F32)
-    EEC_DW_LAUNCH((dwconv_kernel<float, float, DW_EVAL>), float, (const float*)g, w, bias, bn_w, bn_b, run_mean, run_var, (float*)out, nullptr, T, C);
+    EEC_DW_LAUNCH((dwconv_kernel<float, float, DW_EVAL>), float, (const float*)g, w, bias, bn_w, bn_b, run_mean, run_var, (float*)out, nullptr, T, C, active_items());
   else
-    EEC_DW_LAUNCH((dwconv_kernel<__nv_bfloat16, __nv_bfloat16, DW_EVAL>), __nv_bfloat16, (const __nv_bfloat16*)g, w, bias, bn_w, bn_b, run_mean, run_var, (__nv_bfloat16*)out, nullptr, T, C);
+    EEC_DW_LAUNCH((dwconv_kernel<__nv_bfloat16, __nv_bfloat16, DW_EVAL>), __nv_bfloat16, (const __nv_bfloat16*)g, w, bias, bn_w, bn_b, run_mean, run_var, (__nv_bfloat16*)out, nullptr, T, C, active_items());
   EEC_LAUNCH_CHECK();
   return 0;
 }
@@ -418,9 +419,9 @@ extern "C" int eec_dwconv_stats(const void* g, int dtype, const float* w, const 
                                 int B, int T, int C, int K, eec_stream_t stream) {
   DW_ARGS_OK();
   if (dtype == EEC_F32)
-    EEC_DW_LAUNCH((dwconv_kernel<float, float, DW_STATS>), float, (const float*)g, w, bias, nullptr, nullptr, nullptr, nullptr, c, sums, T, C);
+    EEC_DW_LAUNCH((dwconv_kernel<float, float, DW_STATS>), float, (const float*)g, w, bias, nullptr, nullptr, nullptr, nullptr, c, sums, T, C, ActiveItems{nullptr, 0, 0});
   else
-    EEC_DW_LAUNCH((dwconv_kernel<__nv_bfloat16, float, DW_STATS>), __nv_bfloat16, (const __nv_bfloat16*)g, w, bias, nullptr, nullptr, nullptr, nullptr, c, sums, T, C);
+    EEC_DW_LAUNCH((dwconv_kernel<__nv_bfloat16, float, DW_STATS>), __nv_bfloat16, (const __nv_bfloat16*)g, w, bias, nullptr, nullptr, nullptr, nullptr, c, sums, T, C, ActiveItems{nullptr, 0, 0});
   EEC_LAUNCH_CHECK();
   return 0;
 }
@@ -478,11 +479,11 @@ extern "C" int eec_dwconv_bwd(const float* dc, const void* g, int dtype, const f
   EEC_CHECK_ARG(workspace != nullptr, "dwconv_bwd: workspace is NULL (eec_dwconv_bwd_workspace_bytes)");
   float* ws = reinterpret_cast<float*>(workspace);
   if (dtype == EEC_F32) {
-    EEC_DW_LAUNCH((dwconv_kernel<float, float, DW_BWD_DATA>), float, dc, w, nullptr, nullptr, nullptr, nullptr, nullptr, (float*)dg, nullptr, T, C);
+    EEC_DW_LAUNCH((dwconv_kernel<float, float, DW_BWD_DATA>), float, dc, w, nullptr, nullptr, nullptr, nullptr, nullptr, (float*)dg, nullptr, T, C, ActiveItems{nullptr, 0, 0});
     EEC_LAUNCH_CHECK();
     EEC_DW_LAUNCH((dwconv_wgrad_kernel<float>), float, dc, (const float*)g, ws, T, C);
   } else {
-    EEC_DW_LAUNCH((dwconv_kernel<float, __nv_bfloat16, DW_BWD_DATA>), float, dc, w, nullptr, nullptr, nullptr, nullptr, nullptr, (__nv_bfloat16*)dg, nullptr, T, C);
+    EEC_DW_LAUNCH((dwconv_kernel<float, __nv_bfloat16, DW_BWD_DATA>), float, dc, w, nullptr, nullptr, nullptr, nullptr, nullptr, (__nv_bfloat16*)dg, nullptr, T, C, ActiveItems{nullptr, 0, 0});
     EEC_LAUNCH_CHECK();
     EEC_DW_LAUNCH((dwconv_wgrad_kernel<__nv_bfloat16>), __nv_bfloat16, dc, (const __nv_bfloat16*)g, ws, T, C);
   }

@@ -21,6 +21,7 @@ struct SimtParams {
   int accumulate;
   int k_per_split;
   DropArgs drop;   // dropout right after the activation (element index m*N + n); state NULL = off
+  ActiveItems act_items;   // rows past the active-item limit are skipped (early-exit inference)
 };
 
 template <typename TIn, typename TOut, typename TPre, bool ACC>
@@ -31,6 +32,7 @@ __global__ void __launch_bounds__(NT) gemm_simt_kernel(SimtParams p) {
   const TIn* __restrict__ B = reinterpret_cast<const TIn*>(p.B);
   const int tid = threadIdx.x;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  if (m0 >= active_rows(p.act_items, p.M)) return;
   const int k_begin = blockIdx.z * p.k_per_split;
   const int k_end = min(p.K, k_begin + p.k_per_split);
   const int ty = tid / 16, tx = tid % 16;
@@ -158,6 +160,7 @@ int gemm_simt(const eec_gemm_desc* d, cudaStream_t st) {
   if (p.act == EEC_ACT_DSILU) EEC_CHECK_ARG(d->preact != nullptr, "gemm: DSILU needs preact");
   if (d->accumulate) EEC_CHECK_ARG(d->out_dtype == EEC_F32, "gemm: accumulate needs fp32 C");
   p.drop = make_drop(d->drop_state, d->drop_p, d->drop_site);
+  p.act_items = d->a_kmajor ? active_items() : ActiveItems{nullptr, 0, 0};   // (rows of A are frames only in the K-major forward form)
   if (p.drop.state) EEC_CHECK_ARG(!glu && !d->accumulate && d->N % 8 == 0, "gemm(simt): dropout with GLU / accumulate / N %% 8 != 0 unsupported");
   int tiles = cdiv(p.N, BN) * cdiv(p.M, BM);
   int splits = 1;

@@ -63,6 +63,7 @@ struct P3 {
   int debug;       // EEC_GEMM_DEBUG bitmask (perf triage only): 1 = no bulk store issue, 2 = no staging, 4 = no activation math
   long long* tl;   // EEC_GEMM_TL=1 (perf triage only): clock64 accumulators of CTA 0, see gemm_tc3()
   DropArgs drop;   // DROP instantiations only: dropout right after the activation, element index m*N + n
+  ActiveItems act_items;   // m-tiles past the active-item limit are skipped by all three roles (early-exit inference)
 };
 
 // per-warp staging: values -> swizzled smem box -> bulk tensor store / reduce of a [32 rows x 32 cols] box
@@ -244,12 +245,14 @@ __global__ void __launch_bounds__(NT3, 1) gemm_tc3_kernel(const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
   if (p.tl && blockIdx.x == 0 && threadIdx.x == 0) p.tl[9] = gtime();
+  const int mt_eff = (active_rows(p.act_items, p.M) + BM - 1) / BM;   // == p.m_tiles unless an active-item limit is set
 
   if (warp == 0) {
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 1;   // stage ring position + parity of the "empty" wait
       for (UnitIter ui(p); ui.u < n_units; ui.next(p)) {
+        if (ui.mt >= mt_eff) continue;
         const int m0 = ui.mt * BM;
         const int n0 = (EPI == EPI_GLU) ? ui.nt * 128 : ui.nt * BN;
         const int kb0 = ui.split * p.kb_per_split, kb1 = min(total_kb, kb0 + p.kb_per_split);
@@ -302,6 +305,7 @@ __global__ void __launch_bounds__(NT3, 1) gemm_tc3_kernel(const __grid_constant_
 #endif
       long long w_tempty = 0, w_full = 0, t_ = 0, t_begin = prof ? clock64() : 0;
       for (UnitIter ui(p); ui.u < n_units; ui.next(p), ++ut) {
+        if (ui.mt >= mt_eff) { --ut; continue; }   // (skipped units do not advance the accumulator / phase counters)
         const int kb0 = ui.split * p.kb_per_split, kb1 = min(total_kb, kb0 + p.kb_per_split);
         const uint32_t acc = ut & 1;
         if (prof) t_ = clock64();
@@ -357,6 +361,7 @@ __global__ void __launch_bounds__(NT3, 1) gemm_tc3_kernel(const __grid_constant_
     DropKey dkey{};
     if (DROP) dkey = drop_key(p.drop);
     for (UnitIter ui(p); ui.u < n_units; ui.next(p), ++ut) {
+      if (ui.mt >= mt_eff) { --ut; continue; }
       TL_STAMP(t0_); TL_ACC(e_rest, ut ? t0_ - t2_ : 0);
       const int split = ui.split;
       const int m0 = ui.mt * BM;
@@ -632,6 +637,7 @@ struct PLN {
   int has_res, ln_bf16;
   const float* ln_gamma; const float* ln_beta; float* ln_mean; float* ln_rstd;
   DropArgs drop;   // DROP instantiation only: x = residual + alpha * dropout(A W^T + bias), element index m*256 + n
+  ActiveItems act_items;
 };
 
 template <bool DROP>
@@ -675,12 +681,13 @@ __global__ void __launch_bounds__(LN_NT, 1) gemm_ln3_kernel(const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  const int m_tiles = (active_rows(p.act_items, p.M) + BM - 1) / BM;   // == p.m_tiles unless an active-item limit is set
 
   if (warp == 0) {
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 1;
-      for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x) {
+      for (int mt = blockIdx.x; mt < m_tiles; mt += gridDim.x) {
         const int m0 = mt * BM;
         for (int kb = 0; kb < total_kb; ++kb) {
           mbar_wait(&empty_bar[s], ph);
@@ -697,7 +704,7 @@ __global__ void __launch_bounds__(LN_NT, 1) gemm_ln3_kernel(const __grid_constan
       constexpr uint32_t idesc = make_idesc_bf16(BM, BN, false, false);
       uint32_t ut = 0, ph = 0;
       int s = 0;
-      for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x, ++ut) {
+      for (int mt = blockIdx.x; mt < m_tiles; mt += gridDim.x, ++ut) {
         const uint32_t acc = ut & 1;
         mbar_wait(&tempty_bar[acc], ((ut >> 1) & 1) ^ 1);
         tc_fence_after();
@@ -729,7 +736,7 @@ __global__ void __launch_bounds__(LN_NT, 1) gemm_ln3_kernel(const __grid_constan
     uint32_t ut = 0;
     DropKey dkey{};
     if (DROP) dkey = drop_key(p.drop);
-    for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x, ++ut) {
+    for (int mt = blockIdx.x; mt < m_tiles; mt += gridDim.x, ++ut) {
       const int m0 = mt * BM;
       const int row0 = m0 + q * 32;
       const int m = m0 + r;
@@ -941,6 +948,7 @@ int gemm_tc3(const eec_gemm_desc* d, cudaStream_t st) {
   EEC_CHECK_ARG(!d->a_colsum || (!d->a_kmajor && !d->b_kmajor && !d->bias && epi == EPI_GENERIC),
                 "gemm_tc3: a_colsum needs the weight-gradient form (MN-major A and B, no bias)");
   p.a_colsum = d->a_colsum; p.a_colsum_scale = d->a_colsum_scale;
+  p.act_items = (d->a_kmajor && !d->accumulate) ? active_items() : ActiveItems{nullptr, 0, 0};   // forward form only: rows of A are frames
   p.drop = make_drop(d->drop_state, d->drop_p, d->drop_site);
   if (p.drop.state)
     EEC_CHECK_ARG(epi == EPI_GENERIC && !four && d->a_kmajor && !d->accumulate && d->N % 16 == 0,
@@ -1012,6 +1020,7 @@ int gemm_ln3(const eec_gemm_desc* d, cudaStream_t st) {
   p.bias = d->bias; p.alpha = d->alpha; p.has_res = d->residual != nullptr; p.ln_bf16 = d->ln_dtype == EEC_BF16;
   p.ln_gamma = d->ln_gamma; p.ln_beta = d->ln_beta; p.ln_mean = d->ln_mean; p.ln_rstd = d->ln_rstd;
   p.drop = make_drop(d->drop_state, d->drop_p, d->drop_site);
+  p.act_items = active_items();
   static bool attr_set = false;
   if (!attr_set) {
     EEC_CUDA(cudaFuncSetAttribute(gemm_ln3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, LN_SMEM_BYTES));

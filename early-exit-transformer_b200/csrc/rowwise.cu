@@ -11,12 +11,13 @@ constexpr float LN_EPS = 1e-5f;
 template <typename TOut>
 __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                             const float* __restrict__ beta, TOut* __restrict__ out,
-                                                            float* __restrict__ mean, float* __restrict__ rstd, int rows) {
+                                                            float* __restrict__ mean, float* __restrict__ rstd, int rows,
+                                                            const ActiveItems act_items) {
   pdl_trigger();
   pdl_wait();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  if (warp >= rows) return;
+  if (warp >= active_rows(act_items, rows)) return;
   const int c0 = lane * 8;
   float v[8], g[8], b[8];
   ld8<float>(x + (long)warp * 256 + c0, v);
@@ -294,6 +295,14 @@ __global__ void dropout_advance_kernel(uint64_t* state) {
   if (threadIdx.x == 0 && blockIdx.x == 0) state[1] += 1;
 }
 
+// dst[i] = src[clamp(idx[i])]  (compacted copy of a per-utterance int64 vector: raw lengths of the surviving utterances)
+__global__ void gather_i64_kernel(const int64_t* __restrict__ src, const int32_t* __restrict__ idx, int64_t* __restrict__ dst, int n) {
+  pdl_trigger();
+  pdl_wait();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[min(max(idx[i], 0), n - 1)];
+}
+
 __global__ void axpy_kernel(const float* __restrict__ x, float a, float* __restrict__ y, long n) {
   pdl_trigger();
   pdl_wait();
@@ -406,9 +415,9 @@ extern "C" int eec_layernorm_fwd(const float* x, const float* gamma, const float
   if (rows == 0) return 0;
   int blocks = cdiv(rows, 8);
   if (out_dtype == EEC_F32)
-    launch_pdl(layernorm_fwd_kernel<float>, dim3(blocks), dim3(256), 0, S(stream), x, gamma, beta, (float*)out, mean, rstd, rows);
+    launch_pdl(layernorm_fwd_kernel<float>, dim3(blocks), dim3(256), 0, S(stream), x, gamma, beta, (float*)out, mean, rstd, rows, active_items());
   else
-    launch_pdl(layernorm_fwd_kernel<__nv_bfloat16>, dim3(blocks), dim3(256), 0, S(stream), x, gamma, beta, (__nv_bfloat16*)out, mean, rstd, rows);
+    launch_pdl(layernorm_fwd_kernel<__nv_bfloat16>, dim3(blocks), dim3(256), 0, S(stream), x, gamma, beta, (__nv_bfloat16*)out, mean, rstd, rows, active_items());
   EEC_LAUNCH_CHECK();
   return 0;
 }
@@ -503,6 +512,13 @@ extern "C" int eec_colsum(const void* in, int dtype, int ld, float* out, float s
   dim3 grid(cdiv(cols, 32), cdiv(rows, rpb));
   if (dtype == EEC_F32) launch_pdl(colsum_kernel<float>, dim3(grid), dim3(256), 0, S(stream), (const float*)in, ld, out, rows, cols, rpb, scale);
   else launch_pdl(colsum_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, S(stream), (const __nv_bfloat16*)in, ld, out, rows, cols, rpb, scale);
+  EEC_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int eec_gather_i64(const int64_t* src, const int32_t* idx, int64_t* dst, int n, eec_stream_t stream) {
+  if (n == 0) return 0;
+  launch_pdl(gather_i64_kernel, dim3(cdiv(n, 128)), dim3(128), 0, S(stream), src, idx, dst, n);
   EEC_LAUNCH_CHECK();
   return 0;
 }

@@ -1,11 +1,11 @@
 """eec -- B200-native early-exit conformer (CTC hot path) behind the reference's module interface.
 
-    from eec import Early_conformer, Splitformer, CTCLoss, multi_exit_ctc_loss, greedy_decode, GraphedTrainStep
+    from eec import Early_conformer, Splitformer, CTCLoss, multi_exit_ctc_loss, greedy_decode, GraphedTrainStep, GraphedEarlyExit
 """
 from .lib import EecError, load, LIB_PATH, EXPORTS  # noqa: F401
 from .early_exit import Early_conformer, Splitformer, greedy_decode  # noqa: F401
 from .ctc import CTCLoss, multi_exit_ctc_loss  # noqa: F401
 from .aed import full_conformer  # noqa: F401
-from .graph import GraphedForward, GraphedTrainStep  # noqa: F401
+from .graph import GraphedEarlyExit, GraphedForward, GraphedTrainStep  # noqa: F401
 from .optim import FusedNoamAdamW  # noqa: F401
 from . import distributed  # noqa: F401,E402

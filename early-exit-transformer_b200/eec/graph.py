@@ -182,3 +182,57 @@ class GraphedForward:
         self.src.copy_(src, non_blocking=True)
         self.lengths.copy_(lengths, non_blocking=True)
         return self.replay()
+
+
+class GraphedEarlyExit:
+    """Dynamic early-exit inference (``model.forward_early_exit``) as ONE CUDA graph: exit decisions, survivor compaction and the
+    per-kernel active-row limits all live on the device, so the captured graph is valid for any mix of exits.
+
+        ee = eec.GraphedEarlyExit(model.eval(), batch_size=64, t_in=1501, threshold=2.5)
+        exit_index, tokens, n_tokens, mean_entropy = ee(src, lengths)       # static device buffers; one D2H copy when read
+    """
+
+    def __init__(self, model, batch_size: int, t_in: int, threshold: float, n_mels: Optional[int] = None, warmup: int = 2):
+        from . import early_exit_infer
+        params = list(model.parameters())
+        if not params or not params[0].is_cuda:
+            raise EecError("GraphedEarlyExit: move the model to a CUDA device first (no CPU path)")
+        if model.training:
+            raise EecError("GraphedEarlyExit captures an inference forward: call model.eval() first")
+        model._check_supported()
+        dev = params[0].device
+        self.model, self.threshold = model, float(threshold)
+        n_mels = n_mels if n_mels is not None else model._features_length
+        self.src = torch.zeros(batch_size, n_mels, t_in, dtype=torch.float32, device=dev)
+        self.lengths = torch.full((batch_size,), t_in, dtype=torch.int64, device=dev)
+        self._pin_len = torch.empty(batch_size, dtype=torch.int64).pin_memory()
+        self.t_out = ((t_in - 3) // 2 + 1 - 3) // 2 + 1
+        run = lambda: early_exit_infer.run(model, self.src, self.lengths, self.threshold)   # noqa: E731
+        lib = load()
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side), torch.no_grad():
+            for _ in range(max(warmup, 1)):
+                run()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        n0 = lib.eec_launch_count()
+        with torch.no_grad(), torch.cuda.graph(self.graph):
+            self.out = run()
+        self.launches = int(lib.eec_launch_count() - n0)
+
+    def replay(self):
+        self.graph.replay()
+        return self.out
+
+    def __call__(self, src: torch.Tensor, lengths: torch.Tensor):
+        if tuple(src.shape) != tuple(self.src.shape) or lengths.numel() != self.src.shape[0]:
+            raise EecError(f"GraphedEarlyExit: input shape {tuple(src.shape)} != captured {tuple(self.src.shape)}")
+        if not lengths.is_cuda:
+            engine.check_lengths(lengths, self.t_out)
+            self._pin_len.copy_(lengths.reshape(-1))
+            lengths = self._pin_len
+        self.src.copy_(src, non_blocking=True)
+        self.lengths.copy_(lengths, non_blocking=True)
+        return self.replay()

@@ -75,6 +75,8 @@ _SIGS = {
     "eec_scale_rows_dev": [vp, vp, vp, i32, i64, vp],
     "eec_exit_select": [vp, vp, vp, vp, vp, i32, i32, f32, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp],
     "eec_gather_rows": [vp, vp, vp, vp, i32, i64, vp],
+    "eec_set_active_items": [vp, i32, i32],
+    "eec_gather_i64": [vp, vp, vp, i32, vp],
     "eec_stride2_gather": [vp, vp, i32, i32, i32, vp],
     "eec_repeat2_add": [vp, vp, i32, i32, i32, vp],
     "eec_repeat2_bwd": [vp, vp, i32, i32, i32, vp],

@@ -231,6 +231,15 @@ def gather_rows(x, y, gather_idx, n_alive, B, row_elems):
     call("eec_gather_rows", ptr(x), ptr(y), ptr(gather_idx), ptr(n_alive), B, row_elems, stream())
 
 
+def set_active_items(n_items_dev, rows_per_item: int = 0, pad_items: int = 0):
+    """Limit the inference kernels launched by this thread to the first *n_items_dev (+ pad_items) utterances (None clears)."""
+    call("eec_set_active_items", ptr(n_items_dev), int(rows_per_item), int(pad_items))
+
+
+def gather_i64(src, idx, dst):
+    call("eec_gather_i64", ptr(src), ptr(idx), ptr(dst), src.numel(), stream())
+
+
 def stride2_gather(x, y, B, T, D=256):
     call("eec_stride2_gather", ptr(x), ptr(y), B, T, D, stream())
 

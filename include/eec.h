@@ -249,6 +249,19 @@ int eec_exit_select(const float* entropy, const int32_t* argmax, const int32_t* 
                     int blank, eec_stream_t stream);
 int eec_gather_rows(const float* x, float* y, const int32_t* gather_idx, const int32_t* n_alive,
                     int B, int64_t row_elems, eec_stream_t stream);
+/* Active-item limit of the calling thread: while n_items_dev != NULL, the forward (inference) forms of eec_gemm (K-major A),
+ * eec_layernorm_fwd, eec_attn_fwd and eec_dwconv_bn_silu_eval process only the first *n_items_dev utterances, i.e. the leading
+ * *n_items_dev * rows_per_item rows of every frame-major tensor; tiles / rows / utterance blocks past the limit return at once,
+ * so compaction after an exit actually removes the finished utterances' work from the later layers.  The count is read ON THE
+ * DEVICE at kernel start (eec_exit_select keeps it current): no host sync, and a captured CUDA graph stays valid when it changes.
+ * pad_items further utterances behind the count are processed as well: the tensor-core attention loads 128-row K/V tiles that
+ * overhang into the following utterance (masked in the softmax, but 0 x NaN = NaN in P.V), so the rows right behind the last
+ * survivor must be finite; the caller keeps one utterance of stale-but-finite data there (pad_items = 1 when T' >= 128).
+ * Rows past the limit are left untouched (their contents are unspecified).  Pass NULL to clear. */
+int eec_set_active_items(const int32_t* n_items_dev, int rows_per_item, int pad_items);
+/* dst[i] = src[idx[i]], i < n (idx clamped to [0, n)): the raw lengths of the surviving utterances in compacted order (Splitformer's
+ * parallel branch masks with the RAW fbank lengths, early_exit.py:332-338) */
+int eec_gather_i64(const int64_t* src, const int32_t* idx, int64_t* dst, int n, eec_stream_t stream);
 
 /* ---- Splitformer branch glue (early_exit.py:318-356) --------------------------------- */
 int eec_stride2_gather(const float* x, float* y, int B, int T, int D, eec_stream_t stream);

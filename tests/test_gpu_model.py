@@ -424,3 +424,56 @@ def test_graphed_forward_matches_eager():
     assert rel(fwd1(src2, lengths2)[0], ref2[0]) < 1e-6 and fwd1.out.shape[0] == 1
     with pytest.raises(AssertionError):
         fwd(src2, torch.full((src.shape[0],), 100, dtype=torch.int64))
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("split", [False, True])
+def test_early_exit_compaction_skips_finished_rows(split, precision):
+    """BASELINE configs[3]: (Splitformer) inference with dynamic early exit and on-device batch compaction.  After an exit the
+    survivors are compacted and the later layers run on them only (eec_set_active_items: the kernels read the device-side
+    count); decisions, tokens and the survivors' entropies must equal the selection rule applied to the FULL forward's output,
+    for every threshold, eagerly and through the CUDA graph (one capture, thresholds/inputs change between replays)."""
+    import eec
+    E, Bn = 3, 7
+    sd = O.make_params(13, n_exits=E, n_layers=1, splitformer=split)
+    src, lengths = O.synthetic_batch(Bn, 331 if not split else 203, seed=14, min_frac=0.4)   # (203 -> odd T': the branch pads)
+    cls = eec.Splitformer if split else eec.Early_conformer
+    m = cls(src_pad_idx=0, n_enc_exits=E, enc_voc_size=256, dec_voc_size=256, d_model=256, n_head=8, max_len=2000,
+            d_feed_forward=2048, n_enc_layers=1, features_length=80, drop_prob=0.1, depthwise_kernel_size=31,
+            device=torch.device("cuda"))
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda().eval()
+    m.precision = precision
+    with torch.no_grad():
+        full = m(src.cuda(), lengths).cpu()
+    T = full.shape[2]
+    key_len = O.encoder_lengths(lengths, T)
+    _, _, Hm = O.early_exit_select(full, key_len, 1e9)
+    # thresholds: nobody exits early / a mix at every exit / everybody at the first exit
+    srt = Hm[0].sort().values
+    mids = [float((srt[2] + srt[3]) / 2), float(Hm[:2].max()) + 1e-3]
+    for thr in [-1.0] + mids + [1e9]:
+        ex_ref, tok_ref, _ = O.early_exit_select(full, key_len, thr)
+        exit_index, tokens, n_tokens, mean_ent = m.forward_early_exit(src.cuda(), lengths, thr)
+        ent_tol = 1e-3 if precision == "fp32" else 3e-2
+        # a decision may legitimately flip only if an entropy sits within the arithmetic tolerance of the threshold
+        margin = float((Hm - thr).abs().min())
+        if margin > 2 * ent_tol:
+            assert exit_index.cpu().tolist() == ex_ref.tolist(), (thr, exit_index.cpu().tolist(), ex_ref.tolist())
+            if precision == "fp32":
+                for b in range(Bn):
+                    assert tokens[b, : int(n_tokens[b])].cpu().tolist() == tok_ref[b]
+            for b in range(Bn):
+                for e in range(int(ex_ref[b]) + 1):
+                    assert abs(float(mean_ent[e, b]) - float(Hm[e, b])) < ent_tol, (thr, b, e)
+    # graph: captured once, replayed on another batch
+    thr = mids[0]
+    ee = eec.GraphedEarlyExit(m, Bn, src.shape[2], thr)
+    a = [t.clone() for t in ee(src, lengths)]
+    b = m.forward_early_exit(src.cuda(), lengths, thr)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2])
+    src2, lengths2 = O.synthetic_batch(Bn, src.shape[2], seed=15, min_frac=0.4)
+    a2 = [t.clone() for t in ee(src2, lengths2)]
+    b2 = m.forward_early_exit(src2.cuda(), lengths2, thr)
+    assert torch.equal(a2[0], b2[0]) and torch.equal(a2[1], b2[1])
+    assert ee.launches > 20
