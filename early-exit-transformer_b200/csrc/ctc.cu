@@ -482,6 +482,71 @@ __global__ void im2col_k3s2_kernel(const TI* __restrict__ in, long sb, long sc, 
   st_from_float<TO>(out + i, v);
 }
 
+// Fast path A: channel-major input with contiguous time (the fbank, in[b][c][f], st == 1).  Block = (32 output frames, utterance):
+// the 65-frame span of every channel is read along time (coalesced), transposed through shared memory, and every output row
+// leaves as 16-byte stores.  (The element-per-thread kernel above touched a different cache line per thread: 66 us per launch.)
+constexpr int IM_TT = 32;                 // output frames per block
+constexpr int IM_SPAN = 2 * IM_TT + 1;    // input frames they read
+template <typename TO>
+__global__ void __launch_bounds__(256) im2col_k3s2_tmajor_kernel(const float* __restrict__ in, long sb, long sc, TO* __restrict__ out, int ldo,
+                                                              int C, int T_out) {
+  pdl_trigger();
+  pdl_wait();
+  extern __shared__ float im_tile[];      // [C][IM_SPAN + 1]
+  const int b = blockIdx.y, t0 = blockIdx.x * IM_TT;
+  const int f0 = 2 * t0, f_last = 2 * (T_out - 1) + 2;   // last input frame any output of this utterance reads
+  const float* src = in + (long)b * sb;
+  for (int idx = threadIdx.x; idx < C * IM_SPAN; idx += 256) {
+    const int c = idx / IM_SPAN, x = idx - c * IM_SPAN;
+    im_tile[c * (IM_SPAN + 1) + x] = (f0 + x <= f_last) ? src[(long)c * sc + f0 + x] : 0.f;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int r = warp; r < IM_TT; r += 8) {
+    const int t = t0 + r;
+    if (t >= T_out) break;
+    TO* orow = out + ((long)b * T_out + t) * ldo;
+    for (int k0 = lane * 8; k0 < ldo; k0 += 256) {
+      float v[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int k = k0 + e, c = k / 3, j = k - 3 * c;
+        v[e] = (k < 3 * C) ? im_tile[c * (IM_SPAN + 1) + 2 * r + j] : 0.f;
+      }
+      st8<TO>(orow + k0, v);
+    }
+  }
+}
+// Fast path B: frame-major input (in[b][f][c], sc == 1): one warp per output row reads its three input rows with 128-bit loads and
+// writes the (c*3 + j)-interleaved row with 16-byte stores.
+template <typename TO>
+__global__ void __launch_bounds__(256) im2col_k3s2_fmajor_kernel(const float* __restrict__ in, long sb, long st, TO* __restrict__ out, int ldo,
+                                                              int B, int C, int T_out) {
+  pdl_trigger();
+  pdl_wait();
+  extern __shared__ float im_rows[];      // [8 warps][3][C]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long row = (long)blockIdx.x * 8 + warp;
+  if (row >= (long)B * T_out) return;
+  const int b = (int)(row / T_out), t = (int)(row % T_out);
+  float* mine = im_rows + warp * 3 * C;
+  const float* src = in + (long)b * sb + (long)(2 * t) * st;
+  for (int j = 0; j < 3; ++j)
+    for (int c = lane * 4; c < C; c += 128)
+      *reinterpret_cast<float4*>(mine + j * C + c) = *reinterpret_cast<const float4*>(src + (long)j * st + c);
+  __syncwarp();
+  TO* orow = out + row * ldo;
+  for (int k0 = lane * 8; k0 < ldo; k0 += 256) {
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int k = k0 + e, c = k / 3, j = k - 3 * c;
+      v[e] = (k < 3 * C) ? mine[j * C + c] : 0.f;
+    }
+    st8<TO>(orow + k0, v);
+  }
+}
+
 __global__ void col2im_k3s2_kernel(const float* __restrict__ dcols, int ldc, float* __restrict__ dx, int B, int C, int T_in,
                                    int T_out) {
   pdl_trigger();
@@ -604,6 +669,23 @@ extern "C" int eec_im2col_k3s2(const void* in, int in_dtype, int64_t sb, int64_t
   EEC_CHECK_ARG(in_dtype == EEC_F32, "im2col: input must be fp32");
   long total = (long)B * T_out * ldo;
   if (total == 0) return 0;
+  const bool aligned = ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+  if (aligned && st == 1 && (size_t)C * (IM_SPAN + 1) * 4 <= 48 * 1024) {   // channel-major, time contiguous (the fbank)
+    const dim3 grid(cdiv(T_out, IM_TT), B);
+    const size_t smem = (size_t)C * (IM_SPAN + 1) * 4;
+    if (out_dtype == EEC_F32) launch_pdl(im2col_k3s2_tmajor_kernel<float>, grid, dim3(256), smem, S(stream), (const float*)in, (long)sb, (long)sc, (float*)out, ldo, C, T_out);
+    else launch_pdl(im2col_k3s2_tmajor_kernel<__nv_bfloat16>, grid, dim3(256), smem, S(stream), (const float*)in, (long)sb, (long)sc, (__nv_bfloat16*)out, ldo, C, T_out);
+    EEC_LAUNCH_CHECK();
+    return 0;
+  }
+  if (aligned && sc == 1 && C % 4 == 0 && st % 4 == 0 && sb % 4 == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0 && (size_t)C * 96 <= 48 * 1024) {   // frame-major
+    const dim3 grid((unsigned)cdiv64((long)B * T_out, 8));
+    const size_t smem = (size_t)8 * 3 * C * 4;
+    if (out_dtype == EEC_F32) launch_pdl(im2col_k3s2_fmajor_kernel<float>, grid, dim3(256), smem, S(stream), (const float*)in, (long)sb, (long)st, (float*)out, ldo, B, C, T_out);
+    else launch_pdl(im2col_k3s2_fmajor_kernel<__nv_bfloat16>, grid, dim3(256), smem, S(stream), (const float*)in, (long)sb, (long)st, (__nv_bfloat16*)out, ldo, B, C, T_out);
+    EEC_LAUNCH_CHECK();
+    return 0;
+  }
   int blocks = (int)cdiv64(total, 256);
   if (out_dtype == EEC_F32)
     launch_pdl(im2col_k3s2_kernel<float, float>, dim3(blocks), dim3(256), 0, S(stream), (const float*)in, sb, sc, st, (float*)out, ldo, B, C, T_out);

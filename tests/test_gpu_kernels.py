@@ -277,6 +277,21 @@ def test_frontend_pieces(ops):
     x1 = rnd(B * T1, D, seed=61)
     cols2 = torch.empty(B * T2, 3 * D, device="cuda")
     ops.im2col_k3s2(x1, T1 * D, 1, D, cols2, 3 * D, B, D, T2)
+    ref2 = torch.stack([x1.view(B, T1, D)[:, j: j + 2 * T2 - 1: 2, :] for j in range(3)], -1).reshape(B * T2, 3 * D)   # [(b,t), c*3+j]
+    assert torch.equal(cols2, ref2)
+    for Tq in (163, 1501):   # bf16 outputs (what the tensor-core path consumes), ragged tile edges
+        Tq1 = (Tq - 3) // 2 + 1
+        Tq2 = (Tq1 - 3) // 2 + 1
+        s2 = rnd(3, C, Tq, seed=63)
+        cb = torch.empty(3 * Tq1, 256, device="cuda", dtype=torch.bfloat16)
+        ops.im2col_k3s2(s2, C * Tq, Tq, 1, cb, 256, 3, C, Tq1)
+        r = torch.stack([s2[:, :, j: j + 2 * Tq1 - 1: 2] for j in range(3)], -1).permute(0, 2, 1, 3).reshape(3 * Tq1, C * 3)
+        assert torch.equal(cb[:, :240], r.to(torch.bfloat16)) and float(cb[:, 240:].float().abs().max()) == 0
+        xq = rnd(3 * Tq1, D, seed=64)
+        cq = torch.empty(3 * Tq2, 3 * D, device="cuda", dtype=torch.bfloat16)
+        ops.im2col_k3s2(xq, Tq1 * D, 1, D, cq, 3 * D, 3, D, Tq2)
+        rq = torch.stack([xq.view(3, Tq1, D)[:, j: j + 2 * Tq2 - 1: 2, :] for j in range(3)], -1).reshape(3 * Tq2, 3 * D)
+        assert torch.equal(cq, rq.to(torch.bfloat16))
     dcols = rnd(B * T2, 3 * D, seed=62)
     dx = torch.empty(B * T1, D, device="cuda")
     ops.col2im_k3s2(dcols, 3 * D, dx, B, D, T1, T2)
