@@ -236,6 +236,13 @@ def test_graphed_train_step_matches_eager(precision):
     assert abs(float(loss2) - ref_loss2) <= tol * abs(ref_loss2)
     k = "conformer.0.conformer_layers.0.ffn1.sequential.1.weight"
     assert rel(dict(m.named_parameters())[k].grad, ref_g2[k]) < max(tol, 2e-4)
+    # prefetch path: features uploaded on a side stream into a staging buffer, committed before the replay
+    step.load_inputs(src, lengths2, targets2, tl2)           # (static src now holds the OTHER batch)
+    step.prefetch(src2.pin_memory())
+    step.commit_prefetch()
+    loss3 = step.replay()
+    torch.cuda.synchronize()
+    assert abs(float(loss3) - ref_loss2) <= tol * abs(ref_loss2)
     with pytest.raises(AssertionError):
         step(src2, torch.full((Bn,), 100, dtype=torch.int64), targets2, tl2)
 
