@@ -484,3 +484,55 @@ def test_early_exit_compaction_skips_finished_rows(split, precision):
     b2 = m.forward_early_exit(src2.cuda(), lengths2, thr)
     assert torch.equal(a2[0], b2[0]) and torch.equal(a2[1], b2[1])
     assert ee.launches > 20
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_edge_shapes_one_model_many_batches(precision):
+    """The reference feeds length-sorted sub-batches of different shapes through one model (data_loader.py:166-188, train.py:26):
+    the same eec model must take a stream of different (B, T_in) -- single utterance, T' = 1 and 2, ragged tile edges, T' just above
+    one / two attention tiles -- in eval and in train mode, each checked against the CPU oracle run live."""
+    import eec
+    sd = O.make_params(23, n_exits=2, n_layers=1)
+    m = eec.Early_conformer(src_pad_idx=0, n_enc_exits=2, enc_voc_size=256, dec_voc_size=256, d_model=256, n_head=8,
+                            max_len=2000, d_feed_forward=2048, n_enc_layers=1, features_length=80, drop_prob=0.0,
+                            depthwise_kernel_size=31, device=torch.device("cuda"))
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda()
+    m.precision = precision
+    shapes = [(1, 7), (1, 11), (2, 19), (5, 131), (1, 523), (3, 1031), (4, 67)]      # T' = 1, 2, 4, 32, 130, 257, 16
+    for i, (Bn, t_in) in enumerate(shapes):
+        src, lengths = O.synthetic_batch(Bn, t_in, seed=50 + i, min_frac=0.6)
+        lengths[0] = t_in
+        m.eval()
+        with torch.no_grad():
+            out = m(src.cuda(), lengths)
+            ref = O.early_conformer_forward(sd, src, lengths)
+        assert out.shape == ref.shape
+        for e in range(2):
+            assert rel(out[e], ref[e]) < TOL[precision], ("eval", Bn, t_in, e, rel(out[e], ref[e]))
+        if Bn * out.shape[2] < 2:
+            continue        # train-mode BatchNorm needs more than one value per channel (torch raises there too)
+        m.train()
+        running = {k: v.clone() for k, v in m.state_dict().items() if "running" in k or "num_batches" in k}
+        targets, tl = O.synthetic_targets(Bn, seed=70 + i, lo=1, hi=max(1, min(3, out.shape[2] // 2 - 1)))
+        m.zero_grad(set_to_none=True)
+        out_t = m(src.cuda(), lengths)
+        loss = eec.multi_exit_ctc_loss(out_t, targets, tl)
+        loss.backward()
+        sdg = {k: (v.clone().double().requires_grad_(True) if v.is_floating_point() and "running" not in k and k != "positional_encoder.pe"
+                   else (v.double() if v.is_floating_point() else v)) for k, v in sd.items()}
+        ref_t = O.early_conformer_forward(sdg, src.double(), lengths, training=True)
+        in_len = torch.full((Bn,), ref_t.shape[2], dtype=torch.long)
+        ref_loss = sum(torch.nn.functional.ctc_loss(ref_t[e].permute(1, 0, 2), targets, in_len, tl, blank=0, zero_infinity=True)
+                       for e in range(2))
+        for e in range(2):
+            assert rel(out_t[e], ref_t[e].detach()) < TOL[precision], ("train", Bn, t_in, e)
+        if float(ref_loss) > 0:
+            assert abs(loss.item() - ref_loss.item()) / abs(ref_loss.item()) < TOL[precision], (Bn, t_in, loss.item(), ref_loss.item())
+            ref_loss.backward()
+            gt = 5e-3 if precision == "fp32" else 6e-2
+            gmax = max(float(sdg[n].grad.norm()) for n, _ in m.named_parameters())
+            for n, p in m.named_parameters():
+                err = abs(p.grad.double().norm().item() - sdg[n].grad.norm().item()) / max(sdg[n].grad.norm().item(), 1e-3 * gmax)
+                assert err < gt, (Bn, t_in, n, err)
+        m.load_state_dict({**m.state_dict(), **running})     # keep the BatchNorm running stats of `sd` for the next eval comparison
