@@ -269,12 +269,13 @@ def run_ours(args):
         ms_e2e = timed(e2e_step, args.steps)
 
     # inference RTFx per exit (BASELINE metric part (i)): forward truncated after exit e, bf16, eval
-    rtfx = ee_leg = None
+    rtfx = ee_leg = fb_leg = None
     if rank == 0 and not args.skip_rtfx and not args.profile:
         audio_s = float(lengths.sum()) * FRAME_S
         rtfx = rtfx_per_exit(model, src_dev, lengths, audio_s, use_graph=not args.no_graph)
         model.train()
         ee_leg = early_exit_leg(layers, args.precision, dev, src_dev, lengths, audio_s) if not args.no_graph else None
+        fb_leg = fbank_leg(dev, with_cpu=(world == 1 and not args.skip_cpu))
 
     # the same step at the reference's DEFAULT --drop_prob 0.1 (util/conf.py:283-291): fused counter-based dropout at all
     # seven sites per layer + after the positional encoding, masks regenerated in backward (nothing stored)
@@ -334,6 +335,8 @@ def run_ours(args):
             line["train_with_dropout"] = drop_leg
         if ee_leg is not None:
             line["early_exit_inference"] = ee_leg
+        if fb_leg is not None:
+            line["fbank_frontend"] = fb_leg
         print(json.dumps(line), file=_JSON_OUT, flush=True)
     if world > 1:
         graphed = None          # (graphs that hold captured NCCL kernels are released before the communicator)
@@ -406,6 +409,36 @@ def early_exit_leg(layers, precision, dev, src_dev, lengths, audio_s):
     return {"model": f"splitformer {N_EXITS} exits x {layers} layers, batch {src_dev.shape[0]}", "criterion": "mean frame entropy < threshold",
             "threshold": round(thr, 4), "utterances_leaving_at_exit": hist, "ms": round(ms_ee, 3), "rtfx": round(audio_s / (ms_ee / 1e3), 1),
             "all_exits_forward_ms": round(ms_full, 3), "gpu_launches": ee.launches, "launch": "one CUDA graph replay, no host sync"}
+
+
+def fbank_leg(dev, with_cpu):
+    """waveform -> 80-dim power-mel features (util/data_loader.py:7-18) for the whole 64 x 15 s batch on the GPU
+    (csrc/fbank.cu + two split-bf16 tcgen05 GEMMs), next to the numpy port of the reference's per-utterance CPU transform."""
+    import eec
+    g = torch.Generator().manual_seed(7)
+    L = (T_IN - 1) * 160
+    waves = (torch.randn(B, L, generator=g) * 0.1).to(dev)
+    lens = torch.full((B,), L, dtype=torch.int64, device=dev)
+    fb = eec.Fbank().cuda_tables(dev)
+    for _ in range(3):
+        fb(waves, lens)
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(10):
+        fb(waves, lens)
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1) / 10
+    leg = {"ms_per_batch": round(ms, 3), "audio_s_per_s": round(B * L / 16000.0 / (ms / 1e3), 1),
+           "algorithmic_bytes": B * L * 4 + B * N_MELS * T_IN * 4, "batch": f"{B} x {L} samples (15 s at 16 kHz) -> ({B}, {N_MELS}, {T_IN})"}
+    if with_cpu:
+        from oracle import fbank_oracle as FO
+        w1 = waves[0].cpu().numpy()
+        t0 = time.perf_counter()
+        FO.fbank(w1)
+        leg["cpu_port_ms_per_utterance"] = round((time.perf_counter() - t0) * 1e3, 1)
+    return leg
 
 
 def roofline_dominant(dev, pk):

@@ -8,4 +8,5 @@ from .ctc import CTCLoss, multi_exit_ctc_loss  # noqa: F401
 from .aed import full_conformer  # noqa: F401
 from .graph import GraphedEarlyExit, GraphedForward, GraphedTrainStep  # noqa: F401
 from .optim import FusedNoamAdamW  # noqa: F401
+from .features import Fbank  # noqa: F401
 from . import distributed  # noqa: F401,E402

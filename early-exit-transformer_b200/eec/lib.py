@@ -76,6 +76,10 @@ _SIGS = {
     "eec_exit_select": [vp, vp, vp, vp, vp, i32, i32, f32, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp],
     "eec_gather_rows": [vp, vp, vp, vp, i32, i64, vp],
     "eec_set_active_items": [vp, i32, i32],
+    "eec_fbank_frames": [vp, vp, i64, vp, vp, i32, i32, i32, i32, vp],
+    "eec_fbank_power": [vp, i32, vp, i64, i32, i32, vp],
+    "eec_fbank_finish": [vp, i32, vp, i32, i32, i32, vp],
+    "eec_fbank_split_operand": [vp, i32, vp, i64, i32, vp],
     "eec_gather_i64": [vp, vp, vp, i32, vp],
     "eec_stride2_gather": [vp, vp, i32, i32, i32, vp],
     "eec_repeat2_add": [vp, vp, i32, i32, i32, vp],

@@ -263,6 +263,24 @@ int eec_set_active_items(const int32_t* n_items_dev, int rows_per_item, int pad_
  * parallel branch masks with the RAW fbank lengths, early_exit.py:332-338) */
 int eec_gather_i64(const int64_t* src, const int32_t* idx, int64_t* dst, int n, eec_stream_t stream);
 
+/* ---- feature front end: util/data_loader.py:7-18 -- torchaudio Spectrogram(n_fft = 1024, win_length = 320,
+ *      hop_length = 160; hann, center, reflect, power 2) followed by MelScale(16 kHz, 80 mels, n_stft = 513), computed by the
+ *      reference per utterance on the CPU in the collate function (data_loader.py:124-125).  Batched here:
+ *        eec_fbank_frames -> eec_gemm ([re|im] = frames x [cos|sin]^T) -> eec_fbank_power -> eec_gemm (mel = power x fb) -> eec_fbank_finish
+ *      Both GEMMs run on the bf16 tensor cores at fp32 accuracy: operands are split v = hi + lo (bf16 each) and the partial
+ *      products hi*hi + hi*lo + lo*hi are contracted in one GEMM over K' = 3K: activations are laid out [hi | hi | lo] (written
+ *      by eec_fbank_frames / eec_fbank_power), constant operands [hi | lo | hi] (eec_fbank_split_operand).
+ * frames_bf16x3 [B*T, 3*win] bf16: row (b, t) = window[i] * wave[b][reflect(t*hop - win/2 + i)], i < win, zero for t >= 1 + wave_len[b]/hop
+ * (only the win_length samples under the centred, zero-padded window are non-zero: the n_fft-point DFT is a K = win contraction). */
+int eec_fbank_frames(const float* wave, const int64_t* wave_len, int64_t ldw, const float* window, void* frames_bf16x3,
+                     int B, int T, int win, int hop, eec_stream_t stream);
+/* spec [rows, lds] fp32 = [re (n_freqs) | im (n_freqs) | pad] -> power_bf16x3 [rows, 3*kp] bf16 ([hi | hi | lo] of re^2 + im^2, zero padded) */
+int eec_fbank_power(const float* spec, int lds, void* power_bf16x3, int64_t rows, int n_freqs, int kp, eec_stream_t stream);
+/* mel [B*T, ldm] fp32 (frame-major) -> out [B, n_mels, T] fp32, the layout Early_conformer.forward takes (early_exit.py:617-620) */
+int eec_fbank_finish(const float* mel, int ldm, float* out, int B, int T, int n_mels, eec_stream_t stream);
+/* constant operand w [rows, k] fp32 -> out_bf16x3 [rows, 3*kp] bf16 = [hi | lo | hi], zero padded to kp columns per part */
+int eec_fbank_split_operand(const float* w, int k, void* out_bf16x3, int64_t rows, int kp, eec_stream_t stream);
+
 /* ---- Splitformer branch glue (early_exit.py:318-356) --------------------------------- */
 int eec_stride2_gather(const float* x, float* y, int B, int T, int D, eec_stream_t stream);
 /* y[b,t,:] += up[b,t/2,:] */

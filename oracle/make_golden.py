@@ -10,6 +10,7 @@ are regenerated at test time by ``oracle.conformer_oracle.make_params(seed, ...)
 (the script proves they load into the reference module with ``strict=True``).
 TEST INFRASTRUCTURE ONLY -- nothing under early-exit-transformer_b200/ imports this.
 """
+import math
 import os
 import sys
 
@@ -252,6 +253,27 @@ def run_dropout_case(name, kind, n_exits, n_layers, B, t_in, lo, hi, p, dseed, s
     print(name, "T'=", lp.shape[2], "loss=", loss.item(), "(p=0 loss differs)", os.path.getsize(path) // 1024, "KiB")
 
 
+def fbank_case():
+    """tests/golden/fbank_ref.npz: the real torchaudio transforms called exactly like util/data_loader.py:7-18 (the reference's own
+    util.data_loader cannot be imported here -- no matter: these two calls ARE its feature extraction) on seeded waveforms."""
+    import torchaudio.transforms as TT
+    from types import SimpleNamespace
+    args = SimpleNamespace(n_fft=512, hop_length=160, win_length=320, sample_rate=16000, n_mels=80)   # util/conf.py:335-380
+    g = torch.Generator().manual_seed(77)
+    lens = [16000, 9999, 4803, 1600]
+    out = {"lengths": np.array(lens, dtype=np.int64), "seed": 77}
+    for i, n in enumerate(lens):
+        wave = torch.randn(1, n, generator=g) * 0.1
+        wave[0, : n // 3] += 0.3 * torch.sin(torch.arange(n // 3) * 2 * math.pi * 440.0 / 16000)
+        spec = TT.Spectrogram(n_fft=args.n_fft * 2, hop_length=args.hop_length, win_length=args.win_length)(wave)
+        mel = TT.MelScale(sample_rate=args.sample_rate, n_mels=args.n_mels, n_stft=args.n_fft + 1)(spec)
+        out[f"wave{i}"] = wave[0].numpy()
+        out[f"fbank{i}"] = mel[0].numpy()
+    path = os.path.join(ROOT, "tests", "golden", "fbank_ref.npz")
+    np.savez_compressed(path, **out)
+    print("fbank_ref", [out[f"fbank{i}"].shape for i in range(len(lens))], os.path.getsize(path) // 1024, "KiB")
+
+
 FC_RENAME = (("linears.", "linears_1."), ("positional_encoder.", "positional_encoder_1."))
 AED_CE_WEIGHT, AED_CTC_WEIGHT = 0.7, 0.3   # util/conf.py --aed_ce_weight / --aed_ctc_weight defaults
 
@@ -346,5 +368,6 @@ if __name__ == "__main__":
         run_case(name, kind, e, l, B, t, lo, hi, seed=100 + 10 * i)
     ctc_cases()
     run_fc_case("fc_e2l1d1_b2_t163", 2, 1, 1, 2, 163, 3, 8, seed=150)
+    fbank_case()
     for i, (name, (kind, e, l, B, t, lo, hi, p, ds)) in enumerate(DROP_CASES.items()):
         run_dropout_case(name, kind, e, l, B, t, lo, hi, p, ds, seed=200 + 10 * i)
