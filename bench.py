@@ -170,6 +170,7 @@ def run_ours(args):
     pk = peaks()
     layers = args.layers_per_exit
     model = build_model(layers, args.precision, dev).train()
+    model.dropout = args.train_drop_prob     # 0 by default (the parity configuration); > 0 profiles the dropout step
     src, lengths, targets, tl = synthetic(rank)
     src_pin = src.pin_memory()
     src_dev = src.to(dev)
@@ -318,7 +319,8 @@ def run_ours(args):
             "config": {"workload": f"early_conformer CTC training step (fwd + summed 6-exit CTC + bwd), {N_EXITS} exits x {layers} "
                                    f"layers, d_model 256, batch {B}/GPU x 15 s (T_in {T_IN} -> T' {T}), grad all-reduce "
                                    f"{('NCCL fp32, per exit group, overlapped with backward inside the graph' if overlap else 'NCCL fp32 flat buffer after backward') if world > 1 else 'n/a'}; "
-                                   + ("optimizer step excluded" if opt is None else "clip_grad_norm + Noam + AdamW update included (fused, flat buffers)"),
+                                   + ("optimizer step excluded" if opt is None else "clip_grad_norm + Noam + AdamW update included (fused, flat buffers)")
+                                   + (f"; dropout {args.train_drop_prob}" if args.train_drop_prob > 0 else "; dropout 0 (parity configuration)"),
                        "global_batch": world * B, "parallelism": f"dp{world}",
                        "l2": "per-step working set ~8 GB >> 126 MB L2 (no flush needed)",
                        "launch": "eager (ctypes launches)" if graphed is None else "one CUDA graph replay per step",
@@ -550,6 +552,8 @@ def main():
     ap.add_argument("--no-opt", action="store_true", help="time forward + loss + backward only (no clip / Noam / AdamW update)")
     ap.add_argument("--no-graph", action="store_true", help="issue the ~600 kernels of a step eagerly instead of replaying the CUDA graph")
     ap.add_argument("--skip-rtfx", action="store_true")
+    ap.add_argument("--train-drop-prob", type=float, default=0.0, help="dropout probability of the HEADLINE step (default 0, the parity "
+                    "configuration of SURVEY 8d); used with --profile to capture the launch list of the dropout step")
     ap.add_argument("--no-overlap", action="store_true", help="N > 1: one all-reduce of the flat gradient buffer after backward "
                     "(outside the graph) instead of per-exit-group all-reduces overlapped with backward")
     ap.add_argument("--drop-prob", type=float, default=0.1, help="extra leg: the same training step with dropout at this probability "
