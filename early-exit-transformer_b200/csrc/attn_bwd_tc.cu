@@ -190,19 +190,21 @@ __global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_tc_kernel(const __grid
     float s[32], dp[32];
     // dropout on the probabilities (DROP): with M = mask * scale regenerated from the forward's counters,
     //   dV uses P.M (the tile written to sP), dS = P (dP.M - D) and D = dO . O is unchanged (O = (P.M) V).
-    DropKey dkey{};
-    if (DROP) dkey = drop_key(drop);
+    const uint32_t* dbits = reinterpret_cast<const uint32_t*>(drop.bits);   // keep-mask words of the forward (eec_dropout_bits, W = 32)
+    const long dR = (long)gridDim.z * H * T;
     if (active) {
       for (int i = 0; i < nq; ++i) {
         const int t = i * BT + r;
         const bool rvalid = t < T;
-        const uint64_t dgrp0 = ((uint64_t)(b * H + h) * T + t) * (uint64_t)((T + 7) >> 3);
+        const long drow = (long)(b * H + h) * T + t;
         const float l2 = rvalid ? lse[((long)b * H + h) * T + t] * LOG2E : 0.f;
         const float di = rvalid ? dvec[((long)b * H + h) * T + t] : 0.f;
 #pragma unroll 1
         for (int hk = 0; hk < 2; ++hk) {
           const int n = 2 * i + hk;
           const int c0 = hk * 64 + half * 32;    // first key column (within the block) of this warp's slab
+          uint32_t dword = 0u;                    // keep-mask word of (row t, these 32 keys): in flight while S / dP are being computed
+          if (DROP && rvalid && k0 + c0 < klen) dword = dbits[(long)((k0 + c0) >> 5) * dR + drow];
           mbar_wait(sdp_full, n & 1);
           tc_fence_after();
           tmem_ld32x2(trow + C_S + half * 32, trow + C_DP + half * 32, s, dp);
@@ -210,18 +212,14 @@ __global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_tc_kernel(const __grid
           mbar_arrive(sdp_free);                  // S / dP are in registers: the MMA warp may start the next half
           if (DROP) {
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              float f[8];
-              drop_factors8(dkey, drop, dgrp0 + (uint64_t)((k0 + c0) >> 3) + g, f);
-#pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                const bool ok = rvalid && (k0 + c0 + g * 8 + e < klen);
-                float p;
-                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p) : "f"(fmaf(s[g * 8 + e], sc2, -l2)));
-                p = ok ? p : 0.f;
-                s[g * 8 + e] = p * f[e];
-                dp[g * 8 + e] = ok ? p * (dp[g * 8 + e] * f[e] - di) : 0.f;
-              }
+            for (int e = 0; e < 32; ++e) {
+              const bool ok = rvalid && (k0 + c0 + e < klen);
+              const float f = (dword & (1u << e)) ? drop.scale : 0.f;
+              float p;
+              asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p) : "f"(fmaf(s[e], sc2, -l2)));
+              p = ok ? p : 0.f;
+              s[e] = p * f;
+              dp[e] = ok ? p * (dp[e] * f - di) : 0.f;
             }
           } else if (rvalid && k0 + c0 + 32 <= klen) {   // common case: no masked key in this slab
 #pragma unroll

@@ -275,11 +275,16 @@ static bool force_simt() {
 }
 
 extern "C" int eec_attn_fwd(const void* qkv, int dtype, const int32_t* key_len, void* ctx, float* lse, int B, int T,
-                            int H, int dh, const uint64_t* drop_state, float drop_p, uint32_t drop_site, eec_stream_t stream) {
+                            int H, int dh, const uint64_t* drop_state, float drop_p, uint32_t drop_site, const void* drop_bits,
+                            eec_stream_t stream) {
   EEC_CHECK_ARG(dh == 32, "attn_fwd: head dim must be 32 (got %d)", dh);
   if (B == 0 || T == 0) return 0;
-  const DropArgs drop = make_drop(drop_state, drop_p, drop_site);
-  if (dtype == EEC_BF16 && !force_simt() && attn_tc_ready()) return attn_fwd_tc(qkv, key_len, ctx, lse, B, T, H, dh, drop, S(stream));
+  DropArgs drop = make_drop(drop_state, drop_p, drop_site);
+  drop.bits = drop_bits;
+  const bool tc_path = dtype == EEC_BF16 && !force_simt() && attn_tc_ready();
+  EEC_CHECK_ARG(!(tc_path && drop.state && !drop_bits), "attn_fwd (tensor-core path): dropout needs the keep-mask words of "
+                "eec_dropout_bits(R = B*H*T, C = T, Cs = 8*ceil(T/8), W = 32) in drop_bits");
+  if (tc_path) return attn_fwd_tc(qkv, key_len, ctx, lse, B, T, H, dh, drop, S(stream));
   dim3 grid(cdiv(T, QB), H, B);
   if (dtype == EEC_F32)
     attn_fwd_simt_kernel<float, true><<<grid, 128, 0, S(stream)>>>((const float*)qkv, key_len, (float*)ctx, lse, T, H, drop, active_items());
@@ -291,11 +296,14 @@ extern "C" int eec_attn_fwd(const void* qkv, int dtype, const int32_t* key_len, 
 
 extern "C" int eec_attn_bwd(const void* qkv, const void* ctx, const void* dctx, int dtype, const float* lse,
                             const int32_t* key_len, void* dqkv, float* dvec, float* dq32, int B, int T, int H, int dh,
-                            const uint64_t* drop_state, float drop_p, uint32_t drop_site, eec_stream_t stream) {
+                            const uint64_t* drop_state, float drop_p, uint32_t drop_site, const void* drop_bits, eec_stream_t stream) {
   EEC_CHECK_ARG(dh == 32, "attn_bwd: head dim must be 32 (got %d)", dh);
   if (B == 0 || T == 0) return 0;
-  const DropArgs drop = make_drop(drop_state, drop_p, drop_site);
-  if (dtype == EEC_BF16 && !force_simt() && attn_tc_ready())
+  DropArgs drop = make_drop(drop_state, drop_p, drop_site);
+  drop.bits = drop_bits;
+  const bool tc_path = dtype == EEC_BF16 && !force_simt() && attn_tc_ready();
+  EEC_CHECK_ARG(!(tc_path && drop.state && !drop_bits), "attn_bwd (tensor-core path): dropout needs the forward's keep-mask words in drop_bits");
+  if (tc_path)
     return attn_bwd_tc(qkv, ctx, dctx, lse, key_len, dqkv, dvec, dq32, B, T, H, dh, drop, S(stream));
   dim3 grid(cdiv(T, QB), H, B);
   if (dtype == EEC_F32) {

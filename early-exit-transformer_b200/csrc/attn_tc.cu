@@ -133,11 +133,18 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_fwd_tc_kernel(const __grid
     for (int i = 0; i < DHEAD; ++i) o[i] = 0.f;
     float v[32];
     // dropout on the probabilities (DROP): the row sum keeps the undropped values, the P tile fed to the P V product is masked
-    DropKey dkey{};
-    if (DROP) dkey = drop_key(drop);
-    const uint64_t dgrp0 = ((uint64_t)(b * H + h) * T + (q0 + r)) * (uint64_t)((T + 7) >> 3);   // group index of (b, h, t, key 0)
+    // keep-mask words (eec_dropout_bits, W = 32): word (k/32, row) at bits[(k/32)*R + row], row = (b*H + h)*T + t, R = B*H*T
+    const uint32_t* dbits = reinterpret_cast<const uint32_t*>(drop.bits);
+    const long drow = (long)(b * H + h) * T + (q0 + r), dR = (long)gridDim.z * H * T;
+    const bool dvalid = (q0 + r) < T;
     for (int j = 0; j < nblk; ++j) {
       const int nvalid = min(KB, klen - j * KB);   // only the last key block can be partial
+      uint32_t dword[4] = {0u, 0u, 0u, 0u};          // this row's keep-mask words of the block: in flight while S is being computed
+      if (DROP && dvalid) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          if (c * 32 < nvalid) dword[c] = dbits[(long)((j * KB) / 32 + c) * dR + drow];
+      }
       mbar_wait(s_full, j & 1);
       tc_fence_after();
       // pass 1: row max (raw scores; the positive scale is applied once) over the valid keys of this block
@@ -169,15 +176,7 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_fwd_tc_kernel(const __grid
 #pragma unroll
             for (int i = 0; i < 32; ++i) { v[i] = (c0 + i < nvalid) ? ex2_fast(fmaf(v[i], sc, -mx)) : 0.f; psum += v[i]; }
           }
-          if (DROP) {
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              float f[8];
-              drop_factors8(dkey, drop, dgrp0 + (uint64_t)((j * KB + c0) >> 3) + g, f);
-#pragma unroll
-              for (int e = 0; e < 8; ++e) v[g * 8 + e] *= f[e];
-            }
-          }
+          if (DROP) drop_apply_bits<32>(v, c0 == 0 ? dword[0] : c0 == 32 ? dword[1] : c0 == 64 ? dword[2] : dword[3], drop.scale);
         } else {
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = 0.f;

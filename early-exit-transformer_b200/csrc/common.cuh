@@ -132,6 +132,7 @@ struct DropArgs {          // built on the host (make_drop), passed to kernels b
   uint32_t site;
   uint32_t thr;            // element dropped iff its 16-bit draw < thr   (thr = round(p * 65536))
   float scale;             // 65536 / (65536 - thr)
+  const void* bits;        // tensor-core kernels: keep-mask words written by eec_dropout_bits (they do not run Philox themselves)
 };
 static inline DropArgs make_drop(const uint64_t* state, float p, uint32_t site) {
   DropArgs a{};
@@ -202,6 +203,13 @@ int gemm_tc(const eec_gemm_desc* d, cudaStream_t st, int32_t* argmax, float* ent
 int gemm_tc2(const eec_gemm_desc* d, cudaStream_t st, int32_t* argmax, float* entropy, int logsoftmax);  // persistent v2
 int gemm_tc3(const eec_gemm_desc* d, cudaStream_t st);   // v3 epilogue (GENERIC / GLU modes), called by gemm_tc2
 int gemm_ln3(const eec_gemm_desc* d, cudaStream_t st);   // v3 LayerNorm-tail epilogue (N == 256), called by gemm_tc2
+// x[j] = bit j of `word` ? x[j] * scale : 0   (j < n <= 32; the epilogue-side half of the dropout)
+template <int N>
+__device__ __forceinline__ void drop_apply_bits(float (&x)[N], uint32_t word, float scale) {
+#pragma unroll
+  for (int j = 0; j < N; ++j) x[j] = (word & (1u << j)) ? x[j] * scale : 0.f;
+}
+
 int attn_bwd_tc(const void* qkv, const void* ctx, const void* dctx, const float* lse, const int32_t* key_len, void* dqkv,
                 float* dvec, float* dq32, int B, int T, int H, int dh, const DropArgs& drop, cudaStream_t st);
 int attn_fwd_tc(const void* qkv, const int32_t* key_len, void* ctx, float* lse, int B, int T, int H, int dh,

@@ -358,8 +358,6 @@ __global__ void __launch_bounds__(NT3, 1) gemm_tc3_kernel(const __grid_constant_
 #endif
     int cs = 0;             // a_colsum: this warp's position in the operand ring (walks every k-block of every unit)
     uint32_t cph = 0;
-    DropKey dkey{};
-    if (DROP) dkey = drop_key(p.drop);
     for (UnitIter ui(p); ui.u < n_units; ui.next(p), ++ut) {
       if (ui.mt >= mt_eff) { --ut; continue; }
       TL_STAMP(t0_); TL_ACC(e_rest, ut ? t0_ - t2_ : 0);
@@ -430,6 +428,18 @@ __global__ void __launch_bounds__(NT3, 1) gemm_tc3_kernel(const __grid_constant_
             }
           }
           __syncwarp();
+        }
+        // dropout keep-mask of this thread's 64 outputs: four 16-bit words written by eec_dropout_bits ([n/16][m] layout: the 32 rows
+        // of a warp read 64 contiguous bytes); loaded before the accumulator wait so that the latency hides behind the main loop
+        uint32_t dw[2] = {0xffffffffu, 0xffffffffu};
+        if (DROP && valid) {
+          const uint16_t* db = reinterpret_cast<const uint16_t*>(p.drop.bits);
+#pragma unroll
+          for (int ss = 0; ss < 4; ++ss) {
+            const int n = nb + ss * 16;
+            const uint32_t wv = (n < p.N) ? (uint32_t)db[(long)(n >> 4) * p.M + m] : 0xffffu;
+            dw[ss >> 1] = (ss & 1) ? ((dw[ss >> 1] & 0xffffu) | (wv << 16)) : ((dw[ss >> 1] & 0xffff0000u) | wv);
+          }
         }
         mbar_wait(&tfull_bar[acc], (ut >> 1) & 1);
         TL_STAMP(t1_); TL_ACC(e_wait, t1_ - t0_);
@@ -530,15 +540,7 @@ __global__ void __launch_bounds__(NT3, 1) gemm_tc3_kernel(const __grid_constant_
             }
             mul_dsilu16(x, st.buf + sl * 2048, half, lane, p.alpha);   // (alpha folded in)
           }
-          if (DROP) {   // keep masks regenerated from (seed, offset, site, element index): nothing is stored for the backward pass
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-              float f[8];
-              drop_factors8(dkey, p.drop, ((uint64_t)m * p.N + n + c * 8) >> 3, f);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) x[c * 8 + j] *= f[j];
-            }
-          }
+          if (DROP) drop_apply_bits<16>(x, (dw[ss >> 1] >> ((ss & 1) * 16)) & 0xffffu, p.drop.scale);
           if (p.alpha != 1.0f && !dsilu) {
             const float2 al = make_float2(p.alpha, p.alpha);
 #pragma unroll
@@ -734,13 +736,17 @@ __global__ void __launch_bounds__(LN_NT, 1) gemm_ln3_kernel(const __grid_constan
     const int sw = lane & 7;
     float x[128];   // this thread's 128 x-values (its row, its column half): TMEM is read once, the values never leave registers
     uint32_t ut = 0;
-    DropKey dkey{};
-    if (DROP) dkey = drop_key(p.drop);
     for (int mt = blockIdx.x; mt < m_tiles; mt += gridDim.x, ++ut) {
       const int m0 = mt * BM;
       const int row0 = m0 + q * 32;
       const int m = m0 + r;
       const bool valid = m < p.M;
+      uint32_t dw[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};   // dropout keep-mask words of this thread's 4 x 32 columns
+      if (DROP && valid) {
+        const uint32_t* db = reinterpret_cast<const uint32_t*>(p.drop.bits);
+#pragma unroll
+        for (int s = 0; s < 4; ++s) dw[s] = db[(long)((cb >> 5) + s) * p.M + m];
+      }
       const uint32_t acc = ut & 1;
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + cb;
       if (p.has_res && lane == 0) {
@@ -771,15 +777,7 @@ __global__ void __launch_bounds__(LN_NT, 1) gemm_ln3_kernel(const __grid_constan
           v[g * 4] = (v[g * 4] + f.x) * p.alpha; v[g * 4 + 1] = (v[g * 4 + 1] + f.y) * p.alpha;
           v[g * 4 + 2] = (v[g * 4 + 2] + f.z) * p.alpha; v[g * 4 + 3] = (v[g * 4 + 3] + f.w) * p.alpha;
         }
-        if (DROP) {
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            float f[8];
-            drop_factors8(dkey, p.drop, ((uint64_t)m * 256 + cb + s * 32 + g * 8) >> 3, f);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[g * 8 + j] *= f[j];
-          }
-        }
+        if (DROP) drop_apply_bits<32>(v, dw[s], p.drop.scale);
         uint8_t* b = buf[s & 1];
         uint8_t* row = b + lane * 128;
         if (p.has_res) {
@@ -950,9 +948,12 @@ int gemm_tc3(const eec_gemm_desc* d, cudaStream_t st) {
   p.a_colsum = d->a_colsum; p.a_colsum_scale = d->a_colsum_scale;
   p.act_items = (d->a_kmajor && !d->accumulate) ? active_items() : ActiveItems{nullptr, 0, 0};   // forward form only: rows of A are frames
   p.drop = make_drop(d->drop_state, d->drop_p, d->drop_site);
-  if (p.drop.state)
+  p.drop.bits = d->drop_bits;
+  if (p.drop.state) {
     EEC_CHECK_ARG(epi == EPI_GENERIC && !four && d->a_kmajor && !d->accumulate && d->N % 16 == 0,
                   "gemm_tc3: dropout is fused into the SiLU / dSiLU / plain bf16-output epilogues of K-major-A GEMMs only");
+    EEC_CHECK_ARG(d->drop_bits != nullptr, "gemm (tensor-core path): dropout needs the keep-mask words of eec_dropout_bits(R = M, C = N, Cs = N, W = 16) in drop_bits");
+  }
   const int n_units = p.m_tiles * p.n_tiles * p.splits;
   const int grid = min(n_units, g_sms3);
   {
@@ -1020,6 +1021,9 @@ int gemm_ln3(const eec_gemm_desc* d, cudaStream_t st) {
   p.bias = d->bias; p.alpha = d->alpha; p.has_res = d->residual != nullptr; p.ln_bf16 = d->ln_dtype == EEC_BF16;
   p.ln_gamma = d->ln_gamma; p.ln_beta = d->ln_beta; p.ln_mean = d->ln_mean; p.ln_rstd = d->ln_rstd;
   p.drop = make_drop(d->drop_state, d->drop_p, d->drop_site);
+  p.drop.bits = d->drop_bits;
+  if (p.drop.state)
+    EEC_CHECK_ARG(d->drop_bits != nullptr, "gemm (LayerNorm tail): dropout needs the keep-mask words of eec_dropout_bits(R = M, C = 256, Cs = 256, W = 32) in drop_bits");
   p.act_items = active_items();
   static bool attr_set = false;
   if (!attr_set) {

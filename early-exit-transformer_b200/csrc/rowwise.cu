@@ -289,6 +289,47 @@ __global__ void __launch_bounds__(256) dropout_kernel(const TI* __restrict__ in,
     }
   }
 }
+// Keep-mask words for the tensor-core kernels: the GEMM / attention epilogues are instruction-issue bound, so they do not run Philox
+// themselves (measured: +75 % on the FFN epilogues); this kernel evaluates the SAME counter-based draws once per forward into
+// 1 bit per element, laid out so that the consumer's thread (one row, W consecutive columns) reads one coalesced word:
+//   logical tensor [R, C], element index r*Cs + c;  word (c/W, r) -> bits[(c/W)*R + r];  bit j <-> element (c/W)*W + j is kept.
+template <int W, typename TW>
+__global__ void __launch_bounds__(256) dropout_bits_kernel(TW* __restrict__ bits, long R, int C, long Cs, const DropArgs drop) {
+  pdl_trigger();
+  pdl_wait();
+  const DropKey key = drop_key(drop);
+  // the kernel is bound by the integer ALU pipe, so everything that is not Philox itself is kept off it: the ten round keys are
+  // formed once per thread (not per call), a draw is compared in place (hi half: w >= thr << 16; lo half: w << 16 >= thr << 16) and
+  // a kept element ORs a constant into the word under a predicate (two ALU instructions per element)
+  uint32_t rk0[10], rk1[10];
+#pragma unroll
+  for (int i = 0; i < 10; ++i) { rk0[i] = key.k0 + (uint32_t)i * 0x9E3779B9u; rk1[i] = key.k1 + (uint32_t)i * 0xBB67AE85u; }
+  const uint32_t thr_hi = drop.thr << 16;
+  const long cw = blockIdx.y;                                  // word column: grid.y = ceil(C / W) (no divisions in the loop)
+  for (long r = (long)blockIdx.x * blockDim.x + threadIdx.x; r < R; r += (long)gridDim.x * blockDim.x) {
+    const uint64_t g0 = ((uint64_t)r * Cs + (uint64_t)cw * W) >> 3;
+    uint32_t word = 0;
+#pragma unroll
+    for (int q = 0; q < W / 8; ++q) {
+      const uint64_t g = g0 + q;
+      uint32_t c0 = (uint32_t)g, c1 = (uint32_t)(g >> 32), c2 = key.c2, c3 = key.c3;
+#pragma unroll
+      for (int i = 0; i < 10; ++i) {
+        const uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ rk0[i], n2 = (uint32_t)(p0 >> 32) ^ c3 ^ rk1[i];
+        c1 = (uint32_t)p1; c3 = (uint32_t)p0; c0 = n0; c2 = n2;
+      }
+      const uint32_t w4[4] = {c0, c1, c2, c3};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if ((w4[i] << 16) >= thr_hi) word |= 1u << (q * 8 + 2 * i);        // low 16-bit draw  -> element 2i
+        if (w4[i] >= thr_hi) word |= 1u << (q * 8 + 2 * i + 1);            // high 16-bit draw -> element 2i + 1
+      }
+    }
+    bits[cw * R + r] = (TW)word;
+  }
+}
+
 __global__ void dropout_advance_kernel(uint64_t* state) {
   pdl_trigger();
   pdl_wait();
@@ -454,6 +495,22 @@ extern "C" int eec_dropout(const void* x, int in_dtype, void* y, int out_dtype, 
   else if (in_dtype == EEC_BF16 && out_dtype == EEC_BF16) EEC_DROPK(__nv_bfloat16, __nv_bfloat16);
   else EEC_DROPK(__nv_bfloat16, float);
 #undef EEC_DROPK
+  EEC_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int eec_dropout_bits(const uint64_t* state, float p, uint32_t site, int64_t R, int C, int64_t Cs, int W, void* bits,
+                                eec_stream_t stream) {
+  EEC_CHECK_ARG(state != nullptr && bits != nullptr, "dropout_bits: NULL state / bits");
+  EEC_CHECK_ARG(W == 16 || W == 32, "dropout_bits: word width must be 16 or 32 (got %d)", W);
+  EEC_CHECK_ARG(Cs % 8 == 0 && Cs >= C, "dropout_bits: row stride (%lld) must be a multiple of 8 and >= C", (long long)Cs);
+  if (R == 0 || C == 0) return 0;
+  DropArgs drop = make_drop(state, p, site);
+  if (!drop.state) { drop.state = state; drop.site = site; drop.thr = 0; drop.scale = 1.f; }   // p == 0: all kept
+  const int ncw = (C + W - 1) / W;
+  const dim3 grid((unsigned)min((long)cdiv64(R, 256), (long)max(1, 148 * 32 / ncw)), (unsigned)ncw);
+  if (W == 16) launch_pdl(dropout_bits_kernel<16, uint16_t>, grid, dim3(256), 0, S(stream), (uint16_t*)bits, (long)R, C, (long)Cs, drop);
+  else launch_pdl(dropout_bits_kernel<32, uint32_t>, grid, dim3(256), 0, S(stream), (uint32_t*)bits, (long)R, C, (long)Cs, drop);
   EEC_LAUNCH_CHECK();
   return 0;
 }

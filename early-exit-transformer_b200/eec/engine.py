@@ -159,18 +159,29 @@ def layer_forward(P: Dict[str, Tensor], W: Operands, pre: str, x: Tensor, key_le
     def stat():
         return (_empty((N,), f32, dev), _empty((N,), f32, dev)) if save else (None, None)
 
+    bf16 = cfg.precision == "bf16"
+    dsites = {}      # dropout sites whose keep-mask words the backward kernels read again (tensor-core path)
+
+    def site(k: int, R: int = 0, C: int = 0, Cs: int = 0, Wd: int = 0, keep: bool = False):
+        d = _at(drop, k)
+        if d is not None and bf16 and Wd:
+            d = d.with_bits(R, C, Cs, Wd)
+            if keep:
+                dsites[k] = d
+        return d
+
     def ffn(tag: str, x_in: Tensor, u: Tensor, ln_next_g, ln_next_b, ln_out_dtype, s_act: int, s_out: int):
         q = pre + tag + ".sequential."
         W1 = W.get(q + "1.weight", P[q + "1.weight"], (F, D))
         W2 = W.get(q + "4.weight", P[q + "4.weight"], (D, F))
         hpre = _empty((N, F), TD, dev) if save else None
         a = _empty((N, F), TD, dev)
-        linear(u, W1, a, N, F, D, bias=P[q + "1.bias"], act=ACT_SILU, preact=hpre, drop=_at(drop, s_act))
+        linear(u, W1, a, N, F, D, bias=P[q + "1.bias"], act=ACT_SILU, preact=hpre, drop=site(s_act, N, F, F, 16, keep=save))
         x_out = _empty((N, D), f32, dev)
         u_next = _empty((N, D), ln_out_dtype, dev)
         m, r = stat()
         linear(a, W2, x_out, N, D, F, bias=P[q + "4.bias"], alpha=0.5, residual=x_in, ln_gamma=ln_next_g, ln_beta=ln_next_b,
-               ln_out=u_next, ln_mean=m, ln_rstd=r, drop=_at(drop, s_out))
+               ln_out=u_next, ln_mean=m, ln_rstd=r, drop=site(s_out, N, D, D, 32))
         return x_out, u_next, hpre, a, m, r
 
     # ---- FFN1 (TA:185-187): x1 = x + 0.5*FFN(LN(x));  u2 = LN_attn(x1) fused into the GEMM tail
@@ -188,13 +199,13 @@ def layer_forward(P: Dict[str, Tensor], W: Operands, pre: str, x: Tensor, key_le
     linear(u2, Wqkv, qkv, N, 3 * D, D, bias=P[pre + "self_attn.in_proj_bias"])
     ctx = _empty((N, D), TD, dev)
     lse = _empty((B, H, T), f32, dev)
-    ops.attn_fwd(qkv, key_len, ctx, lse, B, T, H, drop=_at(drop, S_ATTN_P))
+    ops.attn_fwd(qkv, key_len, ctx, lse, B, T, H, drop=site(S_ATTN_P, B * H * T, T, 8 * ((T + 7) // 8), 32, keep=save))
     x2 = _empty((N, D), f32, dev)
     u3 = _empty((N, D), TD, dev)
     m3, r3 = stat()
     c = pre + "conv_module."
     linear(ctx, Wo, x2, N, D, D, bias=P[pre + "self_attn.out_proj.bias"], residual=x1, ln_gamma=P[c + "layer_norm.weight"],
-           ln_beta=P[c + "layer_norm.bias"], ln_out=u3, ln_mean=m3, ln_rstd=r3, drop=_at(drop, S_ATTN_OUT))
+           ln_beta=P[c + "layer_norm.bias"], ln_out=u3, ln_mean=m3, ln_rstd=r3, drop=site(S_ATTN_OUT, N, D, D, 32))
 
     # ---- convolution module (TA:42-75, 168-174)
     Wp1 = W.get(c + "sequential.0.weight", P[c + "sequential.0.weight"], (2 * D, D))
@@ -221,7 +232,7 @@ def layer_forward(P: Dict[str, Tensor], W: Operands, pre: str, x: Tensor, key_le
     m4, r4 = stat()
     q2 = pre + "ffn2.sequential."
     linear(s, Wp2, x3, N, D, D, bias=P[c + "sequential.5.bias"], residual=x2, ln_gamma=P[q2 + "0.weight"],
-           ln_beta=P[q2 + "0.bias"], ln_out=u4, ln_mean=m4, ln_rstd=r4, drop=_at(drop, S_CONV_OUT))
+           ln_beta=P[q2 + "0.bias"], ln_out=u4, ln_mean=m4, ln_rstd=r4, drop=site(S_CONV_OUT, N, D, D, 32))
 
     # ---- FFN2 + final LayerNorm (TA:207-211): x4 = x3 + 0.5*FFN(u4); y = LN_final(x4)
     x4, y, h2pre, a2, m5, r5 = ffn("ffn2", x3, u4, P[pre + "final_layer_norm.weight"], P[pre + "final_layer_norm.bias"], f32,
@@ -230,7 +241,7 @@ def layer_forward(P: Dict[str, Tensor], W: Operands, pre: str, x: Tensor, key_le
     if save:
         tape.update(dict(x=x, u1=u1, m1=m1, r1=r1, h1pre=h1pre, a1=a1, x1=x1, u2=u2, m2=m2, r2=r2, qkv=qkv, ctx=ctx, lse=lse,
                          x2=x2, u3=u3, m3=m3, r3=r3, z=z, g=g, c=cbuf, sm=sm, sr=sr, s=s, x3=x3, u4=u4, m4=m4, r4=r4,
-                         h2pre=h2pre, a2=a2, x4=x4, m5=m5, r5=r5, key_len=key_len, B=B, T=T, drop=drop))
+                         h2pre=h2pre, a2=a2, x4=x4, m5=m5, r5=r5, key_len=key_len, B=B, T=T, drop=drop, dsites=dsites))
     return y
 
 
@@ -244,7 +255,8 @@ def layer_backward(P, W: Operands, G: Dict[str, Tensor], pre: str, t: dict, dY: 
     c = pre + "conv_module."
 
     bf16 = cfg.precision == "bf16"
-    drop = t.get("drop")     # the forward's dropout site base: every mask is regenerated from it, none was stored
+    drop = t.get("drop")     # the forward's dropout site base: masks are regenerated from it (LayerNorm backward, fp32 path) ...
+    dsites = t.get("dsites") or {}   # ... or read back as the forward's keep-mask words (tensor-core dSiLU and attention backward)
 
     def ln_bwd(dy, x_in, m, r, key, accumulate, want_h=True, bias_key=None, bias_scale=1.0, s_out=None):
         """LayerNorm backward into the residual-gradient stream dX; also emits the GEMM-operand copy of dX and,
@@ -267,7 +279,7 @@ def layer_backward(P, W: Operands, G: Dict[str, Tensor], pre: str, t: dict, dY: 
         W2 = W.get(q + "4.weight", P[q + "4.weight"], (D, F))
         wgrad(dXh, a, G[q + "4.weight"], N, D, F, alpha=0.5)     # (this FFN's output-bias grad came fused from ln_bwd)
         dh = _empty((N, F), TD, dev)
-        dgrad(dXh, W2, dh, N, D, F, act=ACT_DSILU, preact=hpre, alpha=0.5, drop=_at(drop, s_act))
+        dgrad(dXh, W2, dh, N, D, F, act=ACT_DSILU, preact=hpre, alpha=0.5, drop=dsites.get(s_act, _at(drop, s_act)))
         wgrad(dh, u, G[q + "1.weight"], N, F, D, dbias=G[q + "1.bias"])
         du = _empty((N, D), f32, dev)
         dgrad(dh, W1, du, N, F, D)
@@ -306,7 +318,7 @@ def layer_backward(P, W: Operands, G: Dict[str, Tensor], pre: str, t: dict, dY: 
     dqkv = _empty((N, 3 * D), TD, dev)
     dvec = _empty((B * H * T,), f32, dev)
     dq32 = _empty((N, D), f32, dev) if bf16 else None
-    ops.attn_bwd(t["qkv"], t["ctx"], dctx, t["lse"], t["key_len"], dqkv, dvec, B, T, H, dq32, drop=_at(drop, S_ATTN_P))
+    ops.attn_bwd(t["qkv"], t["ctx"], dctx, t["lse"], t["key_len"], dqkv, dvec, B, T, H, dq32, drop=dsites.get(S_ATTN_P, _at(drop, S_ATTN_P)))
     wgrad(dqkv, t["u2"], G[pre + "self_attn.in_proj_weight"], N, 3 * D, D, dbias=G[pre + "self_attn.in_proj_bias"])
     du2 = _empty((N, D), f32, dev)
     dgrad(dqkv, Wqkv, du2, N, 3 * D, D)

@@ -39,6 +39,7 @@ class GemmDesc(C.Structure):
         ("a_colsum", vp),
         ("a_colsum_scale", f32),
         ("drop_state", vp), ("drop_p", f32), ("drop_site", C.c_uint32),
+        ("drop_bits", vp),
     ]
 
 
@@ -48,8 +49,9 @@ _SIGS = {
     "eec_ffn_fwd": [vp, vp, vp, vp, vp, vp, f32, vp, vp, vp, vp, i32, vp, vp, vp, i32, i32, i32, vp],
     "eec_layernorm_fwd": [vp, vp, vp, vp, i32, vp, vp, i32, i32, vp],
     "eec_layernorm_bwd": [vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, i32, vp, f32, vp, f32, u32, i32, i32, vp],
-    "eec_attn_fwd": [vp, i32, vp, vp, vp, i32, i32, i32, i32, vp, f32, u32, vp],
-    "eec_attn_bwd": [vp, vp, vp, i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp, f32, u32, vp],
+    "eec_attn_fwd": [vp, i32, vp, vp, vp, i32, i32, i32, i32, vp, f32, u32, vp, vp],
+    "eec_attn_bwd": [vp, vp, vp, i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp, f32, u32, vp, vp],
+    "eec_dropout_bits": [vp, f32, u32, i64, i32, i64, i32, vp, vp],
     "eec_dropout": [vp, i32, vp, i32, i64, vp, f32, u32, vp],
     "eec_dropout_advance": [vp, vp],
     "eec_dwconv_bn_silu_eval": [vp, i32, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp],

@@ -16,14 +16,25 @@ Tensor = torch.Tensor
 
 class Drop:
     """One dropout site of one forward pass: (device state {seed, offset} as an int64[2] tensor, probability, site id).
-    Kernels regenerate the keep mask from these three and the element index (include/eec.h "dropout")."""
-    __slots__ = ("state", "p", "site")
+    The keep mask is a pure function of these three and the element index (include/eec.h "dropout").  `bits` (optional) holds
+    the mask as 1 bit per element (eec_dropout_bits) for the tensor-core kernels, whose epilogues do not run Philox themselves;
+    the same words serve the forward and the backward kernel of the site."""
+    __slots__ = ("state", "p", "site", "bits")
 
-    def __init__(self, state: Tensor, p: float, site: int):
-        self.state, self.p, self.site = state, float(p), int(site)
+    def __init__(self, state: Tensor, p: float, site: int, bits: Optional[Tensor] = None):
+        self.state, self.p, self.site, self.bits = state, float(p), int(site), bits
 
     def at(self, k: int) -> "Drop":
         return Drop(self.state, self.p, self.site + k)
+
+    def with_bits(self, R: int, C: int, Cs: int, W: int) -> "Drop":
+        """this site with its keep-mask words generated (one launch): logical tensor [R, C], element index r*Cs + c"""
+        if self.p <= 0.0:
+            return self
+        words = R * ((C + W - 1) // W)
+        bits = torch.empty(words, dtype=torch.int16 if W == 16 else torch.int32, device=self.state.device)
+        call("eec_dropout_bits", self.state.data_ptr(), self.p, self.site, R, C, Cs, W, bits.data_ptr(), stream())
+        return Drop(self.state, self.p, self.site, bits)
 
 
 def _d(drop):
@@ -78,7 +89,10 @@ def gemm(
     d.ld_ln = N
     d.ln_mean, d.ln_rstd = ptr(ln_mean), ptr(ln_rstd)
     d.a_colsum, d.a_colsum_scale = ptr(a_colsum), a_colsum_scale
+    if drop is not None and drop.p > 0.0 and drop.bits is None and A.dtype == torch.bfloat16:
+        drop = drop.with_bits(M, N, N, 32 if ln_out is not None else 16)    # (callers that also run the backward keep the words)
     d.drop_state, d.drop_p, d.drop_site = _d(drop)
+    d.drop_bits = ptr(drop.bits) if (drop is not None and drop.p > 0.0) else None
     call("eec_gemm", C.byref(d), stream())
 
 
@@ -104,13 +118,26 @@ def layernorm_bwd(dy, x, mean, rstd, gamma, dx, accumulate, dgamma, dbeta, dx_co
          stream())
 
 
+def attn_drop(drop: Optional[Drop], qkv, B, T, H) -> Optional[Drop]:
+    """the attention-probability site with keep-mask words when the tensor-core kernels will run (bf16 operands)"""
+    if drop is None or drop.p <= 0.0 or drop.bits is not None or qkv.dtype != torch.bfloat16:
+        return drop
+    return drop.with_bits(B * H * T, T, 8 * ((T + 7) // 8), 32)
+
+
+def _bits(drop):
+    return ptr(drop.bits) if (drop is not None and drop.p > 0.0) else None
+
+
 def attn_fwd(qkv, key_len, ctx, lse, B, T, H, drop: Optional[Drop] = None):
-    call("eec_attn_fwd", ptr(qkv), dt(qkv), ptr(key_len), ptr(ctx), ptr(lse), B, T, H, 32, *_d(drop), stream())
+    drop = attn_drop(drop, qkv, B, T, H)
+    call("eec_attn_fwd", ptr(qkv), dt(qkv), ptr(key_len), ptr(ctx), ptr(lse), B, T, H, 32, *_d(drop), _bits(drop), stream())
 
 
 def attn_bwd(qkv, ctx, dctx, lse, key_len, dqkv, dvec, B, T, H, dq32=None, drop: Optional[Drop] = None):
+    drop = attn_drop(drop, qkv, B, T, H)
     call("eec_attn_bwd", ptr(qkv), ptr(ctx), ptr(dctx), dt(qkv), ptr(lse), ptr(key_len), ptr(dqkv), ptr(dvec), ptr(dq32), B, T,
-         H, 32, *_d(drop), stream())
+         H, 32, *_d(drop), _bits(drop), stream())
 
 
 def dropout(x, y, drop: Drop):

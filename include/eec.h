@@ -83,6 +83,8 @@ typedef struct {
   /* dropout (see "dropout" below) applied right after the activation: v = act(v + bias); v = dropout(v); v = alpha * v; ...
    * element index of (m, n) is m*N + n.  SILU / DSILU / NONE epilogues and the LayerNorm tail; drop_state NULL = off.     */
   const uint64_t* drop_state; float drop_p; uint32_t drop_site;
+  const void* drop_bits;    /* bf16 (tensor-core) path: keep-mask words of eec_dropout_bits for this site -- R = M, C = Cs = N, W = 16
+                             * (SILU / DSILU / NONE epilogues) or W = 32 (LayerNorm tail); the fp32 path evaluates Philox in place */
 } eec_gemm_desc;
 int eec_gemm(const eec_gemm_desc* d, eec_stream_t stream);
 
@@ -97,6 +99,12 @@ int eec_gemm(const eec_gemm_desc* d, eec_stream_t stream);
 /* y[i] = x[i] * mask_i * scale  (dtype enums of x / y; x == y allowed when the dtypes agree) */
 int eec_dropout(const void* x, int in_dtype, void* y, int out_dtype, int64_t n, const uint64_t* state, float p,
                 uint32_t site, eec_stream_t stream);
+/* Keep-mask words for the tensor-core kernels.  Their epilogues are instruction-issue bound, so they do not evaluate Philox
+ * themselves: this kernel evaluates the same draws once per forward into 1 bit per element, and the forward AND backward kernels of
+ * the site read them (one coalesced word per thread and tile).  Logical tensor [R, C] with element index r*Cs + c (Cs % 8 == 0),
+ * word width W = 16 | 32:  word (c/W, r) -> bits[(c/W)*R + r] (uint16 / uint32), bit j <-> element (c/W)*W + j is kept. */
+int eec_dropout_bits(const uint64_t* state, float p, uint32_t site, int64_t R, int C, int64_t Cs, int W, void* bits,
+                     eec_stream_t stream);
 /* state[1] += 1 (one launch; lives inside the captured training step) */
 int eec_dropout_advance(uint64_t* state, eec_stream_t stream);
 
@@ -133,12 +141,13 @@ int eec_layernorm_bwd(const float* dy, const float* x, const float* mean, const 
  * element index of probability (b, h, t, t') is ((b*H + h)*T + t) * (8*ceil(T/8)) + t'. */
 int eec_attn_fwd(const void* qkv, int dtype, const int32_t* key_len, void* ctx, float* lse,
                  int B, int T, int H, int dh, const uint64_t* drop_state, float drop_p, uint32_t drop_site,
+                 const void* drop_bits /* EEC_BF16: eec_dropout_bits(R = B*H*T, C = T, Cs = 8*ceil(T/8), W = 32) */,
                  eec_stream_t stream);
 /* dvec: fp32 workspace [B*H*T] (row dots dO.O); dq32: fp32 workspace [B*T, H*dh] (bf16 path: dQ
  * partials of the key blocks are summed there with vector atomics; may be NULL for EEC_F32) */
 int eec_attn_bwd(const void* qkv, const void* ctx, const void* dctx, int dtype, const float* lse,
                  const int32_t* key_len, void* dqkv, float* dvec, float* dq32, int B, int T, int H, int dh,
-                 const uint64_t* drop_state, float drop_p, uint32_t drop_site, eec_stream_t stream);
+                 const uint64_t* drop_state, float drop_p, uint32_t drop_site, const void* drop_bits, eec_stream_t stream);
 
 /* ---- conformer convolution module interior (TA:52-65) ------------------------------
  * g [B,T,C] (dtype) -> depthwise conv k (SAME, zero pad per utterance) + bias.
