@@ -64,6 +64,7 @@ struct P3 {
   long long* tl;   // EEC_GEMM_TL=1 (perf triage only): clock64 accumulators of CTA 0, see gemm_tc3()
   DropArgs drop;   // DROP instantiations only: dropout right after the activation, element index m*N + n
   ActiveItems act_items;   // m-tiles past the active-item limit are skipped by all three roles (early-exit inference)
+  int l2_pf;               // operand L2 prefetch distance in k-blocks (0 = off): the producer asks L2 for k-block kb + l2_pf when it loads kb
 };
 
 // per-warp staging: values -> swizzled smem box -> bulk tensor store / reduce of a [32 rows x 32 cols] box
@@ -263,6 +264,20 @@ __global__ void __launch_bounds__(NT3, 1) gemm_tc3_kernel(const __grid_constant_
           if (p.debug & 32) { mbar_arrive(&full_bar[s]); continue; }   // triage: MMAs run on whatever is in smem
           mbar_expect_tx(&full_bar[s], STAGE_BYTES);
           const int k = kb * BK;
+          if (p.l2_pf && kb + p.l2_pf < kb1) {
+            // the ring holds NST x 48 KB per SM and an HBM round trip is ~1.9 us, so a long-K GEMM streams at (bytes in flight) /
+            // latency; asking L2 for the operands a few k-blocks ahead turns the ring's loads into L2 hits (shorter round trip)
+            const int kp = k + p.l2_pf * BK;
+            if (A_KMAJ) tma_prefetch_l2_2d(&tmA, kp, m0);
+            else { tma_prefetch_l2_2d(&tmA, m0, kp); tma_prefetch_l2_2d(&tmA, m0 + 64, kp); }
+            if (B_KMAJ) {
+              tma_prefetch_l2_2d(&tmB, kp, n0);
+              if (EPI == EPI_GLU) tma_prefetch_l2_2d(&tmB, kp, p.N / 2 + n0);
+            } else {
+#pragma unroll
+              for (int a = 0; a < BN / 64; ++a) tma_prefetch_l2_2d(&tmB, n0 + a * 64, kp);
+            }
+          }
           if (A_KMAJ) {
             tma_load_2d(sa, &tmA, &full_bar[s], k, m0);
           } else {
@@ -638,6 +653,7 @@ struct PLN {
   float alpha;
   int has_res, ln_bf16;
   const float* ln_gamma; const float* ln_beta; float* ln_mean; float* ln_rstd;
+  int l2_pf;       // A-operand L2 prefetch distance in k-blocks (0 = off), see gemm_tc3_kernel
   DropArgs drop;   // DROP instantiation only: x = residual + alpha * dropout(A W^T + bias), element index m*256 + n
   ActiveItems act_items;
 };
@@ -695,6 +711,7 @@ __global__ void __launch_bounds__(LN_NT, 1) gemm_ln3_kernel(const __grid_constan
           mbar_wait(&empty_bar[s], ph);
           uint8_t* sa = smem + s * STAGE_BYTES;
           mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+          if (p.l2_pf && kb + p.l2_pf < total_kb) tma_prefetch_l2_2d(&tmA, (kb + p.l2_pf) * BK, m0);   // (the weight tile is L2 resident anyway)
           tma_load_2d(sa, &tmA, &full_bar[s], kb * BK, m0);
           tma_load_2d(sa + A_BYTES, &tmB, &full_bar[s], kb * BK, 0);
           if (++s == LN_NSTAGE) { s = 0; ph ^= 1; }
@@ -966,6 +983,9 @@ int gemm_tc3(const eec_gemm_desc* d, cudaStream_t st) {
   static int dbg = -1;
   if (dbg < 0) { const char* e = getenv("EEC_GEMM_DEBUG"); dbg = e ? atoi(e) : 0; }
   p.debug = dbg;
+  static int pf_env = -1;
+  if (pf_env < 0) { const char* e = getenv("EEC_GEMM_L2PF"); pf_env = e ? atoi(e) : 0; }
+  p.l2_pf = (p.kb_per_split >= 16) ? pf_env : 0;   // long-K forms only (weight gradients, K = 2048 dgrad)
   static int tl_env = -1;
   static long long* tl_buf = nullptr;
   if (tl_env < 0) { const char* e = getenv("EEC_GEMM_TL"); tl_env = (e && e[0] == '1') ? 1 : 0; }
@@ -1020,6 +1040,11 @@ int gemm_ln3(const eec_gemm_desc* d, cudaStream_t st) {
   p.M = d->M; p.K = d->K; p.m_tiles = cdiv(d->M, BM);
   p.bias = d->bias; p.alpha = d->alpha; p.has_res = d->residual != nullptr; p.ln_bf16 = d->ln_dtype == EEC_BF16;
   p.ln_gamma = d->ln_gamma; p.ln_beta = d->ln_beta; p.ln_mean = d->ln_mean; p.ln_rstd = d->ln_rstd;
+  {
+    static int pf_env = -1;
+    if (pf_env < 0) { const char* e = getenv("EEC_GEMM_L2PF"); pf_env = e ? atoi(e) : 0; }
+    p.l2_pf = (cdiv(d->K, BK) >= 16) ? pf_env : 0;
+  }
   p.drop = make_drop(d->drop_state, d->drop_p, d->drop_site);
   p.drop.bits = d->drop_bits;
   if (p.drop.state)

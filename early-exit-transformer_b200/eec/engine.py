@@ -147,8 +147,60 @@ def _at(drop, k):
     return drop.at(k) if drop is not None else None
 
 
+def site_geometry(B: int, T: int):
+    """logical tensor (R, C, Cs, W) of every dropout site of a layer run on B utterances of T frames (include/eec.h eec_dropout_bits)"""
+    N = B * T
+    g = {k: (N, D, D, 32) for k in (S_FFN1_OUT, S_ATTN_OUT, S_CONV_OUT, S_FFN2_OUT)}
+    g[S_FFN1_ACT] = g[S_FFN2_ACT] = (N, F, F, 16)
+    g[S_ATTN_P] = (B * H * T, T, 8 * ((T + 7) // 8), 32)
+    return g
+
+
+_SIDE_STREAMS: Dict[torch.device, "torch.cuda.Stream"] = {}
+
+
+class MaskPlan:
+    """Keep-mask words of every dropout site of one forward (tensor-core path), generated on a SIDE stream: the generator is
+    integer-ALU work that depends on nothing but the forward's {seed, counter}, while the compute stream runs tensor-core / TMA
+    bound kernels -- so all layers' words are issued up front on a second stream (a parallel branch of the step's CUDA graph)
+    and each layer waits for its own event.  Buffers are allocated on the compute stream first: the side stream only ever
+    touches them before the event the compute stream waits on, so the caching allocator's single-stream bookkeeping stays valid."""
+
+    def __init__(self, drop0: ops.Drop, layers):   # layers: [(uid, B, T)] in execution order
+        dev = drop0.state.device
+        cur = torch.cuda.current_stream(dev)
+        side = _SIDE_STREAMS.get(dev)
+        if side is None:
+            side = _SIDE_STREAMS[dev] = torch.cuda.Stream(device=dev)
+        self.sites, self.events, fills = {}, {}, {}
+        for uid, B, T in layers:
+            base = drop0.at((1 + uid) * SITES_PER_LAYER)
+            self.sites[uid], fills[uid] = {}, []
+            for k, geo in site_geometry(B, T).items():
+                d, fill = base.at(k).alloc_bits(*geo)
+                self.sites[uid][k] = d
+                fills[uid].append(fill)
+        side.wait_stream(cur)          # (the drop state was written on the compute stream)
+        with torch.cuda.stream(side):
+            for uid, _, _ in layers:
+                for fill in fills[uid]:
+                    fill()
+                ev = torch.cuda.Event()
+                ev.record(side)
+                self.events[uid] = ev
+        self.side = side
+
+    def take(self, uid: int):
+        """-> {site: Drop with words}; the compute stream waits for this layer's words"""
+        torch.cuda.current_stream(self.side.device).wait_event(self.events[uid])
+        return self.sites[uid]
+
+    def join(self):
+        torch.cuda.current_stream(self.side.device).wait_stream(self.side)
+
+
 def layer_forward(P: Dict[str, Tensor], W: Operands, pre: str, x: Tensor, key_len: Tensor, B: int, T: int, cfg: Config,
-                  training: bool, tape: Optional[dict], drop: Optional[ops.Drop] = None):
+                  training: bool, tape: Optional[dict], drop: Optional[ops.Drop] = None, masks: Optional[dict] = None):
     """x: fp32 [B*T, 256] -> fp32 [B*T, 256].  TA:176-212.  `drop` = this layer's dropout site base (train mode, p > 0)."""
     N = B * T
     dev = x.device
@@ -165,7 +217,7 @@ def layer_forward(P: Dict[str, Tensor], W: Operands, pre: str, x: Tensor, key_le
     def site(k: int, R: int = 0, C: int = 0, Cs: int = 0, Wd: int = 0, keep: bool = False):
         d = _at(drop, k)
         if d is not None and bf16 and Wd:
-            d = d.with_bits(R, C, Cs, Wd)
+            d = masks[k] if masks is not None else d.with_bits(R, C, Cs, Wd)   # (MaskPlan: generated ahead on the side stream)
             if keep:
                 dsites[k] = d
         return d
@@ -427,6 +479,16 @@ def model_forward(P: Dict[str, Tensor], W: Operands, cfg: Config, src: Tensor, l
     def layer_drop(uid: int):
         return drop0.at((1 + uid) * SITES_PER_LAYER) if drop0 is not None else None
 
+    plan = None
+    if drop0 is not None and cfg.precision == "bf16" and src.shape[2] >= 7:
+        Tp = ((src.shape[2] - 3) // 2 + 1 - 3) // 2 + 1
+        order = []
+        for e in range(cfg.n_exits):
+            order += [(e * cfg.n_layers + l, src.shape[0], Tp) for l in range(cfg.n_layers)]
+            if cfg.splitformer and (e == 0 or e == cfg.n_exits - 1):
+                order.append((1000 + e // (cfg.n_exits - 1), src.shape[0], (Tp + 1) // 2))
+        plan = MaskPlan(drop0, order)
+
     x, T = frontend_forward(P, W, src, cfg, tape.front if tape else None, drop0)
     B = src.shape[0]
     N = B * T
@@ -447,7 +509,8 @@ def model_forward(P: Dict[str, Tensor], W: Operands, cfg: Config, src: Tensor, l
         for l in range(cfg.n_layers):
             pre = f"conformer.{e}.conformer_layers.{l}."
             lt = {"pre": pre} if tape else None
-            x = layer_forward(P, W, pre, x, key_len, B, T, cfg, training, lt, layer_drop(e * cfg.n_layers + l))
+            uid = e * cfg.n_layers + l
+            x = layer_forward(P, W, pre, x, key_len, B, T, cfg, training, lt, layer_drop(uid), plan.take(uid) if plan else None)
             if tape:
                 tape.layers.append(lt)
         br = None
@@ -463,7 +526,7 @@ def model_forward(P: Dict[str, Tensor], W: Operands, cfg: Config, src: Tensor, l
             ops.encoder_lengths(lengths_dev, len2, T2, 2, pad)
             pre = f"conformer_parallel.{i}.conformer_layers.0."
             br = {"pre": pre} if tape else None
-            yd = layer_forward(P, W, pre, xd, len2, B, T2, cfg, training, br, layer_drop(1000 + i))
+            yd = layer_forward(P, W, pre, xd, len2, B, T2, cfg, training, br, layer_drop(1000 + i), plan.take(1000 + i) if plan else None)
             if x is x_in:
                 x = x.clone()
             ops.repeat2_add(yd, x, B, T)
@@ -481,6 +544,8 @@ def model_forward(P: Dict[str, Tensor], W: Operands, cfg: Config, src: Tensor, l
             side.setdefault("entropy", []).append(en.view(B, T))
         if tape:
             tape.heads.append({"xh": xh})
+    if plan is not None:
+        plan.join()
     if want_side:
         side["key_len"] = key_len
     if tape:

@@ -27,14 +27,24 @@ class Drop:
     def at(self, k: int) -> "Drop":
         return Drop(self.state, self.p, self.site + k)
 
-    def with_bits(self, R: int, C: int, Cs: int, W: int) -> "Drop":
-        """this site with its keep-mask words generated (one launch): logical tensor [R, C], element index r*Cs + c"""
-        if self.p <= 0.0:
-            return self
+    def alloc_bits(self, R: int, C: int, Cs: int, W: int):
+        """-> (this site with an UNFILLED word buffer, fill()): allocation and generation are separate so that the engine can
+        allocate on the compute stream and generate on a side stream (logical tensor [R, C], element index r*Cs + c)"""
         words = R * ((C + W - 1) // W)
         bits = torch.empty(words, dtype=torch.int16 if W == 16 else torch.int32, device=self.state.device)
-        call("eec_dropout_bits", self.state.data_ptr(), self.p, self.site, R, C, Cs, W, bits.data_ptr(), stream())
-        return Drop(self.state, self.p, self.site, bits)
+        d = Drop(self.state, self.p, self.site, bits)
+
+        def fill():
+            call("eec_dropout_bits", d.state.data_ptr(), d.p, d.site, R, C, Cs, W, bits.data_ptr(), stream())
+        return d, fill
+
+    def with_bits(self, R: int, C: int, Cs: int, W: int) -> "Drop":
+        """this site with its keep-mask words generated (one launch on the current stream)"""
+        if self.p <= 0.0:
+            return self
+        d, fill = self.alloc_bits(R, C, Cs, W)
+        fill()
+        return d
 
 
 def _d(drop):
