@@ -114,15 +114,53 @@ def dgrad(dY, W, out, M, N_out, K_in, **kw):
 _FUSE_COLSUM = not (os.environ.get("EEC_GEMM_V1") == "1" or os.environ.get("EEC_GEMM_V2") == "1" or os.environ.get("EEC_FORCE_SIMT") == "1")
 
 
-def wgrad(dY, X, dW, M, N_out, K_in, alpha=1.0, dbias=None):
+class SideQueue:
+    """Weight-gradient GEMMs off the critical path.  The data-gradient chain of backward (dgrad -> LayerNorm backward -> dgrad ...)
+    never reads a weight gradient, so every wgrad is issued on a second stream: it starts as soon as its dY exists (event fork)
+    and only has to finish before the gradients are consumed (join before the data-parallel hook of its exit group / at the end of
+    backward).  Inside the step's CUDA graph this is a parallel branch: the wgrad CTAs fill the tails and launch gaps of the
+    chain's kernels and co-reside with its bandwidth-bound ones.  Operand tensors are kept referenced until the join, so the
+    caching allocator cannot hand their memory to a later allocation of the compute stream while the side stream still reads them.
+    bf16 path only (there every dY operand is a private copy; the fp32 path feeds the in-place residual gradient)."""
+
+    def __init__(self, dev):
+        side = _SIDE_STREAMS.get(("wgrad", dev))
+        if side is None:
+            side = _SIDE_STREAMS[("wgrad", dev)] = torch.cuda.Stream(device=dev)
+        self.dev, self.side, self.refs = dev, side, []
+
+    def run(self, fn, *tensors):
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.dev))
+        self.side.wait_event(ev)
+        with torch.cuda.stream(self.side):
+            fn()
+        self.refs.extend(tensors)
+
+    def join(self):
+        torch.cuda.current_stream(self.dev).wait_stream(self.side)
+        self.refs.clear()
+
+
+_WGRAD_SIDE = os.environ.get("EEC_WGRAD_SIDE", "1") != "0"
+
+
+def wgrad(dY, X, dW, M, N_out, K_in, alpha=1.0, dbias=None, sq: Optional["SideQueue"] = None):
     """dW[N_out,K_in] += alpha * dY[M,N_out]^T @ X[M,K_in];  dbias[N_out] += column sums of dY (optional).
     On the tcgen05 path the bias gradient is summed from the dY tiles while they sit in shared memory as the GEMM's
-    A operand (eec_gemm_desc.a_colsum): the [M, N_out] tensor is not read a second time."""
+    A operand (eec_gemm_desc.a_colsum): the [M, N_out] tensor is not read a second time.
+    sq: run on the side stream (SideQueue)."""
     fuse = dbias is not None and _FUSE_COLSUM and dY.dtype == torch.bfloat16
-    ops.gemm(dY, X, dW, N_out, K_in, M, a_kmajor=False, b_kmajor=False, lda=N_out, ldb=K_in, alpha=alpha, accumulate=True,
-             a_colsum=dbias if fuse else None)
-    if dbias is not None and not fuse:
-        ops.colsum(dY, dbias, M, N_out)
+
+    def go():
+        ops.gemm(dY, X, dW, N_out, K_in, M, a_kmajor=False, b_kmajor=False, lda=N_out, ldb=K_in, alpha=alpha, accumulate=True,
+                 a_colsum=dbias if fuse else None)
+        if dbias is not None and not fuse:
+            ops.colsum(dY, dbias, M, N_out)
+    if sq is not None and dY.dtype == torch.bfloat16:
+        sq.run(go, dY, X)
+    else:
+        go()
 
 
 def to_act(x32: Tensor, cfg: Config) -> Tensor:
@@ -297,7 +335,8 @@ def layer_forward(P: Dict[str, Tensor], W: Operands, pre: str, x: Tensor, key_le
     return y
 
 
-def layer_backward(P, W: Operands, G: Dict[str, Tensor], pre: str, t: dict, dY: Tensor, cfg: Config) -> Tensor:
+def layer_backward(P, W: Operands, G: Dict[str, Tensor], pre: str, t: dict, dY: Tensor, cfg: Config,
+                   sq: Optional[SideQueue] = None) -> Tensor:
     """dY: fp32 grad wrt the layer output -> fp32 grad wrt the layer input (dY's buffer is reused)."""
     B, T = t["B"], t["T"]
     N = B * T
@@ -329,10 +368,10 @@ def layer_backward(P, W: Operands, G: Dict[str, Tensor], pre: str, t: dict, dY: 
         q = pre + tag + ".sequential."
         W1 = W.get(q + "1.weight", P[q + "1.weight"], (F, D))
         W2 = W.get(q + "4.weight", P[q + "4.weight"], (D, F))
-        wgrad(dXh, a, G[q + "4.weight"], N, D, F, alpha=0.5)     # (this FFN's output-bias grad came fused from ln_bwd)
+        wgrad(dXh, a, G[q + "4.weight"], N, D, F, alpha=0.5, sq=sq)     # (this FFN's output-bias grad came fused from ln_bwd)
         dh = _empty((N, F), TD, dev)
         dgrad(dXh, W2, dh, N, D, F, act=ACT_DSILU, preact=hpre, alpha=0.5, drop=dsites.get(s_act, _at(drop, s_act)))
-        wgrad(dh, u, G[q + "1.weight"], N, F, D, dbias=G[q + "1.bias"])
+        wgrad(dh, u, G[q + "1.weight"], N, F, D, dbias=G[q + "1.bias"], sq=sq)
         du = _empty((N, D), f32, dev)
         dgrad(dh, W1, du, N, F, D)
         return ln_bwd(du, x_in, m, r, q + "0.", True, want_h, next_bias, s_out=next_site)
@@ -344,7 +383,7 @@ def layer_backward(P, W: Operands, G: Dict[str, Tensor], pre: str, t: dict, dY: 
     # conv module: x3 = x2 + pw2(s) + b
     Wp1 = W.get(c + "sequential.0.weight", P[c + "sequential.0.weight"], (2 * D, D))
     Wp2 = W.get(c + "sequential.5.weight", P[c + "sequential.5.weight"], (D, D))
-    wgrad(dXh, t["s"], G[c + "sequential.5.weight"].view(D, D), N, D, D)
+    wgrad(dXh, t["s"], G[c + "sequential.5.weight"].view(D, D), N, D, D, sq=sq)
     ds = _empty((N, D), TD, dev)
     dgrad(dXh, Wp2, ds, N, D, D)
     dc = _empty((N, D), f32, dev)
@@ -356,7 +395,7 @@ def layer_backward(P, W: Operands, G: Dict[str, Tensor], pre: str, t: dict, dY: 
     ops.dwconv_bwd(dc, t["g"], wdw, dg, G[c + "sequential.2.weight"].view(D, KW), G[c + "sequential.2.bias"], B, T, KW)
     dz = _empty((N, 2 * D), TD, dev)
     ops.glu_bwd(t["z"], dg, dz)
-    wgrad(dz, t["u3"], G[c + "sequential.0.weight"].view(2 * D, D), N, 2 * D, D, dbias=G[c + "sequential.0.bias"])
+    wgrad(dz, t["u3"], G[c + "sequential.0.weight"].view(2 * D, D), N, 2 * D, D, dbias=G[c + "sequential.0.bias"], sq=sq)
     du3 = _empty((N, D), f32, dev)
     dgrad(dz, Wp1, du3, N, 2 * D, D)
     dXh = ln_bwd(du3, t["x2"], t["m3"], t["r3"], c + "layer_norm.", True, True, pre + "self_attn.out_proj.bias", s_out=S_ATTN_OUT)
@@ -364,14 +403,14 @@ def layer_backward(P, W: Operands, G: Dict[str, Tensor], pre: str, t: dict, dY: 
     # MHSA: x2 = x1 + out_proj(attn(qkv)) ; qkv = in_proj(u2); u2 = LN(x1)
     Wqkv = W.get(pre + "self_attn.in_proj_weight", P[pre + "self_attn.in_proj_weight"], (3 * D, D))
     Wo = W.get(pre + "self_attn.out_proj.weight", P[pre + "self_attn.out_proj.weight"], (D, D))
-    wgrad(dXh, t["ctx"], G[pre + "self_attn.out_proj.weight"], N, D, D)
+    wgrad(dXh, t["ctx"], G[pre + "self_attn.out_proj.weight"], N, D, D, sq=sq)
     dctx = _empty((N, D), TD, dev)
     dgrad(dXh, Wo, dctx, N, D, D)
     dqkv = _empty((N, 3 * D), TD, dev)
     dvec = _empty((B * H * T,), f32, dev)
     dq32 = _empty((N, D), f32, dev) if bf16 else None
     ops.attn_bwd(t["qkv"], t["ctx"], dctx, t["lse"], t["key_len"], dqkv, dvec, B, T, H, dq32, drop=dsites.get(S_ATTN_P, _at(drop, S_ATTN_P)))
-    wgrad(dqkv, t["u2"], G[pre + "self_attn.in_proj_weight"], N, 3 * D, D, dbias=G[pre + "self_attn.in_proj_bias"])
+    wgrad(dqkv, t["u2"], G[pre + "self_attn.in_proj_weight"], N, 3 * D, D, dbias=G[pre + "self_attn.in_proj_bias"], sq=sq)
     du2 = _empty((N, D), f32, dev)
     dgrad(dqkv, Wqkv, du2, N, 3 * D, D)
     dXh = ln_bwd(du2, t["x1"], t["m2"], t["r2"], pre + "self_attn_layer_norm.", True, True, pre + "ffn1.sequential.4.bias", 0.5,
@@ -593,6 +632,7 @@ def model_backward(P, W: Operands, cfg: Config, tape: Tape, gout: Tensor, names:
         off += k
     G["__flat__"] = flat
     spans = group_ranges(P, names, E) if on_ready is not None else None
+    sq = SideQueue(dev) if (_WGRAD_SIDE and cfg.precision == "bf16") else None   # weight gradients run beside the data-gradient chain
     dX: Optional[Tensor] = None
     li = len(tape.layers)
     for e in reversed(range(E)):
@@ -601,7 +641,7 @@ def model_backward(P, W: Operands, cfg: Config, tape: Tape, gout: Tensor, names:
         ops.logsoftmax_bwd(gout[e], tape.out[e], dlog)
         dlogh = to_act(dlog, cfg)
         Wh = W.get(f"linears.{e}.weight", P[f"linears.{e}.weight"], (V, D))
-        wgrad(dlogh, tape.heads[e]["xh"], G[f"linears.{e}.weight"], N, V, D)
+        wgrad(dlogh, tape.heads[e]["xh"], G[f"linears.{e}.weight"], N, V, D, sq=sq)
         ops.colsum(dlog, G[f"linears.{e}.bias"], N, V)
         if dX is None:
             dX = _empty((N, D), f32, dev)
@@ -617,16 +657,20 @@ def model_backward(P, W: Operands, cfg: Config, tape: Tape, gout: Tensor, names:
             T2 = (T + 1) // 2
             dyd = _empty((B * T2, D), f32, dev)
             ops.repeat2_bwd(dX, dyd, B, T)
-            d_in_extra = layer_backward(P, W, G, br["pre"], br, dyd, cfg)
+            d_in_extra = layer_backward(P, W, G, br["pre"], br, dyd, cfg, sq)
         for l in reversed(range(cfg.n_layers)):
             li -= 1
             lt = tape.layers[li]
-            dX = layer_backward(P, W, G, lt["pre"], lt, dX, cfg)
+            dX = layer_backward(P, W, G, lt["pre"], lt, dX, cfg, sq)
         if d_in_extra is not None:
             ops.stride2_scatter_add(d_in_extra, dX, B, T)
         if spans is not None:
+            if sq is not None:
+                sq.join()          # this group's weight gradients are final before its slice leaves for the all-reduce
             on_ready(flat, *spans[0][e])
     frontend_backward(P, W, G, tape.front, dX, cfg)
+    if sq is not None:
+        sq.join()
     if on_ready is not None:
         if spans is None:
             on_ready(flat, 0, total)
