@@ -499,9 +499,18 @@ def cpu_baseline(layers, sample_b=8, steps=1):
     for _ in range(steps):
         cpu_step(sd, src, lengths, targets, tl)
     dt = (time.perf_counter() - t0) / steps
+    # BASELINE configs[0] (the reference's CPU-runnable case): eval forward of all six exits, no grad, same sample
+    from oracle import conformer_oracle as O
+    with torch.no_grad():
+        t1 = time.perf_counter()
+        O.early_conformer_forward(sd, src, lengths)
+        dti = time.perf_counter() - t1
+    audio_s = float(lengths.sum()) * FRAME_S
     return {"value": round(sample_b / dt, 3), "unit": "utt/s", "cores": cores, "kind": "port",
             "sample": f"{steps} training step(s) (fwd + 6-exit CTC + bwd, fp32) on {sample_b} of the 64 utterances, same T_in={T_IN}, "
-                      f"{N_EXITS}x{layers} layers; {dt:.1f} s per step"}
+                      f"{N_EXITS}x{layers} layers; {dt:.1f} s per step",
+            "inference_rtfx_all_exits": round(audio_s / dti, 1),
+            "inference_sample": f"eval forward of all {N_EXITS} exits (fp32, no grad) on the same {sample_b} utterances: {dti:.2f} s for {audio_s:.0f} s of audio"}
 
 
 def run_reference(args):
