@@ -6,6 +6,7 @@
 // frame = one coalesced line), a block walks a tile of TT output frames; every input frame is
 // loaded ONCE into a register and scattered into the <=31 accumulators it feeds (loops are
 // fully unrolled, so tap indices are compile-time).  Algorithmic bytes: read g + write out.
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace eec {
@@ -95,6 +96,198 @@ __global__ void __launch_bounds__(256, 3) dwconv_kernel(const TI* __restrict__ g
 #pragma unroll
     for (int t = 0; t < TT; ++t)
       if (t0 + t < T) st_from_float<TO>(ob + (long)(t0 + t) * C, acc[t]);
+  }
+}
+
+// Persistent, double-buffered variant for bf16 inputs (forward: eval and train pass A).  The kernel above stages a tile, waits, then
+// computes: with three blocks per SM (register-limited) the FMA pipe idles while tiles are in flight (ncu: 55-63 % issue active).
+// Here every block walks tiles with a stride of gridDim.x and the cp.async copy of tile i+1 runs under the 992 FMAs per thread of
+// tile i; the depthwise weights stay in registers across tiles and the BatchNorm statistics of pass A are accumulated per thread
+// over all of a block's tiles (one pair of double atomics per thread instead of one per tile).
+// Packed variant: 128 threads, each owns a channel PAIR -- one 32-bit shared-memory load feeds both channels and the 31 x 32 multiply-
+// adds are FFMA2 (fp32x2, sm_100): half the FMA-pipe instructions per output.  (The 3-register FFMA issues every second cycle per
+// SMSP, which is what bounds this kernel; 64 accumulator + 62 weight registers per thread only pay off with the tile copy overlapped.)
+template <typename TO, int MODE>
+__global__ void __launch_bounds__(128, 3) dwconv_pipe2_kernel(const __nv_bfloat16* __restrict__ g, const float* __restrict__ w,
+                                                           const float* __restrict__ bias, const float* __restrict__ bn_w,
+                                                           const float* __restrict__ bn_b, const float* __restrict__ run_mean,
+                                                           const float* __restrict__ run_var, TO* __restrict__ out,
+                                                           double* __restrict__ sums, int B, int T, const ActiveItems act_items) {
+  pdl_trigger();
+  pdl_wait();
+  constexpr int C = 256, ROWS = TT + KW - 1, CPR = C * 2 / 16;
+  extern __shared__ __align__(16) uint8_t dw_smem[];
+  const int c0 = 2 * threadIdx.x;                            // channels c0, c0 + 1
+  const int nt = (T + TT - 1) / TT;
+  const int Beff = (MODE == DW_EVAL && act_items.n_dev) ? min(B, active_count(act_items)) : B;
+  const int tiles = nt * Beff;
+  float2 wr[KW];
+#pragma unroll
+  for (int j = 0; j < KW; ++j) wr[j] = make_float2(w[c0 * KW + j], w[(c0 + 1) * KW + j]);
+  const float2 bv = make_float2(bias[c0], bias[c0 + 1]);
+  float2 sc = make_float2(0.f, 0.f), sh = sc;
+  if (MODE == DW_EVAL) {
+    sc = make_float2(bn_w[c0] * rsqrtf(run_var[c0] + BN_EPS), bn_w[c0 + 1] * rsqrtf(run_var[c0 + 1] + BN_EPS));
+    sh = make_float2(bn_b[c0] - run_mean[c0] * sc.x, bn_b[c0 + 1] - run_mean[c0 + 1] * sc.y);
+  }
+  auto issue = [&](int tile, int buf) {
+    const int b = tile / nt, t_first = (tile - b * nt) * TT - HALF;
+    const __nv_bfloat16* src = g + (long)b * T * C;
+    uint8_t* base = dw_smem + buf * (ROWS * C * 2);
+    for (int i = threadIdx.x; i < ROWS * CPR; i += 128) {
+      const int r = i / CPR, c = i % CPR;
+      const int t = t_first + r;
+      uint8_t* dst = base + (size_t)i * 16;
+      if (t >= 0 && t < T) {
+        const uint8_t* sp = reinterpret_cast<const uint8_t*>(src + (long)t * C) + c * 16;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(sp) : "memory");
+      } else {
+        *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  float2 s1 = make_float2(0.f, 0.f), s2 = s1;
+  int tile = blockIdx.x, buf = 0;
+  if (tile < tiles) issue(tile, 0);
+  for (; tile < tiles; tile += gridDim.x, buf ^= 1) {
+    const int nxt = tile + gridDim.x;
+    if (nxt < tiles) {
+      issue(nxt, buf ^ 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    const __nv_bfloat162* tl = reinterpret_cast<const __nv_bfloat162*>(dw_smem + buf * (ROWS * C * 2));
+    float2 acc[TT];
+#pragma unroll
+    for (int t = 0; t < TT; ++t) acc[t] = bv;
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+      const float2 x = __bfloat1622float2(tl[r * (C / 2) + threadIdx.x]);
+#pragma unroll
+      for (int t = 0; t < TT; ++t) {
+        const int j = r - t;
+        if (j >= 0 && j < KW) acc[t] = __ffma2_rn(wr[j], x, acc[t]);
+      }
+    }
+    const int b = tile / nt, t0 = (tile - b * nt) * TT;
+    TO* ob = out + (long)b * T * C + c0;
+    if (MODE == DW_EVAL) {
+#pragma unroll
+      for (int t = 0; t < TT; ++t)
+        if (t0 + t < T) {
+          const float2 n = __ffma2_rn(acc[t], sc, sh);
+          *reinterpret_cast<__nv_bfloat162*>(ob + (long)(t0 + t) * C) = __floats2bfloat162_rn(n.x * sigmoid_acc(n.x), n.y * sigmoid_acc(n.y));
+        }
+    } else {
+#pragma unroll
+      for (int t = 0; t < TT; ++t)
+        if (t0 + t < T) {
+          *reinterpret_cast<float2*>(ob + (long)(t0 + t) * C) = acc[t];
+          s1.x += acc[t].x; s1.y += acc[t].y;
+          s2 = __ffma2_rn(acc[t], acc[t], s2);
+        }
+    }
+    __syncthreads();
+  }
+  if (MODE == DW_STATS && blockIdx.x < tiles) {
+    atomicAdd(sums + c0, (double)s1.x);
+    atomicAdd(sums + c0 + 1, (double)s1.y);
+    atomicAdd(sums + C + c0, (double)s2.x);
+    atomicAdd(sums + C + c0 + 1, (double)s2.y);
+  }
+}
+
+template <typename TO, int MODE>
+__global__ void __launch_bounds__(256, 3) dwconv_pipe_kernel(const __nv_bfloat16* __restrict__ g, const float* __restrict__ w,
+                                                          const float* __restrict__ bias, const float* __restrict__ bn_w,
+                                                          const float* __restrict__ bn_b, const float* __restrict__ run_mean,
+                                                          const float* __restrict__ run_var, TO* __restrict__ out,
+                                                          double* __restrict__ sums, int B, int T, const ActiveItems act_items) {
+  pdl_trigger();
+  pdl_wait();
+  constexpr int C = 256, ROWS = TT + KW - 1, CPR = C * 2 / 16;   // 32 16-byte chunks per bf16 row
+  extern __shared__ __align__(16) uint8_t dw_smem[];
+  const int ch = threadIdx.x;
+  const int nt = (T + TT - 1) / TT;
+  const int Beff = (MODE == DW_EVAL && act_items.n_dev) ? min(B, active_count(act_items)) : B;
+  const int tiles = nt * Beff;
+  float wr[KW];
+#pragma unroll
+  for (int j = 0; j < KW; ++j) wr[j] = w[ch * KW + j];
+  const float bv = bias[ch];
+  float sc = 0.f, sh = 0.f;
+  if (MODE == DW_EVAL) {
+    sc = bn_w[ch] * rsqrtf(run_var[ch] + BN_EPS);
+    sh = bn_b[ch] - run_mean[ch] * sc;
+  }
+  auto issue = [&](int tile, int buf) {
+    const int b = tile / nt, t_first = (tile - b * nt) * TT - HALF;
+    const __nv_bfloat16* src = g + (long)b * T * C;
+    uint8_t* base = dw_smem + buf * (ROWS * C * 2);
+    for (int i = threadIdx.x; i < ROWS * CPR; i += 256) {
+      const int r = i / CPR, c = i % CPR;
+      const int t = t_first + r;
+      uint8_t* dst = base + (size_t)i * 16;
+      if (t >= 0 && t < T) {
+        const uint8_t* sp = reinterpret_cast<const uint8_t*>(src + (long)t * C) + c * 16;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(sp) : "memory");
+      } else {
+        *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  float s1 = 0.f, s2 = 0.f;
+  int tile = blockIdx.x, buf = 0;
+  if (tile < tiles) issue(tile, 0);
+  for (; tile < tiles; tile += gridDim.x, buf ^= 1) {
+    const int nxt = tile + gridDim.x;
+    if (nxt < tiles) {
+      issue(nxt, buf ^ 1);                                   // (its previous readers passed the barrier at the end of the last iteration)
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    const __nv_bfloat16* tl = reinterpret_cast<const __nv_bfloat16*>(dw_smem + buf * (ROWS * C * 2));
+    float acc[TT];
+#pragma unroll
+    for (int t = 0; t < TT; ++t) acc[t] = bv;
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+      const float x = __bfloat162float(tl[r * C + ch]);
+#pragma unroll
+      for (int t = 0; t < TT; ++t) {
+        const int j = r - t;
+        if (j >= 0 && j < KW) acc[t] = fmaf(wr[j], x, acc[t]);
+      }
+    }
+    const int b = tile / nt, t0 = (tile - b * nt) * TT;
+    TO* ob = out + (long)b * T * C + ch;
+    if (MODE == DW_EVAL) {
+#pragma unroll
+      for (int t = 0; t < TT; ++t)
+        if (t0 + t < T) {
+          const float n = fmaf(acc[t], sc, sh);
+          st_from_float<TO>(ob + (long)(t0 + t) * C, n * sigmoid_acc(n));
+        }
+    } else {
+#pragma unroll
+      for (int t = 0; t < TT; ++t)
+        if (t0 + t < T) {
+          st_from_float<TO>(ob + (long)(t0 + t) * C, acc[t]);
+          s1 += acc[t];
+          s2 = fmaf(acc[t], acc[t], s2);
+        }
+    }
+    __syncthreads();                                          // every thread has read `buf` before the next iteration refills it
+  }
+  if (MODE == DW_STATS && blockIdx.x < tiles) {
+    atomicAdd(sums + ch, (double)s1);
+    atomicAdd(sums + C + ch, (double)s2);
   }
 }
 
@@ -397,6 +590,45 @@ static int stream_grid(int rows) {
     launch_pdl(kernel, dim3(grid), dim3(256), dw_smem_bytes<TI>(), S(stream), __VA_ARGS__);                                                   \
   } while (0)
 
+static int dw_pipe_mode() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("EEC_DW_PIPE"); v = e ? atoi(e) : 1; }   // 0: one tile per block; 1: pipelined; 2: pipelined + FFMA2 channel pairs (opt-in until verified on the GPU)
+  return v;
+}
+static bool dw_pipe_enabled() { return dw_pipe_mode() != 0; }
+template <typename TO, int MODE>
+static int dw_pipe_launch(const __nv_bfloat16* g, const float* w, const float* bias, const float* bn_w, const float* bn_b,
+                          const float* run_mean, const float* run_var, TO* out, double* sums, int B, int T, cudaStream_t st) {
+  constexpr int SMEM = 2 * (TT + KW - 1) * 256 * 2;
+  static bool attr = false;
+  if (!attr) {
+    EEC_CUDA(cudaFuncSetAttribute(dwconv_pipe_kernel<TO, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    attr = true;
+  }
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 148;
+  }
+  const int tiles = cdiv(T, TT) * B;
+  if (tiles == 0) return 0;
+  if (dw_pipe_mode() == 2) {
+    static bool attr2 = false;
+    if (!attr2) {
+      EEC_CUDA(cudaFuncSetAttribute(dwconv_pipe2_kernel<TO, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+      attr2 = true;
+    }
+    launch_pdl(dwconv_pipe2_kernel<TO, MODE>, dim3(min(tiles, sms * 3)), dim3(128), SMEM, st, g, w, bias, bn_w, bn_b, run_mean, run_var, out, sums, B, T,
+               active_items());
+    EEC_LAUNCH_CHECK();
+    return 0;
+  }
+  launch_pdl(dwconv_pipe_kernel<TO, MODE>, dim3(min(tiles, sms * 3)), dim3(256), SMEM, st, g, w, bias, bn_w, bn_b, run_mean, run_var, out, sums, B, T,
+             active_items());
+  EEC_LAUNCH_CHECK();
+  return 0;
+}
+
 #define DW_ARGS_OK()                                                                 \
   EEC_CHECK_ARG(K == KW, "dwconv: depthwise_kernel_size must be 31 (got %d)", K);    \
   EEC_CHECK_ARG(C % 256 == 0, "dwconv: channels must be a multiple of 256 (got %d)", C); \
@@ -407,6 +639,10 @@ extern "C" int eec_dwconv_bn_silu_eval(const void* g, int dtype, const float* w,
                                        const float* bn_b, const float* run_mean, const float* run_var, void* out, int B,
                                        int T, int C, int K, eec_stream_t stream) {
   DW_ARGS_OK();
+  if (dtype == EEC_BF16 && C == 256 && dw_pipe_enabled()) {
+    if (int r = dw_pipe_launch<__nv_bfloat16, DW_EVAL>((const __nv_bfloat16*)g, w, bias, bn_w, bn_b, run_mean, run_var, (__nv_bfloat16*)out, nullptr, B, T, S(stream))) return r;
+    return 0;
+  }
   if (dtype == EEC_F32)
     EEC_DW_LAUNCH((dwconv_kernel<float, float, DW_EVAL>), float, (const float*)g, w, bias, bn_w, bn_b, run_mean, run_var, (float*)out, nullptr, T, C, active_items());
   else
@@ -418,6 +654,10 @@ extern "C" int eec_dwconv_bn_silu_eval(const void* g, int dtype, const float* w,
 extern "C" int eec_dwconv_stats(const void* g, int dtype, const float* w, const float* bias, float* c, double* sums,
                                 int B, int T, int C, int K, eec_stream_t stream) {
   DW_ARGS_OK();
+  if (dtype == EEC_BF16 && C == 256 && dw_pipe_enabled()) {
+    if (int r = dw_pipe_launch<float, DW_STATS>((const __nv_bfloat16*)g, w, bias, nullptr, nullptr, nullptr, nullptr, c, sums, B, T, S(stream))) return r;
+    return 0;
+  }
   if (dtype == EEC_F32)
     EEC_DW_LAUNCH((dwconv_kernel<float, float, DW_STATS>), float, (const float*)g, w, bias, nullptr, nullptr, nullptr, nullptr, c, sums, T, C, ActiveItems{nullptr, 0, 0});
   else
