@@ -270,13 +270,21 @@ def run_ours(args):
         ms_e2e = timed(e2e_step, args.steps)
 
     # inference RTFx per exit (BASELINE metric part (i)): forward truncated after exit e, bf16, eval
-    rtfx = ee_leg = fb_leg = None
+    rtfx = ee_leg = fb_leg = eager_leg = None
     if rank == 0 and not args.skip_rtfx and not args.profile:
         audio_s = float(lengths.sum()) * FRAME_S
         rtfx = rtfx_per_exit(model, src_dev, lengths, audio_s, use_graph=not args.no_graph)
         model.train()
-        ee_leg = early_exit_leg(layers, args.precision, dev, src_dev, lengths, audio_s) if not args.no_graph else None
-        fb_leg = fbank_leg(dev, with_cpu=(world == 1 and not args.skip_cpu))
+        # auxiliary legs never take the headline down with them: a failure is reported in place of the leg's numbers
+        def guarded(fn, *a, **k):
+            try:
+                return fn(*a, **k)
+            except Exception as e:   # noqa: BLE001
+                return {"failed": f"{type(e).__name__}: {e}"[:300]}
+        ee_leg = guarded(early_exit_leg, layers, args.precision, dev, src_dev, lengths, audio_s) if not args.no_graph else None
+        fb_leg = guarded(fbank_leg, dev, with_cpu=(world == 1 and not args.skip_cpu))
+        if world == 1 and not args.skip_cpu:
+            eager_leg = guarded(torch_eager_leg, layers, dev, src_dev, lengths, tg_dev, tl_dev, audio_s)
 
     # the same step at the reference's DEFAULT --drop_prob 0.1 (util/conf.py:283-291): fused counter-based dropout at all
     # seven sites per layer + after the positional encoding, masks regenerated in backward (nothing stored)
@@ -339,6 +347,8 @@ def run_ours(args):
             line["early_exit_inference"] = ee_leg
         if fb_leg is not None:
             line["fbank_frontend"] = fb_leg
+        if eager_leg is not None:
+            line["torch_eager_same_gpu"] = eager_leg
         print(json.dumps(line), file=_JSON_OUT, flush=True)
     if world > 1:
         graphed = None          # (graphs that hold captured NCCL kernels are released before the communicator)
@@ -411,6 +421,85 @@ def early_exit_leg(layers, precision, dev, src_dev, lengths, audio_s):
     return {"model": f"splitformer {N_EXITS} exits x {layers} layers, batch {src_dev.shape[0]}", "criterion": "mean frame entropy < threshold",
             "threshold": round(thr, 4), "utterances_leaving_at_exit": hist, "ms": round(ms_ee, 3), "rtfx": round(audio_s / (ms_ee / 1e3), 1),
             "all_exits_forward_ms": round(ms_full, 3), "gpu_launches": ee.launches, "launch": "one CUDA graph replay, no host sync"}
+
+
+def torch_eager_leg(layers, dev, src_dev, lengths, tg_dev, tl_dev, audio_s):
+    """"the existing Blackwell kernel bar" -- the same model assembled from the LIBRARY modules the reference itself
+    calls (torchaudio.models.Conformer x 6, nn.Conv1d x 2, nn.Linear heads, nn.CTCLoss; early_exit.py:594-634, train.py:53-70) and run
+    by eager PyTorch on the same B200: cuBLAS / cuDNN / SDPA / ATen kernels, fp32 with torch's default TF32 settings like the reference,
+    and once more under bf16 autocast.  Same batch, same step contents (forward, summed 6-exit CTC, backward, clip_grad_norm_, AdamW).
+    A reported baseline: none of this is on the product path."""
+    try:
+        import torchaudio
+    except Exception as e:     # pragma: no cover
+        return {"unavailable": f"torchaudio import failed: {e}"}
+    nn = torch.nn
+
+    class Ref(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.c1, self.c2 = nn.Conv1d(N_MELS, 256, 3, 2), nn.Conv1d(256, 256, 3, 2)
+            pe = torch.zeros(2000, 256)
+            pos = torch.arange(2000).unsqueeze(1)
+            div = torch.exp(torch.arange(0, 256, 2) * (-torch.log(torch.tensor(10000.0)) / 256))
+            pe[:, 0::2], pe[:, 1::2] = torch.sin(pos * div), torch.cos(pos * div)
+            self.register_buffer("pe", pe)
+            self.heads = nn.ModuleList([nn.Linear(256, 256) for _ in range(N_EXITS)])
+            self.groups = nn.ModuleList([torchaudio.models.Conformer(input_dim=256, num_heads=8, ffn_dim=2048, num_layers=layers,
+                                                                      depthwise_conv_kernel_size=31, dropout=0.0) for _ in range(N_EXITS)])
+
+        def forward(self, x, lens):
+            x = self.c2(self.c1(x)).permute(0, 2, 1)
+            x = x + self.pe[: x.size(1)]
+            ln = torch.clamp(lens / 4, max=x.size(1)).to(torch.int).to(x.device)
+            outs = []
+            for head, grp in zip(self.heads, self.groups):
+                x, _ = grp(x, ln)
+                outs.append(torch.log_softmax(head(x), dim=2).unsqueeze(0))
+            return torch.cat(outs)
+
+    torch.manual_seed(0)
+    m = Ref().to(dev)
+    opt = torch.optim.AdamW(m.parameters(), lr=1e-4, betas=(0.9, 0.98), eps=1e-9, weight_decay=5e-4)
+    ctc = nn.CTCLoss(blank=0, zero_infinity=True)
+    T = t_out(T_IN)
+    in_len = torch.full((B,), T, dtype=torch.long)
+
+    def train_step(autocast):
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+            out = m(src_dev, lengths)
+        loss = sum(ctc(enc.float().permute(1, 0, 2), tg_dev, in_len, tl_dev) for enc in out)
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(m.parameters(), 1.0)
+        opt.step()
+
+    def infer(autocast):
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+            m(src_dev, lengths)
+
+    def t(fn, n=3):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(n):
+            fn()
+        ev1.record()
+        torch.cuda.synchronize()
+        return ev0.elapsed_time(ev1) / n
+    res = {"what": "torchaudio.models.Conformer x 6 + nn.Conv1d/Linear/CTCLoss, eager PyTorch on the same GPU (library kernels)"}
+    m.train()
+    res["train_ms_per_step_fp32"] = round(t(lambda: train_step(False)), 2)
+    res["train_ms_per_step_bf16_autocast"] = round(t(lambda: train_step(True)), 2)
+    m.eval()
+    ms32, ms16 = t(lambda: infer(False)), t(lambda: infer(True))
+    res["inference_all_exits_ms_fp32"], res["inference_all_exits_ms_bf16_autocast"] = round(ms32, 2), round(ms16, 2)
+    res["inference_rtfx_bf16_autocast"] = round(audio_s / (ms16 / 1e3), 1)
+    del m, opt
+    torch.cuda.empty_cache()
+    return res
 
 
 def fbank_leg(dev, with_cpu):
