@@ -204,6 +204,9 @@ class _EarlyExitBase(nn.Module):
             seed = self.__dict__.get("_drop_seed")
             if seed is None:
                 seed = torch.initial_seed()
+                # data parallel: every rank usually shares torch's seed; give each rank its own mask stream
+                if torch.distributed.is_available() and torch.distributed.is_initialized():
+                    seed = (seed + torch.distributed.get_rank() * 0x9E3779B97F4A7C15) & 0x7FFFFFFFFFFFFFFF
             st = torch.tensor([seed & 0x7FFFFFFFFFFFFFFF, 0], dtype=torch.int64, device=dev)
             self.__dict__["_drop_state"] = st
         return st
