@@ -66,3 +66,32 @@ def test_fbank_full_size_vs_oracle_and_into_the_model():
         out = m(feats, frames.cpu())
         want = O.early_conformer_forward(sd, torch.from_numpy(ref), torch.from_numpy(ref_frames))
     assert float((out.cpu() - want).abs().max() / want.abs().max()) < 1e-3
+
+
+def test_waveform_to_loss_pipeline_trains_with_dropout():
+    """The whole replaced pipeline on a fixed batch: waveform -> eec.Fbank -> Early_conformer (train mode, the reference's default
+    drop_prob 0.1) -> fused multi-exit CTC -> clip + AdamW, as ONE CUDA graph per step.  The loss must fall while dropout draws
+    fresh masks every replay."""
+    import eec
+    g = torch.Generator().manual_seed(3)
+    Bn, L = 4, 32000
+    waves = torch.randn(Bn, L, generator=g) * 0.1
+    lens = torch.tensor([32000, 30000, 28000, 32000])
+    feats, frames = eec.Fbank()(waves.cuda(), lens)
+    feats = torch.log1p(feats)                         # (tame the power-mel dynamic range for this tiny optimisation problem)
+    targets, tl = O.synthetic_targets(Bn, seed=4, lo=3, hi=6)
+    sd = O.make_params(41, n_exits=2, n_layers=1)
+    m = eec.Early_conformer(src_pad_idx=0, n_enc_exits=2, enc_voc_size=256, dec_voc_size=256, d_model=256, n_head=8, max_len=2000,
+                            d_feed_forward=2048, n_enc_layers=1, features_length=80, drop_prob=0.1, depthwise_kernel_size=31,
+                            device=torch.device("cuda"))
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda().train()
+    m.precision = "bf16"
+    m.set_dropout_seed(7)
+    opt = eec.FusedNoamAdamW(m, model_size=256, warmup=50, clip=1.0, lr=3e-4)
+    step = eec.GraphedTrainStep(m, Bn, feats.shape[2], targets.shape[1], optimizer=opt)
+    step.load_inputs(feats, frames.cpu(), targets, tl)
+    losses = [float(step.replay().clone()) for _ in range(40)]
+    assert all(np.isfinite(losses))
+    assert np.mean(losses[-5:]) < 0.7 * np.mean(losses[:5]), losses
+    assert len(set(round(x, 4) for x in losses)) > 30          # fresh masks + moving weights: no two steps alike
