@@ -7,6 +7,9 @@
 // fuses the occupancy reduction and writes d(loss)/d(logits) = scale*(softmax - occupancy)
 // directly, so log-softmax backward never runs as a separate kernel.
 #include "common.cuh"
+#ifndef EEC_CTC_PF
+#define EEC_CTC_PF 4
+#endif
 
 namespace eec {
 
@@ -160,7 +163,7 @@ __global__ void __launch_bounds__(64) ctc_warp_kernel(const float* __restrict__ 
   // recursion backward in time (the two T-step dependency chains are the whole cost of this kernel and are independent);
   // both leave their lattices in the workspace, then the two warps share the embarrassingly parallel occupancy pass.
   constexpr int NL = SPL / 2;   // label states per lane
-  constexpr int PF = 4;         // prefetch distance (time steps)
+  constexpr int PF = EEC_CTC_PF;         // prefetch distance (time steps)
   constexpr int SW = 32 * SPL;  // workspace row width
   __shared__ float s_ll;
   const int wg = blockIdx.x;
