@@ -344,6 +344,35 @@ __global__ void gather_i64_kernel(const int64_t* __restrict__ src, const int32_t
   if (i < n) dst[i] = src[min(max(idx[i], 0), n - 1)];
 }
 
+// out_bf16[r, c] = bf16(in[r, c]) and colsum[c] += scale * sum_r in[r, c] in ONE pass over a [rows, cols] fp32 tensor (cols % 256 == 0):
+// the exit heads' backward needs both the bf16 operand copy of d(logits) and the bias gradient (its column sums)
+__global__ void __launch_bounds__(256) cast_colsum_kernel(const float* __restrict__ in, int ld, __nv_bfloat16* __restrict__ out, int ldo,
+                                                        float* __restrict__ colsum, int rows, int rows_per_block, float scale) {
+  pdl_trigger();
+  pdl_wait();
+  __shared__ float red[8][256];
+  const int cg = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int c0 = blockIdx.x * 256 + cg * 8;
+  const int r0 = blockIdx.y * rows_per_block, r1 = min(rows, r0 + rows_per_block);
+  float acc[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+  for (int r = r0 + rl; r < r1; r += 8) {
+    float v[8];
+    ld8<float>(in + (long)r * ld + c0, v);
+    st8<__nv_bfloat16>(out + (long)r * ldo + c0, v);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] += v[k];
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) red[rl][cg * 8 + k] = acc[k];
+  __syncthreads();
+  float t = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
+  atomicAdd(colsum + blockIdx.x * 256 + threadIdx.x, t * scale);
+}
+
 __global__ void axpy_kernel(const float* __restrict__ x, float a, float* __restrict__ y, long n) {
   pdl_trigger();
   pdl_wait();
@@ -576,6 +605,16 @@ extern "C" int eec_colsum(const void* in, int dtype, int ld, float* out, float s
 extern "C" int eec_gather_i64(const int64_t* src, const int32_t* idx, int64_t* dst, int n, eec_stream_t stream) {
   if (n == 0) return 0;
   launch_pdl(gather_i64_kernel, dim3(cdiv(n, 128)), dim3(128), 0, S(stream), src, idx, dst, n);
+  EEC_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int eec_cast_colsum(const float* in, int ld, void* out_bf16, int ldo, float* colsum, float scale, int rows, int cols,
+                               eec_stream_t stream) {
+  EEC_CHECK_ARG(cols % 256 == 0 && ld % 8 == 0 && ldo % 8 == 0, "cast_colsum: cols %% 256, ld %% 8, ldo %% 8 required");
+  if (rows == 0 || cols == 0) return 0;
+  const int rpb = 128;
+  launch_pdl(cast_colsum_kernel, dim3(cols / 256, cdiv(rows, rpb)), dim3(256), 0, S(stream), in, ld, (__nv_bfloat16*)out_bf16, ldo, colsum, rows, rpb, scale);
   EEC_LAUNCH_CHECK();
   return 0;
 }

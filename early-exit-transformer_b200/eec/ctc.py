@@ -38,6 +38,8 @@ class _CtcFn(torch.autograd.Function):
         gl = gloss.contiguous().float()
         ops.scale_rows_dev(g, gl, g)   # every exit's slab times its upstream scalar, on device, one launch
         ctx.grad = None
+        from . import engine
+        engine.mark_logit_grad(g)      # rows sum to zero: the encoder's backward may skip the log-softmax backward for this tensor
         return g, None, None, None
 
 

@@ -592,6 +592,31 @@ def model_forward(P: Dict[str, Tensor], W: Operands, cfg: Config, src: Tensor, l
     return out, tape
 
 
+# Gradients that are known to be d(loss)/d(logits) already.  The fused CTC kernel returns (softmax - occupancy) scaled per utterance:
+# its rows sum to zero, so the log-softmax backward (g - softmax * rowsum(g)) would hand it back unchanged.  _CtcFn.backward registers the
+# tensor it returns; when exactly that tensor (same storage, shape and version) arrives as the encoder's upstream gradient, the six
+# log-softmax backward launches are skipped.  Anything else (a user's own loss on the log-probs, an accumulated gradient) misses the
+# registry and takes the general path.  An entry is only valid inside the backward pass (autograd graph task) that created it.
+_LOGIT_GRADS: Dict[int, tuple] = {}
+
+
+def _backward_pass_id() -> int:
+    fn = getattr(torch._C, "_current_graph_task_id", None)
+    return int(fn()) if fn is not None else -1
+
+
+def mark_logit_grad(g: Tensor) -> None:
+    _LOGIT_GRADS.clear()                      # (one pending step at a time: nothing accumulates here)
+    task = _backward_pass_id()
+    if task >= 0:
+        _LOGIT_GRADS[g.data_ptr()] = (tuple(g.shape), g._version, task)
+
+
+def take_logit_grad(g: Tensor) -> bool:
+    hit = _LOGIT_GRADS.pop(g.data_ptr(), None)
+    return hit is not None and hit == (tuple(g.shape), g._version, _backward_pass_id())
+
+
 def group_ranges(P, names: List[str], n_exits: int):
     """[lo, hi) of every exit group's parameters inside the flat gradient buffer (layout = `names` order), or None when a
     group is not contiguous there.  Backward finishes the groups last-to-first: each slice can leave for the data-parallel
@@ -618,6 +643,7 @@ def model_backward(P, W: Operands, cfg: Config, tape: Tape, gout: Tensor, names:
     on_ready(flat, lo, hi) (optional) is called as soon as flat[lo:hi] holds final gradients (one exit group at a time,
     then the rest): the data-parallel reducer's hook (eec.distributed.OverlappedGradReducer)."""
     dev, f32 = gout.device, torch.float32
+    logit_grad = gout.is_contiguous() and take_logit_grad(gout)
     gout = gout.contiguous()
     B, T = tape.B, tape.T
     N = B * T
@@ -637,12 +663,19 @@ def model_backward(P, W: Operands, cfg: Config, tape: Tape, gout: Tensor, names:
     li = len(tape.layers)
     for e in reversed(range(E)):
         # exit head: out[e] = log_softmax(x W^T + b)
-        dlog = _empty((N, V), f32, dev)
-        ops.logsoftmax_bwd(gout[e], tape.out[e], dlog)
-        dlogh = to_act(dlog, cfg)
+        if logit_grad:
+            dlog = gout[e].view(N, V)         # already d/d(logits) (fused CTC): log-softmax backward is the identity on it
+        else:
+            dlog = _empty((N, V), f32, dev)
+            ops.logsoftmax_bwd(gout[e], tape.out[e], dlog)
         Wh = W.get(f"linears.{e}.weight", P[f"linears.{e}.weight"], (V, D))
+        if cfg.precision == "bf16":
+            dlogh = _empty((N, V), torch.bfloat16, dev)
+            ops.cast_colsum(dlog, dlogh, G[f"linears.{e}.bias"], N, V)     # operand copy + bias gradient in one pass
+        else:
+            dlogh = dlog
+            ops.colsum(dlog, G[f"linears.{e}.bias"], N, V)
         wgrad(dlogh, tape.heads[e]["xh"], G[f"linears.{e}.weight"], N, V, D, sq=sq)
-        ops.colsum(dlog, G[f"linears.{e}.bias"], N, V)
         if dX is None:
             dX = _empty((N, D), f32, dev)
             dgrad(dlogh, Wh, dX, N, V, D)

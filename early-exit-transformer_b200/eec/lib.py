@@ -72,6 +72,7 @@ _SIGS = {
     "eec_cast": [vp, i32, vp, i32, i64, vp],
     "eec_noam_adamw_step": [vp, vp, vp, vp, vp, i64, vp, f32, f32, f32, f32, f32, f32, f32, f32, vp],
     "eec_colsum": [vp, i32, i32, vp, f32, i32, i32, vp],
+    "eec_cast_colsum": [vp, i32, vp, i32, vp, f32, i32, i32, vp],
     "eec_axpy": [vp, f32, vp, i64, vp],
     "eec_scale_dev": [vp, vp, vp, i64, vp],
     "eec_scale_rows_dev": [vp, vp, vp, i32, i64, vp],

@@ -244,6 +244,10 @@ def colsum(inp, out, rows, cols, scale=1.0, ld=None):
     call("eec_colsum", ptr(inp), dt(inp), ld if ld is not None else cols, ptr(out), scale, rows, cols, stream())
 
 
+def cast_colsum(inp, out_bf16, colsum_out, rows, cols, scale=1.0):
+    call("eec_cast_colsum", ptr(inp), cols, ptr(out_bf16), cols, ptr(colsum_out), scale, rows, cols, stream())
+
+
 def axpy(x, a, y):
     call("eec_axpy", ptr(x), a, ptr(y), x.numel(), stream())
 

@@ -229,6 +229,10 @@ int eec_cast(const void* in, int in_dtype, void* out, int out_dtype, int64_t n, 
 /* out[n] += scale * sum_m in[m, n]   (bias gradients; out accumulates) */
 int eec_colsum(const void* in, int dtype, int ld, float* out, float scale, int rows, int cols,
                eec_stream_t stream);
+/* out_bf16[r, c] = bf16(in[r, c]) and colsum[c] += scale * sum_r in[r, c] in one pass (cols % 256 == 0): the bf16 operand copy of
+ * d(logits) and the exit head's bias gradient (autograd of early_exit.py:629) */
+int eec_cast_colsum(const float* in, int ld, void* out_bf16, int ldo, float* colsum, float scale, int rows, int cols,
+                    eec_stream_t stream);
 /* y = (*s_dev) * x  (device scalar; used to apply an upstream loss gradient without a host sync) */
 int eec_scale_dev(const float* x, const float* s_dev, float* y, int64_t n, eec_stream_t stream);
 /* y[r, 0:slab] = s_dev[r] * x[r, 0:slab], r < rows (x, y contiguous; slab % 4 == 0): every exit's CTC gradient scaled by its

@@ -108,7 +108,9 @@ def test_train_step_vs_reference_golden(name, precision):
     loss2.backward()
     P2 = dict(m2.named_parameters())
     k = "conformer.0.conformer_layers.0.ffn1.sequential.1.weight"
-    assert rel(P2[k].grad, P[k].grad) < 1e-3
+    # (the fused loss hands the encoder d(loss)/d(logits) directly, the per-exit calls go through the general log-softmax backward: equal up to
+    #  fp32 round-off, which the bf16 operand casts amplify to a few bf16 ulps)
+    assert rel(P2[k].grad, P[k].grad) < (1e-3 if precision == "fp32" else 5e-3)
 
 
 def test_ctc_known_answers():
