@@ -229,6 +229,238 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_fwd_tc_kernel(const __grid
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// Persistent variant (EEC_ATTN_PERSIST): the kernel above lives for one (128 queries, head, utterance) item of ~3 key blocks, and the
+// ncu source view puts ~45 % of its warp-stall samples on TMEM allocation / barrier set-up / tear-down.  Here a grid of 2 CTAs per SM
+// walks the work items: one TMEM allocation and one barrier initialisation per CTA, barrier phases running on across items, and a
+// q_empty barrier so that the producer refills the Q tile only after the item's last S MMA has completed.
+template <bool DROP>
+__global__ void __launch_bounds__(AT_THREADS, 2) attn_fwd_tcp_kernel(const __grid_constant__ CUtensorMap tm_qkv,
+                                                                 const int32_t* __restrict__ key_len,
+                                                                 __nv_bfloat16* __restrict__ ctx, float* __restrict__ lse,
+                                                                 int T, int H, int B, const DropArgs drop, const ActiveItems act_items) {
+  pdl_trigger();
+  pdl_wait();
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + Q_BYTES;                       // [stage]
+  uint8_t* sV = sK + KV_STAGES * K_BYTES;           // [stage]
+  uint8_t* sP = sV + KV_STAGES * V_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + P_BYTES);
+  uint64_t* q_full = bars;
+  uint64_t* kv_full = bars + 1;                     // [2]
+  uint64_t* kv_empty = bars + 3;                    // [2]
+  uint64_t* s_full = bars + 5;
+  uint64_t* s_free = bars + 6;
+  uint64_t* p_full = bars + 7;
+  uint64_t* o_full = bars + 8;
+  uint64_t* q_empty = bars + 9;                     // every S MMA of the current work item has been issued and has completed: sQ may be refilled
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 10);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int D = H * DHEAD;
+  const int nqt = (T + QT - 1) / QT;
+  const int Beff = act_items.n_dev ? min(B, active_count(act_items)) : B;    // utterances past the active-item limit are not work items
+  const int n_items = nqt * H * Beff;
+  // work item w = (b * H + h) * nqt + qt, walked with a stride of gridDim.x.  Barrier phases run on across items: `it` counts the
+  // items of this CTA that loaded a Q tile (nblk > 0), `jbase` the key blocks it has processed so far.
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tm_qkv);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < KV_STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+    mbar_init(s_full, 1);
+    mbar_init(s_free, 128);
+    mbar_init(p_full, 128);
+    mbar_init(o_full, 1);
+    mbar_init(q_empty, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_ptr_smem, TMEM_COLS); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it = 0, jbase = 0;
+      for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
+        const int qt = w % nqt, bh = w / nqt, h = bh % H, b = bh / H;
+        const int q0 = qt * QT, row0 = b * T;
+        const int klen = min(key_len[b], T);
+        const int nblk = (klen + KB - 1) / KB;
+        if (nblk == 0) continue;
+        if (it > 0) mbar_wait(q_empty, (it - 1) & 1);        // the previous item's S MMAs are done with sQ
+        mbar_expect_tx(q_full, Q_BYTES);
+        tma_load_2d(sQ, &tm_qkv, q_full, h * DHEAD, row0 + q0);
+        for (int j = 0; j < nblk; ++j) {
+          const uint32_t jb = jbase + j;
+          const int s = jb % KV_STAGES;
+          mbar_wait(&kv_empty[s], ((jb / KV_STAGES) & 1) ^ 1);
+          mbar_expect_tx(&kv_full[s], K_BYTES + V_BYTES);
+          tma_load_2d(sK + s * K_BYTES, &tm_qkv, &kv_full[s], D + h * DHEAD, row0 + j * KB);
+          tma_load_2d(sV + s * V_BYTES, &tm_qkv, &kv_full[s], 2 * D + h * DHEAD, row0 + j * KB);
+        }
+        ++it;
+        jbase += nblk;
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(QT, KB, false, false);
+      constexpr uint32_t idesc_o = make_idesc_bf16(QT, DHEAD, false, true);
+      uint32_t it = 0, jbase = 0;
+      for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
+      const int b = (w / nqt) / H;
+      const int klen = min(key_len[b], T);
+      const int nblk = (klen + KB - 1) / KB;
+      if (nblk == 0) continue;
+      mbar_wait(q_full, it & 1);
+      for (int j = 0; j < nblk; ++j) {
+        const uint32_t jb = jbase + j;
+        const int s = jb % KV_STAGES;
+        mbar_wait(&kv_full[s], (jb / KV_STAGES) & 1);
+        if (jb > 0) mbar_wait(s_free, (jb - 1) & 1);   // softmax threads have drained S of the previous block (of this or the previous item)
+        tc_fence_after();
+        const uint32_t aq = smem_u32(sQ), bk = smem_u32(sK + s * K_BYTES), bv = smem_u32(sV + s * V_BYTES);
+#pragma unroll
+        for (int k = 0; k < DHEAD / 16; ++k)
+          umma_bf16(tmem_base + S_COL, make_smem_desc(aq + k * 32, 0, 512, SW64), make_smem_desc(bk + k * 32, 0, 512, SW64),
+                    idesc_s, k > 0 ? 1u : 0u);
+        umma_commit(s_full);
+        if (j == nblk - 1) umma_commit(q_empty);     // last S MMA of the item: once it completes sQ is free
+        mbar_wait(p_full, jb & 1);                   // P_j is in smem (and O_{j-1} has been consumed)
+        tc_fence_after();
+        const uint32_t ap = smem_u32(sP);
+#pragma unroll
+        for (int k = 0; k < KB / 16; ++k)
+          umma_bf16(tmem_base + O_COL, make_smem_desc(ap + (k >> 2) * 16384 + (k & 3) * 32, 0, 1024, SW128),
+                    make_smem_desc(bv + k * 1024, 0, 512, SW64), idesc_o, k > 0 ? 1u : 0u);
+        umma_commit(o_full);
+        umma_commit(&kv_empty[s]);
+      }
+      ++it;
+      jbase += nblk;
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- softmax + epilogue: one thread per query row
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+    const float sc = rsqrtf((float)DHEAD) * 1.4426950408889634f;  // 1/sqrt(dh) * log2(e)
+    uint32_t jbase = 0;
+    for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
+    const int qt = w % nqt, bh = w / nqt, h = bh % H, b = bh / H;
+    const int q0 = qt * QT, row0 = b * T;
+    const int klen = min(key_len[b], T);
+    const int nblk = (klen + KB - 1) / KB;
+    float m_run = -INFINITY, l_run = 0.f;
+    float o[DHEAD];
+#pragma unroll
+    for (int i = 0; i < DHEAD; ++i) o[i] = 0.f;
+    float v[32];
+    // dropout on the probabilities (DROP): the row sum keeps the undropped values, the P tile fed to the P V product is masked
+    // keep-mask words (eec_dropout_bits, W = 32): word (k/32, row) at bits[(k/32)*R + row], row = (b*H + h)*T + t, R = B*H*T
+    const uint32_t* dbits = reinterpret_cast<const uint32_t*>(drop.bits);
+    const long drow = (long)(b * H + h) * T + (q0 + r), dR = (long)B * H * T;
+    const bool dvalid = (q0 + r) < T;
+    for (int j = 0; j < nblk; ++j) {
+      const int nvalid = min(KB, klen - j * KB);   // only the last key block can be partial
+      uint32_t dword[4] = {0u, 0u, 0u, 0u};          // this row's keep-mask words of the block: in flight while S is being computed
+      if (DROP && dvalid) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          if (c * 32 < nvalid) dword[c] = dbits[(long)((j * KB) / 32 + c) * dR + drow];
+      }
+      const uint32_t jb = jbase + j;
+      mbar_wait(s_full, jb & 1);
+      tc_fence_after();
+      // pass 1: row max (raw scores; the positive scale is applied once) over the valid keys of this block
+      float mraw = -INFINITY;
+#pragma unroll 1
+      for (int c0 = 0; c0 < KB; c0 += 32) {
+        if (c0 >= nvalid) break;               // uniform
+        tmem_ld32(trow + S_COL + c0, v);
+        if (c0 + 32 <= nvalid) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mraw = fmaxf(mraw, v[i]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c0 + i < nvalid) mraw = fmaxf(mraw, v[i]);
+        }
+      }
+      const float mx = fmaxf(m_run, mraw * sc);
+      // pass 2: p = exp2(s*sc - mx), row sum, bf16 P tile in swizzled smem
+      float psum = 0.f;
+#pragma unroll 1
+      for (int c0 = 0; c0 < KB; c0 += 32) {
+        if (c0 < nvalid) {
+          tmem_ld32(trow + S_COL + c0, v);
+          if (c0 + 32 <= nvalid) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) { v[i] = ex2_fast(fmaf(v[i], sc, -mx)); psum += v[i]; }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) { v[i] = (c0 + i < nvalid) ? ex2_fast(fmaf(v[i], sc, -mx)) : 0.f; psum += v[i]; }
+          }
+          if (DROP) drop_apply_bits<32>(v, c0 == 0 ? dword[0] : c0 == 32 ? dword[1] : c0 == 64 ? dword[2] : dword[3], drop.scale);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = 0.f;
+        }
+        uint8_t* prow = sP + (c0 >> 6) * 16384 + r * 128;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {  // 4 chunks of 8 keys (16 B) in this 32-key span
+          const int chunk = ((c0 & 63) >> 3) + g;
+          uint4 u;
+          __nv_bfloat162* hh = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) hh[e] = __floats2bfloat162_rn(v[g * 8 + 2 * e], v[g * 8 + 2 * e + 1]);
+          *reinterpret_cast<uint4*>(prow + ((chunk ^ (r & 7)) << 4)) = u;
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(s_free);
+      fence_proxy_async();
+      mbar_arrive(p_full);
+      const float corr = (m_run == -INFINITY) ? 0.f : ex2_fast(m_run - mx);
+      l_run = l_run * corr + psum;
+      m_run = mx;
+      mbar_wait(o_full, jb & 1);
+      tc_fence_after();
+      tmem_ld32(trow + O_COL, v);
+#pragma unroll
+      for (int i = 0; i < DHEAD; ++i) o[i] = fmaf(o[i], corr, v[i]);
+    }
+    const int t = q0 + r;
+    if (t < T) {
+      const float inv = (l_run > 0.f) ? 1.0f / l_run : 0.f;
+      __nv_bfloat16* dst = ctx + ((long)(row0 + t)) * D + h * DHEAD;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        float tt[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) tt[e] = o[g * 8 + e] * inv;
+        st8<__nv_bfloat16>(dst + g * 8, tt);
+      }
+      if (lse) lse[((long)b * H + h) * T + t] = (l_run > 0.f) ? (m_run + log2f(l_run)) * 0.6931471805599453f : -INFINITY;
+    }
+    jbase += nblk;
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------------
 // Eight softmax warps (EEC_ATTN_FWD8): the kernel above gives each query row ONE thread, so an SM runs 8 softmax warps (2 CTAs x 4)
 // and the softmax phase is latency-bound (tcgen05.ld, ex2, shared-memory stores back to back per row).  Here two threads share a row:
 // thread (quarter q, half h) owns keys [64h, 64h + 64) of the S tile and head-dim columns [16h, 16h + 16) of O.  The row maximum is
@@ -454,6 +686,25 @@ int attn_fwd_tc(const void* qkv, const int32_t* key_len, void* ctx, float* lse, 
     attr_set = true;
   }
   dim3 grid(cdiv(T, QT), H, B);
+  static int persist = -1;
+  if (persist < 0) { const char* e = getenv("EEC_ATTN_PERSIST"); persist = (e && e[0] == '0') ? 0 : 1; }   // persistent CTAs (default; 0 = one CTA per work item)
+  if (persist) {
+    static bool attrp = false;
+    static int sms = 0;
+    if (!attrp) {
+      EEC_CUDA(cudaFuncSetAttribute(attn_fwd_tcp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
+      EEC_CUDA(cudaFuncSetAttribute(attn_fwd_tcp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
+      int dev = 0;
+      if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 148;
+      attrp = true;
+    }
+    const int items = cdiv(T, QT) * H * B;
+    const dim3 pgrid(min(items, 2 * sms));
+    if (drop.state) launch_pdl(attn_fwd_tcp_kernel<true>, pgrid, dim3(AT_THREADS), AT_SMEM, st, tm, key_len, (__nv_bfloat16*)ctx, lse, T, H, B, drop, active_items());
+    else launch_pdl(attn_fwd_tcp_kernel<false>, pgrid, dim3(AT_THREADS), AT_SMEM, st, tm, key_len, (__nv_bfloat16*)ctx, lse, T, H, B, drop, active_items());
+    EEC_LAUNCH_CHECK();
+    return 0;
+  }
   static int fwd8 = -1;
   if (fwd8 < 0) { const char* e = getenv("EEC_ATTN_FWD8"); fwd8 = (e && e[0] == '1') ? 1 : 0; }   // eight softmax warps (opt-in until measured)
   if (fwd8) {
