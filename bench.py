@@ -270,7 +270,7 @@ def run_ours(args):
         ms_e2e = timed(e2e_step, args.steps)
 
     # inference RTFx per exit (BASELINE metric part (i)): forward truncated after exit e, bf16, eval
-    rtfx = ee_leg = fb_leg = eager_leg = None
+    rtfx = ee_leg = fb_leg = eager_leg = hbm_leg = None
     if rank == 0 and not args.skip_rtfx and not args.profile:
         audio_s = float(lengths.sum()) * FRAME_S
         rtfx = rtfx_per_exit(model, src_dev, lengths, audio_s, use_graph=not args.no_graph)
@@ -283,6 +283,7 @@ def run_ours(args):
                 return {"failed": f"{type(e).__name__}: {e}"[:300]}
         ee_leg = guarded(early_exit_leg, layers, args.precision, dev, src_dev, lengths, audio_s) if not args.no_graph else None
         fb_leg = guarded(fbank_leg, dev, with_cpu=(world == 1 and not args.skip_cpu))
+        hbm_leg = guarded(roofline_hbm_leg, dev, pk)
         if world == 1 and not args.skip_cpu:
             eager_leg = guarded(torch_eager_leg, layers, dev, src_dev, lengths, tg_dev, tl_dev, audio_s)
 
@@ -347,6 +348,8 @@ def run_ours(args):
             line["early_exit_inference"] = ee_leg
         if fb_leg is not None:
             line["fbank_frontend"] = fb_leg
+        if hbm_leg is not None:
+            line["roofline_hbm_kernel"] = hbm_leg
         if eager_leg is not None:
             line["torch_eager_same_gpu"] = eager_leg
         print(json.dumps(line), file=_JSON_OUT, flush=True)
@@ -563,6 +566,42 @@ def roofline_dominant(dev, pk):
             "achieved": round(ach, 2), "peak": pk["tf_burst"], "unit": "TFLOP/s", "frac": round(ach / pk["tf_burst"], 4),
             "traffic": 59.64e6, "ms_per_launch": round(ms, 4), "peak_source": pk["src"] + " burst (kernel timed alone)",
             "algorithmic_flops_per_launch": fl, "algorithmic_bytes_per_launch": 2 * (M * K + N * K + M * N)}
+
+
+def roofline_hbm_leg(dev, pk):
+    """The north star's second target (>= 70 % of HBM peak on the norm kernels): LayerNorm backward at the BASELINE row count, timed alone
+    with CUDA events and an L2 flush between launches.  Algorithmic bytes per launch: dy + x + dx in + dx out (fp32) + the bf16 operand
+    copy = N x 256 x 18 B = 110 MB; 60 launches per training step (22 us each there, partly out of L2)."""
+    from eec import ops
+    N = B * t_out(T_IN)
+    x = torch.randn(N, 256, device=dev)
+    dy = torch.randn(N, 256, device=dev)
+    g, b_ = torch.ones(256, device=dev), torch.zeros(256, device=dev)
+    out = torch.empty(N, 256, device=dev, dtype=torch.bfloat16)
+    mean, rstd = torch.empty(N, device=dev), torch.empty(N, device=dev)
+    ops.layernorm_fwd(x, g, b_, out, mean, rstd)
+    dx = torch.zeros(N, 256, device=dev)
+    dcopy = torch.empty(N, 256, device=dev, dtype=torch.bfloat16)
+    dg, db, cs = torch.zeros(256, device=dev), torch.zeros(256, device=dev), torch.zeros(256, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    run = lambda: ops.layernorm_bwd(dy, x, mean, rstd, g, dx, True, dg, db, dcopy, cs, 1.0)   # noqa: E731
+    for _ in range(3):
+        run()
+    total, n = 0.0, 10
+    for _ in range(n):
+        flush.zero_()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        run()
+        ev1.record()
+        torch.cuda.synchronize()
+        total += ev0.elapsed_time(ev1)
+    ms = total / n
+    nbytes = N * 256 * (4 * 4 + 2) + N * 8
+    ach = nbytes / (ms / 1e3) / 1e9
+    return {"kernel": "layernorm_bwd_kernel<bf16 copy> 23936 x 256 (+ dgamma/dbeta, fused bias-gradient column sums)", "bound": "hbm",
+            "achieved": round(ach, 1), "peak": pk["hbm"], "unit": "GB/s", "frac": round(ach / pk["hbm"], 4), "traffic": None,
+            "ms_per_launch": round(ms, 4), "algorithmic_bytes_per_launch": nbytes, "launches_per_step": 60}
 
 
 def cpu_step(sd, src, lengths, targets, tl):
