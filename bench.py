@@ -152,6 +152,137 @@ def synthetic(rank):
     return synthetic_batch(B, 1234 + rank)
 
 
+REF_DIR = os.path.join(ROOT, "baseline", "_ref")
+
+
+def load_reference():
+    """The UNMODIFIED reference (models/model/early_exit.py Early_conformer + util/noam_opt.py NoamOpt) from baseline/_ref
+    (byte-for-byte copies made by baseline/install_ref.py; git-ignored, shipped to the GPU box), or None when that directory is
+    absent -- the callers then fall back to the oracle port and say kind = "port"."""
+    if not os.path.isdir(os.path.join(REF_DIR, "models")):
+        return None
+    if REF_DIR not in sys.path:
+        sys.path.insert(0, REF_DIR)
+    try:
+        from models.model.early_exit import Early_conformer   # noqa: E402  (the reference)
+        from util.noam_opt import NoamOpt                      # noqa: E402
+    except Exception:   # noqa: BLE001
+        return None
+    return Early_conformer, NoamOpt
+
+
+def reference_model(ref, layers, device):
+    """the reference class with its own ctor call (train.py:166-178) and the benchmark's random-init weights"""
+    m = ref[0](src_pad_idx=0, n_enc_exits=N_EXITS, enc_voc_size=256, dec_voc_size=256, d_model=256, n_head=8, max_len=2000,
+               d_feed_forward=2048, n_enc_layers=layers, features_length=N_MELS, drop_prob=0.0, depthwise_kernel_size=31,
+               device=device)
+    m.load_state_dict(synthetic_state_dict(layers), strict=True)
+    return m.to(device)
+
+
+class ReferenceTrainer:
+    """The reference's own training step, statement for statement (train.py:53-70 with --decoder_mode ctc; loss and optimiser as
+    built at train.py:258-262): model(src, lengths) -> six nn.CTCLoss calls summed -> zero_grad -> backward -> clip_grad_norm_ ->
+    NoamOpt(AdamW).step().  Nothing of this repo's kernels, engine or model mirror is on this path."""
+
+    def __init__(self, ref, layers, device, autocast=False):
+        self.model = reference_model(ref, layers, device).train()
+        self.ctc = torch.nn.CTCLoss(blank=0, zero_infinity=True)
+        self.opt = ref[1](256, 25000, torch.optim.AdamW(params=self.model.parameters(), lr=0, betas=(0.9, 0.98), eps=1e-9,
+                                                        weight_decay=5e-4))
+        self.device, self.autocast = device, autocast
+
+    def step(self, src, lengths, targets, tl):
+        with torch.autocast(torch.device(self.device).type, dtype=torch.bfloat16, enabled=self.autocast):
+            encoder = self.model(src, lengths)
+        in_len = torch.full(size=(encoder.size(1),), fill_value=encoder.size(2), dtype=torch.long)
+        loss = 0
+        for enc in encoder:
+            loss += self.ctc(enc.float().permute(1, 0, 2), targets, in_len, tl)
+        self.model.zero_grad()
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(self.model.parameters(), 1.0)
+        with open(os.devnull, "w") as null:     # (NoamOpt.step prints "RATE: ..." every call, util/noam_opt.py:33)
+            import contextlib
+            with contextlib.redirect_stdout(null):
+                self.opt.step()
+        return loss
+
+
+def workload_config(layers):
+    """`config` of the JSON line: ONE definition for both arms (ours and --impl reference), so the driver sees the same workload."""
+    T = t_out(T_IN)
+    return {"workload": f"early_conformer CTC training step (fwd + summed {N_EXITS}-exit CTC + bwd + clip_grad_norm + Noam/AdamW update), "
+                        f"{N_EXITS} exits x {layers} layers, d_model 256, 15 s utterances (T_in {T_IN} -> T' {T}), batch {B} per model "
+                        f"call, dropout 0 (parity configuration), synthetic fbank + random-init weights",
+            "batch_per_gpu": B, "t_in": T_IN, "exits_x_layers": f"{N_EXITS}x{layers}",
+            "l2": "per-step working set ~8 GB >> 126 MB L2 (no flush needed)"}
+
+
+class TrainLeg:
+    """One complete training configuration on this rank: model, fused optimiser, [overlapped gradient reducer,] the step's CUDA graph."""
+
+    def __init__(self, args, layers, dev, world, rank, drop_p=0.0):
+        import torch.distributed as dist
+        import eec
+        self.args, self.world, self.dist, self.eec = args, world, dist, eec
+        self.model = model = build_model(layers, args.precision, dev).train()
+        model.dropout = drop_p
+        self.src, self.lengths, self.targets, self.tl = synthetic(rank)
+        self.tg_dev, self.tl_dev = self.targets.to(dev), self.tl.to(dev)
+        # optimiser (SURVEY 8f N1): clip_grad_norm_ + Noam + AdamW as three launches over flat buffers, reference hyper-parameters
+        self.opt = None if args.no_opt else eec.FusedNoamAdamW(model, model_size=256, warmup=25000, betas=(0.9, 0.98), eps=1e-9,
+                                                               weight_decay=5e-4, clip=1.0)
+        # data parallel: the gradient all-reduce runs DURING backward, one exit group at a time on a side stream
+        # (eec.distributed.OverlappedGradReducer); the collectives are stream-ordered, so they are captured into the step's graph
+        self.overlap = world > 1 and not args.no_overlap
+        if world > 1:
+            eec.distributed.broadcast_parameters(model, 0)
+            if self.opt is not None:
+                self.opt.refresh_shadow()
+        if self.overlap:
+            eec.distributed.OverlappedGradReducer(model, grad_dtype=args.grad_dtype)
+        self.in_graph = world == 1 or self.overlap      # is the whole step (incl. exchange + update) one graph?
+        self.graphed = None
+        self.parity = None
+
+    def capture(self, dev):
+        # the whole step (forward, 6-exit CTC, backward, [overlapped all-reduce,] clip + Noam + AdamW) is ONE CUDA graph.
+        # With --no-overlap the single flat-buffer all-reduce sits between the graph and an eager update.
+        if not self.args.no_graph:
+            self.graphed = self.eec.GraphedTrainStep(self.model, B, T_IN, self.targets.shape[1], optimizer=self.opt if self.in_graph else None)
+            self.graphed.load_inputs(self.src.to(dev), self.lengths, self.tg_dev, self.tl_dev)
+            self.src_dev = self.graphed.src   # timed steps run on inputs already resident in the graph's static buffer
+        else:
+            self.src_dev = self.src.to(dev)
+
+    def step(self, x=None):
+        g, model, opt = self.graphed, self.model, self.opt
+        if g is not None:
+            if x is not None and x is not g.src:
+                g.src.copy_(x, non_blocking=True)
+            loss = g.replay()
+        else:
+            out = model(self.src_dev if x is None else x, self.lengths)
+            loss = self.eec.multi_exit_ctc_loss(out, self.tg_dev, self.tl_dev)
+            model.zero_grad(set_to_none=True)
+            loss.backward()
+            if opt is not None and self.in_graph:
+                opt.step()
+        if not self.in_graph:
+            self.dist.all_reduce(model._flat_grad, op=self.dist.ReduceOp.AVG)
+            if opt is not None:
+                opt.step()
+        return loss
+
+    @property
+    def launches(self):
+        return self.graphed.launches_per_step if self.graphed is not None else None
+
+    def close(self):
+        self.graphed = None
+
+
 def run_ours(args):
     import torch.distributed as dist
     import eec
@@ -169,51 +300,7 @@ def run_ours(args):
     eec.load()
     pk = peaks()
     layers = args.layers_per_exit
-    model = build_model(layers, args.precision, dev).train()
-    model.dropout = args.train_drop_prob     # 0 by default (the parity configuration); > 0 profiles the dropout step
-    src, lengths, targets, tl = synthetic(rank)
-    src_pin = src.pin_memory()
-    src_dev = src.to(dev)
-    tg_dev, tl_dev = targets.to(dev), tl.to(dev)
     T = t_out(T_IN)
-
-    # optimiser: clip_grad_norm_ + Noam + AdamW as three launches over flat buffers, reference hyper-parameters
-    opt = None if args.no_opt else eec.FusedNoamAdamW(model, model_size=256, warmup=25000, betas=(0.9, 0.98), eps=1e-9,
-                                                      weight_decay=5e-4, clip=1.0)
-    # data parallel: the gradient all-reduce runs DURING backward, one exit group (21 MB) at a time on a side stream
-    # (eec.distributed.OverlappedGradReducer); the collectives are stream-ordered, so they are captured into the step's graph
-    overlap = world > 1 and not args.no_overlap
-    if overlap:
-        eec.distributed.broadcast_parameters(model, 0)
-        eec.distributed.OverlappedGradReducer(model)
-    in_graph = world == 1 or overlap      # is the whole step (incl. exchange + update) one graph?
-    graphed = None
-    if not args.no_graph:
-        # the whole step (forward, 6-exit CTC, backward, [overlapped all-reduce,] clip + Noam + AdamW) is ONE CUDA graph.
-        # With --no-overlap the single flat-buffer all-reduce sits between the graph and an eager update.
-        graphed = eec.GraphedTrainStep(model, B, T_IN, targets.shape[1], optimizer=opt if in_graph else None)
-        graphed.load_inputs(src_dev, lengths, tg_dev, tl_dev)
-
-    def step(x):
-        if graphed is not None:
-            if x is not graphed.src:
-                graphed.src.copy_(x, non_blocking=True)
-            loss = graphed.replay()
-        else:
-            out = model(x, lengths)
-            loss = eec.multi_exit_ctc_loss(out, tg_dev, tl_dev)
-            model.zero_grad(set_to_none=True)
-            loss.backward()
-            if opt is not None and in_graph:
-                opt.step()
-        if not in_graph:
-            dist.all_reduce(model._flat_grad, op=dist.ReduceOp.AVG)
-            if opt is not None:
-                opt.step()
-        return loss
-
-    if graphed is not None:
-        src_dev = graphed.src   # timed steps run on inputs already resident in the graph's static buffer
 
     def barrier():
         if world > 1:
@@ -235,31 +322,52 @@ def run_ours(args):
             ms = float(t.item())
         return ms
 
-    for _ in range(max(args.warmup, 3)):
-        step(src_dev)
+    # auxiliary legs never take the headline down with them: a failure is reported in place of the leg's numbers
+    def guarded(fn, *a, **k):
+        try:
+            return fn(*a, **k)
+        except Exception as e:   # noqa: BLE001
+            return {"failed": f"{type(e).__name__}: {e}"[:300]}
+
+    leg = TrainLeg(args, layers, dev, world, rank, drop_p=args.train_drop_prob)
+    model, lengths = leg.model, leg.lengths
+    # parity of the benchmarked step, in the run that times it (rank 0; initial weights; the reference's CPU forward on the same batch)
+    parity = None
+    if rank == 0 and not args.skip_cpu and not args.skip_parity and not args.profile:
+        parity = guarded(parity_leg, model, layers, leg.src, lengths, leg.targets, leg.tl, dev)
+    leg.capture(dev)
+    src_pin = leg.src.pin_memory()
+    graphed = leg.graphed
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
+        leg.step()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     launches0 = L.load().eec_launch_count()
     if args.profile:
         torch.cuda.profiler.start()
-    ms = timed(lambda: step(src_dev), args.steps)
+    ms = timed(leg.step, args.steps)
     if args.profile:
         torch.cuda.profiler.stop()
-    launches = graphed.launches_per_step if graphed is not None else (L.load().eec_launch_count() - launches0) // args.steps
+    launches = leg.launches if graphed is not None else (L.load().eec_launch_count() - launches0) // args.steps
     clocks = sampler.stop() if rank == 0 else None
 
     # end to end: every step uploads one batch of features from pinned host memory and reads its loss back.  With the graph the
     # upload of step i+1 is issued right after step i's replay (GraphedTrainStep.prefetch: side stream -> staging buffer) and is
     # committed to the graph's static input at the start of step i+1, so it overlaps step i's kernels like a prefetching loader.
+    # lengths / targets / target lengths (5.8 KB) are uploaded with every step as well (GraphedTrainStep.load_small).
+    small_bytes = (leg.lengths.numel() + leg.targets.numel() + leg.tl.numel()) * 8
+
     def e2e_step():
         if graphed is not None:
             graphed.commit_prefetch()
-            loss = step(graphed.src)
+            graphed.load_small(leg.lengths, leg.targets, leg.tl)
+            loss = leg.step()
             graphed.prefetch(src_pin)
             return float(loss.item())
         x = src_pin.to(dev, non_blocking=True)
-        return float(step(x).item())
+        return float(leg.step(x).item())
 
     if args.profile:
         ms_e2e = float("nan")
@@ -269,23 +377,24 @@ def run_ours(args):
         e2e_step()
         ms_e2e = timed(e2e_step, args.steps)
 
+    # DP step kernel list (torch.profiler / CUPTI on rank 0; ncu cannot follow a multi-rank job): written next to the JSON line
+    if args.kernel_trace and graphed is not None:
+        guarded(kernel_trace, leg.step, args.kernel_trace, rank)
+
     # inference RTFx per exit (BASELINE metric part (i)): forward truncated after exit e, bf16, eval
-    rtfx = ee_leg = fb_leg = eager_leg = hbm_leg = None
+    rtfx = ee_leg = fb_leg = eager_leg = hbm_leg = f32_leg = None
+    src_dev = leg.src_dev
+    audio_s = float(lengths.sum()) * FRAME_S
     if rank == 0 and not args.skip_rtfx and not args.profile:
-        audio_s = float(lengths.sum()) * FRAME_S
         rtfx = rtfx_per_exit(model, src_dev, lengths, audio_s, use_graph=not args.no_graph)
         model.train()
-        # auxiliary legs never take the headline down with them: a failure is reported in place of the leg's numbers
-        def guarded(fn, *a, **k):
-            try:
-                return fn(*a, **k)
-            except Exception as e:   # noqa: BLE001
-                return {"failed": f"{type(e).__name__}: {e}"[:300]}
         ee_leg = guarded(early_exit_leg, layers, args.precision, dev, src_dev, lengths, audio_s) if not args.no_graph else None
         fb_leg = guarded(fbank_leg, dev, with_cpu=(world == 1 and not args.skip_cpu))
         hbm_leg = guarded(roofline_hbm_leg, dev, pk)
+        if world == 1 and not args.no_graph and args.precision == "bf16":
+            f32_leg = guarded(fp32_leg, layers, dev, src_dev, lengths, leg.tg_dev, leg.tl_dev, audio_s, leg.targets.shape[1])
         if world == 1 and not args.skip_cpu:
-            eager_leg = guarded(torch_eager_leg, layers, dev, src_dev, lengths, tg_dev, tl_dev, audio_s)
+            eager_leg = guarded(torch_eager_leg, layers, dev, src_dev, lengths, leg.tg_dev, leg.tl_dev, audio_s)
 
     # the same step at the reference's DEFAULT --drop_prob 0.1 (util/conf.py:283-291): fused counter-based dropout at all
     # seven sites per layer + after the positional encoding, masks regenerated in backward (nothing stored)
@@ -293,15 +402,15 @@ def run_ours(args):
     if args.drop_prob > 0 and not args.profile and graphed is not None:
         model.train()
         model.dropout = args.drop_prob
-        g2 = eec.GraphedTrainStep(model, B, T_IN, targets.shape[1], optimizer=opt if in_graph else None)
-        g2.load_inputs(src_dev, lengths, tg_dev, tl_dev)
+        g2 = eec.GraphedTrainStep(model, B, T_IN, leg.targets.shape[1], optimizer=leg.opt if leg.in_graph else None)
+        g2.load_inputs(src_dev, lengths, leg.tg_dev, leg.tl_dev)
 
         def dstep():
             loss = g2.replay()
-            if not in_graph:
+            if not leg.in_graph:
                 dist.all_reduce(model._flat_grad, op=dist.ReduceOp.AVG)
-                if opt is not None:
-                    opt.step()
+                if leg.opt is not None:
+                    leg.opt.step()
             return loss
         for _ in range(3):
             dstep()
@@ -310,6 +419,32 @@ def run_ours(args):
                     "value": round(world * B / (ms_d / args.steps / 1e3), 2), "unit": "utt/s", "gpu_launches": g2.launches_per_step}
         model.dropout = 0.0
         del g2
+
+    # BASELINE configs[2]: the 18-layer (6 exits x 3 layers) model, data parallel at N = 2 / 4 / 8 (and at N = 1 for the efficiency's
+    # denominator): the same complete step, gradient slices of 31 MB per exit group (188 MB per step)
+    deep_leg = None
+    if layers != 3 and not args.skip_deep and not args.profile and graphed is not None:
+        leg.close()
+        graphed = None
+        del leg
+        torch.cuda.empty_cache()
+
+        def deep():
+            dl = TrainLeg(args, 3, dev, world, rank)
+            dl.capture(dev)
+            for _ in range(3):
+                dl.step()
+            ms_deep = timed(dl.step, args.steps) / args.steps
+            fl = 3.0 * model_flops_fwd(B * T, T, N_EXITS * 3)
+            res = {"config": "BASELINE configs[2]: early_conformer 6 exits x 3 layers (18 layers), batch 64 per GPU, data parallel "
+                             f"dp{world}", "ms_per_step": round(ms_deep, 3), "value": round(world * B / (ms_deep / 1e3), 2), "unit": "utt/s",
+                   "n_gpus": world, "gpu_launches": dl.launches, "grad_bytes_all_reduced_per_step": 46977536 * (2 if args.grad_dtype == "bf16" else 4) if world > 1 else 0,
+                   "step_tensor_frac_of_sustained": round(fl / (ms_deep / 1e3) / 1e12 / pk["tf_sust"], 4)}
+            dl.close()
+            return res
+        deep_leg = guarded(deep)
+        if world > 1:
+            barrier()
 
     roof = cpu = None
     if rank == 0:
@@ -321,43 +456,135 @@ def run_ours(args):
         per_step = ms / args.steps
         value = world * B / (per_step / 1e3)
         flops = 3.0 * model_flops_fwd(B * T, T, N_EXITS * layers)
+        overlap = world > 1 and not args.no_overlap
+        cfg = workload_config(layers)
         line = {
             "metric": "train_utts_per_sec", "value": round(value, 2), "unit": "utt/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": round(per_step, 3), "higher_is_better": True, "scaling": "weak",
+            "warmup": warm, "ms_per_step": round(per_step, 3), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
-            "config": {"workload": f"early_conformer CTC training step (fwd + summed 6-exit CTC + bwd), {N_EXITS} exits x {layers} "
-                                   f"layers, d_model 256, batch {B}/GPU x 15 s (T_in {T_IN} -> T' {T}), grad all-reduce "
-                                   f"{('NCCL fp32, per exit group, overlapped with backward inside the graph' if overlap else 'NCCL fp32 flat buffer after backward') if world > 1 else 'n/a'}; "
-                                   + ("optimizer step excluded" if opt is None else "clip_grad_norm + Noam + AdamW update included (fused, flat buffers)")
-                                   + (f"; dropout {args.train_drop_prob}" if args.train_drop_prob > 0 else "; dropout 0 (parity configuration)"),
-                       "global_batch": world * B, "parallelism": f"dp{world}",
-                       "l2": "per-step working set ~8 GB >> 126 MB L2 (no flush needed)",
-                       "launch": "eager (ctypes launches)" if graphed is None else "one CUDA graph replay per step",
-                       "step_tflops_algorithmic": round(flops / 1e12, 3),
-                       "step_tensor_frac_of_sustained": round(flops / (per_step / 1e3) / 1e12 / pk["tf_sust"], 4),
-                       "peaks": pk["src"]},
+            "config": cfg,
+            "details": {"global_batch": world * B, "parallelism": f"dp{world}",
+                        "grad_all_reduce": (f"NCCL {args.grad_dtype}, per exit group, overlapped with backward inside the graph" if overlap
+                                            else "NCCL fp32 flat buffer after backward") if world > 1 else "n/a",
+                        "optimizer": "excluded" if args.no_opt else "clip_grad_norm + Noam + AdamW update included (fused, flat buffers)",
+                        "dropout": args.train_drop_prob,
+                        "launch": "eager (ctypes launches)" if args.no_graph else "one CUDA graph replay per step",
+                        "step_tflops_algorithmic": round(flops / 1e12, 3),
+                        "step_tensor_frac_of_sustained": round(flops / (per_step / 1e3) / 1e12 / pk["tf_sust"], 4),
+                        "peaks": pk["src"]},
             "e2e": {"value": round(world * B / (ms_e2e / args.steps / 1e3), 2), "unit": "utt/s",
-                    "h2d_bytes_per_step": src_pin.numel() * 4, "d2h_bytes_per_step": 4},
+                    "h2d_bytes_per_step": src_pin.numel() * 4 + small_bytes, "d2h_bytes_per_step": 4},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+            "parity_vs_reference": parity,
         }
-        if rtfx is not None:
-            line["rtfx_per_exit"] = rtfx
-        if drop_leg is not None:
-            line["train_with_dropout"] = drop_leg
-        if ee_leg is not None:
-            line["early_exit_inference"] = ee_leg
-        if fb_leg is not None:
-            line["fbank_frontend"] = fb_leg
-        if hbm_leg is not None:
-            line["roofline_hbm_kernel"] = hbm_leg
-        if eager_leg is not None:
-            line["torch_eager_same_gpu"] = eager_leg
+        for key, val in (("rtfx_per_exit", rtfx), ("train_with_dropout", drop_leg), ("dp_18_layers", deep_leg),
+                         ("early_exit_inference", ee_leg), ("fbank_frontend", fb_leg), ("roofline_hbm_kernel", hbm_leg),
+                         ("fp32_mode", f32_leg), ("torch_eager_same_gpu", eager_leg)):
+            if val is not None:
+                line[key] = val
         print(json.dumps(line), file=_JSON_OUT, flush=True)
     if world > 1:
         graphed = None          # (graphs that hold captured NCCL kernels are released before the communicator)
         torch.cuda.synchronize()
         dist.barrier()
         dist.destroy_process_group()
+
+
+def kernel_trace(step, path, rank):
+    """Kernel list of ONE training step on rank 0 through torch.profiler (CUPTI activity records: names + device durations, including the
+    ncclDevKernel_* launches captured in the step's graph) -- ncu replays kernels and cannot profile a multi-rank job."""
+    from torch.profiler import ProfilerActivity, profile
+    if rank != 0:
+        for _ in range(3):
+            step()
+        torch.cuda.synchronize()
+        return
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        for _ in range(3):
+            step()
+        torch.cuda.synchronize()
+    rows = {}
+    for ev in prof.events():
+        if ev.device_type is not None and str(ev.device_type).endswith("CUDA") and ev.device_time > 0:
+            r = rows.setdefault(ev.name, [0, 0.0])
+            r[0] += 1
+            r[1] += ev.device_time
+    tot = sum(v[1] for v in rows.values())
+    os.makedirs(os.path.dirname(os.path.abspath(path)) or ".", exist_ok=True)
+    with open(path, "w") as f:
+        f.write("# torch.profiler (CUPTI) kernel list of 3 replays of the training-step graph, rank 0; device time per launch\n")
+        f.write(f"# total kernel time {tot / 3 / 1e3:.3f} ms per step\n")
+        f.write("share%  total_us_per_step  launches_per_step  avg_us  kernel\n")
+        for name, (n, us) in sorted(rows.items(), key=lambda kv: -kv[1][1]):
+            f.write(f"{100 * us / tot:6.2f}  {us / 3:10.1f}  {n / 3:8.1f}  {us / n:9.2f}  {name[:160]}\n")
+
+
+def parity_leg(model, layers, src, lengths, targets, tl, dev):
+    """The HEADLINE step checked in the run that times it: train-mode log-probabilities of every exit and the summed 6-exit CTC loss of the
+    benchmarked model on the benchmarked batch (B = 64, initial weights), from the CUDA path and from the reference's CPU path (baseline/_ref,
+    unmodified, fp32; oracle port when absent) -- relative errors per exit (maxabs(a-b)/maxabs(b), the north star's definition) and of the loss."""
+    import eec
+    bufs = {n: b.detach().clone() for n, b in model.named_buffers()}      # a train-mode forward moves the BatchNorm running stats:
+    with torch.no_grad():
+        out = model(src.to(dev), lengths)
+        loss = float(eec.multi_exit_ctc_loss(out, targets, tl))
+        for n, b in model.named_buffers():                                  # ... put them back, the timed steps start from the same state
+            b.copy_(bufs[n])
+    out = out.cpu()
+    t0 = time.perf_counter()
+    torch.set_num_threads(len(os.sched_getaffinity(0)))
+    ref = load_reference()
+    with torch.no_grad():
+        if ref is not None:
+            kind = "reference"
+            r = reference_model(ref, layers, torch.device("cpu")).train()(src, lengths)
+        else:
+            from oracle import conformer_oracle as O
+            kind = "port"
+            r = O.early_conformer_forward(synthetic_state_dict(layers), src, lengths, training=True, bn_out={})
+        in_len = torch.full((r.shape[1],), r.shape[2], dtype=torch.long)
+        ctc = torch.nn.CTCLoss(blank=0, zero_infinity=True)
+        rloss = float(sum(ctc(enc.permute(1, 0, 2), targets, in_len, tl) for enc in r))
+    per_exit = [round(float((out[e] - r[e]).abs().max() / r[e].abs().max()), 6) for e in range(r.shape[0])]
+    tol = 2e-2 if model.precision == "bf16" else 1e-3
+    return {"against": f"the reference's CPU forward (kind {kind}, fp32, train-mode BatchNorm) on the same {src.shape[0]}-utterance batch and weights",
+            "kind": kind, "logprob_rel_err_per_exit": per_exit, "loss": round(loss, 5), "loss_reference": round(rloss, 5),
+            "loss_rel_err": round(abs(loss - rloss) / abs(rloss), 7), "tolerance": tol,
+            "ok": bool(max(per_exit) < tol and abs(loss - rloss) / abs(rloss) < tol), "cpu_seconds": round(time.perf_counter() - t0, 1)}
+
+
+def _time_loop(run, n, warm=3):
+    for _ in range(warm):
+        run()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(n):
+        run()
+    ev1.record()
+    torch.cuda.synchronize()
+    return ev0.elapsed_time(ev1) / n
+
+
+def fp32_leg(layers, dev, src_dev, lengths, tg_dev, tl_dev, audio_s, targets_w):
+    """model.precision = "fp32" (the mirror's DEFAULT, what INTEGRATION.md's two-line switch gives a maintainer before opting into bf16):
+    CUDA-core FFMA GEMMs and attention, reference-accurate (greedy tokens bit-exact).  Training step and six-exit forward, one graph each."""
+    import eec
+    m = build_model(layers, "fp32", dev).train()
+    opt = eec.FusedNoamAdamW(m, model_size=256, warmup=25000, betas=(0.9, 0.98), eps=1e-9, weight_decay=5e-4, clip=1.0)
+    g = eec.GraphedTrainStep(m, B, T_IN, targets_w, optimizer=opt)
+    g.load_inputs(src_dev, lengths, tg_dev, tl_dev)
+    ms_train = _time_loop(g.replay, 3, warm=2)
+    del g, opt
+    m.eval()
+    with torch.no_grad():
+        fwd = eec.GraphedForward(m, B, T_IN)
+        fwd(src_dev, lengths)
+        ms_fwd = _time_loop(fwd.replay, 5, warm=2)
+    del fwd, m
+    torch.cuda.empty_cache()
+    return {"precision": "fp32 (FFMA kernels, no tensor cores)", "train_ms_per_step": round(ms_train, 2), "train_utt_per_s": round(B / (ms_train / 1e3), 1),
+            "inference_all_exits_ms": round(ms_fwd, 2), "inference_rtfx": round(audio_s / (ms_fwd / 1e3), 1)}
 
 
 def rtfx_per_exit(model, src_dev, lengths, audio_s, use_graph=True):
@@ -427,59 +654,13 @@ def early_exit_leg(layers, precision, dev, src_dev, lengths, audio_s):
 
 
 def torch_eager_leg(layers, dev, src_dev, lengths, tg_dev, tl_dev, audio_s):
-    """"the existing Blackwell kernel bar" -- the same model assembled from the LIBRARY modules the reference itself
-    calls (torchaudio.models.Conformer x 6, nn.Conv1d x 2, nn.Linear heads, nn.CTCLoss; early_exit.py:594-634, train.py:53-70) and run
-    by eager PyTorch on the same B200: cuBLAS / cuDNN / SDPA / ATen kernels, fp32 with torch's default TF32 settings like the reference,
-    and once more under bf16 autocast.  Same batch, same step contents (forward, summed 6-exit CTC, backward, clip_grad_norm_, AdamW).
-    A reported baseline: none of this is on the product path."""
-    try:
-        import torchaudio
-    except Exception as e:     # pragma: no cover
-        return {"unavailable": f"torchaudio import failed: {e}"}
-    nn = torch.nn
-
-    class Ref(nn.Module):
-        def __init__(self):
-            super().__init__()
-            self.c1, self.c2 = nn.Conv1d(N_MELS, 256, 3, 2), nn.Conv1d(256, 256, 3, 2)
-            pe = torch.zeros(2000, 256)
-            pos = torch.arange(2000).unsqueeze(1)
-            div = torch.exp(torch.arange(0, 256, 2) * (-torch.log(torch.tensor(10000.0)) / 256))
-            pe[:, 0::2], pe[:, 1::2] = torch.sin(pos * div), torch.cos(pos * div)
-            self.register_buffer("pe", pe)
-            self.heads = nn.ModuleList([nn.Linear(256, 256) for _ in range(N_EXITS)])
-            self.groups = nn.ModuleList([torchaudio.models.Conformer(input_dim=256, num_heads=8, ffn_dim=2048, num_layers=layers,
-                                                                      depthwise_conv_kernel_size=31, dropout=0.0) for _ in range(N_EXITS)])
-
-        def forward(self, x, lens):
-            x = self.c2(self.c1(x)).permute(0, 2, 1)
-            x = x + self.pe[: x.size(1)]
-            ln = torch.clamp(lens / 4, max=x.size(1)).to(torch.int).to(x.device)
-            outs = []
-            for head, grp in zip(self.heads, self.groups):
-                x, _ = grp(x, ln)
-                outs.append(torch.log_softmax(head(x), dim=2).unsqueeze(0))
-            return torch.cat(outs)
-
-    torch.manual_seed(0)
-    m = Ref().to(dev)
-    opt = torch.optim.AdamW(m.parameters(), lr=1e-4, betas=(0.9, 0.98), eps=1e-9, weight_decay=5e-4)
-    ctc = nn.CTCLoss(blank=0, zero_infinity=True)
-    T = t_out(T_IN)
-    in_len = torch.full((B,), T, dtype=torch.long)
-
-    def train_step(autocast):
-        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
-            out = m(src_dev, lengths)
-        loss = sum(ctc(enc.float().permute(1, 0, 2), tg_dev, in_len, tl_dev) for enc in out)
-        opt.zero_grad(set_to_none=True)
-        loss.backward()
-        torch.nn.utils.clip_grad_norm_(m.parameters(), 1.0)
-        opt.step()
-
-    def infer(autocast):
-        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
-            m(src_dev, lengths)
+    """"the existing Blackwell kernel bar" -- the UNMODIFIED reference module (baseline/_ref: models/model/early_exit.py
+    Early_conformer over torchaudio.models.Conformer, nn.CTCLoss, clip_grad_norm_, NoamOpt(AdamW); train.py:53-70) run by eager PyTorch
+    on the same B200: cuBLAS / cuDNN / SDPA / ATen kernels, fp32 with torch's default TF32 settings like the reference, and once more under
+    bf16 autocast.  Same batch, same weights, same step contents.  A reported baseline: none of this is on the product path."""
+    ref = load_reference()
+    if ref is None:
+        return {"unavailable": "baseline/_ref absent (python baseline/install_ref.py in the authoring container)"}
 
     def t(fn, n=3):
         for _ in range(2):
@@ -492,16 +673,22 @@ def torch_eager_leg(layers, dev, src_dev, lengths, tg_dev, tl_dev, audio_s):
         ev1.record()
         torch.cuda.synchronize()
         return ev0.elapsed_time(ev1) / n
-    res = {"what": "torchaudio.models.Conformer x 6 + nn.Conv1d/Linear/CTCLoss, eager PyTorch on the same GPU (library kernels)"}
-    m.train()
-    res["train_ms_per_step_fp32"] = round(t(lambda: train_step(False)), 2)
-    res["train_ms_per_step_bf16_autocast"] = round(t(lambda: train_step(True)), 2)
-    m.eval()
-    ms32, ms16 = t(lambda: infer(False)), t(lambda: infer(True))
-    res["inference_all_exits_ms_fp32"], res["inference_all_exits_ms_bf16_autocast"] = round(ms32, 2), round(ms16, 2)
-    res["inference_rtfx_bf16_autocast"] = round(audio_s / (ms16 / 1e3), 1)
-    del m, opt
-    torch.cuda.empty_cache()
+    res = {"what": "the reference's own Early_conformer module + train.py step (baseline/_ref, unmodified), eager PyTorch on the same GPU "
+                   "(library kernels)", "kind": "reference"}
+    for key, ac in (("fp32", False), ("bf16_autocast", True)):
+        tr = ReferenceTrainer(ref, layers, dev, autocast=ac)
+        res[f"train_ms_per_step_{key}"] = round(t(lambda: tr.step(src_dev, lengths, tg_dev, tl_dev)), 2)
+        tr.model.eval()
+
+        def infer():
+            with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=ac):
+                tr.model(src_dev, lengths)
+        ms = t(infer)
+        res[f"inference_all_exits_ms_{key}"] = round(ms, 2)
+        if ac:
+            res["inference_rtfx_bf16_autocast"] = round(audio_s / (ms / 1e3), 1)
+        del tr
+        torch.cuda.empty_cache()
     return res
 
 
@@ -535,6 +722,18 @@ def fbank_leg(dev, with_cpu):
     return leg
 
 
+def ncu_traffic(key):
+    """(bytes per launch, source) of kernel `key` from profiles/ncu_traffic.json -- written by tools/ncu_traffic.py from an
+    `ncu --set full` capture (dram__bytes_read.sum + dram__bytes_write.sum) -- or (None, None)."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        with open(path) as f:
+            e = json.load(f)[key]
+        return float(e["dram_bytes_read"]) + float(e["dram_bytes_write"]), e.get("source")
+    except Exception:   # noqa: BLE001
+        return None, None
+
+
 def roofline_dominant(dev, pk):
     """Dominant kernel = the FFN up-projection GEMM (M=23936, N=2048, K=256, bias+SiLU epilogue; 24 launches per
     forward, ~37% of model FLOPs together with its twin).  Timed alone with CUDA events, L2 flushed between launches."""
@@ -559,12 +758,12 @@ def roofline_dominant(dev, pk):
     ms = total / n
     fl = 2.0 * M * N * K
     ach = fl / (ms / 1e3) / 1e12
-    # traffic: dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of this kernel from the committed ncu --set full capture
-    # (profiles/r01n_kernels_full.txt: 13.36 MB read + 46.28 MB written; the rest of the 98 MB output is still in the 126 MB L2
-    # when the kernel ends, so DRAM traffic is BELOW the algorithmic bytes: nothing is re-read)
+    # traffic: dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of this kernel, taken from the ncu --set full capture that
+    # tools/ncu_traffic.py summarised into profiles/ncu_traffic.json (null when that file does not name this kernel: nothing is typed in)
+    traffic, traffic_src = ncu_traffic("ffn_up_silu")
     return {"kernel": "gemm_tc3_kernel<K-major,K-major,EPI_GENERIC> FFN up-proj 23936x2048x256 +bias+SiLU", "bound": "tensor",
             "achieved": round(ach, 2), "peak": pk["tf_burst"], "unit": "TFLOP/s", "frac": round(ach / pk["tf_burst"], 4),
-            "traffic": 59.64e6, "ms_per_launch": round(ms, 4), "peak_source": pk["src"] + " burst (kernel timed alone)",
+            "traffic": traffic, "traffic_source": traffic_src, "ms_per_launch": round(ms, 4), "peak_source": pk["src"] + " burst (kernel timed alone)",
             "algorithmic_flops_per_launch": fl, "algorithmic_bytes_per_launch": 2 * (M * K + N * K + M * N)}
 
 
@@ -600,11 +799,12 @@ def roofline_hbm_leg(dev, pk):
     nbytes = N * 256 * (4 * 4 + 2) + N * 8
     ach = nbytes / (ms / 1e3) / 1e9
     return {"kernel": "layernorm_bwd_kernel<bf16 copy> 23936 x 256 (+ dgamma/dbeta, fused bias-gradient column sums)", "bound": "hbm",
-            "achieved": round(ach, 1), "peak": pk["hbm"], "unit": "GB/s", "frac": round(ach / pk["hbm"], 4), "traffic": None,
+            "achieved": round(ach, 1), "peak": pk["hbm"], "unit": "GB/s", "frac": round(ach / pk["hbm"], 4), "traffic": ncu_traffic("layernorm_bwd")[0], "traffic_source": ncu_traffic("layernorm_bwd")[1],
             "ms_per_launch": round(ms, 4), "algorithmic_bytes_per_launch": nbytes, "launches_per_step": 60}
 
 
-def cpu_step(sd, src, lengths, targets, tl):
+def port_step(sd, src, lengths, targets, tl):
+    """fallback when baseline/_ref is absent: the oracle port of the same step (kind = "port"; forward + loss + backward only)"""
     from oracle import conformer_oracle as O
     sdg = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k and k != "positional_encoder.pe" else v)
            for k, v in sd.items()}
@@ -617,31 +817,55 @@ def cpu_step(sd, src, lengths, targets, tl):
     return float(loss.detach())
 
 
-def cpu_baseline(layers, sample_b=8, steps=1):
-    """The reference's CPU path (oracle port: same arithmetic, torch CPU ops, all host threads) on a bounded sample."""
+def cpu_arm(layers, sample_b):
+    """-> (step(), kind, infer()): the reference's CPU path on `sample_b` utterances of the benchmark batch -- the real reference
+    module from baseline/_ref when present (kind "reference"), else the oracle port (kind "port")."""
+    src, lengths, targets, tl = synthetic_batch(sample_b, 1234)
+    ref = load_reference()
+    if ref is not None:
+        tr = ReferenceTrainer(ref, layers, torch.device("cpu"))
+
+        def infer():
+            tr.model.eval()
+            with torch.no_grad():
+                tr.model(src, lengths)
+            tr.model.train()
+        return (lambda: tr.step(src, lengths, targets, tl)), "reference", infer, lengths
+    sd = synthetic_state_dict(layers)
+    from oracle import conformer_oracle as O
+
+    def infer():
+        with torch.no_grad():
+            O.early_conformer_forward(sd, src, lengths)
+    return (lambda: port_step(sd, src, lengths, targets, tl)), "port", infer, lengths
+
+
+def cpu_baseline(layers, sample_b=16, steps=2):
+    """The reference's CPU path on the GPU box's host cores, on a bounded sample (`sample_b` of the 64 utterances per step: 16 is the
+    sub-batch size the reference's own loader feeds the model, batch_size 64 / n_batch_split 4, util/data_loader.py:166-188)."""
     cores = len(os.sched_getaffinity(0))
     torch.set_num_threads(cores)
-    sd = synthetic_state_dict(layers)
-    src, lengths, targets, tl = synthetic_batch(sample_b, 1234)
+    step, kind, infer, lengths = cpu_arm(layers, sample_b)
+    step()                                        # one untimed step (allocator, thread pool)
     t0 = time.perf_counter()
     for _ in range(steps):
-        cpu_step(sd, src, lengths, targets, tl)
+        step()
     dt = (time.perf_counter() - t0) / steps
     # BASELINE configs[0] (the reference's CPU-runnable case): eval forward of all six exits, no grad, same sample
-    from oracle import conformer_oracle as O
-    with torch.no_grad():
-        t1 = time.perf_counter()
-        O.early_conformer_forward(sd, src, lengths)
-        dti = time.perf_counter() - t1
+    t1 = time.perf_counter()
+    infer()
+    dti = time.perf_counter() - t1
     audio_s = float(lengths.sum()) * FRAME_S
-    return {"value": round(sample_b / dt, 3), "unit": "utt/s", "cores": cores, "kind": "port",
-            "sample": f"{steps} training step(s) (fwd + 6-exit CTC + bwd, fp32) on {sample_b} of the 64 utterances, same T_in={T_IN}, "
-                      f"{N_EXITS}x{layers} layers; {dt:.1f} s per step",
+    return {"value": round(sample_b / dt, 3), "unit": "utt/s", "cores": cores, "kind": kind,
+            "sample": f"{steps} training steps (fwd + 6-exit CTC + bwd + clip + Noam/AdamW, fp32) on {sample_b} of the 64 utterances per "
+                      f"step, same T_in={T_IN}, {N_EXITS}x{layers} layers; {dt:.2f} s per step",
             "inference_rtfx_all_exits": round(audio_s / dti, 1),
             "inference_sample": f"eval forward of all {N_EXITS} exits (fp32, no grad) on the same {sample_b} utterances: {dti:.2f} s for {audio_s:.0f} s of audio"}
 
 
 def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the step (baseline/_ref, unmodified) on all host cores, each step a
+    bounded sample (--cpu-sample utterances of the 64-utterance batch) of the same workload, same metric / unit / config."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -649,25 +873,23 @@ def run_reference(args):
     torch.set_num_threads(cores)
     layers = args.layers_per_exit
     sb = args.cpu_sample
-    sd = synthetic_state_dict(layers)
-    src, lengths, targets, tl = synthetic_batch(sb, 1234)
-    for _ in range(min(args.warmup, 1)):
-        cpu_step(sd, src, lengths, targets, tl)
+    step, kind, _, _ = cpu_arm(layers, sb)
+    warm = args.warmup
+    for _ in range(warm):
+        step()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        cpu_step(sd, src, lengths, targets, tl)
+        step()
     dt = (time.perf_counter() - t0) / args.steps
     value = sb / dt
-    T = t_out(T_IN)
     line = {
         "impl": "reference", "metric": "train_utts_per_sec", "value": round(value, 3), "unit": "utt/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": round(dt * 1e3, 1), "higher_is_better": True,
+        "steps": args.steps, "warmup": warm, "ms_per_step": round(dt * 1e3, 1), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"early_conformer CTC training step (fwd + summed 6-exit CTC + bwd), {N_EXITS} exits x {layers} layers, "
-                               f"d_model 256, T_in {T_IN} -> T' {T}; CPU reference path, bounded sample of {sb} utterances per step",
-                   "global_batch": sb, "parallelism": "cpu"},
-        "cpu_baseline": {"value": round(value, 3), "unit": "utt/s", "cores": cores, "kind": "port",
-                         "sample": f"{args.steps} steps x {sb} utterances (of the 64-utterance batch), {dt:.1f} s per step"},
+        "config": workload_config(layers),
+        "cpu_baseline": {"value": round(value, 3), "unit": "utt/s", "cores": cores, "kind": kind,
+                         "sample": f"{args.steps} timed steps x {sb} utterances (of the 64-utterance batch; 16 = the reference loader's own "
+                                   f"sub-batch, batch_size 64 / n_batch_split 4), {dt:.2f} s per step"},
         "e2e": {"value": round(value, 3), "unit": "utt/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), file=_JSON_OUT, flush=True)
@@ -684,7 +906,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--layers-per-exit", type=int, default=2, help="2 = BASELINE configs[1]; 3 = configs[2] (18 layers)")
-    ap.add_argument("--cpu-sample", type=int, default=64, help="utterances per CPU-baseline step (64 = the full batch)")
+    ap.add_argument("--cpu-sample", type=int, default=16, help="utterances per CPU step of the reference arm / cpu_baseline leg (16 = the reference loader's own sub-batch; 64 = the full batch)")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--no-opt", action="store_true", help="time forward + loss + backward only (no clip / Noam / AdamW update)")
     ap.add_argument("--no-graph", action="store_true", help="issue the ~600 kernels of a step eagerly instead of replaying the CUDA graph")
@@ -695,6 +917,10 @@ def main():
                     "(outside the graph) instead of per-exit-group all-reduces overlapped with backward")
     ap.add_argument("--drop-prob", type=float, default=0.1, help="extra leg: the same training step with dropout at this probability "
                     "(the reference's default); the headline step runs at 0 like the parity tests (SURVEY 8d). 0 skips the leg")
+    ap.add_argument("--skip-parity", action="store_true", help="skip the in-run parity check of the headline step against the reference's CPU forward")
+    ap.add_argument("--skip-deep", action="store_true", help="skip the 18-layer (BASELINE configs[2]) leg")
+    ap.add_argument("--grad-dtype", default="fp32", choices=["fp32", "bf16"], help="N > 1: wire format of the overlapped gradient all-reduce")
+    ap.add_argument("--kernel-trace", default="", help="write a torch.profiler kernel list of one step (rank 0) to this path")
     ap.add_argument("--profile", action="store_true", help="bracket the timed region with cudaProfilerStart/Stop (for ncu "
                     "--profile-from-start off) and skip the e2e / rtfx / roofline / cpu legs")
     args = ap.parse_args()

@@ -1,5 +1,8 @@
 // api.cu -- C-ABI glue: error state, device check, GEMM backend dispatch.
 #include <atomic>
+#include <mutex>
+#include <utility>
+#include <vector>
 #include <stdarg.h>
 #include <stdlib.h>
 #include <string.h>
@@ -19,8 +22,16 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
-static thread_local ActiveItems g_active = {nullptr, 0, 0};
-ActiveItems active_items() { return g_active; }
+// active-item limits are keyed by the stream the kernels are launched on: two models (or two streams) in one process never see each
+// other's limit, and the handle a caller passes is the stream it already passes to every entry point
+static std::mutex g_active_mu;
+static std::vector<std::pair<cudaStream_t, ActiveItems>> g_active;
+ActiveItems active_items(cudaStream_t stream) {
+  std::lock_guard<std::mutex> lk(g_active_mu);
+  for (const auto& e : g_active)
+    if (e.first == stream) return e.second;
+  return ActiveItems{nullptr, 0, 0};
+}
 
 static bool force_simt_gemm() {
   static int v = -1;
@@ -34,13 +45,20 @@ bool pdl_enabled() {
   return v == 1;
 }
 
+#ifdef EEC_EXPERIMENTS   // `make experiments` (eec/libeec_exp.so): the first-generation tcgen05 GEMM kept for A/B timing, EEC_GEMM_V1=1
 static bool gemm_v1() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("EEC_GEMM_V1"); v = (e && e[0] == '1') ? 1 : 0; }
   return v == 1;
 }
+#else
+static bool gemm_v1() { return false; }
+#endif
 static int tc_dispatch(const eec_gemm_desc* d, cudaStream_t st, int32_t* argmax, float* entropy, int logsoftmax) {
-  return gemm_v1() ? gemm_tc(d, st, argmax, entropy, logsoftmax) : gemm_tc2(d, st, argmax, entropy, logsoftmax);
+#ifdef EEC_EXPERIMENTS
+  if (gemm_v1()) return gemm_tc(d, st, argmax, entropy, logsoftmax);
+#endif
+  return gemm_tc2(d, st, argmax, entropy, logsoftmax);
 }
 
 // LayerNorm tails for the FFMA path (the tcgen05 path fuses them into the GEMM epilogue)
@@ -78,9 +96,16 @@ extern "C" int eec_device_ok(void) {
   return prop.major == 10 ? 1 : 0;
 }
 
-extern "C" int eec_set_active_items(const int32_t* n_items_dev, int rows_per_item, int pad_items) {
+extern "C" int eec_set_active_items(const int32_t* n_items_dev, int rows_per_item, int pad_items, eec_stream_t stream) {
   EEC_CHECK_ARG(n_items_dev == nullptr || (rows_per_item > 0 && pad_items >= 0), "set_active_items: rows_per_item must be positive and pad_items >= 0 (got %d, %d)", rows_per_item, pad_items);
-  g_active.n_dev = n_items_dev; g_active.rows_per_item = rows_per_item; g_active.pad_items = pad_items;
+  std::lock_guard<std::mutex> lk(g_active_mu);
+  for (size_t i = 0; i < g_active.size(); ++i)
+    if (g_active[i].first == S(stream)) {
+      if (n_items_dev) g_active[i].second = ActiveItems{n_items_dev, rows_per_item, pad_items};
+      else g_active.erase(g_active.begin() + i);
+      return 0;
+    }
+  if (n_items_dev) g_active.emplace_back(S(stream), ActiveItems{n_items_dev, rows_per_item, pad_items});
   return 0;
 }
 

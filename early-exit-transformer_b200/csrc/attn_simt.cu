@@ -287,9 +287,9 @@ extern "C" int eec_attn_fwd(const void* qkv, int dtype, const int32_t* key_len, 
   if (tc_path) return attn_fwd_tc(qkv, key_len, ctx, lse, B, T, H, dh, drop, S(stream));
   dim3 grid(cdiv(T, QB), H, B);
   if (dtype == EEC_F32)
-    attn_fwd_simt_kernel<float, true><<<grid, 128, 0, S(stream)>>>((const float*)qkv, key_len, (float*)ctx, lse, T, H, drop, active_items());
+    attn_fwd_simt_kernel<float, true><<<grid, 128, 0, S(stream)>>>((const float*)qkv, key_len, (float*)ctx, lse, T, H, drop, active_items(S(stream)));
   else
-    attn_fwd_simt_kernel<__nv_bfloat16, false><<<grid, 128, 0, S(stream)>>>((const __nv_bfloat16*)qkv, key_len, (__nv_bfloat16*)ctx, lse, T, H, drop, active_items());
+    attn_fwd_simt_kernel<__nv_bfloat16, false><<<grid, 128, 0, S(stream)>>>((const __nv_bfloat16*)qkv, key_len, (__nv_bfloat16*)ctx, lse, T, H, drop, active_items(S(stream)));
   EEC_LAUNCH_CHECK();
   return 0;
 }

@@ -460,217 +460,6 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_fwd_tcp_kernel(const __gri
 }
 
 
-// ---------------------------------------------------------------------------------------------------------------------
-// Eight softmax warps (EEC_ATTN_FWD8): the kernel above gives each query row ONE thread, so an SM runs 8 softmax warps (2 CTAs x 4)
-// and the softmax phase is latency-bound (tcgen05.ld, ex2, shared-memory stores back to back per row).  Here two threads share a row:
-// thread (quarter q, half h) owns keys [64h, 64h + 64) of the S tile and head-dim columns [16h, 16h + 16) of O.  The row maximum is
-// exchanged through shared memory (double-buffered slot + one 64-thread named barrier per block), each thread keeps a partial row sum
-// that is combined once at the end.  Same MMA / TMA warps, same barriers with doubled arrival counts.
-constexpr int AT8_THREADS = 320;
-constexpr int AT8_SMEM = AT_SMEM + 3 * 1024;
-
-template <bool DROP>
-__global__ void __launch_bounds__(AT8_THREADS, 2) attn_fwd_tc8_kernel(const __grid_constant__ CUtensorMap tm_qkv,
-                                                                   const int32_t* __restrict__ key_len,
-                                                                   __nv_bfloat16* __restrict__ ctx, float* __restrict__ lse,
-                                                                   int T, int H, const DropArgs drop, const ActiveItems act_items) {
-  pdl_trigger();
-  pdl_wait();
-  if (act_items.n_dev && (int)blockIdx.z >= active_count(act_items)) return;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;
-  uint8_t* sK = sQ + Q_BYTES;
-  uint8_t* sV = sK + KV_STAGES * K_BYTES;
-  uint8_t* sP = sV + KV_STAGES * V_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + P_BYTES);
-  uint64_t* q_full = bars;
-  uint64_t* kv_full = bars + 1;
-  uint64_t* kv_empty = bars + 3;
-  uint64_t* s_full = bars + 5;
-  uint64_t* s_free = bars + 6;
-  uint64_t* p_full = bars + 7;
-  uint64_t* o_full = bars + 8;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 9);
-  float* xch = reinterpret_cast<float*>(sP + P_BYTES + 256);     // [2 slots][2 halves][128 rows] row maxima, then [2][128] row sums
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * QT;
-  const int klen = min(key_len[b], T);
-  const int nblk = (klen + KB - 1) / KB;
-  const int D = H * DHEAD;
-  const int row0 = b * T;
-
-  if (threadIdx.x == 0) {
-    tma_prefetch_desc(&tm_qkv);
-    mbar_init(q_full, 1);
-    for (int s = 0; s < KV_STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
-    mbar_init(s_full, 1);
-    mbar_init(s_free, 256);
-    mbar_init(p_full, 256);
-    mbar_init(o_full, 1);
-    fence_barrier_init();
-  }
-  if (warp == 1) { tmem_alloc(tmem_ptr_smem, TMEM_COLS); tmem_relinquish(); }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr_smem;
-
-  if (warp == 0) {
-    if (lane == 0 && nblk > 0) {
-      mbar_expect_tx(q_full, Q_BYTES);
-      tma_load_2d(sQ, &tm_qkv, q_full, h * DHEAD, row0 + q0);
-      for (int j = 0; j < nblk; ++j) {
-        const int s = j % KV_STAGES;
-        mbar_wait(&kv_empty[s], ((j / KV_STAGES) & 1) ^ 1);
-        mbar_expect_tx(&kv_full[s], K_BYTES + V_BYTES);
-        tma_load_2d(sK + s * K_BYTES, &tm_qkv, &kv_full[s], D + h * DHEAD, row0 + j * KB);
-        tma_load_2d(sV + s * V_BYTES, &tm_qkv, &kv_full[s], 2 * D + h * DHEAD, row0 + j * KB);
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0 && nblk > 0) {
-      constexpr uint32_t idesc_s = make_idesc_bf16(QT, KB, false, false);
-      constexpr uint32_t idesc_o = make_idesc_bf16(QT, DHEAD, false, true);
-      mbar_wait(q_full, 0);
-      for (int j = 0; j < nblk; ++j) {
-        const int s = j % KV_STAGES;
-        mbar_wait(&kv_full[s], (j / KV_STAGES) & 1);
-        if (j > 0) mbar_wait(s_free, (j - 1) & 1);
-        tc_fence_after();
-        const uint32_t aq = smem_u32(sQ), bk = smem_u32(sK + s * K_BYTES), bv = smem_u32(sV + s * V_BYTES);
-#pragma unroll
-        for (int k = 0; k < DHEAD / 16; ++k)
-          umma_bf16(tmem_base + S_COL, make_smem_desc(aq + k * 32, 0, 512, SW64), make_smem_desc(bk + k * 32, 0, 512, SW64),
-                    idesc_s, k > 0 ? 1u : 0u);
-        umma_commit(s_full);
-        mbar_wait(p_full, j & 1);
-        tc_fence_after();
-        const uint32_t ap = smem_u32(sP);
-#pragma unroll
-        for (int k = 0; k < KB / 16; ++k)
-          umma_bf16(tmem_base + O_COL, make_smem_desc(ap + (k >> 2) * 16384 + (k & 3) * 32, 0, 1024, SW128),
-                    make_smem_desc(bv + k * 1024, 0, 512, SW64), idesc_o, k > 0 ? 1u : 0u);
-        umma_commit(o_full);
-        umma_commit(&kv_empty[s]);
-      }
-    }
-  } else {
-    const int q = warp & 3;                 // TMEM lane quarter of this warp
-    const int half = (warp - 2) >> 2;       // key half of the S tile / head-dim half of O
-    const int r = q * 32 + lane;
-    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
-    const float sc = rsqrtf((float)DHEAD) * 1.4426950408889634f;
-    float m_run = -INFINITY, l_run = 0.f;
-    float o[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) o[i] = 0.f;
-    float v[32];
-    const uint32_t* dbits = reinterpret_cast<const uint32_t*>(drop.bits);
-    const long drow = (long)(b * H + h) * T + (q0 + r), dR = (long)gridDim.z * H * T;
-    const bool dvalid = (q0 + r) < T;
-    const int kc0 = half * 64;
-    for (int j = 0; j < nblk; ++j) {
-      const int nvalid = min(KB, klen - j * KB);
-      const int nv = max(0, min(64, nvalid - kc0));          // valid keys among this thread's 64
-      uint32_t dword[2] = {0u, 0u};
-      if (DROP && dvalid) {
-#pragma unroll
-        for (int c = 0; c < 2; ++c)
-          if (c * 32 < nv) dword[c] = dbits[(long)((j * KB + kc0) / 32 + c) * dR + drow];
-      }
-      mbar_wait(s_full, j & 1);
-      tc_fence_after();
-      float mraw = -INFINITY;
-#pragma unroll 1
-      for (int c0 = 0; c0 < 64; c0 += 32) {
-        if (c0 >= nv) break;
-        tmem_ld32(trow + S_COL + kc0 + c0, v);
-        if (c0 + 32 <= nv) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) mraw = fmaxf(mraw, v[i]);
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (c0 + i < nv) mraw = fmaxf(mraw, v[i]);
-        }
-      }
-      float* slot = xch + (j & 1) * 256;                     // double-buffered: the slot of block j-2 is free (barrier of block j-1 passed)
-      slot[half * 128 + r] = mraw;
-      bar_sync(1 + q, 64);
-      mraw = fmaxf(mraw, slot[(half ^ 1) * 128 + r]);
-      const float mx = fmaxf(m_run, mraw * sc);              // (every block has at least one valid key: finite)
-      float psum = 0.f;
-#pragma unroll 1
-      for (int c0 = 0; c0 < 64; c0 += 32) {
-        if (c0 < nv) {
-          tmem_ld32(trow + S_COL + kc0 + c0, v);
-          if (c0 + 32 <= nv) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) { v[i] = ex2_fast(fmaf(v[i], sc, -mx)); psum += v[i]; }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) { v[i] = (c0 + i < nv) ? ex2_fast(fmaf(v[i], sc, -mx)) : 0.f; psum += v[i]; }
-          }
-          if (DROP) drop_apply_bits<32>(v, c0 == 0 ? dword[0] : dword[1], drop.scale);
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = 0.f;
-        }
-        uint8_t* prow = sP + half * 16384 + r * 128;
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const int chunk = (c0 >> 3) + g;
-          uint4 u;
-          __nv_bfloat162* hh = reinterpret_cast<__nv_bfloat162*>(&u);
-#pragma unroll
-          for (int e = 0; e < 4; ++e) hh[e] = __floats2bfloat162_rn(v[g * 8 + 2 * e], v[g * 8 + 2 * e + 1]);
-          *reinterpret_cast<uint4*>(prow + ((chunk ^ (r & 7)) << 4)) = u;
-        }
-      }
-      tc_fence_before();
-      mbar_arrive(s_free);
-      fence_proxy_async();
-      mbar_arrive(p_full);
-      const float corr = (m_run == -INFINITY) ? 0.f : ex2_fast(m_run - mx);
-      l_run = l_run * corr + psum;
-      m_run = mx;
-      mbar_wait(o_full, j & 1);
-      tc_fence_after();
-      uint32_t ro[16];
-      tmem_ld16_async(trow + O_COL + half * 16, ro);
-      tmem_ld_wait16(ro);
-#pragma unroll
-      for (int i = 0; i < 16; ++i) o[i] = fmaf(o[i], corr, __uint_as_float(ro[i]));
-    }
-    // combine the two partial row sums
-    float* xl = xch + 512;
-    xl[half * 128 + r] = l_run;
-    bar_sync(1 + q, 64);
-    const float l_tot = l_run + xl[(half ^ 1) * 128 + r];
-    const int t = q0 + r;
-    if (t < T) {
-      const float inv = (l_tot > 0.f) ? 1.0f / l_tot : 0.f;
-      __nv_bfloat16* dst = ctx + ((long)(row0 + t)) * D + h * DHEAD + half * 16;
-#pragma unroll
-      for (int g = 0; g < 2; ++g) {
-        float tt[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) tt[e] = o[g * 8 + e] * inv;
-        st8<__nv_bfloat16>(dst + g * 8, tt);
-      }
-      if (lse && half == 0) lse[((long)b * H + h) * T + t] = (l_tot > 0.f) ? (m_run + log2f(l_tot)) * 0.6931471805599453f : -INFINITY;
-    }
-    tc_fence_before();
-  }
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
-  }
-}
-
 }  // namespace
 
 int attn_fwd_tc(const void* qkv, const int32_t* key_len, void* ctx, float* lse, int B, int T, int H, int dh, const DropArgs& drop,
@@ -700,27 +489,13 @@ int attn_fwd_tc(const void* qkv, const int32_t* key_len, void* ctx, float* lse, 
     }
     const int items = cdiv(T, QT) * H * B;
     const dim3 pgrid(min(items, 2 * sms));
-    if (drop.state) launch_pdl(attn_fwd_tcp_kernel<true>, pgrid, dim3(AT_THREADS), AT_SMEM, st, tm, key_len, (__nv_bfloat16*)ctx, lse, T, H, B, drop, active_items());
-    else launch_pdl(attn_fwd_tcp_kernel<false>, pgrid, dim3(AT_THREADS), AT_SMEM, st, tm, key_len, (__nv_bfloat16*)ctx, lse, T, H, B, drop, active_items());
+    if (drop.state) launch_pdl(attn_fwd_tcp_kernel<true>, pgrid, dim3(AT_THREADS), AT_SMEM, st, tm, key_len, (__nv_bfloat16*)ctx, lse, T, H, B, drop, active_items(st));
+    else launch_pdl(attn_fwd_tcp_kernel<false>, pgrid, dim3(AT_THREADS), AT_SMEM, st, tm, key_len, (__nv_bfloat16*)ctx, lse, T, H, B, drop, active_items(st));
     EEC_LAUNCH_CHECK();
     return 0;
   }
-  static int fwd8 = -1;
-  if (fwd8 < 0) { const char* e = getenv("EEC_ATTN_FWD8"); fwd8 = (e && e[0] == '1') ? 1 : 0; }   // eight softmax warps (opt-in until measured)
-  if (fwd8) {
-    static bool attr8 = false;
-    if (!attr8) {
-      EEC_CUDA(cudaFuncSetAttribute(attn_fwd_tc8_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT8_SMEM));
-      EEC_CUDA(cudaFuncSetAttribute(attn_fwd_tc8_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT8_SMEM));
-      attr8 = true;
-    }
-    if (drop.state) launch_pdl(attn_fwd_tc8_kernel<true>, dim3(grid), dim3(AT8_THREADS), AT8_SMEM, st, tm, key_len, (__nv_bfloat16*)ctx, lse, T, H, drop, active_items());
-    else launch_pdl(attn_fwd_tc8_kernel<false>, dim3(grid), dim3(AT8_THREADS), AT8_SMEM, st, tm, key_len, (__nv_bfloat16*)ctx, lse, T, H, drop, active_items());
-    EEC_LAUNCH_CHECK();
-    return 0;
-  }
-  if (drop.state) launch_pdl(attn_fwd_tc_kernel<true>, dim3(grid), dim3(AT_THREADS), AT_SMEM, st, tm, key_len, (__nv_bfloat16*)ctx, lse, T, H, drop, active_items());
-  else launch_pdl(attn_fwd_tc_kernel<false>, dim3(grid), dim3(AT_THREADS), AT_SMEM, st, tm, key_len, (__nv_bfloat16*)ctx, lse, T, H, drop, active_items());
+  if (drop.state) launch_pdl(attn_fwd_tc_kernel<true>, dim3(grid), dim3(AT_THREADS), AT_SMEM, st, tm, key_len, (__nv_bfloat16*)ctx, lse, T, H, drop, active_items(st));
+  else launch_pdl(attn_fwd_tc_kernel<false>, dim3(grid), dim3(AT_THREADS), AT_SMEM, st, tm, key_len, (__nv_bfloat16*)ctx, lse, T, H, drop, active_items(st));
   EEC_LAUNCH_CHECK();
   return 0;
 }

@@ -191,7 +191,7 @@ static inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 // next utterance's rows (masked in the softmax, but 0 x NaN = NaN in P.V), so the rows right behind the last survivor must hold
 // finite numbers -- one padding utterance (T' >= 128 rows) of stale-but-finite data guarantees that.
 struct ActiveItems { const int32_t* n_dev; int rows_per_item; int pad_items; };
-ActiveItems active_items();
+ActiveItems active_items(cudaStream_t stream);   // the limit set for THIS stream (eec_set_active_items), or {nullptr, 0, 0}
 __device__ __forceinline__ int active_count(const ActiveItems& a) { return *a.n_dev + a.pad_items; }
 __device__ __forceinline__ int active_rows(const ActiveItems& a, int rows) {
   return a.n_dev ? min(rows, active_count(a) * a.rows_per_item) : rows;

@@ -104,102 +104,6 @@ __global__ void __launch_bounds__(256, 3) dwconv_kernel(const TI* __restrict__ g
 // Here every block walks tiles with a stride of gridDim.x and the cp.async copy of tile i+1 runs under the 992 FMAs per thread of
 // tile i; the depthwise weights stay in registers across tiles and the BatchNorm statistics of pass A are accumulated per thread
 // over all of a block's tiles (one pair of double atomics per thread instead of one per tile).
-// Packed variant: 128 threads, each owns a channel PAIR -- one 32-bit shared-memory load feeds both channels and the 31 x 32 multiply-
-// adds are FFMA2 (fp32x2, sm_100): half the FMA-pipe instructions per output.  (The 3-register FFMA issues every second cycle per
-// SMSP, which is what bounds this kernel; 64 accumulator + 62 weight registers per thread only pay off with the tile copy overlapped.)
-template <typename TO, int MODE>
-__global__ void __launch_bounds__(128, 3) dwconv_pipe2_kernel(const __nv_bfloat16* __restrict__ g, const float* __restrict__ w,
-                                                           const float* __restrict__ bias, const float* __restrict__ bn_w,
-                                                           const float* __restrict__ bn_b, const float* __restrict__ run_mean,
-                                                           const float* __restrict__ run_var, TO* __restrict__ out,
-                                                           double* __restrict__ sums, int B, int T, const ActiveItems act_items) {
-  pdl_trigger();
-  pdl_wait();
-  constexpr int C = 256, ROWS = TT + KW - 1, CPR = C * 2 / 16;
-  extern __shared__ __align__(16) uint8_t dw_smem[];
-  const int c0 = 2 * threadIdx.x;                            // channels c0, c0 + 1
-  const int nt = (T + TT - 1) / TT;
-  const int Beff = (MODE == DW_EVAL && act_items.n_dev) ? min(B, active_count(act_items)) : B;
-  const int tiles = nt * Beff;
-  float2 wr[KW];
-#pragma unroll
-  for (int j = 0; j < KW; ++j) wr[j] = make_float2(w[c0 * KW + j], w[(c0 + 1) * KW + j]);
-  const float2 bv = make_float2(bias[c0], bias[c0 + 1]);
-  float2 sc = make_float2(0.f, 0.f), sh = sc;
-  if (MODE == DW_EVAL) {
-    sc = make_float2(bn_w[c0] * rsqrtf(run_var[c0] + BN_EPS), bn_w[c0 + 1] * rsqrtf(run_var[c0 + 1] + BN_EPS));
-    sh = make_float2(bn_b[c0] - run_mean[c0] * sc.x, bn_b[c0 + 1] - run_mean[c0 + 1] * sc.y);
-  }
-  auto issue = [&](int tile, int buf) {
-    const int b = tile / nt, t_first = (tile - b * nt) * TT - HALF;
-    const __nv_bfloat16* src = g + (long)b * T * C;
-    uint8_t* base = dw_smem + buf * (ROWS * C * 2);
-    for (int i = threadIdx.x; i < ROWS * CPR; i += 128) {
-      const int r = i / CPR, c = i % CPR;
-      const int t = t_first + r;
-      uint8_t* dst = base + (size_t)i * 16;
-      if (t >= 0 && t < T) {
-        const uint8_t* sp = reinterpret_cast<const uint8_t*>(src + (long)t * C) + c * 16;
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(sp) : "memory");
-      } else {
-        *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
-      }
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-  };
-  float2 s1 = make_float2(0.f, 0.f), s2 = s1;
-  int tile = blockIdx.x, buf = 0;
-  if (tile < tiles) issue(tile, 0);
-  for (; tile < tiles; tile += gridDim.x, buf ^= 1) {
-    const int nxt = tile + gridDim.x;
-    if (nxt < tiles) {
-      issue(nxt, buf ^ 1);
-      asm volatile("cp.async.wait_group 1;" ::: "memory");
-    } else {
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
-    }
-    __syncthreads();
-    const __nv_bfloat162* tl = reinterpret_cast<const __nv_bfloat162*>(dw_smem + buf * (ROWS * C * 2));
-    float2 acc[TT];
-#pragma unroll
-    for (int t = 0; t < TT; ++t) acc[t] = bv;
-#pragma unroll
-    for (int r = 0; r < ROWS; ++r) {
-      const float2 x = __bfloat1622float2(tl[r * (C / 2) + threadIdx.x]);
-#pragma unroll
-      for (int t = 0; t < TT; ++t) {
-        const int j = r - t;
-        if (j >= 0 && j < KW) acc[t] = __ffma2_rn(wr[j], x, acc[t]);
-      }
-    }
-    const int b = tile / nt, t0 = (tile - b * nt) * TT;
-    TO* ob = out + (long)b * T * C + c0;
-    if (MODE == DW_EVAL) {
-#pragma unroll
-      for (int t = 0; t < TT; ++t)
-        if (t0 + t < T) {
-          const float2 n = __ffma2_rn(acc[t], sc, sh);
-          *reinterpret_cast<__nv_bfloat162*>(ob + (long)(t0 + t) * C) = __floats2bfloat162_rn(n.x * sigmoid_acc(n.x), n.y * sigmoid_acc(n.y));
-        }
-    } else {
-#pragma unroll
-      for (int t = 0; t < TT; ++t)
-        if (t0 + t < T) {
-          *reinterpret_cast<float2*>(ob + (long)(t0 + t) * C) = acc[t];
-          s1.x += acc[t].x; s1.y += acc[t].y;
-          s2 = __ffma2_rn(acc[t], acc[t], s2);
-        }
-    }
-    __syncthreads();
-  }
-  if (MODE == DW_STATS && blockIdx.x < tiles) {
-    atomicAdd(sums + c0, (double)s1.x);
-    atomicAdd(sums + c0 + 1, (double)s1.y);
-    atomicAdd(sums + C + c0, (double)s2.x);
-    atomicAdd(sums + C + c0 + 1, (double)s2.y);
-  }
-}
-
 template <typename TO, int MODE>
 __global__ void __launch_bounds__(256, 3) dwconv_pipe_kernel(const __nv_bfloat16* __restrict__ g, const float* __restrict__ w,
                                                           const float* __restrict__ bias, const float* __restrict__ bn_w,
@@ -413,13 +317,13 @@ __global__ void __launch_bounds__(SW_WARPS * 32, 3) bn_silu_train_kernel(const f
                                                             float* __restrict__ run_mean, float* __restrict__ run_var,
                                                             int64_t* __restrict__ nbt, float momentum,
                                                             float* __restrict__ save_mean, float* __restrict__ save_rstd,
-                                                            TO* __restrict__ out, int rows, int C) {
+                                                            TO* __restrict__ out, int rows, int C, long stat_rows) {
   pdl_trigger();
   pdl_wait();
   constexpr bool FAST = sizeof(TO) == 2;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ch0 = blockIdx.y * 256 + (warp & 1) * 128 + lane * CPL;
-  const double inv_n = 1.0 / (double)rows;
+  const double inv_n = 1.0 / (double)stat_rows;   // (data parallel with synchronised statistics: rows of ALL ranks)
   float sc[CPL], sh[CPL];
 #pragma unroll
   for (int k = 0; k < CPL; ++k) {
@@ -434,7 +338,7 @@ __global__ void __launch_bounds__(SW_WARPS * 32, 3) bn_silu_train_kernel(const f
       save_rstd[ch] = rstd;
       if (run_mean) {
         run_mean[ch] = (1.f - momentum) * run_mean[ch] + momentum * mean;
-        const double unb = (rows > 1) ? var_d * ((double)rows / ((double)rows - 1.0)) : var_d;
+        const double unb = (stat_rows > 1) ? var_d * ((double)stat_rows / ((double)stat_rows - 1.0)) : var_d;
         run_var[ch] = (1.f - momentum) * run_var[ch] + momentum * (float)unb;
         if (ch == 0 && nbt) *nbt += 1;
       }
@@ -466,7 +370,8 @@ __global__ void __launch_bounds__(SW_WARPS * 32, 3) bn_silu_bwd_kernel(const TI*
                                                           const float* __restrict__ save_mean, const float* __restrict__ save_rstd,
                                                           const float* __restrict__ bn_w, const float* __restrict__ bn_b,
                                                           double* __restrict__ sums2, float* __restrict__ dc,
-                                                          float* __restrict__ dgamma, float* __restrict__ dbeta, int rows, int C) {
+                                                          float* __restrict__ dgamma, float* __restrict__ dbeta, int rows, int C, long stat_rows,
+                                                          const double* __restrict__ sums2_local) {
   pdl_trigger();
   pdl_wait();
   constexpr bool FAST = sizeof(TI) == 2;
@@ -474,7 +379,7 @@ __global__ void __launch_bounds__(SW_WARPS * 32, 3) bn_silu_bwd_kernel(const TI*
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ch0 = blockIdx.y * 256 + (warp & 1) * 128 + lane * CPL;
   float a1[CPL], a0[CPL], gam[CPL], bet[CPL], m1[CPL], m2[CPL], s1[CPL], s2[CPL];   // nhat = c * a1 + a0
-  const float inv_n = 1.0f / (float)rows;
+  const float inv_n = 1.0f / (float)stat_rows;
 #pragma unroll
   for (int k = 0; k < CPL; ++k) {
     const int ch = ch0 + k;
@@ -487,8 +392,9 @@ __global__ void __launch_bounds__(SW_WARPS * 32, 3) bn_silu_bwd_kernel(const TI*
       m1[k] = t1 * inv_n;
       m2[k] = t2 * inv_n;
       if (blockIdx.x == 0 && warp < 2) {   // warps 0 and 1 cover the two channel halves
-        atomicAdd(dbeta + ch, t1);
-        atomicAdd(dgamma + ch, t2);
+        // synchronised statistics: the parameter gradients are THIS rank's sums (the gradient all-reduce averages them)
+        atomicAdd(dbeta + ch, sums2_local ? (float)sums2_local[ch] : t1);
+        atomicAdd(dgamma + ch, sums2_local ? (float)sums2_local[C + ch] : t2);
       }
     }
   }
@@ -592,7 +498,7 @@ static int stream_grid(int rows) {
 
 static int dw_pipe_mode() {
   static int v = -1;
-  if (v < 0) { const char* e = getenv("EEC_DW_PIPE"); v = e ? atoi(e) : 1; }   // 0: one tile per block; 1: pipelined; 2: pipelined + FFMA2 channel pairs (opt-in until verified on the GPU)
+  if (v < 0) { const char* e = getenv("EEC_DW_PIPE"); v = e ? atoi(e) : 1; }   // 0: one tile per block; 1 (default): persistent, double-buffered tiles
   return v;
 }
 static bool dw_pipe_enabled() { return dw_pipe_mode() != 0; }
@@ -612,19 +518,8 @@ static int dw_pipe_launch(const __nv_bfloat16* g, const float* w, const float* b
   }
   const int tiles = cdiv(T, TT) * B;
   if (tiles == 0) return 0;
-  if (dw_pipe_mode() == 2) {
-    static bool attr2 = false;
-    if (!attr2) {
-      EEC_CUDA(cudaFuncSetAttribute(dwconv_pipe2_kernel<TO, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-      attr2 = true;
-    }
-    launch_pdl(dwconv_pipe2_kernel<TO, MODE>, dim3(min(tiles, sms * 3)), dim3(128), SMEM, st, g, w, bias, bn_w, bn_b, run_mean, run_var, out, sums, B, T,
-               active_items());
-    EEC_LAUNCH_CHECK();
-    return 0;
-  }
   launch_pdl(dwconv_pipe_kernel<TO, MODE>, dim3(min(tiles, sms * 3)), dim3(256), SMEM, st, g, w, bias, bn_w, bn_b, run_mean, run_var, out, sums, B, T,
-             active_items());
+             active_items(st));
   EEC_LAUNCH_CHECK();
   return 0;
 }
@@ -644,9 +539,9 @@ extern "C" int eec_dwconv_bn_silu_eval(const void* g, int dtype, const float* w,
     return 0;
   }
   if (dtype == EEC_F32)
-    EEC_DW_LAUNCH((dwconv_kernel<float, float, DW_EVAL>), float, (const float*)g, w, bias, bn_w, bn_b, run_mean, run_var, (float*)out, nullptr, T, C, active_items());
+    EEC_DW_LAUNCH((dwconv_kernel<float, float, DW_EVAL>), float, (const float*)g, w, bias, bn_w, bn_b, run_mean, run_var, (float*)out, nullptr, T, C, active_items(S(stream)));
   else
-    EEC_DW_LAUNCH((dwconv_kernel<__nv_bfloat16, __nv_bfloat16, DW_EVAL>), __nv_bfloat16, (const __nv_bfloat16*)g, w, bias, bn_w, bn_b, run_mean, run_var, (__nv_bfloat16*)out, nullptr, T, C, active_items());
+    EEC_DW_LAUNCH((dwconv_kernel<__nv_bfloat16, __nv_bfloat16, DW_EVAL>), __nv_bfloat16, (const __nv_bfloat16*)g, w, bias, bn_w, bn_b, run_mean, run_var, (__nv_bfloat16*)out, nullptr, T, C, active_items(S(stream)));
   EEC_LAUNCH_CHECK();
   return 0;
 }
@@ -669,14 +564,15 @@ extern "C" int eec_dwconv_stats(const void* g, int dtype, const float* w, const 
 extern "C" int eec_bn_silu_train(const float* c, const double* sums, const float* bn_w, const float* bn_b,
                                  float* run_mean, float* run_var, int64_t* num_batches_tracked, float momentum,
                                  float* save_mean, float* save_rstd, void* out, int dtype, int rows, int C,
-                                 eec_stream_t stream) {
+                                 int64_t stat_rows, eec_stream_t stream) {
   EEC_CHECK_ARG(C % 256 == 0, "bn_silu_train: C %% 256");
   if (rows == 0) return 0;
+  const long sr = stat_rows > 0 ? (long)stat_rows : (long)rows;
   dim3 grid(stream_grid(rows), C / 256);
   if (dtype == EEC_F32)
-    launch_pdl(bn_silu_train_kernel<float>, dim3(grid), dim3(SW_WARPS * 32), 0, S(stream), c, sums, bn_w, bn_b, run_mean, run_var, num_batches_tracked, momentum, save_mean, save_rstd, (float*)out, rows, C);
+    launch_pdl(bn_silu_train_kernel<float>, dim3(grid), dim3(SW_WARPS * 32), 0, S(stream), c, sums, bn_w, bn_b, run_mean, run_var, num_batches_tracked, momentum, save_mean, save_rstd, (float*)out, rows, C, sr);
   else
-    launch_pdl(bn_silu_train_kernel<__nv_bfloat16>, dim3(grid), dim3(SW_WARPS * 32), 0, S(stream), c, sums, bn_w, bn_b, run_mean, run_var, num_batches_tracked, momentum, save_mean, save_rstd, (__nv_bfloat16*)out, rows, C);
+    launch_pdl(bn_silu_train_kernel<__nv_bfloat16>, dim3(grid), dim3(SW_WARPS * 32), 0, S(stream), c, sums, bn_w, bn_b, run_mean, run_var, num_batches_tracked, momentum, save_mean, save_rstd, (__nv_bfloat16*)out, rows, C, sr);
   EEC_LAUNCH_CHECK();
   return 0;
 }
@@ -688,23 +584,25 @@ extern "C" int eec_bn_silu_bwd_stats(const void* ds, int dtype, const float* c, 
   if (rows == 0) return 0;
   dim3 grid(stream_grid(rows), C / 256);
   if (dtype == EEC_F32)
-    launch_pdl(bn_silu_bwd_kernel<float, false>, dim3(grid), dim3(SW_WARPS * 32), 0, S(stream), (const float*)ds, c, save_mean, save_rstd, bn_w, bn_b, sums2, nullptr, nullptr, nullptr, rows, C);
+    launch_pdl(bn_silu_bwd_kernel<float, false>, dim3(grid), dim3(SW_WARPS * 32), 0, S(stream), (const float*)ds, c, save_mean, save_rstd, bn_w, bn_b, sums2, nullptr, nullptr, nullptr, rows, C, (long)rows, nullptr);
   else
-    launch_pdl(bn_silu_bwd_kernel<__nv_bfloat16, false>, dim3(grid), dim3(SW_WARPS * 32), 0, S(stream), (const __nv_bfloat16*)ds, c, save_mean, save_rstd, bn_w, bn_b, sums2, nullptr, nullptr, nullptr, rows, C);
+    launch_pdl(bn_silu_bwd_kernel<__nv_bfloat16, false>, dim3(grid), dim3(SW_WARPS * 32), 0, S(stream), (const __nv_bfloat16*)ds, c, save_mean, save_rstd, bn_w, bn_b, sums2, nullptr, nullptr, nullptr, rows, C, (long)rows, nullptr);
   EEC_LAUNCH_CHECK();
   return 0;
 }
 
 extern "C" int eec_bn_silu_bwd_apply(const void* ds, int dtype, const float* c, const float* save_mean,
                                      const float* save_rstd, const float* bn_w, const float* bn_b, const double* sums2,
-                                     float* dc, float* dgamma, float* dbeta, int rows, int C, eec_stream_t stream) {
+                                     float* dc, float* dgamma, float* dbeta, int rows, int C, int64_t stat_rows,
+                                     const double* sums2_local, eec_stream_t stream) {
   EEC_CHECK_ARG(C % 256 == 0, "bn_silu_bwd_apply: C %% 256");
   if (rows == 0) return 0;
+  const long sr = stat_rows > 0 ? (long)stat_rows : (long)rows;
   dim3 grid(stream_grid(rows), C / 256);
   if (dtype == EEC_F32)
-    launch_pdl(bn_silu_bwd_kernel<float, true>, dim3(grid), dim3(SW_WARPS * 32), 0, S(stream), (const float*)ds, c, save_mean, save_rstd, bn_w, bn_b, const_cast<double*>(sums2), dc, dgamma, dbeta, rows, C);
+    launch_pdl(bn_silu_bwd_kernel<float, true>, dim3(grid), dim3(SW_WARPS * 32), 0, S(stream), (const float*)ds, c, save_mean, save_rstd, bn_w, bn_b, const_cast<double*>(sums2), dc, dgamma, dbeta, rows, C, sr, sums2_local);
   else
-    launch_pdl(bn_silu_bwd_kernel<__nv_bfloat16, true>, dim3(grid), dim3(SW_WARPS * 32), 0, S(stream), (const __nv_bfloat16*)ds, c, save_mean, save_rstd, bn_w, bn_b, const_cast<double*>(sums2), dc, dgamma, dbeta, rows, C);
+    launch_pdl(bn_silu_bwd_kernel<__nv_bfloat16, true>, dim3(grid), dim3(SW_WARPS * 32), 0, S(stream), (const __nv_bfloat16*)ds, c, save_mean, save_rstd, bn_w, bn_b, const_cast<double*>(sums2), dc, dgamma, dbeta, rows, C, sr, sums2_local);
   EEC_LAUNCH_CHECK();
   return 0;
 }

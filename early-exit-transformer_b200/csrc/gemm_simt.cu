@@ -160,7 +160,7 @@ int gemm_simt(const eec_gemm_desc* d, cudaStream_t st) {
   if (p.act == EEC_ACT_DSILU) EEC_CHECK_ARG(d->preact != nullptr, "gemm: DSILU needs preact");
   if (d->accumulate) EEC_CHECK_ARG(d->out_dtype == EEC_F32, "gemm: accumulate needs fp32 C");
   p.drop = make_drop(d->drop_state, d->drop_p, d->drop_site);
-  p.act_items = d->a_kmajor ? active_items() : ActiveItems{nullptr, 0, 0};   // (rows of A are frames only in the K-major forward form)
+  p.act_items = d->a_kmajor ? active_items(st) : ActiveItems{nullptr, 0, 0};   // (rows of A are frames only in the K-major forward form)
   if (p.drop.state) EEC_CHECK_ARG(!glu && !d->accumulate && d->N % 8 == 0, "gemm(simt): dropout with GLU / accumulate / N %% 8 != 0 unsupported");
   int tiles = cdiv(p.N, BN) * cdiv(p.M, BM);
   int splits = 1;

@@ -963,7 +963,7 @@ int gemm_tc3(const eec_gemm_desc* d, cudaStream_t st) {
   EEC_CHECK_ARG(!d->a_colsum || (!d->a_kmajor && !d->b_kmajor && !d->bias && epi == EPI_GENERIC),
                 "gemm_tc3: a_colsum needs the weight-gradient form (MN-major A and B, no bias)");
   p.a_colsum = d->a_colsum; p.a_colsum_scale = d->a_colsum_scale;
-  p.act_items = (d->a_kmajor && !d->accumulate) ? active_items() : ActiveItems{nullptr, 0, 0};   // forward form only: rows of A are frames
+  p.act_items = (d->a_kmajor && !d->accumulate) ? active_items(st) : ActiveItems{nullptr, 0, 0};   // forward form only: rows of A are frames
   p.drop = make_drop(d->drop_state, d->drop_p, d->drop_site);
   p.drop.bits = d->drop_bits;
   if (p.drop.state) {
@@ -1049,7 +1049,7 @@ int gemm_ln3(const eec_gemm_desc* d, cudaStream_t st) {
   p.drop.bits = d->drop_bits;
   if (p.drop.state)
     EEC_CHECK_ARG(d->drop_bits != nullptr, "gemm (LayerNorm tail): dropout needs the keep-mask words of eec_dropout_bits(R = M, C = 256, Cs = 256, W = 32) in drop_bits");
-  p.act_items = active_items();
+  p.act_items = active_items(st);
   static bool attr_set = false;
   if (!attr_set) {
     EEC_CUDA(cudaFuncSetAttribute(gemm_ln3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, LN_SMEM_BYTES));

@@ -485,9 +485,9 @@ extern "C" int eec_layernorm_fwd(const float* x, const float* gamma, const float
   if (rows == 0) return 0;
   int blocks = cdiv(rows, 8);
   if (out_dtype == EEC_F32)
-    launch_pdl(layernorm_fwd_kernel<float>, dim3(blocks), dim3(256), 0, S(stream), x, gamma, beta, (float*)out, mean, rstd, rows, active_items());
+    launch_pdl(layernorm_fwd_kernel<float>, dim3(blocks), dim3(256), 0, S(stream), x, gamma, beta, (float*)out, mean, rstd, rows, active_items(S(stream)));
   else
-    launch_pdl(layernorm_fwd_kernel<__nv_bfloat16>, dim3(blocks), dim3(256), 0, S(stream), x, gamma, beta, (__nv_bfloat16*)out, mean, rstd, rows, active_items());
+    launch_pdl(layernorm_fwd_kernel<__nv_bfloat16>, dim3(blocks), dim3(256), 0, S(stream), x, gamma, beta, (__nv_bfloat16*)out, mean, rstd, rows, active_items(S(stream)));
   EEC_LAUNCH_CHECK();
   return 0;
 }

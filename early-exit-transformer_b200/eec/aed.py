@@ -102,8 +102,9 @@ class full_conformer(_EarlyExitBase):
         return _EncoderFn.apply(self, want_tape, cfg, True, src, lengths, *params)
 
     def _encoder_(self, src: Tensor, lengths: Tensor, layer_n: int) -> Tensor:
-        """early_exit.py:719-737: encoder state after exit group `layer_n` (1-based; groups past the last one clamp)."""
-        n = max(1, min(int(layer_n), self.n_enc_exits))
+        """early_exit.py:719-737: encoder state after exit group `layer_n` (1-based).  The reference's loop only breaks when its counter
+        EQUALS layer_n, so layer_n <= 0 or > n_enc_exits runs ALL groups."""
+        n = int(layer_n) if 1 <= int(layer_n) <= self.n_enc_exits else self.n_enc_exits
         _, hidden = self._encode(src, lengths, n)
         return hidden[n - 1]
 
@@ -114,7 +115,7 @@ class full_conformer(_EarlyExitBase):
         tgt_key_padding_mask = self.create_pad_mask(trg, self.trg_pad_idx).to(dev)
         trg = self.emb(trg)
         trg = self._pos2(trg)
-        i = max(1, min(int(layer_n), self.n_enc_exits)) - 1
+        i = (int(layer_n) if 1 <= int(layer_n) <= self.n_enc_exits else self.n_enc_exits) - 1   # (:751-755: same loop quirk)
         out_d = self.decoders[i](trg, enc, tgt_mask=tgt_mask, tgt_key_padding_mask=tgt_key_padding_mask)
         return torch.nn.functional.log_softmax(self.linears_2[i](out_d), dim=2)
 

@@ -11,7 +11,7 @@ from __future__ import annotations
 import torch
 
 from . import ops
-from .lib import EecError
+from .lib import EecError, on_device
 
 
 class _CtcFn(torch.autograd.Function):
@@ -25,7 +25,8 @@ class _CtcFn(torch.autograd.Function):
         loss = torch.zeros(E, dtype=torch.float32, device=dev)
         need_grad = ctx.needs_input_grad[0]
         grad = torch.empty_like(lp_ebtv) if need_grad else None
-        ops.ctc_fwd_bwd(lp_ebtv, tg, tl, nll, loss, grad, 1.0, blank)
+        with on_device(dev):
+            ops.ctc_fwd_bwd(lp_ebtv, tg, tl, nll, loss, grad, 1.0, blank)
         ctx.grad = grad
         ctx.nll = nll
         return loss
@@ -36,7 +37,8 @@ class _CtcFn(torch.autograd.Function):
         if g is None:
             raise EecError("ctc: gradient was not computed in forward")
         gl = gloss.contiguous().float()
-        ops.scale_rows_dev(g, gl, g)   # every exit's slab times its upstream scalar, on device, one launch
+        with on_device(g.device):
+            ops.scale_rows_dev(g, gl, g)   # every exit's slab times its upstream scalar, on device, one launch
         ctx.grad = None
         from . import engine
         engine.mark_logit_grad(g)      # rows sum to zero: the encoder's backward may skip the log-softmax backward for this tensor

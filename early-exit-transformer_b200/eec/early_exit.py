@@ -21,7 +21,7 @@ import torch
 from torch import nn
 
 from . import engine, ops
-from .lib import EecError
+from .lib import EecError, on_device
 
 Tensor = torch.Tensor
 
@@ -122,8 +122,10 @@ class _EncoderFn(torch.autograd.Function):
             # ran in between; the module's counter moves on (on device: a graph replay draws new masks every step)
             st = module._dropout_state(src.device)
             drop_state = st.clone()
-            ops.dropout_advance(st)
-        out, tape = engine.model_forward(P, module._operands, cfg, src, lengths, module.training, want_tape, side, drop_state)
+            with on_device(src.device):
+                ops.dropout_advance(st)
+        with on_device(src.device):     # kernels launch on the current stream of the TENSORS' device (no global set_device needed)
+            out, tape = engine.model_forward(P, module._operands, cfg, src, lengths, module.training, want_tape, side, drop_state)
         ctx.module, ctx.tape, ctx.P, ctx.cfg, ctx.want_hidden = module, tape, P, cfg, want_hidden
         return (out, side["hidden"]) if want_hidden else out
 
@@ -135,11 +137,12 @@ class _EncoderFn(torch.autograd.Function):
                                       "(eval-mode BatchNorm backward is not implemented)")
         names = m._param_names
         red = m.__dict__.get("_grad_reducer")     # eec.distributed.OverlappedGradReducer: per-exit-group all-reduce during backward
-        G = engine.model_backward(ctx.P, m._operands, ctx.cfg, ctx.tape, gout, names,
-                                  ghid.contiguous() if ctx.want_hidden and ghid is not None else None,
-                                  on_ready=red.on_ready if red is not None else None)
-        if red is not None:
-            red.finish()
+        with on_device(gout.device):
+            G = engine.model_backward(ctx.P, m._operands, ctx.cfg, ctx.tape, gout, names,
+                                      ghid.contiguous() if ctx.want_hidden and ghid is not None else None,
+                                      on_ready=red.on_ready if red is not None else None)
+            if red is not None:
+                red.finish()
         ctx.tape = None
         m.__dict__["_flat_grad"] = G["__flat__"]  # p.grad tensors are views of this buffer (DP all-reduces it once)
         return (None, None, None, None, None, None) + tuple(G[n] for n in names)
@@ -191,8 +194,10 @@ class _EarlyExitBase(nn.Module):
             raise EecError(f"precision must be 'fp32' or 'bf16', got {self.precision!r}")
 
     def _cfg(self) -> engine.Config:
+        bs = self.__dict__.get("_bn_sync")      # eec.distributed.sync_batchnorm(model)
         return engine.Config(n_exits=self.n_enc_exits, n_layers=self.num_layers, n_mels=self._features_length,
-                             splitformer=self._splitformer, precision=self.precision, drop_p=float(self.dropout))
+                             splitformer=self._splitformer, precision=self.precision, drop_p=float(self.dropout),
+                             bn_sync=bs[0] if bs else None, bn_world=bs[1] if bs else 1)
 
     # -- dropout (train mode, drop_prob > 0): counter-based masks, include/eec.h "dropout".  PyTorch's RNG streams cannot be
     #    matched; the seed follows torch's global seed at first use, so torch.manual_seed(s) before training
@@ -255,7 +260,8 @@ class _EarlyExitBase(nn.Module):
         self._check_supported()
         if self.training:
             raise EecError("forward_early_exit is an inference API: call model.eval() first")
-        return early_exit_infer.run(self, src, lengths, threshold)
+        with on_device(src.device):
+            return early_exit_infer.run(self, src, lengths, threshold)
 
 
 class Early_conformer(_EarlyExitBase):
@@ -288,8 +294,9 @@ def greedy_decode(log_probs: Tensor, blank: int = 0):
     dev = lp.device
     am = torch.empty(Bx * T, dtype=torch.int32, device=dev)
     scratch = torch.empty_like(lp)
-    ops.call("eec_logsoftmax_fwd", ops.ptr(lp), ops.ptr(scratch), ops.ptr(am), None, Bx * T, Vv, ops.stream())
     tokens = torch.empty(Bx, T, dtype=torch.int32, device=dev)
     n_tok = torch.empty(Bx, dtype=torch.int32, device=dev)
-    ops.greedy_collapse(am, tokens, n_tok, Bx, T, blank)
+    with on_device(dev):
+        ops.call("eec_logsoftmax_fwd", ops.ptr(lp), ops.ptr(scratch), ops.ptr(am), None, Bx * T, Vv, ops.stream())
+        ops.greedy_collapse(am, tokens, n_tok, Bx, T, blank)
     return tokens.view(*shp[:-2], T), n_tok.view(*shp[:-2])

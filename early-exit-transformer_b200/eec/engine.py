@@ -37,6 +37,14 @@ class Config:
     splitformer: bool = False
     precision: str = "fp32"   # "fp32" (FFMA parity path) or "bf16" (tcgen05 path)
     drop_p: float = 0.0       # train-mode dropout probability (the reference's --drop_prob; applied when a drop state is passed)
+    bn_sync: Optional[object] = None   # data parallel with synchronised BatchNorm (eec.distributed.sync_batchnorm): callable that
+    bn_world: int = 1                  #   SUM-all-reduces a double tensor in place over bn_world ranks of equal batch shape
+    total_exits: int = 0      # exits of the FULL model when n_exits is a truncation (Splitformer: the parallel branches sit at group 0 and
+                              # at the full model's last group, early_exit.py:314 / :340); 0 = n_exits
+
+    @property
+    def last_exit(self) -> int:
+        return (self.total_exits or self.n_exits) - 1
 
     @property
     def act_dtype(self):
@@ -310,10 +318,13 @@ def layer_forward(P: Dict[str, Tensor], W: Operands, pre: str, x: Tensor, key_le
         cbuf = _empty((N, D), f32, dev)
         sums = torch.zeros(2 * D, dtype=torch.float64, device=dev)
         ops.dwconv_stats(g, wdw, P[c + "sequential.2.bias"], cbuf, sums, B, T, KW)
+        if cfg.bn_sync is not None:
+            cfg.bn_sync(sums)          # per-channel sum / sum of squares over the GLOBAL batch (TA:59 BatchNorm1d under sync-BN)
         sm, sr = _empty((D,), f32, dev), _empty((D,), f32, dev)
         ops.bn_silu_train(cbuf, sums, P[c + "sequential.3.weight"], P[c + "sequential.3.bias"],
                           P[c + "sequential.3.running_mean"], P[c + "sequential.3.running_var"],
-                          P[c + "sequential.3.num_batches_tracked"], BN_MOMENTUM, sm, sr, s)
+                          P[c + "sequential.3.num_batches_tracked"], BN_MOMENTUM, sm, sr, s,
+                          stat_rows=N * cfg.bn_world if cfg.bn_sync is not None else 0)
     else:
         ops.dwconv_bn_silu_eval(g, wdw, P[c + "sequential.2.bias"], P[c + "sequential.3.weight"], P[c + "sequential.3.bias"],
                                 P[c + "sequential.3.running_mean"], P[c + "sequential.3.running_var"], s, B, T, KW)
@@ -389,7 +400,7 @@ def layer_backward(P, W: Operands, G: Dict[str, Tensor], pre: str, t: dict, dY: 
     dc = _empty((N, D), f32, dev)
     sums2 = torch.zeros(2 * D, dtype=torch.float64, device=dev)
     ops.bn_silu_bwd(ds, t["c"], t["sm"], t["sr"], P[c + "sequential.3.weight"], P[c + "sequential.3.bias"], sums2, dc,
-                    G[c + "sequential.3.weight"], G[c + "sequential.3.bias"])
+                    G[c + "sequential.3.weight"], G[c + "sequential.3.bias"], sync=cfg.bn_sync, world=cfg.bn_world)
     dg = _empty((N, D), TD, dev)
     wdw = P[c + "sequential.2.weight"].detach().reshape(D, KW)
     ops.dwconv_bwd(dc, t["g"], wdw, dg, G[c + "sequential.2.weight"].view(D, KW), G[c + "sequential.2.bias"], B, T, KW)
@@ -524,8 +535,8 @@ def model_forward(P: Dict[str, Tensor], W: Operands, cfg: Config, src: Tensor, l
         order = []
         for e in range(cfg.n_exits):
             order += [(e * cfg.n_layers + l, src.shape[0], Tp) for l in range(cfg.n_layers)]
-            if cfg.splitformer and (e == 0 or e == cfg.n_exits - 1):
-                order.append((1000 + e // (cfg.n_exits - 1), src.shape[0], (Tp + 1) // 2))
+            if cfg.splitformer and (e == 0 or e == cfg.last_exit):
+                order.append((1000 + e // cfg.last_exit, src.shape[0], (Tp + 1) // 2))
         plan = MaskPlan(drop0, order)
 
     x, T = frontend_forward(P, W, src, cfg, tape.front if tape else None, drop0)
@@ -553,10 +564,10 @@ def model_forward(P: Dict[str, Tensor], W: Operands, cfg: Config, src: Tensor, l
             if tape:
                 tape.layers.append(lt)
         br = None
-        if cfg.splitformer and (e == 0 or e == E - 1):
+        if cfg.splitformer and (e == 0 or e == cfg.last_exit):
             # early_exit.py:314-356: parallel stride-2 branch on the group's INPUT; its key mask uses the RAW
             # fbank lengths (reference quirk) -> clamp((lengths+pad)/2, max=T2)
-            i = e // (E - 1)
+            i = e // cfg.last_exit     # (a 1-exit Splitformer divides by zero here exactly like the reference, early_exit.py:316)
             T2 = (T + 1) // 2
             pad = T % 2
             xd = _empty((B * T2, D), f32, dev)

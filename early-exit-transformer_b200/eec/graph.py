@@ -26,7 +26,7 @@ import torch
 
 from . import engine
 from .ctc import multi_exit_ctc_loss
-from .lib import EecError, load
+from .lib import EecError, on_device, load
 
 
 class GraphedTrainStep:
@@ -55,6 +55,13 @@ class GraphedTrainStep:
         self.t_out = ((t_in - 3) // 2 + 1 - 3) // 2 + 1
 
         lib = load()
+        self._uploaded = None            # event after the last H2D copy out of the pinned staging buffers
+        # warm-up and capture run the step on the all-zero static input: they must leave NO trace in the model -- the BatchNorm
+        # running statistics / num_batches_tracked and the dropout counter are put back afterwards (the weights do not move:
+        # the optimiser is left out of the warm-up, and the captured graph is not executed by the capture)
+        saved = {n: b.detach().clone() for n, b in model.named_buffers()}
+        drop_state = model.__dict__.get("_drop_state")
+        saved_drop = drop_state.clone() if drop_state is not None else None
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):   # eager warm-up off the default stream (lazy module loads, kernel attributes, tensor maps)
@@ -62,6 +69,14 @@ class GraphedTrainStep:
                 self._eager_step(with_optimizer=False)   # (warm-up must not move the weights)
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
+        with torch.no_grad():
+            for n, b in model.named_buffers():
+                b.copy_(saved[n])
+            if model.__dict__.get("_drop_state") is not None:
+                if saved_drop is not None:
+                    model.__dict__["_drop_state"].copy_(saved_drop)
+                else:
+                    model.__dict__["_drop_state"][1] = 0
         # parameter casts must be IN the graph: drop the operand cache so capture re-issues them
         model._operands._cache.clear()
         model.zero_grad(set_to_none=True)
@@ -90,11 +105,38 @@ class GraphedTrainStep:
             raise EecError("GraphedTrainStep: batch / target shape does not fit the captured step")
         if not lengths.is_cuda:
             engine.check_lengths(lengths, self.t_out)   # the reference's AssertionError, raised on the host before any launch
+        # the pinned staging buffers are single: a previous call's asynchronous H2D copy may still be queued behind an earlier
+        # replay, so wait for it before the host overwrites them (otherwise that step would train on a torn / future batch)
+        self._wait_uploaded()
         if src.is_cuda:
             self.src.copy_(src, non_blocking=True)
         else:
             self._pin_src.copy_(src)
             self.src.copy_(self._pin_src, non_blocking=True)
+        self._load_small(lengths, targets, target_lengths)
+        self._mark_uploaded()
+
+    def _wait_uploaded(self) -> None:
+        if self._uploaded is not None:
+            self._uploaded.synchronize()
+
+    def _mark_uploaded(self) -> None:
+        if self._uploaded is None:
+            self._uploaded = torch.cuda.Event()
+        self._uploaded.record(torch.cuda.current_stream(self.src.device))
+
+    def load_small(self, lengths: torch.Tensor, targets: torch.Tensor, target_lengths: torch.Tensor) -> None:
+        """Upload only the step's integer tensors (lengths, targets, target lengths) -- the features come through prefetch()."""
+        if targets.shape[0] != self.B or targets.shape[1] > self.L or lengths.numel() != self.B or target_lengths.numel() != self.B:
+            raise EecError("GraphedTrainStep: batch / target shape does not fit the captured step")
+        if not lengths.is_cuda:
+            engine.check_lengths(lengths, self.t_out)
+        self._wait_uploaded()
+        self._load_small(lengths, targets, target_lengths)
+        self._mark_uploaded()
+
+    def _load_small(self, lengths, targets, target_lengths) -> None:
+        B, L = self.B, self.L
         if lengths.is_cuda or targets.is_cuda or target_lengths.is_cuda:
             self.lengths.copy_(lengths, non_blocking=True)
             self.targets.fill_(self.pad_token)
@@ -168,8 +210,10 @@ class GraphedForward:
         dev = params[0].device
         self.model = model
         full = model._cfg()
+        # a truncated Splitformer keeps the parallel branch of group 0 (early_exit.py:314-356 applies it whatever follows); only the
+        # last group's branch disappears with the last group: total_exits tells the engine where "last" is
         self.cfg = engine.Config(n_exits=n_exits or full.n_exits, n_layers=full.n_layers, n_mels=full.n_mels,
-                                 splitformer=full.splitformer and (n_exits in (None, full.n_exits)), precision=full.precision)
+                                 splitformer=full.splitformer, precision=full.precision, total_exits=full.n_exits)
         n_mels = n_mels if n_mels is not None else model._features_length
         self.src = torch.zeros(batch_size, n_mels, t_in, dtype=torch.float32, device=dev)
         self.lengths = torch.full((batch_size,), t_in, dtype=torch.int64, device=dev)
@@ -191,7 +235,8 @@ class GraphedForward:
 
     def _run(self):
         m = self.model
-        out, _ = engine.model_forward(m._tensor_dict(), m._operands, self.cfg, self.src, self.lengths, False, False)
+        with on_device(self.src.device):
+            out, _ = engine.model_forward(m._tensor_dict(), m._operands, self.cfg, self.src, self.lengths, False, False)
         return out
 
     def replay(self) -> torch.Tensor:
@@ -233,7 +278,9 @@ class GraphedEarlyExit:
         self.lengths = torch.full((batch_size,), t_in, dtype=torch.int64, device=dev)
         self._pin_len = torch.empty(batch_size, dtype=torch.int64).pin_memory()
         self.t_out = ((t_in - 3) // 2 + 1 - 3) // 2 + 1
-        run = lambda: early_exit_infer.run(model, self.src, self.lengths, self.threshold)   # noqa: E731
+        def run():
+            with on_device(dev):
+                return early_exit_infer.run(model, self.src, self.lengths, self.threshold)
         lib = load()
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))

@@ -46,7 +46,6 @@ class GemmDesc(C.Structure):
 # name -> argtypes (stream last); every function returns int unless noted
 _SIGS = {
     "eec_gemm": [C.POINTER(GemmDesc), vp],
-    "eec_ffn_fwd": [vp, vp, vp, vp, vp, vp, f32, vp, vp, vp, vp, i32, vp, vp, vp, i32, i32, i32, vp],
     "eec_layernorm_fwd": [vp, vp, vp, vp, i32, vp, vp, i32, i32, vp],
     "eec_layernorm_bwd": [vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, i32, vp, f32, vp, f32, u32, i32, i32, vp],
     "eec_attn_fwd": [vp, i32, vp, vp, vp, i32, i32, i32, i32, vp, f32, u32, vp, vp],
@@ -56,9 +55,9 @@ _SIGS = {
     "eec_dropout_advance": [vp, vp],
     "eec_dwconv_bn_silu_eval": [vp, i32, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp],
     "eec_dwconv_stats": [vp, i32, vp, vp, vp, vp, i32, i32, i32, i32, vp],
-    "eec_bn_silu_train": [vp, vp, vp, vp, vp, vp, vp, f32, vp, vp, vp, i32, i32, i32, vp],
+    "eec_bn_silu_train": [vp, vp, vp, vp, vp, vp, vp, f32, vp, vp, vp, i32, i32, i32, i64, vp],
     "eec_bn_silu_bwd_stats": [vp, i32, vp, vp, vp, vp, vp, vp, i32, i32, vp],
-    "eec_bn_silu_bwd_apply": [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, vp],
+    "eec_bn_silu_bwd_apply": [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i64, vp, vp],
     "eec_dwconv_bwd": [vp, vp, i32, vp, vp, vp, vp, i32, i32, i32, i32, vp, vp],
     "eec_glu_bwd": [vp, vp, vp, i32, i32, i32, vp],
     "eec_logsoftmax_fwd": [vp, vp, vp, vp, i32, i32, vp],
@@ -78,7 +77,7 @@ _SIGS = {
     "eec_scale_rows_dev": [vp, vp, vp, i32, i64, vp],
     "eec_exit_select": [vp, vp, vp, vp, vp, i32, i32, f32, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp],
     "eec_gather_rows": [vp, vp, vp, vp, i32, i64, vp],
-    "eec_set_active_items": [vp, i32, i32],
+    "eec_set_active_items": [vp, i32, i32, vp],
     "eec_fbank_frames": [vp, vp, i64, vp, vp, i32, i32, i32, i32, vp],
     "eec_fbank_power": [vp, i32, vp, i64, i32, i32, vp],
     "eec_fbank_finish": [vp, i32, vp, i32, i32, i32, vp],
@@ -91,6 +90,11 @@ _SIGS = {
 }
 EXPORTS = sorted(list(_SIGS) + ["eec_last_error", "eec_version", "eec_device_ok", "eec_ctc_workspace_bytes", "eec_dwconv_bwd_workspace_bytes",
                              "eec_launch_count"])
+
+# entry points of eec/libeec_exp.so only (`make experiments`, include/eec_experiments.h): bound when the loaded library has them
+_SIGS_EXPERIMENTAL = {
+    "eec_ffn_fwd": [vp, vp, vp, vp, vp, vp, f32, vp, vp, vp, vp, i32, vp, vp, vp, i32, i32, i32, vp],
+}
 
 _lib = None
 
@@ -114,6 +118,11 @@ def load():
         fn = getattr(lib, name)
         fn.argtypes = args
         fn.restype = i32
+    for name, args in _SIGS_EXPERIMENTAL.items():
+        fn = getattr(lib, name, None)
+        if fn is not None:
+            fn.argtypes = args
+            fn.restype = i32
     lib.eec_last_error.restype = C.c_char_p
     lib.eec_last_error.argtypes = []
     lib.eec_version.restype = i32
@@ -130,7 +139,10 @@ def load():
 
 def call(name: str, *args):
     lib = load()
-    rc = getattr(lib, name)(*args)
+    fn = getattr(lib, name, None)
+    if fn is None:
+        raise EecError(f"{name} is not in {LIB_PATH} (experimental entry points: make -C early-exit-transformer_b200 experiments; EEC_LIB=eec/libeec_exp.so)")
+    rc = fn(*args)
     if rc != 0:
         raise EecError(f"{name} failed ({rc}): {lib.eec_last_error().decode()}")
 
@@ -143,7 +155,18 @@ def ptr(t):
 
 
 def stream():
+    """torch's current stream of the CURRENT device.  Every tensor handed to a kernel must live on that device: `call` is always
+    reached through a model / op whose entry point has switched to the tensors' device (eec.early_exit._on_device), so a model on
+    cuda:1 works without a global torch.cuda.set_device(1)."""
     return torch.cuda.current_stream().cuda_stream
+
+
+def on_device(dev):
+    """Context: make `dev` torch's current CUDA device (so `stream()` is the stream of the tensors' device); a CPU device passes through
+    -- the entry point it guards raises the "no CPU path" error itself."""
+    import contextlib
+    dev = torch.device(dev)
+    return torch.cuda.device(dev) if dev.type == "cuda" else contextlib.nullcontext()
 
 
 def dt(t: torch.Tensor) -> int:

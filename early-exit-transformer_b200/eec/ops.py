@@ -107,7 +107,7 @@ def gemm(
 
 
 def ffn_fwd(u, w1, b1, w2, b2, residual, alpha, ln_gamma, ln_beta, x_out, ln_out, ln_mean=None, ln_rstd=None, hpre=None):
-    """Fused feed-forward module + following LayerNorm (include/eec.h::eec_ffn_fwd); bf16 operands."""
+    """Fused feed-forward module + following LayerNorm (include/eec_experiments.h::eec_ffn_fwd, libeec_exp.so only); bf16 operands."""
     for t, n in ((u, "u"), (w1, "w1"), (w2, "w2"), (residual, "residual"), (x_out, "x_out"), (ln_out, "ln_out")):
         _chk(t, "ffn_fwd." + n)
     rows, f = u.numel() // 256, w1.shape[0]
@@ -175,18 +175,23 @@ def dwconv_stats(g, w, bias, c, sums, B, T, K):
     call("eec_dwconv_stats", ptr(g), dt(g), ptr(w), ptr(bias), ptr(c), ptr(sums), B, T, 256, K, stream())
 
 
-def bn_silu_train(c, sums, bn_w, bn_b, rm, rv, nbt, momentum, save_mean, save_rstd, out):
+def bn_silu_train(c, sums, bn_w, bn_b, rm, rv, nbt, momentum, save_mean, save_rstd, out, stat_rows=0):
     rows = c.numel() // 256
     call("eec_bn_silu_train", ptr(c), ptr(sums), ptr(bn_w), ptr(bn_b), ptr(rm), ptr(rv), ptr(nbt), momentum, ptr(save_mean),
-         ptr(save_rstd), ptr(out), dt(out), rows, 256, stream())
+         ptr(save_rstd), ptr(out), dt(out), rows, 256, stat_rows, stream())
 
 
-def bn_silu_bwd(ds, c, save_mean, save_rstd, bn_w, bn_b, sums2, dc, dgamma, dbeta):
+def bn_silu_bwd(ds, c, save_mean, save_rstd, bn_w, bn_b, sums2, dc, dgamma, dbeta, sync=None, world=1):
+    """sync (optional): in-place SUM all-reduce of a double tensor over the data-parallel ranks (synchronised BatchNorm)"""
     rows = c.numel() // 256
     call("eec_bn_silu_bwd_stats", ptr(ds), dt(ds), ptr(c), ptr(save_mean), ptr(save_rstd), ptr(bn_w), ptr(bn_b), ptr(sums2),
          rows, 256, stream())
+    local = None
+    if sync is not None:
+        local = sums2.clone()
+        sync(sums2)
     call("eec_bn_silu_bwd_apply", ptr(ds), dt(ds), ptr(c), ptr(save_mean), ptr(save_rstd), ptr(bn_w), ptr(bn_b), ptr(sums2),
-         ptr(dc), ptr(dgamma), ptr(dbeta), rows, 256, stream())
+         ptr(dc), ptr(dgamma), ptr(dbeta), rows, 256, rows * world if sync is not None else 0, ptr(local), stream())
 
 
 def dwconv_bwd(dc, g, w, dg, dw, dbias, B, T, K):
@@ -273,8 +278,8 @@ def gather_rows(x, y, gather_idx, n_alive, B, row_elems):
 
 
 def set_active_items(n_items_dev, rows_per_item: int = 0, pad_items: int = 0):
-    """Limit the inference kernels launched by this thread to the first *n_items_dev (+ pad_items) utterances (None clears)."""
-    call("eec_set_active_items", ptr(n_items_dev), int(rows_per_item), int(pad_items))
+    """Limit the inference kernels launched on the current stream to the first *n_items_dev (+ pad_items) utterances (None clears)."""
+    call("eec_set_active_items", ptr(n_items_dev), int(rows_per_item), int(pad_items), stream())
 
 
 def gather_i64(src, idx, dst):

@@ -20,7 +20,7 @@ from typing import Dict
 import torch
 
 from . import ops
-from .lib import EecError
+from .lib import EecError, on_device
 
 
 class FusedNoamAdamW:
@@ -53,9 +53,11 @@ class FusedNoamAdamW:
         self.exp_avg_sq = torch.zeros_like(self.flat_p)
         self.state = torch.zeros(4, dtype=torch.float64, device=dev)   # step, sum g^2, lr, clip coefficient
         self.shadow = torch.empty(self.total, dtype=torch.bfloat16, device=dev)
-        ops.cast(self.flat_p, self.shadow)
+        with on_device(self.flat_p.device):
+            ops.cast(self.flat_p, self.shadow)
         self._versions = {n: p._version for n, p in params}
         self._attach()
+        model.__dict__["_fused_optimizer"] = self     # (eec.distributed.broadcast_parameters refreshes the shadow through this)
 
     def _attach(self):
         ob = self.model._operands
@@ -70,9 +72,10 @@ class FusedNoamAdamW:
             raise EecError("FusedNoamAdamW.step: gradients are not in the engine's flat buffer (run loss.backward() on an eec model first)")
         if first.data_ptr() != self.flat_p.data_ptr():
             raise EecError("FusedNoamAdamW.step: parameters were re-allocated (model.to()/load with assign=True?) after the optimiser was built")
-        ops.call("eec_noam_adamw_step", ops.ptr(self.flat_p), ops.ptr(flat_g), ops.ptr(self.exp_avg), ops.ptr(self.exp_avg_sq),
-                 ops.ptr(self.shadow), self.total, ops.ptr(self.state), self.model_size, self.warmup, float(self.betas[0]),
-                 float(self.betas[1]), self.eps, self.weight_decay, self.clip, -1.0 if self.lr is None else float(self.lr), ops.stream())
+        with on_device(self.flat_p.device):
+            ops.call("eec_noam_adamw_step", ops.ptr(self.flat_p), ops.ptr(flat_g), ops.ptr(self.exp_avg), ops.ptr(self.exp_avg_sq),
+                     ops.ptr(self.shadow), self.total, ops.ptr(self.state), self.model_size, self.warmup, float(self.betas[0]),
+                     float(self.betas[1]), self.eps, self.weight_decay, self.clip, -1.0 if self.lr is None else float(self.lr), ops.stream())
         ob = m._operands
         if ob._shadow is not self.shadow:
             self._attach()          # precision switch rebuilt the operand cache
@@ -97,18 +100,34 @@ class FusedNoamAdamW:
         return float(self.state[1].item()) ** 0.5
 
     def state_dict(self):
-        return {"step": self._step, "exp_avg": self.exp_avg.clone(), "exp_avg_sq": self.exp_avg_sq.clone(), "warmup": self.warmup,
-                "model_size": self.model_size}
+        """A superset of the reference's NoamOpt.state_dict() (util/noam_opt.py:12-17: every attribute but the wrapped optimiser, i.e.
+        `_step`, `warmup`, `model_size`, `_rate`), so a file written here loads into the reference's NoamOpt (`__dict__.update`, :19-25:
+        the extra keys are inert attributes there), plus the Adam moments the reference never saves (train.py:122-125 stores the model
+        and this scheduler state only, so a resumed reference run restarts its moments at zero)."""
+        step = self._step
+        return {"_step": step, "warmup": self.warmup, "model_size": self.model_size, "_rate": self.rate(step),
+                "step": step, "exp_avg": self.exp_avg.clone(), "exp_avg_sq": self.exp_avg_sq.clone()}
 
     def load_state_dict(self, sd):
+        """Accepts this class's files and the reference's `lr###-transformer` NoamOpt state (`_step`, `warmup`, `model_size`, `_rate`);
+        moments missing from the file start at zero, which is exactly what the reference does on resume."""
+        step = sd["_step"] if "_step" in sd else sd["step"]
         self.state.zero_()
-        self.state[0] = float(sd["step"])
-        self.exp_avg.copy_(sd["exp_avg"])
-        self.exp_avg_sq.copy_(sd["exp_avg_sq"])
+        self.state[0] = float(step)
+        if "warmup" in sd:
+            self.warmup = float(sd["warmup"])
+        if "model_size" in sd:
+            self.model_size = float(sd["model_size"])
+        for name, buf in (("exp_avg", self.exp_avg), ("exp_avg_sq", self.exp_avg_sq)):
+            if sd.get(name) is not None:
+                buf.copy_(sd[name])
+            else:
+                buf.zero_()
 
     def refresh_shadow(self) -> None:
         """Call after writing parameters behind the optimiser's back (e.g. load_state_dict into the model)."""
-        ops.cast(self.flat_p, self.shadow)
+        with on_device(self.flat_p.device):
+            ops.cast(self.flat_p, self.shadow)
         self._versions = {n: p._version for n, p in self.model.named_parameters()}
         self._attach()
         self.model._operands.invalidate()

@@ -108,17 +108,6 @@ int eec_dropout_bits(const uint64_t* state, float p, uint32_t site, int64_t R, i
 /* state[1] += 1 (one launch; lives inside the captured training step) */
 int eec_dropout_advance(uint64_t* state, eec_stream_t stream);
 
-/* ---- fused feed-forward module (TA:91-119 + half-step residual TA:185-187, 207-209 + the LayerNorm that follows:
- *      TA:151 self_attn_layer_norm after ffn1, TA:211 final_layer_norm after ffn2).  bf16 operands only (tcgen05):
- *        x_out  = residual + alpha * ( SiLU(u W1^T + b1) W2^T + b2 )          fp32 [rows, 256]
- *        ln_out = LayerNorm(x_out; ln_gamma, ln_beta)                          bf16|fp32 [rows, 256], eps 1e-5
- *      u [rows,256] bf16 = LayerNorm output feeding the module; w1 [f,256], w2 [256,f] bf16 (nn.Linear layout);
- *      hpre (optional, bf16 [rows,f]) receives u W1^T + b1 for the backward pass; the [rows,f] activation itself
- *      never leaves the SM.  ln_mean / ln_rstd optional.  d must be 256, f a multiple of 128. */
-int eec_ffn_fwd(const void* u, const void* w1, const float* b1, const void* w2, const float* b2, const float* residual,
-                float alpha, const float* ln_gamma, const float* ln_beta, float* x_out, void* ln_out, int ln_dtype,
-                float* ln_mean, float* ln_rstd, void* hpre, int rows, int d, int f, eec_stream_t stream);
-
 /* ---- LayerNorm (TA:103,151,42,211) ------------------------------------------------- */
 int eec_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* out, int out_dtype,
                       float* mean, float* rstd, int rows, int d, eec_stream_t stream);
@@ -163,6 +152,8 @@ int eec_dwconv_stats(const void* g, int dtype, const float* w, const float* bias
 int eec_bn_silu_train(const float* c, const double* sums, const float* bn_w, const float* bn_b,
                       float* run_mean, float* run_var, int64_t* num_batches_tracked, float momentum,
                       float* save_mean, float* save_rstd, void* out, int dtype, int rows, int C,
+                      int64_t stat_rows /* 0 = rows; data parallel with synchronised statistics: `sums` was all-reduced (SUM)
+                                           over the ranks and stat_rows is the row count of ALL ranks */,
                       eec_stream_t stream);
 /* backward of train-mode BN+SiLU+dwconv.  Step 1: dn = ds*silu'(n); sums2 = {sum dn, sum dn*nhat}.
  * Step 2: dc = gamma*rstd*(dn - mean(dn) - nhat*mean(dn*nhat)); dgamma/dbeta accumulate.
@@ -173,6 +164,9 @@ int eec_bn_silu_bwd_stats(const void* ds, int dtype, const float* c, const float
 int eec_bn_silu_bwd_apply(const void* ds, int dtype, const float* c, const float* save_mean,
                           const float* save_rstd, const float* bn_w, const float* bn_b,
                           const double* sums2, float* dc, float* dgamma, float* dbeta, int rows, int C,
+                          int64_t stat_rows /* 0 = rows */,
+                          const double* sums2_local /* NULL, or (synchronised statistics) this rank's own sums for dgamma / dbeta
+                                                       while `sums2` holds the all-reduced ones */,
                           eec_stream_t stream);
 /* workspace: eec_dwconv_bwd_workspace_bytes(B, T, C) bytes of device memory (per-block partial weight gradients: the kernel
  * writes them without atomics and a second launch reduces them into dw / dbias, both accumulated) */
@@ -262,16 +256,19 @@ int eec_exit_select(const float* entropy, const int32_t* argmax, const int32_t* 
                     int blank, eec_stream_t stream);
 int eec_gather_rows(const float* x, float* y, const int32_t* gather_idx, const int32_t* n_alive,
                     int B, int64_t row_elems, eec_stream_t stream);
-/* Active-item limit of the calling thread: while n_items_dev != NULL, the forward (inference) forms of eec_gemm (K-major A),
- * eec_layernorm_fwd, eec_attn_fwd and eec_dwconv_bn_silu_eval process only the first *n_items_dev utterances, i.e. the leading
+/* Active-item limit of ONE STREAM (the handle is the stream the caller already passes to every entry point, so two models or two
+ * streams in one process never see each other's limit): while n_items_dev != NULL, the forward (inference) forms of eec_gemm (K-major A),
+ * eec_layernorm_fwd, eec_attn_fwd and eec_dwconv_bn_silu_eval launched on that stream process only the first *n_items_dev utterances, i.e. the leading
  * *n_items_dev * rows_per_item rows of every frame-major tensor; tiles / rows / utterance blocks past the limit return at once,
  * so compaction after an exit actually removes the finished utterances' work from the later layers.  The count is read ON THE
  * DEVICE at kernel start (eec_exit_select keeps it current): no host sync, and a captured CUDA graph stays valid when it changes.
  * pad_items further utterances behind the count are processed as well: the tensor-core attention loads 128-row K/V tiles that
  * overhang into the following utterance (masked in the softmax, but 0 x NaN = NaN in P.V), so the rows right behind the last
  * survivor must be finite; the caller keeps one utterance of stale-but-finite data there (pad_items = 1 when T' >= 128).
+ * The limit is looked up on the host when a kernel is LAUNCHED on `stream`: it applies to the launches (or graph-captured launches)
+ * issued on that stream between the set and the clear.
  * Rows past the limit are left untouched (their contents are unspecified).  Pass NULL to clear. */
-int eec_set_active_items(const int32_t* n_items_dev, int rows_per_item, int pad_items);
+int eec_set_active_items(const int32_t* n_items_dev, int rows_per_item, int pad_items, eec_stream_t stream);
 /* dst[i] = src[idx[i]], i < n (idx clamped to [0, n)): the raw lengths of the surviving utterances in compacted order (Splitformer's
  * parallel branch masks with the RAW fbank lengths, early_exit.py:332-338) */
 int eec_gather_i64(const int64_t* src, const int32_t* idx, int64_t* dst, int n, eec_stream_t stream);

@@ -1,0 +1,117 @@
+"""Parity of the BENCHMARKED models: the 12-layer / 6-exit BASELINE early_conformer (configs[1]; fp32 and bf16) and the
+18-layer / 6-exit data-parallel model (configs[2]; bf16), at the benchmark's utterance length (T_in = 1501 -> T' = 374),
+against the CPU oracle run live in this process (ragged lengths with lengths[0] == T_in).
+
+Asserted at the north star's tolerances (fp32 1e-3, bf16 2e-2 relative = maxabs(a-b)/maxabs(b), stated per exit): train-mode
+log-probabilities of every exit, the summed 6-exit CTC loss (train.py:53-65), every parameter-gradient norm, the eval-mode
+log-probabilities and -- fp32 -- bit-exact greedy CTC tokens.  A failure names the first exit (= the layer pair) at which the
+drift crosses the bar, with the whole per-exit error profile.  B = 8 keeps the oracle's forward + backward at a few seconds."""
+import functools
+
+import pytest
+import torch
+
+from oracle import conformer_oracle as O
+
+pytestmark = pytest.mark.gpu
+TOL = {"fp32": 1e-3, "bf16": 2e-2}
+GTOL = {"fp32": 5e-3, "bf16": 6e-2}     # per-tensor gradient norms (same bars as tests/test_gpu_model.py)
+B, T_IN, N_EXITS = 8, 1501, 6
+
+
+def rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def rel_l2(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+@functools.lru_cache(maxsize=None)
+def oracle_case(layers_per_exit: int):
+    """(sd, inputs, oracle train log-probs, loss, gradient norms, eval log-probs) -- computed once per model depth"""
+    torch.set_num_threads(max(torch.get_num_threads(), 8))
+    sd = O.make_params(100 + layers_per_exit, n_exits=N_EXITS, n_layers=layers_per_exit)
+    src, lengths = O.synthetic_batch(B, T_IN, seed=200 + layers_per_exit)       # lengths[0] == T_in
+    targets, tl = O.synthetic_targets(B, seed=300 + layers_per_exit, lo=20, hi=80)
+    leaf = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k and k != "positional_encoder.pe" else v.clone())
+            for k, v in sd.items()}
+    out = O.early_conformer_forward(leaf, src, lengths, training=True, bn_out={})
+    in_len = torch.full((B,), out.shape[2], dtype=torch.long)
+    loss = sum(torch.nn.functional.ctc_loss(out[e].permute(1, 0, 2), targets, in_len, tl, blank=0, zero_infinity=True)
+               for e in range(N_EXITS))
+    loss.backward()
+    gnorm = {k: float(v.grad.double().norm()) for k, v in leaf.items() if v.requires_grad and v.grad is not None}
+    with torch.no_grad():
+        ev = O.early_conformer_forward(sd, src, lengths)
+    return sd, src, lengths, targets, tl, out.detach(), float(loss.detach()), gnorm, ev
+
+
+def build(sd, layers_per_exit, precision):
+    import eec
+    m = eec.Early_conformer(src_pad_idx=0, n_enc_exits=N_EXITS, enc_voc_size=256, dec_voc_size=256, d_model=256, n_head=8,
+                            max_len=2000, d_feed_forward=2048, n_enc_layers=layers_per_exit, features_length=80, drop_prob=0.0,
+                            depthwise_kernel_size=31, device=torch.device("cuda"))
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda()
+    m.precision = precision
+    return m
+
+
+def exit_profile(out, ref):
+    return [(e, round(rel(out[e], ref[e]), 6), round(rel_l2(out[e], ref[e]), 6)) for e in range(ref.shape[0])]
+
+
+def check_exits(out, ref, tol, layers_per_exit, what):
+    prof = exit_profile(out, ref)
+    for e, r, _ in prof:
+        assert r < tol, (f"{what}: drift crosses {tol} at exit {e} (after layer {(e + 1) * layers_per_exit}); "
+                         f"per-exit (exit, maxabs-rel, l2-rel) = {prof}")
+    return prof
+
+
+@pytest.mark.parametrize("layers_per_exit,precision", [(2, "fp32"), (2, "bf16"), (3, "bf16")])
+def test_headline_model_vs_live_oracle(layers_per_exit, precision):
+    import eec
+    sd, src, lengths, targets, tl, ref_train, ref_loss, ref_gn, ref_eval = oracle_case(layers_per_exit)
+    assert int(lengths[0]) == T_IN and int(lengths.min()) < T_IN
+    tol, gtol = TOL[precision], GTOL[precision]
+
+    # ---- train mode (batch-statistics BatchNorm), the benchmarked step: log-probs of every exit, loss, all gradient norms
+    m = build(sd, layers_per_exit, precision).train()
+    out = m(src.cuda(), lengths)
+    assert out.shape == (N_EXITS, B, 374, 256)
+    prof = check_exits(out.detach(), ref_train, tol, layers_per_exit, f"train log-probs [{precision}, {N_EXITS}x{layers_per_exit}]")
+    loss = eec.multi_exit_ctc_loss(out, targets, tl)
+    lerr = abs(float(loss) - ref_loss) / abs(ref_loss)
+    assert lerr < tol, (float(loss), ref_loss, lerr)
+    loss.backward()
+    gmax = max(ref_gn.values())
+    worst = ("", 0.0)
+    n_checked = 0
+    for n, p in m.named_parameters():
+        if n not in ref_gn:
+            continue
+        got = float(p.grad.double().norm())
+        err = abs(got - ref_gn[n]) / max(ref_gn[n], 1e-3 * gmax)
+        if err > worst[1]:
+            worst = (n, err)
+        n_checked += 1
+    assert n_checked == len(list(m.parameters())), (n_checked, len(ref_gn))
+    assert worst[1] < gtol, f"gradient norm of {worst[0]} off by {worst[1]:.3e} (bar {gtol})"
+    print(f"[{precision} {N_EXITS}x{layers_per_exit}] train per-exit (exit, maxabs-rel, l2-rel): {prof}; loss rel {lerr:.2e}; "
+          f"worst grad-norm rel {worst[1]:.2e} ({worst[0]})")
+
+    # ---- eval mode (running-statistics BatchNorm): what inference.py runs
+    m.eval()
+    with torch.no_grad():
+        ev = m(src.cuda(), lengths)
+    check_exits(ev, ref_eval, tol, layers_per_exit, f"eval log-probs [{precision}, {N_EXITS}x{layers_per_exit}]")
+    if precision == "fp32":
+        tokens, n_tok = eec.greedy_decode(ev)
+        tokens, n_tok = tokens.cpu(), n_tok.cpu()
+        for e in range(N_EXITS):
+            for b in range(B):
+                assert tokens[e, b, : int(n_tok[e, b])].tolist() == O.greedy_ctc(ref_eval[e, b]), (e, b)   # bit-exact (north star)

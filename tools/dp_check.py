@@ -7,7 +7,11 @@ Every rank runs the same weights on its own synthetic batch and computes the ave
   (a) eager backward, then ONE all-reduce of the flat gradient buffer (eec.distributed.all_reduce_gradients);
   (b) eager backward with eec.distributed.OverlappedGradReducer (per-exit-group all-reduce on a side stream during backward);
   (c) the same as (b) captured into the training CUDA graph (GraphedTrainStep) and replayed twice.
-(b) and (c) must equal (a) up to the summation order of the atomics inside backward.  Prints PASS / FAIL on rank 0."""
+(b) and (c) must equal (a) up to the summation order of the atomics inside backward.
+Then the SEMANTIC check: with eec.distributed.sync_batchnorm(model) the N-rank step on N shards of a batch must equal the
+1-rank step on the concatenated batch -- loss, every averaged gradient, BatchNorm running statistics -- in fp32 (tight) and bf16,
+eagerly and as one graph replay; without synchronised BatchNorm the same comparison must FAIL to agree (the check has teeth), and
+sync_bn_buffers() must leave identical running statistics on every rank.  Prints PASS / FAIL on rank 0."""
 import os
 import sys
 
@@ -71,12 +75,73 @@ def main():
         print(f"dp_check world={world}: |overlapped-eager - flat|/max = {float(t[0]):.2e}, |overlapped-graph - flat|/max = {float(t[1]):.2e}, "
               f"averaging changed the local buffer by {float(t[2]):.2e}, rank agreement {agree:.1e}, slices per backward {calls_eager}, "
               f"loss {float(la):.4f}/{float(lb):.4f}, launches in graph {step.launches_per_step}: {'PASS' if ok else 'FAIL'}", flush=True)
+    red.remove(model)
+    ok = bool(ok) and sync_bn_check(rank, world, dev)
     # (a captured graph that holds NCCL kernels must be released before the communicator goes away)
     del step
     torch.cuda.synchronize()
     dist.barrier()
     sys.stdout.flush()
     os._exit(0 if ok else 1)
+
+
+def sync_bn_check(rank, world, dev):
+    import bench
+    import eec
+    Bn, layers = 4, 2
+    results = []
+    bench.T_IN = 403
+    full = bench.synthetic_batch(Bn * world, 4242)            # the GLOBAL batch, identical on every rank; rank r owns rows [r*Bn, (r+1)*Bn)
+    for r in range(world):
+        full[1][r * Bn] = bench.T_IN                          # the reference's precondition max(lengths)//4 >= T' holds per model call
+    lo = rank * Bn
+    mine = [t[lo:lo + Bn].contiguous() for t in full]
+    for precision, tol in (("fp32", 2e-4), ("bf16", 3e-2)):
+        def run(shard, sync, graph=False):
+            """-> (loss, flat averaged gradient, running_mean of the first BatchNorm) of one step from the initial weights"""
+            bench.B = shard[0].shape[0]
+            m = bench.build_model(layers, precision, dev).train()
+            src, lengths, targets, tl = shard
+            if sync is not None:
+                eec.distributed.sync_batchnorm(m, sync)
+                eec.distributed.OverlappedGradReducer(m)
+            if graph:
+                st = eec.GraphedTrainStep(m, src.shape[0], src.shape[2], targets.shape[1])
+                loss = st(src, lengths, targets, tl).clone()
+            else:
+                out = m(src.to(dev), lengths)
+                loss = eec.multi_exit_ctc_loss(out, targets.to(dev), tl.to(dev))
+                loss.backward()
+            torch.cuda.synchronize()
+            bn = dict(m.named_buffers())["conformer.1.conformer_layers.0.conv_module.sequential.3.running_mean"].clone()
+            res = float(loss), m._flat_grad.clone(), bn, m
+            if graph:
+                del st
+            return res
+        l1, g1, bn1, _ = run(full, None)                                   # 1 rank, concatenated batch
+        lN, gN, bnN, mN = run(mine, True)                                  # N ranks, synchronised BatchNorm, eager
+        lG, gG, bnG, _ = run(mine, True, graph=True)                       # ... as one graph replay
+        lU, gU, bnU, mU = run(mine, False)                                 # N ranks, per-rank BatchNorm statistics
+        lsum = torch.tensor([lN, lG], device=dev, dtype=torch.float64)
+        dist.all_reduce(lsum)                                              # global loss = mean over ranks of the local means (equal shard sizes)
+        scale = float(g1.abs().max())
+        e_sync, e_graph, e_unsync = (float((g - g1).abs().max()) / scale for g in (gN, gG, gU))
+        e_loss = abs(float(lsum[0]) / world - l1) / abs(l1)
+        e_bn = float((bnN - bn1).abs().max()) / float(bn1.abs().max())
+        eec.distributed.sync_bn_buffers(mU)
+        bn_avg = dict(mU.named_buffers())["conformer.1.conformer_layers.0.conv_module.sequential.3.running_mean"]
+        same = bn_avg.clone()
+        dist.all_reduce(same, op=dist.ReduceOp.MAX)
+        e_buf = float((same - bn_avg).abs().max())
+        t = torch.tensor([e_sync, e_graph, e_loss, e_bn, e_buf, -e_unsync], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ok = bool(t[0] < tol and t[1] < tol and t[2] < tol and t[3] < tol and t[4] == 0.0 and (-t[5] > 5 * tol or precision == "bf16"))
+        results.append(ok)
+        if rank == 0:
+            print(f"dp_check sync-BN [{precision}] world={world}: N-rank vs 1-rank on the concatenated batch: grad {float(t[0]):.2e} (graph {float(t[1]):.2e}), "
+                  f"loss {float(t[2]):.2e}, BN running_mean {float(t[3]):.2e} (bar {tol}); without sync-BN the gradients differ by {float(-t[5]):.2e}; "
+                  f"sync_bn_buffers rank spread {float(t[4]):.1e}: {'PASS' if ok else 'FAIL'}", flush=True)
+    return all(results)
 
 
 if __name__ == "__main__":
