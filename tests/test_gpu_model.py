@@ -538,3 +538,87 @@ def test_edge_shapes_one_model_many_batches(precision):
                 err = abs(p.grad.double().norm().item() - sdg[n].grad.norm().item()) / max(sdg[n].grad.norm().item(), 1e-3 * gmax)
                 assert err < gt, (Bn, t_in, n, err)
         m.load_state_dict({**m.state_dict(), **running})     # keep the BatchNorm running stats of `sd` for the next eval comparison
+
+
+def test_optimizer_state_interchanges_with_reference_noamopt():
+    """FusedNoamAdamW.state_dict() is a superset of the reference's NoamOpt.state_dict() (util/noam_opt.py:12-17:
+    `_step`, `warmup`, `model_size`, `_rate`), and load_state_dict() accepts a reference `lr###-transformer` state (no Adam moments:
+    they restart at zero, as in the reference, train.py:122-125 never saves them)."""
+    import eec
+    name = "ec_e2l1_b3_t163"
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    m, sd, src, lengths = build(name, g, "bf16")
+    m.train()
+    targets, tl = O.synthetic_targets(src.shape[0], seed=31, lo=3, hi=6)
+    opt = eec.FusedNoamAdamW(m, model_size=256, warmup=7)
+    for _ in range(2):
+        opt.zero_grad()
+        eec.multi_exit_ctc_loss(m(src.cuda(), lengths), targets, tl).backward()
+        opt.step()
+    st = opt.state_dict()
+    assert st["_step"] == 2 and st["warmup"] == 7 and st["model_size"] == 256
+    assert abs(st["_rate"] - _noam_rate(2, 256, 7)) < 1e-12
+
+    class NoamOpt:   # the reference's scheduler restated (its state handling is `__dict__` based, util/noam_opt.py:12-25)
+        def __init__(self):
+            self.optimizer, self._step, self.warmup, self.model_size, self._rate = None, 0, 25000, 256, 0
+
+        def state_dict(self):
+            return {k: v for k, v in self.__dict__.items() if k != "optimizer"}
+
+        def load_state_dict(self, s):
+            self.__dict__.update(s)
+    ref = NoamOpt()
+    ref.load_state_dict(st)                       # a file written here resumes the reference's schedule at the right step
+    assert ref._step == 2 and ref.warmup == 7
+    ref._step, ref.warmup = 11, 13
+    opt.load_state_dict(ref.state_dict())         # ... and the reference's file loads here
+    assert opt._step == 11 and opt.warmup == 13.0
+    assert float(opt.exp_avg.abs().max()) == 0.0 and float(opt.exp_avg_sq.abs().max()) == 0.0
+    opt.load_state_dict(st)
+    assert opt._step == 2 and opt.warmup == 7.0 and float(opt.exp_avg.abs().max()) > 0.0
+
+
+def test_truncated_splitformer_graph_keeps_first_branch():
+    """GraphedForward(n_exits < E) on a Splitformer must equal the first exits of the FULL model (the parallel branch of
+    group 0 is applied whatever follows, early_exit.py:314-356)."""
+    import eec
+    g = np.load(os.path.join(GOLDEN, "sf_e3l1_b2_t203.npz"))
+    m, sd, src, lengths = build("sf_e3l1_b2_t203", g, "bf16")
+    m.eval()
+    with torch.no_grad():
+        ref = m(src.cuda(), lengths)
+    for n in (1, 2):
+        fwd = eec.GraphedForward(m, src.shape[0], src.shape[2], n_exits=n)
+        out = fwd(src, lengths)
+        assert out.shape[0] == n
+        for e in range(n):
+            assert rel(out[e], ref[e]) < 1e-6, (n, e)
+
+
+def test_graph_warmup_leaves_model_state_untouched():
+    """building a GraphedTrainStep must not move BatchNorm running statistics, num_batches_tracked or the weights."""
+    import eec
+    name = "ec_e2l1_b3_t163"
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    m, sd, src, lengths = build(name, g, "bf16")
+    m.train()
+    before = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    step = eec.GraphedTrainStep(m, src.shape[0], src.shape[2], 12)
+    torch.cuda.synchronize()
+    for k, v in m.state_dict().items():
+        assert torch.equal(v, before[k]), k
+    # two loads back to back without a sync in between: the second must not tear the first one's staged batch (pinned buffers are single)
+    targets, tl = O.synthetic_targets(src.shape[0], seed=11, lo=3, hi=6)
+    src2, lengths2 = O.synthetic_batch(src.shape[0], src.shape[2], seed=78)
+    l1 = float(step(src, lengths, targets, tl).clone())
+    step.load_inputs(src, lengths, targets, tl)
+    a = step.replay().clone()
+    step.load_inputs(src2, lengths2, targets, tl)
+    b = step.replay().clone()
+    torch.cuda.synchronize()
+    assert abs(float(a) - l1) <= 1e-2 * abs(l1)
+    step.load_inputs(src2, lengths2, targets, tl)
+    b2 = step.replay().clone()
+    torch.cuda.synchronize()
+    assert torch.isfinite(a) and torch.isfinite(b) and torch.isfinite(b2)

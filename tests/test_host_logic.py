@@ -181,6 +181,24 @@ def test_dropin_rebinds_reference_classes():
         importlib.invalidate_caches()
 
 
+def test_dropin_ctc_patch_is_scoped_to_one_module():
+    """eec.dropin.patch_ctc(train_module): the module's `nn.CTCLoss(blank=0, zero_infinity=True)` builds eec.CTCLoss; torch.nn itself and
+    every other configuration are untouched."""
+    import types
+    import eec
+    import eec.dropin
+    mod = types.ModuleType("fake_train")
+    mod.nn = torch.nn
+    orig = torch.nn.CTCLoss
+    eec.dropin.patch_ctc(mod)
+    assert torch.nn.CTCLoss is orig                                           # global namespace unchanged
+    assert isinstance(mod.nn.CTCLoss(blank=0, zero_infinity=True), eec.CTCLoss)
+    assert isinstance(mod.nn.CTCLoss(blank=0), orig) and isinstance(torch.nn.CTCLoss(blank=0, zero_infinity=True), orig)
+    assert mod.nn.Linear is torch.nn.Linear and mod.nn.functional is torch.nn.functional
+    with pytest.raises(AttributeError):
+        eec.dropin.patch_ctc(types.ModuleType("no_nn"))
+
+
 def _overlap_worker(rank, world, port, q):
     import sys
     sys.path.insert(0, os.path.join(ROOT, "early-exit-transformer_b200"))
