@@ -36,15 +36,15 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
 }
 
 // D[b,h,t] = sum_d dO[b,t,h,d] * O[b,t,h,d]      (one warp per frame row: lane owns 8 channels = 1/4 head)
-__global__ void __launch_bounds__(256) attn_dvec_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ d_o,
+__global__ void __launch_bounds__(256) attn_dvec_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ d_o, int ldo,
                                                         float* __restrict__ dvec, int B, int T, int H) {
   pdl_trigger();
   pdl_wait();
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (row >= B * T) return;
   float a[8], g[8];
-  ld8<__nv_bfloat16>(o + (long)row * 256 + lane * 8, a);
-  ld8<__nv_bfloat16>(d_o + (long)row * 256 + lane * 8, g);
+  ld8<__nv_bfloat16>(o + (long)row * ldo + lane * 8, a);
+  ld8<__nv_bfloat16>(d_o + (long)row * ldo + lane * 8, g);
   float s = 0.f;
 #pragma unroll
   for (int i = 0; i < 8; ++i) s = fmaf(a[i], g[i], s);
@@ -56,8 +56,8 @@ __global__ void __launch_bounds__(256) attn_dvec_kernel(const __nv_bfloat16* __r
   }
 }
 
-// dqkv[:, 0:256] = bf16(scale * dq32)
-__global__ void dq_convert_kernel(const float* __restrict__ dq32, __nv_bfloat16* __restrict__ dqkv, long rows, float scale) {
+// dq[:, 0:256] (row pitch lddq) = bf16(scale * dq32)
+__global__ void dq_convert_kernel(const float* __restrict__ dq32, __nv_bfloat16* __restrict__ dqkv, int lddq, long rows, float scale) {
   pdl_trigger();
   pdl_wait();
   long i = ((long)blockIdx.x * blockDim.x + threadIdx.x) * 8;
@@ -68,15 +68,27 @@ __global__ void dq_convert_kernel(const float* __restrict__ dq32, __nv_bfloat16*
   ld8<float>(dq32 + i, v);
 #pragma unroll
   for (int k = 0; k < 8; ++k) v[k] *= scale;
-  st8<__nv_bfloat16>(dqkv + r * 768 + c, v);
+  st8<__nv_bfloat16>(dqkv + r * lddq + c, v);
 }
 
-template <bool DROP>
-__global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv,
-                                                                 const __grid_constant__ CUtensorMap tm_do,
-                                                                 const int32_t* __restrict__ key_len, const float* __restrict__ lse,
+// geometry of a call: see attn_tc.cu (self-attention over the packed projection, causal decoder self-attention, cross-attention)
+struct BwGeom {
+  int Tq, Tk, H;
+  int q_col, k_col, v_col;
+  const int32_t* key_len;
+  const uint32_t* key_bits;
+  int causal;
+  __nv_bfloat16* dk; int lddk;      // head 0 of dK / dV at these pointers
+  __nv_bfloat16* dv; int lddv;
+};
+
+template <bool DROP, bool GENERAL>
+__global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q,
+                                                                 const __grid_constant__ CUtensorMap tm_kv,
+                                                                 const __grid_constant__ CUtensorMap tm_do, const BwGeom g,
+                                                                 const float* __restrict__ lse,
                                                                  const float* __restrict__ dvec, float* __restrict__ dq32,
-                                                                 __nv_bfloat16* __restrict__ dqkv, int T, int H, const DropArgs drop) {
+                                                                 const DropArgs drop) {
   pdl_trigger();
   pdl_wait();
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -100,14 +112,17 @@ __global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_tc_kernel(const __grid
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.z, h = blockIdx.y, k0 = blockIdx.x * BT;
-  const int klen = min(key_len[b], T);
-  const int D = H * DHD, D3 = 3 * D;
-  const int row0 = b * T;
-  const int nq = (T + BT - 1) / BT;
-  const bool active = k0 < klen;   // block has at least one unmasked key
+  const int H = g.H, Tq = g.Tq, Tk = g.Tk;
+  const int klen = g.key_len ? min(g.key_len[b], Tk) : Tk;
+  const int D = H * DHD;
+  const int rowq = b * Tq, rowk = b * Tk;
+  const int nq = (Tq + BT - 1) / BT;
+  const int i_begin = (GENERAL && g.causal) ? k0 / BT : 0;     // queries before the block's first key see none of its keys
+  const bool active = k0 < klen && i_begin < nq;   // block has at least one key some query may see
 
   if (threadIdx.x == 0) {
-    tma_prefetch_desc(&tm_qkv);
+    tma_prefetch_desc(&tm_q);
+    tma_prefetch_desc(&tm_kv);
     tma_prefetch_desc(&tm_do);
     mbar_init(kv_full, 1);
     for (int s = 0; s < ST; ++s) { mbar_init(&qdo_full[s], 1); mbar_init(&qdo_empty[s], 1); }
@@ -127,14 +142,14 @@ __global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_tc_kernel(const __grid
   if (warp == 0) {
     if (lane == 0 && active) {
       mbar_expect_tx(kv_full, 2 * TILE_QD);
-      tma_load_2d(sK, &tm_qkv, kv_full, D + h * DHD, row0 + k0);
-      tma_load_2d(sV, &tm_qkv, kv_full, 2 * D + h * DHD, row0 + k0);
-      for (int i = 0; i < nq; ++i) {
+      tma_load_2d(sK, &tm_kv, kv_full, g.k_col + h * DHD, rowk + k0);
+      tma_load_2d(sV, &tm_kv, kv_full, g.v_col + h * DHD, rowk + k0);
+      for (int i = 0; i < nq - i_begin; ++i) {        // i counts the query blocks this CTA visits (barrier phases); block index i_begin + i
         const int s = i % ST;
         mbar_wait(&qdo_empty[s], ((i / ST) & 1) ^ 1);
         mbar_expect_tx(&qdo_full[s], 2 * TILE_QD);
-        tma_load_2d(sQ + s * TILE_QD, &tm_qkv, &qdo_full[s], h * DHD, row0 + i * BT);
-        tma_load_2d(sdO + s * TILE_QD, &tm_do, &qdo_full[s], h * DHD, row0 + i * BT);
+        tma_load_2d(sQ + s * TILE_QD, &tm_q, &qdo_full[s], g.q_col + h * DHD, rowq + (i_begin + i) * BT);
+        tma_load_2d(sdO + s * TILE_QD, &tm_do, &qdo_full[s], h * DHD, rowq + (i_begin + i) * BT);
       }
     }
   } else if (warp == 1) {
@@ -144,7 +159,7 @@ __global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_tc_kernel(const __grid
       constexpr uint32_t id_q = make_idesc_bf16(BT, DHD, false, true);    // dQ     : A K-major,      B MN-major
       mbar_wait(kv_full, 0);
       const uint32_t ak = smem_u32(sK), av = smem_u32(sV), ap = smem_u32(sP), ads = smem_u32(sdS);
-      for (int i = 0; i < nq; ++i) {
+      for (int i = 0; i < nq - i_begin; ++i) {
         const int s = i % ST;
         mbar_wait(&qdo_full[s], (i / ST) & 1);
         const uint32_t aq = smem_u32(sQ + s * TILE_QD), ado = smem_u32(sdO + s * TILE_QD);
@@ -191,14 +206,15 @@ __global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_tc_kernel(const __grid
     // dropout on the probabilities (DROP): with M = mask * scale regenerated from the forward's counters,
     //   dV uses P.M (the tile written to sP), dS = P (dP.M - D) and D = dO . O is unchanged (O = (P.M) V).
     const uint32_t* dbits = reinterpret_cast<const uint32_t*>(drop.bits);   // keep-mask words of the forward (eec_dropout_bits, W = 32)
-    const long dR = (long)gridDim.z * H * T;
+    const long dR = (long)gridDim.z * H * Tq;
+    const uint32_t* kbits = GENERAL && g.key_bits ? g.key_bits + (long)b * ((Tk + 31) >> 5) : nullptr;
     if (active) {
-      for (int i = 0; i < nq; ++i) {
-        const int t = i * BT + r;
-        const bool rvalid = t < T;
-        const long drow = (long)(b * H + h) * T + t;
-        const float l2 = rvalid ? lse[((long)b * H + h) * T + t] * LOG2E : 0.f;
-        const float di = rvalid ? dvec[((long)b * H + h) * T + t] : 0.f;
+      for (int i = 0; i < nq - i_begin; ++i) {
+        const int t = (i_begin + i) * BT + r;
+        const bool rvalid = t < Tq;
+        const long drow = (long)(b * H + h) * Tq + t;
+        const float l2 = rvalid ? lse[((long)b * H + h) * Tq + t] * LOG2E : 0.f;
+        const float di = rvalid ? dvec[((long)b * H + h) * Tq + t] : 0.f;
 #pragma unroll 1
         for (int hk = 0; hk < 2; ++hk) {
           const int n = 2 * i + hk;
@@ -210,7 +226,26 @@ __global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_tc_kernel(const __grid
           tmem_ld32x2(trow + C_S + half * 32, trow + C_DP + half * 32, s, dp);
           tc_fence_before();
           mbar_arrive(sdp_free);                  // S / dP are in registers: the MMA warp may start the next half
-          if (DROP) {
+          if (GENERAL) {
+            // visibility word of (row t, these 32 keys): length, causal and per-key validity masks
+            const int base = k0 + c0;
+            uint32_t mk = !rvalid ? 0u : (base + 32 <= klen) ? ~0u : (base >= klen ? 0u : ((1u << (klen - base)) - 1u));
+            if (g.causal) {
+              const int lim = t - base;
+              mk &= lim >= 31 ? ~0u : (lim < 0 ? 0u : ((2u << lim) - 1u));
+            }
+            if (kbits && base < Tk) mk &= kbits[base >> 5];
+            const bool lfin = l2 > -INFINITY;         // a row without any visible key has lse = -inf: its probabilities are 0
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+              const bool ok = ((mk >> e) & 1u) && lfin;
+              float p;
+              asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p) : "f"(fmaf(s[e], sc2, -l2)));
+              p = ok ? p : 0.f;
+              s[e] = p;
+              dp[e] = ok ? p * (dp[e] - di) : 0.f;
+            }
+          } else if (DROP) {
 #pragma unroll
             for (int e = 0; e < 32; ++e) {
               const bool ok = rvalid && (k0 + c0 + e < klen);
@@ -248,15 +283,15 @@ __global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_tc_kernel(const __grid
           uint8_t* prow = sP + hk * 16384 + r * 128;
           uint8_t* drow = sdS + hk * 16384 + r * 128;
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const int off = ((half * 4 + g) ^ (r & 7)) << 4;
+          for (int gg = 0; gg < 4; ++gg) {
+            const int off = ((half * 4 + gg) ^ (r & 7)) << 4;
             uint4 u, w;
             __nv_bfloat162* hu = reinterpret_cast<__nv_bfloat162*>(&u);
             __nv_bfloat162* hw = reinterpret_cast<__nv_bfloat162*>(&w);
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              hu[e] = __floats2bfloat162_rn(s[g * 8 + 2 * e], s[g * 8 + 2 * e + 1]);
-              hw[e] = __floats2bfloat162_rn(dp[g * 8 + 2 * e], dp[g * 8 + 2 * e + 1]);
+              hu[e] = __floats2bfloat162_rn(s[gg * 8 + 2 * e], s[gg * 8 + 2 * e + 1]);
+              hw[e] = __floats2bfloat162_rn(dp[gg * 8 + 2 * e], dp[gg * 8 + 2 * e + 1]);
             }
             *reinterpret_cast<uint4*>(prow + off) = u;
             *reinterpret_cast<uint4*>(drow + off) = w;
@@ -269,9 +304,9 @@ __global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_tc_kernel(const __grid
           tc_fence_after();
           tmem_ld32(trow + C_DQ, s);
           if (rvalid) {
-            float* dst = dq32 + ((long)(row0 + t)) * D + h * DHD;
+            float* dst = dq32 + ((long)(rowq + t)) * D + h * DHD;
 #pragma unroll
-            for (int g = 0; g < 8; ++g) red_add_v4(dst + g * 4, s[g * 4], s[g * 4 + 1], s[g * 4 + 2], s[g * 4 + 3]);
+            for (int gg = 0; gg < 8; ++gg) red_add_v4(dst + gg * 4, s[gg * 4], s[gg * 4 + 1], s[gg * 4 + 2], s[gg * 4 + 3]);
           }
           tc_fence_before();
         }
@@ -287,15 +322,15 @@ __global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_tc_kernel(const __grid
 #pragma unroll
       for (int e = 0; e < 32; ++e) s[e] = 0.f;
     }
-    if (tk < T) {
+    if (tk < Tk) {
       const float scale = (half == 0) ? 1.0f : rsqrtf((float)DHD);
-      __nv_bfloat16* dst = dqkv + ((long)(row0 + tk)) * D3 + (half == 0 ? 2 * D : D) + h * DHD;
+      __nv_bfloat16* dst = (half == 0 ? g.dv + ((long)(rowk + tk)) * g.lddv : g.dk + ((long)(rowk + tk)) * g.lddk) + h * DHD;
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
+      for (int gg = 0; gg < 4; ++gg) {
         float a[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) a[e] = s[g * 8 + e] * scale;
-        st8<__nv_bfloat16>(dst + g * 8, a);
+        for (int e = 0; e < 8; ++e) a[e] = s[gg * 8 + e] * scale;
+        st8<__nv_bfloat16>(dst + gg * 8, a);
       }
     }
     tc_fence_before();
@@ -307,6 +342,30 @@ __global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_tc_kernel(const __grid
   }
 }
 
+static int bwd_launch(const CUtensorMap& tq, const CUtensorMap& tkv, const CUtensorMap& td, const BwGeom& g, int B, const void* ctx,
+                      const void* dctx, int ldo, const float* lse, float* dvec, float* dq32, void* dq, int lddq, const DropArgs& drop,
+                      bool general, cudaStream_t st) {
+  const long rows = (long)B * g.Tq;
+  launch_pdl(attn_dvec_kernel, dim3((int)cdiv64(rows * 32, 256)), dim3(256), 0, st, (const __nv_bfloat16*)ctx, (const __nv_bfloat16*)dctx, ldo, dvec, B, g.Tq, g.H);
+  EEC_LAUNCH_CHECK();
+  EEC_CUDA(cudaMemsetAsync(dq32, 0, (size_t)rows * 256 * sizeof(float), st));
+  static bool attr_set = false;
+  if (!attr_set) {
+    EEC_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BW_SMEM));
+    EEC_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BW_SMEM));
+    EEC_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BW_SMEM));
+    attr_set = true;
+  }
+  dim3 grid(cdiv(g.Tk, BT), g.H, B);
+  if (general) launch_pdl(attn_bwd_tc_kernel<false, true>, dim3(grid), dim3(BW_THREADS), BW_SMEM, st, tq, tkv, td, g, lse, dvec, dq32, drop);
+  else if (drop.state) launch_pdl(attn_bwd_tc_kernel<true, false>, dim3(grid), dim3(BW_THREADS), BW_SMEM, st, tq, tkv, td, g, lse, dvec, dq32, drop);
+  else launch_pdl(attn_bwd_tc_kernel<false, false>, dim3(grid), dim3(BW_THREADS), BW_SMEM, st, tq, tkv, td, g, lse, dvec, dq32, drop);
+  EEC_LAUNCH_CHECK();
+  launch_pdl(dq_convert_kernel, dim3((int)cdiv64(rows * 32, 256)), dim3(256), 0, st, dq32, (__nv_bfloat16*)dq, lddq, rows, rsqrtf((float)DHD));
+  EEC_LAUNCH_CHECK();
+  return 0;
+}
+
 }  // namespace
 
 int attn_bwd_tc(const void* qkv, const void* ctx, const void* dctx, const float* lse, const int32_t* key_len, void* dqkv,
@@ -314,25 +373,33 @@ int attn_bwd_tc(const void* qkv, const void* ctx, const void* dctx, const float*
   EEC_CHECK_ARG(dh == DHD && H * dh == 256, "attn_bwd_tc: needs 8 heads of 32");
   EEC_CHECK_ARG(dq32 != nullptr, "attn_bwd_tc: dq32 workspace is NULL");
   const long rows = (long)B * T;
-  launch_pdl(attn_dvec_kernel, dim3((int)cdiv64(rows * 32, 256)), dim3(256), 0, st, (const __nv_bfloat16*)ctx, (const __nv_bfloat16*)dctx, dvec, B, T, H);
-  EEC_LAUNCH_CHECK();
-  EEC_CUDA(cudaMemsetAsync(dq32, 0, (size_t)rows * 256 * sizeof(float), st));
   CUtensorMap tq, td;
   if (int r = get_tmap_2d(&tq, qkv, 768, (uint64_t)rows, 768 * 2, DHD, 128, /*SWIZZLE_64B*/ 2)) return r;
   if (int r = get_tmap_2d(&td, dctx, 256, (uint64_t)rows, 256 * 2, DHD, 128, 2)) return r;
-  static bool attr_set = false;
-  if (!attr_set) {
-    EEC_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BW_SMEM));
-    EEC_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BW_SMEM));
-    attr_set = true;
-  }
-  dim3 grid(cdiv(T, BT), H, B);
-  if (drop.state) launch_pdl(attn_bwd_tc_kernel<true>, dim3(grid), dim3(BW_THREADS), BW_SMEM, st, tq, td, key_len, lse, dvec, dq32, (__nv_bfloat16*)dqkv, T, H, drop);
-  else launch_pdl(attn_bwd_tc_kernel<false>, dim3(grid), dim3(BW_THREADS), BW_SMEM, st, tq, td, key_len, lse, dvec, dq32, (__nv_bfloat16*)dqkv, T, H, drop);
-  EEC_LAUNCH_CHECK();
-  launch_pdl(dq_convert_kernel, dim3((int)cdiv64(rows * 32, 256)), dim3(256), 0, st, dq32, (__nv_bfloat16*)dqkv, rows, rsqrtf((float)dh));
-  EEC_LAUNCH_CHECK();
-  return 0;
+  BwGeom g{};
+  g.Tq = g.Tk = T; g.H = H; g.q_col = 0; g.k_col = 256; g.v_col = 512; g.key_len = key_len;
+  g.dk = (__nv_bfloat16*)dqkv + 256; g.dv = (__nv_bfloat16*)dqkv + 512; g.lddk = g.lddv = 768;
+  return bwd_launch(tq, tq, td, g, B, ctx, dctx, 256, lse, dvec, dq32, dqkv, 768, drop, false, st);
+}
+
+int attn_general_bwd_tc(const eec_attn_desc* d, const void* ctx, const void* dctx, int ldo, const float* lse, void* dq, int lddq, void* dk,
+                        int lddk, void* dv, int lddv, float* dvec, float* dq32, cudaStream_t st) {
+  EEC_CHECK_ARG(d->dh == DHD && d->H * d->dh == 256, "attn_general_bwd_tc: needs 8 heads of 32");
+  EEC_CHECK_ARG(dq32 != nullptr, "attn_general_bwd_tc: dq32 workspace is NULL");
+  const uintptr_t k = (uintptr_t)d->k, v = (uintptr_t)d->v;
+  const void* kv_base = k < v ? d->k : d->v;
+  BwGeom g{};
+  g.Tq = d->Tq; g.Tk = d->Tk; g.H = d->H;
+  g.q_col = 0; g.k_col = (int)((k - (uintptr_t)kv_base) / 2); g.v_col = (int)((v - (uintptr_t)kv_base) / 2);
+  g.key_len = d->key_len; g.key_bits = d->key_valid_bits; g.causal = d->causal;
+  g.dk = (__nv_bfloat16*)dk; g.lddk = lddk; g.dv = (__nv_bfloat16*)dv; g.lddv = lddv;
+  CUtensorMap tq, tkv, td;
+  if (int r = get_tmap_2d(&tq, d->q, (uint64_t)d->H * d->dh, (uint64_t)d->B * d->Tq, (uint64_t)d->ldq * 2, DHD, 128, 2)) return r;
+  const uint64_t kv_cols = (uint64_t)(g.k_col > g.v_col ? g.k_col : g.v_col) + (uint64_t)d->H * d->dh;
+  if (int r = get_tmap_2d(&tkv, kv_base, kv_cols, (uint64_t)d->B * d->Tk, (uint64_t)d->ldk * 2, DHD, 128, 2)) return r;
+  if (int r = get_tmap_2d(&td, dctx, (uint64_t)d->H * d->dh, (uint64_t)d->B * d->Tq, (uint64_t)ldo * 2, DHD, 128, 2)) return r;
+  DropArgs drop{};
+  return bwd_launch(tq, tkv, td, g, d->B, ctx, dctx, ldo, lse, dvec, dq32, dq, lddq, drop, true, st);
 }
 
 }  // namespace eec

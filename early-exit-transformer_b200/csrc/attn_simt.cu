@@ -10,40 +10,62 @@ constexpr int QB = 32;    // queries (or keys, in the dK/dV pass) per block
 constexpr int KC = 128;   // keys (or queries) staged per chunk
 constexpr int DH = 32;
 
-// grid (ceil(T/QB), H, B), 128 threads: warp w owns rows w*8 .. w*8+7 of the block
+// Geometry of one attention call (host-built, passed by value).  Self-attention over a packed [rows, 3D] tensor, causal decoder
+// self-attention and encoder-decoder cross-attention (Q rows from one tensor, K / V rows from another, Tq != Tk) are the same kernels:
+//   Q(b, t, h, d)  = q[(b*Tq + t)*ldq + h*32 + d]      K(b, t', h, d) = k[(b*Tk + t')*ldk + h*32 + d]      (likewise V, and the outputs)
+// a key t' is visible to query t iff  t' < key_len[b] (when given)  and  bit t' of key_bits[b] is set (when given)  and  (!causal or t' <= t).
+struct AttnGeom {
+  const void* q; const void* k; const void* v;
+  int ldq, ldk, ldv;
+  int Tq, Tk, H;
+  const int32_t* key_len;
+  const uint32_t* key_bits;    // [B, ceil(Tk/32)] words
+  int causal;
+};
+__device__ __forceinline__ int geom_klen(const AttnGeom& g, int b) { return g.key_len ? min(g.key_len[b], g.Tk) : g.Tk; }
+__device__ __forceinline__ bool geom_visible(const AttnGeom& g, int b, int t, int key, int klen) {
+  if (key >= klen) return false;
+  if (g.causal && key > t) return false;
+  if (g.key_bits && !((g.key_bits[(long)b * ((g.Tk + 31) >> 5) + (key >> 5)] >> (key & 31)) & 1u)) return false;
+  return true;
+}
+
+// grid (ceil(Tq/QB), H, B), 128 threads: warp w owns rows w*8 .. w*8+7 of the block
 template <typename T, bool ACC>
-__global__ void __launch_bounds__(128) attn_fwd_simt_kernel(const T* __restrict__ qkv, const int32_t* __restrict__ key_len,
-                                                           T* __restrict__ ctx, float* __restrict__ lse, int Tn, int H,
+__global__ void __launch_bounds__(128) attn_fwd_simt_kernel(const AttnGeom g, T* __restrict__ ctx, int ldo, float* __restrict__ lse,
                                                            const DropArgs drop, const ActiveItems act_items) {
   if (act_items.n_dev && (int)blockIdx.z >= active_count(act_items)) return;
   __shared__ float Ks[KC][DH + 1];
   __shared__ float Vs[KC][DH];
   DropKey dkey{};
   if (drop.state) dkey = drop_key(drop);
-  const uint64_t tk8 = (uint64_t)((Tn + 7) >> 3) * 8;   // dropout element index of (b, h, t, key) = ((b*H + h)*T + t) * tk8 + key
+  const int Tq = g.Tq, Tk = g.Tk, H = g.H;
+  const uint64_t tk8 = (uint64_t)((Tk + 7) >> 3) * 8;   // dropout element index of (b, h, t, key) = ((b*H + h)*Tq + t) * tk8 + key
   __shared__ float Qs[QB][DH];
   __shared__ float Ps[4][KC];
   const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * QB;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  const int D3 = 3 * H * DH, D = H * DH;
   const float scale = rsqrtf((float)DH);
-  const int klen = min(key_len[b], Tn);
-  const T* base = qkv + (long)b * Tn * D3;
+  const int klen = geom_klen(g, b);
+  const int kend = g.causal ? min(klen, q0 + QB) : klen;      // keys past the block's last query are invisible to all of its rows
+  const T* qb = reinterpret_cast<const T*>(g.q) + (long)b * Tq * g.ldq + h * DH;
+  const T* kb = reinterpret_cast<const T*>(g.k) + (long)b * Tk * g.ldk + h * DH;
+  const T* vb = reinterpret_cast<const T*>(g.v) + (long)b * Tk * g.ldv + h * DH;
   for (int i = tid; i < QB * DH; i += 128) {
     int r = i / DH, d = i % DH;
-    Qs[r][d] = (q0 + r < Tn) ? ld_as_float<T>(base + (long)(q0 + r) * D3 + h * DH + d) * scale : 0.f;
+    Qs[r][d] = (q0 + r < Tq) ? ld_as_float<T>(qb + (long)(q0 + r) * g.ldq + d) * scale : 0.f;
   }
   float m[8], l[8], o[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) { m[i] = -INFINITY; l[i] = 0.f; o[i] = 0.f; }
 
-  for (int k0 = 0; k0 < klen; k0 += KC) {
+  for (int k0 = 0; k0 < kend; k0 += KC) {
     __syncthreads();
     for (int i = tid; i < KC * DH; i += 128) {
       int r = i / DH, d = i % DH;
       bool ok = (k0 + r < klen);
-      Ks[r][d] = ok ? ld_as_float<T>(base + (long)(k0 + r) * D3 + D + h * DH + d) : 0.f;
-      Vs[r][d] = ok ? ld_as_float<T>(base + (long)(k0 + r) * D3 + 2 * D + h * DH + d) : 0.f;
+      Ks[r][d] = ok ? ld_as_float<T>(kb + (long)(k0 + r) * g.ldk + d) : 0.f;
+      Vs[r][d] = ok ? ld_as_float<T>(vb + (long)(k0 + r) * g.ldv + d) : 0.f;
     }
     __syncthreads();
 #pragma unroll
@@ -57,7 +79,7 @@ __global__ void __launch_bounds__(128) attn_fwd_simt_kernel(const T* __restrict_
         float a = 0.f;
 #pragma unroll
         for (int d = 0; d < DH; ++d) a = fmaf(Qs[qr][d], Ks[key][d], a);
-        s[jj] = (k0 + key < klen) ? a : -INFINITY;
+        s[jj] = geom_visible(g, b, q0 + qr, k0 + key, klen) ? a : -INFINITY;
         cmax = fmaxf(cmax, s[jj]);
       }
       cmax = warp_max(cmax);
@@ -67,7 +89,7 @@ __global__ void __launch_bounds__(128) attn_fwd_simt_kernel(const T* __restrict_
       for (int jj = 0; jj < 4; ++jj) {
         float p = (s[jj] == -INFINITY) ? 0.f : (ACC ? expf(s[jj] - mn) : __expf(s[jj] - mn));
         psum += p;   // (the softmax denominator is taken before dropout)
-        if (drop.state) p *= drop_factor1(dkey, drop, ((uint64_t)(b * H + h) * Tn + (q0 + qr)) * tk8 + (k0 + lane + 32 * jj));
+        if (drop.state) p *= drop_factor1(dkey, drop, ((uint64_t)(b * H + h) * Tq + (q0 + qr)) * tk8 + (k0 + lane + 32 * jj));
         Ps[w][lane + 32 * jj] = p;
       }
       psum = warp_sum(psum);
@@ -85,22 +107,22 @@ __global__ void __launch_bounds__(128) attn_fwd_simt_kernel(const T* __restrict_
 #pragma unroll
   for (int qi = 0; qi < 8; ++qi) {
     const int t = q0 + w * 8 + qi;
-    if (t >= Tn) continue;
+    if (t >= Tq) continue;
     const float outv = (l[qi] > 0.f) ? o[qi] / l[qi] : 0.f;
-    st_from_float<T>(ctx + ((long)b * Tn + t) * D + h * DH + lane, outv);
-    if (lse && lane == 0) lse[((long)b * H + h) * Tn + t] = (l[qi] > 0.f) ? m[qi] + logf(l[qi]) : -INFINITY;
+    st_from_float<T>(ctx + ((long)b * Tq + t) * ldo + h * DH + lane, outv);
+    if (lse && lane == 0) lse[((long)b * H + h) * Tq + t] = (l[qi] > 0.f) ? m[qi] + logf(l[qi]) : -INFINITY;
   }
 }
 
 // Backward pass 1: D_i = dO_i . O_i ; dQ_i = scale * sum_j dS_ij K_j
 template <typename T>
-__global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const T* __restrict__ qkv, const T* __restrict__ ctx,
-                                                         const T* __restrict__ dctx, const float* __restrict__ lse,
-                                                         const int32_t* __restrict__ key_len, T* __restrict__ dqkv,
-                                                         float* __restrict__ dvec, int Tn, int H, const DropArgs drop) {
+__global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const AttnGeom g, const T* __restrict__ ctx, const T* __restrict__ dctx, int ldo,
+                                                         const float* __restrict__ lse, T* __restrict__ dq_out, int lddq,
+                                                         float* __restrict__ dvec, const DropArgs drop) {
   DropKey dkey{};
   if (drop.state) dkey = drop_key(drop);
-  const uint64_t tk8 = (uint64_t)((Tn + 7) >> 3) * 8;
+  const int Tq = g.Tq, Tk = g.Tk, H = g.H;
+  const uint64_t tk8 = (uint64_t)((Tk + 7) >> 3) * 8;
   __shared__ float Ks[KC][DH + 1];
   __shared__ float Vs[KC][DH + 1];
   __shared__ float Qs[QB][DH];
@@ -108,34 +130,36 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const T* __restrict__ 
   __shared__ float Ps[4][KC];
   const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * QB;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  const int D3 = 3 * H * DH, D = H * DH;
   const float scale = rsqrtf((float)DH);
-  const int klen = min(key_len[b], Tn);
-  const T* base = qkv + (long)b * Tn * D3;
+  const int klen = geom_klen(g, b);
+  const int kend = g.causal ? min(klen, q0 + QB) : klen;
+  const T* qb = reinterpret_cast<const T*>(g.q) + (long)b * Tq * g.ldq + h * DH;
+  const T* kb = reinterpret_cast<const T*>(g.k) + (long)b * Tk * g.ldk + h * DH;
+  const T* vb = reinterpret_cast<const T*>(g.v) + (long)b * Tk * g.ldv + h * DH;
   for (int i = tid; i < QB * DH; i += 128) {
     int r = i / DH, d = i % DH;
-    bool ok = q0 + r < Tn;
-    Qs[r][d] = ok ? ld_as_float<T>(base + (long)(q0 + r) * D3 + h * DH + d) * scale : 0.f;
-    dOs[r][d] = ok ? ld_as_float<T>(dctx + ((long)b * Tn + q0 + r) * D + h * DH + d) : 0.f;
+    bool ok = q0 + r < Tq;
+    Qs[r][d] = ok ? ld_as_float<T>(qb + (long)(q0 + r) * g.ldq + d) * scale : 0.f;
+    dOs[r][d] = ok ? ld_as_float<T>(dctx + ((long)b * Tq + q0 + r) * ldo + h * DH + d) : 0.f;
   }
   __syncthreads();
   float Di[8], Li[8], dq[8];
 #pragma unroll
   for (int qi = 0; qi < 8; ++qi) {
     const int t = q0 + w * 8 + qi;
-    float ov = (t < Tn) ? ld_as_float<T>(ctx + ((long)b * Tn + t) * D + h * DH + lane) : 0.f;
+    float ov = (t < Tq) ? ld_as_float<T>(ctx + ((long)b * Tq + t) * ldo + h * DH + lane) : 0.f;
     Di[qi] = warp_sum(ov * dOs[w * 8 + qi][lane]);
-    Li[qi] = (t < Tn) ? lse[((long)b * H + h) * Tn + t] : 0.f;
+    Li[qi] = (t < Tq) ? lse[((long)b * H + h) * Tq + t] : 0.f;
     dq[qi] = 0.f;
-    if (t < Tn && lane == 0) dvec[((long)b * H + h) * Tn + t] = Di[qi];
+    if (t < Tq && lane == 0) dvec[((long)b * H + h) * Tq + t] = Di[qi];
   }
-  for (int k0 = 0; k0 < klen; k0 += KC) {
+  for (int k0 = 0; k0 < kend; k0 += KC) {
     __syncthreads();
     for (int i = tid; i < KC * DH; i += 128) {
       int r = i / DH, d = i % DH;
       bool ok = (k0 + r < klen);
-      Ks[r][d] = ok ? ld_as_float<T>(base + (long)(k0 + r) * D3 + D + h * DH + d) : 0.f;
-      Vs[r][d] = ok ? ld_as_float<T>(base + (long)(k0 + r) * D3 + 2 * D + h * DH + d) : 0.f;
+      Ks[r][d] = ok ? ld_as_float<T>(kb + (long)(k0 + r) * g.ldk + d) : 0.f;
+      Vs[r][d] = ok ? ld_as_float<T>(vb + (long)(k0 + r) * g.ldv + d) : 0.f;
     }
     __syncthreads();
 #pragma unroll
@@ -150,8 +174,8 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const T* __restrict__ 
           a = fmaf(Qs[qr][d], Ks[key][d], a);
           dp = fmaf(dOs[qr][d], Vs[key][d], dp);
         }
-        float p = (k0 + key < klen && Li[qi] != -INFINITY) ? expf(a - Li[qi]) : 0.f;
-        if (drop.state) dp *= drop_factor1(dkey, drop, ((uint64_t)(b * H + h) * Tn + (q0 + qr)) * tk8 + (k0 + key));
+        float p = (geom_visible(g, b, q0 + qr, k0 + key, klen) && Li[qi] != -INFINITY) ? expf(a - Li[qi]) : 0.f;
+        if (drop.state) dp *= drop_factor1(dkey, drop, ((uint64_t)(b * H + h) * Tq + (q0 + qr)) * tk8 + (k0 + key));
         Ps[w][key] = p * (dp - Di[qi]);
       }
       __syncwarp();
@@ -165,19 +189,20 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const T* __restrict__ 
 #pragma unroll
   for (int qi = 0; qi < 8; ++qi) {
     const int t = q0 + w * 8 + qi;
-    if (t < Tn) st_from_float<T>(dqkv + ((long)b * Tn + t) * D3 + h * DH + lane, dq[qi] * scale);
+    if (t < Tq) st_from_float<T>(dq_out + ((long)b * Tq + t) * lddq + h * DH + lane, dq[qi] * scale);
   }
 }
 
 // Backward pass 2: block owns QB keys; dV_j = sum_i P_ij dO_i ; dK_j = scale * sum_i dS_ij Q_i
 template <typename T>
-__global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(const T* __restrict__ qkv, const T* __restrict__ dctx,
+__global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(const AttnGeom g, const T* __restrict__ dctx, int ldo,
                                                           const float* __restrict__ lse, const float* __restrict__ dvec,
-                                                          const int32_t* __restrict__ key_len, T* __restrict__ dqkv,
-                                                          int Tn, int H, const DropArgs drop) {
+                                                          T* __restrict__ dk_out, int lddk, T* __restrict__ dv_out, int lddv,
+                                                          const DropArgs drop) {
   DropKey dkey{};
   if (drop.state) dkey = drop_key(drop);
-  const uint64_t tk8 = (uint64_t)((Tn + 7) >> 3) * 8;
+  const int Tq = g.Tq, Tk = g.Tk, H = g.H;
+  const uint64_t tk8 = (uint64_t)((Tk + 7) >> 3) * 8;
   __shared__ float Qs[KC][DH + 1];
   __shared__ float dOs[KC][DH + 1];
   __shared__ float Ksm[QB][DH];
@@ -187,39 +212,40 @@ __global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(const T* __restrict__
   __shared__ float Ls[KC], Ds[KC];
   const int b = blockIdx.z, h = blockIdx.y, j0 = blockIdx.x * QB;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  const int D3 = 3 * H * DH, D = H * DH;
   const float scale = rsqrtf((float)DH);
-  const int klen = min(key_len[b], Tn);
-  const T* base = qkv + (long)b * Tn * D3;
+  const int klen = geom_klen(g, b);
+  const T* qb = reinterpret_cast<const T*>(g.q) + (long)b * Tq * g.ldq + h * DH;
+  const T* kb = reinterpret_cast<const T*>(g.k) + (long)b * Tk * g.ldk + h * DH;
+  const T* vb = reinterpret_cast<const T*>(g.v) + (long)b * Tk * g.ldv + h * DH;
   for (int i = tid; i < QB * DH; i += 128) {
     int r = i / DH, d = i % DH;
-    bool ok = j0 + r < Tn;
-    Ksm[r][d] = ok ? ld_as_float<T>(base + (long)(j0 + r) * D3 + D + h * DH + d) : 0.f;
-    Vsm[r][d] = ok ? ld_as_float<T>(base + (long)(j0 + r) * D3 + 2 * D + h * DH + d) : 0.f;
+    bool ok = j0 + r < Tk;
+    Ksm[r][d] = ok ? ld_as_float<T>(kb + (long)(j0 + r) * g.ldk + d) : 0.f;
+    Vsm[r][d] = ok ? ld_as_float<T>(vb + (long)(j0 + r) * g.ldv + d) : 0.f;
   }
   float dk[8], dv[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) { dk[i] = 0.f; dv[i] = 0.f; }
   const bool any_valid = j0 < klen;
   if (any_valid) {
-    for (int i0 = 0; i0 < Tn; i0 += KC) {
+    const int i_begin = g.causal ? (j0 / KC) * KC : 0;     // queries before the block's first key see none of its keys
+    for (int i0 = i_begin; i0 < Tq; i0 += KC) {
       __syncthreads();
       for (int i = tid; i < KC * DH; i += 128) {
         int r = i / DH, d = i % DH;
-        bool ok = (i0 + r < Tn);
-        Qs[r][d] = ok ? ld_as_float<T>(base + (long)(i0 + r) * D3 + h * DH + d) * scale : 0.f;
-        dOs[r][d] = ok ? ld_as_float<T>(dctx + ((long)b * Tn + i0 + r) * D + h * DH + d) : 0.f;
+        bool ok = (i0 + r < Tq);
+        Qs[r][d] = ok ? ld_as_float<T>(qb + (long)(i0 + r) * g.ldq + d) * scale : 0.f;
+        dOs[r][d] = ok ? ld_as_float<T>(dctx + ((long)b * Tq + i0 + r) * ldo + h * DH + d) : 0.f;
       }
       for (int i = tid; i < KC; i += 128) {
-        bool ok = (i0 + i < Tn);
-        Ls[i] = ok ? lse[((long)b * H + h) * Tn + i0 + i] : -INFINITY;
-        Ds[i] = ok ? dvec[((long)b * H + h) * Tn + i0 + i] : 0.f;
+        bool ok = (i0 + i < Tq);
+        Ls[i] = ok ? lse[((long)b * H + h) * Tq + i0 + i] : -INFINITY;
+        Ds[i] = ok ? dvec[((long)b * H + h) * Tq + i0 + i] : 0.f;
       }
       __syncthreads();
 #pragma unroll
       for (int ki = 0; ki < 8; ++ki) {
         const int kr = w * 8 + ki;
-        const bool kvalid = (j0 + kr < klen);
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj) {
           const int q = lane + 32 * jj;
@@ -229,9 +255,9 @@ __global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(const T* __restrict__
             a = fmaf(Qs[q][d], Ksm[kr][d], a);
             dp = fmaf(dOs[q][d], Vsm[kr][d], dp);
           }
-          float p = (kvalid && Ls[q] != -INFINITY) ? expf(a - Ls[q]) : 0.f;
+          float p = (geom_visible(g, b, i0 + q, j0 + kr, klen) && Ls[q] != -INFINITY) ? expf(a - Ls[q]) : 0.f;
           float f = 1.f;
-          if (drop.state) f = drop_factor1(dkey, drop, ((uint64_t)(b * H + h) * Tn + (i0 + q)) * tk8 + (j0 + kr));
+          if (drop.state) f = drop_factor1(dkey, drop, ((uint64_t)(b * H + h) * Tq + (i0 + q)) * tk8 + (j0 + kr));
           Ps[w][q] = p * f;                      // dV = (P.M)^T dO
           dSs[w][q] = p * (dp * f - Ds[q]);      // dS = P (dP.M - D)
         }
@@ -251,11 +277,29 @@ __global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(const T* __restrict__
 #pragma unroll
   for (int ki = 0; ki < 8; ++ki) {
     const int t = j0 + w * 8 + ki;
-    if (t < Tn) {
-      st_from_float<T>(dqkv + ((long)b * Tn + t) * D3 + D + h * DH + lane, dk[ki]);
-      st_from_float<T>(dqkv + ((long)b * Tn + t) * D3 + 2 * D + h * DH + lane, dv[ki]);
+    if (t < Tk) {
+      st_from_float<T>(dk_out + ((long)b * Tk + t) * lddk + h * DH + lane, dk[ki]);
+      st_from_float<T>(dv_out + ((long)b * Tk + t) * lddv + h * DH + lane, dv[ki]);
     }
   }
+}
+
+template <typename T>
+static int simt_fwd(const AttnGeom& g, int B, void* ctx, int ldo, float* lse, const DropArgs& drop, cudaStream_t st, bool acc) {
+  dim3 grid(cdiv(g.Tq, QB), g.H, B);
+  if (acc) attn_fwd_simt_kernel<T, true><<<grid, 128, 0, st>>>(g, (T*)ctx, ldo, lse, drop, active_items(st));
+  else attn_fwd_simt_kernel<T, false><<<grid, 128, 0, st>>>(g, (T*)ctx, ldo, lse, drop, active_items(st));
+  EEC_LAUNCH_CHECK();
+  return 0;
+}
+template <typename T>
+static int simt_bwd(const AttnGeom& g, int B, const void* ctx, const void* dctx, int ldo, const float* lse, void* dq, int lddq, void* dk,
+                    int lddk, void* dv, int lddv, float* dvec, const DropArgs& drop, cudaStream_t st) {
+  attn_bwd_dq_kernel<T><<<dim3(cdiv(g.Tq, QB), g.H, B), 128, 0, st>>>(g, (const T*)ctx, (const T*)dctx, ldo, lse, (T*)dq, lddq, dvec, drop);
+  EEC_LAUNCH_CHECK();
+  attn_bwd_dkv_kernel<T><<<dim3(cdiv(g.Tk, QB), g.H, B), 128, 0, st>>>(g, (const T*)dctx, ldo, lse, dvec, (T*)dk, lddk, (T*)dv, lddv, drop);
+  EEC_LAUNCH_CHECK();
+  return 0;
 }
 
 }  // namespace eec
@@ -285,13 +329,12 @@ extern "C" int eec_attn_fwd(const void* qkv, int dtype, const int32_t* key_len, 
   EEC_CHECK_ARG(!(tc_path && drop.state && !drop_bits), "attn_fwd (tensor-core path): dropout needs the keep-mask words of "
                 "eec_dropout_bits(R = B*H*T, C = T, Cs = 8*ceil(T/8), W = 32) in drop_bits");
   if (tc_path) return attn_fwd_tc(qkv, key_len, ctx, lse, B, T, H, dh, drop, S(stream));
-  dim3 grid(cdiv(T, QB), H, B);
-  if (dtype == EEC_F32)
-    attn_fwd_simt_kernel<float, true><<<grid, 128, 0, S(stream)>>>((const float*)qkv, key_len, (float*)ctx, lse, T, H, drop, active_items(S(stream)));
-  else
-    attn_fwd_simt_kernel<__nv_bfloat16, false><<<grid, 128, 0, S(stream)>>>((const __nv_bfloat16*)qkv, key_len, (__nv_bfloat16*)ctx, lse, T, H, drop, active_items(S(stream)));
-  EEC_LAUNCH_CHECK();
-  return 0;
+  AttnGeom g{};
+  const int es = dtype == EEC_F32 ? 4 : 2, D = H * dh;
+  g.q = qkv; g.k = (const char*)qkv + (size_t)D * es; g.v = (const char*)qkv + (size_t)2 * D * es;
+  g.ldq = g.ldk = g.ldv = 3 * D; g.Tq = g.Tk = T; g.H = H; g.key_len = key_len;
+  if (dtype == EEC_F32) return simt_fwd<float>(g, B, ctx, D, lse, drop, S(stream), true);
+  return simt_fwd<__nv_bfloat16>(g, B, ctx, D, lse, drop, S(stream), false);
 }
 
 extern "C" int eec_attn_bwd(const void* qkv, const void* ctx, const void* dctx, int dtype, const float* lse,
@@ -305,16 +348,46 @@ extern "C" int eec_attn_bwd(const void* qkv, const void* ctx, const void* dctx, 
   EEC_CHECK_ARG(!(tc_path && drop.state && !drop_bits), "attn_bwd (tensor-core path): dropout needs the forward's keep-mask words in drop_bits");
   if (tc_path)
     return attn_bwd_tc(qkv, ctx, dctx, lse, key_len, dqkv, dvec, dq32, B, T, H, dh, drop, S(stream));
-  dim3 grid(cdiv(T, QB), H, B);
-  if (dtype == EEC_F32) {
-    attn_bwd_dq_kernel<float><<<grid, 128, 0, S(stream)>>>((const float*)qkv, (const float*)ctx, (const float*)dctx, lse, key_len, (float*)dqkv, dvec, T, H, drop);
-    EEC_LAUNCH_CHECK();
-    attn_bwd_dkv_kernel<float><<<grid, 128, 0, S(stream)>>>((const float*)qkv, (const float*)dctx, lse, dvec, key_len, (float*)dqkv, T, H, drop);
-  } else {
-    attn_bwd_dq_kernel<__nv_bfloat16><<<grid, 128, 0, S(stream)>>>((const __nv_bfloat16*)qkv, (const __nv_bfloat16*)ctx, (const __nv_bfloat16*)dctx, lse, key_len, (__nv_bfloat16*)dqkv, dvec, T, H, drop);
-    EEC_LAUNCH_CHECK();
-    attn_bwd_dkv_kernel<__nv_bfloat16><<<grid, 128, 0, S(stream)>>>((const __nv_bfloat16*)qkv, (const __nv_bfloat16*)dctx, lse, dvec, key_len, (__nv_bfloat16*)dqkv, T, H, drop);
-  }
-  EEC_LAUNCH_CHECK();
+  AttnGeom g{};
+  const int es = dtype == EEC_F32 ? 4 : 2, D = H * dh;
+  g.q = qkv; g.k = (const char*)qkv + (size_t)D * es; g.v = (const char*)qkv + (size_t)2 * D * es;
+  g.ldq = g.ldk = g.ldv = 3 * D; g.Tq = g.Tk = T; g.H = H; g.key_len = key_len;
+  char* dq = (char*)dqkv;
+  if (dtype == EEC_F32)
+    return simt_bwd<float>(g, B, ctx, dctx, D, lse, dq, 3 * D, dq + (size_t)D * es, 3 * D, dq + (size_t)2 * D * es, 3 * D, dvec, drop, S(stream));
+  return simt_bwd<__nv_bfloat16>(g, B, ctx, dctx, D, lse, dq, 3 * D, dq + (size_t)D * es, 3 * D, dq + (size_t)2 * D * es, 3 * D, dvec, drop, S(stream));
+}
+
+/* ---- general attention (decoder self-attention with causal + key masks, encoder-decoder cross-attention): include/eec.h ---- */
+static int geom_from_desc(const eec_attn_desc* d, AttnGeom& g) {
+  EEC_CHECK_ARG(d != nullptr, "attn: NULL descriptor");
+  EEC_CHECK_ARG(d->dh == 32 && d->H >= 1, "attn: head dim must be 32 (got %d)", d->dh);
+  EEC_CHECK_ARG(d->q && d->k && d->v, "attn: NULL operand");
+  EEC_CHECK_ARG(d->dtype == EEC_F32 || d->dtype == EEC_BF16, "attn: dtype");
+  g.q = d->q; g.k = d->k; g.v = d->v; g.ldq = d->ldq; g.ldk = d->ldk; g.ldv = d->ldv;
+  g.Tq = d->Tq; g.Tk = d->Tk; g.H = d->H; g.key_len = d->key_len; g.key_bits = d->key_valid_bits; g.causal = d->causal;
   return 0;
+}
+
+extern "C" int eec_attn_general_fwd(const eec_attn_desc* d, void* ctx, int ldo, float* lse, eec_stream_t stream) {
+  AttnGeom g{};
+  if (int r = geom_from_desc(d, g)) return r;
+  if (d->B == 0 || d->Tq == 0) return 0;
+  DropArgs drop{};
+  const bool tc_path = d->dtype == EEC_BF16 && !force_simt() && attn_tc_ready() && attn_general_tc_ok(d);
+  if (tc_path) return attn_general_fwd_tc(d, ctx, ldo, lse, S(stream));
+  if (d->dtype == EEC_F32) return simt_fwd<float>(g, d->B, ctx, ldo, lse, drop, S(stream), true);
+  return simt_fwd<__nv_bfloat16>(g, d->B, ctx, ldo, lse, drop, S(stream), false);
+}
+
+extern "C" int eec_attn_general_bwd(const eec_attn_desc* d, const void* ctx, const void* dctx, int ldo, const float* lse, void* dq,
+                                    int lddq, void* dk, int lddk, void* dv, int lddv, float* dvec, float* dq32, eec_stream_t stream) {
+  AttnGeom g{};
+  if (int r = geom_from_desc(d, g)) return r;
+  if (d->B == 0 || d->Tq == 0) return 0;
+  DropArgs drop{};
+  const bool tc_path = d->dtype == EEC_BF16 && !force_simt() && attn_tc_ready() && attn_general_tc_ok(d);
+  if (tc_path) return attn_general_bwd_tc(d, ctx, dctx, ldo, lse, dq, lddq, dk, lddk, dv, lddv, dvec, dq32, S(stream));
+  if (d->dtype == EEC_F32) return simt_bwd<float>(g, d->B, ctx, dctx, ldo, lse, dq, lddq, dk, lddk, dv, lddv, dvec, drop, S(stream));
+  return simt_bwd<__nv_bfloat16>(g, d->B, ctx, dctx, ldo, lse, dq, lddq, dk, lddk, dv, lddv, dvec, drop, S(stream));
 }

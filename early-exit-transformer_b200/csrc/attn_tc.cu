@@ -36,208 +36,36 @@ __device__ __forceinline__ float ex2_fast(float x) {
   return y;
 }
 
-template <bool DROP>
-__global__ void __launch_bounds__(AT_THREADS, 2) attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv,
-                                                                 const int32_t* __restrict__ key_len,
-                                                                 __nv_bfloat16* __restrict__ ctx, float* __restrict__ lse,
-                                                                 int T, int H, const DropArgs drop, const ActiveItems act_items) {
-  pdl_trigger();
-  pdl_wait();
-  if (act_items.n_dev && (int)blockIdx.z >= active_count(act_items)) return;   // utterance past the active-item limit (whole CTA, before any barrier)
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;
-  uint8_t* sK = sQ + Q_BYTES;                       // [stage]
-  uint8_t* sV = sK + KV_STAGES * K_BYTES;           // [stage]
-  uint8_t* sP = sV + KV_STAGES * V_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + P_BYTES);
-  uint64_t* q_full = bars;
-  uint64_t* kv_full = bars + 1;                     // [2]
-  uint64_t* kv_empty = bars + 3;                    // [2]
-  uint64_t* s_full = bars + 5;
-  uint64_t* s_free = bars + 6;
-  uint64_t* p_full = bars + 7;
-  uint64_t* o_full = bars + 8;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 9);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * QT;
-  const int klen = min(key_len[b], T);
-  const int nblk = (klen + KB - 1) / KB;
-  const int D = H * DHEAD;
-  const int row0 = b * T;
-
-  if (threadIdx.x == 0) {
-    tma_prefetch_desc(&tm_qkv);
-    mbar_init(q_full, 1);
-    for (int s = 0; s < KV_STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
-    mbar_init(s_full, 1);
-    mbar_init(s_free, 128);
-    mbar_init(p_full, 128);
-    mbar_init(o_full, 1);
-    fence_barrier_init();
-  }
-  if (warp == 1) { tmem_alloc(tmem_ptr_smem, TMEM_COLS); tmem_relinquish(); }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr_smem;
-
-  if (warp == 0) {
-    if (lane == 0 && nblk > 0) {
-      mbar_expect_tx(q_full, Q_BYTES);
-      tma_load_2d(sQ, &tm_qkv, q_full, h * DHEAD, row0 + q0);
-      for (int j = 0; j < nblk; ++j) {
-        const int s = j % KV_STAGES;
-        mbar_wait(&kv_empty[s], ((j / KV_STAGES) & 1) ^ 1);
-        mbar_expect_tx(&kv_full[s], K_BYTES + V_BYTES);
-        tma_load_2d(sK + s * K_BYTES, &tm_qkv, &kv_full[s], D + h * DHEAD, row0 + j * KB);
-        tma_load_2d(sV + s * V_BYTES, &tm_qkv, &kv_full[s], 2 * D + h * DHEAD, row0 + j * KB);
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0 && nblk > 0) {
-      constexpr uint32_t idesc_s = make_idesc_bf16(QT, KB, false, false);
-      constexpr uint32_t idesc_o = make_idesc_bf16(QT, DHEAD, false, true);
-      mbar_wait(q_full, 0);
-      for (int j = 0; j < nblk; ++j) {
-        const int s = j % KV_STAGES;
-        mbar_wait(&kv_full[s], (j / KV_STAGES) & 1);
-        if (j > 0) mbar_wait(s_free, (j - 1) & 1);   // softmax threads have drained S of block j-1
-        tc_fence_after();
-        const uint32_t aq = smem_u32(sQ), bk = smem_u32(sK + s * K_BYTES), bv = smem_u32(sV + s * V_BYTES);
-#pragma unroll
-        for (int k = 0; k < DHEAD / 16; ++k)
-          umma_bf16(tmem_base + S_COL, make_smem_desc(aq + k * 32, 0, 512, SW64), make_smem_desc(bk + k * 32, 0, 512, SW64),
-                    idesc_s, k > 0 ? 1u : 0u);
-        umma_commit(s_full);
-        mbar_wait(p_full, j & 1);                    // P_j is in smem (and O_{j-1} has been consumed)
-        tc_fence_after();
-        const uint32_t ap = smem_u32(sP);
-#pragma unroll
-        for (int k = 0; k < KB / 16; ++k)
-          umma_bf16(tmem_base + O_COL, make_smem_desc(ap + (k >> 2) * 16384 + (k & 3) * 32, 0, 1024, SW128),
-                    make_smem_desc(bv + k * 1024, 0, 512, SW64), idesc_o, k > 0 ? 1u : 0u);
-        umma_commit(o_full);
-        umma_commit(&kv_empty[s]);
-      }
-    }
-  } else {
-    // ---------------------------------------------------------------- softmax + epilogue: one thread per query row
-    const int q = warp & 3;
-    const int r = q * 32 + lane;
-    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
-    const float sc = rsqrtf((float)DHEAD) * 1.4426950408889634f;  // 1/sqrt(dh) * log2(e)
-    float m_run = -INFINITY, l_run = 0.f;
-    float o[DHEAD];
-#pragma unroll
-    for (int i = 0; i < DHEAD; ++i) o[i] = 0.f;
-    float v[32];
-    // dropout on the probabilities (DROP): the row sum keeps the undropped values, the P tile fed to the P V product is masked
-    // keep-mask words (eec_dropout_bits, W = 32): word (k/32, row) at bits[(k/32)*R + row], row = (b*H + h)*T + t, R = B*H*T
-    const uint32_t* dbits = reinterpret_cast<const uint32_t*>(drop.bits);
-    const long drow = (long)(b * H + h) * T + (q0 + r), dR = (long)gridDim.z * H * T;
-    const bool dvalid = (q0 + r) < T;
-    for (int j = 0; j < nblk; ++j) {
-      const int nvalid = min(KB, klen - j * KB);   // only the last key block can be partial
-      uint32_t dword[4] = {0u, 0u, 0u, 0u};          // this row's keep-mask words of the block: in flight while S is being computed
-      if (DROP && dvalid) {
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-          if (c * 32 < nvalid) dword[c] = dbits[(long)((j * KB) / 32 + c) * dR + drow];
-      }
-      mbar_wait(s_full, j & 1);
-      tc_fence_after();
-      // pass 1: row max (raw scores; the positive scale is applied once) over the valid keys of this block
-      float mraw = -INFINITY;
-#pragma unroll 1
-      for (int c0 = 0; c0 < KB; c0 += 32) {
-        if (c0 >= nvalid) break;               // uniform
-        tmem_ld32(trow + S_COL + c0, v);
-        if (c0 + 32 <= nvalid) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) mraw = fmaxf(mraw, v[i]);
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (c0 + i < nvalid) mraw = fmaxf(mraw, v[i]);
-        }
-      }
-      const float mx = fmaxf(m_run, mraw * sc);
-      // pass 2: p = exp2(s*sc - mx), row sum, bf16 P tile in swizzled smem
-      float psum = 0.f;
-#pragma unroll 1
-      for (int c0 = 0; c0 < KB; c0 += 32) {
-        if (c0 < nvalid) {
-          tmem_ld32(trow + S_COL + c0, v);
-          if (c0 + 32 <= nvalid) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) { v[i] = ex2_fast(fmaf(v[i], sc, -mx)); psum += v[i]; }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) { v[i] = (c0 + i < nvalid) ? ex2_fast(fmaf(v[i], sc, -mx)) : 0.f; psum += v[i]; }
-          }
-          if (DROP) drop_apply_bits<32>(v, c0 == 0 ? dword[0] : c0 == 32 ? dword[1] : c0 == 64 ? dword[2] : dword[3], drop.scale);
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = 0.f;
-        }
-        uint8_t* prow = sP + (c0 >> 6) * 16384 + r * 128;
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {  // 4 chunks of 8 keys (16 B) in this 32-key span
-          const int chunk = ((c0 & 63) >> 3) + g;
-          uint4 u;
-          __nv_bfloat162* hh = reinterpret_cast<__nv_bfloat162*>(&u);
-#pragma unroll
-          for (int e = 0; e < 4; ++e) hh[e] = __floats2bfloat162_rn(v[g * 8 + 2 * e], v[g * 8 + 2 * e + 1]);
-          *reinterpret_cast<uint4*>(prow + ((chunk ^ (r & 7)) << 4)) = u;
-        }
-      }
-      tc_fence_before();
-      mbar_arrive(s_free);
-      fence_proxy_async();
-      mbar_arrive(p_full);
-      const float corr = (m_run == -INFINITY) ? 0.f : ex2_fast(m_run - mx);
-      l_run = l_run * corr + psum;
-      m_run = mx;
-      mbar_wait(o_full, j & 1);
-      tc_fence_after();
-      tmem_ld32(trow + O_COL, v);
-#pragma unroll
-      for (int i = 0; i < DHEAD; ++i) o[i] = fmaf(o[i], corr, v[i]);
-    }
-    const int t = q0 + r;
-    if (t < T) {
-      const float inv = (l_run > 0.f) ? 1.0f / l_run : 0.f;
-      __nv_bfloat16* dst = ctx + ((long)(row0 + t)) * D + h * DHEAD;
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        float tt[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) tt[e] = o[g * 8 + e] * inv;
-        st8<__nv_bfloat16>(dst + g * 8, tt);
-      }
-      if (lse) lse[((long)b * H + h) * T + t] = (l_run > 0.f) ? (m_run + log2f(l_run)) * 0.6931471805599453f : -INFINITY;
-    }
-    tc_fence_before();
-  }
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
-  }
+// Geometry of a call (host-built).  Self-attention over the packed [rows, 3D] projection, the decoder's causal self-attention and its
+// cross-attention over the encoder states (Tq != Tk, Q and K/V in different tensors) run the same kernel: two tensor maps (Q tensor,
+// K/V tensor) and the column at which each block starts.
+struct TcGeom {
+  int Tq, Tk, H, B;
+  int q_col, k_col, v_col;          // first column of head 0 of Q (in the Q tensor) and of K / V (in the K/V tensor)
+  const int32_t* key_len;           // [B] or NULL
+  const uint32_t* key_bits;         // [B, ceil(Tk/32)] or NULL (GENERAL only)
+  int causal;                       // (GENERAL only)
+  int ldo;                          // row pitch of ctx in elements
+};
+__device__ __forceinline__ int tc_klen(const TcGeom& g, int b) { return g.key_len ? min(g.key_len[b], g.Tk) : g.Tk; }
+// key blocks an item has to visit: those holding a key < klen and, under the causal mask, a key <= the tile's last query
+__device__ __forceinline__ int tc_nblk(const TcGeom& g, int klen, int q0) {
+  int n = (klen + KB - 1) / KB;
+  if (g.causal) n = min(n, (min(q0 + QT, g.Tq) - 1) / KB + 1);
+  return n;
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// Persistent variant (EEC_ATTN_PERSIST): the kernel above lives for one (128 queries, head, utterance) item of ~3 key blocks, and the
-// ncu source view puts ~45 % of its warp-stall samples on TMEM allocation / barrier set-up / tear-down.  Here a grid of 2 CTAs per SM
-// walks the work items: one TMEM allocation and one barrier initialisation per CTA, barrier phases running on across items, and a
-// q_empty barrier so that the producer refills the Q tile only after the item's last S MMA has completed.
-template <bool DROP>
-__global__ void __launch_bounds__(AT_THREADS, 2) attn_fwd_tcp_kernel(const __grid_constant__ CUtensorMap tm_qkv,
-                                                                 const int32_t* __restrict__ key_len,
+// Persistent kernel: a CTA that lives for one (128 queries, head, utterance) item of ~3 key blocks spends ~45 % of its warp-stall
+// samples on TMEM allocation / barrier set-up / tear-down (ncu source view, round 1).  Here a grid of 2 CTAs per SM walks the work
+// items: one TMEM allocation and one barrier initialisation per CTA, barrier phases running on across items, and a q_empty barrier so
+// that the producer refills the Q tile only after the item's last S MMA has completed.
+// GENERAL adds the decoder's masks (causal, per-key validity bits) to the softmax; the encoder instantiation does not carry them.
+template <bool DROP, bool GENERAL>
+__global__ void __launch_bounds__(AT_THREADS, 2) attn_fwd_tcp_kernel(const __grid_constant__ CUtensorMap tm_q,
+                                                                 const __grid_constant__ CUtensorMap tm_kv, const TcGeom g,
                                                                  __nv_bfloat16* __restrict__ ctx, float* __restrict__ lse,
-                                                                 int T, int H, int B, const DropArgs drop, const ActiveItems act_items) {
+                                                                 const DropArgs drop, const ActiveItems act_items) {
   pdl_trigger();
   pdl_wait();
   extern __shared__ uint8_t smem_raw[];
@@ -258,15 +86,16 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_fwd_tcp_kernel(const __gri
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 10);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int D = H * DHEAD;
-  const int nqt = (T + QT - 1) / QT;
-  const int Beff = act_items.n_dev ? min(B, active_count(act_items)) : B;    // utterances past the active-item limit are not work items
+  const int H = g.H, Tq = g.Tq, Tk = g.Tk;
+  const int nqt = (Tq + QT - 1) / QT;
+  const int Beff = act_items.n_dev ? min(g.B, active_count(act_items)) : g.B;    // utterances past the active-item limit are not work items
   const int n_items = nqt * H * Beff;
   // work item w = (b * H + h) * nqt + qt, walked with a stride of gridDim.x.  Barrier phases run on across items: `it` counts the
   // items of this CTA that loaded a Q tile (nblk > 0), `jbase` the key blocks it has processed so far.
 
   if (threadIdx.x == 0) {
-    tma_prefetch_desc(&tm_qkv);
+    tma_prefetch_desc(&tm_q);
+    tma_prefetch_desc(&tm_kv);
     mbar_init(q_full, 1);
     for (int s = 0; s < KV_STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
     mbar_init(s_full, 1);
@@ -287,20 +116,19 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_fwd_tcp_kernel(const __gri
       uint32_t it = 0, jbase = 0;
       for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
         const int qt = w % nqt, bh = w / nqt, h = bh % H, b = bh / H;
-        const int q0 = qt * QT, row0 = b * T;
-        const int klen = min(key_len[b], T);
-        const int nblk = (klen + KB - 1) / KB;
+        const int q0 = qt * QT;
+        const int nblk = tc_nblk(g, tc_klen(g, b), q0);
         if (nblk == 0) continue;
         if (it > 0) mbar_wait(q_empty, (it - 1) & 1);        // the previous item's S MMAs are done with sQ
         mbar_expect_tx(q_full, Q_BYTES);
-        tma_load_2d(sQ, &tm_qkv, q_full, h * DHEAD, row0 + q0);
+        tma_load_2d(sQ, &tm_q, q_full, g.q_col + h * DHEAD, b * Tq + q0);
         for (int j = 0; j < nblk; ++j) {
           const uint32_t jb = jbase + j;
           const int s = jb % KV_STAGES;
           mbar_wait(&kv_empty[s], ((jb / KV_STAGES) & 1) ^ 1);
           mbar_expect_tx(&kv_full[s], K_BYTES + V_BYTES);
-          tma_load_2d(sK + s * K_BYTES, &tm_qkv, &kv_full[s], D + h * DHEAD, row0 + j * KB);
-          tma_load_2d(sV + s * V_BYTES, &tm_qkv, &kv_full[s], 2 * D + h * DHEAD, row0 + j * KB);
+          tma_load_2d(sK + s * K_BYTES, &tm_kv, &kv_full[s], g.k_col + h * DHEAD, b * Tk + j * KB);
+          tma_load_2d(sV + s * V_BYTES, &tm_kv, &kv_full[s], g.v_col + h * DHEAD, b * Tk + j * KB);
         }
         ++it;
         jbase += nblk;
@@ -313,8 +141,7 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_fwd_tcp_kernel(const __gri
       uint32_t it = 0, jbase = 0;
       for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
       const int b = (w / nqt) / H;
-      const int klen = min(key_len[b], T);
-      const int nblk = (klen + KB - 1) / KB;
+      const int nblk = tc_nblk(g, tc_klen(g, b), (w % nqt) * QT);
       if (nblk == 0) continue;
       mbar_wait(q_full, it & 1);
       for (int j = 0; j < nblk; ++j) {
@@ -353,9 +180,9 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_fwd_tcp_kernel(const __gri
     uint32_t jbase = 0;
     for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
     const int qt = w % nqt, bh = w / nqt, h = bh % H, b = bh / H;
-    const int q0 = qt * QT, row0 = b * T;
-    const int klen = min(key_len[b], T);
-    const int nblk = (klen + KB - 1) / KB;
+    const int q0 = qt * QT;
+    const int klen = tc_klen(g, b);
+    const int nblk = tc_nblk(g, klen, q0);
     float m_run = -INFINITY, l_run = 0.f;
     float o[DHEAD];
 #pragma unroll
@@ -364,8 +191,9 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_fwd_tcp_kernel(const __gri
     // dropout on the probabilities (DROP): the row sum keeps the undropped values, the P tile fed to the P V product is masked
     // keep-mask words (eec_dropout_bits, W = 32): word (k/32, row) at bits[(k/32)*R + row], row = (b*H + h)*T + t, R = B*H*T
     const uint32_t* dbits = reinterpret_cast<const uint32_t*>(drop.bits);
-    const long drow = (long)(b * H + h) * T + (q0 + r), dR = (long)B * H * T;
-    const bool dvalid = (q0 + r) < T;
+    const long drow = (long)(b * H + h) * Tq + (q0 + r), dR = (long)g.B * H * Tq;
+    const bool dvalid = (q0 + r) < Tq;
+    const uint32_t* kbits = GENERAL && g.key_bits ? g.key_bits + (long)b * ((Tk + 31) >> 5) : nullptr;
     for (int j = 0; j < nblk; ++j) {
       const int nvalid = min(KB, klen - j * KB);   // only the last key block can be partial
       uint32_t dword[4] = {0u, 0u, 0u, 0u};          // this row's keep-mask words of the block: in flight while S is being computed
@@ -375,6 +203,21 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_fwd_tcp_kernel(const __gri
           if (c * 32 < nvalid) dword[c] = dbits[(long)((j * KB) / 32 + c) * dR + drow];
       }
       const uint32_t jb = jbase + j;
+      // GENERAL: visibility word of this row for each 32-key span of the block (length, causal and per-key validity masks)
+      uint32_t vis[4] = {~0u, ~0u, ~0u, ~0u};
+      if (GENERAL) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int base = j * KB + c * 32;
+          uint32_t mk = (base + 32 <= klen) ? ~0u : (base >= klen ? 0u : ((1u << (klen - base)) - 1u));
+          if (g.causal) {
+            const int lim = q0 + r - base;        // key base + i is visible iff i <= lim
+            mk &= lim >= 31 ? ~0u : (lim < 0 ? 0u : ((2u << lim) - 1u));
+          }
+          if (kbits && base < Tk) mk &= kbits[base >> 5];
+          vis[c] = mk;
+        }
+      }
       mbar_wait(s_full, jb & 1);
       tc_fence_after();
       // pass 1: row max (raw scores; the positive scale is applied once) over the valid keys of this block
@@ -383,7 +226,12 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_fwd_tcp_kernel(const __gri
       for (int c0 = 0; c0 < KB; c0 += 32) {
         if (c0 >= nvalid) break;               // uniform
         tmem_ld32(trow + S_COL + c0, v);
-        if (c0 + 32 <= nvalid) {
+        if (GENERAL) {
+          const uint32_t mk = c0 == 0 ? vis[0] : c0 == 32 ? vis[1] : c0 == 64 ? vis[2] : vis[3];
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if ((mk >> i) & 1u) mraw = fmaxf(mraw, v[i]);
+        } else if (c0 + 32 <= nvalid) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) mraw = fmaxf(mraw, v[i]);
         } else {
@@ -399,7 +247,11 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_fwd_tcp_kernel(const __gri
       for (int c0 = 0; c0 < KB; c0 += 32) {
         if (c0 < nvalid) {
           tmem_ld32(trow + S_COL + c0, v);
-          if (c0 + 32 <= nvalid) {
+          if (GENERAL) {
+            const uint32_t mk = c0 == 0 ? vis[0] : c0 == 32 ? vis[1] : c0 == 64 ? vis[2] : vis[3];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) { v[i] = ((mk >> i) & 1u) ? ex2_fast(fmaf(v[i], sc, -mx)) : 0.f; psum += v[i]; }
+          } else if (c0 + 32 <= nvalid) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) { v[i] = ex2_fast(fmaf(v[i], sc, -mx)); psum += v[i]; }
           } else {
@@ -413,12 +265,12 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_fwd_tcp_kernel(const __gri
         }
         uint8_t* prow = sP + (c0 >> 6) * 16384 + r * 128;
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {  // 4 chunks of 8 keys (16 B) in this 32-key span
-          const int chunk = ((c0 & 63) >> 3) + g;
+        for (int gg = 0; gg < 4; ++gg) {  // 4 chunks of 8 keys (16 B) in this 32-key span
+          const int chunk = ((c0 & 63) >> 3) + gg;
           uint4 u;
           __nv_bfloat162* hh = reinterpret_cast<__nv_bfloat162*>(&u);
 #pragma unroll
-          for (int e = 0; e < 4; ++e) hh[e] = __floats2bfloat162_rn(v[g * 8 + 2 * e], v[g * 8 + 2 * e + 1]);
+          for (int e = 0; e < 4; ++e) hh[e] = __floats2bfloat162_rn(v[gg * 8 + 2 * e], v[gg * 8 + 2 * e + 1]);
           *reinterpret_cast<uint4*>(prow + ((chunk ^ (r & 7)) << 4)) = u;
         }
       }
@@ -436,17 +288,17 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_fwd_tcp_kernel(const __gri
       for (int i = 0; i < DHEAD; ++i) o[i] = fmaf(o[i], corr, v[i]);
     }
     const int t = q0 + r;
-    if (t < T) {
+    if (t < Tq) {
       const float inv = (l_run > 0.f) ? 1.0f / l_run : 0.f;
-      __nv_bfloat16* dst = ctx + ((long)(row0 + t)) * D + h * DHEAD;
+      __nv_bfloat16* dst = ctx + ((long)b * Tq + t) * g.ldo + h * DHEAD;
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
+      for (int gg = 0; gg < 4; ++gg) {
         float tt[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) tt[e] = o[g * 8 + e] * inv;
-        st8<__nv_bfloat16>(dst + g * 8, tt);
+        for (int e = 0; e < 8; ++e) tt[e] = o[gg * 8 + e] * inv;
+        st8<__nv_bfloat16>(dst + gg * 8, tt);
       }
-      if (lse) lse[((long)b * H + h) * T + t] = (l_run > 0.f) ? (m_run + log2f(l_run)) * 0.6931471805599453f : -INFINITY;
+      if (lse) lse[((long)b * H + h) * Tq + t] = (l_run > 0.f) ? (m_run + log2f(l_run)) * 0.6931471805599453f : -INFINITY;
     }
     jbase += nblk;
     }
@@ -459,6 +311,26 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_fwd_tcp_kernel(const __gri
   }
 }
 
+static int fwd_launch(const CUtensorMap& tq, const CUtensorMap& tkv, const TcGeom& g, void* ctx, float* lse, const DropArgs& drop,
+                      bool general, cudaStream_t st) {
+  static bool attr_set = false;
+  static int sms = 0;
+  if (!attr_set) {
+    EEC_CUDA(cudaFuncSetAttribute(attn_fwd_tcp_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
+    EEC_CUDA(cudaFuncSetAttribute(attn_fwd_tcp_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
+    EEC_CUDA(cudaFuncSetAttribute(attn_fwd_tcp_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 148;
+    attr_set = true;
+  }
+  const int items = cdiv(g.Tq, QT) * g.H * g.B;
+  const dim3 pgrid(min(items, 2 * sms));
+  if (general) launch_pdl(attn_fwd_tcp_kernel<false, true>, pgrid, dim3(AT_THREADS), AT_SMEM, st, tq, tkv, g, (__nv_bfloat16*)ctx, lse, drop, active_items(st));
+  else if (drop.state) launch_pdl(attn_fwd_tcp_kernel<true, false>, pgrid, dim3(AT_THREADS), AT_SMEM, st, tq, tkv, g, (__nv_bfloat16*)ctx, lse, drop, active_items(st));
+  else launch_pdl(attn_fwd_tcp_kernel<false, false>, pgrid, dim3(AT_THREADS), AT_SMEM, st, tq, tkv, g, (__nv_bfloat16*)ctx, lse, drop, active_items(st));
+  EEC_LAUNCH_CHECK();
+  return 0;
+}
 
 }  // namespace
 
@@ -466,38 +338,42 @@ int attn_fwd_tc(const void* qkv, const int32_t* key_len, void* ctx, float* lse, 
                 cudaStream_t st) {
   EEC_CHECK_ARG(dh == DHEAD, "attn_fwd_tc: head dim must be 32");
   CUtensorMap tm;
-  const int D3 = 3 * H * dh;
+  const int D = H * dh, D3 = 3 * D;
   if (int r = get_tmap_2d(&tm, qkv, (uint64_t)D3, (uint64_t)B * T, (uint64_t)D3 * 2, DHEAD, 128, /*SWIZZLE_64B*/ 2)) return r;
-  static bool attr_set = false;
-  if (!attr_set) {
-    EEC_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
-    EEC_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
-    attr_set = true;
-  }
-  dim3 grid(cdiv(T, QT), H, B);
-  static int persist = -1;
-  if (persist < 0) { const char* e = getenv("EEC_ATTN_PERSIST"); persist = (e && e[0] == '0') ? 0 : 1; }   // persistent CTAs (default; 0 = one CTA per work item)
-  if (persist) {
-    static bool attrp = false;
-    static int sms = 0;
-    if (!attrp) {
-      EEC_CUDA(cudaFuncSetAttribute(attn_fwd_tcp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
-      EEC_CUDA(cudaFuncSetAttribute(attn_fwd_tcp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
-      int dev = 0;
-      if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 148;
-      attrp = true;
-    }
-    const int items = cdiv(T, QT) * H * B;
-    const dim3 pgrid(min(items, 2 * sms));
-    if (drop.state) launch_pdl(attn_fwd_tcp_kernel<true>, pgrid, dim3(AT_THREADS), AT_SMEM, st, tm, key_len, (__nv_bfloat16*)ctx, lse, T, H, B, drop, active_items(st));
-    else launch_pdl(attn_fwd_tcp_kernel<false>, pgrid, dim3(AT_THREADS), AT_SMEM, st, tm, key_len, (__nv_bfloat16*)ctx, lse, T, H, B, drop, active_items(st));
-    EEC_LAUNCH_CHECK();
-    return 0;
-  }
-  if (drop.state) launch_pdl(attn_fwd_tc_kernel<true>, dim3(grid), dim3(AT_THREADS), AT_SMEM, st, tm, key_len, (__nv_bfloat16*)ctx, lse, T, H, drop, active_items(st));
-  else launch_pdl(attn_fwd_tc_kernel<false>, dim3(grid), dim3(AT_THREADS), AT_SMEM, st, tm, key_len, (__nv_bfloat16*)ctx, lse, T, H, drop, active_items(st));
-  EEC_LAUNCH_CHECK();
+  TcGeom g{};
+  g.Tq = g.Tk = T; g.H = H; g.B = B; g.q_col = 0; g.k_col = D; g.v_col = 2 * D; g.key_len = key_len; g.ldo = D;
+  return fwd_launch(tm, tm, g, ctx, lse, drop, false, st);
+}
+
+// The decoder's attention on the tensor cores needs K and V in ONE row-major tensor (a packed projection output) and 16-byte aligned rows
+bool attn_general_tc_ok(const eec_attn_desc* d) {
+  const uintptr_t q = (uintptr_t)d->q, k = (uintptr_t)d->k, v = (uintptr_t)d->v;
+  const uintptr_t lo = k < v ? k : v, hi = k < v ? v : k;
+  return d->dh == DHEAD && d->ldk == d->ldv && (hi - lo) < (uintptr_t)d->ldk * 2 && (hi - lo) % 2 == 0 && (q % 16) == 0 && (lo % 16) == 0 &&
+         ((hi - lo) % 16) == 0 && (d->ldq % 8) == 0 && (d->ldk % 8) == 0 && d->H * d->dh <= d->ldq;
+}
+
+static int general_geom(const eec_attn_desc* d, TcGeom& g, CUtensorMap& tq, CUtensorMap& tkv) {
+  const uintptr_t k = (uintptr_t)d->k, v = (uintptr_t)d->v;
+  const void* kv_base = k < v ? d->k : d->v;
+  g.Tq = d->Tq; g.Tk = d->Tk; g.H = d->H; g.B = d->B;
+  g.q_col = 0; g.k_col = (int)((k - (uintptr_t)kv_base) / 2); g.v_col = (int)((v - (uintptr_t)kv_base) / 2);
+  g.key_len = d->key_len; g.key_bits = d->key_valid_bits; g.causal = d->causal;
+  // the maps start at the given pointers (a column offset inside a wider packed tensor): [H*dh (+ the K/V column distance) columns, rows]
+  // with the wide tensor's row pitch
+  if (int r = get_tmap_2d(&tq, d->q, (uint64_t)d->H * d->dh, (uint64_t)d->B * d->Tq, (uint64_t)d->ldq * 2, DHEAD, 128, 2)) return r;
+  const uint64_t kv_cols = (uint64_t)(g.k_col > g.v_col ? g.k_col : g.v_col) + (uint64_t)d->H * d->dh;
+  if (int r = get_tmap_2d(&tkv, kv_base, kv_cols, (uint64_t)d->B * d->Tk, (uint64_t)d->ldk * 2, DHEAD, 128, 2)) return r;
   return 0;
+}
+
+int attn_general_fwd_tc(const eec_attn_desc* d, void* ctx, int ldo, float* lse, cudaStream_t st) {
+  TcGeom g{};
+  CUtensorMap tq, tkv;
+  if (int r = general_geom(d, g, tq, tkv)) return r;
+  g.ldo = ldo;
+  DropArgs drop{};
+  return fwd_launch(tq, tkv, g, ctx, lse, drop, true, st);
 }
 
 }  // namespace eec

@@ -105,6 +105,10 @@ __global__ void __launch_bounds__(NT) gemm_simt_kernel(SimtParams p) {
         float h = ld_as_float<TPre>(P + (long)m * p.ldp + n);
         float s = ACC ? sigmoid_acc(h) : sigmoidf_(h);
         v *= s * (1.0f + h * (1.0f - s));
+      } else if (p.act == EEC_ACT_RELU) {
+        v = fmaxf(v, 0.f);
+      } else if (p.act == EEC_ACT_DRELU) {
+        v = ld_as_float<TPre>(P + (long)m * p.ldp + n) > 0.f ? v : 0.f;     // P = the forward's activation output relu(h)
       }
       if (p.drop.state) v *= df[j];
       v *= p.alpha;
@@ -157,7 +161,7 @@ int gemm_simt(const eec_gemm_desc* d, cudaStream_t st) {
     p.act = EEC_ACT_NONE; p.C = d->preact; p.ldc = d->ldp; p.alpha = 1.f; p.preact = nullptr;
     out_dtype = d->preact_dtype;
   }
-  if (p.act == EEC_ACT_DSILU) EEC_CHECK_ARG(d->preact != nullptr, "gemm: DSILU needs preact");
+  if (p.act == EEC_ACT_DSILU || p.act == EEC_ACT_DRELU) EEC_CHECK_ARG(d->preact != nullptr, "gemm: DSILU / DRELU need preact");
   if (d->accumulate) EEC_CHECK_ARG(d->out_dtype == EEC_F32, "gemm: accumulate needs fp32 C");
   p.drop = make_drop(d->drop_state, d->drop_p, d->drop_site);
   p.act_items = d->a_kmajor ? active_items(st) : ActiveItems{nullptr, 0, 0};   // (rows of A are frames only in the K-major forward form)

@@ -453,7 +453,8 @@ int gemm_tc2(const eec_gemm_desc* d, cudaStream_t st, int32_t* argmax, float* en
     EEC_CHECK_ARG(d->N % 256 == 0 && d->b_kmajor && d->a_kmajor, "gemm_tc2: GLU needs N %% 256 == 0 and K-major operands");
     EEC_CHECK_ARG(!d->residual && !d->accumulate, "gemm_tc2: GLU with residual/accumulate unsupported");
   }
-  if (d->act == EEC_ACT_DSILU) EEC_CHECK_ARG(d->preact != nullptr && d->preact_dtype == EEC_BF16, "gemm_tc2: DSILU needs a bf16 preact");
+  if (d->act == EEC_ACT_DSILU || d->act == EEC_ACT_DRELU) EEC_CHECK_ARG(d->preact != nullptr && d->preact_dtype == EEC_BF16, "gemm_tc2: DSILU / DRELU need a bf16 preact");
+  if (d->act == EEC_ACT_RELU || d->act == EEC_ACT_DRELU) EEC_CHECK_ARG(d->out_dtype == EEC_BF16 && !d->accumulate, "gemm (tcgen05): RELU / DRELU epilogues write bf16, no accumulate");
   if (d->act == EEC_ACT_SILU && d->preact) EEC_CHECK_ARG(d->preact_dtype == EEC_BF16, "gemm_tc2: preact store must be bf16");
   if (d->accumulate) EEC_CHECK_ARG(d->out_dtype == EEC_F32 && d->act == EEC_ACT_NONE, "gemm_tc2: accumulate needs fp32 C, no act");
 
@@ -462,7 +463,7 @@ int gemm_tc2(const eec_gemm_desc* d, cudaStream_t st, int32_t* argmax, float* en
     static int v2_env = -1;
     if (v2_env < 0) { const char* e = getenv("EEC_GEMM_V2"); v2_env = (e && e[0] == '1') ? 1 : 0; }
     // (v3 stages dSiLU / SiLU+pre-activation outputs in bf16 boxes only; the fp32-output variants of those stay here)
-    const bool v3_ok = d->out_dtype == EEC_BF16 || !(d->act == EEC_ACT_DSILU || (d->act == EEC_ACT_SILU && d->preact));
+    const bool v3_ok = d->out_dtype == EEC_BF16 || !(d->act == EEC_ACT_DSILU || d->act == EEC_ACT_DRELU || (d->act == EEC_ACT_SILU && d->preact));
     if (!v2_env && v3_ok && (epi == EPI_GENERIC || epi == EPI_GLU)) return gemm_tc3(d, st);
     if (!v2_env && epi == EPI_LN && d->res_row_mod == 0 && (!d->residual || d->ldr == 256)) return gemm_ln3(d, st);
   }

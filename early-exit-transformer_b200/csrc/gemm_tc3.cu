@@ -176,6 +176,23 @@ __device__ __forceinline__ void mul_dsilu16(float (&x)[16], const uint8_t* box, 
   }
 }
 
+// backward of ReLU through the activation OUTPUT a = relu(h) (a > 0 <=> h > 0): x = alpha * x * [a > 0]
+__device__ __forceinline__ void mul_drelu16(float (&x)[16], const uint8_t* box, int half, int lane, float alpha) {
+  const uint8_t* row = box + lane * 64;
+  const int sw = (lane >> 1) & 3;
+#pragma unroll
+  for (int cc = 0; cc < 2; ++cc) {
+    const uint4 u = *reinterpret_cast<const uint4*>(row + (((half * 2 + cc) ^ sw) << 4));
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 a = __bfloat1622float2(h[e]);
+      x[cc * 8 + 2 * e] = a.x > 0.f ? x[cc * 8 + 2 * e] * alpha : 0.f;
+      x[cc * 8 + 2 * e + 1] = a.y > 0.f ? x[cc * 8 + 2 * e + 1] * alpha : 0.f;
+    }
+  }
+}
+
 // work unit u = split * (m_tiles * n_tiles) + mt * n_tiles + nt, walked with a stride of gridDim.x units
 struct UnitIter {
   int u, mt, nt, split;
@@ -424,7 +441,8 @@ __global__ void __launch_bounds__(NT3, 1) gemm_tc3_kernel(const __grid_constant_
         const int cb = cg * 64;
         const int nb = n0 + cb;
         const int nslab = (nb + 32 < p.N) ? 2 : (nb < p.N) ? 1 : 0;   // warp-uniform
-        const bool dsilu = p.act == EEC_ACT_DSILU, silu = p.act == EEC_ACT_SILU;
+        const bool drelu = p.act == EEC_ACT_DRELU, relu = p.act == EEC_ACT_RELU;
+        const bool dsilu = p.act == EEC_ACT_DSILU || drelu, silu = p.act == EEC_ACT_SILU;   // (dsilu: "multiply by a TMA-loaded box" data flow)
         if (dsilu && nslab) {
           // pre-activation boxes of both slabs: in flight while the main loop of this tile runs
           if (lane == 0) {
@@ -553,7 +571,11 @@ __global__ void __launch_bounds__(NT3, 1) gemm_tc3_kernel(const __grid_constant_
               mbar_wait(lbar, lphase);
               lphase ^= 1;
             }
-            mul_dsilu16(x, st.buf + sl * 2048, half, lane, p.alpha);   // (alpha folded in)
+            if (drelu) mul_drelu16(x, st.buf + sl * 2048, half, lane, p.alpha);
+            else mul_dsilu16(x, st.buf + sl * 2048, half, lane, p.alpha);   // (alpha folded in)
+          } else if (relu) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) x[j] = fmaxf(x[j], 0.f);
           }
           if (DROP) drop_apply_bits<16>(x, (dw[ss >> 1] >> ((ss & 1) * 16)) & 0xffffu, p.drop.scale);
           if (p.alpha != 1.0f && !dsilu) {
@@ -942,7 +964,7 @@ int gemm_tc3(const eec_gemm_desc* d, cudaStream_t st) {
   else if (int r = get_tmap_box32(&tcm, d->C, out_bf16, (uint64_t)n_out, (uint64_t)d->M, (uint64_t)d->ldc)) return r;
   const bool store_pre = d->preact && (d->act == EEC_ACT_SILU || epi == EPI_GLU);
   tpm = tcm;
-  if (store_pre || d->act == EEC_ACT_DSILU) {
+  if (store_pre || d->act == EEC_ACT_DSILU || d->act == EEC_ACT_DRELU) {
     if (int r = get_tmap_box32(&tpm, d->preact, true, (uint64_t)d->N, (uint64_t)d->M, (uint64_t)d->ldp)) return r;
   }
   P3 p{};

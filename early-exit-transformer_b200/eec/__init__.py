@@ -9,4 +9,5 @@ from .aed import full_conformer  # noqa: F401
 from .graph import GraphedEarlyExit, GraphedForward, GraphedTrainStep  # noqa: F401
 from .optim import FusedNoamAdamW  # noqa: F401
 from .features import Fbank  # noqa: F401
-from . import distributed  # noqa: F401,E402
+from .decoder import CUCTCDecoder, CUCTCHypothesis, ctc_cuda_predict, cuda_ctc_decoder  # noqa: F401
+from . import batching, distributed  # noqa: F401,E402

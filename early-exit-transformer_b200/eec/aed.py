@@ -1,11 +1,12 @@
 """``full_conformer`` (reference early_exit.py:637-811): the AED-mode model of BASELINE configs[4].
 
-SURVEY §8 row a17 puts the ENCODER half on the hot path: front end, positional encoding, the six Conformer groups
-and the ``linears_1`` CTC heads are the same arithmetic as ``Early_conformer`` and run on the sm_100a kernels; the
-per-exit encoder states additionally leave the engine (fp32, [E,B,T',256]) because the attention decoders consume
-them, and their gradient flows back into the engine's backward pass.  The six ``nn.TransformerDecoder`` stacks,
-``linears_2`` and the embedding are row N4 ("next"): they stay the same torch.nn library modules the reference
-instantiates (early_exit.py:701-717), called exactly as the reference calls them (:742-762, :772-798).
+Encoder half: front end, positional encoding, the six Conformer groups and the ``linears_1`` CTC heads are the
+same arithmetic as ``Early_conformer`` and run on the sm_100a kernels through ``eec.engine``; the per-exit encoder states leave the
+engine (fp32, [E,B,T',256]) for the decoders, and their gradient flows back into the engine's backward pass.
+Decoder half (row N4): embedding + positional encoding, the six pre-norm ``nn.TransformerDecoder`` stacks (causal self-attention with
+the target padding mask, cross-attention over the encoder states, ReLU feed-forward, ONE shared final LayerNorm) and ``linears_2`` run
+on the same kernels through ``eec.decoder_engine``.  The torch.nn modules below are parameter containers only (same construction order
+as early_exit.py:667-717, so default init under a seed and the state_dict layout are the reference's); they are never called.
 
 Same constructor signature, ``forward(src, lengths, trg) -> (dec_out (E,B,L,V) logits, enc_out (E,B,T',V) log-probs)``,
 ``_encoder_(src, lengths, layer_n)`` / ``_decoder_(trg, enc, layer_n)`` (used by the reference's AED beam search,
@@ -19,8 +20,9 @@ from typing import Dict, List
 import torch
 from torch import nn
 
-from . import engine
+from . import decoder_engine, engine, ops
 from .early_exit import Conformer, Conv1dSubampling, PositionalEncoding, _EarlyExitBase, _EncoderFn
+from .lib import EecError, on_device
 
 Tensor = torch.Tensor
 
@@ -34,6 +36,32 @@ def _engine_name(name: str) -> str:
         if name.startswith(a):
             return b + name[len(a):]
     return name
+
+
+class _DecoderFn(torch.autograd.Function):
+    """forward(module, want_tape, cfg, exits, mem_index, trg, hidden, *decoder params) -> logits [len(exits), B, L, V]"""
+
+    @staticmethod
+    def forward(ctx, module, want_tape, cfg, exits, mem_index, trg, hidden, *params):
+        P = module._decoder_tensor_dict()
+        with on_device(hidden.device):
+            out, tape = decoder_engine.decoder_forward(P, module._dec_operands, cfg, module.n_dec_layers, trg.to(hidden.device),
+                                                       module.trg_pad_idx, hidden.contiguous(), exits, mem_index, want_tape)
+        ctx.module, ctx.tape, ctx.P, ctx.cfg, ctx.hshape = module, tape, P, cfg, tuple(hidden.shape)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        m = ctx.module
+        if ctx.tape is None:
+            raise NotImplementedError("eec: decoder backward needs train() mode with grad enabled")
+        names = m._decoder_param_names
+        ghid = torch.zeros(ctx.hshape, dtype=torch.float32, device=gout.device)
+        with on_device(gout.device):
+            G = decoder_engine.decoder_backward(ctx.P, m._dec_operands, ctx.cfg, ctx.tape, gout, names, ghid)
+        ctx.tape = None
+        m.__dict__["_flat_grad_decoder"] = G["__flat__"]
+        return (None, None, None, None, None, None, ghid) + tuple(G[n] for n in names)
 
 
 class full_conformer(_EarlyExitBase):
@@ -92,6 +120,39 @@ class full_conformer(_EarlyExitBase):
         d.update({_engine_name(n): b for n, b in self.named_buffers() if n.startswith(_ENCODER_PREFIXES)})
         return d
 
+    # ---- the decoder half, as eec.decoder_engine sees it -------------------------------------------------------------------------
+    @property
+    def _decoder_param_names(self) -> List[str]:
+        return [n for n, _ in self.named_parameters() if not n.startswith(_ENCODER_PREFIXES)]
+
+    def _decoder_tensor_dict(self) -> Dict[str, Tensor]:
+        d = {n: p for n, p in self.named_parameters() if not n.startswith(_ENCODER_PREFIXES)}
+        d["positional_encoder_2.pe"] = self.positional_encoder_2.pe
+        return d
+
+    @property
+    def _dec_operands(self) -> engine.Operands:
+        ob = self.__dict__.get("_dec_operands_obj")
+        if ob is None or ob.cfg.precision != self.precision:
+            ob = engine.Operands(self._cfg())
+            self.__dict__["_dec_operands_obj"] = ob
+        return ob
+
+    def _decode(self, trg: Tensor, hidden: Tensor, exits: List[int], mem_index: List[int]) -> Tensor:
+        """decoder stacks `exits` (0-based), stack exits[i] attending to hidden[mem_index[i]] -> logits [len(exits), B, L, V]"""
+        self._check_supported()
+        if self.training and float(self.dropout) > 0.0:
+            raise EecError("eec.full_conformer: train-mode dropout inside the decoder stacks is not implemented yet (the encoder half "
+                           "supports it): build the model with drop_prob=0 for AED training, or call .eval()")
+        names = self._decoder_param_names
+        expect = decoder_engine.decoder_param_names(self.n_enc_exits, self.n_dec_layers)
+        if names != expect:
+            raise EecError("eec.full_conformer: unexpected decoder parameter layout")
+        P = dict(self.named_parameters())
+        params = [P[n] for n in names]
+        want_tape = self.training and torch.is_grad_enabled() and (hidden.requires_grad or any(p.requires_grad for p in params))
+        return _DecoderFn.apply(self, want_tape, self._cfg(), list(exits), list(mem_index), trg, hidden, *params)
+
     def _encode(self, src: Tensor, lengths: Tensor, n_exits: int):
         """-> (enc_out [n_exits,B,T',V] log-probs, hidden [n_exits,B,T',D]) for the first `n_exits` groups."""
         self._check_supported()
@@ -109,33 +170,20 @@ class full_conformer(_EarlyExitBase):
         return hidden[n - 1]
 
     def _decoder_(self, trg: Tensor, enc: Tensor, layer_n: int) -> Tensor:
-        """early_exit.py:739-762 (torch.nn decoder stack `layer_n`, log-softmax output)."""
-        dev = enc.device
-        tgt_mask = self.create_tgt_mask(trg.size(1)).to(dev)
-        tgt_key_padding_mask = self.create_pad_mask(trg, self.trg_pad_idx).to(dev)
-        trg = self.emb(trg)
-        trg = self._pos2(trg)
+        """early_exit.py:739-762: decoder stack `layer_n` (1-based) on the encoder state `enc` (B, T', D), log-softmax output."""
         i = (int(layer_n) if 1 <= int(layer_n) <= self.n_enc_exits else self.n_enc_exits) - 1   # (:751-755: same loop quirk)
-        out_d = self.decoders[i](trg, enc, tgt_mask=tgt_mask, tgt_key_padding_mask=tgt_key_padding_mask)
-        return torch.nn.functional.log_softmax(self.linears_2[i](out_d), dim=2)
-
-    def _pos2(self, x: Tensor) -> Tensor:
-        # positional_encoding.py:65-73 on a batch-first (B, L, D) tensor: permute -> + pe[:L] -> permute back -> dropout
-        pe = self.positional_encoder_2
-        return pe.dropout(x + pe.pe[: x.size(1), 0, :].unsqueeze(0))
+        logits = self._decode(trg, enc.unsqueeze(0), [i], [0])[0]
+        B, Ln, Vv = logits.shape
+        out = torch.empty_like(logits)
+        with on_device(logits.device):
+            ops.call("eec_logsoftmax_fwd", ops.ptr(logits.contiguous()), ops.ptr(out), None, None, B * Ln, Vv, ops.stream())
+        return out
 
     def forward(self, src: Tensor, lengths: Tensor, trg: Tensor):
         """early_exit.py:764-800 -> (dec_out [E,B,L,V] logits, enc_out [E,B,T',V] log-probs)."""
         enc_out, hidden = self._encode(src, lengths, self.n_enc_exits)
-        dev = hidden.device
-        tgt_mask = self.create_tgt_mask(trg.size(1)).to(dev)
-        tgt_key_padding_mask = self.create_pad_mask(trg, self.trg_pad_idx).to(dev)
-        t = self._pos2(self.emb(trg))
-        dec_out = []
-        for e, (linear_2, decoder) in enumerate(zip(self.linears_2, self.decoders)):
-            out_d = decoder(t, hidden[e], tgt_mask=tgt_mask, tgt_key_padding_mask=tgt_key_padding_mask)
-            dec_out.append(linear_2(out_d).unsqueeze(0))
-        return torch.cat(dec_out), enc_out
+        idx = list(range(self.n_enc_exits))
+        return self._decode(trg, hidden, idx, idx), enc_out
 
     def create_pad_mask(self, matrix: Tensor, pad_token: int) -> Tensor:
         return matrix == pad_token

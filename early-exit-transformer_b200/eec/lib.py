@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("EEC_LIB") or os.path.join(_HERE, "libeec.so")   # EEC_LIB: A/B-test another build of the same ABI
 
 F32, BF16 = 0, 1
-ACT_NONE, ACT_SILU, ACT_GLU, ACT_DSILU = 0, 1, 2, 3
+ACT_NONE, ACT_SILU, ACT_GLU, ACT_DSILU, ACT_RELU, ACT_DRELU = 0, 1, 2, 3, 4, 5
 
 vp, i32, i64, f32, u32 = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_uint32
 
@@ -43,6 +43,19 @@ class GemmDesc(C.Structure):
     ]
 
 
+class AttnDesc(C.Structure):
+    _fields_ = [
+        ("B", i32), ("H", i32), ("dh", i32), ("Tq", i32), ("Tk", i32),
+        ("q", vp), ("ldq", i32),
+        ("k", vp), ("ldk", i32),
+        ("v", vp), ("ldv", i32),
+        ("dtype", i32),
+        ("key_len", vp),
+        ("key_valid_bits", vp),
+        ("causal", i32),
+    ]
+
+
 # name -> argtypes (stream last); every function returns int unless noted
 _SIGS = {
     "eec_gemm": [C.POINTER(GemmDesc), vp],
@@ -50,6 +63,12 @@ _SIGS = {
     "eec_layernorm_bwd": [vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, i32, vp, f32, vp, f32, u32, i32, i32, vp],
     "eec_attn_fwd": [vp, i32, vp, vp, vp, i32, i32, i32, i32, vp, f32, u32, vp, vp],
     "eec_attn_bwd": [vp, vp, vp, i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp, f32, u32, vp, vp],
+    "eec_attn_general_fwd": [C.POINTER(AttnDesc), vp, i32, vp, vp],
+    "eec_attn_general_bwd": [C.POINTER(AttnDesc), vp, vp, i32, vp, vp, i32, vp, i32, vp, i32, vp, vp, vp],
+    "eec_key_bits_from_tokens": [vp, i32, i32, i64, vp, vp],
+    "eec_embed_pe": [vp, vp, vp, vp, i32, i32, i32, i32, vp],
+    "eec_embed_bwd": [vp, vp, vp, i32, i32, i32, i32, vp],
+    "eec_cross_entropy": [vp, vp, i32, i32, vp, vp, vp],
     "eec_dropout_bits": [vp, f32, u32, i64, i32, i64, i32, vp, vp],
     "eec_dropout": [vp, i32, vp, i32, i64, vp, f32, u32, vp],
     "eec_dropout_advance": [vp, vp],
@@ -65,6 +84,7 @@ _SIGS = {
     "eec_head_logsoftmax": [vp, i32, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp],
     "eec_ctc_fwd_bwd": [vp, vp, vp, i32, i32, i32, i32, i32, i32, f32, vp, vp, vp, vp, vp],
     "eec_greedy_collapse": [vp, vp, vp, i32, i32, i32, vp],
+    "eec_ctc_beam_search": [vp, vp, i32, i32, i32, i32, i32, i32, f32, vp, vp, vp, vp, vp],
     "eec_im2col_k3s2": [vp, i32, i64, i64, i64, vp, i32, i32, i32, i32, i32, vp],
     "eec_col2im_k3s2": [vp, i32, vp, i32, i32, i32, i32, vp],
     "eec_encoder_lengths": [vp, vp, i32, i32, i32, i32, vp],
@@ -89,7 +109,7 @@ _SIGS = {
     "eec_stride2_scatter_add": [vp, vp, i32, i32, i32, vp],
 }
 EXPORTS = sorted(list(_SIGS) + ["eec_last_error", "eec_version", "eec_device_ok", "eec_ctc_workspace_bytes", "eec_dwconv_bwd_workspace_bytes",
-                             "eec_launch_count"])
+                             "eec_launch_count", "eec_ctc_beam_workspace_bytes"])
 
 # entry points of eec/libeec_exp.so only (`make experiments`, include/eec_experiments.h): bound when the loaded library has them
 _SIGS_EXPERIMENTAL = {
@@ -131,6 +151,8 @@ def load():
     lib.eec_launch_count.argtypes = []
     lib.eec_ctc_workspace_bytes.restype = i64
     lib.eec_ctc_workspace_bytes.argtypes = [i32, i32, i32, i32]
+    lib.eec_ctc_beam_workspace_bytes.restype = i64
+    lib.eec_ctc_beam_workspace_bytes.argtypes = [i32, i32, i32]
     lib.eec_dwconv_bwd_workspace_bytes.restype = i64
     lib.eec_dwconv_bwd_workspace_bytes.argtypes = [i32, i32, i32]
     _lib = lib

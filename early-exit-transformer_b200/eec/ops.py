@@ -9,7 +9,7 @@ from typing import Optional
 import torch
 
 from . import lib as L
-from .lib import ACT_DSILU, ACT_GLU, ACT_NONE, ACT_SILU, BF16, F32, call, dt, ptr, stream
+from .lib import ACT_DRELU, ACT_DSILU, ACT_GLU, ACT_NONE, ACT_RELU, ACT_SILU, BF16, F32, call, dt, ptr, stream
 
 Tensor = torch.Tensor
 
@@ -150,6 +150,62 @@ def attn_bwd(qkv, ctx, dctx, lse, key_len, dqkv, dvec, B, T, H, dq32=None, drop:
          H, 32, *_d(drop), _bits(drop), stream())
 
 
+def _attn_desc(q, k, v, B, Tq, Tk, H, key_len, key_bits, causal):
+    """q / k / v: 2-D views (rows, H*32) of row-major tensors -- a column block of a packed projection output is passed as its slice"""
+    for t, n in ((q, "q"), (k, "k"), (v, "v")):
+        if not t.is_cuda or t.dim() != 2 or t.stride(1) != 1:
+            raise L.EecError(f"attn.{n}: expected a 2-D CUDA view with unit column stride")
+    if not (q.dtype == k.dtype == v.dtype):
+        raise L.EecError("attn: q / k / v dtypes differ")
+    d = L.AttnDesc()
+    d.B, d.H, d.dh, d.Tq, d.Tk = B, H, 32, Tq, Tk
+    d.q, d.ldq = q.data_ptr(), q.stride(0)
+    d.k, d.ldk = k.data_ptr(), k.stride(0)
+    d.v, d.ldv = v.data_ptr(), v.stride(0)
+    d.dtype = dt(q)
+    d.key_len, d.key_valid_bits, d.causal = ptr(key_len), ptr(key_bits), int(bool(causal))
+    return d
+
+
+def attn_general_fwd(q, k, v, ctx, lse, B, Tq, Tk, H, key_len=None, key_bits=None, causal=False):
+    """include/eec.h::eec_attn_general_fwd (decoder self-attention with causal / padding masks, cross-attention over encoder states)"""
+    d = _attn_desc(q, k, v, B, Tq, Tk, H, key_len, key_bits, causal)
+    call("eec_attn_general_fwd", C.byref(d), ptr(ctx), ctx.stride(0), ptr(lse), stream())
+
+
+def attn_general_bwd(q, k, v, ctx, dctx, lse, dq, dk, dv, B, Tq, Tk, H, key_len=None, key_bits=None, causal=False):
+    """dq / dk / dv: 2-D views like q / k / v (written, not accumulated)"""
+    d = _attn_desc(q, k, v, B, Tq, Tk, H, key_len, key_bits, causal)
+    dev = q.device
+    dvec = torch.empty(B * H * Tq, dtype=torch.float32, device=dev)
+    dq32 = torch.empty(B * Tq, H * 32, dtype=torch.float32, device=dev) if q.dtype == torch.bfloat16 else None
+    call("eec_attn_general_bwd", C.byref(d), ptr(ctx), ptr(dctx), ctx.stride(0), ptr(lse), dq.data_ptr(), dq.stride(0), dk.data_ptr(),
+         dk.stride(0), dv.data_ptr(), dv.stride(0), ptr(dvec), ptr(dq32), stream())
+
+
+def key_bits_from_tokens(tokens, pad):
+    """uint32 words [B, ceil(L/32)]: bit set iff tokens[b, t] != pad"""
+    B, Ln = tokens.shape
+    bits = torch.empty(B, (Ln + 31) // 32, dtype=torch.int32, device=tokens.device)
+    call("eec_key_bits_from_tokens", ptr(tokens), B, Ln, int(pad), ptr(bits), stream())
+    return bits
+
+
+def embed_pe(tokens, emb, pe, x):
+    B, Ln = tokens.shape
+    call("eec_embed_pe", ptr(tokens), ptr(emb), ptr(pe), ptr(x), B, Ln, emb.shape[1], emb.shape[0], stream())
+
+
+def embed_bwd(tokens, dx, demb):
+    B, Ln = tokens.shape
+    call("eec_embed_bwd", ptr(tokens), ptr(dx), ptr(demb), B, Ln, demb.shape[1], demb.shape[0], stream())
+
+
+def cross_entropy(logits, targets, loss_out, dlogits=None):
+    rows, V = logits.shape
+    call("eec_cross_entropy", ptr(logits), ptr(targets), rows, V, ptr(loss_out), ptr(dlogits), stream())
+
+
 def dropout(x, y, drop: Drop):
     """y = x * keep_mask * 1/(1-p) for the dropout site `drop` (x, y contiguous, same numel; in place allowed)."""
     _chk(x, "dropout.x")
@@ -227,6 +283,21 @@ def ctc_fwd_bwd(lp, targets, target_len, nll, loss_out, grad, gscale=1.0, blank=
 
 def greedy_collapse(argmax, tokens, n_tokens, B, T, blank=0):
     call("eec_greedy_collapse", ptr(argmax), ptr(tokens), ptr(n_tokens), B, T, blank, stream())
+
+
+def ctc_beam_search(lp, enc_len, beam, nbest, blank, log_blank_skip):
+    """lp [..., T, V] fp32 log-probs (contiguous) -> (tokens [n_utt, nbest, T] int32 (-1 padded), n_tokens [n_utt, nbest], scores [n_utt, nbest])"""
+    _chk(lp, "ctc_beam_search.lp")
+    T, V = lp.shape[-2], lp.shape[-1]
+    n_utt = lp.numel() // (T * V)
+    dev = lp.device
+    tokens = torch.empty(n_utt, nbest, T, dtype=torch.int32, device=dev)
+    n_tok = torch.empty(n_utt, nbest, dtype=torch.int32, device=dev)
+    scores = torch.empty(n_utt, nbest, dtype=torch.float32, device=dev)
+    ws = torch.empty(max(L.load().eec_ctc_beam_workspace_bytes(n_utt, T, beam), 4) // 4, dtype=torch.int32, device=dev)
+    call("eec_ctc_beam_search", ptr(lp), ptr(enc_len), n_utt, T, V, beam, nbest, blank, log_blank_skip, ptr(tokens), ptr(n_tok),
+         ptr(scores), ptr(ws), stream())
+    return tokens, n_tok, scores
 
 
 def im2col_k3s2(inp, sb, sc, st, out, ldo, B, Cin, T_out):

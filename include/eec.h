@@ -35,6 +35,8 @@ typedef enum {
   EEC_ACT_SILU = 1,  /* out = silu(acc+bias); optional preact store                        */
   EEC_ACT_GLU = 2,   /* N even; out[:, n] = z[n] * sigmoid(z[n+N/2]), out has N/2 columns   */
   EEC_ACT_DSILU = 3, /* out = (acc) * silu'(preact[m,n])  (backward of SILU)                */
+  EEC_ACT_RELU = 4,  /* out = max(acc+bias, 0)   (nn.TransformerDecoderLayer's feed-forward, early_exit.py:703-711) */
+  EEC_ACT_DRELU = 5, /* out = (acc) * [preact[m,n] > 0]; preact = the forward's ReLU OUTPUT (backward of RELU) */
 } eec_act;
 
 const char* eec_last_error(void);
@@ -138,6 +140,40 @@ int eec_attn_bwd(const void* qkv, const void* ctx, const void* dctx, int dtype, 
                  const int32_t* key_len, void* dqkv, float* dvec, float* dq32, int B, int T, int H, int dh,
                  const uint64_t* drop_state, float drop_p, uint32_t drop_site, const void* drop_bits, eec_stream_t stream);
 
+/* ---- general attention core: the AED decoder stacks (nn.TransformerDecoderLayer's self_attn with the causal
+ *      tgt_mask + tgt_key_padding_mask and multihead_attn over the encoder states, early_exit.py:701-717, :742-800) -----------------
+ * Queries and keys / values may come from different tensors with different lengths:
+ *   Q(b, t, h, :)  = q[(b*Tq + t)*ldq + h*dh ...]   t < Tq        K(b, t', h, :) = k[(b*Tk + t')*ldk + h*dh ...]   t' < Tk   (V likewise)
+ * (point q / k / v at the first column of the respective block of a packed projection output).  Key t' is visible to query t iff
+ * t' < key_len[b] (key_len != NULL), bit (t' & 31) of key_valid_bits[b*ceil(Tk/32) + t'/32] is set (key_valid_bits != NULL) and, with
+ * causal != 0, t' <= t.  Rows without a visible key produce 0.  ctx(b, t, h, :) = ctx[(b*Tq + t)*ldo + h*dh ...]; lse [B, H, Tq]. */
+typedef struct {
+  int B, H, dh, Tq, Tk;
+  const void* q; int ldq;
+  const void* k; int ldk;
+  const void* v; int ldv;
+  int dtype;                        /* eec_dtype of q / k / v / ctx and of the gradients */
+  const int32_t* key_len;           /* [B] or NULL */
+  const uint32_t* key_valid_bits;   /* [B, ceil(Tk/32)] or NULL */
+  int causal;
+} eec_attn_desc;
+int eec_attn_general_fwd(const eec_attn_desc* d, void* ctx, int ldo, float* lse, eec_stream_t stream);
+/* dq [B*Tq rows, lddq], dk / dv [B*Tk rows, lddk / lddv] are WRITTEN (head h at column h*dh of the given pointers); dvec: fp32
+ * workspace [B*H*Tq]; dq32: fp32 workspace [B*Tq, H*dh] (EEC_BF16 tensor-core path; may be NULL for EEC_F32). */
+int eec_attn_general_bwd(const eec_attn_desc* d, const void* ctx, const void* dctx, int ldo, const float* lse, void* dq, int lddq,
+                         void* dk, int lddk, void* dv, int lddv, float* dvec, float* dq32, eec_stream_t stream);
+/* key_valid_bits for a padded token matrix: bit set iff tokens[b, t] != pad  (tgt_key_padding_mask = (trg == pad), early_exit.py:802-805) */
+int eec_key_bits_from_tokens(const int64_t* tokens, int B, int L, int64_t pad, uint32_t* bits, eec_stream_t stream);
+
+/* ---- AED decoder glue ---------------------------------------------------------------------------------------
+ * x[b*L + t, :] = emb[tokens[b, t], :] + pe[t, :]      (nn.Embedding + PositionalEncoding, early_exit.py:776-777; no sqrt(d) scaling) */
+int eec_embed_pe(const int64_t* tokens, const float* emb, const float* pe, float* x, int B, int L, int D, int V, eec_stream_t stream);
+/* demb[tokens[b, t], :] += dx[b*L + t, :]   (fp32 atomics; demb accumulates) */
+int eec_embed_bwd(const int64_t* tokens, const float* dx, float* demb, int B, int L, int D, int V, eec_stream_t stream);
+/* nn.CrossEntropyLoss() with its defaults (mean over ALL rows, no ignore_index: the pad id is scored, train.py:47, :258):
+ * loss_out[0] += mean_r( logsumexp(logits[r, :]) - logits[r, target[r]] );  dlogits (may be NULL) = (softmax - onehot) / rows. */
+int eec_cross_entropy(const float* logits, const int64_t* targets, int rows, int V, float* loss_out, float* dlogits, eec_stream_t stream);
+
 /* ---- conformer convolution module interior (TA:52-65) ------------------------------
  * g [B,T,C] (dtype) -> depthwise conv k (SAME, zero pad per utterance) + bias.
  * eval : out = silu(bn_eval(c))                     (one kernel)
@@ -204,6 +240,20 @@ int eec_ctc_fwd_bwd(const float* lp, const int64_t* targets, const int64_t* targ
 
 /* ---- greedy CTC decode (util/beam_infer.py:21-23): collapse repeats, drop blank ---- */
 int eec_greedy_collapse(const int32_t* argmax, int32_t* tokens, int32_t* n_tokens, int B, int T, int blank,
+                        eec_stream_t stream);
+
+/* ---- CTC prefix beam search: torchaudio's cuda_ctc_decoder(tokens, nbest=1, beam_size, blank_skip_threshold=0.95)
+ *      as called at util/beam_infer.py:100-110 once per exit (inference.py:66-79) -- here for all exits and utterances of a forward in
+ *      ONE launch (one CTA per emission matrix walks its frames on chip).
+ * lp [n_utt, T, V] fp32 log-probabilities (the (E, B, T', V) output of Early_conformer.forward is n_utt = E*B), enc_len [n_utt] int32 or
+ * NULL (= T for every utterance, what the reference passes).  Frames with lp[t, blank] > log_blank_skip are not expanded but
+ * counted as a pure blank emission, p_b' = (p_b + p_nb) p(blank), p_nb' = 0 -- the library's "blank skipping" (pass log(0.95); +inf disables it).  Prefix beam search with merged prefixes, `beam` <= 16 hypotheses, V <= 1024.
+ * Outputs, best hypothesis first: tokens [n_utt, nbest, T] int32 padded with -1, n_tokens [n_utt, nbest], scores [n_utt, nbest]
+ * (log(p_blank + p_non_blank); -inf for missing hypotheses).  workspace: eec_ctc_beam_workspace_bytes(n_utt, T, beam) bytes
+ * (back-pointer trie of the prefixes). */
+int64_t eec_ctc_beam_workspace_bytes(int n_utt, int T, int beam);
+int eec_ctc_beam_search(const float* lp, const int32_t* enc_len, int n_utt, int T, int V, int beam, int nbest, int blank,
+                        float log_blank_skip, int32_t* tokens, int32_t* n_tokens, float* scores, void* workspace,
                         eec_stream_t stream);
 
 /* ---- front end (early_exit.py:24-48, positional_encoding.py:70-72) ----------------

@@ -335,8 +335,10 @@ def run_fc_case(name, n_exits, n_layers, n_dec, B, t_in, lo, hi, seed):
     out["grad_names"], out["grad_norms"] = np.array(names), np.array(norms)
     P = dict(m.named_parameters())
     l0 = "conformer.0.conformer_layers.0."
+    d0 = "decoders.0.layers.0."
+    extra = [d0 + "self_attn.in_proj_bias", d0 + "multihead_attn.in_proj_weight", d0 + "linear1.bias", d0 + "norm2.weight", "emb.weight"] if n_dec > 1 else []
     for k in ["conv_subsample.sequential.0.bias", "linears_1.0.bias", "linears_2.1.bias", l0 + "ffn1.sequential.1.bias",
-              l0 + "final_layer_norm.weight", "layer_norm.weight"]:
+              l0 + "final_layer_norm.weight", "layer_norm.weight"] + extra:
         out["grad::" + k] = P[k].grad.numpy()
     path = os.path.join(ROOT, "tests", "golden", name + ".npz")
     np.savez_compressed(path, **out)
@@ -364,10 +366,14 @@ def ctc_cases():
 
 if __name__ == "__main__":
     torch.set_num_threads(8)
+    if len(sys.argv) > 1 and sys.argv[1] == "fc2":     # only the second AED fixture (two decoder layers per exit, ragged targets with padding)
+        run_fc_case("fc_e2l1d2_b3_t203", 2, 1, 2, 3, 203, 3, 9, seed=160)
+        sys.exit(0)
     for i, (name, (kind, e, l, B, t, lo, hi)) in enumerate(CASES.items()):
         run_case(name, kind, e, l, B, t, lo, hi, seed=100 + 10 * i)
     ctc_cases()
     run_fc_case("fc_e2l1d1_b2_t163", 2, 1, 1, 2, 163, 3, 8, seed=150)
+    run_fc_case("fc_e2l1d2_b3_t203", 2, 1, 2, 3, 203, 3, 9, seed=160)
     fbank_case()
     for i, (name, (kind, e, l, B, t, lo, hi, p, ds)) in enumerate(DROP_CASES.items()):
         run_dropout_case(name, kind, e, l, B, t, lo, hi, p, ds, seed=200 + 10 * i)

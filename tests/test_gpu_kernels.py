@@ -337,3 +337,78 @@ def test_wgrad_fused_bias_colsum():
         ref_b = -1.0 + 0.5 * dy.double().sum(0)
         assert float((dw.double() - ref_w).abs().max() / ref_w.abs().max()) < 2e-5
         assert float((db.double() - ref_b).abs().max() / ref_b.abs().max()) < 2e-5
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("mode", ["causal_self", "cross", "cross_long"])
+def test_attention_general(ops, dtype, mode):
+    """eec_attn_general_fwd / _bwd (the AED decoder's attention, early_exit.py:701-717): causal self-attention with a key-padding mask over a
+    packed [rows, 768] projection, and cross-attention (Tq != Tk, Q and K/V from different tensors, K/V at a column offset of a wider
+    tensor) against the same arithmetic in plain PyTorch fp32 (fp32 kernels 2e-5, bf16 tensor-core kernels 2e-2)."""
+    torch.manual_seed(3)
+    B, Hh, dh = 3, 8, 32
+    Dm = Hh * dh
+    if mode == "causal_self":
+        Tq = Tk = 45
+        qkv = (torch.randn(B * Tq, 3 * Dm, device="cuda") * 0.7).to(dtype)
+        q, k, v = qkv[:, :Dm], qkv[:, Dm:2 * Dm], qkv[:, 2 * Dm:]
+        toks = torch.randint(3, 120, (B, Tk), device="cuda")
+        toks[1, 30:] = 126
+        toks[2, 7:] = 126
+        toks[2, 3] = 126                  # a padded key in the middle
+        bits = ops.key_bits_from_tokens(toks, 126)
+        valid = toks != 126
+        causal = True
+    else:
+        Tq, Tk = (37, 200) if mode == "cross" else (130, 390)
+        qt = (torch.randn(B * Tq, Dm, device="cuda") * 0.7).to(dtype)
+        kvw = (torch.randn(B * Tk, 4 * Dm, device="cuda") * 0.7).to(dtype)     # K | V of "layer 1" of a stacked projection
+        q, k, v = qt, kvw[:, 2 * Dm:3 * Dm], kvw[:, 3 * Dm:]
+        bits, valid, causal = None, torch.ones(B, Tk, dtype=torch.bool, device="cuda"), False
+    ctx = torch.empty(B * Tq, Dm, device="cuda", dtype=dtype)
+    lse = torch.empty(B, Hh, Tq, device="cuda")
+    ops.attn_general_fwd(q, k, v, ctx, lse, B, Tq, Tk, Hh, key_bits=bits, causal=causal)
+    # reference
+    qf = q.float().reshape(B, Tq, Hh, dh).permute(0, 2, 1, 3).clone().requires_grad_(True)
+    kf = k.float().reshape(B, Tk, Hh, dh).permute(0, 2, 1, 3).clone().requires_grad_(True)
+    vf = v.float().reshape(B, Tk, Hh, dh).permute(0, 2, 1, 3).clone().requires_grad_(True)
+    sc = qf @ kf.transpose(-1, -2) / dh ** 0.5
+    mask = valid[:, None, None, :].expand(B, Hh, Tq, Tk).clone()
+    if causal:
+        mask &= torch.tril(torch.ones(Tq, Tk, dtype=torch.bool, device="cuda"))[None, None]
+    sc = sc.masked_fill(~mask, float("-inf"))
+    ref = (torch.softmax(sc, -1) @ vf)
+    ref_ctx = ref.permute(0, 2, 1, 3).reshape(B * Tq, Dm)
+    tol = 2e-5 if dtype == torch.float32 else 2e-2
+    assert rel(ctx, ref_ctx) < tol
+    assert rel(lse, torch.logsumexp(sc, -1)) < (1e-5 if dtype == torch.float32 else 2e-2)
+    dctx = (torch.randn(B * Tq, Dm, device="cuda") * 0.5).to(dtype)
+    ref_ctx.backward(dctx.float())
+    dq = torch.empty(B * Tq, Dm, device="cuda", dtype=dtype)
+    dkv = torch.zeros(B * Tk, 2 * Dm, device="cuda", dtype=dtype)
+    ops.attn_general_bwd(q, k, v, ctx, dctx, lse, dq, dkv[:, :Dm], dkv[:, Dm:], B, Tq, Tk, Hh, key_bits=bits, causal=causal)
+    btol = 1e-4 if dtype == torch.float32 else 3e-2
+    assert rel(dq, qf.grad.permute(0, 2, 1, 3).reshape(B * Tq, Dm)) < btol
+    assert rel(dkv[:, :Dm], kf.grad.permute(0, 2, 1, 3).reshape(B * Tk, Dm)) < btol
+    assert rel(dkv[:, Dm:], vf.grad.permute(0, 2, 1, 3).reshape(B * Tk, Dm)) < btol
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_gemm_relu_epilogues(ops, dtype):
+    """RELU / DRELU epilogues of eec_gemm (nn.TransformerDecoderLayer's feed-forward and its backward)"""
+    torch.manual_seed(5)
+    M, N, K = 300, 2048, 256
+    a = (torch.randn(M, K, device="cuda") * 0.5).to(dtype)
+    w = (torch.randn(N, K, device="cuda") * 0.05).to(dtype)
+    bias = torch.randn(N, device="cuda") * 0.1
+    out = torch.empty(M, N, device="cuda", dtype=dtype)
+    ops.gemm(a, w, out, M, N, K, bias=bias, act=ops.ACT_RELU)
+    ref = torch.relu(a.float() @ w.float().t() + bias)
+    tol = 1e-4 if dtype == torch.float32 else 2e-2
+    assert rel(out, ref) < tol
+    dy = (torch.randn(M, K, device="cuda") * 0.5).to(dtype)       # dY [M, K_in=256] @ W2 [256, 2048] -> [M, 2048], times [a > 0]
+    w2 = (torch.randn(K, N, device="cuda") * 0.05).to(dtype)
+    dh = torch.empty(M, N, device="cuda", dtype=dtype)
+    ops.gemm(dy, w2, dh, M, N, K, a_kmajor=True, b_kmajor=False, lda=K, ldb=N, act=ops.ACT_DRELU, preact=out, alpha=0.5)
+    refd = 0.5 * (dy.float() @ w2.float()) * (out.float() > 0)
+    assert rel(dh, refd) < tol

@@ -266,3 +266,53 @@ def test_bench_reference_arm_contract():
     assert d["steps"] == 1 and d["warmup"] == 0
     assert d["e2e"] == {"value": d["value"], "unit": "utt/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"] and "model" not in d["config"]
+
+
+def test_length_sorted_split_matches_reference_collate():
+    """eec.batching.length_sorted_split == the chunking loop of CollatePaddingFn.__call__ (util/data_loader.py:163-188), restated here
+    statement for statement on (length, id) records, for many random mini-batches; plus the properties train.py:22-26 relies on."""
+    import random
+    from eec import batching
+
+    def reference_chunks(batch, n_split):          # batch: [(width, uid)]; x[0].size(1) -> x[0]
+        batch = sorted(batch, key=lambda x: x[0], reverse=True)
+        s_sum = sum(x[0] for x in batch) / n_split
+        p_sum, chunked_batch, init, end, p_split = 0, [], 0, 0, 0
+        for w, *_ in batch:
+            p_sum += w
+            if p_sum >= s_sum:
+                chunked_batch.append(batch[init:end + 1])
+                p_sum = 0
+                p_split += 1
+                init = end + 1
+            end += 1
+        if p_split != n_split:
+            chunked_batch.append(batch[init:end])
+        return [[u for _, u in c] for c in chunked_batch]
+
+    rng = random.Random(5)
+    n_ok = 0
+    for trial in range(300):
+        n = rng.randint(1, 70)
+        n_split = rng.choice([1, 2, 4, 8])
+        lengths = [rng.randint(200, 3200) for _ in range(n)]
+        if trial % 7 == 0:
+            lengths = [lengths[0]] * n                               # all equal: ties keep the input order
+        got = batching.length_sorted_split(lengths, n_split)
+        assert got == reference_chunks([(w, i) for i, w in enumerate(lengths)], n_split)
+        flat = [i for c in got for i in c]
+        assert sorted(flat) == list(range(n))                        # every utterance exactly once
+        assert all(lengths[a] >= lengths[b] for a, b in zip(flat, flat[1:]))
+        n_ok += batching.trains_on(got, n_split)
+    assert n_ok > 200
+    # the BASELINE shape: 64 utterances, 4 chunks -> ~16 per chunk, far less padding than one 64-utterance call
+    lengths = [rng.randint(750, 1501) for _ in range(64)]
+    ch = batching.length_sorted_split(lengths, 4)
+    assert len(ch) == 4 and 10 <= min(map(len, ch)) and max(map(len, ch)) <= 24
+    assert batching.padding_ratio(lengths, ch) < 0.5 * batching.padding_ratio(lengths, [list(range(64))])
+    # graph cache policy: exact (B, T_in), bucketed target width, LRU eviction
+    made = []
+    cache = batching.GraphedStepCache(lambda B, T, L: made.append((B, T, L)) or (B, T, L), capacity=2)
+    assert cache.get(16, 1501, 70) == (16, 1501, 80) and cache.get(16, 1501, 75) == (16, 1501, 80) and cache.hits == 1
+    cache.get(17, 1501, 70); cache.get(16, 1400, 70)
+    assert cache.evictions == 1 and cache.captures == 3 and (16, 1501, 80) not in cache.steps
