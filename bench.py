@@ -382,7 +382,7 @@ def run_ours(args):
         guarded(kernel_trace, leg.step, args.kernel_trace, rank)
 
     # inference RTFx per exit (BASELINE metric part (i)): forward truncated after exit e, bf16, eval
-    rtfx = ee_leg = fb_leg = eager_leg = hbm_leg = f32_leg = None
+    rtfx = ee_leg = fb_leg = eager_leg = hbm_leg = f32_leg = beam_leg = aed = None
     src_dev = leg.src_dev
     audio_s = float(lengths.sum()) * FRAME_S
     if rank == 0 and not args.skip_rtfx and not args.profile:
@@ -395,6 +395,7 @@ def run_ours(args):
             f32_leg = guarded(fp32_leg, layers, dev, src_dev, lengths, leg.tg_dev, leg.tl_dev, audio_s, leg.targets.shape[1])
         if world == 1 and not args.skip_cpu:
             eager_leg = guarded(torch_eager_leg, layers, dev, src_dev, lengths, leg.tg_dev, leg.tl_dev, audio_s)
+        beam_leg = guarded(beam_search_leg, model, src_dev, lengths) if not args.no_graph else None
 
     # the same step at the reference's DEFAULT --drop_prob 0.1 (util/conf.py:283-291): fused counter-based dropout at all
     # seven sites per layer + after the positional encoding, masks regenerated in backward (nothing stored)
@@ -446,6 +447,12 @@ def run_ours(args):
         if world > 1:
             barrier()
 
+    if rank == 0 and world == 1 and not args.skip_aed and not args.profile and not args.skip_rtfx:
+        if graphed is not None:
+            leg.close()
+            graphed = None
+        torch.cuda.empty_cache()
+        aed = guarded(aed_leg, dev)
     roof = cpu = None
     if rank == 0:
         roof = None if args.profile else roofline_dominant(dev, pk)
@@ -477,7 +484,8 @@ def run_ours(args):
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
             "parity_vs_reference": parity,
         }
-        for key, val in (("rtfx_per_exit", rtfx), ("train_with_dropout", drop_leg), ("dp_18_layers", deep_leg),
+        for key, val in (("rtfx_per_exit", rtfx), ("train_with_dropout", drop_leg), ("dp_18_layers", deep_leg), ("aed_mode", aed),
+                         ("ctc_beam_search", beam_leg),
                          ("early_exit_inference", ee_leg), ("fbank_frontend", fb_leg), ("roofline_hbm_kernel", hbm_leg),
                          ("fp32_mode", f32_leg), ("torch_eager_same_gpu", eager_leg)):
             if val is not None:
@@ -587,6 +595,85 @@ def fp32_leg(layers, dev, src_dev, lengths, tg_dev, tl_dev, audio_s, targets_w):
             "inference_all_exits_ms": round(ms_fwd, 2), "inference_rtfx": round(audio_s / (ms_fwd / 1e3), 1)}
 
 
+def aed_leg(dev, steps=3):
+    """BASELINE configs[4]: early_conformer AED mode -- full_conformer = the 12-layer / 6-exit encoder with per-exit CTC heads plus six
+    6-layer attention decoders (88.8 M parameters), batch 64, long utterances at the model's max_len (T_in 7999 -> T' 1999 encoder
+    frames), targets of 150..400 tokens.  One training step: forward, 0.7 CE + 0.3 CTC over all exits (train.py:36-51), backward (no optimiser:
+    the fused one covers the CTC models).  Encoder AND decoder stacks on the sm_100a kernels; the reference's own module in eager PyTorch
+    (bf16 autocast) beside it when it fits."""
+    import eec
+    Bn, T_in = 64, 7999
+    g = torch.Generator().manual_seed(77)
+    lengths = torch.randint(T_in // 2, T_in + 1, (Bn,), generator=g)
+    lengths[0] = T_in
+    src = torch.randn(Bn, N_MELS, T_in, generator=g)
+    for b in range(Bn):
+        src[b, :, int(lengths[b]):] = 0.0
+    tl = torch.randint(150, 401, (Bn,), generator=g)
+    tg = torch.full((Bn, int(tl.max()) + 2), 126, dtype=torch.int64)
+    for b in range(Bn):
+        k = int(tl[b])
+        tg[b, 0] = 1
+        tg[b, 1:1 + k] = torch.randint(3, 126, (k,), generator=g)
+        tg[b, 1 + k] = 2
+    tl = tl + 2
+    kw = dict(trg_pad_idx=126, n_enc_exits=N_EXITS, enc_voc_size=256, dec_voc_size=256, d_model=256, n_head=8, max_len=2000, d_feed_forward=2048,
+              n_enc_layers=2, n_dec_layers=6, features_length=N_MELS, drop_prob=0.0, depthwise_kernel_size=31)
+    torch.manual_seed(0)
+    m = eec.full_conformer(device=dev, **kw).to(dev).train()
+    m.precision = "bf16"
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    src_d, tg_d, tl_d = src.to(dev), tg.to(dev), tl.to(dev)
+    trg, trg_expect = tg_d[:, :-1].contiguous(), tg_d[:, 1:].contiguous()
+
+    def step():
+        dec, enc = m(src_d, lengths, trg)
+        loss = 0.7 * eec.multi_exit_cross_entropy(dec, trg_expect) + 0.3 * eec.multi_exit_ctc_loss(enc, tg_d, tl_d)
+        m.zero_grad(set_to_none=True)
+        loss.backward()
+        return loss
+    n0 = eec.load().eec_launch_count()
+    loss0 = float(step())
+    launches = int(eec.load().eec_launch_count() - n0)
+    ms = _time_loop(step, steps, warm=1)
+    res = {"config": "BASELINE configs[4]: full_conformer (AED), 6 exits x 2 encoder layers + 6 x 6 decoder layers, batch 64, T_in 7999 -> T' 1999 "
+                     f"(max_len 2000), target width {tg.shape[1]}; fwd + (0.7 CE + 0.3 CTC) + bwd, bf16", "ms_per_step": round(ms, 2),
+           "utt_per_s": round(Bn / (ms / 1e3), 1), "loss_first_step": round(loss0, 4), "gpu_launches": launches,
+           "parameters": sum(p.numel() for p in m.parameters())}
+    del m
+    torch.cuda.empty_cache()
+    ref = load_reference()
+    if ref is not None:
+        try:
+            if REF_DIR not in sys.path:
+                sys.path.insert(0, REF_DIR)
+            from models.model.early_exit import full_conformer as RefFC   # noqa: E402
+            torch.manual_seed(0)
+            r = RefFC(device=dev, **kw).to(dev).train()
+            r.load_state_dict(sd, strict=True)
+            ctc, ce = torch.nn.CTCLoss(blank=0, zero_infinity=True), torch.nn.CrossEntropyLoss()
+
+            def rstep():
+                with torch.autocast("cuda", dtype=torch.bfloat16):
+                    dec, enc = r(src_d, lengths, trg)
+                in_len = torch.full((Bn,), enc.size(2), dtype=torch.long)
+                lc = sum(ctc(e_.float().permute(1, 0, 2), tg_d, in_len, tl_d) for e_ in enc)
+                lce = sum(ce(d_.float().permute(0, 2, 1), trg_expect) for d_ in dec)
+                loss = 0.7 * lce + 0.3 * lc
+                r.zero_grad()
+                loss.backward()
+                return loss
+            rl = float(rstep())
+            res["reference_eager_bf16_autocast_ms_per_step"] = round(_time_loop(rstep, 2, warm=0), 2)
+            res["reference_loss_first_step"] = round(rl, 4)
+            res["loss_rel_err_vs_reference_autocast"] = round(abs(loss0 - rl) / abs(rl), 5)
+            del r
+        except Exception as e:   # noqa: BLE001
+            res["reference_eager"] = f"failed: {type(e).__name__}: {e}"[:200]
+        torch.cuda.empty_cache()
+    return res
+
+
 def rtfx_per_exit(model, src_dev, lengths, audio_s, use_graph=True):
     """Inference RTFx for a forward truncated after exit e (e = 1..6): front end + e exit groups + heads 1..e, bf16, eval;
     each truncated forward is one CUDA graph replay (eager launches with --no-graph)."""
@@ -616,6 +703,38 @@ def rtfx_per_exit(model, src_dev, lengths, audio_s, use_graph=True):
             torch.cuda.synchronize()
             ms = ev0.elapsed_time(ev1) / 5
             res.append({"exit": e, "ms": round(ms, 3), "rtfx": round(audio_s / (ms / 1e3), 1)})
+    return res
+
+
+def beam_search_leg(model, src_dev, lengths):
+    """what `inference.py --decoder_mode ctc` prints -- the beam-10 CTC prefix beam search of ALL six exits of the batch (384
+    emission matrices of 374 x 256) as ONE kernel launch behind the six-exit forward; torchaudio's cuda_ctc_decoder (the reference's
+    library, util/beam_infer.py:100-110) beside it where it runs (it faults on sm_100 for beam_size >= 7, so it is timed at beam 5)."""
+    import eec
+    model.eval()
+    with torch.no_grad():
+        out = eec.GraphedForward(model, src_dev.shape[0], src_dev.shape[2])(src_dev, lengths).clone()
+    model.train()
+    vocab = [str(i) for i in range(out.shape[-1])]
+    res = {"emissions": list(out.shape)}
+    for beam in (10, 5):
+        dec = eec.cuda_ctc_decoder(vocab, nbest=1, beam_size=beam, blank_skip_threshold=0.95)
+        ms = _time_loop(lambda: dec.search(out), 5, warm=2)
+        res[f"all_exits_beam{beam}_ms"] = round(ms, 3)
+    try:
+        import subprocess
+        code = ("import sys,time,torch\nfrom torchaudio.models.decoder import cuda_ctc_decoder\n"
+                "g=torch.Generator().manual_seed(0)\nlp=torch.log_softmax(torch.randn(64,374,256,generator=g),-1).cuda()\n"
+                "lens=torch.full((64,),374,dtype=torch.int32).cuda()\nd=cuda_ctc_decoder([str(i) for i in range(256)],nbest=1,beam_size=5,blank_skip_threshold=0.95)\n"
+                "d(lp,lens);torch.cuda.synchronize();t=time.perf_counter()\nfor _ in range(3): d(lp,lens)\ntorch.cuda.synchronize();print((time.perf_counter()-t)/3*1e3)")
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+        if r.returncode == 0:
+            res["torchaudio_cuda_ctc_decoder_beam5_ms_per_exit"] = round(float(r.stdout.strip().splitlines()[-1]), 2)
+            res["torchaudio_all_exits_beam5_ms"] = round(6 * float(r.stdout.strip().splitlines()[-1]), 2)
+        else:
+            res["torchaudio_cuda_ctc_decoder"] = "failed: " + (r.stderr.strip().splitlines() or ["?"])[-1][:160]
+    except Exception as e:   # noqa: BLE001
+        res["torchaudio_cuda_ctc_decoder"] = f"failed: {type(e).__name__}"
     return res
 
 
@@ -919,6 +1038,7 @@ def main():
                     "(the reference's default); the headline step runs at 0 like the parity tests (SURVEY 8d). 0 skips the leg")
     ap.add_argument("--skip-parity", action="store_true", help="skip the in-run parity check of the headline step against the reference's CPU forward")
     ap.add_argument("--skip-deep", action="store_true", help="skip the 18-layer (BASELINE configs[2]) leg")
+    ap.add_argument("--skip-aed", action="store_true", help="skip the AED-mode (BASELINE configs[4]) leg")
     ap.add_argument("--grad-dtype", default="fp32", choices=["fp32", "bf16"], help="N > 1: wire format of the overlapped gradient all-reduce")
     ap.add_argument("--kernel-trace", default="", help="write a torch.profiler kernel list of one step (rank 0) to this path")
     ap.add_argument("--profile", action="store_true", help="bracket the timed region with cudaProfilerStart/Stop (for ncu "

@@ -5,7 +5,7 @@
 from .lib import EecError, load, LIB_PATH, EXPORTS  # noqa: F401
 from .early_exit import Early_conformer, Splitformer, greedy_decode  # noqa: F401
 from .ctc import CTCLoss, multi_exit_ctc_loss  # noqa: F401
-from .aed import full_conformer  # noqa: F401
+from .aed import full_conformer, multi_exit_cross_entropy  # noqa: F401
 from .graph import GraphedEarlyExit, GraphedForward, GraphedTrainStep  # noqa: F401
 from .optim import FusedNoamAdamW  # noqa: F401
 from .features import Fbank  # noqa: F401

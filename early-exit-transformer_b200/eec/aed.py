@@ -64,6 +64,38 @@ class _DecoderFn(torch.autograd.Function):
         return (None, None, None, None, None, None, ghid) + tuple(G[n] for n in names)
 
 
+class _CeFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits_eblv, targets):
+        E, B, Ln, Vv = logits_eblv.shape
+        x = logits_eblv.contiguous()
+        tg = targets.to(device=x.device, dtype=torch.int64).contiguous().view(-1)
+        loss = torch.zeros(E, dtype=torch.float32, device=x.device)
+        grad = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        with on_device(x.device):
+            for e in range(E):
+                ops.cross_entropy(x[e].view(B * Ln, Vv), tg, loss[e:e + 1], grad[e].view(B * Ln, Vv) if grad is not None else None)
+        ctx.grad = grad
+        return loss
+
+    @staticmethod
+    def backward(ctx, gloss):
+        g = ctx.grad
+        with on_device(g.device):
+            ops.scale_rows_dev(g, gloss.contiguous().float(), g)
+        ctx.grad = None
+        return g, None
+
+
+def multi_exit_cross_entropy(dec_out: Tensor, trg_expect: Tensor, reduce_exits: bool = True) -> Tensor:
+    """train.py:47 for all exits: sum_e nn.CrossEntropyLoss()(dec_out[e].permute(0, 2, 1), trg_expect) -- mean over ALL B*L positions of every
+    exit, no ignore_index (the pad id is scored); one fused log-softmax + NLL (+ gradient) kernel per exit."""
+    if not dec_out.is_cuda or dec_out.dim() != 4 or dec_out.dtype != torch.float32:
+        raise EecError("multi_exit_cross_entropy: expected (E, B, L, V) fp32 logits on a CUDA device")
+    per_exit = _CeFn.apply(dec_out, trg_expect)
+    return per_exit.sum() if reduce_exits else per_exit
+
+
 class full_conformer(_EarlyExitBase):
     """Drop-in for models.model.early_exit.full_conformer (early_exit.py:637-811)."""
     _splitformer = False
