@@ -209,12 +209,20 @@ __global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_tc_kernel(const __grid
     const long dR = (long)gridDim.z * H * Tq;
     const uint32_t* kbits = GENERAL && g.key_bits ? g.key_bits + (long)b * ((Tk + 31) >> 5) : nullptr;
     if (active) {
+      // this row's log-sum-exp and dO.O of the NEXT query block are loaded one iteration ahead (they sit on the critical path otherwise:
+      // ~10 % of the kernel's stall samples in round 1 were the L2 round trip of these two loads)
+      const float* lse_bh = lse + ((long)b * H + h) * Tq;
+      const float* dv_bh = dvec + ((long)b * H + h) * Tq;
+      const int t_first = i_begin * BT + r;
+      float l2_next = t_first < Tq ? lse_bh[t_first] : 0.f;
+      float di_next = t_first < Tq ? dv_bh[t_first] : 0.f;
       for (int i = 0; i < nq - i_begin; ++i) {
         const int t = (i_begin + i) * BT + r;
         const bool rvalid = t < Tq;
         const long drow = (long)(b * H + h) * Tq + t;
-        const float l2 = rvalid ? lse[((long)b * H + h) * Tq + t] * LOG2E : 0.f;
-        const float di = rvalid ? dvec[((long)b * H + h) * Tq + t] : 0.f;
+        const float l2 = l2_next * LOG2E;
+        const float di = di_next;
+        if (t + BT < Tq) { l2_next = lse_bh[t + BT]; di_next = dv_bh[t + BT]; } else { l2_next = 0.f; di_next = 0.f; }
 #pragma unroll 1
         for (int hk = 0; hk < 2; ++hk) {
           const int n = 2 * i + hk;

@@ -77,8 +77,11 @@ def decoder_forward(P: Dict[str, Tensor], W: Operands, cfg: Config, n_dec: int, 
     for oi, e in enumerate(exits):
         mem = to_act(hidden[mem_index[oi]].reshape(Ne, D), cfg)
         wkv, bkv = _kv_stack(P, W, e, n_dec, cfg)
-        kvall = _empty((Ne, n_dec * 2 * D), TD, dev)
-        linear(mem, wkv, kvall, Ne, n_dec * 2 * D, D, bias=bkv)
+        NK = n_dec * 2 * D
+        kvall = _empty((Ne, NK), TD, dev)
+        for c0 in range(0, NK, 2048):             # (the GEMM stages at most 2048 bias values per launch: 4 layers' K | V at a time)
+            c1 = min(c0 + 2048, NK)
+            linear(mem, wkv[c0:c1], kvall[:, c0:c1], Ne, c1 - c0, D, bias=bkv[c0:c1], ldc=NK)
         et = {"e": e, "mi": mem_index[oi], "mem": mem, "wkv": wkv, "kvall": kvall, "layers": []} if want_tape else None
         y = x0
         p0 = _layer_prefix(e, 0)
