@@ -171,9 +171,8 @@ def test_attention_fwd(ops, dtype, T):
     ref, lse_ref = attn_ref(qkv, key_len, B, T, H)
     assert rel(ctx, ref) < (3e-6 if dtype == torch.float32 else 1.5e-2)
     ok = torch.isfinite(lse_ref)
-    # (bf16: the tensor-core kernel sums the bf16 probabilities the P V product actually uses, evaluated by ex2.approx.bf16x2: the
-    #  row sum -- hence the log-sum-exp -- carries their ~0.3 % rounding; ctx = O / L is unaffected because both use the same P)
-    assert float((lse.double().cpu()[ok] - lse_ref[ok]).abs().max()) < (1e-5 if dtype == torch.float32 else 6e-3)
+    # (bf16: the tensor-core kernel's row sum is taken over the bf16-rounded probabilities the P V product actually multiplies)
+    assert float((lse.double().cpu()[ok] - lse_ref[ok]).abs().max()) < (1e-5 if dtype == torch.float32 else 2e-3)
     if T == 40:  # fully masked utterance -> zeros (torch CPU SDPA behaviour)
         assert float(ctx.view(B, T, 256)[2].abs().max()) == 0.0
 
