@@ -247,11 +247,12 @@ __global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_tc_kernel(const __grid
 #pragma unroll
             for (int e = 0; e < 32; ++e) {
               const bool ok = ((mk >> e) & 1u) && lfin;
+              const float f = DROP ? ((dword & (1u << e)) ? drop.scale : 0.f) : 1.f;
               float p;
               asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p) : "f"(fmaf(s[e], sc2, -l2)));
               p = ok ? p : 0.f;
-              s[e] = p;
-              dp[e] = ok ? p * (dp[e] - di) : 0.f;
+              s[e] = p * f;
+              dp[e] = ok ? p * (dp[e] * f - di) : 0.f;
             }
           } else if (DROP) {
 #pragma unroll
@@ -362,10 +363,12 @@ static int bwd_launch(const CUtensorMap& tq, const CUtensorMap& tkv, const CUten
     EEC_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BW_SMEM));
     EEC_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BW_SMEM));
     EEC_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BW_SMEM));
+    EEC_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BW_SMEM));
     attr_set = true;
   }
   dim3 grid(cdiv(g.Tk, BT), g.H, B);
-  if (general) launch_pdl(attn_bwd_tc_kernel<false, true>, dim3(grid), dim3(BW_THREADS), BW_SMEM, st, tq, tkv, td, g, lse, dvec, dq32, drop);
+  if (general && drop.state) launch_pdl(attn_bwd_tc_kernel<true, true>, dim3(grid), dim3(BW_THREADS), BW_SMEM, st, tq, tkv, td, g, lse, dvec, dq32, drop);
+  else if (general) launch_pdl(attn_bwd_tc_kernel<false, true>, dim3(grid), dim3(BW_THREADS), BW_SMEM, st, tq, tkv, td, g, lse, dvec, dq32, drop);
   else if (drop.state) launch_pdl(attn_bwd_tc_kernel<true, false>, dim3(grid), dim3(BW_THREADS), BW_SMEM, st, tq, tkv, td, g, lse, dvec, dq32, drop);
   else launch_pdl(attn_bwd_tc_kernel<false, false>, dim3(grid), dim3(BW_THREADS), BW_SMEM, st, tq, tkv, td, g, lse, dvec, dq32, drop);
   EEC_LAUNCH_CHECK();
@@ -391,7 +394,7 @@ int attn_bwd_tc(const void* qkv, const void* ctx, const void* dctx, const float*
 }
 
 int attn_general_bwd_tc(const eec_attn_desc* d, const void* ctx, const void* dctx, int ldo, const float* lse, void* dq, int lddq, void* dk,
-                        int lddk, void* dv, int lddv, float* dvec, float* dq32, cudaStream_t st) {
+                        int lddk, void* dv, int lddv, float* dvec, float* dq32, const DropArgs& drop, cudaStream_t st) {
   EEC_CHECK_ARG(d->dh == DHD && d->H * d->dh == 256, "attn_general_bwd_tc: needs 8 heads of 32");
   EEC_CHECK_ARG(dq32 != nullptr, "attn_general_bwd_tc: dq32 workspace is NULL");
   const uintptr_t k = (uintptr_t)d->k, v = (uintptr_t)d->v;
@@ -406,7 +409,6 @@ int attn_general_bwd_tc(const eec_attn_desc* d, const void* ctx, const void* dct
   const uint64_t kv_cols = (uint64_t)(g.k_col > g.v_col ? g.k_col : g.v_col) + (uint64_t)d->H * d->dh;
   if (int r = get_tmap_2d(&tkv, kv_base, kv_cols, (uint64_t)d->B * d->Tk, (uint64_t)d->ldk * 2, DHD, 128, 2)) return r;
   if (int r = get_tmap_2d(&td, dctx, (uint64_t)d->H * d->dh, (uint64_t)d->B * d->Tq, (uint64_t)ldo * 2, DHD, 128, 2)) return r;
-  DropArgs drop{};
   return bwd_launch(tq, tkv, td, g, d->B, ctx, dctx, ldo, lse, dvec, dq32, dq, lddq, drop, true, st);
 }
 

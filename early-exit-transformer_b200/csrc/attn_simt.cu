@@ -373,9 +373,11 @@ extern "C" int eec_attn_general_fwd(const eec_attn_desc* d, void* ctx, int ldo, 
   AttnGeom g{};
   if (int r = geom_from_desc(d, g)) return r;
   if (d->B == 0 || d->Tq == 0) return 0;
-  DropArgs drop{};
+  DropArgs drop = make_drop(d->drop_state, d->drop_p, d->drop_site);
+  drop.bits = d->drop_bits;
   const bool tc_path = d->dtype == EEC_BF16 && !force_simt() && attn_tc_ready() && attn_general_tc_ok(d);
-  if (tc_path) return attn_general_fwd_tc(d, ctx, ldo, lse, S(stream));
+  EEC_CHECK_ARG(!(tc_path && drop.state && !d->drop_bits), "attn_general_fwd (tensor-core path): dropout needs keep-mask words in drop_bits");
+  if (tc_path) return attn_general_fwd_tc(d, ctx, ldo, lse, drop, S(stream));
   if (d->dtype == EEC_F32) return simt_fwd<float>(g, d->B, ctx, ldo, lse, drop, S(stream), true);
   return simt_fwd<__nv_bfloat16>(g, d->B, ctx, ldo, lse, drop, S(stream), false);
 }
@@ -385,9 +387,11 @@ extern "C" int eec_attn_general_bwd(const eec_attn_desc* d, const void* ctx, con
   AttnGeom g{};
   if (int r = geom_from_desc(d, g)) return r;
   if (d->B == 0 || d->Tq == 0) return 0;
-  DropArgs drop{};
+  DropArgs drop = make_drop(d->drop_state, d->drop_p, d->drop_site);
+  drop.bits = d->drop_bits;
   const bool tc_path = d->dtype == EEC_BF16 && !force_simt() && attn_tc_ready() && attn_general_tc_ok(d);
-  if (tc_path) return attn_general_bwd_tc(d, ctx, dctx, ldo, lse, dq, lddq, dk, lddk, dv, lddv, dvec, dq32, S(stream));
+  EEC_CHECK_ARG(!(tc_path && drop.state && !d->drop_bits), "attn_general_bwd (tensor-core path): dropout needs the forward's keep-mask words in drop_bits");
+  if (tc_path) return attn_general_bwd_tc(d, ctx, dctx, ldo, lse, dq, lddq, dk, lddk, dv, lddv, dvec, dq32, drop, S(stream));
   if (d->dtype == EEC_F32) return simt_bwd<float>(g, d->B, ctx, dctx, ldo, lse, dq, lddq, dk, lddk, dv, lddv, dvec, drop, S(stream));
   return simt_bwd<__nv_bfloat16>(g, d->B, ctx, dctx, ldo, lse, dq, lddq, dk, lddk, dv, lddv, dvec, drop, S(stream));
 }

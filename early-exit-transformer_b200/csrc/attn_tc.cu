@@ -339,11 +339,6 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
   return d;
 }
-__device__ __forceinline__ uint32_t ex2_bf16x2(uint32_t x) {
-  uint32_t y;
-  asm("ex2.approx.ftz.bf16x2 %0, %1;" : "=r"(y) : "r"(x));
-  return y;
-}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   uint32_t r[16];
   tmem_ld16_async(taddr, r);
@@ -699,14 +694,17 @@ static int fwd_launch(const CUtensorMap& tq, const CUtensorMap& tkv, const TcGeo
       EEC_CUDA(cudaFuncSetAttribute(attn_fwd_v2_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT2_SMEM));
       EEC_CUDA(cudaFuncSetAttribute(attn_fwd_v2_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT2_SMEM));
       EEC_CUDA(cudaFuncSetAttribute(attn_fwd_v2_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT2_SMEM));
+      EEC_CUDA(cudaFuncSetAttribute(attn_fwd_v2_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT2_SMEM));
       attr2 = true;
     }
-    if (general) launch_pdl(attn_fwd_v2_kernel<false, true>, pgrid, dim3(AT_THREADS), AT2_SMEM, st, tq, tkv, g, (__nv_bfloat16*)ctx, lse, drop, active_items(st));
+    if (general && drop.state) launch_pdl(attn_fwd_v2_kernel<true, true>, pgrid, dim3(AT_THREADS), AT2_SMEM, st, tq, tkv, g, (__nv_bfloat16*)ctx, lse, drop, active_items(st));
+    else if (general) launch_pdl(attn_fwd_v2_kernel<false, true>, pgrid, dim3(AT_THREADS), AT2_SMEM, st, tq, tkv, g, (__nv_bfloat16*)ctx, lse, drop, active_items(st));
     else if (drop.state) launch_pdl(attn_fwd_v2_kernel<true, false>, pgrid, dim3(AT_THREADS), AT2_SMEM, st, tq, tkv, g, (__nv_bfloat16*)ctx, lse, drop, active_items(st));
     else launch_pdl(attn_fwd_v2_kernel<false, false>, pgrid, dim3(AT_THREADS), AT2_SMEM, st, tq, tkv, g, (__nv_bfloat16*)ctx, lse, drop, active_items(st));
     EEC_LAUNCH_CHECK();
     return 0;
   }
+  EEC_CHECK_ARG(!(general && drop.state), "attention (two-pass kernel, EEC_ATTN_V2=0): dropout with the decoder masks is implemented by the v2 kernel only");
   if (general) launch_pdl(attn_fwd_tcp_kernel<false, true>, pgrid, dim3(AT_THREADS), AT_SMEM, st, tq, tkv, g, (__nv_bfloat16*)ctx, lse, drop, active_items(st));
   else if (drop.state) launch_pdl(attn_fwd_tcp_kernel<true, false>, pgrid, dim3(AT_THREADS), AT_SMEM, st, tq, tkv, g, (__nv_bfloat16*)ctx, lse, drop, active_items(st));
   else launch_pdl(attn_fwd_tcp_kernel<false, false>, pgrid, dim3(AT_THREADS), AT_SMEM, st, tq, tkv, g, (__nv_bfloat16*)ctx, lse, drop, active_items(st));
@@ -749,12 +747,11 @@ static int general_geom(const eec_attn_desc* d, TcGeom& g, CUtensorMap& tq, CUte
   return 0;
 }
 
-int attn_general_fwd_tc(const eec_attn_desc* d, void* ctx, int ldo, float* lse, cudaStream_t st) {
+int attn_general_fwd_tc(const eec_attn_desc* d, void* ctx, int ldo, float* lse, const DropArgs& drop, cudaStream_t st) {
   TcGeom g{};
   CUtensorMap tq, tkv;
   if (int r = general_geom(d, g, tq, tkv)) return r;
   g.ldo = ldo;
-  DropArgs drop{};
   return fwd_launch(tq, tkv, g, ctx, lse, drop, true, st);
 }
 

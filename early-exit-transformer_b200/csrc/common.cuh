@@ -212,9 +212,9 @@ __device__ __forceinline__ void drop_apply_bits(float (&x)[N], uint32_t word, fl
 
 // general (decoder) attention on the tensor cores; attn_general_tc_ok: can this geometry run there (else the CUDA-core kernels do it)
 bool attn_general_tc_ok(const eec_attn_desc* d);
-int attn_general_fwd_tc(const eec_attn_desc* d, void* ctx, int ldo, float* lse, cudaStream_t st);
+int attn_general_fwd_tc(const eec_attn_desc* d, void* ctx, int ldo, float* lse, const DropArgs& drop, cudaStream_t st);
 int attn_general_bwd_tc(const eec_attn_desc* d, const void* ctx, const void* dctx, int ldo, const float* lse, void* dq, int lddq, void* dk,
-                        int lddk, void* dv, int lddv, float* dvec, float* dq32, cudaStream_t st);
+                        int lddk, void* dv, int lddv, float* dvec, float* dq32, const DropArgs& drop, cudaStream_t st);
 int attn_bwd_tc(const void* qkv, const void* ctx, const void* dctx, const float* lse, const int32_t* key_len, void* dqkv,
                 float* dvec, float* dq32, int B, int T, int H, int dh, const DropArgs& drop, cudaStream_t st);
 int attn_fwd_tc(const void* qkv, const int32_t* key_len, void* ctx, float* lse, int B, int T, int H, int dh,

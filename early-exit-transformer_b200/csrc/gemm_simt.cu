@@ -24,10 +24,69 @@ struct SimtParams {
   ActiveItems act_items;   // rows past the active-item limit are skipped (early-exit inference)
 };
 
-template <typename TIn, typename TOut, typename TPre, bool ACC>
+// One operand tile [BK k][128 rows] of fp32 values into registers (8 per thread), for either operand major:
+//   K-major  (element (row, k) at base[row*ld + k]):  thread -> (row = idx / 4, k = 4 * (idx % 4)), one 16-byte load along k
+//   MN-major (element (row, k) at base[k*ld + row]):  thread -> (k = idx / 32, row = 4 * (idx % 32)), one 16-byte load along rows
+// idx = tid + 256 * i, i = 0, 1.  Vector loads need 16-byte alignment (VEC, decided on the host) and a fully in-range quad; anything else
+// (tile edges, bf16 operands of the debug cross-check) takes the scalar path with zero fill.
+template <typename TIn, bool KMAJ, bool VEC>
+__device__ __forceinline__ void load_tile(const TIn* __restrict__ base, long ld, int row0, int rows, int k0, int k_end, int tid, float (&r)[8]) {
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int idx = tid + NT * i;
+    const int row = KMAJ ? (idx >> 2) : ((idx & 31) << 2);
+    const int k = KMAJ ? ((idx & 3) << 2) : (idx >> 5);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (KMAJ) {
+      if (row0 + row < rows) {
+        const TIn* ptr = base + (long)(row0 + row) * ld + k0 + k;
+        if (VEC && sizeof(TIn) == 4 && k0 + k + 3 < k_end) {
+          v = *reinterpret_cast<const float4*>(ptr);
+        } else {
+          if (k0 + k < k_end) v.x = ld_as_float<TIn>(ptr);
+          if (k0 + k + 1 < k_end) v.y = ld_as_float<TIn>(ptr + 1);
+          if (k0 + k + 2 < k_end) v.z = ld_as_float<TIn>(ptr + 2);
+          if (k0 + k + 3 < k_end) v.w = ld_as_float<TIn>(ptr + 3);
+        }
+      }
+    } else {
+      if (k0 + k < k_end) {
+        const TIn* ptr = base + (long)(k0 + k) * ld + row0 + row;
+        if (VEC && sizeof(TIn) == 4 && row0 + row + 3 < rows) {
+          v = *reinterpret_cast<const float4*>(ptr);
+        } else {
+          if (row0 + row < rows) v.x = ld_as_float<TIn>(ptr);
+          if (row0 + row + 1 < rows) v.y = ld_as_float<TIn>(ptr + 1);
+          if (row0 + row + 2 < rows) v.z = ld_as_float<TIn>(ptr + 2);
+          if (row0 + row + 3 < rows) v.w = ld_as_float<TIn>(ptr + 3);
+        }
+      }
+    }
+    r[4 * i] = v.x; r[4 * i + 1] = v.y; r[4 * i + 2] = v.z; r[4 * i + 3] = v.w;
+  }
+}
+template <bool KMAJ>
+__device__ __forceinline__ void store_tile(float (*S)[BM + 4], int tid, const float (&r)[8]) {
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int idx = tid + NT * i;
+    if (KMAJ) {
+      const int row = idx >> 2, k = (idx & 3) << 2;
+      S[k][row] = r[4 * i]; S[k + 1][row] = r[4 * i + 1]; S[k + 2][row] = r[4 * i + 2]; S[k + 3][row] = r[4 * i + 3];
+    } else {
+      const int k = idx >> 5, row = (idx & 31) << 2;
+      *reinterpret_cast<float4*>(&S[k][row]) = make_float4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
+    }
+  }
+}
+
+// 128 x 128 x 16 tiles, 8 x 8 outputs per thread.  The next k-tile's operands are fetched into registers (16-byte loads) before the
+// current tile's 1024 FMAs per thread and stored into the OTHER shared-memory buffer afterwards: one barrier per k-tile and the
+// global-load latency hidden under the math.
+template <typename TIn, typename TOut, typename TPre, bool ACC, bool AK, bool BKM, bool VEC>
 __global__ void __launch_bounds__(NT) gemm_simt_kernel(SimtParams p) {
-  __shared__ float As[BK][BM + 4];
-  __shared__ float Bs[BK][BN + 4];
+  __shared__ float As[2][BK][BM + 4];
+  __shared__ float Bs[2][BK][BN + 4];
   const TIn* __restrict__ A = reinterpret_cast<const TIn*>(p.A);
   const TIn* __restrict__ B = reinterpret_cast<const TIn*>(p.B);
   const int tid = threadIdx.x;
@@ -41,35 +100,28 @@ __global__ void __launch_bounds__(NT) gemm_simt_kernel(SimtParams p) {
   for (int i = 0; i < 8; ++i)
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  const long lda = AK ? p.sa_m : p.sa_k, ldb = BKM ? p.sb_n : p.sb_k;
 
-  const bool a_k = (p.sa_k == 1), b_k = (p.sb_k == 1);
+  float ra[8], rb[8];
+  load_tile<TIn, AK, VEC>(A, lda, m0, p.M, k_begin, k_end, tid, ra);
+  load_tile<TIn, BKM, VEC>(B, ldb, n0, p.N, k_begin, k_end, tid, rb);
+  store_tile<AK>(As[0], tid, ra);
+  store_tile<BKM>(Bs[0], tid, rb);
+  __syncthreads();
+  int buf = 0;
   for (int k0 = k_begin; k0 < k_end; k0 += BK) {
-#pragma unroll
-    for (int i = 0; i < (BM * BK) / NT; ++i) {
-      int idx = tid + NT * i;
-      int m, k;
-      if (a_k) { m = idx / BK; k = idx % BK; } else { m = idx % BM; k = idx / BM; }
-      float v = 0.f;
-      if (m0 + m < p.M && k0 + k < k_end) v = ld_as_float<TIn>(A + (long)(m0 + m) * p.sa_m + (long)(k0 + k) * p.sa_k);
-      As[k][m] = v;
+    const bool more = k0 + BK < k_end;
+    if (more) {
+      load_tile<TIn, AK, VEC>(A, lda, m0, p.M, k0 + BK, k_end, tid, ra);
+      load_tile<TIn, BKM, VEC>(B, ldb, n0, p.N, k0 + BK, k_end, tid, rb);
     }
-#pragma unroll
-    for (int i = 0; i < (BN * BK) / NT; ++i) {
-      int idx = tid + NT * i;
-      int n, k;
-      if (b_k) { n = idx / BK; k = idx % BK; } else { n = idx % BN; k = idx / BN; }
-      float v = 0.f;
-      if (n0 + n < p.N && k0 + k < k_end) v = ld_as_float<TIn>(B + (long)(n0 + n) * p.sb_n + (long)(k0 + k) * p.sb_k);
-      Bs[k][n] = v;
-    }
-    __syncthreads();
 #pragma unroll
     for (int k = 0; k < BK; ++k) {
       float a[8], b[8];
-      float4 a0 = *reinterpret_cast<const float4*>(&As[k][ty * 8]);
-      float4 a1 = *reinterpret_cast<const float4*>(&As[k][ty * 8 + 4]);
-      float4 b0 = *reinterpret_cast<const float4*>(&Bs[k][tx * 8]);
-      float4 b1 = *reinterpret_cast<const float4*>(&Bs[k][tx * 8 + 4]);
+      float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 8]);
+      float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 8 + 4]);
+      float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 8]);
+      float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 8 + 4]);
       a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
       b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w; b[4] = b1.x; b[5] = b1.y; b[6] = b1.z; b[7] = b1.w;
 #pragma unroll
@@ -77,7 +129,12 @@ __global__ void __launch_bounds__(NT) gemm_simt_kernel(SimtParams p) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
     }
-    __syncthreads();
+    if (more) {
+      store_tile<AK>(As[buf ^ 1], tid, ra);
+      store_tile<BKM>(Bs[buf ^ 1], tid, rb);
+      __syncthreads();
+      buf ^= 1;
+    }
   }
 
   TOut* __restrict__ C = reinterpret_cast<TOut*>(p.C);
@@ -135,12 +192,31 @@ __global__ void glu_tail_kernel(const T* __restrict__ z, int ldz, T* __restrict_
   st_from_float<T>(out + (long)r * ldo + c, alpha * a * s);
 }
 
-template <typename TIn, typename TOut, typename TPre>
-static int launch(const SimtParams& p, dim3 grid, cudaStream_t st, bool acc) {
-  if (acc) gemm_simt_kernel<TIn, TOut, TPre, true><<<grid, NT, 0, st>>>(p);
-  else gemm_simt_kernel<TIn, TOut, TPre, false><<<grid, NT, 0, st>>>(p);
+template <typename TIn, typename TOut, typename TPre, bool ACC>
+static int launch2(const SimtParams& p, dim3 grid, cudaStream_t st) {
+  const bool ak = p.sa_k == 1, bk = p.sb_k == 1;
+  // 16-byte operand loads: fp32 operands, 16-byte aligned bases and row pitches, k ranges that start on a multiple of 4
+  const long lda = ak ? p.sa_m : p.sa_k, ldb = bk ? p.sb_n : p.sb_k;
+  const bool vec = sizeof(TIn) == 4 && (reinterpret_cast<uintptr_t>(p.A) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.B) & 15) == 0 &&
+                   lda % 4 == 0 && ldb % 4 == 0 && p.k_per_split % 4 == 0;
+#define EEC_SIMT(AKV, BKV, VECV) gemm_simt_kernel<TIn, TOut, TPre, ACC, AKV, BKV, VECV><<<grid, NT, 0, st>>>(p)
+  if constexpr (sizeof(TIn) == 4) {
+    if (vec) {
+      if (ak && bk) EEC_SIMT(true, true, true); else if (ak) EEC_SIMT(true, false, true); else if (bk) EEC_SIMT(false, true, true); else EEC_SIMT(false, false, true);
+      EEC_LAUNCH_CHECK();
+      return 0;
+    }
+  }
+  {
+    if (ak && bk) EEC_SIMT(true, true, false); else if (ak) EEC_SIMT(true, false, false); else if (bk) EEC_SIMT(false, true, false); else EEC_SIMT(false, false, false);
+  }
+#undef EEC_SIMT
   EEC_LAUNCH_CHECK();
   return 0;
+}
+template <typename TIn, typename TOut, typename TPre>
+static int launch(const SimtParams& p, dim3 grid, cudaStream_t st, bool /*acc == (TIn is fp32): accurate expf for the parity path*/) {
+  return launch2<TIn, TOut, TPre, sizeof(TIn) == 4>(p, grid, st);
 }
 
 int gemm_simt(const eec_gemm_desc* d, cudaStream_t st) {

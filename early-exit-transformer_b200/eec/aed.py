@@ -44,9 +44,17 @@ class _DecoderFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, module, want_tape, cfg, exits, mem_index, trg, hidden, *params):
         P = module._decoder_tensor_dict()
+        drop0 = None
+        if module.training and cfg.drop_p > 0.0:
+            # this forward's own {seed, offset} (the decoder shares the module's counter with the encoder half: every forward, encoder or
+            # decoder, advances it, and backward regenerates its masks from the snapshot)
+            st = module._dropout_state(hidden.device)
+            with on_device(hidden.device):
+                drop0 = ops.Drop(st.clone(), cfg.drop_p, 0)
+                ops.dropout_advance(st)
         with on_device(hidden.device):
             out, tape = decoder_engine.decoder_forward(P, module._dec_operands, cfg, module.n_dec_layers, trg.to(hidden.device),
-                                                       module.trg_pad_idx, hidden.contiguous(), exits, mem_index, want_tape)
+                                                       module.trg_pad_idx, hidden.contiguous(), exits, mem_index, want_tape, drop0)
         ctx.module, ctx.tape, ctx.P, ctx.cfg, ctx.hshape = module, tape, P, cfg, tuple(hidden.shape)
         return out
 
@@ -173,9 +181,6 @@ class full_conformer(_EarlyExitBase):
     def _decode(self, trg: Tensor, hidden: Tensor, exits: List[int], mem_index: List[int]) -> Tensor:
         """decoder stacks `exits` (0-based), stack exits[i] attending to hidden[mem_index[i]] -> logits [len(exits), B, L, V]"""
         self._check_supported()
-        if self.training and float(self.dropout) > 0.0:
-            raise EecError("eec.full_conformer: train-mode dropout inside the decoder stacks is not implemented yet (the encoder half "
-                           "supports it): build the model with drop_prob=0 for AED training, or call .eval()")
         names = self._decoder_param_names
         expect = decoder_engine.decoder_param_names(self.n_enc_exits, self.n_dec_layers)
         if names != expect:

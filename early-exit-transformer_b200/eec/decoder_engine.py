@@ -24,6 +24,11 @@ from .engine import D, F, H, V, Config, Operands, _empty, dgrad, linear, to_act,
 from .lib import ACT_DRELU, ACT_RELU, EecError
 
 Tensor = torch.Tensor
+# dropout sites (train mode, drop_prob > 0; include/eec.h "dropout"): after emb + positional encoding (positional_encoding.py:72); per
+# decoder layer (stack e, layer l) SITE_BASE + 8 * (e * n_dec + l) + k -- nn.TransformerDecoderLayer's self-attention probabilities
+# (nn.MultiheadAttention(dropout = p)) and dropout1, cross-attention probabilities and dropout2, the feed-forward's inner dropout and dropout3
+SITE_PE, SITE_BASE = 99999, 100000
+D_SA_P, D_SA_OUT, D_CA_P, D_CA_OUT, D_FF_ACT, D_FF_OUT = range(6)
 
 
 def _layer_prefix(e: int, l: int) -> str:
@@ -52,7 +57,7 @@ def _kv_stack(P, W: Operands, e: int, n_dec: int, cfg: Config):
 
 
 def decoder_forward(P: Dict[str, Tensor], W: Operands, cfg: Config, n_dec: int, trg: Tensor, pad_idx: int, hidden: Tensor,
-                    exits: List[int], mem_index: List[int], want_tape: bool):
+                    exits: List[int], mem_index: List[int], want_tape: bool, drop0: Optional[ops.Drop] = None):
     """trg [B, L] int64 (device); hidden [M, B, T, D] fp32 encoder states; exits: which decoder stacks to run, stack exits[i] attending to
     hidden[mem_index[i]].  -> (logits [len(exits), B, L, V] fp32, tape | None)"""
     if not hidden.is_cuda or not trg.is_cuda:
@@ -67,9 +72,20 @@ def decoder_forward(P: Dict[str, Tensor], W: Operands, cfg: Config, n_dec: int, 
     trg = trg.contiguous()
     x0 = _empty((Nd, D), f32, dev)
     ops.embed_pe(trg, P["emb.weight"].detach(), pe.view(-1, D), x0)           # early_exit.py:776-777 (no sqrt(d) scaling)
+    bf16 = cfg.precision == "bf16"
+    if drop0 is not None:
+        ops.dropout(x0, x0, drop0.at(SITE_PE))                                # positional_encoding.py:72
+
+    def site(e, l, k, R=0, C=0, Cs=0, Wd=0):
+        """dropout site k of decoder layer (e, l); the tensor-core kernels get its keep-mask words (generated here, shared with backward)"""
+        if drop0 is None:
+            return None
+        d = drop0.at(SITE_BASE + 8 * (e * n_dec + l) + k)
+        return d.with_bits(R, C, Cs, Wd) if (bf16 and Wd) else d
     key_bits = ops.key_bits_from_tokens(trg, pad_idx)                          # tgt_key_padding_mask (:773-775, :802-805)
     out = _empty((len(exits), B, Ln, V), f32, dev)
-    tape = {"B": B, "L": Ln, "T": T, "trg": trg, "key_bits": key_bits, "exits": [], "n_dec": n_dec} if want_tape else None
+    tape = {"B": B, "L": Ln, "T": T, "trg": trg, "key_bits": key_bits, "exits": [], "n_dec": n_dec, "drop0": drop0} if want_tape else None
+    L8, T8 = 8 * ((Ln + 7) // 8), 8 * ((T + 7) // 8)
 
     def stat():
         return (_empty((Nd,), f32, dev), _empty((Nd,), f32, dev)) if want_tape else (None, None)
@@ -99,12 +115,13 @@ def decoder_forward(P: Dict[str, Tensor], W: Operands, cfg: Config, n_dec: int, 
             linear(u, Wsi, qkv, Nd, 3 * D, D, bias=P[p + "self_attn.in_proj_bias"])
             ctx = _empty((Nd, D), TD, dev)
             lse1 = _empty((B, H, Ln), f32, dev)
-            ops.attn_general_fwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], ctx, lse1, B, Ln, Ln, H, key_bits=key_bits, causal=True)
+            d_sap = site(e, l, D_SA_P, B * H * Ln, Ln, L8, 32)
+            ops.attn_general_fwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], ctx, lse1, B, Ln, Ln, H, key_bits=key_bits, causal=True, drop=d_sap)
             y1 = _empty((Nd, D), f32, dev)
             u2 = _empty((Nd, D), TD, dev)
             m2, r2 = stat()
             linear(ctx, Wso, y1, Nd, D, D, bias=P[p + "self_attn.out_proj.bias"], residual=y, ln_gamma=P[p + "norm2.weight"],
-                   ln_beta=P[p + "norm2.bias"], ln_out=u2, ln_mean=m2, ln_rstd=r2)
+                   ln_beta=P[p + "norm2.bias"], ln_out=u2, ln_mean=m2, ln_rstd=r2, drop=site(e, l, D_SA_OUT, Nd, D, D, 32))
             # ---- cross-attention over the encoder states (no memory mask)
             Wci = W.get(p + "multihead_attn.in_proj_weight", P[p + "multihead_attn.in_proj_weight"], (3 * D, D))
             Wco = W.get(p + "multihead_attn.out_proj.weight", P[p + "multihead_attn.out_proj.weight"], (D, D))
@@ -113,25 +130,27 @@ def decoder_forward(P: Dict[str, Tensor], W: Operands, cfg: Config, n_dec: int, 
             ctx2 = _empty((Nd, D), TD, dev)
             lse2 = _empty((B, H, Ln), f32, dev)
             c0 = l * 2 * D
-            ops.attn_general_fwd(q2, kvall[:, c0:c0 + D], kvall[:, c0 + D:c0 + 2 * D], ctx2, lse2, B, Ln, T, H)
+            d_cap = site(e, l, D_CA_P, B * H * Ln, T, T8, 32)
+            ops.attn_general_fwd(q2, kvall[:, c0:c0 + D], kvall[:, c0 + D:c0 + 2 * D], ctx2, lse2, B, Ln, T, H, drop=d_cap)
             y2 = _empty((Nd, D), f32, dev)
             u3 = _empty((Nd, D), TD, dev)
             m3, r3 = stat()
             linear(ctx2, Wco, y2, Nd, D, D, bias=P[p + "multihead_attn.out_proj.bias"], residual=y1, ln_gamma=P[p + "norm3.weight"],
-                   ln_beta=P[p + "norm3.bias"], ln_out=u3, ln_mean=m3, ln_rstd=r3)
+                   ln_beta=P[p + "norm3.bias"], ln_out=u3, ln_mean=m3, ln_rstd=r3, drop=site(e, l, D_CA_OUT, Nd, D, D, 32))
             # ---- feed-forward (ReLU)
             W1 = W.get(p + "linear1.weight", P[p + "linear1.weight"], (F, D))
             W2 = W.get(p + "linear2.weight", P[p + "linear2.weight"], (D, F))
             a = _empty((Nd, F), TD, dev)
-            linear(u3, W1, a, Nd, F, D, bias=P[p + "linear1.bias"], act=ACT_RELU)
+            d_act = site(e, l, D_FF_ACT, Nd, F, F, 16)
+            linear(u3, W1, a, Nd, F, D, bias=P[p + "linear1.bias"], act=ACT_RELU, drop=d_act)
             y3 = _empty((Nd, D), f32, dev)
             un = _empty((Nd, D), TD, dev)
             mn, rn = stat()
             linear(a, W2, y3, Nd, D, F, bias=P[p + "linear2.bias"], residual=y2, ln_gamma=nxt_g, ln_beta=nxt_b, ln_out=un, ln_mean=mn,
-                   ln_rstd=rn)
+                   ln_rstd=rn, drop=site(e, l, D_FF_OUT, Nd, D, D, 32))
             if want_tape:
                 et["layers"].append(dict(y=y, u=u, m1=m1, r1=r1, qkv=qkv, ctx=ctx, lse1=lse1, y1=y1, u2=u2, m2=m2, r2=r2, q2=q2, ctx2=ctx2,
-                                         lse2=lse2, y2=y2, u3=u3, m3=m3, r3=r3, a=a, y3=y3, mn=mn, rn=rn))
+                                         lse2=lse2, y2=y2, u3=u3, m3=m3, r3=r3, a=a, y3=y3, mn=mn, rn=rn, d_sap=d_sap, d_cap=d_cap, d_act=d_act))
             y, u, m1, r1 = y3, un, mn, rn
         Wl = W.get(f"linears_2.{e}.weight", P[f"linears_2.{e}.weight"], (V, D))
         linear(u, Wl, out[oi].view(Nd, V), Nd, V, D, bias=P[f"linears_2.{e}.bias"])
@@ -158,17 +177,22 @@ def decoder_backward(P, W: Operands, cfg: Config, tape: dict, gout: Tensor, name
     G["__flat__"] = flat
     gout = gout.contiguous()
     dX0 = torch.zeros(Nd, D, dtype=f32, device=dev)
+    drop0 = tape.get("drop0")
+
+    def osite(e, l, k):
+        return drop0.at(SITE_BASE + 8 * (e * n_dec + l) + k) if drop0 is not None else None
 
     for oi, et in enumerate(tape["exits"]):
         e = et["e"]
         dX = _empty((Nd, D), f32, dev)
 
-        def ln_bwd(dy, x_in, m, r, key, accumulate, bias_key=None, want_h=True):
+        def ln_bwd(dy, x_in, m, r, key, accumulate, bias_key=None, want_h=True, dsite=None):
             """LayerNorm backward into the residual-gradient stream dX (+ operand copy of the new dX, + its column sums = the bias gradient
-            of the projection whose output joined the residual stream right before this LayerNorm in the forward pass)"""
-            dXh = _empty((Nd, D), TD, dev) if (bf16 and want_h) else None
+            of the projection whose output joined the residual stream right before this LayerNorm in the forward pass; dsite: that output
+            went through dropout -- copy and column sums carry dropout'(dX), the residual gradient itself does not)"""
+            dXh = _empty((Nd, D), TD, dev) if ((bf16 or dsite is not None) and want_h) else None
             ops.layernorm_bwd(dy, x_in, m, r, P[key + "weight"], dX, accumulate, G[key + "weight"], G[key + "bias"], dXh,
-                              G[bias_key] if bias_key else None, 1.0)
+                              G[bias_key] if bias_key else None, 1.0, drop=dsite)
             return dXh if dXh is not None else dX
 
         # ---- linears_2 + the shared final LayerNorm
@@ -184,7 +208,8 @@ def decoder_backward(P, W: Operands, cfg: Config, tape: dict, gout: Tensor, name
         dz = _empty((Nd, D), f32, dev)
         dgrad(dlogh, Wl, dz, Nd, V, D)
         last = et["layers"][-1]
-        dXh = ln_bwd(dz, last["y3"], last["mn"], last["rn"], "layer_norm.", False, _layer_prefix(e, n_dec - 1) + "linear2.bias")
+        dXh = ln_bwd(dz, last["y3"], last["mn"], last["rn"], "layer_norm.", False, _layer_prefix(e, n_dec - 1) + "linear2.bias",
+                     dsite=osite(e, n_dec - 1, D_FF_OUT))
         dkvall = _empty((Ne, n_dec * 2 * D), TD, dev)
         for l in reversed(range(n_dec)):
             p = _layer_prefix(e, l)
@@ -194,11 +219,11 @@ def decoder_backward(P, W: Operands, cfg: Config, tape: dict, gout: Tensor, name
             W2 = W.get(p + "linear2.weight", P[p + "linear2.weight"], (D, F))
             wgrad(dXh, t["a"], G[p + "linear2.weight"], Nd, D, F)
             dh = _empty((Nd, F), TD, dev)
-            dgrad(dXh, W2, dh, Nd, D, F, act=ACT_DRELU, preact=t["a"])
+            dgrad(dXh, W2, dh, Nd, D, F, act=ACT_DRELU, preact=t["a"], drop=t["d_act"])
             wgrad(dh, t["u3"], G[p + "linear1.weight"], Nd, F, D, dbias=G[p + "linear1.bias"])
             du3 = _empty((Nd, D), f32, dev)
             dgrad(dh, W1, du3, Nd, F, D)
-            dXh = ln_bwd(du3, t["y2"], t["m3"], t["r3"], p + "norm3.", True, p + "multihead_attn.out_proj.bias")
+            dXh = ln_bwd(du3, t["y2"], t["m3"], t["r3"], p + "norm3.", True, p + "multihead_attn.out_proj.bias", dsite=osite(e, l, D_CA_OUT))
             # cross-attention: y2 = y1 + Wo ctx2 + bo
             Wci = W.get(p + "multihead_attn.in_proj_weight", P[p + "multihead_attn.in_proj_weight"], (3 * D, D))
             Wco = W.get(p + "multihead_attn.out_proj.weight", P[p + "multihead_attn.out_proj.weight"], (D, D))
@@ -209,11 +234,11 @@ def decoder_backward(P, W: Operands, cfg: Config, tape: dict, gout: Tensor, name
             c0 = l * 2 * D
             kv = et["kvall"]
             ops.attn_general_bwd(t["q2"], kv[:, c0:c0 + D], kv[:, c0 + D:c0 + 2 * D], t["ctx2"], dctx2, t["lse2"], dq2,
-                                 dkvall[:, c0:c0 + D], dkvall[:, c0 + D:c0 + 2 * D], B, Ln, T, H)
+                                 dkvall[:, c0:c0 + D], dkvall[:, c0 + D:c0 + 2 * D], B, Ln, T, H, drop=t["d_cap"])
             wgrad(dq2, t["u2"], G[p + "multihead_attn.in_proj_weight"][:D], Nd, D, D, dbias=G[p + "multihead_attn.in_proj_bias"][:D])
             du2 = _empty((Nd, D), f32, dev)
             dgrad(dq2, Wci[:D], du2, Nd, D, D)
-            dXh = ln_bwd(du2, t["y1"], t["m2"], t["r2"], p + "norm2.", True, p + "self_attn.out_proj.bias")
+            dXh = ln_bwd(du2, t["y1"], t["m2"], t["r2"], p + "norm2.", True, p + "self_attn.out_proj.bias", dsite=osite(e, l, D_SA_OUT))
             # self-attention: y1 = y + Wo ctx + bo
             Wsi = W.get(p + "self_attn.in_proj_weight", P[p + "self_attn.in_proj_weight"], (3 * D, D))
             Wso = W.get(p + "self_attn.out_proj.weight", P[p + "self_attn.out_proj.weight"], (D, D))
@@ -223,12 +248,13 @@ def decoder_backward(P, W: Operands, cfg: Config, tape: dict, gout: Tensor, name
             dqkv = _empty((Nd, 3 * D), TD, dev)
             qkv = t["qkv"]
             ops.attn_general_bwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], t["ctx"], dctx, t["lse1"], dqkv[:, :D], dqkv[:, D:2 * D],
-                                 dqkv[:, 2 * D:], B, Ln, Ln, H, key_bits=tape["key_bits"], causal=True)
+                                 dqkv[:, 2 * D:], B, Ln, Ln, H, key_bits=tape["key_bits"], causal=True, drop=t["d_sap"])
             wgrad(dqkv, t["u"], G[p + "self_attn.in_proj_weight"], Nd, 3 * D, D, dbias=G[p + "self_attn.in_proj_bias"])
             du = _empty((Nd, D), f32, dev)
             dgrad(dqkv, Wsi, du, Nd, 3 * D, D)
             prev_bias = _layer_prefix(e, l - 1) + "linear2.bias" if l > 0 else None
-            dXh = ln_bwd(du, t["y"], t["m1"], t["r1"], p + "norm1.", True, prev_bias, want_h=l > 0)
+            dXh = ln_bwd(du, t["y"], t["m1"], t["r1"], p + "norm1.", True, prev_bias, want_h=l > 0,
+                         dsite=osite(e, l - 1, D_FF_OUT) if l > 0 else None)
         ops.axpy(dX, 1.0, dX0)                                   # every stack reads the same embedded targets
         # ---- K / V projections of the encoder states, all layers of the stack at once
         dwkv = torch.zeros(n_dec * 2 * D, D, dtype=f32, device=dev)
@@ -240,5 +266,7 @@ def decoder_backward(P, W: Operands, cfg: Config, tape: dict, gout: Tensor, name
             G[p + "multihead_attn.in_proj_bias"][D:].copy_(dbkv[l * 2 * D:(l + 1) * 2 * D])
         gh = ghid[et["mi"]].view(Ne, D)
         dgrad(dkvall, et["wkv"], gh, Ne, n_dec * 2 * D, D, residual=gh)
+    if drop0 is not None:
+        ops.dropout(dX0, dX0, drop0.at(SITE_PE))
     ops.embed_bwd(tape["trg"], dX0, G["emb.weight"])
     return G

@@ -53,6 +53,7 @@ class AttnDesc(C.Structure):
         ("key_len", vp),
         ("key_valid_bits", vp),
         ("causal", i32),
+        ("drop_state", vp), ("drop_p", f32), ("drop_site", u32), ("drop_bits", vp),
     ]
 
 

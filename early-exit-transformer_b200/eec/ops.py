@@ -152,7 +152,7 @@ def attn_bwd(qkv, ctx, dctx, lse, key_len, dqkv, dvec, B, T, H, dq32=None, drop:
          H, 32, *_d(drop), _bits(drop), stream())
 
 
-def _attn_desc(q, k, v, B, Tq, Tk, H, key_len, key_bits, causal):
+def _attn_desc(q, k, v, B, Tq, Tk, H, key_len, key_bits, causal, drop=None):
     """q / k / v: 2-D views (rows, H*32) of row-major tensors -- a column block of a packed projection output is passed as its slice"""
     for t, n in ((q, "q"), (k, "k"), (v, "v")):
         if not t.is_cuda or t.dim() != 2 or t.stride(1) != 1:
@@ -166,18 +166,23 @@ def _attn_desc(q, k, v, B, Tq, Tk, H, key_len, key_bits, causal):
     d.v, d.ldv = v.data_ptr(), v.stride(0)
     d.dtype = dt(q)
     d.key_len, d.key_valid_bits, d.causal = ptr(key_len), ptr(key_bits), int(bool(causal))
+    if drop is not None and drop.p > 0.0:
+        if drop.bits is None and q.dtype == torch.bfloat16:
+            raise L.EecError("attn: bf16 dropout needs the site's keep-mask words (Drop.with_bits(B*H*Tq, Tk, 8*ceil(Tk/8), 32))")
+        d.drop_state, d.drop_p, d.drop_site = _d(drop)
+        d.drop_bits = ptr(drop.bits)
     return d
 
 
-def attn_general_fwd(q, k, v, ctx, lse, B, Tq, Tk, H, key_len=None, key_bits=None, causal=False):
+def attn_general_fwd(q, k, v, ctx, lse, B, Tq, Tk, H, key_len=None, key_bits=None, causal=False, drop=None):
     """include/eec.h::eec_attn_general_fwd (decoder self-attention with causal / padding masks, cross-attention over encoder states)"""
-    d = _attn_desc(q, k, v, B, Tq, Tk, H, key_len, key_bits, causal)
+    d = _attn_desc(q, k, v, B, Tq, Tk, H, key_len, key_bits, causal, drop)
     call("eec_attn_general_fwd", C.byref(d), ptr(ctx), ctx.stride(0), ptr(lse), stream())
 
 
-def attn_general_bwd(q, k, v, ctx, dctx, lse, dq, dk, dv, B, Tq, Tk, H, key_len=None, key_bits=None, causal=False):
+def attn_general_bwd(q, k, v, ctx, dctx, lse, dq, dk, dv, B, Tq, Tk, H, key_len=None, key_bits=None, causal=False, drop=None):
     """dq / dk / dv: 2-D views like q / k / v (written, not accumulated)"""
-    d = _attn_desc(q, k, v, B, Tq, Tk, H, key_len, key_bits, causal)
+    d = _attn_desc(q, k, v, B, Tq, Tk, H, key_len, key_bits, causal, drop)
     dev = q.device
     dvec = torch.empty(B * H * Tq, dtype=torch.float32, device=dev)
     dq32 = torch.empty(B * Tq, H * 32, dtype=torch.float32, device=dev) if q.dtype == torch.bfloat16 else None

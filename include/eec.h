@@ -156,6 +156,10 @@ typedef struct {
   const int32_t* key_len;           /* [B] or NULL */
   const uint32_t* key_valid_bits;   /* [B, ceil(Tk/32)] or NULL */
   int causal;
+  /* dropout on the attention probabilities (nn.MultiheadAttention(dropout = p) inside the decoder layers), same conventions as
+   * eec_attn_fwd: element index of probability (b, h, t, t') is ((b*H + h)*Tq + t) * (8*ceil(Tk/8)) + t'; EEC_BF16 needs the keep-mask
+   * words of eec_dropout_bits(R = B*H*Tq, C = Tk, Cs = 8*ceil(Tk/8), W = 32) in drop_bits; drop_state NULL = off */
+  const uint64_t* drop_state; float drop_p; uint32_t drop_site; const void* drop_bits;
 } eec_attn_desc;
 int eec_attn_general_fwd(const eec_attn_desc* d, void* ctx, int ldo, float* lse, eec_stream_t stream);
 /* dq [B*Tq rows, lddq], dk / dv [B*Tk rows, lddk / lddv] are WRITTEN (head h at column h*dh of the given pointers); dvec: fp32
