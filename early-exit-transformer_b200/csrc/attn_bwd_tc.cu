@@ -35,13 +35,19 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-// D[b,h,t] = sum_d dO[b,t,h,d] * O[b,t,h,d]      (one warp per frame row: lane owns 8 channels = 1/4 head)
+// D[b,h,t] = sum_d dO[b,t,h,d] * O[b,t,h,d]      (one warp per frame row: lane owns 8 channels = 1/4 head); the same pass zeroes the row
+// of the fp32 dQ workspace the main kernel accumulates into (it used to be a separate memset node per layer)
 __global__ void __launch_bounds__(256) attn_dvec_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ d_o, int ldo,
-                                                        float* __restrict__ dvec, int B, int T, int H) {
+                                                        float* __restrict__ dvec, float* __restrict__ dq32, int B, int T, int H) {
   pdl_trigger();
   pdl_wait();
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (row >= B * T) return;
+  {
+    float4* z = reinterpret_cast<float4*>(dq32 + (long)row * 256 + lane * 8);
+    z[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+    z[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
   float a[8], g[8];
   ld8<__nv_bfloat16>(o + (long)row * ldo + lane * 8, a);
   ld8<__nv_bfloat16>(d_o + (long)row * ldo + lane * 8, g);
@@ -355,9 +361,8 @@ static int bwd_launch(const CUtensorMap& tq, const CUtensorMap& tkv, const CUten
                       const void* dctx, int ldo, const float* lse, float* dvec, float* dq32, void* dq, int lddq, const DropArgs& drop,
                       bool general, cudaStream_t st) {
   const long rows = (long)B * g.Tq;
-  launch_pdl(attn_dvec_kernel, dim3((int)cdiv64(rows * 32, 256)), dim3(256), 0, st, (const __nv_bfloat16*)ctx, (const __nv_bfloat16*)dctx, ldo, dvec, B, g.Tq, g.H);
+  launch_pdl(attn_dvec_kernel, dim3((int)cdiv64(rows * 32, 256)), dim3(256), 0, st, (const __nv_bfloat16*)ctx, (const __nv_bfloat16*)dctx, ldo, dvec, dq32, B, g.Tq, g.H);
   EEC_LAUNCH_CHECK();
-  EEC_CUDA(cudaMemsetAsync(dq32, 0, (size_t)rows * 256 * sizeof(float), st));
   static bool attr_set = false;
   if (!attr_set) {
     EEC_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BW_SMEM));

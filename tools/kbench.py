@@ -125,6 +125,32 @@ if "ln" in which:
     o = torch.empty(N, 256, device=dev, dtype=torch.bfloat16)
     report("layernorm fwd fp32->bf16", timeit(lambda: ops.layernorm_fwd(x, g, b_, o)), None, N * 256 * 6)
 
+if "lnbwd" in which:
+    x = torch.randn(N, 256, device=dev); dy = torch.randn(N, 256, device=dev)
+    g = torch.ones(256, device=dev); b_ = torch.zeros(256, device=dev)
+    o = torch.empty(N, 256, device=dev, dtype=torch.bfloat16); mean = torch.empty(N, device=dev); rstd = torch.empty(N, device=dev)
+    ops.layernorm_fwd(x, g, b_, o, mean, rstd)
+    dx = torch.zeros(N, 256, device=dev); dcopy = torch.empty(N, 256, device=dev, dtype=torch.bfloat16)
+    dg_, db_, cs_ = torch.zeros(256, device=dev), torch.zeros(256, device=dev), torch.zeros(256, device=dev)
+    report("layernorm bwd (+bf16 copy, dgamma/dbeta, colsum)", timeit(lambda: ops.layernorm_bwd(dy, x, mean, rstd, g, dx, True, dg_, db_, dcopy, cs_, 1.0)), None, N * 256 * 18 + N * 8)
+
+if "beam" in which:
+    lp6 = torch.log_softmax(torch.randn(6, B, T, 256, device=dev), -1)
+    dec = eec.cuda_ctc_decoder([str(i) for i in range(256)], nbest=1, beam_size=10, blank_skip_threshold=0.95)
+    report("ctc prefix beam search, 6 exits x 64 utts, beam 10", timeit(lambda: dec.search(lp6), n=5), None, lp6.numel() * 4)
+
+if "dec" in which:
+    Ld = 82
+    Nd = B * Ld
+    qkv_d = bf(Nd, 768); kv_e = bf(N, 3072); q_d = bf(Nd, 256)
+    toks = torch.randint(3, 120, (B, Ld), device=dev); toks[:, 60:] = 126
+    bits = ops.key_bits_from_tokens(toks, 126)
+    ctx_d = torch.empty(Nd, 256, device=dev, dtype=torch.bfloat16); lse_d = torch.empty(B, H, Ld, device=dev)
+    report("decoder causal self-attention fwd (L = 82)", timeit(lambda: ops.attn_general_fwd(qkv_d[:, :256], qkv_d[:, 256:512], qkv_d[:, 512:], ctx_d, lse_d, B, Ld, Ld, H, key_bits=bits, causal=True)), 4.0 * B * H * Ld * Ld * 32)
+    report("decoder cross-attention fwd (82 x 374)", timeit(lambda: ops.attn_general_fwd(q_d, kv_e[:, 512:768], kv_e[:, 768:1024], ctx_d, lse_d, B, Ld, T, H)), 4.0 * B * H * Ld * T * 32)
+    dctx_d = bf(Nd, 256); dq_d = torch.empty(Nd, 256, device=dev, dtype=torch.bfloat16); dkv_e = torch.empty(N, 512, device=dev, dtype=torch.bfloat16)
+    report("decoder cross-attention bwd (82 x 374)", timeit(lambda: ops.attn_general_bwd(q_d, kv_e[:, 512:768], kv_e[:, 768:1024], ctx_d, dctx_d, lse_d, dq_d, dkv_e[:, :256], dkv_e[:, 256:], B, Ld, T, H), n=3, warm=1), 10.0 * B * H * Ld * T * 32)
+
 if "ctc" in which:
     from oracle import conformer_oracle as O
     lp = torch.log_softmax(torch.randn(6, B, T, 256, device=dev), -1)
