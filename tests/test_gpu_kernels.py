@@ -90,6 +90,36 @@ def test_gemm_epilogues(ops, dtype):
     assert rel(Cacc, 1.0 + 0.5 * Am.double().cpu().t() @ Bm.double().cpu()) < (1e-5 if dtype == torch.float32 else 2e-5)
 
 
+@pytest.mark.parametrize("M,N", [(300, 512), (128 * 5 + 7, 2048), (23936, 768), (64, 256)])
+def test_gemm_weight_stationary(ops, M, N):
+    """K = 256 projections with a bf16 output run on the weight-stationary kernel (csrc/gemm_ws.cu): bias, SiLU, SiLU + stored
+    pre-activation (K-major weights) and the dSiLU data gradient (MN-major weights), incl. an m-tile tail and several CTAs per
+    weight tile; EEC_GEMM_WS=0 routes the same descriptors to the v3 kernel."""
+    K = 256
+    A = rnd(M, K, seed=31, dtype=torch.bfloat16)
+    W = rnd(N, K, seed=32, scale=0.1, dtype=torch.bfloat16)
+    bias = rnd(N, seed=33)
+    base = ref_gemm(A, W, True, True) + bias.double().cpu()
+    out = torch.full((M, N), float("nan"), device="cuda", dtype=torch.bfloat16)
+    ops.gemm(A, W, out, M, N, K, bias=bias)
+    assert rel(out, base) < 6e-3
+    out.fill_(float("nan"))
+    ops.gemm(A, W, out, M, N, K, bias=bias, act=ops.ACT_SILU)
+    assert rel(out, base * torch.sigmoid(base)) < 8e-3
+    out.fill_(float("nan"))
+    pre = torch.full((M, N), float("nan"), device="cuda", dtype=torch.bfloat16)
+    ops.gemm(A, W, out, M, N, K, bias=bias, act=ops.ACT_SILU, preact=pre)
+    assert rel(pre, base) < 6e-3
+    assert rel(out, base * torch.sigmoid(base)) < 8e-3
+    # dSiLU data gradient: dH = alpha * (dY Wt) o dSiLU(pre), Wt [K, N] (MN-major B)
+    Wt = rnd(K, N, seed=34, scale=0.1, dtype=torch.bfloat16)
+    dh = torch.full((M, N), float("nan"), device="cuda", dtype=torch.bfloat16)
+    ops.gemm(A, Wt, dh, M, N, K, a_kmajor=True, b_kmajor=False, lda=K, ldb=N, act=ops.ACT_DSILU, preact=pre, alpha=0.5)
+    h = pre.double().cpu()
+    sg = torch.sigmoid(h)
+    assert rel(dh, 0.5 * ref_gemm(A, Wt, True, False) * (sg * (1 + h * (1 - sg)))) < 8e-3
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_gemm_layernorm_tail(ops, dtype):
     M, N, K = 333, 256, 512
