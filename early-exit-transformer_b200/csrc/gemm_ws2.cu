@@ -1,24 +1,17 @@
-// gemm_ws.cu -- weight-stationary bf16 tcgen05 GEMM for the K = 256 projections of a conformer layer
-// (FFN up-projection TA:104-105 and its dSiLU data gradient, the attention in-projection TA:194, pointwise conv 1 + GLU TA:44-51).
+// gemm_ws2.cu -- weight-stationary bf16 tcgen05 GEMM for the K = 256 projections, CTA-PAIR version (tcgen05 cta_group::2).
 //
-//   C[M,N] (bf16) = epi( A[M,256] * B(n,k) )       128 x 256 tile, one CTA per SM, every CTA keeps ONE weight tile
+//   C[M,N] (bf16) = epi( A[M,256] * B(n,k) )      256 x 256 tile per CTA pair (2 SMs of one TPC), 128 rows per CTA
 //
-// Why a second kernel next to gemm_tc3: measured on B200 (profiles/r02_gemm_triage.txt) the v3 kernel needs 28.7 us for the
-// 23936 x 2048 x 256 product with its epilogue switched OFF -- per 128 x 256 tile it streams 64 KB of A and 128 KB of B through
-// shared memory (1.9 k clk at the measured 103 B/clk/SM) for 2.0 k clk of tcgen05.mma -- and its run-time-dispatched epilogue
-// executes 755 instructions per warp and tile (27 % of them useful).  Here
-//   * the [256 n x 256 k] weight tile (128 KB) is loaded ONCE per CTA and stays in shared memory: CTA c owns n-tile c % n_tiles and
-//     walks the m-tiles r, r + cnt, ...; only the 64 KB A tile streams (4 x 16 KB ring = exactly one tile of look-ahead);
-//   * the epilogue is a template: no run-time mode tests, bias folded into the tanh argument (h = 0.5 x + 0.5 b: one FFMA2),
-//     packed fp32x2 math, one 2 KB staging box per warp;
-//   * SiLU + pre-activation: the bf16 pre-activation leaves straight from registers (one 256-bit store per thread and 16 columns:
-//     whole 32-byte sectors), the activation through the staged TMA store; dSiLU: the pre-activation arrives through 256-bit
-//     loads issued before the accumulator wait (both forms are HBM-bound: 208 MB per launch);
-//   * mbarrier waits use the suspend-time hint (no hot polling next to the epilogue warps).
-//
-//   warp 0      : TMA producer (weight tile once, then the A ring)
-//   warp 1      : tcgen05.mma issuer, two 256-column TMEM accumulators
-//   warps 2..17 : epilogue; quarter = warp % 4 (TMEM lanes), column group = (warp - 2) / 4 -> accumulator columns [cg*64, +64)
+// Why pairs (measured with the single-CTA kernel gemm_ws.cu, profiles/r02_gemm_ws_*.txt): a 128 x 256 x 16 tcgen05.mma reads 4 KB of A
+// and 8 KB of B from shared memory every 128 clk = 96 B/clk of the SM's 128 B/clk, next to the TMA writes of the A ring, the staging
+// stores and the bulk-store reads -- the tensor pipe was active 2.6 k clk per tile instead of 2.0 k and the tile period sat at 3.5 k.
+// With cta_group::2 every CTA supplies its own 128 rows of A and only HALF of the weight tile (128 of the 256 n-rows): 64 B/clk per
+// SM, the resident weights shrink to 64 KB per CTA and the A ring grows to 8 x 16 KB = two full tiles of look-ahead.
+//   * cluster (2,1,1); pair p owns weight tile p % n_tiles and walks the 256-row super-tiles r, r + cnt, ...
+//   * both CTAs load their A rows / B half with cp.async.bulk.tensor...cta_group::2, completing on the LEADER's mbarriers;
+//   * the leader's warp 1 issues tcgen05.mma.cta_group::2 (M = 256) and commits with a multicast arrive to both CTAs' barriers
+//     (smem slot free, accumulator full); the epilogue warps of both CTAs release the accumulator on the leader's barrier;
+//   * the epilogue is the one of gemm_ws.cu (template modes, bias folded into the tanh argument, staggered store fences).
 #include <stdlib.h>
 #include "tc_common.cuh"
 
@@ -26,14 +19,15 @@ namespace eec {
 namespace {
 using namespace tc;
 
-constexpr int BM = 128, BN = 256, BK = 64, NKB = 4;   // K == 256
+constexpr int BM = 128, BN = 256, BK = 64, NKB = 4;   // K == 256; BM = rows per CTA (256 per pair)
+constexpr int NSA = 8;                                // A ring: two tiles
 constexpr int A_STAGE = BM * BK * 2;                  // 16 KB
-constexpr int B_KBLK = BN * BK * 2;                   // 32 KB
+constexpr int B_KBLK = (BN / 2) * BK * 2;             // 16 KB: this CTA's half of the weight tile's k-block
 constexpr int NEW = 16;
 constexpr int NTW = 64 + NEW * 32;                    // 576 threads
 constexpr int OFF_B = 0;
-constexpr int OFF_A = OFF_B + NKB * B_KBLK;           // 131072
-constexpr int OFF_STG = OFF_A + NKB * A_STAGE;        // 196608
+constexpr int OFF_A = OFF_B + NKB * B_KBLK;           // 65536
+constexpr int OFF_STG = OFF_A + NSA * A_STAGE;        // 196608
 constexpr int OFF_BIAS = OFF_STG + NEW * 2048;        // 229376
 constexpr int OFF_BAR = OFF_BIAS + 256 * 4;           // 230400
 constexpr int WS_SMEM = OFF_BAR + 256;                // 230656 <= 232448
@@ -61,16 +55,6 @@ __device__ __forceinline__ bool mbar_try_wait_h(uint64_t* bar, uint32_t parity) 
       : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)
       : "memory");
   return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait_s(uint64_t* bar, uint32_t parity, bool spin) {
-  if (spin) mbar_wait(bar, parity);
-  else {
-    if (mbar_try_wait_h(bar, parity)) return;
-    const long long t0 = clock64();
-    while (!mbar_try_wait_h(bar, parity)) {
-      if (clock64() - t0 > 4000000000LL) { printf("eec: gemm_ws mbarrier wait timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x); __trap(); }
-    }
-  }
 }
 __device__ __forceinline__ void mbar_wait_h(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait_h(bar, parity)) return;
@@ -136,18 +120,52 @@ __device__ __forceinline__ void epi16(const uint32_t (&c)[16], const float* b, u
   }
 }
 
+// ---- cta_group::2 forms of the async primitives (PTX ISA tcgen05 / cp.async.bulk.tensor; cross-checked against
+// cute/arch/copy_sm100_tma.hpp, cutlass/arch/barrier.h and cute/arch/mma_sm100_umma.hpp of the vendored CUTLASS headers)
+constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;   // shared::cluster address of the same offset in the pair's even (leader) CTA
+__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int x, int y) {
+  asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & PEER_MASK), "r"(x), "r"(y)
+               : "memory");
+}
+__device__ __forceinline__ void umma2_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// completion of all MMAs issued so far by this thread -> one arrival on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma2_commit_both(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {   // arrive on the LEADER CTA's copy of `bar`
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & PEER_MASK) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t* smem_result, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
 template <int MODE, bool B_KMAJ>
-__global__ void __launch_bounds__(NTW, 1) gemm_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                                                         const __grid_constant__ CUtensorMap tmC, const PW p) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTW, 1)
+    gemm_ws2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC, const PW p) {
   pdl_trigger();
   extern __shared__ __align__(1024) uint8_t smem[];
-  if (threadIdx.x == 0 && (smem_u32(smem) & 1023u)) { printf("eec: gemm_ws smem base not 1024-aligned\n"); __trap(); }
+  if (threadIdx.x == 0 && (smem_u32(smem) & 1023u)) { printf("eec: gemm_ws2 smem base not 1024-aligned\n"); __trap(); }
   float* bias_s = reinterpret_cast<float*>(smem + OFF_BIAS);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + OFF_BAR);   // [4]  A k-block kb of the current tile has landed
-  uint64_t* empty_bar = full_bar + NKB;                               // [4]  its MMAs have completed
-  uint64_t* tfull_bar = empty_bar + NKB;                              // [2]
-  uint64_t* tempty_bar = tfull_bar + 2;                               // [2]
-  uint64_t* bfull_bar = tempty_bar + 2;                               // [4]  k-block kb of the weight tile has landed
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + OFF_BAR);   // [8]  (leader's copy is used) A stage s of BOTH CTAs has landed
+  uint64_t* empty_bar = full_bar + NSA;                               // [8]  (per CTA) its MMAs have completed
+  uint64_t* tfull_bar = empty_bar + NSA;                              // [2]  (per CTA) accumulator ready
+  uint64_t* tempty_bar = tfull_bar + 2;                               // [2]  (leader's copy) drained by the epilogue warps of both CTAs
+  uint64_t* bfull_bar = tempty_bar + 2;                               // [4]  (leader's copy) k-block kb of both weight halves has landed
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bfull_bar + NKB);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -159,21 +177,23 @@ __global__ void __launch_bounds__(NTW, 1) gemm_ws_kernel(const __grid_constant__
 #else
 #define WS_TL(cond, stmt) do { } while (0)
 #endif
-  const int nt = blockIdx.x % p.n_tiles;        // this CTA's weight tile
-  const int r0 = blockIdx.x / p.n_tiles;        // its rank among the CTAs that share it
-  const int cnt = ((int)gridDim.x - nt + p.n_tiles - 1) / p.n_tiles;
+  const uint32_t rank = cluster_ctarank();      // 0 = leader (issues the MMAs)
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int nt = pair % p.n_tiles;              // this pair's weight tile
+  const int r0 = pair / p.n_tiles;              // its rank among the pairs that share it
+  const int cnt = (npairs - nt + p.n_tiles - 1) / p.n_tiles;
   const int n0 = nt * BN;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmC);
-    for (int s = 0; s < NKB; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], NEW); }
+    for (int s = 0; s < NSA; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 2 * NEW); }
     for (int s = 0; s < NKB; ++s) mbar_init(&bfull_bar[s], 1);
     fence_barrier_init();
   }
-  if (warp == 1) { tmem_alloc(tmem_ptr_smem, 512); tmem_relinquish(); }
+  if (warp == 1) tmem_alloc2(tmem_ptr_smem, 512);
   pdl_wait();
   if (threadIdx.x < 256) {
     float b = p.bias ? p.bias[n0 + threadIdx.x] : 0.f;
@@ -181,73 +201,60 @@ __global__ void __launch_bounds__(NTW, 1) gemm_ws_kernel(const __grid_constant__
     bias_s[threadIdx.x] = b;
   }
   tc_fence_before();
-  __syncthreads();
+  cluster_sync_all();     // barriers of both CTAs initialised, TMEM allocated in both
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
-  const int mt_eff = (active_rows(p.act_items, p.M) + BM - 1) / BM;
-  const bool spin = p.knobs & 1;
-  volatile long long* tl_issue = reinterpret_cast<volatile long long*>(smem + OFF_BAR + 192);
-  (void)tl_issue;
+  const int st_eff = (active_rows(p.act_items, p.M) + 2 * BM - 1) / (2 * BM);   // 256-row super-tiles
   WS_TL(threadIdx.x == 0, p.tl[9] = gtime());
   long long w0_ = 0, w1_ = 0, w2_ = 0, w3_ = 0, w4_ = 0, t_ = 0, tb_ = 0;
   (void)w0_; (void)w1_; (void)w2_; (void)w3_; (void)w4_; (void)t_; (void)tb_;
 
   if (warp == 0) {
     if (lane == 0) {
-      // weight tile: one barrier per k-block, interleaved with the first A tile, so that the first MMAs start after 48 KB instead of 192 KB
+      int s = 0;
       uint32_t ph = 1;
       bool first = true;
-      for (int mt = r0; mt < mt_eff; mt += cnt, ph ^= 1) {
-        // the ring holds ONE tile of look-ahead (64 KB in flight per SM): against a 1.9 us HBM round trip that alone streams 34 GB/s
-        // per SM (measured: 1.7 k clk of operand wait per tile), so the tiles after the next are pulled into L2 ahead of time
-        if (first && !(p.knobs & 4)) {
-#pragma unroll
-          for (int kb = 0; kb < NKB; ++kb) {
-            if (mt + cnt < mt_eff) tma_prefetch_l2_2d(&tmA, kb * BK, (mt + cnt) * BM);
-            if (mt + 2 * cnt < mt_eff) tma_prefetch_l2_2d(&tmA, kb * BK, (mt + 2 * cnt) * BM);
-          }
-        }
-        if (mt + 3 * cnt < mt_eff && !(p.knobs & 4)) {
-#pragma unroll
-          for (int kb = 0; kb < NKB; ++kb) tma_prefetch_l2_2d(&tmA, kb * BK, (mt + 3 * cnt) * BM);
-        }
+      const int nb = n0 + (int)rank * (BN / 2);   // this CTA's half of the weight tile: n-rows [nb, nb + 128)
+      for (int st = r0; st < st_eff; st += cnt) {
+        const int m0 = st * 2 * BM + (int)rank * BM;
 #pragma unroll
         for (int kb = 0; kb < NKB; ++kb) {
           if (first) {
             uint8_t* sb = smem + OFF_B + kb * B_KBLK;
-            mbar_expect_tx(&bfull_bar[kb], B_KBLK);
+            if (rank == 0) mbar_expect_tx(&bfull_bar[kb], 2 * B_KBLK);
             if (B_KMAJ) {
-              tma_load_2d(sb, &tmB, &bfull_bar[kb], kb * BK, n0);
+              tma_load_2d_2sm(sb, &tmB, &bfull_bar[kb], kb * BK, nb);
             } else {
 #pragma unroll
-              for (int a = 0; a < BN / 64; ++a) tma_load_2d(sb + a * 8192, &tmB, &bfull_bar[kb], n0 + a * 64, kb * BK);
+              for (int a = 0; a < BN / 128; ++a) tma_load_2d_2sm(sb + a * 8192, &tmB, &bfull_bar[kb], nb + a * 64, kb * BK);
             }
           }
-          mbar_wait_s(&empty_bar[kb], ph, spin);
-          WS_TL(kb == 0, tl_issue[0] = clock64());
-          mbar_expect_tx(&full_bar[kb], A_STAGE);
-          tma_load_2d(smem + OFF_A + kb * A_STAGE, &tmA, &full_bar[kb], kb * BK, mt * BM);
+          mbar_wait_h(&empty_bar[s], ph);
+          if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * A_STAGE);
+          tma_load_2d_2sm(smem + OFF_A + s * A_STAGE, &tmA, &full_bar[s], kb * BK, m0);
+          if (++s == NSA) { s = 0; ph ^= 1; }
         }
         first = false;
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, false, !B_KMAJ);
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(2 * BM, BN, false, !B_KMAJ);
       constexpr uint64_t B_KSTEP = (B_KMAJ ? 32 : 2048) >> 4;
-      uint64_t adesc[NKB], bdesc[NKB];
+      uint64_t bdesc[NKB];
 #pragma unroll
       for (int kb = 0; kb < NKB; ++kb) {
-        adesc[kb] = make_smem_desc(smem_u32(smem + OFF_A + kb * A_STAGE), 0, 1024);
         const uint32_t sb = smem_u32(smem + OFF_B + kb * B_KBLK);
         bdesc[kb] = B_KMAJ ? make_smem_desc(sb, 0, 1024) : make_smem_desc(sb, 8192, 1024);
       }
+      const uint64_t adesc0 = make_smem_desc(smem_u32(smem + OFF_A), 0, 1024);
       WS_TL(true, p.tl[12] = gtime(); tb_ = clock64());
-      uint32_t ut = 0;
-      for (int mt = r0; mt < mt_eff; mt += cnt, ++ut) {
+      uint32_t ut = 0, ph = 0;
+      int s = 0;
+      for (int st = r0; st < st_eff; st += cnt, ++ut) {
         const uint32_t acc = ut & 1;
         WS_TL(true, t_ = clock64());
-        mbar_wait_s(&tempty_bar[acc], ((ut >> 1) & 1) ^ 1, spin);
+        mbar_wait_h(&tempty_bar[acc], ((ut >> 1) & 1) ^ 1);
         WS_TL(true, w0_ += clock64() - t_);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
@@ -255,19 +262,19 @@ __global__ void __launch_bounds__(NTW, 1) gemm_ws_kernel(const __grid_constant__
         for (int kb = 0; kb < NKB; ++kb) {
           WS_TL(true, t_ = clock64());
           if (ut == 0) mbar_wait_h(&bfull_bar[kb], 0);
-          const bool had_to_wait = !mbar_try_wait(&full_bar[kb], ut & 1);
-          mbar_wait_s(&full_bar[kb], ut & 1, spin);
+          mbar_wait_h(&full_bar[s], ph);
           WS_TL(true, w1_ += clock64() - t_);
-          WS_TL(kb == 0 && had_to_wait && ut > 0, w2_ += clock64() - tl_issue[0]; ++w3_);
-          (void)had_to_wait;
           tc_fence_after();
+          const uint64_t ad = adesc0 + (uint64_t)((s * A_STAGE) >> 4);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) umma_bf16(d_tmem, adesc[kb] + k * 2, bdesc[kb] + k * B_KSTEP, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-          umma_commit(&empty_bar[kb]);
+          for (int k = 0; k < BK / 16; ++k)
+            if (!(p.knobs & 8)) umma2_bf16(d_tmem, ad + k * 2, bdesc[kb] + k * B_KSTEP, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          umma2_commit_both(&empty_bar[s]);
+          if (++s == NSA) { s = 0; ph ^= 1; }
         }
-        umma_commit(&tfull_bar[acc]);
+        umma2_commit_both(&tfull_bar[acc]);
       }
-      WS_TL(true, p.tl[10] = gtime(); p.tl[0] = clock64() - tb_; p.tl[1] = w0_; p.tl[2] = w1_; p.tl[3] = ut; p.tl[14] = w2_; p.tl[15] = w3_);
+      WS_TL(true, p.tl[10] = gtime(); p.tl[0] = clock64() - tb_; p.tl[1] = w0_; p.tl[2] = w1_; p.tl[3] = ut);
     }
   } else {
     // ================================================================== epilogue warps
@@ -305,18 +312,19 @@ __global__ void __launch_bounds__(NTW, 1) gemm_ws_kernel(const __grid_constant__
     // sub-slab of the next tile), so that one pair's fences overlap the other pair's tanh evaluations.
     constexpr bool CAN_DEFER = (MODE == WS_SILU || MODE == WS_BIAS);
     const bool defer = CAN_DEFER && (cg & 1) && !(p.knobs & 2);
+    const bool spin = false; (void)spin;
     uint32_t pa0[8], pa1[8], pb0[8], pb1[8];   // packed outputs of sub-slabs 0..3
     int prev_row0 = -1;
     uint32_t ut = 0;
-    for (int mt = r0; mt < mt_eff; mt += cnt, ++ut) {
-      const int row0 = mt * BM + q * 32;
+    for (int st = r0; st < st_eff; st += cnt, ++ut) {
+      const int row0 = st * 2 * BM + (int)rank * BM + q * 32;
       const int m = row0 + lane;
       const bool valid = m < p.M;
       uint32_t pin[4][8];
       if (MODE == WS_DSILU) {
         const __nv_bfloat16* pp = p.pre + (long)m * p.ldp + ncol;
         // this lane's 128 bytes of the NEXT tile's pre-activation: into L2 now, so that the loads below are L2 hits a tile later
-        if (mt + cnt < mt_eff && m + cnt * BM < p.M) asm volatile("prefetch.global.L2 [%0];" ::"l"(pp + (long)cnt * BM * p.ldp));
+        if (st + cnt < st_eff && m + cnt * 2 * BM < p.M) asm volatile("prefetch.global.L2 [%0];" ::"l"(pp + (long)cnt * 2 * BM * p.ldp));
 #pragma unroll
         for (int ss = 0; ss < 4; ++ss) {
           if (valid) ldg256(pp + ss * 16, pin[ss]);
@@ -365,7 +373,7 @@ __global__ void __launch_bounds__(NTW, 1) gemm_ws_kernel(const __grid_constant__
       WS_TL(e == 0 && lane == 0, w2_ += clock64() - t_);
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);   // the accumulator slice is in registers: the MMA warp may reuse it
+      if (lane == 0) mbar_arrive_leader(&tempty_bar[acc]);   // the accumulator slice is in registers: the leader's MMA warp may reuse it
       epi16<MODE>(rb, bsl + 48, pb1, po1, pin[(MODE == WS_DSILU) ? 3 : 0], p.alpha);
       if (MODE == WS_SILU_PRE && valid) stg256(pout + 48, po1);
       if (!defer) store_box(pb0, pb1, ncol + 32, row0);
@@ -377,57 +385,40 @@ __global__ void __launch_bounds__(NTW, 1) gemm_ws_kernel(const __grid_constant__
     if (lane == 0) bulk_wait_all();
     tc_fence_before();
   }
-  __syncthreads();
+  cluster_sync_all();   // the leader's MMAs write the peer's TMEM and read its shared memory: neither CTA may leave early
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    tmem_dealloc2(tmem_base, 512);
   }
   WS_TL(threadIdx.x == 32, p.tl[11] = gtime());
 }
 
 template <int MODE, bool B_KMAJ>
-int launch_ws(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc_, const PW& p, int grid, cudaStream_t st) {
+int launch_ws2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc_, const PW& p, int grid, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    EEC_CUDA(cudaFuncSetAttribute(gemm_ws_kernel<MODE, B_KMAJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM));
+    EEC_CUDA(cudaFuncSetAttribute(gemm_ws2_kernel<MODE, B_KMAJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM));
     attr_set = true;
   }
-  launch_pdl(gemm_ws_kernel<MODE, B_KMAJ>, dim3(grid), dim3(NTW), WS_SMEM, st, ta, tb, tc_, p);
+  gemm_ws2_kernel<MODE, B_KMAJ><<<dim3(grid), dim3(NTW), WS_SMEM, st>>>(ta, tb, tc_, p);   // (static cluster dims 2 x 1 x 1)
   EEC_LAUNCH_CHECK();
   return 0;
 }
 
-int g_sms_ws = 0;
+int g_sms_ws2 = 0;
 
 }  // namespace
 
-// can this descriptor run on the weight-stationary kernel?  (checked by gemm_tc3 before its own path)
-bool gemm_ws_ok(const eec_gemm_desc* d) {
-  static int env = -1;
-  if (env < 0) { const char* e = getenv("EEC_GEMM_WS"); env = (e && e[0] == '0') ? 0 : 1; }
-  if (!env) return false;
-  if (d->K != 256 || !d->a_kmajor || d->N % 256 != 0 || d->out_dtype != EEC_BF16 || d->in_dtype != EEC_BF16) return false;
-  if (d->accumulate || d->residual || d->a_colsum || d->ln_out || (d->drop_state && d->drop_p > 0.f)) return false;
-  if (d->act == EEC_ACT_NONE) return d->b_kmajor && d->alpha == 1.0f && !d->preact;
-  if (d->act == EEC_ACT_SILU) return d->b_kmajor && d->alpha == 1.0f && (!d->preact || d->preact_dtype == EEC_BF16);
-  if (d->act == EEC_ACT_DSILU) return !d->b_kmajor && !d->bias && d->preact && d->preact_dtype == EEC_BF16 && d->ldp % 16 == 0;
-  return false;
-}
-
-int gemm_ws(const eec_gemm_desc* d, cudaStream_t st) {
-  {
-    static int pair = -1;   // EEC_GEMM_WS=2: the CTA-pair (cta_group::2) version, gemm_ws2.cu
-    if (pair < 0) { const char* e = getenv("EEC_GEMM_WS"); pair = (e && e[0] == '2') ? 1 : 0; }
-    if (pair) return gemm_ws2(d, st);
-  }
-  if (!g_sms_ws) {
+// CTA-pair version of gemm_ws (same eligibility: gemm_ws_ok); needs an even number of SMs
+int gemm_ws2(const eec_gemm_desc* d, cudaStream_t st) {
+  if (!g_sms_ws2) {
     int dev = 0;
     EEC_CUDA(cudaGetDevice(&dev));
-    EEC_CUDA(cudaDeviceGetAttribute(&g_sms_ws, cudaDevAttrMultiProcessorCount, dev));
+    EEC_CUDA(cudaDeviceGetAttribute(&g_sms_ws2, cudaDevAttrMultiProcessorCount, dev));
   }
   CUtensorMap ta, tb, tcm;
   if (int r = get_tmap_2d(&ta, d->A, d->K, d->M, (uint64_t)d->lda * 2, 64, 128)) return r;
-  if (d->b_kmajor) { if (int r = get_tmap_2d(&tb, d->B, d->K, d->N, (uint64_t)d->ldb * 2, 64, 256)) return r; }
+  if (d->b_kmajor) { if (int r = get_tmap_2d(&tb, d->B, d->K, d->N, (uint64_t)d->ldb * 2, 64, 128)) return r; }   // one CTA's half of a weight tile
   else { if (int r = get_tmap_2d(&tb, d->B, d->N, d->K, (uint64_t)d->ldb * 2, 64, 64)) return r; }
   if (int r = get_tmap_box32(&tcm, d->C, true, (uint64_t)d->N, (uint64_t)d->M, (uint64_t)d->ldc)) return r;
   PW p{};
@@ -450,7 +441,7 @@ int gemm_ws(const eec_gemm_desc* d, cudaStream_t st) {
       long long h[16];
       if (!b || cudaStreamSynchronize(s) != cudaSuccess || cudaMemcpy(h, b, sizeof(h), cudaMemcpyDeviceToHost) != cudaSuccess) return;
       const double t = h[3] ? (double)h[3] : 1.0;
-      fprintf(stderr, "gemm_ws %dx%dx256 CTA0: %lld tiles; per tile (clk): MMA thread %.0f = wait accumulator %.0f + wait A %.0f + issue; epilogue warp: wait tfull %.0f, busy %.0f (tmem ld waits %.0f, staging-free waits %.0f, fence + store issue %.0f)\n",
+      fprintf(stderr, "gemm_ws2 %dx%dx256 CTA0: %lld tiles; per tile (clk): MMA thread %.0f = wait accumulator %.0f + wait A %.0f + issue; epilogue warp: wait tfull %.0f, busy %.0f (tmem ld waits %.0f, staging-free waits %.0f, fence + store issue %.0f)\n",
               M, N, h[3], h[0] / t, h[1] / t, h[2] / t, h[4] / t, h[5] / t, h[6] / t, h[7] / t, h[13] / t);
       fprintf(stderr, "        A k-block 0: TMA issue -> seen by the MMA thread %.0f clk (%lld waits)\n", h[15] ? (double)h[14] / h[15] : 0.0, h[15]);
       fprintf(stderr, "        CTA0 globaltimer (ns): setup %lld, weight tile landed +%lld, main loop %lld, drain+teardown %lld, total %lld\n", h[9] - h[8], h[12] - h[9],
@@ -463,11 +454,11 @@ int gemm_ws(const eec_gemm_desc* d, cudaStream_t st) {
     p.tl = tl_buf;
     report.b = tl_buf;
   }
-  const int grid = min(p.m_tiles * p.n_tiles, g_sms_ws);
-  EEC_CHECK_ARG(grid >= p.n_tiles, "gemm_ws: fewer CTAs (%d) than weight tiles (%d)", grid, p.n_tiles);
-  if (d->act == EEC_ACT_NONE) return launch_ws<WS_BIAS, true>(ta, tb, tcm, p, grid, st);
-  if (d->act == EEC_ACT_SILU) return store_pre ? launch_ws<WS_SILU_PRE, true>(ta, tb, tcm, p, grid, st) : launch_ws<WS_SILU, true>(ta, tb, tcm, p, grid, st);
-  return launch_ws<WS_DSILU, false>(ta, tb, tcm, p, grid, st);
+  const int grid = 2 * min(cdiv(p.m_tiles, 2) * p.n_tiles, g_sms_ws2 / 2);   // CTA pairs
+  EEC_CHECK_ARG(grid / 2 >= p.n_tiles, "gemm_ws2: fewer CTA pairs (%d) than weight tiles (%d)", grid / 2, p.n_tiles);
+  if (d->act == EEC_ACT_NONE) return launch_ws2<WS_BIAS, true>(ta, tb, tcm, p, grid, st);
+  if (d->act == EEC_ACT_SILU) return store_pre ? launch_ws2<WS_SILU_PRE, true>(ta, tb, tcm, p, grid, st) : launch_ws2<WS_SILU, true>(ta, tb, tcm, p, grid, st);
+  return launch_ws2<WS_DSILU, false>(ta, tb, tcm, p, grid, st);
 }
 
 }  // namespace eec
