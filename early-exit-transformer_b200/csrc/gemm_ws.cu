@@ -416,8 +416,14 @@ bool gemm_ws_ok(const eec_gemm_desc* d) {
 
 int gemm_ws(const eec_gemm_desc* d, cudaStream_t st) {
   {
-    static int pair = -1;   // EEC_GEMM_WS=2: the CTA-pair (cta_group::2) version, gemm_ws2.cu
-    if (pair < 0) { const char* e = getenv("EEC_GEMM_WS"); pair = (e && e[0] == '2') ? 1 : 0; }
+    static int pair = -1;   // default: the CTA-pair (cta_group::2) version, gemm_ws2.cu; EEC_GEMM_WS=1 keeps this single-CTA kernel
+    if (pair < 0) {
+      const char* e = getenv("EEC_GEMM_WS");
+      int sms = 0, dev = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      pair = (e && e[0] == '1') ? 0 : (sms % 2 == 0 ? 1 : 0);
+    }
     if (pair) return gemm_ws2(d, st);
   }
   if (!g_sms_ws) {

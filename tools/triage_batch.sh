@@ -1,4 +1,10 @@
 cd /root/repo
-EEC_GEMM_WS=2 timeout 300 python -m pytest tests/test_gpu_kernels.py -q -x -k "gemm" 2>&1 | tail -4
-for w in 2; do for k in 0 2; do EEC_WS_KNOBS=$k EEC_GEMM_WS=$w timeout 120 python tools/gemm_triage.py all 2>&1 | sed "s/^/ws=$w knobs=$k /"; done; done
-for w in 2; do for c in silu qkv; do echo "== ws=$w $c"; EEC_GEMM_WS=$w EEC_LIB=early-exit-transformer_b200/eec/libeec_tl.so EEC_GEMM_TL=1 timeout 120 python tools/gemm_triage.py $c 2>&1 | grep -A2 "gemm_ws" | sed -n 17,19p | grep -v "k-block"; done; done
+timeout 1500 python -m pytest tests -q -x -m gpu 2>&1 | tail -5
+timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/r2v_bench.json 2> gpurun_out/r2v_bench.err; tail -3 gpurun_out/r2v_bench.err
+python - <<'PY'
+import json
+d = json.loads(open("gpurun_out/r2v_bench.json").read().strip().splitlines()[-1])
+print("step", d["ms_per_step"], "value", d["value"], "e2e", d["e2e"]["value"], "roofline", d["roofline"]["frac"], d["roofline"]["ms_per_launch"])
+print("rtfx", [r["ms"] for r in d.get("rtfx_per_exit", [])], "parity", d.get("parity_vs_reference", {}).get("ok"), d.get("parity_vs_reference", {}).get("logprob_rel_err_per_exit"))
+for k in ("train_with_dropout", "dp_18_layers", "aed_mode"): print(k, d.get(k, {}).get("ms_per_step"))
+PY
