@@ -939,6 +939,7 @@ int g_sms3 = 0;
 // GENERIC / GLU epilogues of eec_gemm (bf16 operands); the caller (gemm_tc2) has validated the descriptor
 int gemm_tc3(const eec_gemm_desc* d, cudaStream_t st) {
   if (gemm_ws_ok(d)) return gemm_ws(d, st);   // K = 256 projections with a bf16 output: weight-stationary kernel (gemm_ws.cu)
+  if (gemm_pair_ok(d, st)) return gemm_pair(d, st);   // fp32-output data / weight gradients: CTA-pair streaming kernel (gemm_pair.cu)
   const int epi = (d->act == EEC_ACT_GLU) ? EPI_GLU : EPI_GENERIC;
   EEC_CHECK_ARG(!d->bias || d->N <= MAX_BIAS, "gemm_tc3: N (%d) > %d with a bias vector is unsupported", d->N, MAX_BIAS);
   if (!g_sms3) {
