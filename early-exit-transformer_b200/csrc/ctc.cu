@@ -6,6 +6,7 @@
 // alpha rows are kept in a shared-memory ping-pong and spilled to a workspace; the beta sweep
 // fuses the occupancy reduction and writes d(loss)/d(logits) = scale*(softmax - occupancy)
 // directly, so log-softmax backward never runs as a separate kernel.
+#include <stdlib.h>
 #include "common.cuh"
 #ifndef EEC_CTC_PF
 #define EEC_CTC_PF 4
@@ -151,7 +152,26 @@ __global__ void ctc_grad_init_kernel(const float4* __restrict__ lp, const int64_
   }
 }
 
-template <int SPL>
+// RING (V == 256): the emission rows travel global -> shared memory as 1 KB bulk copies (cp.async.bulk + mbarrier) through a
+// 16-row ring per warp.  Measured before (B200, T' = 374): the alpha chain alone took 263 us = 1.35 k clk per time step although a step
+// is 146 instructions -- register prefetches of the scattered emissions (4 / 8 / 12 steps ahead: no difference) cannot hide the L2 /
+// HBM latency, because every wait on a load scoreboard also waits for the NEWER loads that share it.  mbarrier phases complete in
+// order, so the ring really keeps 15 rows in flight; it also reads 1 KB per step instead of ~97 scattered 32-byte sectors.
+constexpr int CTC_RING = 16;
+__device__ __forceinline__ void ctc_row_load(float* dst, const float* src, uint64_t* bar) {
+  const uint32_t b = (uint32_t)__cvta_generic_to_shared(bar), d = (uint32_t)__cvta_generic_to_shared(dst);
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(1024) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(d), "l"(src), "r"(1024), "r"(b)
+               : "memory");
+}
+__device__ __forceinline__ void ctc_row_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t b = (uint32_t)__cvta_generic_to_shared(bar);
+  uint32_t ok = 0;
+  while (!ok)
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(b), "r"(parity) : "memory");
+}
+
+template <int SPL, bool RING>
 __global__ void __launch_bounds__(64) ctc_warp_kernel(const float* __restrict__ lp_all, const int64_t* __restrict__ targets,
                                                       const int64_t* __restrict__ target_len, int EB, int B, int T, int V, int Lmax,
                                                       int blank, float gscale, float* __restrict__ nll_all,
@@ -166,9 +186,21 @@ __global__ void __launch_bounds__(64) ctc_warp_kernel(const float* __restrict__ 
   constexpr int PF = EEC_CTC_PF;         // prefetch distance (time steps)
   constexpr int SW = 32 * SPL;  // workspace row width
   __shared__ float s_ll;
+  __shared__ __align__(128) float ring[RING ? 2 : 1][RING ? CTC_RING : 1][RING ? 256 : 1];
+  __shared__ uint64_t rbar[2][CTC_RING];
   const int wg = blockIdx.x;
   const int role = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  if (RING) {
+    if (threadIdx.x == 0) {
+      for (int i = 0; i < 2 * CTC_RING; ++i) {
+        const uint32_t b = (uint32_t)__cvta_generic_to_shared(&rbar[0][0] + i);
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(b), "r"(1));
+      }
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+  }
   const int e = wg / B, b = wg % B;
   const float* lp = lp_all + (long)wg * T * V;
   float* grad = grad_all ? grad_all + (long)wg * T * V : nullptr;
@@ -191,57 +223,108 @@ __global__ void __launch_bounds__(64) ctc_warp_kernel(const float* __restrict__ 
   }
   const float denom = (float)B * (float)max(U, 1);
   float emb[PF], eml[PF][NL];
+  // emission rows of this warp's recursion, in ITS time order: row(n) = base + dir * n
+  const int rdir = (role == 0) ? 1 : -1, rbase = (role == 0) ? 0 : T - 1;
+  float(*rg)[RING ? 256 : 1] = ring[RING ? role : 0];
+  uint64_t* rb = rbar[role];
+  auto ring_fetch = [&](int n, float& lb, float(&ll)[NL]) {      // wait for row n of the sequence, read this lane's emissions (log2 domain)
+    const int sl = n & (CTC_RING - 1);
+    ctc_row_wait(&rb[sl], (n / CTC_RING) & 1);
+    lb = rg[sl][blank] * LOG2E_F;
+#pragma unroll
+    for (int j = 0; j < NL; ++j) ll[j] = rg[sl][lab[j]] * LOG2E_F;
+  };
+  auto ring_refill = [&](int n_done) {                          // every lane has read row n_done: its slot takes row n_done + CTC_RING
+    __syncwarp();
+    if (lane == 0 && n_done + CTC_RING < T)
+      ctc_row_load(rg[n_done & (CTC_RING - 1)], lp + (long)(rbase + rdir * (n_done + CTC_RING)) * V, &rb[n_done & (CTC_RING - 1)]);
+  };
+  if (RING && (role == 0 || grad)) {
+    if (lane == 0)
+      for (int n = 0; n < CTC_RING && n < T; ++n) ctc_row_load(rg[n], lp + (long)(rbase + rdir * n) * V, &rb[n]);
+    __syncwarp();
+  }
   if (role == 0) {
     // ---------------- alpha (forward in time)
     float a[SPL];
 #pragma unroll
-    for (int i = 0; i < SPL; ++i) {
-      const int s = s0 + i;
-      a[i] = CTC_NEG;
-      if (s == 0) a[i] = lp[blank] * LOG2E_F;
-      if (s == 1 && S > 1) a[i] = lp[lab[0]] * LOG2E_F;
-    }
+    for (int i = 0; i < SPL; ++i) a[i] = CTC_NEG;
+    auto alpha_step = [&](int t, float lb_, const float(&ll_)[NL]) {
+      float prev_last = __shfl_up_sync(0xffffffffu, a[SPL - 1], 1);
+      if (lane == 0) prev_last = CTC_NEG;
+      float na[SPL];
 #pragma unroll
-    for (int i = 0; i < SPL; ++i) aw[i] = a[i];
-#pragma unroll
-    for (int k = 0; k < PF; ++k) {
-      const int t = 1 + k;
-      if (t < T) {
-        emb[k] = lp[(long)t * V + blank] * LOG2E_F;
-#pragma unroll
-        for (int j = 0; j < NL; ++j) eml[k][j] = lp[(long)t * V + lab[j]] * LOG2E_F;
+      for (int i = 0; i < SPL; ++i) {
+        const float am1 = (i == 0) ? prev_last : a[i - 1];
+        if ((i & 1) == 0) {
+          na[i] = flse2(a[i], am1) + lb_;
+        } else {
+          const float am2 = (i == 1) ? prev_last : a[i - 2];
+          na[i] = flse3(a[i], am1, skip[i >> 1] ? am2 : CTC_NEG) + ll_[i >> 1];
+        }
+        na[i] = (s0 + i >= S) ? CTC_NEG : fmaxf(na[i], CTC_NEG);
       }
-    }
-    for (int t0 = 1; t0 < T; t0 += PF) {
+#pragma unroll
+      for (int i = 0; i < SPL; ++i) { a[i] = na[i]; aw[(long)t * SW + i] = na[i]; }
+    };
+    if (RING) {
+      float lb_, ll_[NL], nlb = CTC_NEG, nll[NL];
+      ring_fetch(0, lb_, ll_);
+#pragma unroll
+      for (int i = 0; i < SPL; ++i) {
+        const int s = s0 + i;
+        a[i] = CTC_NEG;
+        if (s == 0) a[i] = lb_;
+        if (s == 1 && S > 1) a[i] = ll_[0];
+      }
+#pragma unroll
+      for (int i = 0; i < SPL; ++i) aw[i] = a[i];
+#pragma unroll
+      for (int j = 0; j < NL; ++j) nll[j] = CTC_NEG;
+      if (T > 1) ring_fetch(1, nlb, nll);
+      for (int t = 1; t < T; ++t) {
+        lb_ = nlb;
+#pragma unroll
+        for (int j = 0; j < NL; ++j) ll_[j] = nll[j];
+        ring_refill(t - 1);
+        if (t + 1 < T) ring_fetch(t + 1, nlb, nll);   // one step ahead: the shared-memory reads overlap this step's recursion
+        alpha_step(t, lb_, ll_);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < SPL; ++i) {
+        const int s = s0 + i;
+        a[i] = CTC_NEG;
+        if (s == 0) a[i] = lp[blank] * LOG2E_F;
+        if (s == 1 && S > 1) a[i] = lp[lab[0]] * LOG2E_F;
+      }
+#pragma unroll
+      for (int i = 0; i < SPL; ++i) aw[i] = a[i];
 #pragma unroll
       for (int k = 0; k < PF; ++k) {
-        const int t = t0 + k;
+        const int t = 1 + k;
         if (t < T) {
-          const float lb_ = emb[k];
-          float ll_[NL];
+          emb[k] = lp[(long)t * V + blank] * LOG2E_F;
 #pragma unroll
-          for (int j = 0; j < NL; ++j) ll_[j] = eml[k][j];
-          if (t + PF < T) {
-            emb[k] = lp[(long)(t + PF) * V + blank] * LOG2E_F;
+          for (int j = 0; j < NL; ++j) eml[k][j] = lp[(long)t * V + lab[j]] * LOG2E_F;
+        }
+      }
+      for (int t0 = 1; t0 < T; t0 += PF) {
 #pragma unroll
-            for (int j = 0; j < NL; ++j) eml[k][j] = lp[(long)(t + PF) * V + lab[j]] * LOG2E_F;
-          }
-          float prev_last = __shfl_up_sync(0xffffffffu, a[SPL - 1], 1);
-          if (lane == 0) prev_last = CTC_NEG;
-          float na[SPL];
+        for (int k = 0; k < PF; ++k) {
+          const int t = t0 + k;
+          if (t < T) {
+            const float lb_ = emb[k];
+            float ll_[NL];
 #pragma unroll
-          for (int i = 0; i < SPL; ++i) {
-            const float am1 = (i == 0) ? prev_last : a[i - 1];
-            if ((i & 1) == 0) {
-              na[i] = flse2(a[i], am1) + lb_;
-            } else {
-              const float am2 = (i == 1) ? prev_last : a[i - 2];
-              na[i] = flse3(a[i], am1, skip[i >> 1] ? am2 : CTC_NEG) + ll_[i >> 1];
+            for (int j = 0; j < NL; ++j) ll_[j] = eml[k][j];
+            if (t + PF < T) {
+              emb[k] = lp[(long)(t + PF) * V + blank] * LOG2E_F;
+#pragma unroll
+              for (int j = 0; j < NL; ++j) eml[k][j] = lp[(long)(t + PF) * V + lab[j]] * LOG2E_F;
             }
-            na[i] = (s0 + i >= S) ? CTC_NEG : fmaxf(na[i], CTC_NEG);
+            alpha_step(t, lb_, ll_);
           }
-#pragma unroll
-          for (int i = 0; i < SPL; ++i) { a[i] = na[i]; aw[(long)t * SW + i] = na[i]; }
         }
       }
     }
@@ -268,57 +351,75 @@ __global__ void __launch_bounds__(64) ctc_warp_kernel(const float* __restrict__ 
     // ---------------- beta (backward in time); the workspace receives beta_t(s) - emission_t(s)
     float bt[SPL];
 #pragma unroll
-    for (int k = 0; k < PF; ++k) {
-      const int t = T - 1 - k;
-      if (t >= 0) {
-        emb[k] = lp[(long)t * V + blank] * LOG2E_F;
-#pragma unroll
-        for (int j = 0; j < NL; ++j) eml[k][j] = lp[(long)t * V + lab[j]] * LOG2E_F;
-      }
-    }
-#pragma unroll
     for (int i = 0; i < SPL; ++i) bt[i] = CTC_NEG;
-    for (int t0 = T - 1; t0 >= 0; t0 -= PF) {
+    auto beta_step = [&](int t, float lb_, const float(&ll_)[NL]) {
+      float nb[SPL];
+      if (t == T - 1) {
+#pragma unroll
+        for (int i = 0; i < SPL; ++i) {
+          const int s = s0 + i;
+          nb[i] = (s < S && s >= S - 2) ? (((i & 1) == 0) ? lb_ : ll_[i >> 1]) : CTC_NEG;
+        }
+      } else {
+        float n0 = __shfl_down_sync(0xffffffffu, bt[0], 1);
+        float n1 = __shfl_down_sync(0xffffffffu, bt[1], 1);
+        if (lane == 31) { n0 = CTC_NEG; n1 = CTC_NEG; }
+#pragma unroll
+        for (int i = 0; i < SPL; ++i) {
+          const float bp1 = (i == SPL - 1) ? n0 : bt[i + 1];
+          if ((i & 1) == 0) {
+            nb[i] = flse2(bt[i], bp1) + lb_;
+          } else {
+            const float bp2 = (i == SPL - 1) ? n1 : bt[(i + 2 < SPL) ? i + 2 : i];
+            nb[i] = flse3(bt[i], bp1, skipf[i >> 1] ? bp2 : CTC_NEG) + ll_[i >> 1];
+          }
+          nb[i] = (s0 + i >= S) ? CTC_NEG : fmaxf(nb[i], CTC_NEG);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < SPL; ++i) {
+        bt[i] = nb[i];
+        bw[(long)t * SW + i] = nb[i] - (((i & 1) == 0) ? lb_ : ll_[i >> 1]);
+      }
+    };
+    if (RING) {
+      float lb_, ll_[NL], nlb = CTC_NEG, nll[NL];
+#pragma unroll
+      for (int j = 0; j < NL; ++j) nll[j] = CTC_NEG;
+      ring_fetch(0, nlb, nll);
+      for (int n = 0; n < T; ++n) {
+        lb_ = nlb;
+#pragma unroll
+        for (int j = 0; j < NL; ++j) ll_[j] = nll[j];
+        if (n >= 1) ring_refill(n - 1);
+        if (n + 1 < T) ring_fetch(n + 1, nlb, nll);
+        beta_step(T - 1 - n, lb_, ll_);
+      }
+    } else {
 #pragma unroll
       for (int k = 0; k < PF; ++k) {
-        const int t = t0 - k;
+        const int t = T - 1 - k;
         if (t >= 0) {
-          const float lb_ = emb[k];
-          float ll_[NL];
+          emb[k] = lp[(long)t * V + blank] * LOG2E_F;
 #pragma unroll
-          for (int j = 0; j < NL; ++j) ll_[j] = eml[k][j];
-          if (t - PF >= 0) {
-            emb[k] = lp[(long)(t - PF) * V + blank] * LOG2E_F;
+          for (int j = 0; j < NL; ++j) eml[k][j] = lp[(long)t * V + lab[j]] * LOG2E_F;
+        }
+      }
+      for (int t0 = T - 1; t0 >= 0; t0 -= PF) {
 #pragma unroll
-            for (int j = 0; j < NL; ++j) eml[k][j] = lp[(long)(t - PF) * V + lab[j]] * LOG2E_F;
-          }
-          float nb[SPL];
-          if (t == T - 1) {
+        for (int k = 0; k < PF; ++k) {
+          const int t = t0 - k;
+          if (t >= 0) {
+            const float lb_ = emb[k];
+            float ll_[NL];
 #pragma unroll
-            for (int i = 0; i < SPL; ++i) {
-              const int s = s0 + i;
-              nb[i] = (s < S && s >= S - 2) ? (((i & 1) == 0) ? lb_ : ll_[i >> 1]) : CTC_NEG;
+            for (int j = 0; j < NL; ++j) ll_[j] = eml[k][j];
+            if (t - PF >= 0) {
+              emb[k] = lp[(long)(t - PF) * V + blank] * LOG2E_F;
+#pragma unroll
+              for (int j = 0; j < NL; ++j) eml[k][j] = lp[(long)(t - PF) * V + lab[j]] * LOG2E_F;
             }
-          } else {
-            float n0 = __shfl_down_sync(0xffffffffu, bt[0], 1);
-            float n1 = __shfl_down_sync(0xffffffffu, bt[1], 1);
-            if (lane == 31) { n0 = CTC_NEG; n1 = CTC_NEG; }
-#pragma unroll
-            for (int i = 0; i < SPL; ++i) {
-              const float bp1 = (i == SPL - 1) ? n0 : bt[i + 1];
-              if ((i & 1) == 0) {
-                nb[i] = flse2(bt[i], bp1) + lb_;
-              } else {
-                const float bp2 = (i == SPL - 1) ? n1 : bt[(i + 2 < SPL) ? i + 2 : i];
-                nb[i] = flse3(bt[i], bp1, skipf[i >> 1] ? bp2 : CTC_NEG) + ll_[i >> 1];
-              }
-              nb[i] = (s0 + i >= S) ? CTC_NEG : fmaxf(nb[i], CTC_NEG);
-            }
-          }
-#pragma unroll
-          for (int i = 0; i < SPL; ++i) {
-            bt[i] = nb[i];
-            bw[(long)t * SW + i] = nb[i] - (((i & 1) == 0) ? lb_ : ll_[i >> 1]);
+            beta_step(t, lb_, ll_);
           }
         }
       }
@@ -608,9 +709,16 @@ extern "C" int eec_ctc_fwd_bwd(const float* lp, const int64_t* targets, const in
     }
     const int EB = E * B;
     float* wsb = wsf + (long)EB * T * 32 * spl;
+    static int ring_env = -1;
+    if (ring_env < 0) { const char* e = getenv("EEC_CTC_RING"); ring_env = (e && e[0] == '0') ? 0 : 1; }
+    const bool ring = ring_env && V == 256 && (reinterpret_cast<uintptr_t>(lp) & 15) == 0;   // 1 KB emission rows as bulk copies
 #define EEC_CTC_WARP(SPLV)                                                                                              \
-  launch_pdl(ctc_warp_kernel<SPLV>, dim3(EB), dim3(64), 0, S(stream), lp, targets, target_len, EB, B, T, V, Lmax, blank, gscale, nll, \
-                                                      loss_out, grad, wsf, wsb)
+  do {                                                                                                                  \
+    if (ring) launch_pdl(ctc_warp_kernel<SPLV, true>, dim3(EB), dim3(64), 0, S(stream), lp, targets, target_len, EB, B, T, V, Lmax, blank, gscale, nll, \
+                         loss_out, grad, wsf, wsb);                                                                     \
+    else launch_pdl(ctc_warp_kernel<SPLV, false>, dim3(EB), dim3(64), 0, S(stream), lp, targets, target_len, EB, B, T, V, Lmax, blank, gscale, nll, \
+                    loss_out, grad, wsf, wsb);                                                                          \
+  } while (0)
     if (spl == 2) EEC_CTC_WARP(2);
     else if (spl == 4) EEC_CTC_WARP(4);
     else if (spl == 6) EEC_CTC_WARP(6);

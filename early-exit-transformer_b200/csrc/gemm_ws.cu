@@ -408,7 +408,7 @@ bool gemm_ws_ok(const eec_gemm_desc* d) {
   if (!env) return false;
   if (d->K != 256 || !d->a_kmajor || d->N % 256 != 0 || d->out_dtype != EEC_BF16 || d->in_dtype != EEC_BF16) return false;
   if (d->accumulate || d->residual || d->a_colsum || d->ln_out || (d->drop_state && d->drop_p > 0.f)) return false;
-  if (d->act == EEC_ACT_NONE) return d->b_kmajor && d->alpha == 1.0f && !d->preact;
+  if (d->act == EEC_ACT_NONE) return d->alpha == 1.0f && !d->preact;   // (MN-major B: the N = K = 256 data gradients with a bf16 output)
   if (d->act == EEC_ACT_SILU) return d->b_kmajor && d->alpha == 1.0f && (!d->preact || d->preact_dtype == EEC_BF16);
   if (d->act == EEC_ACT_DSILU) return !d->b_kmajor && !d->bias && d->preact && d->preact_dtype == EEC_BF16 && d->ldp % 16 == 0;
   return false;
@@ -471,7 +471,7 @@ int gemm_ws(const eec_gemm_desc* d, cudaStream_t st) {
   }
   const int grid = min(p.m_tiles * p.n_tiles, g_sms_ws);
   EEC_CHECK_ARG(grid >= p.n_tiles, "gemm_ws: fewer CTAs (%d) than weight tiles (%d)", grid, p.n_tiles);
-  if (d->act == EEC_ACT_NONE) return launch_ws<WS_BIAS, true>(ta, tb, tcm, p, grid, st);
+  if (d->act == EEC_ACT_NONE) return d->b_kmajor ? launch_ws<WS_BIAS, true>(ta, tb, tcm, p, grid, st) : launch_ws<WS_BIAS, false>(ta, tb, tcm, p, grid, st);
   if (d->act == EEC_ACT_SILU) return store_pre ? launch_ws<WS_SILU_PRE, true>(ta, tb, tcm, p, grid, st) : launch_ws<WS_SILU, true>(ta, tb, tcm, p, grid, st);
   return launch_ws<WS_DSILU, false>(ta, tb, tcm, p, grid, st);
 }

@@ -460,7 +460,7 @@ int gemm_ws2(const eec_gemm_desc* d, cudaStream_t st) {
   }
   const int grid = 2 * min(cdiv(p.m_tiles, 2) * p.n_tiles, g_sms_ws2 / 2);   // CTA pairs
   EEC_CHECK_ARG(grid / 2 >= p.n_tiles, "gemm_ws2: fewer CTA pairs (%d) than weight tiles (%d)", grid / 2, p.n_tiles);
-  if (d->act == EEC_ACT_NONE) return launch_ws2<WS_BIAS, true>(ta, tb, tcm, p, grid, st);
+  if (d->act == EEC_ACT_NONE) return d->b_kmajor ? launch_ws2<WS_BIAS, true>(ta, tb, tcm, p, grid, st) : launch_ws2<WS_BIAS, false>(ta, tb, tcm, p, grid, st);
   if (d->act == EEC_ACT_SILU) return store_pre ? launch_ws2<WS_SILU_PRE, true>(ta, tb, tcm, p, grid, st) : launch_ws2<WS_SILU, true>(ta, tb, tcm, p, grid, st);
   return launch_ws2<WS_DSILU, false>(ta, tb, tcm, p, grid, st);
 }

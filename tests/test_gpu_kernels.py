@@ -113,6 +113,9 @@ def test_gemm_weight_stationary(ops, M, N):
     assert rel(out, base * torch.sigmoid(base)) < 8e-3
     # dSiLU data gradient: dH = alpha * (dY Wt) o dSiLU(pre), Wt [K, N] (MN-major B)
     Wt = rnd(K, N, seed=34, scale=0.1, dtype=torch.bfloat16)
+    out.fill_(float("nan"))
+    ops.gemm(A, Wt, out, M, N, K, a_kmajor=True, b_kmajor=False, lda=K, ldb=N)          # plain data gradient with a bf16 output
+    assert rel(out, ref_gemm(A, Wt, True, False)) < 6e-3
     dh = torch.full((M, N), float("nan"), device="cuda", dtype=torch.bfloat16)
     ops.gemm(A, Wt, dh, M, N, K, a_kmajor=True, b_kmajor=False, lda=K, ldb=N, act=ops.ACT_DSILU, preact=pre, alpha=0.5)
     h = pre.double().cpu()

@@ -158,3 +158,5 @@ if "ctc" in which:
     tg, tl = tg.to(dev), tl.to(dev)
     nll = torch.empty(6, B, device=dev); loss = torch.zeros(6, device=dev); grad = torch.empty_like(lp)
     report("ctc fwd+bwd 6 exits x 64 utts", timeit(lambda: ops.ctc_fwd_bwd(lp, tg, tl, nll, loss, grad), n=5), None, lp.numel() * 8)
+    lp1 = lp[:1].contiguous(); nll1 = torch.empty(1, B, device=dev); loss1 = torch.zeros(1, device=dev); grad1 = torch.empty_like(lp1)
+    report("ctc fwd+bwd 1 exit x 64 utts (serial-chain share)", timeit(lambda: ops.ctc_fwd_bwd(lp1, tg, tl, nll1, loss1, grad1), n=5), None, lp1.numel() * 8)
