@@ -106,7 +106,7 @@ struct Unit {
   }
 };
 
-template <bool A_KMAJ, bool B_KMAJ>
+template <bool A_KMAJ, bool B_KMAJ, bool OUT_BF16>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTP, 1)
     gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC, const PP p) {
   pdl_trigger();
@@ -259,7 +259,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTP, 1)
       const uint32_t tcol = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + cg * 64;
       wait_h(&tfull_bar[acc], (ut >> 1) & 1);
       tc_fence_after();
-      uint32_t ra[16], rb[16];
+      uint32_t ra[16], rb[16], pk[16];
       tmem_ld16_async(tcol, ra);
 #pragma unroll
       for (int ss = 0; ss < 4; ++ss) {
@@ -272,6 +272,29 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTP, 1)
           tc_fence_before();
           __syncwarp();
           if (lane == 0) arrive_leader(&tempty_bar[acc]);
+        }
+        if (OUT_BF16) {
+          // bf16 output (data gradients feeding a LayerNorm backward): one [32 rows x 32 cols] box per two sub-slabs
+          if (ncol + (ss & ~1) * 16 >= p.N) continue;   // (warp-uniform) column tail
+#pragma unroll
+          for (int j = 0; j < 16; j += 2) {
+            const __nv_bfloat162 h2 = __floats2bfloat162_rn(__uint_as_float(cur[j]) * p.alpha, __uint_as_float(cur[j + 1]) * p.alpha);
+            pk[(ss & 1) * 8 + (j >> 1)] = *reinterpret_cast<const uint32_t*>(&h2);
+          }
+          if (ss & 1) {
+            if (lane == 0) bulk_wait_read<0>();
+            __syncwarp();
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+              *reinterpret_cast<uint4*>(srow + ((c ^ sw) << 4)) = make_uint4(pk[c * 4], pk[c * 4 + 1], pk[c * 4 + 2], pk[c * 4 + 3]);
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&tmC, buf, ncol + (ss >> 1) * 32, row0);
+              bulk_commit();
+            }
+          }
+          continue;
         }
         if (ncol + ss * 16 >= p.N) continue;   // (warp-uniform) column tail
         float x[16];
@@ -301,14 +324,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTP, 1)
   }
 }
 
-template <bool AK, bool BK_>
+template <bool AK, bool BK_, bool OB = false>
 int launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc_, const PP& p, int grid, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    EEC_CUDA(cudaFuncSetAttribute(gemm_pair_kernel<AK, BK_>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM));
+    EEC_CUDA(cudaFuncSetAttribute(gemm_pair_kernel<AK, BK_, OB>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM));
     attr_set = true;
   }
-  gemm_pair_kernel<AK, BK_><<<dim3(grid), dim3(NTP), PAIR_SMEM, st>>>(ta, tb, tc_, p);   // (static cluster dims 2 x 1 x 1)
+  gemm_pair_kernel<AK, BK_, OB><<<dim3(grid), dim3(NTP), PAIR_SMEM, st>>>(ta, tb, tc_, p);   // (static cluster dims 2 x 1 x 1)
   EEC_LAUNCH_CHECK();
   return 0;
 }
@@ -327,7 +350,9 @@ bool gemm_pair_ok(const eec_gemm_desc* d, cudaStream_t st) {
     if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&g_sms_pair, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return false;
   }
   if (g_sms_pair % 2) return false;
-  if (d->in_dtype != EEC_BF16 || d->out_dtype != EEC_F32 || d->bias || d->act != EEC_ACT_NONE || d->preact || d->residual || d->ln_out) return false;
+  const bool out_bf16 = d->out_dtype == EEC_BF16;
+  if (out_bf16 && (!d->a_kmajor || d->accumulate || d->ldc % 8 != 0)) return false;   // bf16 output: plain data gradients only
+  if (d->in_dtype != EEC_BF16 || (d->out_dtype != EEC_F32 && !out_bf16) || d->bias || d->act != EEC_ACT_NONE || d->preact || d->residual || d->ln_out) return false;
   if (d->b_kmajor) return false;                       // instantiated: (A K-major | MN-major) x B MN-major = data / weight gradients
   if (d->drop_state && d->drop_p > 0.f) return false;
   if (d->a_colsum && d->a_kmajor) return false;
@@ -341,7 +366,9 @@ int gemm_pair(const eec_gemm_desc* d, cudaStream_t st) {
   if (d->a_kmajor) { if (int r = get_tmap_2d(&ta, d->A, d->K, d->M, (uint64_t)d->lda * 2, 64, 128)) return r; }
   else { if (int r = get_tmap_2d(&ta, d->A, d->M, d->K, (uint64_t)d->lda * 2, 64, 64)) return r; }
   if (int r = get_tmap_2d(&tb, d->B, d->N, d->K, (uint64_t)d->ldb * 2, 64, 64)) return r;
-  if (int r = get_tmap_box(&tcm, d->C, false, (uint64_t)d->N, (uint64_t)d->M, (uint64_t)d->ldc, 16, 32, 2 /*SWIZZLE_64B*/)) return r;
+  const bool out_bf16 = d->out_dtype == EEC_BF16;
+  if (out_bf16) { if (int r = get_tmap_box32(&tcm, d->C, true, (uint64_t)d->N, (uint64_t)d->M, (uint64_t)d->ldc)) return r; }
+  else if (int r = get_tmap_box(&tcm, d->C, false, (uint64_t)d->N, (uint64_t)d->M, (uint64_t)d->ldc, 16, 32, 2 /*SWIZZLE_64B*/)) return r;
   PP p{};
   p.M = d->M; p.N = d->N; p.K = d->K;
   p.mt2_tiles = cdiv(d->M, 2 * BM);
@@ -358,6 +385,7 @@ int gemm_pair(const eec_gemm_desc* d, cudaStream_t st) {
   p.alpha = d->alpha; p.accumulate = d->accumulate;
   p.a_colsum = d->a_colsum; p.a_colsum_scale = d->a_colsum_scale;
   const int grid = 2 * min(p.mt2_tiles * p.n_tiles * p.splits, pairs);
+  if (out_bf16) return launch_pair<true, false, true>(ta, tb, tcm, p, grid, st);
   if (d->a_kmajor) return launch_pair<true, false>(ta, tb, tcm, p, grid, st);
   return launch_pair<false, false>(ta, tb, tcm, p, grid, st);
 }

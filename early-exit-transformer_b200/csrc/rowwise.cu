@@ -42,8 +42,8 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
 }
 
 // ------------------------------------------------------------------ LayerNorm backward
-template <typename TC, bool DROP>
-__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+template <typename TC, bool DROP, typename TDY = float>
+__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const TDY* __restrict__ dy, const float* __restrict__ x,
                                                             const float* __restrict__ mean, const float* __restrict__ rstd,
                                                             const float* __restrict__ gamma, float* __restrict__ dx,
                                                             int dx_accumulate, float* __restrict__ dgamma,
@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
   for (int i = 0; i < 8; ++i) { dg[i] = 0.f; db[i] = 0.f; cs[i] = 0.f; }
   for (int r = blockIdx.x * 8 + wib; r < rows; r += gridDim.x * 8) {
     float d[8], v[8];
-    ld8<float>(dy + (long)r * 256 + c0, d);
+    ld8<TDY>(dy + (long)r * 256 + c0, d);
     ld8<float>(x + (long)r * 256 + c0, v);
     const float mu = mean[r], rs = rstd[r];
     float s1 = 0.f, s2 = 0.f, xh[8], dg_[8];
@@ -492,12 +492,26 @@ extern "C" int eec_layernorm_fwd(const float* x, const float* gamma, const float
   return 0;
 }
 
-extern "C" int eec_layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd,
-                                 const float* gamma, float* dx, int dx_accumulate, float* dgamma, float* dbeta,
-                                 void* dx_copy, int dx_copy_dtype, float* dx_colsum, float colsum_scale,
-                                 const uint64_t* drop_state, float drop_p, uint32_t drop_site, int rows, int d,
-                                 eec_stream_t stream) {
+extern "C" int eec_layernorm_bwd_dy(const void* dy_, int dy_dtype, const float* x, const float* mean, const float* rstd,
+                                    const float* gamma, float* dx, int dx_accumulate, float* dgamma, float* dbeta,
+                                    void* dx_copy, int dx_copy_dtype, float* dx_colsum, float colsum_scale,
+                                    const uint64_t* drop_state, float drop_p, uint32_t drop_site, int rows, int d,
+                                    eec_stream_t stream) {
   EEC_CHECK_ARG(d == 256, "layernorm_bwd: d must be 256 (got %d)", d);
+  if (dy_dtype == EEC_BF16) {
+    // upstream gradient in bf16 (the data-gradient GEMM that produced it rounds its fp32 accumulator once): 12 MB less to write and to read
+    EEC_CHECK_ARG(!(dx_copy && dx_copy_dtype == EEC_F32), "layernorm_bwd: a bf16 upstream gradient implies the bf16 path (dx_copy bf16)");
+    if (rows == 0) return 0;
+    const __nv_bfloat16* dy = reinterpret_cast<const __nv_bfloat16*>(dy_);
+    const int blocks = min(cdiv(rows, 8), 148 * 4);
+    const DropArgs drop = make_drop(drop_state, drop_p, drop_site);
+    EEC_CHECK_ARG(!drop.state || dx_copy || dx_colsum, "layernorm_bwd: dropout only affects dx_copy / dx_colsum, and neither was requested");
+    if (drop.state) launch_pdl(layernorm_bwd_kernel<__nv_bfloat16, true, __nv_bfloat16>, dim3(blocks), dim3(256), 0, S(stream), dy, x, mean, rstd, gamma, dx, dx_accumulate, dgamma, dbeta, (__nv_bfloat16*)dx_copy, dx_colsum, colsum_scale, rows, drop);
+    else launch_pdl(layernorm_bwd_kernel<__nv_bfloat16, false, __nv_bfloat16>, dim3(blocks), dim3(256), 0, S(stream), dy, x, mean, rstd, gamma, dx, dx_accumulate, dgamma, dbeta, (__nv_bfloat16*)dx_copy, dx_colsum, colsum_scale, rows, drop);
+    EEC_LAUNCH_CHECK();
+    return 0;
+  }
+  const float* dy = reinterpret_cast<const float*>(dy_);
   if (rows == 0) return 0;
   int blocks = min(cdiv(rows, 8), 148 * 4);
   const DropArgs drop = make_drop(drop_state, drop_p, drop_site);
@@ -508,6 +522,15 @@ extern "C" int eec_layernorm_bwd(const float* dy, const float* x, const float* m
 #undef EEC_LNB
   EEC_LAUNCH_CHECK();
   return 0;
+}
+
+extern "C" int eec_layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd,
+                                 const float* gamma, float* dx, int dx_accumulate, float* dgamma, float* dbeta,
+                                 void* dx_copy, int dx_copy_dtype, float* dx_colsum, float colsum_scale,
+                                 const uint64_t* drop_state, float drop_p, uint32_t drop_site, int rows, int d,
+                                 eec_stream_t stream) {
+  return eec_layernorm_bwd_dy(dy, EEC_F32, x, mean, rstd, gamma, dx, dx_accumulate, dgamma, dbeta, dx_copy, dx_copy_dtype, dx_colsum,
+                              colsum_scale, drop_state, drop_p, drop_site, rows, d, stream);
 }
 
 extern "C" int eec_dropout(const void* x, int in_dtype, void* y, int out_dtype, int64_t n, const uint64_t* state, float p,

@@ -119,6 +119,7 @@ def dgrad(dY, W, out, M, N_out, K_in, **kw):
     ops.gemm(dY, W, out, M, K_in, N_out, a_kmajor=True, b_kmajor=False, lda=N_out, ldb=K_in, **kw)
 
 
+_BF16_DU = os.environ.get("EEC_BF16_DU", "1") != "0"   # 0: keep the LayerNorm-backward inputs in fp32 (A/B runs)
 _FUSE_COLSUM = not (os.environ.get("EEC_GEMM_V1") == "1" or os.environ.get("EEC_GEMM_V2") == "1" or os.environ.get("EEC_FORCE_SIMT") == "1")
 
 
@@ -383,7 +384,7 @@ def layer_backward(P, W: Operands, G: Dict[str, Tensor], pre: str, t: dict, dY: 
         dh = _empty((N, F), TD, dev)
         dgrad(dXh, W2, dh, N, D, F, act=ACT_DSILU, preact=hpre, alpha=0.5, drop=dsites.get(s_act, _at(drop, s_act)))
         wgrad(dh, u, G[q + "1.weight"], N, F, D, dbias=G[q + "1.bias"], sq=sq)
-        du = _empty((N, D), f32, dev)
+        du = _empty((N, D), TD if _BF16_DU else f32, dev)   # bf16 path: the gradient entering the LayerNorm backward is stored in bf16
         dgrad(dh, W1, du, N, F, D)
         return ln_bwd(du, x_in, m, r, q + "0.", True, want_h, next_bias, s_out=next_site)
 
@@ -407,7 +408,7 @@ def layer_backward(P, W: Operands, G: Dict[str, Tensor], pre: str, t: dict, dY: 
     dz = _empty((N, 2 * D), TD, dev)
     ops.glu_bwd(t["z"], dg, dz)
     wgrad(dz, t["u3"], G[c + "sequential.0.weight"].view(2 * D, D), N, 2 * D, D, dbias=G[c + "sequential.0.bias"], sq=sq)
-    du3 = _empty((N, D), f32, dev)
+    du3 = _empty((N, D), TD if _BF16_DU else f32, dev)
     dgrad(dz, Wp1, du3, N, 2 * D, D)
     dXh = ln_bwd(du3, t["x2"], t["m3"], t["r3"], c + "layer_norm.", True, True, pre + "self_attn.out_proj.bias", s_out=S_ATTN_OUT)
 
@@ -422,7 +423,7 @@ def layer_backward(P, W: Operands, G: Dict[str, Tensor], pre: str, t: dict, dY: 
     dq32 = _empty((N, D), f32, dev) if bf16 else None
     ops.attn_bwd(t["qkv"], t["ctx"], dctx, t["lse"], t["key_len"], dqkv, dvec, B, T, H, dq32, drop=dsites.get(S_ATTN_P, _at(drop, S_ATTN_P)))
     wgrad(dqkv, t["u2"], G[pre + "self_attn.in_proj_weight"], N, 3 * D, D, dbias=G[pre + "self_attn.in_proj_bias"], sq=sq)
-    du2 = _empty((N, D), f32, dev)
+    du2 = _empty((N, D), TD if _BF16_DU else f32, dev)
     dgrad(dqkv, Wqkv, du2, N, 3 * D, D)
     dXh = ln_bwd(du2, t["x1"], t["m2"], t["r2"], pre + "self_attn_layer_norm.", True, True, pre + "ffn1.sequential.4.bias", 0.5,
                  s_out=S_FFN1_OUT)

@@ -62,6 +62,7 @@ _SIGS = {
     "eec_gemm": [C.POINTER(GemmDesc), vp],
     "eec_layernorm_fwd": [vp, vp, vp, vp, i32, vp, vp, i32, i32, vp],
     "eec_layernorm_bwd": [vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, i32, vp, f32, vp, f32, u32, i32, i32, vp],
+    "eec_layernorm_bwd_dy": [vp, i32, vp, vp, vp, vp, vp, i32, vp, vp, vp, i32, vp, f32, vp, f32, u32, i32, i32, vp],
     "eec_attn_fwd": [vp, i32, vp, vp, vp, i32, i32, i32, i32, vp, f32, u32, vp, vp],
     "eec_attn_bwd": [vp, vp, vp, i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp, f32, u32, vp, vp],
     "eec_attn_general_fwd": [C.POINTER(AttnDesc), vp, i32, vp, vp],

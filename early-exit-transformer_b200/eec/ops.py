@@ -125,7 +125,7 @@ def layernorm_fwd(x, gamma, beta, out, mean=None, rstd=None):
 def layernorm_bwd(dy, x, mean, rstd, gamma, dx, accumulate, dgamma, dbeta, dx_copy=None, dx_colsum=None, colsum_scale=1.0,
                   drop: Optional[Drop] = None):
     rows = x.numel() // 256
-    call("eec_layernorm_bwd", ptr(dy), ptr(x), ptr(mean), ptr(rstd), ptr(gamma), ptr(dx), int(accumulate), ptr(dgamma),
+    call("eec_layernorm_bwd_dy", ptr(dy), dt(dy), ptr(x), ptr(mean), ptr(rstd), ptr(gamma), ptr(dx), int(accumulate), ptr(dgamma),
          ptr(dbeta), ptr(dx_copy), dt(dx_copy) if dx_copy is not None else BF16, ptr(dx_colsum), colsum_scale, *_d(drop), rows, 256,
          stream())
 

@@ -124,6 +124,13 @@ int eec_layernorm_bwd(const float* dy, const float* x, const float* mean, const 
                       void* dx_copy, int dx_copy_dtype, float* dx_colsum, float colsum_scale,
                       const uint64_t* drop_state, float drop_p, uint32_t drop_site, int rows, int d,
                       eec_stream_t stream);
+/* the same with the upstream gradient dy in dy_dtype (EEC_F32 | EEC_BF16): on the bf16 path the data-gradient GEMM that produces dy
+ * (torch autograd of the nn.Linear / 1x1 Conv1d behind a LayerNorm, TA:104,194,44) writes it in bf16 */
+int eec_layernorm_bwd_dy(const void* dy, int dy_dtype, const float* x, const float* mean, const float* rstd,
+                         const float* gamma, float* dx, int dx_accumulate, float* dgamma, float* dbeta,
+                         void* dx_copy, int dx_copy_dtype, float* dx_colsum, float colsum_scale,
+                         const uint64_t* drop_state, float drop_p, uint32_t drop_site, int rows, int d,
+                         eec_stream_t stream);
 
 /* ---- multi-head self-attention core (nn.MultiheadAttention SDPA branch, TA:194-200) -
  * qkv [B*T, 3*H*dh] rows = [q | k | v], head h = columns [h*dh, (h+1)*dh) of each third.
