@@ -880,7 +880,7 @@ def roofline_dominant(dev, pk):
     # traffic: dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of this kernel, taken from the ncu --set full capture that
     # tools/ncu_traffic.py summarised into profiles/ncu_traffic.json (null when that file does not name this kernel: nothing is typed in)
     traffic, traffic_src = ncu_traffic("ffn_up_silu")
-    return {"kernel": "gemm_tc3_kernel<K-major,K-major,EPI_GENERIC> FFN up-proj 23936x2048x256 +bias+SiLU", "bound": "tensor",
+    return {"kernel": "gemm_ws2_kernel<SILU> (CTA pairs, weight-stationary) FFN up-proj 23936x2048x256 +bias+SiLU", "bound": "tensor",
             "achieved": round(ach, 2), "peak": pk["tf_burst"], "unit": "TFLOP/s", "frac": round(ach / pk["tf_burst"], 4),
             "traffic": traffic, "traffic_source": traffic_src, "ms_per_launch": round(ms, 4), "peak_source": pk["src"] + " burst (kernel timed alone)",
             "algorithmic_flops_per_launch": fl, "algorithmic_bytes_per_launch": 2 * (M * K + N * K + M * N)}
@@ -889,7 +889,7 @@ def roofline_dominant(dev, pk):
 def roofline_hbm_leg(dev, pk):
     """The north star's second target (>= 70 % of HBM peak on the norm kernels): LayerNorm backward at the BASELINE row count, timed alone
     with CUDA events and an L2 flush between launches.  Algorithmic bytes per launch: dy + x + dx in + dx out (fp32) + the bf16 operand
-    copy = N x 256 x 18 B = 110 MB; 60 launches per training step (22 us each there, partly out of L2)."""
+    copy = N x 256 x 18 B = 110 MB; 60 launches per training step (48 of them with a bf16 upstream gradient: 98 MB)."""
     from eec import ops
     N = B * t_out(T_IN)
     x = torch.randn(N, 256, device=dev)

@@ -1,6 +1,7 @@
 // rowwise.cu -- bandwidth-bound row kernels: LayerNorm fwd/bwd, log-softmax (+argmax/entropy),
 // casts, column sums, small glue.  One warp per 256-wide row, 8 contiguous channels per lane
 // (128-bit loads), statistics in fp32 with a two-pass variance held in registers.
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace eec {
@@ -61,42 +62,56 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const TDY* __restric
   ld8<float>(gamma + c0, g);
 #pragma unroll
   for (int i = 0; i < 8; ++i) { dg[i] = 0.f; db[i] = 0.f; cs[i] = 0.f; }
-  for (int r = blockIdx.x * 8 + wib; r < rows; r += gridDim.x * 8) {
-    float d[8], v[8];
-    ld8<TDY>(dy + (long)r * 256 + c0, d);
-    ld8<float>(x + (long)r * 256 + c0, v);
-    const float mu = mean[r], rs = rstd[r];
-    float s1 = 0.f, s2 = 0.f, xh[8], dg_[8];
+  // Two rows per warp and iteration, every load of both rows issued before the first use: the kernel is a pure stream (18 B per element)
+  // and one row per warp left too few bytes in flight (3.5 TB/s cold).
+  constexpr int RPI = 2;
+  const int rstride = gridDim.x * 8;
+  for (int r0 = blockIdx.x * 8 + wib; r0 < rows; r0 += RPI * rstride) {
+    float d[RPI][8], v[RPI][8], old[RPI][8], mu[RPI], rs[RPI];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      xh[i] = (v[i] - mu) * rs;
-      dg_[i] = d[i] * g[i];
-      s1 += dg_[i];
-      s2 += dg_[i] * xh[i];
-      dg[i] += d[i] * xh[i];
-      db[i] += d[i];
+    for (int k = 0; k < RPI; ++k) {
+      const int r = r0 + k * rstride;
+      if (r < rows) {
+        ld8<TDY>(dy + (long)r * 256 + c0, d[k]);
+        ld8<float>(x + (long)r * 256 + c0, v[k]);
+        if (dx_accumulate) ld8<float>(dx + (long)r * 256 + c0, old[k]);
+        mu[k] = mean[r]; rs[k] = rstd[r];
+      }
     }
-    s1 = warp_sum(s1) * (1.0f / 256.0f);
-    s2 = warp_sum(s2) * (1.0f / 256.0f);
-    float o[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) o[i] = rs * (dg_[i] - s1 - xh[i] * s2);
-    if (dx_accumulate) {
-      float old[8];
-      ld8<float>(dx + (long)r * 256 + c0, old);
+    for (int k = 0; k < RPI; ++k) {
+      const int r = r0 + k * rstride;
+      if (r >= rows) break;
+      float s1 = 0.f, s2 = 0.f, xh[8], dg_[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) o[i] += old[i];
+      for (int i = 0; i < 8; ++i) {
+        xh[i] = (v[k][i] - mu[k]) * rs[k];
+        dg_[i] = d[k][i] * g[i];
+        s1 += dg_[i];
+        s2 += dg_[i] * xh[i];
+        dg[i] += d[k][i] * xh[i];
+        db[i] += d[k][i];
+      }
+      s1 = warp_sum(s1) * (1.0f / 256.0f);
+      s2 = warp_sum(s2) * (1.0f / 256.0f);
+      float o[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = rs[k] * (dg_[i] - s1 - xh[i] * s2);
+      if (dx_accumulate) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] += old[k][i];
+      }
+      st8<float>(dx + (long)r * 256 + c0, o);
+      if (DROP) {   // the copy / column sums feed the backward of a projection whose output was dropped out (dx itself is the residual gradient)
+        float f[8];
+        drop_factors8(dkey, drop, (uint64_t)r * 32 + lane, f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] *= f[i];
+      }
+      if (dx_bf16) st8<TC>(dx_bf16 + (long)r * 256 + c0, o);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) cs[i] += o[i];
     }
-    st8<float>(dx + (long)r * 256 + c0, o);
-    if (DROP) {   // the copy / column sums feed the backward of a projection whose output was dropped out (dx itself is the residual gradient)
-      float f[8];
-      drop_factors8(dkey, drop, (uint64_t)r * 32 + lane, f);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) o[i] *= f[i];
-    }
-    if (dx_bf16) st8<TC>(dx_bf16 + (long)r * 256 + c0, o);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) cs[i] += o[i];
   }
   if (dx_colsum) {
 #pragma unroll
@@ -503,7 +518,9 @@ extern "C" int eec_layernorm_bwd_dy(const void* dy_, int dy_dtype, const float* 
     EEC_CHECK_ARG(!(dx_copy && dx_copy_dtype == EEC_F32), "layernorm_bwd: a bf16 upstream gradient implies the bf16 path (dx_copy bf16)");
     if (rows == 0) return 0;
     const __nv_bfloat16* dy = reinterpret_cast<const __nv_bfloat16*>(dy_);
-    const int blocks = min(cdiv(rows, 8), 148 * 4);
+    static int lnb_blocks = 0;
+    if (!lnb_blocks) { const char* e = getenv("EEC_LNB_BLOCKS"); lnb_blocks = e ? atoi(e) : 148 * 2; }
+    const int blocks = min(cdiv(rows, 8), lnb_blocks);   // 128 registers: two resident blocks per SM
     const DropArgs drop = make_drop(drop_state, drop_p, drop_site);
     EEC_CHECK_ARG(!drop.state || dx_copy || dx_colsum, "layernorm_bwd: dropout only affects dx_copy / dx_colsum, and neither was requested");
     if (drop.state) launch_pdl(layernorm_bwd_kernel<__nv_bfloat16, true, __nv_bfloat16>, dim3(blocks), dim3(256), 0, S(stream), dy, x, mean, rstd, gamma, dx, dx_accumulate, dgamma, dbeta, (__nv_bfloat16*)dx_copy, dx_colsum, colsum_scale, rows, drop);

@@ -133,6 +133,8 @@ if "lnbwd" in which:
     dx = torch.zeros(N, 256, device=dev); dcopy = torch.empty(N, 256, device=dev, dtype=torch.bfloat16)
     dg_, db_, cs_ = torch.zeros(256, device=dev), torch.zeros(256, device=dev), torch.zeros(256, device=dev)
     report("layernorm bwd (+bf16 copy, dgamma/dbeta, colsum)", timeit(lambda: ops.layernorm_bwd(dy, x, mean, rstd, g, dx, True, dg_, db_, dcopy, cs_, 1.0)), None, N * 256 * 18 + N * 8)
+    dyh = dy.to(torch.bfloat16)
+    report("layernorm bwd, bf16 upstream gradient (the in-step form)", timeit(lambda: ops.layernorm_bwd(dyh, x, mean, rstd, g, dx, True, dg_, db_, dcopy, cs_, 1.0)), None, N * 256 * 16 + N * 8)
 
 if "beam" in which:
     lp6 = torch.log_softmax(torch.randn(6, B, T, 256, device=dev), -1)

@@ -28,7 +28,7 @@ for r in rows[2:]:
     lines.append(f"{t:9.1f} us  dram rd {rd/1e6:8.2f} MB wr {wr/1e6:8.2f} MB ({(rd+wr)/t/1e3:7.1f} GB/s)  tensor {val(r,'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active') or 0:5.1f}%  "
                  f"warps {val(r,'sm__warps_active.avg.pct_of_peak_sustained_active') or 0:5.1f}%  regs {int(val(r,'launch__registers_per_thread') or 0):3d}  grid {int(val(r,'launch__grid_size') or 0):6d}  {name[:150]}")
     key = None
-    if "gemm_tc3_kernel<1, 1, 0, 3" in name.replace("(bool)", "").replace("(int)", "") and "ffn_up_silu" not in traffic: key = "ffn_up_silu"
+    if "gemm_ws2_kernel<1, 1>" in name.replace("(bool)", "").replace("(int)", "") and "ffn_up_silu" not in traffic: key = "ffn_up_silu"
     if "layernorm_bwd_kernel" in name and "layernorm_bwd" not in traffic: key = "layernorm_bwd"
     if key: traffic[key] = {"kernel": name[:120], "dram_bytes_read": rd, "dram_bytes_write": wr, "us_under_ncu": round(t, 2), "source": os.path.relpath(out)}
 open(out, "w").write("# ncu --set full --clock-control none, one launch per kernel (tools/kbench.py, KBENCH_PROFILE=1, L2 flushed before the launch); cold-cache, serialised times\n" + "\n".join(lines) + "\n")
