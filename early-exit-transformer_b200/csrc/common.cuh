@@ -208,6 +208,8 @@ int gemm_ws(const eec_gemm_desc* d, cudaStream_t st);
 int gemm_ws2(const eec_gemm_desc* d, cudaStream_t st);   // CTA-pair (cta_group::2) version, gemm_ws2.cu
 bool gemm_pair_ok(const eec_gemm_desc* d, cudaStream_t st);   // fp32-output streaming GEMMs (weight / long-K data gradients), CTA pairs: gemm_pair.cu
 int gemm_pair(const eec_gemm_desc* d, cudaStream_t st);
+bool gemm_lnp_ok(const eec_gemm_desc* d, cudaStream_t st);    // LayerNorm-tail GEMM, CTA pairs: gemm_lnp.cu
+int gemm_lnp(const eec_gemm_desc* d, cudaStream_t st);
 // x[j] = bit j of `word` ? x[j] * scale : 0   (j < n <= 32; the epilogue-side half of the dropout)
 template <int N>
 __device__ __forceinline__ void drop_apply_bits(float (&x)[N], uint32_t word, float scale) {

@@ -1048,6 +1048,7 @@ int gemm_tc3(const eec_gemm_desc* d, cudaStream_t st) {
 int gemm_ln3(const eec_gemm_desc* d, cudaStream_t st) {
   EEC_CHECK_ARG(d->res_row_mod == 0, "gemm_ln3: row-periodic residual unsupported");
   EEC_CHECK_ARG(!d->residual || d->ldr == 256, "gemm_ln3: residual must have ld 256");
+  if (gemm_lnp_ok(d, st)) return gemm_lnp(d, st);   // CTA-pair version (gemm_lnp.cu); this kernel stays for early-exit compaction / odd SM counts
   if (!g_sms3) {
     int dev = 0;
     EEC_CUDA(cudaGetDevice(&dev));
