@@ -407,7 +407,15 @@ bool gemm_ws_ok(const eec_gemm_desc* d) {
   if (env < 0) { const char* e = getenv("EEC_GEMM_WS"); env = (e && e[0] == '0') ? 0 : 1; }
   if (!env) return false;
   if (d->K != 256 || !d->a_kmajor || d->N % 256 != 0 || d->out_dtype != EEC_BF16 || d->in_dtype != EEC_BF16) return false;
-  if (d->accumulate || d->residual || d->a_colsum || d->ln_out || (d->drop_state && d->drop_p > 0.f)) return false;
+  if (d->accumulate || d->residual || d->a_colsum || d->ln_out) return false;
+  if (d->drop_state && d->drop_p > 0.f) {   // dropout: the CTA-pair kernel has it for the two training forms (SiLU + stored pre-activation, dSiLU)
+    const char* e = getenv("EEC_GEMM_WS");
+    if (e && e[0] == '1') return false;
+    int sms = 0, dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms % 2) return false;
+    if (!d->drop_bits) return false;
+    if (!((d->act == EEC_ACT_SILU && d->preact) || d->act == EEC_ACT_DSILU)) return false;
+  }
   if (d->act == EEC_ACT_NONE) return d->alpha == 1.0f && !d->preact;   // (MN-major B: the N = K = 256 data gradients with a bf16 output)
   if (d->act == EEC_ACT_SILU) return d->b_kmajor && d->alpha == 1.0f && (!d->preact || d->preact_dtype == EEC_BF16);
   if (d->act == EEC_ACT_DSILU) return !d->b_kmajor && !d->bias && d->preact && d->preact_dtype == EEC_BF16 && d->ldp % 16 == 0;

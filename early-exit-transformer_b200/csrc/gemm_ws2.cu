@@ -44,6 +44,7 @@ struct PW {
   float alpha;
   __nv_bfloat16* pre; int ldp;     // SILU_PRE / GLU_PRE: written; DSILU: read
   ActiveItems act_items;
+  DropArgs drop;   // DROP instantiations: dropout right after the activation (element index m*N + n), keep-mask words of eec_dropout_bits (W = 16)
   int knobs;       // EEC_WS_KNOBS (perf triage): 1 = producer / MMA threads poll their barriers, 2 = no staggered stores, 4 = no L2 prefetch of A
   long long* tl;   // EEC_GEMM_TL=1 on a -DEEC_GEMM_TIMELINE build (perf triage): clock64 / globaltimer accumulators of CTA 0
 };
@@ -91,9 +92,9 @@ __device__ __forceinline__ float2 unpack_bf16(uint32_t u) {   // exact: bf16 -> 
 
 // 16 accumulator columns of this lane's row -> 8 packed bf16 pairs.  `b` = this sub-slab's 16 bias values in shared memory
 // (warp-uniform address: broadcast; already scaled by 0.5 for the SiLU modes).
-template <int MODE>
+template <int MODE, bool DROP = false>
 __device__ __forceinline__ void epi16(const uint32_t (&c)[16], const float* b, uint32_t (&o)[8], uint32_t (&pre_o)[8],
-                                      const uint32_t (&pre_i)[8], float alpha) {
+                                      const uint32_t (&pre_i)[8], float alpha, uint32_t dword = 0xffffu, float dscale = 1.f) {
   const float4* bp = reinterpret_cast<const float4*>(b);
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
@@ -118,6 +119,10 @@ __device__ __forceinline__ void epi16(const uint32_t (&c)[16], const float* b, u
         const float2 q = __ffma2_rn(__fmul2_rn(t, t), make_float2(-cc, -cc), make_float2(cc, cc));
         const float2 d = __ffma2_rn(hh, q, __ffma2_rn(t, make_float2(cc, cc), make_float2(cc, cc)));
         r = __fmul2_rn(x, d);
+      }
+      if (DROP) {   // keep-mask bit j of this thread's 16-column word; kept values are scaled by 1 / (1 - p)
+        r.x = (dword & (1u << j)) ? r.x * dscale : 0.f;
+        r.y = (dword & (2u << j)) ? r.y * dscale : 0.f;
       }
       o[j >> 1] = pack_bf16(r);
     }
@@ -158,7 +163,7 @@ __device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
   asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
 
-template <int MODE, bool B_KMAJ>
+template <int MODE, bool B_KMAJ, bool DROP = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTW, 1)
     gemm_ws2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC, const PW p) {
   pdl_trigger();
@@ -339,6 +344,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTW, 1)
         }
       }
       __nv_bfloat16* pout = (MODE == WS_SILU_PRE) ? p.pre + (long)m * p.ldp + ncol : nullptr;
+      uint32_t dwv[4] = {0xffffu, 0xffffu, 0xffffu, 0xffffu};   // in flight while the main loop of this tile runs
+      if (DROP && valid) {
+        const uint16_t* db = reinterpret_cast<const uint16_t*>(p.drop.bits);
+#pragma unroll
+        for (int ss = 0; ss < 4; ++ss) dwv[ss] = db[(long)((ncol >> 4) + ss) * p.M + m];
+      }
       const uint32_t acc = ut & 1;
       const uint32_t tcol = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + cg * 64;
       WS_TL(e == 0 && lane == 0, t_ = clock64());
@@ -352,7 +363,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTW, 1)
       tmem_ld_wait16(ra);
       WS_TL(e == 0 && lane == 0, w2_ += clock64() - t_);
       tmem_ld16_async(tcol + 16, rb);
-      epi16<MODE>(ra, bsl, pa0, po0, pin[0], p.alpha);
+      epi16<MODE, DROP>(ra, bsl, pa0, po0, pin[0], p.alpha, dwv[0], p.drop.scale);
       if (MODE == WS_SILU_PRE && valid) stg256(pout, po0);
       if (defer && prev_row0 >= 0) store_box(pb0, pb1, ncol + 32, prev_row0);
       // ---- sub-slab 1
@@ -360,7 +371,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTW, 1)
       tmem_ld_wait16(rb);
       WS_TL(e == 0 && lane == 0, w2_ += clock64() - t_);
       tmem_ld16_async(tcol + 32, ra);
-      epi16<MODE>(rb, bsl + 16, pa1, po1, pin[(MODE == WS_DSILU) ? 1 : 0], p.alpha);
+      epi16<MODE, DROP>(rb, bsl + 16, pa1, po1, pin[(MODE == WS_DSILU) ? 1 : 0], p.alpha, dwv[1], p.drop.scale);
       if (MODE == WS_SILU_PRE && valid) stg256(pout + 16, po1);
       if (!defer) store_box(pa0, pa1, ncol, row0);
       // ---- sub-slab 2
@@ -368,7 +379,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTW, 1)
       tmem_ld_wait16(ra);
       WS_TL(e == 0 && lane == 0, w2_ += clock64() - t_);
       tmem_ld16_async(tcol + 48, rb);
-      epi16<MODE>(ra, bsl + 32, pb0, po0, pin[(MODE == WS_DSILU) ? 2 : 0], p.alpha);
+      epi16<MODE, DROP>(ra, bsl + 32, pb0, po0, pin[(MODE == WS_DSILU) ? 2 : 0], p.alpha, dwv[2], p.drop.scale);
       if (MODE == WS_SILU_PRE && valid) stg256(pout + 32, po0);
       if (defer) store_box(pa0, pa1, ncol, row0);
       // ---- sub-slab 3
@@ -378,7 +389,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTW, 1)
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_leader(&tempty_bar[acc]);   // the accumulator slice is in registers: the leader's MMA warp may reuse it
-      epi16<MODE>(rb, bsl + 48, pb1, po1, pin[(MODE == WS_DSILU) ? 3 : 0], p.alpha);
+      epi16<MODE, DROP>(rb, bsl + 48, pb1, po1, pin[(MODE == WS_DSILU) ? 3 : 0], p.alpha, dwv[3], p.drop.scale);
       if (MODE == WS_SILU_PRE && valid) stg256(pout + 48, po1);
       if (!defer) store_box(pb0, pb1, ncol + 32, row0);
       prev_row0 = row0;
@@ -397,14 +408,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTW, 1)
   WS_TL(threadIdx.x == 32, p.tl[11] = gtime());
 }
 
-template <int MODE, bool B_KMAJ>
+template <int MODE, bool B_KMAJ, bool DROP = false>
 int launch_ws2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc_, const PW& p, int grid, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    EEC_CUDA(cudaFuncSetAttribute(gemm_ws2_kernel<MODE, B_KMAJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM));
+    EEC_CUDA(cudaFuncSetAttribute(gemm_ws2_kernel<MODE, B_KMAJ, DROP>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM));
     attr_set = true;
   }
-  gemm_ws2_kernel<MODE, B_KMAJ><<<dim3(grid), dim3(NTW), WS_SMEM, st>>>(ta, tb, tc_, p);   // (static cluster dims 2 x 1 x 1)
+  gemm_ws2_kernel<MODE, B_KMAJ, DROP><<<dim3(grid), dim3(NTW), WS_SMEM, st>>>(ta, tb, tc_, p);   // (static cluster dims 2 x 1 x 1)
   EEC_LAUNCH_CHECK();
   return 0;
 }
@@ -460,6 +471,15 @@ int gemm_ws2(const eec_gemm_desc* d, cudaStream_t st) {
   }
   const int grid = 2 * min(cdiv(p.m_tiles, 2) * p.n_tiles, g_sms_ws2 / 2);   // CTA pairs
   EEC_CHECK_ARG(grid / 2 >= p.n_tiles, "gemm_ws2: fewer CTA pairs (%d) than weight tiles (%d)", grid / 2, p.n_tiles);
+  p.drop = make_drop(d->drop_state, d->drop_p, d->drop_site);
+  p.drop.bits = d->drop_bits;
+  if (p.drop.state) {
+    EEC_CHECK_ARG(d->drop_bits != nullptr, "gemm (tensor-core path): dropout needs the keep-mask words of eec_dropout_bits(R = M, C = N, Cs = N, W = 16) in drop_bits");
+    if (d->act == EEC_ACT_SILU && store_pre) return launch_ws2<WS_SILU_PRE, true, true>(ta, tb, tcm, p, grid, st);
+    if (d->act == EEC_ACT_DSILU) return launch_ws2<WS_DSILU, false, true>(ta, tb, tcm, p, grid, st);
+    set_error("gemm_ws2: dropout is fused into the SiLU + pre-activation and dSiLU forms only");
+    return 1;
+  }
   if (d->act == EEC_ACT_NONE) return d->b_kmajor ? launch_ws2<WS_BIAS, true>(ta, tb, tcm, p, grid, st) : launch_ws2<WS_BIAS, false>(ta, tb, tcm, p, grid, st);
   if (d->act == EEC_ACT_SILU) return store_pre ? launch_ws2<WS_SILU_PRE, true>(ta, tb, tcm, p, grid, st) : launch_ws2<WS_SILU, true>(ta, tb, tcm, p, grid, st);
   return launch_ws2<WS_DSILU, false>(ta, tb, tcm, p, grid, st);
