@@ -38,6 +38,7 @@ struct PLN {
   int has_res, ln_bf16;
   const float* ln_gamma; const float* ln_beta; float* ln_mean; float* ln_rstd;
   DropArgs drop;   // DROP instantiation only: x = residual + alpha * dropout(A W^T + bias), element index m*256 + n
+  ActiveItems act_items;   // super-tiles past the active-item limit are skipped by all three roles (early-exit inference)
 };
 
 __device__ __forceinline__ bool try_wait_h(uint64_t* bar, uint32_t parity) {
@@ -107,7 +108,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(LN_NT, 1)
   const uint32_t rank = cluster_ctarank();
   const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
   const int total_kb = (p.K + BK - 1) / BK;
-  const int st_tiles = (p.M + 2 * BM - 1) / (2 * BM);   // 256-row super-tiles
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
@@ -132,6 +132,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(LN_NT, 1)
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  const int st_tiles = (active_rows(p.act_items, p.M) + 2 * BM - 1) / (2 * BM);   // 256-row super-tiles (== all of them unless an active-item limit is set)
 
   if (warp == 0) {
     if (lane == 0) {
@@ -336,7 +337,7 @@ bool gemm_lnp_ok(const eec_gemm_desc* d, cudaStream_t st) {
     if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&g_sms_lnp, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return false;
   }
   if (g_sms_lnp % 2) return false;
-  if (active_items(st).n_dev) return false;   // early-exit inference with batch compaction keeps the single-CTA kernel (it skips tiles by the device-side count)
+  (void)st;
   return true;
 }
 
@@ -353,6 +354,7 @@ int gemm_lnp(const eec_gemm_desc* d, cudaStream_t st) {
   p.M = d->M; p.K = d->K; p.m_tiles = cdiv(d->M, BM);
   p.bias = d->bias; p.alpha = d->alpha; p.has_res = d->residual != nullptr; p.ln_bf16 = d->ln_dtype == EEC_BF16;
   p.ln_gamma = d->ln_gamma; p.ln_beta = d->ln_beta; p.ln_mean = d->ln_mean; p.ln_rstd = d->ln_rstd;
+  p.act_items = active_items(st);
   p.drop = make_drop(d->drop_state, d->drop_p, d->drop_site);
   p.drop.bits = d->drop_bits;
   if (p.drop.state)

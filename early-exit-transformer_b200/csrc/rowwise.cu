@@ -405,12 +405,13 @@ __global__ void scale_dev_kernel(const float* __restrict__ x, const float* __res
 
 // y[r, :] = s[r] * x[r, :] for `rows` contiguous slabs of `slab` floats (slab % 4 == 0): all exits' CTC gradient slabs scaled by
 // their upstream scalars in ONE launch, 128-bit accesses, grid-stride
-__global__ void __launch_bounds__(256) scale_rows_dev_kernel(const float4* __restrict__ x, const float* __restrict__ s, float4* __restrict__ y,
+__global__ void __launch_bounds__(256) scale_rows_dev_kernel(const float4* x, const float* __restrict__ s, float4* y,   // (x == y allowed)
                                                              long slab4, long total4) {
   pdl_trigger();
   pdl_wait();
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long)gridDim.x * blockDim.x) {
     const float a = s[i / slab4];
+    if (a == 1.0f && x == y) continue;   // in place with a unit scale (the usual upstream of loss.sum()): nothing to move -- 294 MB of traffic per step saved
     float4 v = x[i];
     v.x *= a; v.y *= a; v.z *= a; v.w *= a;
     y[i] = v;

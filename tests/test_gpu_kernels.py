@@ -116,6 +116,13 @@ def test_gemm_weight_stationary(ops, M, N):
     out.fill_(float("nan"))
     ops.gemm(A, Wt, out, M, N, K, a_kmajor=True, b_kmajor=False, lda=K, ldb=N)          # plain data gradient with a bf16 output
     assert rel(out, ref_gemm(A, Wt, True, False)) < 6e-3
+    # long-K data gradient with a bf16 output (the CTA-pair streaming kernel, csrc/gemm_pair.cu): dU[M, 256] = dH[M, N] Wl[N, 256]
+    if N >= 512:
+        Wl = rnd(N, 256, seed=35, scale=0.05, dtype=torch.bfloat16)
+        H_ = rnd(M, N, seed=36, dtype=torch.bfloat16)
+        du = torch.full((M, 256), float("nan"), device="cuda", dtype=torch.bfloat16)
+        ops.gemm(H_, Wl, du, M, 256, N, a_kmajor=True, b_kmajor=False, lda=N, ldb=256)
+        assert rel(du, ref_gemm(H_, Wl, True, False)) < 6e-3
     dh = torch.full((M, N), float("nan"), device="cuda", dtype=torch.bfloat16)
     ops.gemm(A, Wt, dh, M, N, K, a_kmajor=True, b_kmajor=False, lda=K, ldb=N, act=ops.ACT_DSILU, preact=pre, alpha=0.5)
     h = pre.double().cpu()
@@ -178,6 +185,19 @@ def test_layernorm_fwd_bwd(ops):
     outb = torch.empty(rows, 256, device="cuda", dtype=torch.bfloat16)
     ops.layernorm_fwd(x, g, b, outb)
     assert rel(outb, ref.detach()) < 1e-2
+    # upstream gradient in bf16 (eec_layernorm_bwd_dy: what the data-gradient GEMMs of the bf16 path hand over) + bf16 copy + column sums
+    dyh = dy.to(torch.bfloat16)
+    xd2 = x.double().cpu().requires_grad_(True)
+    gd2, bd2 = g.double().cpu().requires_grad_(True), b.double().cpu().requires_grad_(True)
+    torch.nn.functional.layer_norm(xd2, (256,), gd2, bd2, 1e-5).backward(dyh.double().cpu())
+    dx2 = torch.ones_like(x)
+    dg2, db2, cs2 = torch.zeros(256, device="cuda"), torch.zeros(256, device="cuda"), torch.zeros(256, device="cuda")
+    copy = torch.empty(rows, 256, device="cuda", dtype=torch.bfloat16)
+    ops.layernorm_bwd(dyh, x, mean, rstd, g, dx2, True, dg2, db2, copy, cs2, 0.5)
+    assert rel(dx2 - 1, xd2.grad) < 1e-5
+    assert rel(dg2, gd2.grad) < 1e-5 and rel(db2, bd2.grad) < 1e-5
+    assert rel(copy, dx2) < 5e-3
+    assert rel(cs2, 0.5 * dx2.double().cpu().sum(0)) < 1e-4     # (summed from the fp32 values, before the copy is rounded)
 
 
 def attn_ref(qkv, key_len, B, T, H):
