@@ -33,6 +33,7 @@ constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;
 
 struct PLN {
   int M, K, m_tiles;
+  int rb;          // rows per CTA and tile: 128, 96 or 64 (the MMA is always 256 x 256; rows past rb of a CTA's accumulator are never read)
   const float* bias;
   float alpha;
   int has_res, ln_bf16;
@@ -132,7 +133,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(LN_NT, 1)
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
-  const int st_tiles = (active_rows(p.act_items, p.M) + 2 * BM - 1) / (2 * BM);   // 256-row super-tiles (== all of them unless an active-item limit is set)
+  const int st_tiles = (active_rows(p.act_items, p.M) + 2 * p.rb - 1) / (2 * p.rb);   // (2 rb)-row super-tiles (== all of them unless an active-item limit is set)
 
   if (warp == 0) {
     if (lane == 0) {
@@ -140,11 +141,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(LN_NT, 1)
       uint32_t ph = 1;
       const int nb = (int)rank * (BN / 2);
       for (int st = pair; st < st_tiles; st += npairs) {
-        const int m0 = st * 2 * BM + (int)rank * BM;
+        const int m0 = st * 2 * p.rb + (int)rank * p.rb;
         for (int kb = 0; kb < total_kb; ++kb) {
           wait_h(&empty_bar[s], ph);
           uint8_t* sa = smem + s * STAGE;
-          if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * STAGE);
+          if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * (p.rb * BK * 2 + B_BYTES));   // the A box holds rb rows
           tma_load_2d_2sm(sa, &tmA, &full_bar[s], kb * BK, m0);
           tma_load_2d_2sm(sa + A_BYTES, &tmB, &full_bar[s], kb * BK, nb);
           if (++s == LN_NSTAGE) { s = 0; ph ^= 1; }
@@ -187,10 +188,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(LN_NT, 1)
     float x[128];   // this thread's 128 x-values (its row, its column half): TMEM is read once, the values never leave registers
     uint32_t ut = 0;
     for (int st = pair; st < st_tiles; st += npairs, ++ut) {
-      const int m0 = st * 2 * BM + (int)rank * BM;
+      const int m0 = st * 2 * p.rb + (int)rank * p.rb;
       const int row0 = m0 + q * 32;
       const int m = m0 + r;
       const bool valid = m < p.M;
+      if (q * 32 >= p.rb) {   // (warp-uniform) rb < 128: this lane quarter holds no rows of the tile; only the accumulator hand-shake remains
+        mbar_wait(&tfull_bar[ut & 1], (ut >> 1) & 1);
+        tc_fence_after();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) arrive_leader(&tempty_bar[ut & 1]);
+        continue;
+      }
       uint32_t dw[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};   // dropout keep-mask words of this thread's 4 x 32 columns
       if (DROP && valid) {
         const uint32_t* db = reinterpret_cast<const uint32_t*>(p.drop.bits);
@@ -344,14 +353,30 @@ bool gemm_lnp_ok(const eec_gemm_desc* d, cudaStream_t st) {
 // LayerNorm-tail epilogue of eec_gemm (N == 256, K-major bf16 operands, fp32 C with ldc 256); validated by gemm_tc2 / gemm_ln3
 int gemm_lnp(const eec_gemm_desc* d, cudaStream_t st) {
   CUtensorMap ta, tb, tcm, trm, tlm;
-  if (int r = get_tmap_2d(&ta, d->A, d->K, d->M, (uint64_t)d->lda * 2, 64, 128)) return r;
+  // Rows per CTA and tile.  M = 23 936 is 93.5 tiles of 256 rows for 74 pairs: the second wave would stream on 27 % of the SMs (measured:
+  // 16 of the FFN-down GEMM's 52 us).  With 96 (64) rows per CTA the same 2 (3) waves carry 192 rows per pair instead of 256; the MMA
+  // still runs 256 x 256 (these GEMMs are bandwidth-bound), the A box and the epilogue simply stop at rb rows.
+  const int pairs = g_sms_lnp / 2;
+  static int rb_env = -1;
+  if (rb_env < 0) { const char* e = getenv("EEC_LNP_RB"); rb_env = e ? atoi(e) : 0; }
+  int rb = 128;
+  if (rb_env == 128 || rb_env == 96 || rb_env == 64) rb = rb_env;
+  else {
+    long best = -1;
+    for (int c : {128, 96, 64}) {
+      const long waves = cdiv(cdiv(d->M, 2 * c), pairs);
+      const long cost = waves * (c + 8);   // + a per-tile constant for the row-wise epilogue
+      if (best < 0 || cost < best) { best = cost; rb = c; }
+    }
+  }
+  if (int r = get_tmap_2d(&ta, d->A, d->K, d->M, (uint64_t)d->lda * 2, 64, (uint32_t)rb)) return r;
   if (int r = get_tmap_2d(&tb, d->B, d->K, d->N, (uint64_t)d->ldb * 2, 64, 128)) return r;   // one CTA's half of the weight k-block
   if (int r = get_tmap_box32(&tcm, d->C, false, 256, (uint64_t)d->M, (uint64_t)d->ldc)) return r;
   trm = tcm;
   if (d->residual) { if (int r = get_tmap_box32(&trm, d->residual, false, 256, (uint64_t)d->M, 256)) return r; }
   if (int r = get_tmap_box32(&tlm, d->ln_out, d->ln_dtype == EEC_BF16, 256, (uint64_t)d->M, (uint64_t)d->ld_ln)) return r;
   PLN p{};
-  p.M = d->M; p.K = d->K; p.m_tiles = cdiv(d->M, BM);
+  p.M = d->M; p.K = d->K; p.m_tiles = cdiv(d->M, BM); p.rb = rb;
   p.bias = d->bias; p.alpha = d->alpha; p.has_res = d->residual != nullptr; p.ln_bf16 = d->ln_dtype == EEC_BF16;
   p.ln_gamma = d->ln_gamma; p.ln_beta = d->ln_beta; p.ln_mean = d->ln_mean; p.ln_rstd = d->ln_rstd;
   p.act_items = active_items(st);
@@ -365,7 +390,7 @@ int gemm_lnp(const eec_gemm_desc* d, cudaStream_t st) {
     EEC_CUDA(cudaFuncSetAttribute(gemm_lnp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, LNP_SMEM_BYTES));
     attr_set = true;
   }
-  const int grid = 2 * min(cdiv(d->M, 2 * BM), g_sms_lnp / 2);
+  const int grid = 2 * min(cdiv(d->M, 2 * rb), pairs);
   if (p.drop.state) gemm_lnp_kernel<true><<<dim3(grid), dim3(LN_NT), LNP_SMEM_BYTES, st>>>(ta, tb, tcm, trm, tlm, p);
   else gemm_lnp_kernel<false><<<dim3(grid), dim3(LN_NT), LNP_SMEM_BYTES, st>>>(ta, tb, tcm, trm, tlm, p);
   EEC_LAUNCH_CHECK();
