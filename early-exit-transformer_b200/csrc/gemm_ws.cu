@@ -418,6 +418,13 @@ bool gemm_ws_ok(const eec_gemm_desc* d) {
   }
   if (d->act == EEC_ACT_NONE) return d->alpha == 1.0f && !d->preact;   // (MN-major B: the N = K = 256 data gradients with a bf16 output)
   if (d->act == EEC_ACT_SILU) return d->b_kmajor && d->alpha == 1.0f && (!d->preact || d->preact_dtype == EEC_BF16);
+  if (d->act == EEC_ACT_GLU) {   // value * sigmoid(gate) of pointwise conv 1: CTA-pair kernel only (the leader holds the value rows, its peer the gate rows)
+    const char* e = getenv("EEC_GEMM_WS");
+    if (e && e[0] == '1') return false;
+    int sms = 0, dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms % 2) return false;
+    return d->b_kmajor && d->alpha == 1.0f && (!d->preact || (d->preact_dtype == EEC_BF16 && d->ldp % 16 == 0)) && !(d->drop_state && d->drop_p > 0.f);
+  }
   if (d->act == EEC_ACT_DSILU) return !d->b_kmajor && !d->bias && d->preact && d->preact_dtype == EEC_BF16 && d->ldp % 16 == 0;
   return false;
 }

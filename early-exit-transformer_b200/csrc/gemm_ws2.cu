@@ -205,8 +205,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTW, 1)
   if (warp == 1) tmem_alloc2(tmem_ptr_smem, 512);
   pdl_wait();
   if (threadIdx.x < 256) {
-    float b = p.bias ? p.bias[n0 + threadIdx.x] : 0.f;
-    if (MODE == WS_SILU || MODE == WS_SILU_PRE) b *= 0.5f;
+    float b;
+    if (MODE == WS_GLU || MODE == WS_GLU_PRE) {
+      const int i = threadIdx.x;
+      b = p.bias ? 0.5f * p.bias[i < 128 ? nt * 128 + i : p.N / 2 + nt * 128 + (i - 128)] : 0.f;   // halved: value/2 and gate/2 are what the epilogue needs
+    } else {
+      b = p.bias ? p.bias[n0 + threadIdx.x] : 0.f;
+      if (MODE == WS_SILU || MODE == WS_SILU_PRE) b *= 0.5f;
+    }
     bias_s[threadIdx.x] = b;
   }
   tc_fence_before();
@@ -223,7 +229,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTW, 1)
       int s = 0;
       uint32_t ph = 1;
       bool first = true;
-      const int nb = n0 + (int)rank * (BN / 2);   // this CTA's half of the weight tile: n-rows [nb, nb + 128)
+      // this CTA's half of the weight tile: n-rows [nb, nb + 128).  GLU: the leader holds the 128 value rows of output channels
+      // [nt*128, +128), its peer the 128 gate rows (N/2 further down): accumulator columns [0,128) = value, [128,256) = gate in both CTAs
+      const int nb = (MODE == WS_GLU || MODE == WS_GLU_PRE) ? (rank == 0 ? nt * 128 : p.N / 2 + nt * 128) : n0 + (int)rank * (BN / 2);
       for (int st = r0; st < st_eff; st += cnt) {
         const int m0 = st * 2 * BM + (int)rank * BM;
 #pragma unroll
@@ -350,6 +358,51 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTW, 1)
 #pragma unroll
         for (int ss = 0; ss < 4; ++ss) dwv[ss] = db[(long)((ncol >> 4) + ss) * p.M + m];
       }
+      if (MODE == WS_GLU || MODE == WS_GLU_PRE) {
+        // out[:, nt*128 + cg*32 .. +32) = (a + ba) * sigmoid(g + bg): value columns cg*32.., gate columns 128 + cg*32.. of the accumulator;
+        // with ah = (a + ba)/2, gh = (g + bg)/2:  out = ah + ah * tanh(gh); the stored pre-activation z = [2 ah | 2 gh] (exact doubling)
+        const uint32_t acc_ = ut & 1;
+        const uint32_t tc0 = tmem_base + ((uint32_t)(q * 32) << 16) + acc_ * BN + cg * 32;
+        mbar_wait_h(&tfull_bar[acc_], (ut >> 1) & 1);
+        tc_fence_after();
+        uint32_t va[16], vg[16], wa[16], wg[16];
+        tmem_ld16_async(tc0, va);
+        tmem_ld16_async(tc0 + 128, vg);
+        tmem_ld16_async(tc0 + 16, wa);
+        tmem_ld16_async(tc0 + 128 + 16, wg);
+        tmem_ld_wait16(wg);   // (one wait retires all four loads)
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_leader(&tempty_bar[acc_]);
+        const int ocol = nt * 128 + cg * 32;
+        __nv_bfloat16* zrow = (MODE == WS_GLU_PRE) ? p.pre + (long)m * p.ldp : nullptr;
+#pragma unroll
+        for (int ss = 0; ss < 2; ++ss) {
+          const uint32_t(&ca)[16] = ss ? wa : va;
+          const uint32_t(&cgt)[16] = ss ? wg : vg;
+          const float4* ba = reinterpret_cast<const float4*>(bias_s + cg * 32 + ss * 16);
+          const float4* bg = reinterpret_cast<const float4*>(bias_s + 128 + cg * 32 + ss * 16);
+          uint32_t za[8], zg[8];
+          uint32_t(&o)[8] = ss ? pa1 : pa0;
+#pragma unroll
+          for (int g4 = 0; g4 < 4; ++g4) {
+            const float4 fa = ba[g4], fg = bg[g4];
+#pragma unroll
+            for (int h2 = 0; h2 < 2; ++h2) {
+              const int j = g4 * 4 + h2 * 2;
+              const float2 ah = __ffma2_rn(make_float2(__uint_as_float(ca[j]), __uint_as_float(ca[j + 1])), make_float2(0.5f, 0.5f),
+                                           h2 ? make_float2(fa.z, fa.w) : make_float2(fa.x, fa.y));
+              const float2 gh = __ffma2_rn(make_float2(__uint_as_float(cgt[j]), __uint_as_float(cgt[j + 1])), make_float2(0.5f, 0.5f),
+                                           h2 ? make_float2(fg.z, fg.w) : make_float2(fg.x, fg.y));
+              if (MODE == WS_GLU_PRE) { za[j >> 1] = pack_bf16(__fadd2_rn(ah, ah)); zg[j >> 1] = pack_bf16(__fadd2_rn(gh, gh)); }
+              o[j >> 1] = pack_bf16(__ffma2_rn(ah, make_float2(tanh_fast(gh.x), tanh_fast(gh.y)), ah));
+            }
+          }
+          if (MODE == WS_GLU_PRE && valid) { stg256(zrow + ocol + ss * 16, za); stg256(zrow + p.N / 2 + ocol + ss * 16, zg); }
+        }
+        store_box(pa0, pa1, ocol, row0);
+        continue;
+      }
       const uint32_t acc = ut & 1;
       const uint32_t tcol = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + cg * 64;
       WS_TL(e == 0 && lane == 0, t_ = clock64());
@@ -435,13 +488,15 @@ int gemm_ws2(const eec_gemm_desc* d, cudaStream_t st) {
   if (int r = get_tmap_2d(&ta, d->A, d->K, d->M, (uint64_t)d->lda * 2, 64, 128)) return r;
   if (d->b_kmajor) { if (int r = get_tmap_2d(&tb, d->B, d->K, d->N, (uint64_t)d->ldb * 2, 64, 128)) return r; }   // one CTA's half of a weight tile
   else { if (int r = get_tmap_2d(&tb, d->B, d->N, d->K, (uint64_t)d->ldb * 2, 64, 64)) return r; }
-  if (int r = get_tmap_box32(&tcm, d->C, true, (uint64_t)d->N, (uint64_t)d->M, (uint64_t)d->ldc)) return r;
+  const bool glu = d->act == EEC_ACT_GLU;   // output [M, N/2]
+  if (int r = get_tmap_box32(&tcm, d->C, true, (uint64_t)(glu ? d->N / 2 : d->N), (uint64_t)d->M, (uint64_t)d->ldc)) return r;
   PW p{};
   p.M = d->M; p.N = d->N; p.m_tiles = cdiv(d->M, BM); p.n_tiles = d->N / BN;
   p.bias = d->bias; p.alpha = d->alpha;
   p.pre = reinterpret_cast<__nv_bfloat16*>(d->preact); p.ldp = d->ldp;
   p.act_items = (d->act != EEC_ACT_DSILU) ? active_items(st) : ActiveItems{nullptr, 0, 0};   // forward forms: rows of A are frames
   const bool store_pre = d->act == EEC_ACT_SILU && d->preact;
+  if (glu && d->preact) EEC_CHECK_ARG(d->ldp % 16 == 0 && (reinterpret_cast<uintptr_t>(d->preact) & 31) == 0, "gemm_ws2: GLU pre-activation needs 32-byte aligned rows");
   if (store_pre) EEC_CHECK_ARG(d->ldp % 16 == 0 && (reinterpret_cast<uintptr_t>(d->preact) & 31) == 0, "gemm_ws: pre-activation needs 32-byte aligned rows");
   if (d->act == EEC_ACT_DSILU) EEC_CHECK_ARG((reinterpret_cast<uintptr_t>(d->preact) & 31) == 0, "gemm_ws: pre-activation needs 32-byte aligned rows");
   static int knobs = -1;
@@ -480,6 +535,7 @@ int gemm_ws2(const eec_gemm_desc* d, cudaStream_t st) {
     set_error("gemm_ws2: dropout is fused into the SiLU + pre-activation and dSiLU forms only");
     return 1;
   }
+  if (d->act == EEC_ACT_GLU) return d->preact ? launch_ws2<WS_GLU_PRE, true>(ta, tb, tcm, p, grid, st) : launch_ws2<WS_GLU, true>(ta, tb, tcm, p, grid, st);
   if (d->act == EEC_ACT_NONE) return d->b_kmajor ? launch_ws2<WS_BIAS, true>(ta, tb, tcm, p, grid, st) : launch_ws2<WS_BIAS, false>(ta, tb, tcm, p, grid, st);
   if (d->act == EEC_ACT_SILU) return store_pre ? launch_ws2<WS_SILU_PRE, true>(ta, tb, tcm, p, grid, st) : launch_ws2<WS_SILU, true>(ta, tb, tcm, p, grid, st);
   return launch_ws2<WS_DSILU, false>(ta, tb, tcm, p, grid, st);

@@ -55,6 +55,21 @@ def _empty(shape, dtype, dev):
     return torch.empty(shape, dtype=dtype, device=dev)
 
 
+class _ZeroPool:
+    """Per-layer BatchNorm statistic accumulators (2 x 256 doubles each) carved out of ONE zero-filled buffer per forward / backward:
+    one fill launch instead of one per layer (24 launches of a 12-layer step)."""
+
+    def __init__(self, n: int, dev):
+        self.buf = torch.zeros(max(n, 1), 2 * D, dtype=torch.float64, device=dev)
+        self.i = 0
+
+    def take(self) -> Tensor:
+        if self.i >= self.buf.shape[0]:
+            return torch.zeros(2 * D, dtype=torch.float64, device=self.buf.device)
+        self.i += 1
+        return self.buf[self.i - 1]
+
+
 class Operands:
     """GEMM-operand views of the parameters in the activation dtype.  fp32: zero-copy reshapes;
     bf16: cast by eec_cast into buffers that are refreshed when a parameter's version changes."""
@@ -317,7 +332,8 @@ def layer_forward(P: Dict[str, Tensor], W: Operands, pre: str, x: Tensor, key_le
     cbuf = sm = sr = None
     if training:
         cbuf = _empty((N, D), f32, dev)
-        sums = torch.zeros(2 * D, dtype=torch.float64, device=dev)
+        zp = getattr(cfg, "_zero_pool", None)
+        sums = zp.take() if zp is not None else torch.zeros(2 * D, dtype=torch.float64, device=dev)
         ops.dwconv_stats(g, wdw, P[c + "sequential.2.bias"], cbuf, sums, B, T, KW)
         if cfg.bn_sync is not None:
             cfg.bn_sync(sums)          # per-channel sum / sum of squares over the GLOBAL batch (TA:59 BatchNorm1d under sync-BN)
@@ -399,7 +415,8 @@ def layer_backward(P, W: Operands, G: Dict[str, Tensor], pre: str, t: dict, dY: 
     ds = _empty((N, D), TD, dev)
     dgrad(dXh, Wp2, ds, N, D, D)
     dc = _empty((N, D), f32, dev)
-    sums2 = torch.zeros(2 * D, dtype=torch.float64, device=dev)
+    zp = getattr(cfg, "_zero_pool", None)
+    sums2 = zp.take() if zp is not None else torch.zeros(2 * D, dtype=torch.float64, device=dev)
     ops.bn_silu_bwd(ds, t["c"], t["sm"], t["sr"], P[c + "sequential.3.weight"], P[c + "sequential.3.bias"], sums2, dc,
                     G[c + "sequential.3.weight"], G[c + "sequential.3.bias"], sync=cfg.bn_sync, world=cfg.bn_world)
     dg = _empty((N, D), TD, dev)
@@ -521,6 +538,8 @@ def model_forward(P: Dict[str, Tensor], W: Operands, cfg: Config, src: Tensor, l
         src = src.float()
     dev, f32 = src.device, torch.float32
     tape = Tape() if want_tape else None
+    if training:
+        cfg._zero_pool = _ZeroPool(cfg.n_exits * cfg.n_layers + 2, dev)
     drop0 = None
     if training and cfg.drop_p > 0.0:
         if drop_state is None:
@@ -662,6 +681,7 @@ def model_backward(P, W: Operands, cfg: Config, tape: Tape, gout: Tensor, names:
     E = cfg.n_exits
     # all parameter gradients live in ONE flat fp32 buffer (one memset; one NCCL all-reduce under DP)
     total = sum(P[n].numel() for n in names)
+    cfg._zero_pool = _ZeroPool(cfg.n_exits * cfg.n_layers + 2, dev)
     flat = torch.zeros(total, dtype=f32, device=dev)
     G, off = {}, 0
     for n in names:
