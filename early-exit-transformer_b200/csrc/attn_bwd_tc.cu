@@ -31,6 +31,14 @@ constexpr uint32_t C_S = 0, C_DP = 64, C_DV = 128, C_DK = 160, C_DQ = 192;
 constexpr uint32_t TMEM_COLS = 256;
 constexpr uint32_t SW64 = 4, SW128 = 2;
 
+// -DEEC_ATTN_BWD_TIMELINE (make attn_bwd_timeline): CTA (0,0,0) stamps clock64 at the hand-overs of its first query blocks and prints them
+#ifdef EEC_ATTN_BWD_TIMELINE
+__device__ long long g_btl[96];
+#define BTL(slot) do { if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) g_btl[slot] = clock64(); } while (0)
+#else
+#define BTL(slot) do { } while (0)
+#endif
+
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
@@ -97,6 +105,7 @@ __global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_tc_kernel(const __grid
                                                                  const DropArgs drop) {
   pdl_trigger();
   pdl_wait();
+  if (threadIdx.x == 0) BTL(0);
   extern __shared__ __align__(1024) uint8_t smem[];
   if (threadIdx.x == 0 && (smem_u32(smem) & 1023u)) { printf("eec: attn_bwd smem base not 1024-aligned\n"); __trap(); }
   uint8_t* sK = smem;
@@ -111,10 +120,11 @@ __global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_tc_kernel(const __grid
   uint64_t* qdo_empty = bars + 3;    // [2]
   uint64_t* sdp_full = bars + 5;
   uint64_t* sdp_free = bars + 6;     // N_MATH arrivals
-  uint64_t* pds_full = bars + 7;     // N_MATH arrivals
+  uint64_t* pds_full = bars + 7;     // P / dS of key half 0 written (one phase per query block)
+  uint64_t* pds_full1 = bars + 10;   // ... of key half 1 (two barriers: a parity wait on ONE barrier with two phases per block can alias)
   uint64_t* dq_full = bars + 8;
   uint64_t* acc_full = bars + 9;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 10);
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 11);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.z, h = blockIdx.y, k0 = blockIdx.x * BT;
@@ -133,8 +143,9 @@ __global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_tc_kernel(const __grid
     mbar_init(kv_full, 1);
     for (int s = 0; s < ST; ++s) { mbar_init(&qdo_full[s], 1); mbar_init(&qdo_empty[s], 1); }
     mbar_init(sdp_full, 1);
-    mbar_init(sdp_free, N_MATH);
-    mbar_init(pds_full, N_MATH);
+    mbar_init(sdp_free, N_MATH / 32);   // one arrival per softmax warp (after __syncwarp): 256 per-thread arrivals on one mbarrier serialise
+    mbar_init(pds_full, N_MATH / 32);
+    mbar_init(pds_full1, N_MATH / 32);
     mbar_init(dq_full, 1);
     mbar_init(acc_full, 1);
     fence_barrier_init();
@@ -144,6 +155,7 @@ __global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_tc_kernel(const __grid
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  if (threadIdx.x == 0) BTL(1);
 
   if (warp == 0) {
     if (lane == 0 && active) {
@@ -164,40 +176,67 @@ __global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_tc_kernel(const __grid
       constexpr uint32_t id_t = make_idesc_bf16(BT, DHD, true, true);     // dV, dK : A^T (MN-major), B MN-major
       constexpr uint32_t id_q = make_idesc_bf16(BT, DHD, false, true);    // dQ     : A K-major,      B MN-major
       mbar_wait(kv_full, 0);
+      BTL(2);
       const uint32_t ak = smem_u32(sK), av = smem_u32(sV), ap = smem_u32(sP), ads = smem_u32(sdS);
-      for (int i = 0; i < nq - i_begin; ++i) {
+      const int cnt = nq - i_begin;
+      // UMMA descriptors built ONCE (the single issuing thread spent ~70 clk per MMA re-deriving them: 1.7 k clk for the 24 MMAs of a block);
+      // per MMA only a 16-byte-unit offset is added to the address field
+      const uint64_t d_k64 = make_smem_desc(ak, 0, 512, SW64), d_v64 = make_smem_desc(av, 0, 512, SW64);
+      const uint64_t d_pT = make_smem_desc(ap, 16384, 1024, SW128), d_dsT = make_smem_desc(ads, 16384, 1024, SW128);   // MN-major reads (dV, dK)
+      const uint64_t d_dsK = make_smem_desc(ads, 0, 1024, SW128);                                                       // K-major read (dQ)
+      uint64_t d_q64[ST], d_do64[ST];
+#pragma unroll
+      for (int s = 0; s < ST; ++s) {
+        d_q64[s] = make_smem_desc(smem_u32(sQ + s * TILE_QD), 0, 512, SW64);
+        d_do64[s] = make_smem_desc(smem_u32(sdO + s * TILE_QD), 0, 512, SW64);
+      }
+      // S / dP of one 64-key half of query block i: TMEM [0,64) / [64,128), single-buffered (the softmax warps hand them back through sdp_free)
+      auto issue_sdp = [&](int i, int hk) {
+        const uint64_t dq = (i % ST) ? d_q64[1] : d_q64[0], ddo = (i % ST) ? d_do64[1] : d_do64[0];
+        const int n = 2 * i + hk;                    // half-step counter: phases of sdp_full / sdp_free / pds_full
+        if (n > 0) mbar_wait(sdp_free, (n - 1) & 1);  // the softmax warps have read the previous S / dP out of TMEM
+        tc_fence_after();
+        const uint64_t koff = (uint64_t)((hk * 64 * 64) >> 4);          // 64 key rows of 64 B
+#pragma unroll
+        for (int k = 0; k < DHD / 16; ++k) umma_bf16(tmem_base + C_S, dq + k * 2, d_k64 + koff + k * 2, id_s, k);
+#pragma unroll
+        for (int k = 0; k < DHD / 16; ++k) umma_bf16(tmem_base + C_DP, ddo + k * 2, d_v64 + koff + k * 2, id_s, k);
+        umma_commit(sdp_full);
+      };
+      if (cnt > 0) {
+        mbar_wait(&qdo_full[0], 0);
+        BTL(8);
+        issue_sdp(0, 0);
+        BTL(9);
+      }
+      for (int i = 0; i < cnt; ++i) {
         const int s = i % ST;
-        mbar_wait(&qdo_full[s], (i / ST) & 1);
-        const uint32_t aq = smem_u32(sQ + s * TILE_QD), ado = smem_u32(sdO + s * TILE_QD);
-        for (int hk = 0; hk < 2; ++hk) {
-          const int n = 2 * i + hk;                    // half-step counter: phases of sdp_full / sdp_free / pds_full
-          if (n > 0) mbar_wait(sdp_free, (n - 1) & 1);  // the softmax warps have read the previous S / dP out of TMEM
-          tc_fence_after();
-          const uint32_t koff = hk * 64 * 64;          // 64 key rows of 64 B
-#pragma unroll
-          for (int k = 0; k < DHD / 16; ++k)
-            umma_bf16(tmem_base + C_S, make_smem_desc(aq + k * 32, 0, 512, SW64), make_smem_desc(ak + koff + k * 32, 0, 512, SW64), id_s, k);
-#pragma unroll
-          for (int k = 0; k < DHD / 16; ++k)
-            umma_bf16(tmem_base + C_DP, make_smem_desc(ado + k * 32, 0, 512, SW64), make_smem_desc(av + koff + k * 32, 0, 512, SW64), id_s, k);
-          umma_commit(sdp_full);
-          if (hk == 1) mbar_wait(pds_full, (n - 1) & 1);   // phases complete in order: wait for both halves' P / dS
+        const uint64_t dq = s ? d_q64[1] : d_q64[0], ddo = s ? d_do64[1] : d_do64[0];
+        issue_sdp(i, 1);
+        BTL(8 + i * 8 + 2);
+        // the first half of the NEXT query block before this block's dV / dK / dQ: its softmax math then overlaps those 24 MMAs
+        // (measured before: S ready 2.8 k clk after the hand-over, the whole chain of a block strictly serial: 8 k clk per block)
+        if (i + 1 < cnt) {
+          mbar_wait(&qdo_full[(i + 1) % ST], ((i + 1) / ST) & 1);
+          BTL(8 + (i + 1) * 8 + 0);
+          issue_sdp(i + 1, 0);
+          BTL(8 + (i + 1) * 8 + 1);
         }
-        mbar_wait(pds_full, (2 * i + 1) & 1);
+        mbar_wait(pds_full, i & 1);    // both halves' P / dS of block i are in shared memory
+        mbar_wait(pds_full1, i & 1);
+        BTL(8 + i * 8 + 3);
         tc_fence_after();
 #pragma unroll
         for (int k = 0; k < BT / 16; ++k) {  // contraction over the 128 queries of block i
-          umma_bf16(tmem_base + C_DV, make_smem_desc(ap + k * 2048, 16384, 1024, SW128), make_smem_desc(ado + k * 1024, 0, 512, SW64),
-                    id_t, (i > 0 || k > 0) ? 1u : 0u);
-          umma_bf16(tmem_base + C_DK, make_smem_desc(ads + k * 2048, 16384, 1024, SW128), make_smem_desc(aq + k * 1024, 0, 512, SW64),
-                    id_t, (i > 0 || k > 0) ? 1u : 0u);
+          umma_bf16(tmem_base + C_DV, d_pT + k * 128, ddo + k * 64, id_t, (i > 0 || k > 0) ? 1u : 0u);
+          umma_bf16(tmem_base + C_DK, d_dsT + k * 128, dq + k * 64, id_t, (i > 0 || k > 0) ? 1u : 0u);
         }
 #pragma unroll
         for (int k = 0; k < BT / 16; ++k)    // contraction over the 128 keys of block j
-          umma_bf16(tmem_base + C_DQ, make_smem_desc(ads + (k >> 2) * 16384 + (k & 3) * 32, 0, 1024, SW128),
-                    make_smem_desc(ak + k * 1024, 0, 512, SW64), id_q, k > 0 ? 1u : 0u);
+          umma_bf16(tmem_base + C_DQ, d_dsK + (uint64_t)((k >> 2) * 1024 + (k & 3) * 2), d_k64 + k * 64, id_q, k > 0 ? 1u : 0u);
         umma_commit(dq_full);
         umma_commit(&qdo_empty[s]);
+        BTL(8 + i * 8 + 4);
       }
       umma_commit(acc_full);
     }
@@ -222,6 +261,21 @@ __global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_tc_kernel(const __grid
       const int t_first = i_begin * BT + r;
       float l2_next = t_first < Tq ? lse_bh[t_first] : 0.f;
       float di_next = t_first < Tq ? dv_bh[t_first] : 0.f;
+      // dQ partial of (query block ii, this key block): 128 rows x 32 fp32 in TMEM; warp (q, half) adds columns [16 half, +16) of its 32 rows
+      auto drain_dq = [&](int ii) {
+        const int tp = (i_begin + ii) * BT + r;
+        uint32_t dqv[16];
+        tc_fence_after();
+        tmem_ld16_async(trow + C_DQ + half * 16, dqv);
+        tmem_ld_wait16(dqv);
+        if (tp < Tq) {
+          float* dst = dq32 + ((long)(rowq + tp)) * D + h * DHD + half * 16;
+#pragma unroll
+          for (int gg = 0; gg < 4; ++gg)
+            red_add_v4(dst + gg * 4, __uint_as_float(dqv[gg * 4]), __uint_as_float(dqv[gg * 4 + 1]), __uint_as_float(dqv[gg * 4 + 2]), __uint_as_float(dqv[gg * 4 + 3]));
+        }
+        tc_fence_before();
+      };
       for (int i = 0; i < nq - i_begin; ++i) {
         const int t = (i_begin + i) * BT + r;
         const bool rvalid = t < Tq;
@@ -236,10 +290,13 @@ __global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_tc_kernel(const __grid
           uint32_t dword = 0u;                    // keep-mask word of (row t, these 32 keys): in flight while S / dP are being computed
           if (DROP && rvalid && k0 + c0 < klen) dword = dbits[(long)((k0 + c0) >> 5) * dR + drow];
           mbar_wait(sdp_full, n & 1);
+          if (threadIdx.x == 64) BTL(40 + i * 16 + hk * 6 + 0);
           tc_fence_after();
           tmem_ld32x2(trow + C_S + half * 32, trow + C_DP + half * 32, s, dp);
           tc_fence_before();
-          mbar_arrive(sdp_free);                  // S / dP are in registers: the MMA warp may start the next half
+          __syncwarp();
+          if (lane == 0) mbar_arrive(sdp_free);   // S / dP are in registers: the MMA warp may start the next half
+          if (threadIdx.x == 64) BTL(40 + i * 16 + hk * 6 + 1);
           if (GENERAL) {
             // visibility word of (row t, these 32 keys): length, causal and per-key validity masks
             const int base = k0 + c0;
@@ -290,11 +347,14 @@ __global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_tc_kernel(const __grid
               dp[e] = ok ? p * (dp[e] - di) : 0.f;
             }
           }
-          if (hk == 0 && i > 0 && half == 1) {
-            // (P / dS of the previous query block are still being read by its dV / dK / dQ MMAs until dq_full flips;
-            //  the half-0 warps wait for dq_full anyway when they drain dQ)
+          if (hk == 0 && i > 0) {
+            // P / dS of the previous query block are read by its dV / dK / dQ MMAs until dq_full flips: only now may this block's tiles
+            // overwrite them -- and only now is the previous block's dQ partial complete.  Draining it HERE (after this half's math, all
+            // eight warps, 16 columns each) keeps the exponentials of block i under the MMAs of block i - 1.
             mbar_wait(dq_full, (i - 1) & 1);
+            drain_dq(i - 1);
           }
+          if (threadIdx.x == 64) BTL(40 + i * 16 + hk * 6 + 2);
           uint8_t* prow = sP + hk * 16384 + r * 128;
           uint8_t* drow = sdS + hk * 16384 + r * 128;
 #pragma unroll
@@ -311,22 +371,19 @@ __global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_tc_kernel(const __grid
             *reinterpret_cast<uint4*>(prow + off) = u;
             *reinterpret_cast<uint4*>(drow + off) = w;
           }
+          if (threadIdx.x == 64) BTL(40 + i * 16 + hk * 6 + 3);
           fence_proxy_async();
-          mbar_arrive(pds_full);
-        }
-        if (half == 0) {   // dQ partial of this (query block, key block): 128 rows x 32, one lane quarter per warp
-          mbar_wait(dq_full, i & 1);
-          tc_fence_after();
-          tmem_ld32(trow + C_DQ, s);
-          if (rvalid) {
-            float* dst = dq32 + ((long)(rowq + t)) * D + h * DHD;
-#pragma unroll
-            for (int gg = 0; gg < 8; ++gg) red_add_v4(dst + gg * 4, s[gg * 4], s[gg * 4 + 1], s[gg * 4 + 2], s[gg * 4 + 3]);
-          }
-          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(hk ? pds_full1 : pds_full);
+          if (threadIdx.x == 64) BTL(40 + i * 16 + hk * 6 + 4);
         }
       }
+      if (nq - i_begin > 0) {   // the last block's dQ partial
+        mbar_wait(dq_full, (nq - i_begin - 1) & 1);
+        drain_dq(nq - i_begin - 1);
+      }
       mbar_wait(acc_full, 0);
+      if (threadIdx.x == 64) BTL(3);
       tc_fence_after();
     }
     // dK / dV rows of this key block (zeros for fully masked blocks): the half-0 warps write dV, the half-1 warps dK
@@ -350,11 +407,24 @@ __global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_tc_kernel(const __grid
     }
     tc_fence_before();
   }
+  if (threadIdx.x == 64) BTL(4);
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
   }
+#ifdef EEC_ATTN_BWD_TIMELINE
+  if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 32) {
+    const long long t0 = g_btl[0];
+    printf("attn_bwd CTA(0,0,0) clk since start: setup %lld, K/V landed %lld, acc_full seen %lld, outputs written %lld, end %lld\n", g_btl[1] - t0, g_btl[2] - t0,
+           g_btl[3] - t0, g_btl[4] - t0, clock64() - t0);
+    for (int i = 0; i < 3; ++i)
+      printf("  i=%d MMA: Q/dO landed %lld, S/dP(h0) issued %lld, S/dP(h1) issued %lld, P/dS complete %lld, dV/dK/dQ issued %lld | softmax h0: S ready %lld, in regs %lld, math done %lld, stored %lld, arrived %lld; h1: %lld %lld %lld %lld %lld; dQ ready %lld, reduced %lld\n",
+             i, g_btl[8 + i * 8] - t0, g_btl[9 + i * 8] - t0, g_btl[10 + i * 8] - t0, g_btl[11 + i * 8] - t0, g_btl[12 + i * 8] - t0, g_btl[40 + i * 16] - t0,
+             g_btl[41 + i * 16] - t0, g_btl[42 + i * 16] - t0, g_btl[43 + i * 16] - t0, g_btl[44 + i * 16] - t0, g_btl[46 + i * 16] - t0, g_btl[47 + i * 16] - t0,
+             g_btl[48 + i * 16] - t0, g_btl[49 + i * 16] - t0, g_btl[50 + i * 16] - t0, g_btl[52 + i * 16] - t0, g_btl[53 + i * 16] - t0);
+  }
+#endif
 }
 
 static int bwd_launch(const CUtensorMap& tq, const CUtensorMap& tkv, const CUtensorMap& td, const BwGeom& g, int B, const void* ctx,

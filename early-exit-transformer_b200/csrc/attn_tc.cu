@@ -406,8 +406,8 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_fwd_v2_kernel(const __grid
     mbar_init(q_full, 1);
     for (int s = 0; s < KV_STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
     mbar_init(s_full, 1);
-    mbar_init(s_free, 128);
-    mbar_init(p_full, 128);
+    mbar_init(s_free, 4);     // one arrival per softmax warp (after __syncwarp): 128 per-thread arrivals on one mbarrier serialise
+    mbar_init(p_full, 4);
     mbar_init(o_full, 1);
     mbar_init(q_empty, 1);
     fence_barrier_init();
@@ -456,6 +456,22 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_fwd_v2_kernel(const __grid
       constexpr uint32_t idesc_o = make_idesc_bf16(QT, DHEAD, false, true);
       constexpr uint32_t idesc_l = make_idesc_bf16(QT, 16, false, true);
       const uint32_t aq = smem_u32(sQ), ap = smem_u32(sP), a1 = smem_u32(sOnes);
+      // UMMA descriptors built once (the issuing thread spent ~80 clk per MMA re-deriving them: 1.3 k clk for the 16 MMAs of a block, on
+      // the path between "P written" and "P V done"); per MMA only an offset in 16-byte units is added
+      const uint64_t d_q = make_smem_desc(aq, 0, 512, SW64), d_p = make_smem_desc(ap, 0, 1024, SW128), d_1 = make_smem_desc(a1, 0, 512, SW64);
+      uint64_t d_k[KV_STAGES], d_v[KV_STAGES];
+#pragma unroll
+      for (int s = 0; s < KV_STAGES; ++s) {
+        d_k[s] = make_smem_desc(smem_u32(sK + s * K_BYTES), 0, 512, SW64);
+        d_v[s] = make_smem_desc(smem_u32(sV + s * V_BYTES), 0, 512, SW64);
+      }
+      auto pick = [](const uint64_t(&d)[KV_STAGES], int s) {   // (explicit selects keep the descriptor arrays in registers)
+        uint64_t r = d[0];
+#pragma unroll
+        for (int i = 1; i < KV_STAGES; ++i)
+          if (s == i) r = d[i];
+        return r;
+      };
       uint32_t it = 0, jbase = 0;
       // S MMA of block jb (its K tile is stage jb % 2); the S tile is free once the softmax threads hold block jb - 1 in registers
       auto issue_s = [&](uint32_t jb, bool last_of_item) {
@@ -463,11 +479,9 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_fwd_v2_kernel(const __grid
         mbar_wait(&kv_full[s], (jb / KV_STAGES) & 1);
         if (jb > 0) mbar_wait(s_free, (jb - 1) & 1);
         tc_fence_after();
-        const uint32_t bk = smem_u32(sK + s * K_BYTES);
+        const uint64_t dk = pick(d_k, s);
 #pragma unroll
-        for (int k = 0; k < DHEAD / 16; ++k)
-          umma_bf16(tmem_base + S_COL, make_smem_desc(aq + k * 32, 0, 512, SW64), make_smem_desc(bk + k * 32, 0, 512, SW64), idesc_s,
-                    k > 0 ? 1u : 0u);
+        for (int k = 0; k < DHEAD / 16; ++k) umma_bf16(tmem_base + S_COL, d_q + k * 2, dk + k * 2, idesc_s, k > 0 ? 1u : 0u);
         umma_commit(s_full);
         if (last_of_item) umma_commit(q_empty);      // once it completes sQ may be refilled
       };
@@ -483,13 +497,13 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_fwd_v2_kernel(const __grid
           mbar_wait(p_full, jb & 1);
           ATL(0, jb);                                           // MMA thread: P of block jb seen
           tc_fence_after();
-          const uint32_t bv = smem_u32(sV + s * V_BYTES);
+          const uint64_t dv = pick(d_v, s);
           const uint32_t accf = j > 0 ? 1u : 0u;                // the first block of an item overwrites O and L
 #pragma unroll
           for (int k = 0; k < KB / 16; ++k) {
-            const uint64_t pd = make_smem_desc(ap + (k >> 2) * 16384 + (k & 3) * 32, 0, 1024, SW128);
-            umma_bf16(tmem_base + O_COL, pd, make_smem_desc(bv + k * 1024, 0, 512, SW64), idesc_o, (k > 0) ? 1u : accf);
-            umma_bf16(tmem_base + L_COL, pd, make_smem_desc(a1 + k * 1024, 0, 512, SW64), idesc_l, (k > 0) ? 1u : accf);
+            const uint64_t pd = d_p + (uint64_t)((k >> 2) * 1024 + (k & 3) * 2);
+            umma_bf16(tmem_base + O_COL, pd, dv + k * 64, idesc_o, (k > 0) ? 1u : accf);
+            umma_bf16(tmem_base + L_COL, pd, d_1 + k * 64, idesc_l, (k > 0) ? 1u : accf);
           }
           umma_commit(o_full);
           umma_commit(&kv_empty[s]);
@@ -551,7 +565,8 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_fwd_v2_kernel(const __grid
         tmem_ld32x2(trow + S_COL, trow + S_COL + 32, *reinterpret_cast<float(*)[32]>(&x[0]), *reinterpret_cast<float(*)[32]>(&x[32]));
         tmem_ld32x2(trow + S_COL + 64, trow + S_COL + 96, *reinterpret_cast<float(*)[32]>(&x[64]), *reinterpret_cast<float(*)[32]>(&x[96]));
         tc_fence_before();
-        mbar_arrive(s_free);                         // S lives in registers: the next block's Q K^T may overwrite the tile
+        __syncwarp();
+        if (lane == 0) mbar_arrive(s_free);          // S lives in registers: the next block's Q K^T may overwrite the tile
         if (threadIdx.x == 64) ATL(4, jb);           // softmax: S in registers
         if (!all_vis) {
 #pragma unroll
@@ -622,7 +637,8 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_fwd_v2_kernel(const __grid
         }
         if (DROP) l_run += psum;
         fence_proxy_async();
-        mbar_arrive(p_full);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_full);
         if (threadIdx.x == 64) ATL(7, jb);           // softmax: P written
       }
       // ---- epilogue of the item: O / L out of TMEM once
