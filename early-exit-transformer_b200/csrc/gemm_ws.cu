@@ -407,6 +407,9 @@ bool gemm_ws_ok(const eec_gemm_desc* d) {
   if (env < 0) { const char* e = getenv("EEC_GEMM_WS"); env = (e && e[0] == '0') ? 0 : 1; }
   if (!env) return false;
   if (d->K != 256 || !d->a_kmajor || d->N % 256 != 0 || d->out_dtype != EEC_BF16 || d->in_dtype != EEC_BF16) return false;
+  if (d->N / 256 > 64) return false;                                  // one weight tile per CTA (pair): more n-tiles than CTAs stay on the v3 kernel
+  if (d->preact && ((reinterpret_cast<uintptr_t>(d->preact) & 31) != 0 || d->ldp % 16 != 0)) return false;   // 256-bit row accesses
+  if ((reinterpret_cast<uintptr_t>(d->C) & 15) != 0 || d->ldc % 8 != 0) return false;
   if (d->accumulate || d->residual || d->a_colsum || d->ln_out) return false;
   if (d->drop_state && d->drop_p > 0.f) {   // dropout: the CTA-pair kernel has it for the two training forms (SiLU + stored pre-activation, dSiLU)
     const char* e = getenv("EEC_GEMM_WS");
