@@ -137,6 +137,7 @@ class _EncoderFn(torch.autograd.Function):
                                       "(eval-mode BatchNorm backward is not implemented)")
         names = m._param_names
         red = m.__dict__.get("_grad_reducer")     # eec.distributed.OverlappedGradReducer: per-exit-group all-reduce during backward
+        ctx.cfg._dp_kick = red.kick if (red is not None and getattr(red, "defer", False)) else None
         with on_device(gout.device):
             G = engine.model_backward(ctx.P, m._operands, ctx.cfg, ctx.tape, gout, names,
                                       ghid.contiguous() if ctx.want_hidden and ghid is not None else None,

@@ -408,6 +408,10 @@ def layer_backward(P, W: Operands, G: Dict[str, Tensor], pre: str, t: dict, dY: 
     dXh = ffn_bwd("ffn2", t["x3"], t["u4"], t["m4"], t["r4"], t["h2pre"], t["a2"], dXh, True, S_FFN2_ACT, c + "sequential.5.bias",
                   S_CONV_OUT)
 
+    kick = getattr(cfg, "_dp_kick", None)
+    if kick is not None:
+        kick()     # data parallel: gradient slices that are final leave for their all-reduce here (see OverlappedGradReducer.kick)
+
     # conv module: x3 = x2 + pw2(s) + b
     Wp1 = W.get(c + "sequential.0.weight", P[c + "sequential.0.weight"], (2 * D, D))
     Wp2 = W.get(c + "sequential.5.weight", P[c + "sequential.5.weight"], (D, D))
