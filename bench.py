@@ -495,7 +495,13 @@ def run_ours(args):
         graphed = None          # (graphs that hold captured NCCL kernels are released before the communicator)
         torch.cuda.synchronize()
         dist.barrier()
-        dist.destroy_process_group()
+        # Hard exit instead of dist.destroy_process_group(): with CUDA graphs that captured NCCL kernels still alive in several legs, the
+        # communicator teardown hung intermittently AFTER the JSON line was out (2 of 9 multi-GPU runs in round 2: the line was complete,
+        # the processes never left).  The result is printed and flushed, every rank has passed the barrier; the driver reclaims the rest.
+        _JSON_OUT.flush()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def kernel_trace(step, path, rank):
