@@ -370,7 +370,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTW, 1)
         tmem_ld16_async(tc0 + 128, vg);
         tmem_ld16_async(tc0 + 16, wa);
         tmem_ld16_async(tc0 + 128 + 16, wg);
-        tmem_ld_wait16(wg);   // (one wait retires all four loads)
+        tmem_ld_wait16(wg);   // (one wait retires all four loads; only wg is threaded through the wait statement -- checked in the SASS:
+                              //  the first consumers of va / vg / wa sit behind it; tie all four arrays to the wait when this block changes)
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_leader(&tempty_bar[acc_]);
