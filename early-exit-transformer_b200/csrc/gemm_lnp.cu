@@ -29,7 +29,6 @@ constexpr int LN_OFF_VEC = LN_OFF_STG + LN_WARPS * LN_WBUF;   // float[3][256]: 
 constexpr int LN_OFF_XCH = LN_OFF_VEC + 3 * 256 * 4;          // float[2 halves][128 rows][2]
 constexpr int LN_OFF_BAR = LN_OFF_XCH + 2 * 128 * 2 * 4;
 constexpr int LNP_SMEM_BYTES = LN_OFF_BAR + 512;
-constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;
 
 struct PLN {
   int M, K, m_tiles;
@@ -62,28 +61,6 @@ __device__ __forceinline__ void wait_h(uint64_t* bar, uint32_t parity) {
       __trap();
     }
   }
-}
-__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int x, int y) {
-  asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
-                   smem_u32(smem_dst)),
-               "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & PEER_MASK), "r"(x), "r"(y)
-               : "memory");
-}
-__device__ __forceinline__ void umma2_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma2_commit_both(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
-               "h"((uint16_t)3)
-               : "memory");
-}
-__device__ __forceinline__ void arrive_leader(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & PEER_MASK) : "memory");
 }
 
 template <bool DROP>

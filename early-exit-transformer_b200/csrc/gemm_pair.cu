@@ -33,7 +33,6 @@ constexpr int OFF_STG = NS * STAGE;                   // 196608
 constexpr int OFF_SCR = OFF_STG + NEW * 2048;         // 229376: float[512] scratch (a_colsum partial sums)
 constexpr int OFF_BAR = OFF_SCR + 2048;               // 231424
 constexpr int PAIR_SMEM = OFF_BAR + 256;              // 231680 <= 232448
-constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;           // shared::cluster address of the same offset in the pair's even (leader) CTA
 
 struct PP {
   int M, N, K;
@@ -63,28 +62,6 @@ __device__ __forceinline__ void wait_h(uint64_t* bar, uint32_t parity) {
       __trap();
     }
   }
-}
-__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int x, int y) {
-  asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
-                   smem_u32(smem_dst)),
-               "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & PEER_MASK), "r"(x), "r"(y)
-               : "memory");
-}
-__device__ __forceinline__ void umma2_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma2_commit_both(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
-               "h"((uint16_t)3)
-               : "memory");
-}
-__device__ __forceinline__ void arrive_leader(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & PEER_MASK) : "memory");
 }
 __device__ __forceinline__ void arrive_peer(uint64_t* bar) {   // the leader arrives on the odd CTA's copy of `bar`
   asm volatile(

@@ -129,32 +129,7 @@ __device__ __forceinline__ void epi16(const uint32_t (&c)[16], const float* b, u
   }
 }
 
-// ---- cta_group::2 forms of the async primitives (PTX ISA tcgen05 / cp.async.bulk.tensor; cross-checked against
-// cute/arch/copy_sm100_tma.hpp, cutlass/arch/barrier.h and cute/arch/mma_sm100_umma.hpp of the vendored CUTLASS headers)
-constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;   // shared::cluster address of the same offset in the pair's even (leader) CTA
-__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int x, int y) {
-  asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
-                   smem_u32(smem_dst)),
-               "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & PEER_MASK), "r"(x), "r"(y)
-               : "memory");
-}
-__device__ __forceinline__ void umma2_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// completion of all MMAs issued so far by this thread -> one arrival on the barrier at this offset in BOTH CTAs of the pair
-__device__ __forceinline__ void umma2_commit_both(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
-               "h"((uint16_t)3)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {   // arrive on the LEADER CTA's copy of `bar`
-  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & PEER_MASK) : "memory");
-}
+// (2SM TMA loads, cta_group::2 MMA / commit and the remote arrive live in tc_common.cuh)  TMEM of a pair: one warp of EACH CTA allocates
 __device__ __forceinline__ void tmem_alloc2(uint32_t* smem_result, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)), "r"(ncols) : "memory");
   asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
@@ -374,7 +349,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTW, 1)
                               //  the first consumers of va / vg / wa sit behind it; tie all four arrays to the wait when this block changes)
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive_leader(&tempty_bar[acc_]);
+        if (lane == 0) arrive_leader(&tempty_bar[acc_]);
         const int ocol = nt * 128 + cg * 32;
         __nv_bfloat16* zrow = (MODE == WS_GLU_PRE) ? p.pre + (long)m * p.ldp : nullptr;
 #pragma unroll
@@ -442,7 +417,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTW, 1)
       WS_TL(e == 0 && lane == 0, w2_ += clock64() - t_);
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_leader(&tempty_bar[acc]);   // the accumulator slice is in registers: the leader's MMA warp may reuse it
+      if (lane == 0) arrive_leader(&tempty_bar[acc]);   // the accumulator slice is in registers: the leader's MMA warp may reuse it
       epi16<MODE, DROP>(rb, bsl + 48, pb1, po1, pin[(MODE == WS_DSILU) ? 3 : 0], p.alpha, dwv[3], p.drop.scale);
       if (MODE == WS_SILU_PRE && valid) stg256(pout + 48, po1);
       if (!defer) store_box(pb0, pb1, ncol + 32, row0);

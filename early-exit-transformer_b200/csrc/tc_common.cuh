@@ -280,6 +280,37 @@ struct Stager {
   }
 };
 
+// ---------------------------------------------------------------- CTA pairs (tcgen05 cta_group::2): shared by gemm_ws2.cu, gemm_pair.cu, gemm_lnp.cu
+// (PTX ISA tcgen05 / cp.async.bulk.tensor; cross-checked against cute/arch/copy_sm100_tma.hpp, cutlass/arch/barrier.h and
+// cute/arch/mma_sm100_umma.hpp of the vendored CUTLASS headers)
+constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;   // shared::cluster address of the same offset in the pair's even (leader) CTA
+// both CTAs load their part of a stage; the bytes complete on the LEADER's barrier
+__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int x, int y) {
+  asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & PEER_MASK), "r"(x), "r"(y)
+               : "memory");
+}
+// D[tmem of both CTAs] (+)= A[both CTAs' smem, 128 rows each] * B[each CTA holds N/2 rows]; issued by the leader only
+__device__ __forceinline__ void umma2_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// completion of all MMAs issued so far by this thread -> one arrival on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma2_commit_both(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+// arrive on the LEADER CTA's copy of `bar` (default semantics: .release.cluster costs ~1.9 k clk per arrival, measured)
+__device__ __forceinline__ void arrive_leader(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & PEER_MASK) : "memory");
+}
+
 // ---------------------------------------------------------------- descriptors
 // shared-memory matrix descriptor, SWIZZLE_128B, version 1 (sm_100)
 //   K-major operand : rows of 64 bf16 (128 B), 8-row groups 1024 B apart  -> SBO = 1024, LBO unused
